@@ -1,0 +1,191 @@
+/*
+ * d2t_b200.h -- C ABI of libd2t_b200.so: the Detect-to-Track per-frame-pair hot path as
+ * hand-written sm_100a CUDA kernels.  Plain pointers and sizes only; no torch types.
+ *
+ * Part 1 re-exports, name for name and argument for argument, the `extern "C"` launchers
+ * the reference's own C glue links against; each prototype cites
+ * the reference declaration it replaces (paths relative to /root/reference/lib/model/).
+ * Part 2 is the stream-ordered / batched / workspace-explicit surface the Python host
+ * layer actually calls.
+ *
+ * Conventions for every entry point:
+ *   - all tensor pointers are DEVICE pointers to contiguous fp32 / int32 NCHW data;
+ *   - return 1 = success, 0 = failure (never exit(), never printf); after a 0 the message
+ *     is available from d2t_last_error();
+ *   - kernels are launched on the stream passed in; nothing synchronises the device except
+ *     nms_cuda_compute(), whose reference contract is synchronous;
+ *   - the caller owns every buffer.  Part 1 symbols that need scratch use a per-device
+ *     cache inside the library (grown with cudaMalloc on first use, guarded by a mutex:
+ *     one in-flight call per device per op); Part 2 symbols take the workspace explicitly.
+ */
+#ifndef D2T_B200_H
+#define D2T_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ library ---------- */
+const char* d2t_version(void);
+const char* d2t_last_error(void);          /* thread-local, "" when no error */
+int d2t_device_sm_count(void);             /* SMs of the current device (148 on B200) */
+
+/* ====================================================================================
+ * Part 1 -- reference launcher symbols
+ * ==================================================================================== */
+
+/* correlation/src/correlation_cuda_kernel.h:5-39.  rInput1/rInput2 (the reference's padded
+ * NHWC scratch) are accepted and ignored.  Strides are accepted; tensors must be contiguous
+ * NCHW (the reference kernels assume it too).  `output` need not be pre-zeroed. */
+int Correlation_forward_cuda_kernel(
+    float* output, int ob, int oc, int oh, int ow, int osb, int osc, int osh, int osw,
+    float* input1, int ic, int ih, int iw, int isb, int isc, int ish, int isw,
+    float* input2, int gc, int gsb, int gsc, int gsh, int gsw,
+    float* rInput1, float* rInput2,
+    int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+    int corr_type_multiply, cudaStream_t stream);
+
+/* correlation/src/correlation_cuda_kernel.h:41-88.  Writes the exact adjoint of the forward
+ * into gradInput1/gradInput2 (every element is written; pre-zeroing is not required).  See
+ * DESIGN.md "Correlation backward" for where the reference kernels deviate from it. */
+int Correlation_backward_cuda_kernel(
+    float* gradOutput, int gob, int goc, int goh, int gow, int gosb, int gosc, int gosh, int gosw,
+    float* input1, int ic, int ih, int iw, int isb, int isc, int ish, int isw,
+    float* input2, int gsb, int gsc, int gsh, int gsw,
+    float* gradInput1, int gisb, int gisc, int gish, int gisw,
+    float* gradInput2, int ggc, int ggsb, int ggsc, int ggsh, int ggsw,
+    float* rInput1, float* rInput2,
+    int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+    int corr_type_multiply, cudaStream_t stream);
+
+/* psroi_pooling/src/psroi_pooling_kernel.h:8-11.  mapping_channel may be NULL (skipped). */
+int PSROIPoolForwardLauncher(
+    const float* bottom_data, const float spatial_scale, const int num_rois, const int height,
+    const int width, const int channels, const int pooled_height, const int pooled_width,
+    const float* bottom_rois, const int group_size, const int output_dim, float* top_data,
+    int* mapping_channel, cudaStream_t stream);
+
+/* psroi_pooling/src/psroi_pooling_kernel.h:14 (pooled_width BEFORE pooled_height, as in the
+ * reference).  Adds into bottom_diff, which the caller zero-fills (functions/psroi_pool.py:40).
+ * mapping_channel may be NULL: the channel is a pure function of the output index
+ * (group_size is then taken to be pooled_width). */
+int PSROIPoolBackwardLauncher(
+    const float* top_diff, const int* mapping_channel, const int batch_size, const int num_rois,
+    const float spatial_scale, const int channels, const int height, const int width,
+    const int pooled_width, const int pooled_height, const int output_dim, float* bottom_diff,
+    const float* bottom_rois, cudaStream_t stream);
+
+/* roi_align/src/roi_align_kernel.h:18-22 and :29-33 (sic: "Laucher"). */
+int ROIAlignForwardLaucher(
+    const float* bottom_data, const float spatial_scale, const int num_rois, const int height,
+    const int width, const int channels, const int aligned_height, const int aligned_width,
+    const float* bottom_rois, float* top_data, cudaStream_t stream);
+int ROIAlignBackwardLaucher(
+    const float* top_diff, const float spatial_scale, const int batch_size, const int num_rois,
+    const int height, const int width, const int channels, const int aligned_height,
+    const int aligned_width, const float* bottom_rois, float* bottom_diff, cudaStream_t stream);
+
+/* roi_pooling/src/roi_pooling_kernel.h:8-18 (sic).  argmax_data may be NULL in forward. */
+int ROIPoolForwardLaucher(
+    const float* bottom_data, const float spatial_scale, const int num_rois, const int height,
+    const int width, const int channels, const int pooled_height, const int pooled_width,
+    const float* bottom_rois, float* top_data, int* argmax_data, cudaStream_t stream);
+int ROIPoolBackwardLaucher(
+    const float* top_diff, const float spatial_scale, const int batch_size, const int num_rois,
+    const int height, const int width, const int channels, const int pooled_height,
+    const int pooled_width, const float* bottom_rois, float* bottom_diff, const int* argmax_data,
+    cudaStream_t stream);
+
+/* roi_crop/src/roi_crop_cuda_kernel.h:6-17 and :19-32.  inputImages is NCHW despite the
+ * "BHWD" name; grids is [ob, oh, ow, 2] in (y, x) order.  Only contiguous tensors. */
+int BilinearSamplerBHWD_updateOutput_cuda_kernel(
+    int oc, int ow, int oh, int ob, int ic, int ih, int iw, int ib,
+    float* inputImages, int isb, int isc, int ish, int isw,
+    float* grids, int gsb, int gsc, int gsh, int gsw,
+    float* output, int osb, int osc, int osh, int osw, cudaStream_t stream);
+int BilinearSamplerBHWD_updateGradInput_cuda_kernel(
+    int goc, int gow, int goh, int gob, int ic, int ih, int iw, int ib,
+    float* inputImages, int isb, int isc, int ish, int isw,
+    float* grids, int gsb, int gsc, int gsh, int gsw,
+    float* gradInputImages, int gisb, int gisc, int gish, int gisw,
+    float* gradGrids, int ggsb, int ggsc, int ggsh, int ggsw,
+    float* gradOutput, int gosb, int gosc, int gosh, int gosw, cudaStream_t stream);
+
+/* nms/src/nms_cuda_kernel.h:5-6.  All three pointers are DEVICE pointers (as the reference's
+ * caller passes them).  Synchronous on return, like the reference.  keep_out[0..*num_out) =
+ * kept indices ascending; entries beyond are left untouched. */
+void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_num,
+                      int boxes_dim, float nms_overlap_thresh);
+
+/* ====================================================================================
+ * Part 2 -- stream-ordered surface used by the Python host layer
+ * ==================================================================================== */
+
+/* ---- NMS: B independent, caller-sorted box lists in one launch pair ----
+ * boxes   [B, N, box_dim] fp32 (x1,y1,x2,y2,...), n_valid [B] int32 or NULL (= N each)
+ * keep    [B, keep_stride] int32, num_keep [B] int32; at most max_keep (<= keep_stride)
+ *         indices are produced per list (max_keep <= 0: no cap, needs keep_stride >= N).
+ * workspace: d2t_nms_workspace_bytes(B, N) bytes, 16-byte aligned. */
+size_t d2t_nms_workspace_bytes(int B, int N);
+int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int box_dim,
+                    float thresh, int max_keep, int* keep, int keep_stride, int* num_keep,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- PSRoI with explicit workspace; mapping may be NULL; accumulate=0 overwrites the
+ * touched planes of bottom_diff (no pre-zeroing needed for channels < D*G*G). ---- */
+size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w);
+int d2t_psroi_forward(const float* bottom, int batch, int channels, int height, int width,
+                      const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,
+                      int group, int out_dim, float* top, int* mapping,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int d2t_psroi_backward(const float* top_diff, int batch, int channels, int height, int width,
+                       const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,
+                       int group, int out_dim, float* bottom_diff, int accumulate,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Integer bin windows [num_rois, PH, PW, 4] = (hstart, hend, wstart, wend), for the
+ * bit-exact RoI->bin parity test. */
+int d2t_psroi_bins(const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,
+                   int height, int width, int* bins, cudaStream_t stream);
+
+/* ---- Correlation without the legacy stride/scratch arguments ---- */
+int d2t_correlation_shape(int H, int W, int pad, int k, int md, int s1, int s2, int* out3);
+int d2t_correlation_forward(const float* in1, const float* in2, int B, int C, int H, int W,
+                            int pad, int k, int md, int s1, int s2, float* out,
+                            cudaStream_t stream);
+int d2t_correlation_backward(const float* in1, const float* in2, const float* grad_out,
+                             int B, int C, int H, int W, int pad, int k, int md, int s1,
+                             int s2, float* grad1, float* grad2, cudaStream_t stream);
+
+/* ---- RPN proposal step (rpn/proposal_layer.py:67-159) ----
+ * decode+clip: anchors [A,4], deltas [B,4A,H,W], scores = fg half of cls_prob [B,2A,H,W],
+ * im_info [B,3] -> boxes [B, H*W*A, 4] and scores_out [B, H*W*A] in (y, x, a) order. */
+int d2t_proposal_decode(const float* anchors, int A, const float* deltas, const float* cls_prob,
+                        const float* im_info, int B, int H, int W, int feat_stride,
+                        float* boxes, float* scores_out, cudaStream_t stream);
+/* gather the top `n_take` boxes of each image through `order` [B, order_stride] (int64)
+ * into dets [B, n_take, 5] = (x1,y1,x2,y2,score). */
+int d2t_proposal_gather(const float* boxes, const float* scores, const int64_t* order,
+                        int B, int n_total, int order_stride, int n_take, float* dets,
+                        cudaStream_t stream);
+/* rois [B, post, 5]: col 0 = image index, rows >= num_keep[b] zero (proposal_layer.py:127,158-159) */
+int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
+                            const int* num_keep, int B, int n_take, int post, float* rois,
+                            cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* D2T_B200_H */

@@ -1,0 +1,220 @@
+// nms.cu -- greedy IoU NMS entirely on the device, batched over images, for sm_100a.
+//
+// Replaces nms_kernel + the host-side part of nms_cuda_compute
+// (/root/reference/lib/model/nms/src/nms_cuda_kernel.cu:31-39 devIoU, :41-85 mask kernel,
+// :87-161 cudaMalloc / D2H of the whole mask / serial CPU sweep / H2D / cudaFree).
+//
+// Bit-exactness: devIoU is evaluated with the exact instruction sequence nvcc emits for the
+// reference source on sm_100a (checked with cuobjdump -sass on oracle/_ref):
+//     Sa = FMUL(a2-a0+1, a3-a1+1)      a = the EARLIER box (the reference's row / cur_box)
+//     t  = FFMA(b2-b0+1, b3-b1+1, Sa)  b = the LATER box   (the reference's column box)
+//     I  = FMUL(w, h);  den = FADD(t, -I);  iou = I / den (IEEE);  suppress iff iou > thresh
+// The roles matter: FFMA(wb,hb,wa*ha) and FFMA(wa,ha,wb*hb) can differ in the last ulp.
+//
+// Design (B200):
+//   kernel 1 (nms_mask): 64x64 IoU tiles of the UPPER triangle only (the reference computes the
+//     full square), all images in one launch; boxes of the column block staged in shared memory
+//     as SoA; pairs with empty intersection skip the division.  Diagonal tiles store the full
+//     symmetric 64-bit word per box in `diag`, off-diagonal tiles store mask[row][colblock].
+//   kernel 2 (nms_sweep): one CTA per image walks the 64-box chunks in order.  Warp 0 resolves
+//     the intra-chunk dependency chain with a ballot fix-point on the symmetric diag words
+//     (a box is kept once every earlier box that overlaps it is known to be removed; it is
+//     removed once one of them is known to be kept) instead of a 64-step serial loop; the kept
+//     rows of the chunk are then OR-ed into the shared-memory `removed` bitmap by the whole CTA
+//     with every load in flight at once.  Early exit once max_keep boxes are kept.
+//   No cudaMalloc, no host round trip, stream-ordered.
+#include "common.cuh"
+
+namespace d2t {
+namespace {
+
+typedef unsigned long long u64;
+
+// a = earlier box, b = later box; both as (x1,y1,x2,y2).
+__device__ __forceinline__ bool iou_gt(float4 a, float Sa, float4 b, float thresh, bool fast_reject) {
+    float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+    float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+    float inter = __fmul_rn(w, h);
+    // inter == 0 -> iou is 0, -0 or NaN, none of which is > thresh when thresh >= 0
+    if (fast_reject && inter == 0.f) return false;
+    float wb = __fadd_rn(__fsub_rn(b.z, b.x), 1.f), hb = __fadd_rn(__fsub_rn(b.w, b.y), 1.f);
+    float t = __fmaf_rn(wb, hb, Sa);
+    float den = __fsub_rn(t, inter);
+    return __fdiv_rn(inter, den) > thresh;
+}
+__device__ __forceinline__ float box_area(float4 a) {
+    return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+}
+__device__ __forceinline__ float4 load_box(const float* p) {
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// grid (cb, cb, B); blocks below the diagonal exit.
+__global__ void __launch_bounds__(64)
+nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N, int box_dim, int cb,
+         float thresh, u64* __restrict__ mask, u64* __restrict__ diag) {
+    const int r = blockIdx.y, c = blockIdx.x, img = blockIdx.z;
+    if (c < r) return;
+    const int n = n_valid ? min(n_valid[img], N) : N;
+    if (r * 64 >= n || c * 64 >= n) return;
+    const float* bx = boxes + (size_t)img * N * box_dim;
+    const int tid = threadIdx.x;
+    const bool fast = thresh >= 0.f;
+
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const int col_size = min(n - c * 64, 64), row_size = min(n - r * 64, 64);
+    if (tid < col_size) {
+        float4 b = load_box(bx + (size_t)(c * 64 + tid) * box_dim);
+        cbox[tid] = b;
+        carea[tid] = box_area(b);
+    }
+    __syncthreads();
+    if (tid >= row_size) return;
+    const int row = r * 64 + tid;
+    const float4 a = (r == c) ? cbox[tid] : load_box(bx + (size_t)row * box_dim);
+    const float Sa = (r == c) ? carea[tid] : box_area(a);
+    u64 bits = 0;
+    if (r == c) {
+        for (int j = 0; j < col_size; ++j) {
+            if (j == tid) continue;
+            bool s = (j > tid) ? iou_gt(a, Sa, cbox[j], thresh, fast) : iou_gt(cbox[j], carea[j], a, thresh, fast);
+            if (s) bits |= 1ull << j;
+        }
+        diag[(size_t)img * N + row] = bits;
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < col_size; ++j)
+            if (iou_gt(a, Sa, cbox[j], thresh, fast)) bits |= 1ull << j;
+        mask[((size_t)img * N + row) * cb + c] = bits;
+    }
+}
+
+constexpr int kSweepThreads = 512;
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep(const u64* __restrict__ mask, const u64* __restrict__ diag, const int* __restrict__ n_valid, int N,
+          int cb, int max_keep, int* __restrict__ keep, int keep_stride, int* __restrict__ num_keep) {
+    extern __shared__ u64 removed[];  // [cb]
+    __shared__ int s_list[64];
+    __shared__ int s_nk, s_count;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = n_valid ? min(n_valid[img], N) : N;
+    const int nchunks = (n + 63) >> 6;
+    const u64* dg = diag + (size_t)img * N;
+    const u64* mk = mask + (size_t)img * N * cb;
+    int* kp = keep + (size_t)img * keep_stride;
+    const int cap = max_keep > 0 ? min(max_keep, keep_stride) : keep_stride;
+
+    for (int t = tid; t < cb; t += blockDim.x) removed[t] = 0;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    int count = 0;  // meaningful in warp 0
+    for (int k = 0; k < nchunks; ++k) {
+        if (warp == 0) {
+            const int base = k << 6;
+            const int i0 = base + lane, i1 = i0 + 32;
+            const u64 S0 = i0 < n ? dg[i0] : 0ull, S1 = i1 < n ? dg[i1] : 0ull;
+            const int rem = n - base;
+            const u64 valid = rem >= 64 ? ~0ull : ((1ull << rem) - 1ull);
+            u64 U = ~removed[k] & valid, K = 0;
+            const u64 P0 = S0 & ((1ull << lane) - 1ull);
+            const u64 P1 = S1 & ((1ull << (lane + 32)) - 1ull);
+            while (U != 0ull) {
+                const bool in0 = (U >> lane) & 1ull, in1 = (U >> (lane + 32)) & 1ull;
+                const bool rm0 = in0 && (P0 & K), rm1 = in1 && (P1 & K);
+                const bool kp0 = in0 && !rm0 && !(P0 & U), kp1 = in1 && !rm1 && !(P1 & U);
+                const u64 newK = (u64)__ballot_sync(0xffffffffu, kp0) | ((u64)__ballot_sync(0xffffffffu, kp1) << 32);
+                const u64 dec = (u64)__ballot_sync(0xffffffffu, kp0 || rm0) |
+                                ((u64)__ballot_sync(0xffffffffu, kp1 || rm1) << 32);
+                K |= newK;
+                U &= ~dec;
+            }
+            // keep at most (cap - count) of them, lowest indices first
+            const int room = cap - count;
+            const int rank0 = __popcll(K & ((1ull << lane) - 1ull));
+            const int rank1 = __popcll(K & ((1ull << (lane + 32)) - 1ull));
+            const bool w0 = ((K >> lane) & 1ull) && rank0 < room;
+            const bool w1 = ((K >> (lane + 32)) & 1ull) && rank1 < room;
+            if (w0) { kp[count + rank0] = i0; s_list[rank0] = i0; }
+            if (w1) { kp[count + rank1] = i1; s_list[rank1] = i1; }
+            const int nk = min(__popcll(K), room);
+            count += nk;
+            if (lane == 0) { s_nk = nk; s_count = count; }
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        const bool done = s_count >= cap;
+        if (done || k + 1 >= nchunks) break;
+        // OR the kept rows of this chunk into removed[k+1 .. nchunks)
+        const int ncols = nchunks - (k + 1);
+        for (int ri = warp; ri < nk; ri += kSweepThreads / 32) {
+            const u64* rowp = mk + (size_t)s_list[ri] * cb + (k + 1);
+#pragma unroll 2
+            for (int t = lane; t < ncols; t += 32) {
+                const u64 v = rowp[t];
+                if (v) atomicOr(&removed[k + 1 + t], v);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) num_keep[img] = s_count;
+}
+
+}  // namespace
+}  // namespace d2t
+
+using namespace d2t;
+
+extern "C" size_t d2t_nms_workspace_bytes(int B, int N) {
+    size_t cb = ((size_t)N + 63) / 64;
+    return align_up((size_t)B * N * cb * 8 + (size_t)B * N * 8, 256);
+}
+
+extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int box_dim, float thresh,
+                               int max_keep, int* keep, int keep_stride, int* num_keep, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream) {
+    D2T_REQUIRE(B >= 0 && N >= 0 && box_dim >= 4, "d2t_nms_batched: bad sizes");
+    if (B == 0) return 1;
+    D2T_REQUIRE(num_keep, "d2t_nms_batched: null num_keep");
+    if (N == 0) {
+        D2T_CUDA_OK(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream), "nms memset");
+        return 1;
+    }
+    D2T_REQUIRE(boxes && keep && workspace, "d2t_nms_batched: null pointer");
+    D2T_REQUIRE(workspace_bytes >= d2t_nms_workspace_bytes(B, N), "d2t_nms_batched: workspace too small");
+    D2T_REQUIRE(max_keep > 0 ? keep_stride >= 1 : keep_stride >= N, "d2t_nms_batched: keep_stride too small");
+    const int cb = (N + 63) / 64;
+    D2T_REQUIRE(cb <= 65535 && B <= 65535, "d2t_nms_batched: too many boxes/images");
+    D2T_REQUIRE((size_t)cb * 8 <= 200 * 1024, "d2t_nms_batched: N too large for the sweep bitmap");
+    u64* mask = reinterpret_cast<u64*>(workspace);
+    u64* diag = mask + (size_t)B * N * cb;
+    nms_mask<<<dim3(cb, cb, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask, diag);
+    D2T_CHECK_LAUNCH("nms_mask");
+    size_t smem = (size_t)cb * 8;
+    if (smem > 40 * 1024) {
+        static SmemAttrOnce once;
+        if (!once.ensure(nms_sweep, 200 * 1024, "nms_sweep smem attr")) return 0;
+    }
+    nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep);
+    D2T_CHECK_LAUNCH("nms_sweep");
+    return 1;
+}
+
+// nms_cuda_kernel.h:5-6 -- device pointers, synchronous, legacy default stream.
+extern "C" void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_num, int boxes_dim,
+                                 float nms_overlap_thresh) {
+    if (boxes_num <= 0) {
+        if (num_out) cudaMemsetAsync(num_out, 0, sizeof(int), 0);
+        cudaStreamSynchronize(0);
+        return;
+    }
+    ScratchLease lease;
+    if (!lease_scratch(1, d2t_nms_workspace_bytes(1, boxes_num), lease)) return;
+    if (d2t_nms_batched(boxes_host, nullptr, 1, boxes_num, boxes_dim, nms_overlap_thresh, 0, keep_out, boxes_num,
+                        num_out, lease.ptr, lease.bytes, 0))
+        cudaStreamSynchronize(0);
+}

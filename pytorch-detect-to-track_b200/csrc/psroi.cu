@@ -1,0 +1,426 @@
+// psroi.cu -- position-sensitive RoI pooling, forward + backward, for sm_100a.
+//
+// Replaces PSROIPoolForward / PSROIPoolBackward and their launchers
+// (/root/reference/lib/model/psroi_pooling/src/psroi_pooling_kernel.cu:15-79, 82-106, 109-170,
+// 172-197).  Semantics restated in SURVEY.md App. A.2; arithmetic pinned with explicit
+// __fmul_rn/__fmaf_rn/__fdiv_rn to what nvcc emits for the reference source on sm_100a
+// (FFMA for `end*scale - start` and for `ph*bin + start`), so the integer bin windows are
+// bit-exact and, because each bin is summed in the reference's row-major order, so are the
+// pooled values.
+//
+// Design (B200): the reference reads one channel plane per output element with adjacent
+// threads H*W floats apart -- fully uncoalesced, ~70 MB of sector traffic per image.  Here a
+// CTA owns one (image, ctop, ph) = G consecutive channel planes (pw = 0..G-1), which are ONE
+// contiguous G*H*W*4-byte span of the NCHW tensor: it is pulled into shared memory with a
+// single 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) and every RoI of that image is then served
+// from shared memory.  Features therefore cross HBM exactly once (compulsory traffic), the
+// per-RoI window arithmetic is done once per RoI by a prep kernel instead of once per output
+// element, and lanes (n, pw=0..G-1) write G consecutive floats of the output.
+#include "common.cuh"
+
+namespace d2t {
+namespace {
+
+struct AxisParams {
+    float start, bin;
+};
+
+// psroi_pooling_kernel.cu:31-46 for one axis.
+__device__ __forceinline__ AxisParams psroi_axis(float c1, float c2, float scale, int P) {
+    AxisParams a;
+    a.start = __fmul_rn(roundf(c1), scale);
+    float t = __fadd_rn(roundf(c2), 1.f);
+    float ext = fmaxf(__fmaf_rn(t, scale, -a.start), 0.1f);
+    a.bin = __fdiv_rn(ext, (float)P);
+    return a;
+}
+// psroi_pooling_kernel.cu:48-61 for one axis: [lo, hi) clipped to [0, limit].
+__device__ __forceinline__ int2 psroi_window(AxisParams a, int p, int limit) {
+    int lo = __float2int_rd(__fmaf_rn((float)p, a.bin, a.start));
+    int hi = __float2int_ru(__fmaf_rn((float)(p + 1), a.bin, a.start));
+    lo = min(max(lo, 0), limit);
+    hi = min(max(hi, 0), limit);
+    return make_int2(lo, hi);
+}
+
+struct PsroiWs {
+    int* range;  // [2*B]: range[2b] = max(R - n), range[2b+1] = max(n + 1) over rois of image b
+    int* rb;     // [R] image index, -1 when out of range
+    int* bh;     // [R*PH] lo | hi << 16
+    int* bw;     // [R*PW]
+};
+
+__host__ __device__ inline size_t psroi_ws_ints(int R, int B, int PH, int PW) {
+    return (size_t)2 * B + (size_t)R + (size_t)R * PH + (size_t)R * PW;
+}
+
+__global__ void psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, int PW,
+                           int H, int W, PsroiWs ws, float* top, int D, int zero_invalid) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= R) return;
+    const float* roi = rois + (size_t)n * 5;
+    int b = (int)roi[0];
+    bool valid = b >= 0 && b < B;
+    ws.rb[n] = valid ? b : -1;
+    AxisParams aw = psroi_axis(roi[1], roi[3], scale, PW);
+    AxisParams ah = psroi_axis(roi[2], roi[4], scale, PH);
+    for (int p = 0; p < PH; ++p) {
+        int2 w = psroi_window(ah, p, H);
+        ws.bh[(size_t)n * PH + p] = w.x | (w.y << 16);
+    }
+    for (int p = 0; p < PW; ++p) {
+        int2 w = psroi_window(aw, p, W);
+        ws.bw[(size_t)n * PW + p] = w.x | (w.y << 16);
+    }
+    if (valid) {
+        atomicMax(&ws.range[2 * b], R - n);
+        atomicMax(&ws.range[2 * b + 1], n + 1);
+    } else if (zero_invalid && top) {
+        size_t per = (size_t)D * PH * PW;
+        for (size_t i = 0; i < per; ++i) top[(size_t)n * per + i] = 0.f;
+    }
+}
+
+// Stage G planes [n_el floats starting at src] into shared memory; returns the pointer p with
+// p[i] == src[i].  Interior goes through one or more TMA bulk copies, the <= 3-float misaligned
+// head/tail through ordinary loads.
+__device__ __forceinline__ const float* stage_planes(float* sm, const float* __restrict__ src, int n_el,
+                                                     uint64_t* bar) {
+    const int tid = threadIdx.x;
+    int head = (int)(((16u - (uint32_t)((uintptr_t)src & 15u)) & 15u) >> 2);
+    if (head > n_el) head = n_el;
+    float* plane = sm + ((4 - head) & 3);
+    const int bulk = ((n_el - head) >> 2) << 2;
+    const int tail = n_el - head - bulk;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (bulk > 0) {
+            mbar_expect_tx(bar, (uint32_t)bulk * 4u);
+            constexpr int kChunk = 8192;  // floats per bulk copy (32 KB)
+            for (int o = 0; o < bulk; o += kChunk) {
+                int len = min(kChunk, bulk - o);
+                bulk_g2s(plane + head + o, src + head + o, (uint32_t)len * 4u, bar);
+            }
+        } else {
+            mbar_arrive(bar);
+        }
+    }
+    if (tid < head) plane[tid] = __ldg(src + tid);
+    if (tid < tail) plane[head + bulk + tid] = __ldg(src + head + bulk + tid);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    return plane;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+psroi_fwd_planes(const float* __restrict__ feat, int C, int H, int W, int D, int R, PsroiWs ws,
+                 float* __restrict__ top, int* __restrict__ mapping) {
+    extern __shared__ float4 smem4[];
+    __shared__ uint64_t bar;
+    const int b = blockIdx.y;
+    const int end = ws.range[2 * b + 1];
+    if (end == 0) return;
+    const int begin = R - ws.range[2 * b];
+    const int ctop = blockIdx.x / G, ph = blockIdx.x % G;
+    const int HW = H * W;
+    const int c0 = (ctop * G + ph) * G;
+    const float* src = feat + ((size_t)b * C + c0) * HW;
+    const float* plane = stage_planes(reinterpret_cast<float*>(smem4), src, G * HW, &bar);
+
+    const int nitems = (end - begin) * G;
+    for (int t = threadIdx.x; t < nitems; t += blockDim.x) {
+        const int n = begin + t / G, pw = t % G;
+        if (ws.rb[n] != b) continue;
+        const int hb = ws.bh[(size_t)n * G + ph], wb = ws.bw[(size_t)n * G + pw];
+        const int hs = hb & 0xffff, he = hb >> 16, wsx = wb & 0xffff, we = wb >> 16;
+        const float* p = plane + pw * HW;
+        float s = 0.f;
+        for (int h = hs; h < he; ++h) {
+            const float* row = p + h * W;
+            for (int w = wsx; w < we; ++w) s += row[w];   // reference order: kernel.cu:69-74
+        }
+        const bool empty = (he <= hs) || (we <= wsx);
+        const float area = (float)((he - hs) * (we - wsx));
+        const size_t idx = (((size_t)n * D + ctop) * G + ph) * G + pw;
+        top[idx] = empty ? 0.f : __fdiv_rn(s, area);
+        if (mapping) mapping[idx] = c0 + pw;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+psroi_bwd_planes(const float* __restrict__ top_diff, int C, int H, int W, int D, int R, PsroiWs ws,
+                 float* __restrict__ bottom_diff, int accumulate) {
+    extern __shared__ float4 smem4[];
+    float* acc = reinterpret_cast<float*>(smem4);
+    const int b = blockIdx.y;
+    const int ctop = blockIdx.x / G, ph = blockIdx.x % G;
+    const int HW = H * W, n_el = G * HW;
+    const int c0 = (ctop * G + ph) * G;
+    float* dst = bottom_diff + ((size_t)b * C + c0) * HW;
+    const int end = ws.range[2 * b + 1];
+    if (end == 0) {
+        if (!accumulate)
+            for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] = 0.f;
+        return;
+    }
+    const int begin = R - ws.range[2 * b];
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const int nitems = (end - begin) * G;
+    for (int t = threadIdx.x; t < nitems; t += blockDim.x) {
+        const int n = begin + t / G, pw = t % G;
+        if (ws.rb[n] != b) continue;
+        const int hb = ws.bh[(size_t)n * G + ph], wb = ws.bw[(size_t)n * G + pw];
+        const int hs = hb & 0xffff, he = hb >> 16, wsx = wb & 0xffff, we = wb >> 16;
+        if (he <= hs || we <= wsx) continue;
+        const float area = (float)((he - hs) * (we - wsx));
+        const size_t idx = (((size_t)n * D + ctop) * G + ph) * G + pw;
+        const float dv = __fdiv_rn(top_diff[idx], area);   // kernel.cu:161
+        float* p = acc + pw * HW;
+        for (int h = hs; h < he; ++h)
+            for (int w = wsx; w < we; ++w) atomicAdd(p + h * W + w, dv);
+    }
+    __syncthreads();
+    if (accumulate)
+        for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] += acc[i];
+    else
+        for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] = acc[i];
+}
+
+// Generic fallbacks (any PH/PW/G, any plane size): one thread per output element.
+__global__ void psroi_fwd_generic(const float* __restrict__ feat, int B, int C, int H, int W,
+                                  const float* __restrict__ rois, int R, float scale, int PH, int PW, int G,
+                                  int D, float* __restrict__ top, int* __restrict__ mapping) {
+    const size_t total = (size_t)R * D * PH * PW;
+    for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
+         index += (size_t)gridDim.x * blockDim.x) {
+        int pw = (int)(index % PW);
+        int ph = (int)((index / PW) % PH);
+        int ctop = (int)((index / PW / PH) % D);
+        int n = (int)(index / PW / PH / D);
+        const float* roi = rois + (size_t)n * 5;
+        int b = (int)roi[0];
+        int c = (ctop * G + ph) * G + pw;
+        if (mapping) mapping[index] = c;
+        if (b < 0 || b >= B || c >= C) {
+            top[index] = 0.f;
+            continue;
+        }
+        int2 hw = psroi_window(psroi_axis(roi[2], roi[4], scale, PH), ph, H);
+        int2 ww = psroi_window(psroi_axis(roi[1], roi[3], scale, PW), pw, W);
+        const float* p = feat + ((size_t)b * C + c) * H * W;
+        float s = 0.f;
+        for (int h = hw.x; h < hw.y; ++h)
+            for (int w = ww.x; w < ww.y; ++w) s += __ldg(p + h * W + w);
+        bool empty = (hw.y <= hw.x) || (ww.y <= ww.x);
+        float area = (float)((hw.y - hw.x) * (ww.y - ww.x));
+        top[index] = empty ? 0.f : __fdiv_rn(s, area);
+    }
+}
+
+__global__ void psroi_bwd_generic(const float* __restrict__ top_diff, int B, int C, int H, int W,
+                                  const float* __restrict__ rois, int R, float scale, int PH, int PW, int G,
+                                  int D, float* __restrict__ bottom_diff) {
+    const size_t total = (size_t)R * D * PH * PW;
+    for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
+         index += (size_t)gridDim.x * blockDim.x) {
+        int pw = (int)(index % PW);
+        int ph = (int)((index / PW) % PH);
+        int ctop = (int)((index / PW / PH) % D);
+        int n = (int)(index / PW / PH / D);
+        const float* roi = rois + (size_t)n * 5;
+        int b = (int)roi[0];
+        int c = (ctop * G + ph) * G + pw;
+        if (b < 0 || b >= B || c >= C) continue;
+        int2 hw = psroi_window(psroi_axis(roi[2], roi[4], scale, PH), ph, H);
+        int2 ww = psroi_window(psroi_axis(roi[1], roi[3], scale, PW), pw, W);
+        if (hw.y <= hw.x || ww.y <= ww.x) continue;
+        float area = (float)((hw.y - hw.x) * (ww.y - ww.x));
+        float dv = __fdiv_rn(top_diff[index], area);
+        float* p = bottom_diff + ((size_t)b * C + c) * H * W;
+        for (int h = hw.x; h < hw.y; ++h)
+            for (int w = ww.x; w < ww.y; ++w) atomicAdd(p + h * W + w, dv);
+    }
+}
+
+__global__ void psroi_bins_kernel(const float* __restrict__ rois, int R, float scale, int PH, int PW, int H,
+                                  int W, int* __restrict__ bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * PH * PW) return;
+    int pw = i % PW, ph = (i / PW) % PH, n = i / PW / PH;
+    const float* roi = rois + (size_t)n * 5;
+    int2 hw = psroi_window(psroi_axis(roi[2], roi[4], scale, PH), ph, H);
+    int2 ww = psroi_window(psroi_axis(roi[1], roi[3], scale, PW), pw, W);
+    reinterpret_cast<int4*>(bins)[i] = make_int4(hw.x, hw.y, ww.x, ww.y);
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+bool planes_path_ok(int C, int H, int W, int PH, int PW, int G, int D, size_t* smem_bytes) {
+    if (PH != G || PW != G || G != 7) return false;   // tuned instantiation: the 7x7 R-FCN grid
+    if (H > 0x7fff || W > 0x7fff) return false;
+    if ((size_t)D * G * G > (size_t)C) return false;
+    size_t bytes = ((size_t)G * H * W + 4) * sizeof(float);
+    if (bytes > kMaxDynSmem) return false;
+    *smem_bytes = bytes;
+    return true;
+}
+
+PsroiWs carve(void* workspace, int R, int B, int PH, int PW) {
+    PsroiWs ws;
+    int* p = reinterpret_cast<int*>(workspace);
+    ws.range = p;
+    ws.rb = ws.range + 2 * (size_t)B;
+    ws.bh = ws.rb + R;
+    ws.bw = ws.bh + (size_t)R * PH;
+    return ws;
+}
+
+int run_prep(const float* rois, int R, int B, float scale, int PH, int PW, int H, int W, PsroiWs ws,
+             float* top, int D, int zero_invalid, cudaStream_t stream) {
+    D2T_CUDA_OK(cudaMemsetAsync(ws.range, 0, sizeof(int) * 2 * (size_t)B, stream), "psroi range memset");
+    if (R > 0) {
+        psroi_prep<<<(R + 127) / 128, 128, 0, stream>>>(rois, R, B, scale, PH, PW, H, W, ws, top, D, zero_invalid);
+        D2T_CHECK_LAUNCH("psroi_prep");
+    }
+    return 1;
+}
+
+int grid_for(size_t total) {
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)sm_count() * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+}  // namespace d2t
+
+using namespace d2t;
+
+extern "C" size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w) {
+    return align_up(psroi_ws_ints(num_rois, batch, pooled_h, pooled_w) * sizeof(int), 256);
+}
+
+extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, int height, int width,
+                                 const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,
+                                 int group, int out_dim, float* top, int* mapping, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+    D2T_REQUIRE(batch > 0 && channels > 0 && height > 0 && width > 0 && pooled_h > 0 && pooled_w > 0 &&
+                    group > 0 && out_dim > 0 && num_rois >= 0,
+                "d2t_psroi_forward: bad sizes");
+    if (num_rois == 0) return 1;
+    D2T_REQUIRE(bottom && rois && top, "d2t_psroi_forward: null pointer");
+    size_t smem = 0;
+    if (planes_path_ok(channels, height, width, pooled_h, pooled_w, group, out_dim, &smem) && workspace &&
+        workspace_bytes >= d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w)) {
+        PsroiWs ws = carve(workspace, num_rois, batch, pooled_h, pooled_w);
+        if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, top, out_dim, 1, stream))
+            return 0;
+        static SmemAttrOnce once;
+        if (!once.ensure(psroi_fwd_planes<7>, kMaxDynSmem, "psroi_fwd smem attr")) return 0;
+        dim3 grid(out_dim * group, batch);
+        psroi_fwd_planes<7><<<grid, 256, smem, stream>>>(bottom, channels, height, width, out_dim, num_rois, ws,
+                                                         top, mapping);
+        D2T_CHECK_LAUNCH("psroi_fwd_planes");
+        return 1;
+    }
+    size_t total = (size_t)num_rois * out_dim * pooled_h * pooled_w;
+    psroi_fwd_generic<<<grid_for(total), 256, 0, stream>>>(bottom, batch, channels, height, width, rois, num_rois,
+                                                          scale, pooled_h, pooled_w, group, out_dim, top, mapping);
+    D2T_CHECK_LAUNCH("psroi_fwd_generic");
+    return 1;
+}
+
+extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels, int height, int width,
+                                  const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,
+                                  int group, int out_dim, float* bottom_diff, int accumulate, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+    D2T_REQUIRE(batch > 0 && channels > 0 && height > 0 && width > 0 && pooled_h > 0 && pooled_w > 0 &&
+                    group > 0 && out_dim > 0 && num_rois >= 0,
+                "d2t_psroi_backward: bad sizes");
+    D2T_REQUIRE(bottom_diff, "d2t_psroi_backward: null bottom_diff");
+    size_t smem = 0;
+    if (planes_path_ok(channels, height, width, pooled_h, pooled_w, group, out_dim, &smem) && workspace &&
+        workspace_bytes >= d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w)) {
+        PsroiWs ws = carve(workspace, num_rois, batch, pooled_h, pooled_w);
+        if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, nullptr, out_dim, 0, stream))
+            return 0;
+        static SmemAttrOnce once;
+        if (!once.ensure(psroi_bwd_planes<7>, kMaxDynSmem, "psroi_bwd smem attr")) return 0;
+        if (!accumulate && (size_t)out_dim * group * group < (size_t)channels) {
+            // channels no bin maps to: zero them so the result is the full gradient
+            size_t used = (size_t)out_dim * group * group, hw = (size_t)height * width;
+            for (int b = 0; b < batch; ++b)
+                D2T_CUDA_OK(cudaMemsetAsync(bottom_diff + ((size_t)b * channels + used) * hw, 0,
+                                            (channels - used) * hw * sizeof(float), stream),
+                            "psroi_bwd tail memset");
+        }
+        dim3 grid(out_dim * group, batch);
+        psroi_bwd_planes<7><<<grid, 256, smem, stream>>>(top_diff, channels, height, width, out_dim, num_rois, ws,
+                                                         bottom_diff, accumulate);
+        D2T_CHECK_LAUNCH("psroi_bwd_planes");
+        return 1;
+    }
+    if (!accumulate)
+        D2T_CUDA_OK(cudaMemsetAsync(bottom_diff, 0, (size_t)batch * channels * height * width * sizeof(float), stream),
+                    "psroi_bwd memset");
+    if (num_rois == 0) return 1;
+    size_t total = (size_t)num_rois * out_dim * pooled_h * pooled_w;
+    psroi_bwd_generic<<<grid_for(total), 256, 0, stream>>>(top_diff, batch, channels, height, width, rois, num_rois,
+                                                          scale, pooled_h, pooled_w, group, out_dim, bottom_diff);
+    D2T_CHECK_LAUNCH("psroi_bwd_generic");
+    return 1;
+}
+
+extern "C" int d2t_psroi_bins(const float* rois, int num_rois, float scale, int pooled_h, int pooled_w, int height,
+                              int width, int* bins, cudaStream_t stream) {
+    if (num_rois <= 0) return 1;
+    int total = num_rois * pooled_h * pooled_w;
+    psroi_bins_kernel<<<(total + 255) / 256, 256, 0, stream>>>(rois, num_rois, scale, pooled_h, pooled_w, height,
+                                                               width, bins);
+    D2T_CHECK_LAUNCH("psroi_bins");
+    return 1;
+}
+
+// ---- reference-named launchers (psroi_pooling_kernel.h:8-14) ----
+// The reference forward launcher is not told the batch size (each roi's image index addresses
+// bottom_data directly), and the planes path needs it to size its grid and per-image roi
+// ranges.  The legacy forward therefore runs the generic kernel with B = INT_MAX, i.e. the
+// reference's own addressing; the tuned path is reached through d2t_psroi_forward, where the
+// caller states the batch size (the Python host layer always does).
+extern "C" int PSROIPoolForwardLauncher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                                        const int height, const int width, const int channels,
+                                        const int pooled_height, const int pooled_width, const float* bottom_rois,
+                                        const int group_size, const int output_dim, float* top_data,
+                                        int* mapping_channel, cudaStream_t stream) {
+    if (num_rois <= 0) return 1;
+    D2T_REQUIRE(bottom_data && bottom_rois && top_data, "PSROIPoolForwardLauncher: null pointer");
+    size_t total = (size_t)num_rois * output_dim * pooled_height * pooled_width;
+    psroi_fwd_generic<<<grid_for(total), 256, 0, stream>>>(bottom_data, 0x7fffffff, channels, height, width,
+                                                          bottom_rois, num_rois, spatial_scale, pooled_height,
+                                                          pooled_width, group_size, output_dim, top_data,
+                                                          mapping_channel);
+    D2T_CHECK_LAUNCH("PSROIPoolForwardLauncher");
+    return 1;
+}
+
+extern "C" int PSROIPoolBackwardLauncher(const float* top_diff, const int* mapping_channel, const int batch_size,
+                                         const int num_rois, const float spatial_scale, const int channels,
+                                         const int height, const int width, const int pooled_width,
+                                         const int pooled_height, const int output_dim, float* bottom_diff,
+                                         const float* bottom_rois, cudaStream_t stream) {
+    (void)mapping_channel;  // pure function of the output index (kernel.cu:64-66)
+    const int group = pooled_width;
+    size_t need = d2t_psroi_workspace_bytes(num_rois, batch_size, pooled_height, pooled_width);
+    ScratchLease lease;
+    if (!lease_scratch(0, need, lease)) return 0;
+    return d2t_psroi_backward(top_diff, batch_size, channels, height, width, bottom_rois, num_rois, spatial_scale,
+                              pooled_height, pooled_width, group, output_dim, bottom_diff, /*accumulate=*/1,
+                              lease.ptr, lease.bytes, stream);
+}
