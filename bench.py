@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- Detect-to-Track per-frame-pair hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
+
+A "step" is one eval-mode forward of the D&T graph (Res-101 siamese trunk -> RPN proposals + NMS ->
+PSRoI cls/loc -> 3 correlations -> tracking PSRoI) over the per-GPU batch of synthetic 600x1000
+frame-pairs (BASELINE.json configs[1]: batch = 2 pairs on 1 GPU; N GPUs = N x 2 pairs, sharded by
+image, no data-path collective -> weak scaling).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "pytorch-detect-to-track_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "frame-pairs/sec (Res-101 D&T, 600px)"
+H, W = 600, 1000
+PAIRS_PER_GPU = 2
+CLASSES = tuple(range(31))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def make_inputs(pairs, seed):
+    g = torch.Generator().manual_seed(seed)
+    im_data = torch.rand(pairs, 2, 3, H, W, generator=g) * 256.0 - 128.0     # mean-subtracted-image-like
+    im_info = torch.tensor([float(H), float(W), 1.0]).view(1, 1, 3).expand(pairs, 2, 3).contiguous()
+    return im_data, im_info
+
+
+def build_net(layers=101):
+    from model.faster_rcnn.resnet import resnet
+    torch.manual_seed(3)
+    return resnet(CLASSES, layers, class_agnostic=True).create_architecture().eval()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def flush_l2(buf):
+    buf.add_(1.0)   # 512 MB read+write > 126 MB L2
+
+
+def time_kernel(fn, iters, flush):
+    """Average device time (ms) of fn() over `iters` launches, CUDA events on the current stream,
+    L2 flushed between launches."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def op_microbench(flush, hbm_gbs):
+    """BASELINE configs[3] and [4] at a fixed batch: PSRoI (the roofline kernel of the metric),
+    conv4 correlation, proposal-size NMS.  Algorithmic bytes: SURVEY.md section 8d / DESIGN.md."""
+    import common
+    from d2t_b200 import ops
+    from d2t_b200._lib import lib
+    out = {}
+    B, D, R = 2, 30, 2000
+    torch.manual_seed(20)
+    feat = torch.randn(B, D * 49, 38, 63, device="cuda")
+    rois = torch.from_numpy(common.make_rois(R, B, seed=21)).cuda()
+    top = torch.empty(B * R, D, 7, 7, device="cuda")
+    ws = torch.empty(lib().d2t_psroi_workspace_bytes(B * R, B, 7, 7), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def psroi():   # the C-ABI call itself: prep kernel + planes kernel, mapping_channel skipped
+        lib().d2t_psroi_forward(feat.data_ptr(), B, D * 49, 38, 63, rois.data_ptr(), B * R, 1 / 16., 7, 7, 7, D,
+                                top.data_ptr(), None, ws.data_ptr(), ws.numel(), st)
+    ms = time_kernel(psroi, 30, flush)
+    alg = 4.0 * (D * 49 * 2394 + 5 * R + R * D * 49) * B
+    out["psroi_fwd"] = {"shape": "feat[%d,%d,38,63] rois %d/img D=%d" % (B, D * 49, R, D), "ms": ms,
+                        "algorithmic_bytes": alg, "gbs": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / hbm_gbs}
+    gt = torch.randn_like(top)
+    grad = torch.empty_like(feat)
+
+    def psroi_b():
+        lib().d2t_psroi_backward(gt.data_ptr(), B, D * 49, 38, 63, rois.data_ptr(), B * R, 1 / 16., 7, 7, 7, D,
+                                 grad.data_ptr(), 0, ws.data_ptr(), ws.numel(), st)
+    ms = time_kernel(psroi_b, 20, flush)
+    out["psroi_bwd"] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / hbm_gbs}
+    for name, (C_, Hh, Ww, p, Bc) in {"corr_conv4": (1024, 38, 63, (8, 1, 8, 1, 1), 2), "corr_conv5": (2048, 38, 63, (8, 1, 8, 1, 1), 2),
+                                      "corr_conv3": (512, 75, 125, (8, 1, 8, 2, 2), 2)}.items():
+        a, b = torch.randn(Bc, C_, Hh, Ww, device="cuda"), torch.randn(Bc, C_, Hh, Ww, device="cuda")
+        oc, oh, ow = ops.correlation_shape(Hh, Ww, *p)
+        o = torch.empty(Bc, oc, oh, ow, device="cuda")
+
+        def corr():
+            lib().d2t_correlation_forward(a.data_ptr(), b.data_ptr(), Bc, C_, Hh, Ww, *p, o.data_ptr(), st)
+        ms = time_kernel(corr, 20, flush)
+        touched = (oh * ow) if p[3] > 1 else Hh * Ww      # stride-2 lattice reads 1/4 of the elements
+        alg = 4.0 * (2 * C_ * touched + oc * oh * ow) * Bc
+        flops = 2.0 * oc * oh * ow * C_ * Bc
+        out[name] = {"batch": Bc, "ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6,
+                     "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_fp32": flops / ms / 1e9}
+    for n in (6000, 12000):
+        dets = torch.from_numpy(np.stack([common.make_dets(n, seed=22 + i) for i in range(4)])).cuda()
+        ms = time_kernel(lambda: ops.nms_batched(dets, 0.7, max_keep=300 if n == 6000 else 2000), 10, flush)
+        out["nms_%d_x4img" % n] = {"ms": ms, "us_per_image": ms * 1e3 / 4}
+    return out
+
+
+def cpu_path_pairs_per_sec(threads, steps, warmup, budget_s=240.0):
+    """The reference's CPU path (oracle/cpu_graph.py) on ONE 600x1000 frame-pair per step."""
+    from oracle import cpu as oracle
+    from oracle import cpu_graph
+    torch.set_num_threads(threads)
+    oracle.lib().oracle_set_threads(threads)
+    net = build_net(101)
+    im_data, im_info = make_inputs(1, seed=1)
+    t0 = time.time()
+    cpu_graph.forward_eval(net, im_data, im_info)
+    first = time.time() - t0
+    w_run = max(0, min(warmup - 1, int(budget_s * 0.25 / max(first, 1e-3))))
+    k_run = max(1, min(steps, int(budget_s * 0.75 / max(first, 1e-3))))
+    for _ in range(w_run):
+        cpu_graph.forward_eval(net, im_data, im_info)
+    times = []
+    for _ in range(k_run):
+        t0 = time.time()
+        cpu_graph.forward_eval(net, im_data, im_info)
+        times.append(time.time() - t0)
+    sec = float(np.mean(times))
+    return 1.0 / sec, sec, k_run, w_run + 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    value, sec, k_run, w_run = cpu_path_pairs_per_sec(threads, args.steps, args.warmup)
+    sample = "1 frame-pair (2 frames 600x1000) per step, full eval graph on host cores; %d timed steps" % k_run
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": args.gpus,
+            "steps": k_run, "warmup": w_run, "steps_requested": args.steps, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation",
+                       "pairs_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from d2t_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the d2t_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    hbm_gbs, _tf, peak_src = peaks()
+
+    net = build_net(101).cuda()
+    pairs = PAIRS_PER_GPU
+    im_host, info_host = make_inputs(pairs, seed=1 + rank)          # shard = this rank's own pairs
+    im_pin, info_pin = im_host.pin_memory(), info_host.pin_memory()
+    im_dev, info_dev = im_pin.cuda(non_blocking=True), info_pin.cuda(non_blocking=True)
+    flush = torch.zeros(128 * 1024 * 1024, device="cuda")          # 512 MB
+
+    def step(im, info):
+        with torch.no_grad():
+            return net(im, info, None, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(im_dev, info_dev)
+    barrier()
+
+    # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(im_dev, info_dev)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    my_launches = ops.LAUNCHES - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API: pinned host -> device, forward, results -> host
+    outs_pin = None
+    e2e_evs = []
+    d2h = 0
+    for it in range(3 + args.steps):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        im = im_pin.to("cuda", non_blocking=True)
+        info = info_pin.to("cuda", non_blocking=True)
+        o = step(im, info)[:4]
+        if outs_pin is None:
+            outs_pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
+            d2h = sum(t.numel() * t.element_size() for t in o)
+        for dst, src in zip(outs_pin, o):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        if it >= 3:
+            e2e_evs.append((a, b))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    h2d = im_pin.numel() * 4 + info_pin.numel() * 4
+
+    t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ops_bench = op_microbench(flush, hbm_gbs)
+        ps = ops_bench["psroi_fwd"]
+        roofline = {"kernel": "psroi_fwd_planes<7> (+ psroi_prep) via d2t_psroi_forward", "bound": "hbm",
+                    "achieved": ps["gbs"], "peak": hbm_gbs, "unit": "GB/s", "frac": ps["frac_hbm"],
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ps["algorithmic_bytes"],
+                    "avg_launch_ms": ps["ms"]}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, sec, k_run, _ = cpu_path_pairs_per_sec(threads, 2, 1, budget_s=60.0)
+            cpu_baseline = {"value": v, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+                            "sample": "1 frame-pair (2 frames 600x1000) eval forward x %d on host cores "
+                                      "(torch.nn fp32 convs + oracle/ C restatements)" % k_run}
+        ms_per_step = total_ms / args.steps
+        line = {"metric": METRIC, "value": world * pairs / (ms_per_step / 1e3), "unit": "frame-pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": "Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation "
+                                       "(BASELINE.json configs[1])",
+                           "pairs_per_gpu": pairs, "global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
+                           "l2": "512 MB buffer rewritten between timed steps",
+                           "convs": net.conv_backend if hasattr(net, "conv_backend") else "torch.nn (cuDNN fp32, TF32 off)"},
+                "e2e": {"value": world * pairs / (e2e_ms / args.steps / 1e3), "unit": "frame-pairs/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": my_launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "ops": ops_bench}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,8 +25,36 @@
 #include <string.h>
 #include <float.h>
 
+#include <pthread.h>
+
 #define IMIN(a, b) ((a) < (b) ? (a) : (b))
 #define IMAX(a, b) ((a) > (b) ? (a) : (b))
+
+/* ------------------------------------------------------------------------------------
+ * Host threading for the CPU-baseline timings (no OpenMP runtime in this image): the outer
+ * loop of the forward restatements is split into contiguous index ranges, one per thread.
+ * Every output element is still produced by exactly one thread with the same arithmetic, so
+ * results do not depend on the thread count.  oracle_set_threads(1) (the default) = serial.
+ * ------------------------------------------------------------------------------------ */
+static int g_threads = 1;
+void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+int oracle_get_threads(void) { return g_threads; }
+
+typedef void (*range_fn)(int begin, int end, void* ctx);
+typedef struct { range_fn fn; void* ctx; int begin, end; } range_job;
+static void* range_tramp(void* p) { range_job* j = (range_job*)p; j->fn(j->begin, j->end, j->ctx); return NULL; }
+static void parallel_range(int n, range_fn fn, void* ctx)
+{
+    int T = IMIN(g_threads, n);
+    if (T <= 1) { fn(0, n, ctx); return; }
+    pthread_t th[256]; range_job jobs[256];
+    for (int t = 0; t < T; ++t) {
+        jobs[t].fn = fn; jobs[t].ctx = ctx;
+        jobs[t].begin = (int)((long long)n * t / T); jobs[t].end = (int)((long long)n * (t + 1) / T);
+        pthread_create(&th[t], NULL, range_tramp, &jobs[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+}
 
 /* ------------------------------------------------------------------------------------
  * PSRoI pooling   psroi_pooling/src/psroi_pooling_kernel.cu:15-79 (fwd), :109-170 (bwd)
@@ -81,14 +109,15 @@ void oracle_psroi_bin(const float* roi, float scale, int PH, int PW, int H, int 
 
 /* bins: optional int32 [R, PH, PW, 4] dump of the integer windows (may be NULL).
  * mapping: optional int32 [R, D, PH, PW]. */
-void oracle_psroi_forward(const float* feat, int B, int C, int H, int W,
-                          const float* rois, int R, float scale, int PH, int PW,
-                          int G, int D, int contract,
-                          float* top, int32_t* mapping, int32_t* bins)
+typedef struct { const float* feat; int B, C, H, W; const float* rois; float scale; int PH, PW, G, D, contract;
+                 float* top; int32_t* mapping; int32_t* bins; } psroi_ctx;
+static void psroi_fwd_range(int n0, int n1, void* vp)
 {
-    (void)B;
-    #pragma omp parallel for schedule(static)
-    for (int n = 0; n < R; ++n) {
+    psroi_ctx* q = (psroi_ctx*)vp;
+    const float* feat = q->feat; const float* rois = q->rois; float scale = q->scale;
+    int C = q->C, H = q->H, W = q->W, PH = q->PH, PW = q->PW, G = q->G, D = q->D, contract = q->contract;
+    float* top = q->top; int32_t* mapping = q->mapping; int32_t* bins = q->bins;
+    for (int n = n0; n < n1; ++n) {
         const float* roi = rois + 5 * n;
         int b = (int)roi[0];
         for (int ph = 0; ph < PH; ++ph)
@@ -111,6 +140,14 @@ void oracle_psroi_forward(const float* feat, int B, int C, int H, int W,
                 }
             }
     }
+}
+void oracle_psroi_forward(const float* feat, int B, int C, int H, int W,
+                          const float* rois, int R, float scale, int PH, int PW,
+                          int G, int D, int contract,
+                          float* top, int32_t* mapping, int32_t* bins)
+{
+    psroi_ctx q = { feat, B, C, H, W, rois, scale, PH, PW, G, D, contract, top, mapping, bins };
+    parallel_range(R, psroi_fwd_range, &q);
 }
 
 /* bottom_diff must be zero-filled by the caller (functions/psroi_pool.py:40).
@@ -212,17 +249,19 @@ static inline float padded_at(const float* in, int C, int H, int W, int n, int c
 /* Reduction order follows the reference: lane l of the 32-thread block accumulates
  * channels l, l+32, ... over the k*k window with FFMA (kernel.cu:78-90), lane 0 sums the
  * 32 partials in order and divides by nelems (:93-100). */
-void oracle_correlation_forward(const float* in1, const float* in2, int B, int C, int H,
-                                int W, int pad, int k, int md, int s1, int s2, float* out)
+typedef struct { const float* in1; const float* in2; int B, C, H, W, pad, k, md, s1, s2; float* out; } corr_ctx;
+static void corr_fwd_range(int row0, int row1, void* vp)
 {
+    corr_ctx* q = (corr_ctx*)vp;
+    const float* in1 = q->in1; const float* in2 = q->in2; float* out = q->out;
+    int C = q->C, H = q->H, W = q->W, pad = q->pad, k = q->k, md = q->md, s1 = q->s1, s2 = q->s2;
     int sh[3];
     oracle_correlation_shape(H, W, pad, k, md, s1, s2, sh);
     int oc = sh[0], oh = sh[1], ow = sh[2];
     int kr = (k - 1) / 2, r = md / s2, Dd = 2 * r + 1;
     float nelems = (float)(k * k * C);
-    #pragma omp parallel for collapse(2) schedule(static)
-    for (int n = 0; n < B; ++n)
-        for (int y = 0; y < oh; ++y)
+    for (int row = row0; row < row1; ++row) {
+        int n = row / oh, y = row % oh;
             for (int x = 0; x < ow; ++x) {
                 int y1 = y * s1 + md + kr, x1 = x * s1 + md + kr;
                 for (int tj = -r; tj <= r; ++tj)
@@ -243,6 +282,15 @@ void oracle_correlation_forward(const float* in1, const float* in2, int B, int C
                         out[(((size_t)n * oc + tc) * oh + y) * ow + x] = s / nelems;
                     }
             }
+    }
+}
+void oracle_correlation_forward(const float* in1, const float* in2, int B, int C, int H,
+                                int W, int pad, int k, int md, int s1, int s2, float* out)
+{
+    int sh[3];
+    oracle_correlation_shape(H, W, pad, k, md, s1, s2, sh);
+    corr_ctx q = { in1, in2, B, C, H, W, pad, k, md, s1, s2, out };
+    parallel_range(B * sh[1], corr_fwd_range, &q);
 }
 
 /* Faithful restatement of Correlation_backward_input1/_input2 including their launch
@@ -391,7 +439,6 @@ void oracle_roi_align_forward(const float* feat, int B, int C, int H, int W,
                               float* top)
 {
     (void)B;
-    #pragma omp parallel for schedule(static)
     for (int n = 0; n < R; ++n) {
         const float* roi = rois + 5 * n;
         int b = (int)roi[0];
@@ -457,7 +504,6 @@ void oracle_roi_pool_forward(const float* feat, int B, int C, int H, int W,
                              float* top, int32_t* argmax)
 {
     (void)B;
-    #pragma omp parallel for schedule(static)
     for (int n = 0; n < R; ++n) {
         const float* roi = rois + 5 * n;
         int b = (int)roi[0];
@@ -510,7 +556,6 @@ void oracle_roi_crop_forward(const float* img, int B, int C, int H, int W,
                              const float* grid, int R, int gh, int gw, float* out)
 {
     int per = R / B;
-    #pragma omp parallel for schedule(static)
     for (int b = 0; b < R; ++b) {
         int bi = b / per;
         for (int yo = 0; yo < gh; ++yo)

@@ -1,0 +1,374 @@
+"""Torch-tensor front end of libd2t_b200.so: raw-pointer calls + autograd glue.
+
+Every function takes contiguous fp32 CUDA tensors, enqueues on torch's current stream and
+allocates its outputs / workspaces from torch's caching allocator (stream-ordered, no
+cudaMalloc on the hot path).  The reference-shaped classes under ``model/`` are thin shells
+over the functions here.  Nothing in this file computes on the CPU.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib
+
+
+# kernels of libd2t_b200.so enqueued since import (bench.py reports the delta as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (d2t_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------- PSRoI
+def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, want_mapping=True):
+    """psroi_pooling/functions/psroi_pool.py:18-33 -> d2t_psroi_forward."""
+    _req(features, "features"), _req(rois, "rois")
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be [R, 5]")   # the reference returns 0 silently (psroi_pooling_cuda.c:17-20)
+    B, Cc, H, W = features.shape
+    R = rois.size(0)
+    with torch.cuda.device_of(features):
+        top = torch.empty(R, out_dim, pooled_h, pooled_w, device=features.device)
+        mapping = torch.empty(R, out_dim, pooled_h, pooled_w, dtype=torch.int32, device=features.device) if want_mapping else None
+        nbytes = lib().d2t_psroi_workspace_bytes(R, B, pooled_h, pooled_w)
+        ws = _ws(nbytes, features.device)
+        check(lib().d2t_psroi_forward(features.data_ptr(), B, Cc, H, W, rois.data_ptr(), R, scale, pooled_h, pooled_w,
+                                      group, out_dim, top.data_ptr(), mapping.data_ptr() if want_mapping else None,
+                                      ws.data_ptr(), ws.numel(), _stream()), "d2t_psroi_forward")
+        _count(2)
+    return top, mapping
+
+
+def psroi_backward(top_diff, rois, feature_size, pooled_h, pooled_w, scale, group, out_dim):
+    _req(top_diff, "grad_output"), _req(rois, "rois")
+    B, Cc, H, W = feature_size
+    R = rois.size(0)
+    with torch.cuda.device_of(top_diff):
+        grad = torch.empty(B, Cc, H, W, device=top_diff.device)
+        ws = _ws(lib().d2t_psroi_workspace_bytes(R, B, pooled_h, pooled_w), top_diff.device)
+        check(lib().d2t_psroi_backward(top_diff.data_ptr(), B, Cc, H, W, rois.data_ptr(), R, scale, pooled_h, pooled_w,
+                                       group, out_dim, grad.data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream()),
+              "d2t_psroi_backward")
+        _count(2)
+    return grad
+
+
+def psroi_bins(rois, pooled_h, pooled_w, scale, height, width):
+    _req(rois, "rois")
+    bins = torch.empty(rois.size(0), pooled_h, pooled_w, 4, dtype=torch.int32, device=rois.device)
+    with torch.cuda.device_of(rois):
+        check(lib().d2t_psroi_bins(rois.data_ptr(), rois.size(0), scale, pooled_h, pooled_w, height, width,
+                                   bins.data_ptr(), _stream()), "d2t_psroi_bins")
+        _count(1)
+    return bins
+
+
+class _PSRoI(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ph, pw, scale, group, out_dim, holder):
+        top, mapping = psroi_forward(features, rois, ph, pw, scale, group, out_dim)
+        ctx.cfg = (ph, pw, scale, group, out_dim, tuple(features.shape))
+        ctx.save_for_backward(rois)
+        if holder is not None:   # the reference Function keeps these on itself (psroi_pool.py:28-31)
+            holder.output, holder.mappingchannel, holder.rois, holder.feature_size = top, mapping, rois, features.size()
+        ctx.mark_non_differentiable(mapping)
+        return top, mapping
+
+    @staticmethod
+    def backward(ctx, grad_top, _grad_mapping):
+        ph, pw, scale, group, out_dim, fsize = ctx.cfg
+        (rois,) = ctx.saved_tensors
+        grad = psroi_backward(grad_top.contiguous(), rois, fsize, ph, pw, scale, group, out_dim)
+        return grad, None, None, None, None, None, None, None
+
+
+def psroi_pool(features, rois, ph, pw, scale, group, out_dim, holder=None):
+    return _PSRoI.apply(features, rois, ph, pw, scale, group, out_dim, holder)[0]
+
+
+# ------------------------------------------------------------------------------- correlation
+def correlation_shape(H, W, pad, k, md, s1, s2):
+    out = (C.c_int * 3)()
+    check(lib().d2t_correlation_shape(H, W, pad, k, md, s1, s2, out), "d2t_correlation_shape")
+    return out[0], out[1], out[2]
+
+
+def correlation_forward(in1, in2, pad, k, md, s1, s2):
+    _req(in1, "input1"), _req(in2, "input2")
+    if in1.shape != in2.shape:
+        raise ValueError("correlation inputs must have the same shape")
+    B, Cc, H, W = in1.shape
+    oc, oh, ow = correlation_shape(H, W, pad, k, md, s1, s2)
+    with torch.cuda.device_of(in1):
+        out = torch.empty(B, oc, oh, ow, device=in1.device)
+        check(lib().d2t_correlation_forward(in1.data_ptr(), in2.data_ptr(), B, Cc, H, W, pad, k, md, s1, s2,
+                                            out.data_ptr(), _stream()), "d2t_correlation_forward")
+        _count(1)
+    return out
+
+
+def correlation_backward(in1, in2, grad_out, pad, k, md, s1, s2, need1=True, need2=True):
+    _req(in1, "input1"), _req(in2, "input2"), _req(grad_out, "grad_output")
+    B, Cc, H, W = in1.shape
+    with torch.cuda.device_of(in1):
+        g1 = torch.empty_like(in1) if need1 else None
+        g2 = torch.empty_like(in2) if need2 else None
+        check(lib().d2t_correlation_backward(in1.data_ptr(), in2.data_ptr(), grad_out.data_ptr(), B, Cc, H, W, pad, k,
+                                             md, s1, s2, g1.data_ptr() if need1 else None,
+                                             g2.data_ptr() if need2 else None, _stream()), "d2t_correlation_backward")
+        _count(int(need1) + int(need2))
+    return g1, g2
+
+
+class _Correlation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in1, in2, pad, k, md, s1, s2):
+        ctx.cfg = (pad, k, md, s1, s2)
+        ctx.save_for_backward(in1, in2)
+        return correlation_forward(in1, in2, pad, k, md, s1, s2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        in1, in2 = ctx.saved_tensors
+        g1, g2 = correlation_backward(in1, in2, grad_out.contiguous(), *ctx.cfg,
+                                      need1=ctx.needs_input_grad[0], need2=ctx.needs_input_grad[1])
+        return g1, g2, None, None, None, None, None
+
+
+def correlation(in1, in2, pad, k, md, s1, s2):
+    return _Correlation.apply(in1, in2, pad, k, md, s1, s2)
+
+
+# ------------------------------------------------------------------------------- NMS
+def nms_batched(dets, thresh, max_keep=0, n_valid=None):
+    """dets [B, N, >=4] fp32, each list sorted by the caller.  Returns (keep [B, stride] int32,
+    num_keep [B] int32), both on the device; no host synchronisation."""
+    _req(dets, "dets")
+    B, N, dim = dets.shape
+    stride = max_keep if max_keep > 0 else max(N, 1)
+    with torch.cuda.device_of(dets):
+        keep = torch.empty(B, stride, dtype=torch.int32, device=dets.device)
+        num = torch.empty(B, dtype=torch.int32, device=dets.device)
+        ws = _ws(lib().d2t_nms_workspace_bytes(B, N), dets.device)
+        check(lib().d2t_nms_batched(dets.data_ptr(), n_valid.data_ptr() if n_valid is not None else None, B, N, dim,
+                                    thresh, max_keep, keep.data_ptr(), stride, num.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _stream()), "d2t_nms_batched")
+        _count(2)
+    return keep, num
+
+
+def nms(dets, thresh):
+    """nms/nms_gpu.py:6-11: int32 [K, 1] kept indices.  K is data dependent, so like the
+    reference (``keep[:num_out[0]]``) this reads one int back from the device."""
+    if dets.shape[0] == 0:
+        return dets.new_zeros((0, 1), dtype=torch.int32)
+    keep, num = nms_batched(dets.unsqueeze(0), float(thresh))
+    return keep[0, : int(num.item())].unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------- RoIAlign / RoIPool / RoICrop
+def roi_align_forward(features, rois, ah, aw, scale):
+    _req(features, "features"), _req(rois, "rois")
+    B, Cc, H, W = features.shape
+    with torch.cuda.device_of(features):
+        top = torch.empty(rois.size(0), Cc, ah, aw, device=features.device)
+        check(lib().ROIAlignForwardLaucher(features.data_ptr(), scale, rois.size(0), H, W, Cc, ah, aw, rois.data_ptr(),
+                                           top.data_ptr(), _stream()), "ROIAlignForwardLaucher")
+        _count(1)
+    return top
+
+
+def roi_align_backward(grad_top, rois, feature_size, ah, aw, scale):
+    _req(grad_top, "grad_output"), _req(rois, "rois")
+    B, Cc, H, W = feature_size
+    with torch.cuda.device_of(grad_top):
+        grad = torch.zeros(B, Cc, H, W, device=grad_top.device)
+        check(lib().ROIAlignBackwardLaucher(grad_top.data_ptr(), scale, B, rois.size(0), H, W, Cc, ah, aw,
+                                            rois.data_ptr(), grad.data_ptr(), _stream()), "ROIAlignBackwardLaucher")
+        _count(1)
+    return grad
+
+
+class _RoIAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ah, aw, scale):
+        ctx.cfg = (ah, aw, scale, tuple(features.shape))
+        ctx.save_for_backward(rois)
+        return roi_align_forward(features, rois, ah, aw, scale)
+
+    @staticmethod
+    def backward(ctx, grad_top):
+        ah, aw, scale, fsize = ctx.cfg
+        (rois,) = ctx.saved_tensors
+        return roi_align_backward(grad_top.contiguous(), rois, fsize, ah, aw, scale), None, None, None, None
+
+
+def roi_align(features, rois, ah, aw, scale):
+    return _RoIAlign.apply(features, rois, ah, aw, scale)
+
+
+def roi_pool_forward(features, rois, ph, pw, scale):
+    _req(features, "features"), _req(rois, "rois")
+    B, Cc, H, W = features.shape
+    with torch.cuda.device_of(features):
+        top = torch.empty(rois.size(0), Cc, ph, pw, device=features.device)
+        argmax = torch.empty(rois.size(0), Cc, ph, pw, dtype=torch.int32, device=features.device)
+        check(lib().ROIPoolForwardLaucher(features.data_ptr(), scale, rois.size(0), H, W, Cc, ph, pw, rois.data_ptr(),
+                                          top.data_ptr(), argmax.data_ptr(), _stream()), "ROIPoolForwardLaucher")
+        _count(1)
+    return top, argmax
+
+
+def roi_pool_backward(grad_top, argmax, rois, feature_size, ph, pw, scale):
+    _req(grad_top, "grad_output")
+    B, Cc, H, W = feature_size
+    with torch.cuda.device_of(grad_top):
+        grad = torch.empty(B, Cc, H, W, device=grad_top.device)
+        check(lib().ROIPoolBackwardLaucher(grad_top.data_ptr(), scale, B, rois.size(0), H, W, Cc, ph, pw,
+                                           rois.data_ptr(), grad.data_ptr(), argmax.data_ptr(), _stream()),
+              "ROIPoolBackwardLaucher")
+        _count(1)
+    return grad
+
+
+class _RoIPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ph, pw, scale, holder):
+        top, argmax = roi_pool_forward(features, rois, ph, pw, scale)
+        ctx.cfg = (ph, pw, scale, tuple(features.shape))
+        ctx.save_for_backward(rois, argmax)
+        if holder is not None:
+            holder.argmax, holder.rois, holder.feature_size = argmax, rois, features.size()
+        return top
+
+    @staticmethod
+    def backward(ctx, grad_top):
+        ph, pw, scale, fsize = ctx.cfg
+        rois, argmax = ctx.saved_tensors
+        return roi_pool_backward(grad_top.contiguous(), argmax, rois, fsize, ph, pw, scale), None, None, None, None, None
+
+
+def roi_pool(features, rois, ph, pw, scale, holder=None):
+    return _RoIPool.apply(features, rois, ph, pw, scale, holder)
+
+
+def roi_crop_forward(images, grid):
+    """images [B,C,H,W]; grid [R,gh,gw,2] in (y, x) order (roi_crop_cuda.c:15-52)."""
+    _req(images, "input1"), _req(grid, "input2")
+    B, Cc, H, W = images.shape
+    R, gh, gw, two = grid.shape
+    if two != 2 or R % B != 0:
+        raise ValueError("grid must be [R, gh, gw, 2] with R a multiple of the image batch")
+    with torch.cuda.device_of(images):
+        out = torch.empty(R, Cc, gh, gw, device=images.device)
+        check(lib().BilinearSamplerBHWD_updateOutput_cuda_kernel(
+            Cc, gw, gh, R, Cc, H, W, B, images.data_ptr(), *images.stride(),
+            grid.data_ptr(), grid.stride(0), grid.stride(3), grid.stride(1), grid.stride(2),
+            out.data_ptr(), *out.stride(), _stream()), "BilinearSamplerBHWD_updateOutput_cuda_kernel")
+        _count(1)
+    return out
+
+
+def roi_crop_backward(images, grid, grad_out):
+    _req(grid, "input2"), _req(grad_out, "grad_output")
+    B, Cc, H, W = images.shape
+    R, gh, gw, _ = grid.shape
+    with torch.cuda.device_of(grad_out):
+        gi = torch.zeros(B, Cc, H, W, device=grad_out.device)
+        gg = torch.zeros_like(grid)   # never written by the reference either (roi_crop_cuda_kernel.cu:111-194)
+        check(lib().BilinearSamplerBHWD_updateGradInput_cuda_kernel(
+            Cc, gw, gh, R, Cc, H, W, B, images.data_ptr(), *images.stride(),
+            grid.data_ptr(), grid.stride(0), grid.stride(3), grid.stride(1), grid.stride(2),
+            gi.data_ptr(), *gi.stride(),
+            gg.data_ptr(), gg.stride(0), gg.stride(3), gg.stride(1), gg.stride(2),
+            grad_out.data_ptr(), *grad_out.stride(), _stream()), "BilinearSamplerBHWD_updateGradInput_cuda_kernel")
+        _count(1)
+    return gi, gg
+
+
+class _RoICrop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, grid):
+        ctx.save_for_backward(images, grid)
+        return roi_crop_forward(images, grid)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        images, grid = ctx.saved_tensors
+        return roi_crop_backward(images, grid, grad_out.contiguous())
+
+
+def roi_crop(images, grid):
+    return _RoICrop.apply(images, grid)
+
+
+# ------------------------------------------------------------------------------- RPN proposal step
+def proposal_decode(anchors, deltas, cls_prob, im_info, feat_stride):
+    """-> boxes [B, H*W*A, 4], fg scores [B, H*W*A] in (y, x, a) order."""
+    _req(anchors, "anchors"), _req(deltas, "bbox_deltas"), _req(cls_prob, "rpn_cls_prob"), _req(im_info, "im_info")
+    B, A4, H, W = deltas.shape
+    A = A4 // 4
+    if cls_prob.shape != (B, 2 * A, H, W) or anchors.shape != (A, 4):
+        raise ValueError("proposal_decode: inconsistent shapes")
+    with torch.cuda.device_of(deltas):
+        boxes = torch.empty(B, H * W * A, 4, device=deltas.device)
+        scores = torch.empty(B, H * W * A, device=deltas.device)
+        check(lib().d2t_proposal_decode(anchors.data_ptr(), A, deltas.data_ptr(), cls_prob.data_ptr(), im_info.data_ptr(),
+                                        B, H, W, feat_stride, boxes.data_ptr(), scores.data_ptr(), _stream()),
+              "d2t_proposal_decode")
+        _count(1)
+    return boxes, scores
+
+
+def proposal_gather(boxes, scores, order, n_take):
+    _req(boxes, "boxes"), _req(scores, "scores"), _req(order, "order", torch.int64)
+    B, n_total, _ = boxes.shape
+    with torch.cuda.device_of(boxes):
+        dets = torch.empty(B, n_take, 5, device=boxes.device)
+        check(lib().d2t_proposal_gather(boxes.data_ptr(), scores.data_ptr(), order.data_ptr(), B, n_total,
+                                        order.size(1), n_take, dets.data_ptr(), _stream()), "d2t_proposal_gather")
+        _count(1)
+    return dets
+
+
+def proposal_write_rois(dets, keep, num_keep, post):
+    B, n_take, _ = dets.shape
+    with torch.cuda.device_of(dets):
+        rois = torch.empty(B, post, 5, device=dets.device)
+        check(lib().d2t_proposal_write_rois(dets.data_ptr(), keep.data_ptr(), keep.size(1), num_keep.data_ptr(), B,
+                                            n_take, post, rois.data_ptr(), _stream()), "d2t_proposal_write_rois")
+        _count(1)
+    return rois
+
+
+def proposals(anchors, deltas, cls_prob, im_info, feat_stride, pre_nms_topN, post_nms_topN, nms_thresh):
+    """rpn/proposal_layer.py:67-159 for the whole batch without a python loop or a host sync:
+    decode+clip kernel -> stable descending sort -> gather top pre_nms -> batched on-device NMS
+    capped at post_nms -> padded rois [B, post, 5]."""
+    boxes, scores = proposal_decode(anchors, deltas, cls_prob, im_info, feat_stride)
+    n_total = scores.size(1)
+    n_take = min(pre_nms_topN, n_total) if pre_nms_topN > 0 else n_total
+    order = torch.sort(scores, dim=1, descending=True, stable=True)[1]
+    dets = proposal_gather(boxes, scores, order, n_take)
+    keep, num = nms_batched(dets, float(nms_thresh), max_keep=post_nms_topN)
+    return proposal_write_rois(dets, keep, num, post_nms_topN)

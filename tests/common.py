@@ -1,0 +1,72 @@
+"""Seeded synthetic inputs shared by the tests, the golden generators and bench.py
+(SURVEY.md section 8d).  numpy only -- no torch, no GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pytorch-detect-to-track_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def make_rois(n_per_img, n_img, height=600, width=1000, seed=21, lo=32.0, hi=512.0, shuffle=False):
+    """centre ~ U(image), w,h log-uniform [lo, hi] px, clipped, fractional coords kept; col 0 = image idx."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for b in range(n_img):
+        cx = rng.uniform(0, width, n_per_img)
+        cy = rng.uniform(0, height, n_per_img)
+        w = np.exp(rng.uniform(np.log(lo), np.log(hi), n_per_img))
+        h = np.exp(rng.uniform(np.log(lo), np.log(hi), n_per_img))
+        x1 = np.clip(cx - w / 2, 0, width - 1)
+        x2 = np.clip(cx + w / 2, 0, width - 1)
+        y1 = np.clip(cy - h / 2, 0, height - 1)
+        y2 = np.clip(cy + h / 2, 0, height - 1)
+        out.append(np.stack([np.full(n_per_img, b, np.float64), x1, y1, x2, y2], 1))
+    rois = np.concatenate(out, 0).astype(np.float32)
+    if shuffle:
+        rois = rois[rng.permutation(len(rois))]
+    return rois
+
+
+def make_dets(n, height=600, width=1000, seed=22):
+    """Boxes from make_rois with scores ~ U(0,1), sorted by descending score (stable)."""
+    rois = make_rois(n, 1, height, width, seed=seed)
+    rng = np.random.RandomState(seed + 1000)
+    scores = rng.uniform(0, 1, n).astype(np.float32)
+    order = np.argsort(-scores, kind="stable")
+    return np.concatenate([rois[order, 1:], scores[order, None]], 1).astype(np.float32)
+
+
+def make_clustered_dets(n, seed=23, height=600, width=1000):
+    """Heavily overlapping boxes (jittered copies of a few seeds) -- long suppression chains."""
+    rng = np.random.RandomState(seed)
+    k = max(1, n // 50)
+    base = make_rois(k, 1, height, width, seed=seed)[:, 1:]
+    idx = rng.randint(0, k, n)
+    boxes = base[idx] + rng.normal(0, 6.0, (n, 4)).astype(np.float32)
+    boxes[:, 2] = np.maximum(boxes[:, 2], boxes[:, 0])
+    boxes[:, 3] = np.maximum(boxes[:, 3], boxes[:, 1])
+    scores = rng.uniform(0, 1, n).astype(np.float32)
+    order = np.argsort(-scores, kind="stable")
+    return np.concatenate([boxes[order], scores[order, None]], 1).astype(np.float32)
+
+
+def randn(shape, seed):
+    return np.random.RandomState(seed).standard_normal(shape).astype(np.float32)
+
+
+def make_rpn_inputs(B, H, W, A=12, seed=30, im_h=None, im_w=None):
+    rng = np.random.RandomState(seed)
+    score = rng.standard_normal((B, 2 * A, H, W)).astype(np.float32)
+    # softmax over {bg, fg} pairs like rpn.py:66-68
+    s = score.reshape(B, 2, A * H, W)
+    e = np.exp(s - s.max(1, keepdims=True))
+    prob = (e / e.sum(1, keepdims=True)).reshape(B, 2 * A, H, W).astype(np.float32)
+    deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.3).astype(np.float32)
+    im_info = np.tile(np.array([[im_h or H * 16, im_w or W * 16, 1.0]], np.float32), (B, 1))
+    return prob, deltas, im_info

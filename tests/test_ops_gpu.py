@@ -1,0 +1,382 @@
+"""GPU parity tests: the sm_100a kernels of libd2t_b200.so (through the reference-shaped operator
+API / the C ABI) against (i) the CPU oracle, (ii) the reference's own CUDA kernels recompiled for
+sm_100a (oracle/_ref/libref_oracle.so) on identical inputs, (iii) the committed golden fixtures.
+Bars: integer outputs (bins, mapping channels, argmax, NMS keep sets) bit-exact; floating point
+within the tolerance written at each assert (north star: 1e-4 relative)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import common
+from d2t_b200 import ops
+from d2t_b200._lib import lib
+from oracle import ref_cuda
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # BASELINE.json north_star: "fp outputs within 1e-4 rel of the reference"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=RTOL, atol=1e-6, msg=""):
+    np.testing.assert_allclose(npy(a) if torch.is_tensor(a) else a, npy(b) if torch.is_tensor(b) else b,
+                               rtol=rtol, atol=atol, err_msg=msg)
+
+
+def have_ref():
+    return ref_cuda.available()
+
+
+# =========================================================================== PSRoI
+def _psroi_module(D):
+    from model.psroi_pooling.modules.psroi_pool import _PSRoIPooling
+    return _PSRoIPooling(7, 7, 1.0 / 16.0, 7, D)
+
+
+def test_psroi_bins_bit_exact_vs_oracle(oracle):
+    rois = np.concatenate([common.make_rois(2000, 2, seed=21), cases.psroi_cases()["r7"]["rois"]], 0)
+    bins = npy(ops.psroi_bins(cu(rois), 7, 7, 1.0 / 16.0, 38, 63))
+    feat = np.zeros((2, 49, 38, 63), np.float32)
+    _, _, want = oracle.psroi_forward(feat, rois, 1.0 / 16.0, 7, 7, 7, 1, want_bins=True)
+    np.testing.assert_array_equal(bins, want)
+    # how often would the as-written (unfused) arithmetic have differed?  
+    _, _, unfused = oracle.psroi_forward(feat, rois, 1.0 / 16.0, 7, 7, 7, 1, contract=0, want_bins=True)
+    print("fused != unfused bins:", int((unfused != want).any(-1).sum()), "of", want.shape[0] * 49)
+
+
+def test_psroi_golden_case_forward_backward(oracle, golden_cuda):
+    c = cases.psroi_cases()["r7"]
+    feat, rois = cu(c["feat"]).requires_grad_(True), cu(c["rois"])
+    from model.psroi_pooling.functions.psroi_pool import PSRoIPoolFunction
+    fn = PSRoIPoolFunction(7, 7, c["scale"], 7, c["D"])
+    top = fn(feat, rois)
+    np.testing.assert_array_equal(npy(top), golden_cuda["psroi_r7_top"])          # bit-exact values
+    np.testing.assert_array_equal(npy(fn.mappingchannel), golden_cuda["psroi_r7_map"])
+    assert fn.rois is rois and tuple(fn.feature_size) == tuple(feat.shape)
+    top.backward(cu(c["gtop"]))
+    close(feat.grad, golden_cuda["psroi_r7_grad"], rtol=1e-5)
+    want = oracle.psroi_backward(c["gtop"], c["rois"], c["feat"].shape, c["scale"], 7, 7, 7, c["D"])
+    close(feat.grad, want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("D,B,R", [(4, 2, 300), (31, 2, 300), (30, 1, 2000)])
+def test_psroi_full_size_vs_reference_kernel(D, B, R):
+    """BASELINE configs 2 and 5 shapes against the reference kernel itself on the same inputs."""
+    if not have_ref():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    torch.manual_seed(20)
+    feat = torch.randn(B, D * 49, 38, 63, device="cuda")
+    rois = cu(common.make_rois(R, B, seed=21, shuffle=(D == 4)))
+    top, mapping = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+    rtop, rmap = ref_cuda.psroi_forward(feat, rois, 1.0 / 16.0, 7, 7, 7, D)
+    assert torch.equal(top, rtop) and torch.equal(mapping, rmap)                     # bit-exact
+    gt = torch.randn_like(top)
+    g = ops.psroi_backward(gt, rois, feat.shape, 7, 7, 1.0 / 16.0, 7, D)
+    rg = ref_cuda.psroi_backward(gt, rmap, rois, feat.shape, 1.0 / 16.0, 7, 7, D)
+    close(g, rg, rtol=1e-4, atol=1e-5)
+
+
+def test_psroi_edge_cases(oracle):
+    feat = torch.randn(2, 196, 9, 11, device="cuda")
+    # empty roi list
+    top, _ = ops.psroi_forward(feat, torch.zeros(0, 5, device="cuda"), 7, 7, 1 / 16., 7, 4)
+    assert top.shape == (0, 4, 7, 7)
+    g = ops.psroi_backward(torch.zeros(0, 4, 7, 7, device="cuda"), torch.zeros(0, 5, device="cuda"), feat.shape, 7, 7,
+                           1 / 16., 7, 4)
+    assert float(g.abs().max()) == 0.0
+    # all rois on image 1, none on image 0; ragged & unsorted image indices
+    rois = common.make_rois(17, 2, height=144, width=176, seed=5, lo=4, hi=200, shuffle=True)
+    rois1 = rois.copy(); rois1[:, 0] = 1
+    for r in (rois, rois1):
+        top, mapping = ops.psroi_forward(feat, cu(r), 7, 7, 1 / 16., 7, 4)
+        want, wmap = oracle.psroi_forward(npy(feat), r, 1 / 16., 7, 7, 7, 4)
+        np.testing.assert_array_equal(npy(top), want)
+        np.testing.assert_array_equal(npy(mapping), wmap)
+    # generic path: pooled 3x3 / group 3, and a plane too large for shared memory
+    feat3 = torch.randn(1, 18, 20, 30, device="cuda")
+    r3 = common.make_rois(33, 1, height=320, width=480, seed=6)
+    top, mapping = ops.psroi_forward(feat3, cu(r3), 3, 3, 1 / 16., 3, 2)
+    want, wmap = oracle.psroi_forward(npy(feat3), r3, 1 / 16., 3, 3, 3, 2)
+    np.testing.assert_array_equal(npy(top), want)
+    np.testing.assert_array_equal(npy(mapping), wmap)
+    g = ops.psroi_backward(cu(common.randn(want.shape, 7)), cu(r3), feat3.shape, 3, 3, 1 / 16., 3, 2)
+    close(g, oracle.psroi_backward(common.randn(want.shape, 7), r3, feat3.shape, 1 / 16., 3, 3, 3, 2), rtol=1e-5)
+    big = torch.randn(1, 49, 100, 160, device="cuda")
+    rb = common.make_rois(50, 1, height=1600, width=2560, seed=8, hi=1500)
+    top, _ = ops.psroi_forward(big, cu(rb), 7, 7, 1 / 16., 7, 1)
+    np.testing.assert_array_equal(npy(top), oracle.psroi_forward(npy(big), rb, 1 / 16., 7, 7, 7, 1)[0])
+
+
+def test_psroi_legacy_launcher_symbols(oracle):
+    """PSROIPoolForwardLauncher / PSROIPoolBackwardLauncher with the reference's argument order
+    (psroi_pooling_kernel.h:8-14: pooled_width BEFORE pooled_height in backward)."""
+    c = cases.psroi_cases()["r7"]
+    feat, rois = cu(c["feat"]), cu(c["rois"])
+    R, D = rois.shape[0], c["D"]
+    top = torch.full((R, D, 7, 7), 7.0, device="cuda")
+    mapping = torch.zeros(R, D, 7, 7, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib().PSROIPoolForwardLauncher(feat.data_ptr(), c["scale"], R, 20, 30, D * 49, 7, 7, rois.data_ptr(), 7, D,
+                                          top.data_ptr(), mapping.data_ptr(), st) == 1
+    want, wmap = oracle.psroi_forward(c["feat"], c["rois"], c["scale"], 7, 7, 7, D)
+    np.testing.assert_array_equal(npy(top), want)
+    np.testing.assert_array_equal(npy(mapping), wmap)
+    grad = torch.zeros_like(feat)
+    gt = cu(c["gtop"])
+    assert lib().PSROIPoolBackwardLauncher(gt.data_ptr(), mapping.data_ptr(), 2, R, c["scale"], D * 49, 20, 30, 7, 7, D,
+                                           grad.data_ptr(), rois.data_ptr(), st) == 1
+    close(grad, oracle.psroi_backward(c["gtop"], c["rois"], c["feat"].shape, c["scale"], 7, 7, 7, D), rtol=1e-5)
+
+
+# =========================================================================== NMS
+def test_nms_golden_keep_sets(golden_cuda):
+    from model.nms.nms_wrapper import nms
+    for name, (dets, thresh) in cases.nms_cases().items():
+        keep = nms(cu(dets), thresh)
+        assert keep.dtype == torch.int32 and keep.dim() == 2 and keep.shape[1] == 1
+        np.testing.assert_array_equal(npy(keep).reshape(-1), golden_cuda["nms_%s" % name], err_msg=name)
+
+
+@pytest.mark.parametrize("n,thresh,clustered", [(2, 0.7, False), (63, 0.5, True), (64, 0.5, True), (65, 0.3, True),
+                                                (129, 0.7, True), (300, 0.3, False), (2000, 0.7, False),
+                                                (6000, 0.7, True), (12000, 0.7, False), (12000, 0.7, True)])
+def test_nms_vs_oracle_and_reference_kernel(oracle, n, thresh, clustered):
+    dets = common.make_clustered_dets(n, seed=100 + n) if clustered else common.make_dets(n, seed=100 + n)
+    keep = npy(ops.nms(cu(dets), thresh)).reshape(-1)
+    np.testing.assert_array_equal(keep, oracle.nms(dets, thresh))
+    if have_ref():
+        np.testing.assert_array_equal(keep, npy(ref_cuda.nms(cu(dets), thresh)).reshape(-1))
+
+
+def test_nms_batched_ragged_and_capped(oracle):
+    B, N = 5, 700
+    dets = np.stack([common.make_clustered_dets(N, seed=200 + b) for b in range(B)])
+    n_valid = np.array([700, 0, 1, 65, 333], np.int32)
+    keep, num = ops.nms_batched(cu(dets), 0.7, max_keep=0, n_valid=cu(n_valid))
+    keep, num = npy(keep), npy(num)
+    for b in range(B):
+        want = oracle.nms(dets[b, : n_valid[b]], 0.7)
+        assert num[b] == len(want)
+        np.testing.assert_array_equal(keep[b, : num[b]], want)
+    keep, num = ops.nms_batched(cu(dets), 0.7, max_keep=40)
+    for b in range(B):
+        want = oracle.nms(dets[b], 0.7)[:40]
+        assert int(num[b]) == len(want)
+        np.testing.assert_array_equal(npy(keep[b, : len(want)]), want)
+
+
+def test_nms_degenerate_boxes(oracle):
+    rng = np.random.RandomState(9)
+    dets = common.make_dets(200, seed=9)
+    dets[10:20, 2] = dets[10:20, 0] - 5          # inverted boxes (negative width)
+    dets[30:40, :4] = dets[30, :4]               # exact duplicates
+    dets[50:60, :4] = 0.0                        # zero boxes
+    dets[60:64, :4] = np.array([5, 5, 4, 4])     # width 0 -> 0/0 IoU = NaN, never suppresses
+    for thresh in (0.0, 0.3, 0.7, 1.0):
+        np.testing.assert_array_equal(npy(ops.nms(cu(dets), thresh)).reshape(-1), oracle.nms(dets, thresh))
+
+
+def test_nms_legacy_symbol(oracle):
+    dets = common.make_dets(500, seed=77)
+    d = cu(dets)
+    keep = torch.zeros(500, dtype=torch.int32, device="cuda")
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    lib().nms_cuda_compute(keep.data_ptr(), num.data_ptr(), d.data_ptr(), 500, 5, 0.7)
+    want = oracle.nms(dets, 0.7)
+    assert int(num.item()) == len(want)
+    np.testing.assert_array_equal(npy(keep)[: len(want)], want)
+
+
+# =========================================================================== correlation
+def test_correlation_golden_cases(oracle, golden_cuda):
+    from model.correlation.modules.correlation import Correlation
+    for name, c in cases.corr_cases().items():
+        p = c["params"]
+        a, b = cu(c["in1"]).requires_grad_(True), cu(c["in2"]).requires_grad_(True)
+        out = Correlation(pad_size=p[0], kernel_size=p[1], max_displacement=p[2], stride1=p[3], stride2=p[4])(a, b)
+        close(out, golden_cuda["corr_%s_out" % name], rtol=RTOL, atol=1e-6, msg=name)
+        go = common.randn(tuple(out.shape), c["gseed"])
+        out.backward(cu(go))
+        t1, t2 = oracle.correlation_backward_true(c["in1"], c["in2"], go, *p)
+        close(a.grad, t1, rtol=RTOL, atol=1e-6, msg=name)
+        close(b.grad, t2, rtol=RTOL, atol=1e-6, msg=name)
+        if p[0] == p[2] and p[3] == 1:   # the reference backward is well defined: must agree with it too
+            close(a.grad, golden_cuda["corr_%s_g1" % name], rtol=RTOL, atol=1e-6, msg=name)
+            close(b.grad, golden_cuda["corr_%s_g2" % name], rtol=RTOL, atol=1e-6, msg=name)
+
+
+@pytest.mark.parametrize("C,H,W,p,B", [(1024, 38, 63, (8, 1, 8, 1, 1), 1), (2048, 38, 63, (8, 1, 8, 1, 1), 2),
+                                       (512, 75, 125, (8, 1, 8, 2, 2), 2), (1024, 38, 63, (8, 1, 8, 1, 1), 8)])
+def test_correlation_full_size_vs_reference_kernel(C, H, W, p, B):
+    """The three D&T correlation shapes (rfcn.py:58-60) against the reference kernel itself."""
+    if not have_ref():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    torch.manual_seed(10)
+    a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    out = ops.correlation_forward(a, b, *p)
+    ref = ref_cuda.correlation_forward(a, b, *p)
+    assert out.shape == ref.shape
+    # |out| ~ 1/sqrt(C); relative to the output scale, as the north star states it
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert err < RTOL, err
+    close(out, ref, rtol=1e-3, atol=2e-6)
+
+
+def test_correlation_backward_full_size_vs_reference_kernel():
+    if not have_ref():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    torch.manual_seed(11)
+    B, C, H, W, p = 1, 256, 38, 63, (8, 1, 8, 1, 1)
+    a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, 289, 38, 63, device="cuda")
+    g1, g2 = ops.correlation_backward(a, b, go, *p)
+    r1, r2 = ref_cuda.correlation_backward(a, b, go, *p)
+    for g, r in ((g1, r1), (g2, r2)):
+        assert float((g - r).abs().max() / r.abs().max()) < RTOL
+    # stride-2 (conv3) case: grad1 is well defined in the reference
+    B, C, H, W, p = 1, 64, 75, 125, (8, 1, 8, 2, 2)
+    a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, 81, 38, 63, device="cuda")
+    g1, g2 = ops.correlation_backward(a, b, go, *p)
+    r1, _ = ref_cuda.correlation_backward(a, b, go, *p, slack=4 * a.numel())
+    assert float((g1 - r1).abs().max() / r1.abs().max()) < RTOL
+    assert float(g2[:, :, 1::2, :].abs().max()) == 0.0 and float(g2[:, :, :, 1::2].abs().max()) == 0.0
+
+
+def test_correlation_adjoint_property():
+    """<corr(a,b), g> is bilinear: d/da <out, g> = grad1 exactly => <out, g> == <a, grad1> == <b, grad2>."""
+    torch.manual_seed(12)
+    for (C, H, W, p) in [(1024, 38, 63, (8, 1, 8, 1, 1)), (512, 75, 125, (8, 1, 8, 2, 2)), (24, 17, 19, (3, 3, 4, 2, 1))]:
+        a, b = torch.randn(2, C, H, W, device="cuda"), torch.randn(2, C, H, W, device="cuda")
+        out = ops.correlation_forward(a, b, *p)
+        g = torch.randn_like(out)
+        g1, g2 = ops.correlation_backward(a, b, g, *p)
+        lhs = float((out.double() * g.double()).sum())
+        assert abs(lhs - float((a.double() * g1.double()).sum())) < 1e-4 * max(1.0, abs(lhs))
+        assert abs(lhs - float((b.double() * g2.double()).sum())) < 1e-4 * max(1.0, abs(lhs))
+
+
+def test_correlation_legacy_launcher_symbol(oracle):
+    c = cases.corr_cases()["d2t_s1"]
+    a, b = cu(c["in1"]), cu(c["in2"])
+    B, Cc, H, W = a.shape
+    out = torch.empty(B, 289, H, W, device="cuda")
+    ok = lib().Correlation_forward_cuda_kernel(out.data_ptr(), B, 289, H, W, *out.stride(), a.data_ptr(), Cc, H, W,
+                                               *a.stride(), b.data_ptr(), Cc, *b.stride(), None, None, 8, 1, 8, 1, 1, 1,
+                                               torch.cuda.current_stream().cuda_stream)
+    assert ok == 1
+    close(out, oracle.correlation_forward(c["in1"], c["in2"], 8, 1, 8, 1, 1), rtol=RTOL, atol=1e-6)
+    # non-contiguous strides are refused with a message instead of silently misreading
+    ok = lib().Correlation_forward_cuda_kernel(out.data_ptr(), B, 289, H, W, *out.stride(), a.data_ptr(), Cc, H, W,
+                                               1, 2, 3, 4, b.data_ptr(), Cc, *b.stride(), None, None, 8, 1, 8, 1, 1, 1,
+                                               torch.cuda.current_stream().cuda_stream)
+    assert ok == 0 and b"contiguous" in lib().d2t_last_error()
+
+
+# =========================================================================== RoIAlign / RoIPool / RoICrop
+def test_roi_align_pool_crop_golden(oracle, golden_cuda):
+    from model.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg
+    from model.roi_pooling.modules.roi_pool import _RoIPooling
+    from model.roi_crop.modules.roi_crop import _RoICrop
+    c = cases.roi_cases()
+    rois, grid, scale = cu(c["rois"]), cu(c["grid"]), c["scale"]
+    for ah in (7, 8):
+        feat = cu(c["feat"]).requires_grad_(True)
+        top = RoIAlign(ah, ah, scale)(feat, rois)
+        close(top, golden_cuda["align%d_top" % ah], rtol=1e-6, atol=1e-7)
+        top.backward(cu(common.randn(tuple(top.shape), 80 + ah)))
+        close(feat.grad, golden_cuda["align%d_grad" % ah], rtol=1e-5, atol=1e-6)
+    avg = RoIAlignAvg(7, 7, scale)(cu(c["feat"]), rois)     # 8x8 samples + 2x2 average (roi_align.py:26-29)
+    close(avg, torch.nn.functional.avg_pool2d(cu(golden_cuda["align8_top"]), 2, 1), rtol=1e-6, atol=1e-7)
+    feat = cu(c["feat"]).requires_grad_(True)
+    from model.roi_pooling.functions.roi_pool import RoIPoolFunction
+    fn = RoIPoolFunction(7, 7, scale)
+    top = fn(feat, rois)
+    np.testing.assert_array_equal(npy(top), golden_cuda["pool_top"])
+    np.testing.assert_array_equal(npy(fn.argmax), golden_cuda["pool_arg"])
+    top.backward(cu(common.randn(tuple(top.shape), 90)))
+    close(feat.grad, golden_cuda["pool_grad"], rtol=1e-5, atol=1e-6)
+    close(_RoIPooling(7, 7, scale)(cu(c["feat"]), rois), golden_cuda["pool_top"], rtol=0, atol=0)
+    feat = cu(c["feat"]).requires_grad_(True)
+    g = grid.clone().requires_grad_(True)
+    out = _RoICrop()(feat, g)
+    close(out, golden_cuda["crop_out"], rtol=1e-5, atol=1e-6)
+    out.backward(cu(common.randn(tuple(out.shape), 91)))
+    close(feat.grad, golden_cuda["crop_gimg"], rtol=1e-5, atol=1e-6)
+    assert float(g.grad.abs().max()) == 0.0
+
+
+def test_roi_crop_is_grid_sample_align_corners():
+    """net_utils.py:198-224 names F.grid_sample (torch 0.3 semantics = align_corners=True, zeros
+    padding) with the grid's last axis swapped as the comparator for RoICrop."""
+    c = cases.roi_cases()
+    feat, grid = cu(c["feat"]), cu(c["grid"])
+    out = ops.roi_crop_forward(feat, grid)
+    per = grid.shape[0] // feat.shape[0]
+    src = feat.repeat_interleave(per, 0)
+    want = torch.nn.functional.grid_sample(src, grid.flip(-1), mode="bilinear", padding_mode="zeros", align_corners=True)
+    close(out, want, rtol=1e-4, atol=1e-5)
+
+
+def test_roi_ops_full_size_vs_reference_kernels():
+    if not have_ref():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    torch.manual_seed(13)
+    feat = torch.randn(2, 512, 38, 63, device="cuda")
+    rois = cu(common.make_rois(300, 2, seed=24))
+    a, r = ops.roi_align_forward(feat, rois, 8, 8, 1 / 16.), ref_cuda.roi_align_forward(feat, rois, 1 / 16., 8, 8)
+    close(a, r, rtol=1e-6, atol=1e-7)
+    gt = torch.randn_like(a)
+    close(ops.roi_align_backward(gt, rois, feat.shape, 8, 8, 1 / 16.),
+          ref_cuda.roi_align_backward(gt, rois, feat.shape, 1 / 16., 8, 8), rtol=1e-4, atol=1e-5)
+    (t, am), (rt, ram) = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16.), ref_cuda.roi_pool_forward(feat, rois, 1 / 16., 7, 7)
+    assert torch.equal(t, rt) and torch.equal(am, ram)
+    gt = torch.randn_like(t)
+    close(ops.roi_pool_backward(gt, am, rois, feat.shape, 7, 7, 1 / 16.),
+          ref_cuda.roi_pool_backward(gt, ram, rois, feat.shape, 1 / 16., 7, 7), rtol=1e-4, atol=1e-5)
+
+
+# =========================================================================== proposal step
+def test_proposal_layer_vs_reference_python_golden(golden_rpn):
+    from model.rpn.proposal_layer import _ProposalLayer
+    from model.utils.config import cfg
+    layer = _ProposalLayer(16, cfg.ANCHOR_SCALES, cfg.ANCHOR_RATIOS).cuda()
+    np.testing.assert_array_equal(npy(layer._anchors), golden_rpn["anchors_d2t"].astype(np.float32))
+    cases_ = {"small": dict(B=2, H=10, W=14, seed=30), "config1": dict(B=1, H=19, W=32, seed=31, im_h=300, im_w=500),
+              "full": dict(B=1, H=38, W=63, seed=32, im_h=600, im_w=1000)}
+    for name, kw in cases_.items():
+        prob, deltas, im_info = common.make_rpn_inputs(**kw)
+        for key in ("TEST", "TRAIN"):
+            rois = layer((cu(prob), cu(deltas), cu(im_info), key))
+            ref = golden_rpn["rois_%s_%s" % (name, key)]
+            assert rois.shape == ref.shape
+            # same proposals in the same order; coordinates differ only by exp() rounding
+            close(rois, ref, rtol=1e-5, atol=1e-3, msg="%s %s" % (name, key))
+
+
+def test_proposal_decode_bit_exact_vs_torch_chain():
+    """The fused decode+clip kernel against the reference's op-by-op torch chain run on the GPU."""
+    from model.rpn.bbox_transform import bbox_transform_inv, clip_boxes
+    from model.rpn.generate_anchors import generate_anchors
+    prob, deltas, im_info = common.make_rpn_inputs(B=2, H=38, W=63, seed=35, im_h=600, im_w=1000)
+    anchors = torch.from_numpy(generate_anchors(scales=np.array([4, 8, 16, 32]))).float().cuda()
+    boxes, scores = ops.proposal_decode(anchors, cu(deltas), cu(prob), cu(im_info), 16)
+    A, H, W = 12, 38, 63
+    sx, sy = torch.meshgrid(torch.arange(W) * 16, torch.arange(H) * 16, indexing="xy")
+    shifts = torch.stack([sx.reshape(-1), sy.reshape(-1), sx.reshape(-1), sy.reshape(-1)], 1).float().cuda()
+    all_anchors = (anchors.view(1, A, 4) + shifts.view(-1, 1, 4)).view(1, -1, 4).expand(2, -1, 4)
+    d = cu(deltas).permute(0, 2, 3, 1).contiguous().view(2, -1, 4)
+    want = clip_boxes(bbox_transform_inv(all_anchors, d, 2), cu(im_info), 2)
+    assert torch.equal(boxes, want)
+    assert torch.equal(scores, cu(prob)[:, A:].permute(0, 2, 3, 1).contiguous().view(2, -1))
