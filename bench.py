@@ -333,8 +333,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-only", action="store_true", help="only the per-op microbench (configs[3], [4]); for ncu")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ops_only:
+        torch.cuda.set_device(0)
+        flush = torch.zeros(128 * 1024 * 1024, device="cuda")
+        print(json.dumps({"ops": op_microbench(flush, peaks()[0])}), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -59,6 +59,7 @@ struct SmemAttrOnce {
         if (done[dev]) return true;
         cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) {
+            (void)cudaGetLastError();   // do not leave it behind for the next launch check
             set_error("%s: %s", what, cudaGetErrorString(e));
             return false;
         }

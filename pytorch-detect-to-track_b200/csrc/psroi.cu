@@ -260,7 +260,7 @@ __global__ void psroi_bins_kernel(const float* __restrict__ rois, int R, float s
     reinterpret_cast<int4*>(bins)[i] = make_int4(hw.x, hw.y, ww.x, ww.y);
 }
 
-constexpr size_t kMaxDynSmem = 227 * 1024;
+constexpr size_t kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
 
 bool planes_path_ok(int C, int H, int W, int PH, int PW, int G, int D, size_t* smem_bytes) {
     if (PH != G || PW != G || G != 7) return false;   // tuned instantiation: the 7x7 R-FCN grid
