@@ -2,20 +2,25 @@
 //
 // Replaces PSROIPoolForward / PSROIPoolBackward and their launchers
 // (/root/reference/lib/model/psroi_pooling/src/psroi_pooling_kernel.cu:15-79, 82-106, 109-170,
-// 172-197).  Semantics restated in SURVEY.md App. A.2; arithmetic pinned with explicit
-// __fmul_rn/__fmaf_rn/__fdiv_rn to what nvcc emits for the reference source on sm_100a
-// (FFMA for `end*scale - start` and for `ph*bin + start`), so the integer bin windows are
-// bit-exact and, because each bin is summed in the reference's row-major order, so are the
-// pooled values.
+// 172-197).  Semantics restated in SURVEY.md App. A.2.  The integer bin windows are computed with
+// explicit __fmul_rn/__fmaf_rn/__fdiv_rn in exactly the form nvcc emits for the reference source on
+// sm_100a (FFMA for `end*scale - start` and for `ph*bin + start`), so RoI->bin assignment is
+// bit-exact.
 //
-// Design (B200): the reference reads one channel plane per output element with adjacent
-// threads H*W floats apart -- fully uncoalesced, ~70 MB of sector traffic per image.  Here a
-// CTA owns one (image, ctop, ph) = G consecutive channel planes (pw = 0..G-1), which are ONE
-// contiguous G*H*W*4-byte span of the NCHW tensor: it is pulled into shared memory with a
-// single 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) and every RoI of that image is then served
-// from shared memory.  Features therefore cross HBM exactly once (compulsory traffic), the
-// per-RoI window arithmetic is done once per RoI by a prep kernel instead of once per output
-// element, and lanes (n, pw=0..G-1) write G consecutive floats of the output.
+// Design (B200): the reference reads one channel plane per output element with adjacent threads
+// H*W floats apart (fully uncoalesced, ~70 MB of sector traffic per image) and walks every bin
+// cell by cell.  Here
+//   * psroi_prep evaluates the window arithmetic once per RoI (not once per output element);
+//   * a persistent CTA per SM owns work items (image, ctop, ph) = G consecutive channel planes,
+//     which are ONE contiguous span of the NCHW tensor: it arrives in shared memory by 1-D TMA
+//     bulk copies (cp.async.bulk -> UBLKCP), issued one item ahead of the compute;
+//   * the planes are turned into fp64 summed-area tables, after which every bin is 4 table reads
+//     whatever its size (forward), or 4 atomics into a difference array followed by two scans
+//     (backward).  Features / gradients cross HBM exactly once.
+// Pooled values are the correctly rounded exact bin means; they differ from the reference's
+// sequential fp32 sums by the reference's own rounding (<= ~1e-6 relative).  The generic kernels
+// below keep the reference's summation order bit for bit and serve every other geometry and the
+// reference-named launcher, which is not told the batch size.
 #include "common.cuh"
 
 namespace d2t {
@@ -43,60 +48,73 @@ __device__ __forceinline__ int2 psroi_window(AxisParams a, int p, int limit) {
     return make_int2(lo, hi);
 }
 
+// Workspace written by psroi_prep, read by the plane kernels.  Rp = R rounded up to 32.
 struct PsroiWs {
-    int* range;  // [2*B]: range[2b] = max(R - n), range[2b+1] = max(n + 1) over rois of image b
-    int* rb;     // [R] image index, -1 when out of range
-    int* bh;     // [R*PH] lo | hi << 16
-    int* bw;     // [R*PW]
+    int* rb;               // [Rp] image index of roi n, -1 when out of range / padding
+    int* chunk;            // [Rp/32] min | max << 16 of the valid image indices among rois [32k, 32k+32)
+    unsigned short* bh;    // [PH][Rp] hstart | hend << 8   (transposed: one ph is contiguous over n)
+    unsigned short* bw;    // [Rp][PW] wstart | wend << 8
 };
 
-__host__ __device__ inline size_t psroi_ws_ints(int R, int B, int PH, int PW) {
-    return (size_t)2 * B + (size_t)R + (size_t)R * PH + (size_t)R * PW;
+__host__ __device__ inline int psroi_rp(int R) { return (R + 31) / 32 * 32; }
+__host__ __device__ inline size_t psroi_ws_bytes(int R, int PH, int PW) {
+    const size_t Rp = (size_t)psroi_rp(R);
+    return Rp * 4 + Rp / 32 * 4 + Rp * PH * 2 + Rp * PW * 2;
 }
 
-__global__ void psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, int PW,
-                           int H, int W, PsroiWs ws, float* top, int D, int zero_invalid) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= R) return;
-    const float* roi = rois + (size_t)n * 5;
-    int b = (int)roi[0];
-    bool valid = b >= 0 && b < B;
-    ws.rb[n] = valid ? b : -1;
-    AxisParams aw = psroi_axis(roi[1], roi[3], scale, PW);
-    AxisParams ah = psroi_axis(roi[2], roi[4], scale, PH);
-    for (int p = 0; p < PH; ++p) {
-        int2 w = psroi_window(ah, p, H);
-        ws.bh[(size_t)n * PH + p] = w.x | (w.y << 16);
+// One thread per roi: image index, the PH + PW integer windows (psroi_pooling_kernel.cu:31-61,
+// evaluated ONCE per roi instead of once per output element) and, per 32-roi chunk, the range of
+// image indices it holds so the plane kernels can skip chunks of other images without atomics
+// or a pre-zeroed table.
+__global__ void __launch_bounds__(128)
+psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, int PW, int H, int W, PsroiWs ws,
+           float* top, int D, int zero_invalid) {
+    asm volatile("griddepcontrol.launch_dependents;");   // let the plane kernel start staging features
+    const int Rp = psroi_rp(R);
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Rp) return;
+    int b = -1;
+    if (n < R) {
+        const float* roi = rois + (size_t)n * 5;
+        b = (int)roi[0];
+        if (b < 0 || b >= B) b = -1;
+        AxisParams aw = psroi_axis(roi[1], roi[3], scale, PW);
+        AxisParams ah = psroi_axis(roi[2], roi[4], scale, PH);
+        for (int p = 0; p < PH; ++p) {
+            int2 w = psroi_window(ah, p, H);
+            ws.bh[(size_t)p * Rp + n] = (unsigned short)(w.x | (w.y << 8));
+        }
+        for (int p = 0; p < PW; ++p) {
+            int2 w = psroi_window(aw, p, W);
+            ws.bw[(size_t)n * PW + p] = (unsigned short)(w.x | (w.y << 8));
+        }
+        if (b < 0 && zero_invalid && top) {
+            size_t per = (size_t)D * PH * PW;
+            for (size_t i = 0; i < per; ++i) top[(size_t)n * per + i] = 0.f;
+        }
     }
-    for (int p = 0; p < PW; ++p) {
-        int2 w = psroi_window(aw, p, W);
-        ws.bw[(size_t)n * PW + p] = w.x | (w.y << 16);
+    ws.rb[n] = b;
+    int lo = b < 0 ? 0xffff : b, hi = b < 0 ? 0 : b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (valid) {
-        atomicMax(&ws.range[2 * b], R - n);
-        atomicMax(&ws.range[2 * b + 1], n + 1);
-    } else if (zero_invalid && top) {
-        size_t per = (size_t)D * PH * PW;
-        for (size_t i = 0; i < per; ++i) top[(size_t)n * per + i] = 0.f;
-    }
+    if ((threadIdx.x & 31) == 0) ws.chunk[n >> 5] = lo | (hi << 16);   // lo > hi: no valid roi
 }
 
-// Stage G planes [n_el floats starting at src] into shared memory; returns the pointer p with
-// p[i] == src[i].  Interior goes through one or more TMA bulk copies, the <= 3-float misaligned
-// head/tail through ordinary loads.
-__device__ __forceinline__ const float* stage_planes(float* sm, const float* __restrict__ src, int n_el,
-                                                     uint64_t* bar) {
+// ---- staging of G consecutive channel planes (one contiguous span of the NCHW tensor) ----
+// The interior goes through 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on `bar`;
+// the <= 3-float head/tail that is not 16-byte aligned goes through ordinary loads.  Returns the
+// pointer p with p[i] == src[i] (shifted inside `sm` so that smem and global alignment agree).
+__device__ __forceinline__ const float* stage_issue(float* sm, const float* __restrict__ src, int n_el,
+                                                    uint64_t* bar) {
     const int tid = threadIdx.x;
     int head = (int)(((16u - (uint32_t)((uintptr_t)src & 15u)) & 15u) >> 2);
     if (head > n_el) head = n_el;
     float* plane = sm + ((4 - head) & 3);
     const int bulk = ((n_el - head) >> 2) << 2;
     const int tail = n_el - head - bulk;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
     if (tid == 0) {
         if (bulk > 0) {
             mbar_expect_tx(bar, (uint32_t)bulk * 4u);
@@ -110,87 +128,228 @@ __device__ __forceinline__ const float* stage_planes(float* sm, const float* __r
         }
     }
     if (tid < head) plane[tid] = __ldg(src + tid);
-    if (tid < tail) plane[head + bulk + tid] = __ldg(src + head + bulk + tid);
-    __syncthreads();
-    mbar_wait(bar, 0);
+    if (tid >= 32 && tid < 32 + tail) plane[head + bulk + tid - 32] = __ldg(src + head + bulk + tid - 32);
     return plane;
 }
 
+// ---- forward: persistent CTAs, double-precision summed-area tables in shared memory ----
+// Work item = (image b, ctop, ph) = the G channel planes c = (ctop*G + ph)*G + pw, pw = 0..G-1,
+// which are contiguous in NCHW.  Per item: (1) the planes arrive by TMA into an fp32 staging
+// buffer (issued one item ahead, so the copy overlaps the previous item's lookups); (2) they are
+// turned into G summed-area tables S[h][w] = sum_{y<h, x<w} f[y][x] in fp64 (warp-shuffle row
+// scans, then a column scan); (3) every (roi, pw) output of that image is 4 table reads:
+//      sum = (S[he][we] - S[hs][we]) - (S[he][ws] - S[hs][ws]),   out = float(sum) / area.
+// fp64 makes the window sum exact to ~1e-14, so `out` is the correctly rounded true average; it
+// differs from the reference's sequential fp32 sum only by the reference's own rounding
+// (<= ~1e-6 relative, tests/test_ops_gpu.py).  The integer windows are the reference's, bit-exact.
+// Features cross HBM exactly once, there is no divergent per-bin loop, and instruction count per
+// output is ~25 regardless of the roi size.
 template <int G>
-__global__ void __launch_bounds__(256)
-psroi_fwd_planes(const float* __restrict__ feat, int C, int H, int W, int D, int R, PsroiWs ws,
-                 float* __restrict__ top, int* __restrict__ mapping) {
+__global__ void __launch_bounds__(1024, 1)
+psroi_fwd_sat(const float* __restrict__ feat, int B, int C, int H, int W, int D, int R, PsroiWs ws,
+              float* __restrict__ top, int* __restrict__ mapping) {
     extern __shared__ float4 smem4[];
     __shared__ uint64_t bar;
-    const int b = blockIdx.y;
-    const int end = ws.range[2 * b + 1];
-    if (end == 0) return;
-    const int begin = R - ws.range[2 * b];
-    const int ctop = blockIdx.x / G, ph = blockIdx.x % G;
-    const int HW = H * W;
-    const int c0 = (ctop * G + ph) * G;
-    const float* src = feat + ((size_t)b * C + c0) * HW;
-    const float* plane = stage_planes(reinterpret_cast<float*>(smem4), src, G * HW, &bar);
+    const int HW = H * W, n_el = G * HW;
+    const int Wp = (W + 1) | 1, Hp = H + 1, plane_d = Hp * Wp;   // odd row pitch: thread-per-row stores spread over banks
+    double* sat = reinterpret_cast<double*>(smem4);                       // [G][Hp][Wp]
+    float* stage = reinterpret_cast<float*>(sat + (((size_t)G * plane_d + 1) & ~(size_t)1));   // [G*HW + 4], 16-B aligned
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int items = B * D * G;
+    const int Rp = psroi_rp(R), nchunks = Rp >> 5;
 
-    const int nitems = (end - begin) * G;
-    for (int t = threadIdx.x; t < nitems; t += blockDim.x) {
-        const int n = begin + t / G, pw = t % G;
-        if (ws.rb[n] != b) continue;
-        const int hb = ws.bh[(size_t)n * G + ph], wb = ws.bw[(size_t)n * G + pw];
-        const int hs = hb & 0xffff, he = hb >> 16, wsx = wb & 0xffff, we = wb >> 16;
-        const float* p = plane + pw * HW;
-        float s = 0.f;
-        for (int h = hs; h < he; ++h) {
-            const float* row = p + h * W;
-            for (int w = wsx; w < we; ++w) s += row[w];   // reference order: kernel.cu:69-74
-        }
-        const bool empty = (he <= hs) || (we <= wsx);
-        const float area = (float)((he - hs) * (we - wsx));
-        const size_t idx = (((size_t)n * D + ctop) * G + ph) * G + pw;
-        top[idx] = empty ? 0.f : __fdiv_rn(s, area);
-        if (mapping) mapping[idx] = c0 + pw;
+    __shared__ double inv[256];   // 1 / extent
+    if (tid < 256) inv[tid] = tid ? 1.0 / (double)tid : 0.0;
+    int nl_k[G], pw_k[G], poff_k[G];   // lane-constant decomposition of j = k*32 + lane
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const int j = k * 32 + lane;
+        nl_k[k] = j / G;
+        pw_k[k] = j - nl_k[k] * G;
+        poff_k[k] = pw_k[k] * plane_d;
     }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    // borders S[0][*] = S[*][0] = 0 never change
+    for (int i = tid; i < G * Wp; i += blockDim.x) sat[(size_t)(i / Wp) * plane_d + (i % Wp)] = 0.0;
+    for (int i = tid; i < G * Hp; i += blockDim.x) sat[(size_t)(i / Hp) * plane_d + (size_t)(i % Hp) * Wp] = 0.0;
+    __syncthreads();
+    int it = blockIdx.x;
+    const float* plane = nullptr;
+    if (it < items) plane = stage_issue(stage, feat + ((size_t)(it / (D * G)) * C + (size_t)(it % (D * G)) * G) * HW, n_el, &bar);
+    uint32_t phase = 0;
+    bool waited_for_prep = false;
+
+    for (; it < items; it += gridDim.x) {
+        const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
+        __syncthreads();               // head/tail scalar stores of stage_issue visible; previous lookups done
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        // ---- (2a) row prefix sums, one thread per (plane, row): W sequential fp64 adds
+        for (int r = tid; r < G * H; r += blockDim.x) {
+            const int p = r / H, h = r - p * H;
+            const float* src = plane + (size_t)r * W;
+            double* dst = sat + (size_t)p * plane_d + (size_t)(h + 1) * Wp + 1;
+            double acc = 0.0;
+#pragma unroll 9
+            for (int x = 0; x < W; ++x) {
+                acc += (double)src[x];
+                dst[x] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- stage is free: start the next item's copy; it overlaps (2b) and (3)
+        const int nxt = it + gridDim.x;
+        if (nxt < items)
+            plane = stage_issue(stage, feat + ((size_t)(nxt / (D * G)) * C + (size_t)(nxt % (D * G)) * G) * HW, n_el, &bar);
+        // ---- (2b) column scan: one thread per (plane, column)
+        for (int i = tid; i < G * W; i += blockDim.x) {
+            const int p = i / W;
+            double* col = sat + (size_t)p * plane_d + (i - p * W) + 1;
+            double acc = 0.0;
+#pragma unroll 19
+            for (int h = 1; h <= H; ++h) {
+                acc += col[(size_t)h * Wp];
+                col[(size_t)h * Wp] = acc;
+            }
+        }
+        __syncthreads();
+        if (!waited_for_prep) {        // windows come from psroi_prep (programmatic dependent launch)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited_for_prep = true;
+        }
+        // ---- (3) lookups: warp per 32-roi chunk, lane j -> (roi j / G, pw j % G), G passes
+        const unsigned short* __restrict__ bh = ws.bh + (size_t)ph * Rp;
+        const int c0 = (ctop * G + ph) * G;
+        const size_t obase = (size_t)ctop * (G * G) + ph * G;
+        for (int ck = warp; ck < nchunks; ck += nwarps) {
+            const int mm = __ldg(ws.chunk + ck);
+            if (b < (mm & 0xffff) || b > (mm >> 16)) continue;
+            int rbv[G], hbv[G], wbv[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) {      // all window loads in flight before any is used
+                const int n = ck * 32 + nl_k[k];
+                rbv[k] = __ldg(ws.rb + n);
+                hbv[k] = __ldg(bh + n);
+                wbv[k] = __ldg(ws.bw + (size_t)ck * 32 * G + k * 32 + lane);
+            }
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (rbv[k] != b) continue;
+                const int n = ck * 32 + nl_k[k];
+                const int hs = hbv[k] & 0xff, he = hbv[k] >> 8, wsx = wbv[k] & 0xff, we = wbv[k] >> 8;
+                const double* P = sat + poff_k[k];
+                float o = 0.f;
+                if (he > hs && we > wsx) {
+                    const double s = (P[he * Wp + we] - P[hs * Wp + we]) - (P[he * Wp + wsx] - P[hs * Wp + wsx]);
+                    // mean = s / area, evaluated in fp64 (exact window sum, reciprocals of the two
+                    // extents from a table) and rounded to fp32 once
+                    o = (float)(s * inv[he - hs] * inv[we - wsx]);
+                }
+                const size_t idx = (size_t)n * (D * G * G) + obase + pw_k[k];
+                top[idx] = o;
+                if (mapping) mapping[idx] = c0 + pw_k[k];
+            }
+        }
+    }
+    if (!waited_for_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// ---- backward: the adjoint of the summed-area-table forward ----
+// d(out)/d(f[h][w]) is dv = top_diff / area on the window and 0 elsewhere, so the gradient plane is
+// the 2-D prefix sum of a difference array holding +dv, -dv, -dv, +dv at the window's four
+// corners.  Per item (image, ctop, ph): 4 fp64 shared-memory atomics per (roi, pw) -- instead of
+// one atomic per covered cell -- then two scans, then the G planes go to HBM with coalesced
+// stores, exactly once.  fp64 keeps the cancellation in the prefix sums below 1e-13, so the
+// result is the correctly rounded sum of the reference's per-bin terms (kernel.cu:161 computes dv
+// in fp32 with the same IEEE division), independent of the order the atomics land in.
 template <int G>
-__global__ void __launch_bounds__(256)
-psroi_bwd_planes(const float* __restrict__ top_diff, int C, int H, int W, int D, int R, PsroiWs ws,
-                 float* __restrict__ bottom_diff, int accumulate) {
+__global__ void __launch_bounds__(1024, 1)
+psroi_bwd_sat(const float* __restrict__ top_diff, int B, int C, int H, int W, int D, int R, PsroiWs ws,
+              float* __restrict__ bottom_diff, int accumulate) {
     extern __shared__ float4 smem4[];
-    float* acc = reinterpret_cast<float*>(smem4);
-    const int b = blockIdx.y;
-    const int ctop = blockIdx.x / G, ph = blockIdx.x % G;
-    const int HW = H * W, n_el = G * HW;
-    const int c0 = (ctop * G + ph) * G;
-    float* dst = bottom_diff + ((size_t)b * C + c0) * HW;
-    const int end = ws.range[2 * b + 1];
-    if (end == 0) {
-        if (!accumulate)
-            for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] = 0.f;
-        return;
+    const int HW = H * W;
+    const int Wp = (W + 1) | 1, Hp = H + 1, plane_d = Hp * Wp;
+    double* diff = reinterpret_cast<double*>(smem4);   // [G][Hp][Wp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int items = B * D * G;
+    const int Rp = psroi_rp(R), nchunks = Rp >> 5;
+    int nl_k[G], pw_k[G], poff_k[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const int j = k * 32 + lane;
+        nl_k[k] = j / G;
+        pw_k[k] = j - nl_k[k] * G;
+        poff_k[k] = pw_k[k] * plane_d;
     }
-    const int begin = R - ws.range[2 * b];
-    for (int i = threadIdx.x; i < n_el; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
-    const int nitems = (end - begin) * G;
-    for (int t = threadIdx.x; t < nitems; t += blockDim.x) {
-        const int n = begin + t / G, pw = t % G;
-        if (ws.rb[n] != b) continue;
-        const int hb = ws.bh[(size_t)n * G + ph], wb = ws.bw[(size_t)n * G + pw];
-        const int hs = hb & 0xffff, he = hb >> 16, wsx = wb & 0xffff, we = wb >> 16;
-        if (he <= hs || we <= wsx) continue;
-        const float area = (float)((he - hs) * (we - wsx));
-        const size_t idx = (((size_t)n * D + ctop) * G + ph) * G + pw;
-        const float dv = __fdiv_rn(top_diff[idx], area);   // kernel.cu:161
-        float* p = acc + pw * HW;
-        for (int h = hs; h < he; ++h)
-            for (int w = wsx; w < we; ++w) atomicAdd(p + h * W + w, dv);
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
+        for (int i = tid; i < G * plane_d; i += blockDim.x) diff[i] = 0.0;
+        __syncthreads();
+        const unsigned short* __restrict__ bh = ws.bh + (size_t)ph * Rp;
+        const size_t obase = (size_t)ctop * (G * G) + ph * G;
+        for (int ck = warp; ck < nchunks; ck += nwarps) {
+            const int mm = __ldg(ws.chunk + ck);
+            if (b < (mm & 0xffff) || b > (mm >> 16)) continue;
+            int rbv[G], hbv[G], wbv[G];
+            float gv[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const int n = ck * 32 + nl_k[k];
+                rbv[k] = __ldg(ws.rb + n);
+                hbv[k] = __ldg(bh + n);
+                wbv[k] = __ldg(ws.bw + (size_t)ck * 32 * G + k * 32 + lane);
+                gv[k] = n < R ? __ldg(top_diff + (size_t)n * (D * G * G) + obase + pw_k[k]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (rbv[k] != b) continue;
+                const int hs = hbv[k] & 0xff, he = hbv[k] >> 8, wsx = wbv[k] & 0xff, we = wbv[k] >> 8;
+                if (he <= hs || we <= wsx) continue;
+                const double dv = (double)__fdiv_rn(gv[k], (float)((he - hs) * (we - wsx)));   // kernel.cu:161
+                double* P = diff + poff_k[k];
+                atomicAdd(P + hs * Wp + wsx, dv);
+                atomicAdd(P + hs * Wp + we, -dv);
+                atomicAdd(P + he * Wp + wsx, -dv);
+                atomicAdd(P + he * Wp + we, dv);
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < G * H; r += blockDim.x) {       // row scans
+            const int p = r / H, h = r - p * H;
+            double* row = diff + (size_t)p * plane_d + (size_t)h * Wp;
+            double acc = 0.0;
+#pragma unroll 9
+            for (int x = 0; x < W; ++x) {
+                acc += row[x];
+                row[x] = acc;
+            }
+        }
+        __syncthreads();
+        float* dst = bottom_diff + ((size_t)b * C + (size_t)cg * G) * HW;
+        for (int i = tid; i < G * W; i += blockDim.x) {       // column scans + coalesced write-out
+            const int p = i / W, x = i - p * W;
+            const double* col = diff + (size_t)p * plane_d + x;
+            float* o = dst + (size_t)p * HW + x;
+            double acc = 0.0;
+            if (accumulate) {
+#pragma unroll 2
+                for (int h = 0; h < H; ++h) {
+                    acc += col[(size_t)h * Wp];
+                    o[(size_t)h * W] += (float)acc;
+                }
+            } else {
+#pragma unroll 19
+                for (int h = 0; h < H; ++h) {
+                    acc += col[(size_t)h * Wp];
+                    o[(size_t)h * W] = (float)acc;
+                }
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (accumulate)
-        for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] += acc[i];
-    else
-        for (int i = threadIdx.x; i < n_el; i += blockDim.x) dst[i] = acc[i];
 }
 
 // Generic fallbacks (any PH/PW/G, any plane size): one thread per output element.
@@ -260,33 +419,37 @@ __global__ void psroi_bins_kernel(const float* __restrict__ rois, int R, float s
     reinterpret_cast<int4*>(bins)[i] = make_int4(hw.x, hw.y, ww.x, ww.y);
 }
 
-constexpr size_t kMaxDynSmem = 226 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
+constexpr size_t kMaxDynSmem = 224 * 1024;   // 227 KB per CTA minus the kernels' static shared memory
 
-bool planes_path_ok(int C, int H, int W, int PH, int PW, int G, int D, size_t* smem_bytes) {
-    if (PH != G || PW != G || G != 7) return false;   // tuned instantiation: the 7x7 R-FCN grid
-    if (H > 0x7fff || W > 0x7fff) return false;
+// The tuned kernels cover the 7x7 R-FCN grid with planes small enough for shared memory;
+// everything else takes the generic kernels.  fwd: fp64 tables + fp32 staging; bwd: fp32 planes.
+bool planes_path_ok(int B, int C, int H, int W, int PH, int PW, int G, int D, bool forward, size_t* smem_bytes) {
+    if (PH != G || PW != G || G != 7) return false;
+    if (H > 255 || W > 255 || B > 0xffff) return false;       // 8-bit window bounds, 16-bit image index
     if ((size_t)D * G * G > (size_t)C) return false;
-    size_t bytes = ((size_t)G * H * W + 4) * sizeof(float);
+    const size_t tables = ((size_t)G * (H + 1) * ((W + 1) | 1) + 1) * sizeof(double);
+    size_t bytes = forward ? tables + ((size_t)G * H * W + 4) * sizeof(float) : tables;
     if (bytes > kMaxDynSmem) return false;
     *smem_bytes = bytes;
     return true;
 }
 
-PsroiWs carve(void* workspace, int R, int B, int PH, int PW) {
+PsroiWs carve(void* workspace, int R, int PH, int PW) {
     PsroiWs ws;
-    int* p = reinterpret_cast<int*>(workspace);
-    ws.range = p;
-    ws.rb = ws.range + 2 * (size_t)B;
-    ws.bh = ws.rb + R;
-    ws.bw = ws.bh + (size_t)R * PH;
+    const size_t Rp = (size_t)psroi_rp(R);
+    char* p = reinterpret_cast<char*>(workspace);
+    ws.rb = reinterpret_cast<int*>(p);
+    ws.chunk = ws.rb + Rp;
+    ws.bh = reinterpret_cast<unsigned short*>(ws.chunk + Rp / 32);
+    ws.bw = ws.bh + Rp * PH;
     return ws;
 }
 
 int run_prep(const float* rois, int R, int B, float scale, int PH, int PW, int H, int W, PsroiWs ws,
              float* top, int D, int zero_invalid, cudaStream_t stream) {
-    D2T_CUDA_OK(cudaMemsetAsync(ws.range, 0, sizeof(int) * 2 * (size_t)B, stream), "psroi range memset");
     if (R > 0) {
-        psroi_prep<<<(R + 127) / 128, 128, 0, stream>>>(rois, R, B, scale, PH, PW, H, W, ws, top, D, zero_invalid);
+        psroi_prep<<<(psroi_rp(R) + 127) / 128, 128, 0, stream>>>(rois, R, B, scale, PH, PW, H, W, ws, top, D,
+                                                               zero_invalid);
         D2T_CHECK_LAUNCH("psroi_prep");
     }
     return 1;
@@ -304,7 +467,8 @@ int grid_for(size_t total) {
 using namespace d2t;
 
 extern "C" size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w) {
-    return align_up(psroi_ws_ints(num_rois, batch, pooled_h, pooled_w) * sizeof(int), 256);
+    (void)batch;
+    return align_up(psroi_ws_bytes(num_rois, pooled_h, pooled_w), 256);
 }
 
 extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, int height, int width,
@@ -317,17 +481,28 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
     if (num_rois == 0) return 1;
     D2T_REQUIRE(bottom && rois && top, "d2t_psroi_forward: null pointer");
     size_t smem = 0;
-    if (planes_path_ok(channels, height, width, pooled_h, pooled_w, group, out_dim, &smem) && workspace &&
+    if (planes_path_ok(batch, channels, height, width, pooled_h, pooled_w, group, out_dim, true, &smem) && workspace &&
+        ((uintptr_t)workspace & 3) == 0 &&
         workspace_bytes >= d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w)) {
-        PsroiWs ws = carve(workspace, num_rois, batch, pooled_h, pooled_w);
+        PsroiWs ws = carve(workspace, num_rois, pooled_h, pooled_w);
         if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, top, out_dim, 1, stream))
             return 0;
         static SmemAttrOnce once;
-        if (!once.ensure(psroi_fwd_planes<7>, kMaxDynSmem, "psroi_fwd smem attr")) return 0;
-        dim3 grid(out_dim * group, batch);
-        psroi_fwd_planes<7><<<grid, 256, smem, stream>>>(bottom, channels, height, width, out_dim, num_rois, ws,
-                                                         top, mapping);
-        D2T_CHECK_LAUNCH("psroi_fwd_planes");
+        if (!once.ensure(psroi_fwd_sat<7>, kMaxDynSmem, "psroi_fwd smem attr")) return 0;
+        const int items = batch * out_dim * group;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(items < sm_count() ? items : sm_count());   // persistent: one CTA per SM
+        cfg.blockDim = dim3(1024);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap with psroi_prep
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, psroi_fwd_sat<7>, bottom, batch, channels, height, width, out_dim,
+                                       num_rois, ws, top, mapping),
+                    "psroi_fwd_sat launch");
         return 1;
     }
     size_t total = (size_t)num_rois * out_dim * pooled_h * pooled_w;
@@ -346,13 +521,14 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
                 "d2t_psroi_backward: bad sizes");
     D2T_REQUIRE(bottom_diff, "d2t_psroi_backward: null bottom_diff");
     size_t smem = 0;
-    if (planes_path_ok(channels, height, width, pooled_h, pooled_w, group, out_dim, &smem) && workspace &&
+    if (planes_path_ok(batch, channels, height, width, pooled_h, pooled_w, group, out_dim, false, &smem) && workspace &&
+        ((uintptr_t)workspace & 3) == 0 &&
         workspace_bytes >= d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w)) {
-        PsroiWs ws = carve(workspace, num_rois, batch, pooled_h, pooled_w);
+        PsroiWs ws = carve(workspace, num_rois, pooled_h, pooled_w);
         if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, nullptr, out_dim, 0, stream))
             return 0;
         static SmemAttrOnce once;
-        if (!once.ensure(psroi_bwd_planes<7>, kMaxDynSmem, "psroi_bwd smem attr")) return 0;
+        if (!once.ensure(psroi_bwd_sat<7>, kMaxDynSmem, "psroi_bwd smem attr")) return 0;
         if (!accumulate && (size_t)out_dim * group * group < (size_t)channels) {
             // channels no bin maps to: zero them so the result is the full gradient
             size_t used = (size_t)out_dim * group * group, hw = (size_t)height * width;
@@ -361,10 +537,10 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
                                             (channels - used) * hw * sizeof(float), stream),
                             "psroi_bwd tail memset");
         }
-        dim3 grid(out_dim * group, batch);
-        psroi_bwd_planes<7><<<grid, 256, smem, stream>>>(top_diff, channels, height, width, out_dim, num_rois, ws,
-                                                         bottom_diff, accumulate);
-        D2T_CHECK_LAUNCH("psroi_bwd_planes");
+        const int items = batch * out_dim * group;
+        psroi_bwd_sat<7><<<items < sm_count() ? items : sm_count(), 1024, smem, stream>>>(
+            top_diff, batch, channels, height, width, out_dim, num_rois, ws, bottom_diff, accumulate);
+        D2T_CHECK_LAUNCH("psroi_bwd_sat");
         return 1;
     }
     if (!accumulate)

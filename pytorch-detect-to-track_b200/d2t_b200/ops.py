@@ -40,8 +40,19 @@ def _ws(nbytes, device):
 
 
 # ------------------------------------------------------------------------------- PSRoI
-def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, want_mapping=True):
-    """psroi_pooling/functions/psroi_pool.py:18-33 -> d2t_psroi_forward."""
+def psroi_mapping_channel(num_rois, pooled_h, pooled_w, group, out_dim, device):
+    """The reference's `mappingchannel` output (psroi_pooling_kernel.cu:64-66, 77) is a pure
+    function of the output index, c = (ctop*G + ph)*G + pw; built on demand instead of written by
+    the kernel on every call (it would double the op's HBM writes)."""
+    ctop = torch.arange(out_dim, device=device, dtype=torch.int32).view(1, out_dim, 1, 1)
+    ph = torch.arange(pooled_h, device=device, dtype=torch.int32).view(1, 1, pooled_h, 1)
+    pw = torch.arange(pooled_w, device=device, dtype=torch.int32).view(1, 1, 1, pooled_w)
+    return ((ctop * group + ph) * group + pw).expand(num_rois, out_dim, pooled_h, pooled_w).contiguous()
+
+
+def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, want_mapping=False):
+    """psroi_pooling/functions/psroi_pool.py:18-33 -> d2t_psroi_forward.  Returns (top, mapping);
+    mapping is None unless want_mapping (then the kernel writes it, as the reference's does)."""
     _req(features, "features"), _req(rois, "rois")
     if rois.dim() != 2 or rois.size(1) != 5:
         raise ValueError("rois must be [R, 5]")   # the reference returns 0 silently (psroi_pooling_cuda.c:17-20)
@@ -86,16 +97,15 @@ def psroi_bins(rois, pooled_h, pooled_w, scale, height, width):
 class _PSRoI(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, rois, ph, pw, scale, group, out_dim, holder):
-        top, mapping = psroi_forward(features, rois, ph, pw, scale, group, out_dim)
+        top, _ = psroi_forward(features, rois, ph, pw, scale, group, out_dim)
         ctx.cfg = (ph, pw, scale, group, out_dim, tuple(features.shape))
         ctx.save_for_backward(rois)
         if holder is not None:   # the reference Function keeps these on itself (psroi_pool.py:28-31)
-            holder.output, holder.mappingchannel, holder.rois, holder.feature_size = top, mapping, rois, features.size()
-        ctx.mark_non_differentiable(mapping)
-        return top, mapping
+            holder.output, holder.rois, holder.feature_size = top, rois, features.size()
+        return top
 
     @staticmethod
-    def backward(ctx, grad_top, _grad_mapping):
+    def backward(ctx, grad_top):
         ph, pw, scale, group, out_dim, fsize = ctx.cfg
         (rois,) = ctx.saved_tensors
         grad = psroi_backward(grad_top.contiguous(), rois, fsize, ph, pw, scale, group, out_dim)
@@ -103,7 +113,7 @@ class _PSRoI(torch.autograd.Function):
 
 
 def psroi_pool(features, rois, ph, pw, scale, group, out_dim, holder=None):
-    return _PSRoI.apply(features, rois, ph, pw, scale, group, out_dim, holder)[0]
+    return _PSRoI.apply(features, rois, ph, pw, scale, group, out_dim, holder)
 
 
 # ------------------------------------------------------------------------------- correlation

@@ -15,9 +15,16 @@ class PSRoIPoolFunction(object):
         self.group_size = int(group_size)
         self.output_dim = int(output_dim)
         self.output = None
-        self.mappingchannel = None
         self.rois = None
         self.feature_size = None
+
+    @property
+    def mappingchannel(self):
+        """int32 [R, D, ph, pw] channel map, as the reference keeps it after forward (psroi_pool.py:29)."""
+        if self.output is None:
+            return None
+        return ops.psroi_mapping_channel(self.output.size(0), self.pooled_height, self.pooled_width, self.group_size,
+                                         self.output_dim, self.output.device)
 
     def __call__(self, features, rois):
         return ops.psroi_pool(features, rois, self.pooled_height, self.pooled_width, self.spatial_scale,
