@@ -182,6 +182,53 @@ int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
                             const int* num_keep, int B, int n_take, int post, float* rois,
                             cudaStream_t stream);
 
+
+/* ---- Convolution engine (tcgen05 / TMEM / TMA implicit GEMM) ----
+ * Replaces the cuDNN convolutions + eval-mode BatchNorm + ReLU the reference reaches through
+ * torch.nn for the ResNet-101 trunk and the heads (faster_rcnn/resnet.py:66-129, 258-312, 333-344;
+ * faster_rcnn/rfcn.py:49-53; rpn/rpn.py:28-36, 62-71).
+ * Activations are NHWC fp32 "split" tensors x = hi + lo: hi = x with the low 13 mantissa bits
+ * cleared (exactly a TF32 value), lo = x - hi (exact).  passes = 3 evaluates hi*hi + hi*lo + lo*hi
+ * on the tensor cores (fp32-level accuracy); passes = 1 is a plain single TF32 pass. */
+typedef struct d2t_conv_desc {
+    int N, H, W;              /* input [N, H, W, in_cstride] */
+    int Cin;                  /* input channels read, a multiple of 32 (zero padded) */
+    int in_cstride;           /* channels per pixel of the input buffer, a multiple of 4 */
+    int Cout, R, S;           /* filter [Cout, R, S, Cin] packed by d2t_conv_pack_weights */
+    int stride, pad, dil;
+    int passes;               /* 3 or 1 */
+    int relu;
+    int out_cstride;          /* channels per pixel of the NHWC output buffers */
+    int out_coffset;          /* this conv writes channels [out_coffset, out_coffset + Cout) */
+    int res_cstride;          /* channels per pixel of the residual buffers (0: = Cout) */
+} d2t_conv_desc;
+typedef struct d2t_conv_plan d2t_conv_plan;
+
+/* out = relu?( scale[c] * conv(in, w) + shift[c] + (res_hi + res_lo) ).  scale / shift / res_* /
+ * out_hi+out_lo / out_nchw may be NULL (at least one output is required); out_nchw is a plain
+ * fp32 [N, Cout, OH, OW] copy for consumers that keep the reference's layout.  The plan captures
+ * the pointers (TMA tensor maps); buffers must outlive it.  Returns NULL on error. */
+d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in_hi, const float* in_lo,
+                                    const float* w_hi, const float* w_lo, const float* scale,
+                                    const float* shift, const float* res_hi, const float* res_lo,
+                                    float* out_hi, float* out_lo, float* out_nchw);
+void d2t_conv_plan_destroy(d2t_conv_plan* plan);
+/* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid} */
+int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);
+int d2t_conv_plan_run(const d2t_conv_plan* plan, cudaStream_t stream);
+
+/* OIHW fp32 -> [Cout][R*S][cin_pad] hi / lo (lo may be NULL) */
+int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+                          float* w_hi, float* w_lo, cudaStream_t stream);
+/* plain fp32 NCHW <-> split NHWC with c_stride channels per pixel (padding channels zeroed) */
+int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, float* hi,
+                           float* lo, cudaStream_t stream);
+int d2t_nhwc_split_to_nchw(const float* hi, const float* lo, int N, int C, int H, int W,
+                           int c_stride, int c_offset, float* out, cudaStream_t stream);
+/* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on split NHWC (faster_rcnn/resnet.py:120) */
+int d2t_maxpool3x3s2_nhwc(const float* in_hi, const float* in_lo, int N, int H, int W, int C,
+                          float* out_hi, float* out_lo, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

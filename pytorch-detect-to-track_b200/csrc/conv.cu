@@ -1,0 +1,534 @@
+// conv.cu -- fused convolution (+ folded BatchNorm / bias, + residual, + ReLU) as a TMA-fed
+// tcgen05 implicit GEMM for sm_100a.
+//
+// Replaces the cuDNN calls the reference makes through torch.nn for the dilated ResNet-101 trunk
+// and the R-FCN / RPN / tracking heads (/root/reference/lib/model/faster_rcnn/resnet.py:66-129,
+// 258-312, 333-344; rfcn.py:49-53; rpn/rpn.py:28-36, 62-71): 1x1 convs (stride 1 and 2), 3x3 convs
+// with dilation 1 / 2 / 6, each followed by an eval-mode BatchNorm (a per-channel affine,
+// resnet.py:290-295) or a bias, an optional residual add and an optional ReLU.
+//
+// GEMM view.  D[pixel, cout] = sum over (tap r,s) and cin of  X[n, oh*st - pad + r*dil,
+// ow*st - pad + s*dil, cin] * W[cout, r, s, cin].
+//   M = 128 output pixels = a TH x TW box of one image (TW a power of two, TH*TW = 128);
+//   N = BN output channels; K runs over taps x 32-channel blocks.
+// Activations are NHWC, so for one (tap, channel block) the A operand of a tile is a
+// [1, TH, TW, 32] box of the input tensor: ONE 4-D TMA copy (cp.async.bulk.tensor, 128-byte
+// swizzle) whose start coordinate carries the tap offset, whose element strides carry the conv
+// stride, and whose out-of-bounds zero fill IS the conv padding -- no im2col buffer, no
+// per-element address math.  B is a [BN, 32] box of the packed weight matrix [Cout, R*S*Cin].
+// Both land in shared memory in exactly the K-major SWIZZLE_128B layout tcgen05.mma consumes.
+//
+// Precision.  The reference computes these convolutions in fp32.  tcgen05 has no fp32 kind;
+// kind::tf32 reads fp32 containers but only 10 mantissa bits.  Every tensor is therefore kept as
+// an exact two-term split x = hi + lo (hi = x with the low 13 mantissa bits cleared, lo = x - hi,
+// both exactly representable) and a K-block issues THREE MMAs, hi*hi + hi*lo + lo*hi, into the same
+// fp32 TMEM accumulator ("3xTF32"): the dropped lo*lo term is <= 2^-22 relative, i.e. fp32-level
+// accuracy at one third of the TF32 rate -- still ~5x the fp32 SIMT pipe.  PASSES = 1 runs the plain
+// single-pass TF32 conv (~1e-3 relative) and is reported separately, never as the parity number.
+//
+// Kernel shape (persistent, warp-specialised, one CTA per SM):
+//   warp 0   : TMA producer (one elected lane), NS-stage ring of {A_hi, A_lo, B_hi, B_lo}
+//   warp 1   : MMA issuer  (one elected lane), tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8
+//   warp 2   : TMEM allocation (2 accumulators of BN columns, so the epilogue of tile i overlaps
+//              the main loop of tile i+1)
+//   warps 4-7: epilogue, one TMEM lane (= one output pixel) per thread: tcgen05.ld -> scale/shift
+//              -> + residual -> ReLU -> re-split into hi/lo -> NHWC stores (and / or a plain fp32
+//              NCHW copy for the consumers that keep the reference's layout: correlation, PSRoI,
+//              the proposal step).
+#include <cuda.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace d2t {
+namespace {
+
+constexpr int kBlockM = 128;       // output pixels per tile (TMEM lanes)
+constexpr int kBlockK = 32;        // fp32 elements per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA K step
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;       // warps 4..7 are the epilogue (warp % 4 = TMEM lane quarter)
+
+struct ConvArgs {
+    int N, OH, OW, Cout;
+    int R, S, stride, pad, dil;
+    int kc_blocks;                 // Cin / 32
+    int TW_log2, TH;               // tile = TH x (1 << TW_log2) pixels
+    int tiles_h, tiles_w, m_tiles, n_tiles;
+    const float* scale;            // [Cout] or null (= 1)
+    const float* shift;            // [Cout] or null (= 0)
+    const float* res_hi;           // NHWC [N, OH, OW, res_cstride] or null
+    const float* res_lo;
+    int res_cstride;
+    int relu;
+    float* out_hi;                 // NHWC [N, OH, OW, out_cstride], channels [out_coffset, +Cout); or null
+    float* out_lo;
+    int out_cstride, out_coffset;
+    float* out_nchw;               // plain fp32 [N, Cout, OH, OW] or null
+};
+
+template <int BN, int PASSES>
+struct Cfg {
+    static constexpr int A_BYTES = kBlockM * kBlockK * 4;             // 16 KB
+    static constexpr int B_BYTES = BN * kBlockK * 4;
+    static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // hi (+ lo)
+    static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two >= 32 (BN in {64,128,256})
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes
+// apart (SBO), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;              // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+    d |= (uint64_t)1 << 46;              // version
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = fp32, A = B = tf32, both K-major, M = 128, N = BN
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const ConvArgs p) {
+    using C = Cfg<BN, PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                        // [STAGES]   TMA -> MMA
+    uint64_t* empty = bars + C::STAGES;           // [STAGES]   MMA -> TMA
+    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue
+    uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int k_iters = p.R * p.S * p.kc_blocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmB_hi);
+        if (PASSES == 3) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4 * 32);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+                const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
+                const int iw0 = (tw << p.TW_log2) * p.stride - p.pad, ih0 = th * p.TH * p.stride - p.pad;
+                const int n0 = n_tile * BN;
+                for (int r = 0; r < p.R; ++r)
+                    for (int s = 0; s < p.S; ++s)
+                        for (int kc = 0; kc < p.kc_blocks; ++kc) {
+                            mbar_wait_sleep(&empty[stage], phase ^ 1);
+                            uint8_t* st = smem + stage * C::STAGE_BYTES;
+                            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                            const int kcol = ((r * p.S + s) * p.kc_blocks + kc) * kBlockK;
+                            tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                            if (PASSES == 3) {
+                                tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
+                                            ih0 + r * p.dil, img);
+                                tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
+                                tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
+                            } else {
+                                tma_load_2d(st + C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
+                            }
+                            if (++stage == C::STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<BN>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+                const int acc = local & 1;
+                mbar_wait_sleep(&tempty[acc], ((local >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait_sleep(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t a_hi = make_smem_desc(st);
+                    if (PASSES == 3) {
+                        const uint64_t a_lo = make_smem_desc(st + C::A_BYTES);
+                        const uint64_t b_hi = make_smem_desc(st + 2 * C::A_BYTES);
+                        const uint64_t b_lo = make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {      // small terms first
+                            const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
+                            umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (k | kk) != 0);
+                            umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
+                            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+                        }
+                    } else {
+                        const uint64_t b_hi = make_smem_desc(st + C::A_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+                            const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
+                            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, (k | kk) != 0);
+                        }
+                    }
+                    umma_commit(&empty[stage]);                          // smem slot free once these MMAs retire
+                    if (k == k_iters - 1) umma_commit(&tfull[acc]);      // accumulator complete
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue =====================
+        const int q = warp - kEpiWarp0;                    // TMEM lane quarter of this warp
+        const int m = q * 32 + lane;                       // tile row = TMEM lane = output pixel in the tile
+        const int TW = 1 << p.TW_log2;
+        const int hl = m >> p.TW_log2, wl = m & (TW - 1);
+        int local = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+            const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
+            const int oh = th * p.TH + hl, ow = (tw << p.TW_log2) + wl;
+            const bool pix_ok = oh < p.OH && ow < p.OW;
+            const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
+            const int n0 = n_tile * BN;
+            mbar_wait_sleep(&tfull[acc], (local >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                float v[16];
+                tmem_ld16(taddr + c * 16, v);
+                const int ch0 = n0 + c * 16;
+                if (ch0 >= p.Cout) continue;                 // (warp-uniform)
+                const bool full16 = ch0 + 16 <= p.Cout;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int ch = min(ch0 + j, p.Cout - 1);
+                    const float sc = p.scale ? __ldg(p.scale + ch) : 1.f;
+                    const float sh = p.shift ? __ldg(p.shift + ch) : 0.f;
+                    v[j] = fmaf(v[j], sc, sh);
+                }
+                if (p.res_hi && pix_ok) {
+                    const float* rh = p.res_hi + pix * p.res_cstride + ch0;
+                    const float* rl = p.res_lo + pix * p.res_cstride + ch0;
+                    if (full16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(rh + j));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(rl + j));
+                            v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 16 && ch0 + j < p.Cout; ++j) v[j] += __ldg(rh + j) + __ldg(rl + j);
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.out_nchw && pix_ok) {
+                    float* o = p.out_nchw + (((size_t)img * p.Cout + ch0) * p.OH + oh) * p.OW + ow;
+                    const size_t cs = (size_t)p.OH * p.OW;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full16 || ch0 + j < p.Cout) o[j * cs] = v[j];     // lanes = consecutive ow: coalesced
+                }
+                if (p.out_hi && pix_ok) {
+                    float* oh_ = p.out_hi + pix * p.out_cstride + p.out_coffset + ch0;
+                    float* ol_ = p.out_lo + pix * p.out_cstride + p.out_coffset + ch0;
+                    if (full16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 h, l;
+                            h.x = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);     l.x = v[j] - h.x;
+                            h.y = __uint_as_float(__float_as_uint(v[j + 1]) & 0xffffe000u); l.y = v[j + 1] - h.y;
+                            h.z = __uint_as_float(__float_as_uint(v[j + 2]) & 0xffffe000u); l.z = v[j + 2] - h.z;
+                            h.w = __uint_as_float(__float_as_uint(v[j + 3]) & 0xffffe000u); l.w = v[j + 3] - h.w;
+                            *reinterpret_cast<float4*>(oh_ + j) = h;
+                            *reinterpret_cast<float4*>(ol_ + j) = l;
+                        }
+                    } else {
+                        for (int j = 0; j < 16 && ch0 + j < p.Cout; ++j) {
+                            const float h = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+                            oh_[j] = h;
+                            ol_[j] = v[j] - h;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+            const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return false;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+}  // namespace d2t
+
+using namespace d2t;
+
+struct d2t_conv_plan {
+    alignas(64) CUtensorMap tmA_hi;
+    alignas(64) CUtensorMap tmA_lo;
+    alignas(64) CUtensorMap tmB_hi;
+    alignas(64) CUtensorMap tmB_lo;
+    ConvArgs args;
+    int BN, passes, grid;
+};
+
+template <int BN, int PASSES>
+static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
+    using C = Cfg<BN, PASSES>;
+    static SmemAttrOnce once;
+    if (!once.ensure(conv_igemm_tf32<BN, PASSES>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    conv_igemm_tf32<BN, PASSES><<<pl->grid, kThreads, C::SMEM_BYTES, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
+                                                                             pl->tmB_lo, pl->args);
+    D2T_CHECK_LAUNCH("conv_igemm_tf32");
+    return 1;
+}
+
+extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const float* in_hi, const float* in_lo,
+                                               const float* w_hi, const float* w_lo, const float* scale,
+                                               const float* shift, const float* res_hi, const float* res_lo,
+                                               float* out_hi, float* out_lo, float* out_nchw) {
+    if (!d || !in_hi || !w_hi || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->R <= 0 ||
+        d->S <= 0 || d->stride <= 0 || d->dil <= 0 || d->pad < 0) {
+        set_error("d2t_conv_plan_create: bad descriptor");
+        return nullptr;
+    }
+    if (d->Cin % kBlockK != 0 || d->in_cstride % 4 != 0 || d->in_cstride < d->Cin) {
+        set_error("d2t_conv_plan_create: Cin must be a multiple of 32 (zero-pad) and in_cstride a multiple of 4");
+        return nullptr;
+    }
+    if (d->passes != 1 && d->passes != 3) {
+        set_error("d2t_conv_plan_create: passes must be 1 (TF32) or 3 (3xTF32, fp32-accurate)");
+        return nullptr;
+    }
+    if (d->passes == 3 && (!in_lo || !w_lo)) {
+        set_error("d2t_conv_plan_create: 3-pass mode needs the lo halves of input and weights");
+        return nullptr;
+    }
+    if ((out_hi && (!out_lo || d->out_cstride % 4 != 0 || d->out_coffset % 4 != 0)) || (!out_hi && !out_nchw)) {
+        set_error("d2t_conv_plan_create: need an output (NHWC hi+lo with 4-aligned channel stride/offset, and/or NCHW)");
+        return nullptr;
+    }
+    if (res_hi && !res_lo) {
+        set_error("d2t_conv_plan_create: residual needs both halves");
+        return nullptr;
+    }
+    const int OH = (d->H + 2 * d->pad - d->dil * (d->R - 1) - 1) / d->stride + 1;
+    const int OW = (d->W + 2 * d->pad - d->dil * (d->S - 1) - 1) / d->stride + 1;
+    if (OH <= 0 || OW <= 0) {
+        set_error("d2t_conv_plan_create: empty output");
+        return nullptr;
+    }
+    int twl = 0;
+    while ((1 << twl) < OW && twl < 7) ++twl;            // TW = min(128, next pow2 >= OW)
+    const int TW = 1 << twl, TH = kBlockM / TW;
+    if ((TW - 1) * d->stride + 1 > 256 || (TH - 1) * d->stride + 1 > 256) {
+        set_error("d2t_conv_plan_create: stride too large for the TMA box");
+        return nullptr;
+    }
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(d2t_conv_plan)) != 0) {
+        set_error("d2t_conv_plan_create: out of memory");
+        return nullptr;
+    }
+    d2t_conv_plan* pl = new (mem) d2t_conv_plan();
+    ConvArgs& a = pl->args;
+    a.N = d->N; a.OH = OH; a.OW = OW; a.Cout = d->Cout;
+    a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
+    a.kc_blocks = d->Cin / kBlockK;
+    a.TW_log2 = twl; a.TH = TH;
+    a.tiles_w = (OW + TW - 1) / TW; a.tiles_h = (OH + TH - 1) / TH;
+    a.m_tiles = d->N * a.tiles_h * a.tiles_w;
+    // N tile: 128 unless the layer is narrow
+    pl->BN = d->Cout <= 64 ? 64 : 128;
+    a.n_tiles = (d->Cout + pl->BN - 1) / pl->BN;
+    a.scale = scale; a.shift = shift;
+    a.res_hi = res_hi; a.res_lo = res_lo; a.res_cstride = d->res_cstride > 0 ? d->res_cstride : d->Cout;
+    a.relu = d->relu;
+    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
+    a.out_nchw = out_nchw;
+    pl->passes = d->passes;
+    const int tiles = a.m_tiles * a.n_tiles;
+    pl->grid = tiles < sm_count() ? tiles : sm_count();
+
+    // A: NHWC activation, dims innermost first {C, W, H, N}
+    const cuuint64_t adims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    const cuuint64_t astr[3] = {(cuuint64_t)d->in_cstride * 4, (cuuint64_t)d->W * d->in_cstride * 4,
+                                (cuuint64_t)d->H * d->W * d->in_cstride * 4};
+    const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)((TW - 1) * d->stride + 1),
+                                (cuuint32_t)((TH - 1) * d->stride + 1), 1u};
+    const cuuint32_t aestr[4] = {1u, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1u};
+    // B: packed weights [Cout, R*S*Cin]
+    const cuuint64_t ktot = (cuuint64_t)d->R * d->S * d->Cin;
+    const cuuint64_t bdims[2] = {ktot, (cuuint64_t)d->Cout};
+    const cuuint64_t bstr[1] = {ktot * 4};
+    const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)pl->BN};
+    const cuuint32_t bestr[2] = {1u, 1u};
+    bool ok = encode(&pl->tmA_hi, in_hi, 4, adims, astr, abox, aestr, "A hi") &&
+              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi");
+    if (ok && d->passes == 3)
+        ok = encode(&pl->tmA_lo, in_lo, 4, adims, astr, abox, aestr, "A lo") &&
+             encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo");
+    if (ok && d->passes == 1) {
+        pl->tmA_lo = pl->tmA_hi;
+        pl->tmB_lo = pl->tmB_hi;
+    }
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
+extern "C" void d2t_conv_plan_destroy(d2t_conv_plan* pl) {
+    if (pl) free(pl);
+}
+
+extern "C" int d2t_conv_plan_info(const d2t_conv_plan* pl, int* out8) {
+    D2T_REQUIRE(pl && out8, "d2t_conv_plan_info: null");
+    out8[0] = pl->args.OH; out8[1] = pl->args.OW; out8[2] = pl->args.TH; out8[3] = 1 << pl->args.TW_log2;
+    out8[4] = pl->BN; out8[5] = pl->args.m_tiles; out8[6] = pl->args.n_tiles; out8[7] = pl->grid;
+    return 1;
+}
+
+extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
+    D2T_REQUIRE(pl, "d2t_conv_plan_run: null plan");
+    if (pl->passes == 3) return pl->BN == 64 ? launch_conv<64, 3>(pl, stream) : launch_conv<128, 3>(pl, stream);
+    return pl->BN == 64 ? launch_conv<64, 1>(pl, stream) : launch_conv<128, 1>(pl, stream);
+}

@@ -1,0 +1,162 @@
+// conv_util.cu -- layout / precision-split helpers around the tcgen05 conv kernels (conv.cu).
+//
+// The conv engine keeps activations as NHWC "split" tensors x = hi + lo (hi = x with the low 13
+// mantissa bits cleared = exactly a TF32 value, lo = x - hi, exact).  These kernels move data
+// between that format and the reference's plain fp32 NCHW tensors, pack OIHW weights into the
+// [Cout, R*S*Cin_pad] K-major matrix the weight TMA reads, and implement the stem's
+// MaxPool2d(3, stride 2, padding 0, ceil_mode=True) (/root/reference/lib/model/faster_rcnn/resnet.py:120).
+#include "common.cuh"
+
+namespace d2t {
+namespace {
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+inline int grid_for(size_t total, int per_block = 256) {
+    size_t blocks = (total + per_block - 1) / per_block, cap = (size_t)sm_count() * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+// [N,C,H,W] fp32 -> [N,H,W,cs] hi/lo; channels [C, cs) are zero-filled.  32x32 smem transpose per (n, h).
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int cs, float* __restrict__ hi,
+                   float* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = ct + j, w = wt + tx;
+        tile[j][tx] = (c < C && w < W) ? __ldg(x + (((size_t)n * C + c) * H + h) * W + w) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int w = wt + j, c = ct + tx;
+        if (w < W && c < cs) {
+            const float v = tile[tx][j], a = tf32_hi(v);
+            const size_t o = (((size_t)n * H + h) * W + w) * cs + c;
+            hi[o] = a;
+            if (lo) lo[o] = v - a;
+        }
+    }
+}
+
+// [N,H,W,cs] hi(+lo) -> [N,C,H,W] fp32
+__global__ void __launch_bounds__(256)
+nhwc_split_to_nchw(const float* __restrict__ hi, const float* __restrict__ lo, int N, int C, int H, int W, int cs,
+                   int coff, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int w = wt + j, c = ct + tx;
+        float v = 0.f;
+        if (w < W && c < C) {
+            const size_t i = (((size_t)n * H + h) * W + w) * cs + coff + c;
+            v = __ldg(hi + i) + (lo ? __ldg(lo + i) : 0.f);
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = ct + j, w = wt + tx;
+        if (c < C && w < W) out[(((size_t)n * C + c) * H + h) * W + w] = tile[tx][j];
+    }
+}
+
+// OIHW -> [O][R*S][cin_pad] hi/lo (zero pad)
+__global__ void pack_weights(const float* __restrict__ w, int O, int I, int R, int S, int cin_pad,
+                             float* __restrict__ hi, float* __restrict__ lo) {
+    const size_t total = (size_t)O * R * S * cin_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cin_pad);
+        const int rs = (int)((idx / cin_pad) % (R * S));
+        const int o = (int)(idx / cin_pad / (R * S));
+        const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) : 0.f;
+        const float a = tf32_hi(v);
+        hi[idx] = a;
+        if (lo) lo[idx] = v - a;
+    }
+}
+
+// MaxPool 3x3 stride 2, padding 0, ceil_mode (windows clipped at the border), NHWC: in hi(+lo) -> out hi/lo
+__global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int N, int H, int W,
+                                  int C, int OH, int OW, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    const int C4 = C >> 2;
+    const size_t total = (size_t)N * OH * OW * C4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        const int ow = (int)((idx / C4) % OW);
+        const int oh = (int)((idx / C4 / OW) % OH);
+        const int n = (int)(idx / C4 / OW / OH);
+        float4 m = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
+        for (int r = 0; r < 3; ++r) {
+            const int h = oh * 2 + r;
+            if (h >= H) break;
+            for (int s = 0; s < 3; ++s) {
+                const int w = ow * 2 + s;
+                if (w >= W) break;
+                const size_t i = ((((size_t)n * H + h) * W + w) * C >> 2) + c4;
+                float4 v = __ldg(reinterpret_cast<const float4*>(in_hi) + i);
+                if (in_lo) {
+                    const float4 l = __ldg(reinterpret_cast<const float4*>(in_lo) + i);
+                    v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+                }
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        float4 a = make_float4(tf32_hi(m.x), tf32_hi(m.y), tf32_hi(m.z), tf32_hi(m.w));
+        reinterpret_cast<float4*>(out_hi)[idx] = a;
+        if (out_lo) reinterpret_cast<float4*>(out_lo)[idx] = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
+    }
+}
+
+}  // namespace
+}  // namespace d2t
+
+using namespace d2t;
+
+extern "C" int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, float* hi, float* lo,
+                                      cudaStream_t stream) {
+    D2T_REQUIRE(x && hi && N > 0 && C > 0 && H > 0 && W > 0 && c_stride >= C, "d2t_nchw_to_nhwc_split: bad arguments");
+    D2T_REQUIRE((long long)N * H <= 65535 * 1LL * 1 || true, "unreachable");
+    dim3 grid((W + 31) / 32, (c_stride + 31) / 32, N * H);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc_split: tensor too large for the launch grid");
+    nchw_to_nhwc_split<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, hi, lo);
+    D2T_CHECK_LAUNCH("nchw_to_nhwc_split");
+    return 1;
+}
+
+extern "C" int d2t_nhwc_split_to_nchw(const float* hi, const float* lo, int N, int C, int H, int W, int c_stride,
+                                      int c_offset, float* out, cudaStream_t stream) {
+    D2T_REQUIRE(hi && out && N > 0 && C > 0 && H > 0 && W > 0 && c_stride >= c_offset + C,
+                "d2t_nhwc_split_to_nchw: bad arguments");
+    dim3 grid((W + 31) / 32, (C + 31) / 32, N * H);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nhwc_split_to_nchw: tensor too large for the launch grid");
+    nhwc_split_to_nchw<<<grid, 256, 0, stream>>>(hi, lo, N, C, H, W, c_stride, c_offset, out);
+    D2T_CHECK_LAUNCH("nhwc_split_to_nchw");
+    return 1;
+}
+
+extern "C" int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad, float* w_hi,
+                                     float* w_lo, cudaStream_t stream) {
+    D2T_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && R > 0 && S > 0 && cin_pad >= Cin,
+                "d2t_conv_pack_weights: bad arguments");
+    const size_t total = (size_t)Cout * R * S * cin_pad;
+    pack_weights<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, w_hi, w_lo);
+    D2T_CHECK_LAUNCH("pack_weights");
+    return 1;
+}
+
+extern "C" int d2t_maxpool3x3s2_nhwc(const float* in_hi, const float* in_lo, int N, int H, int W, int C, float* out_hi,
+                                     float* out_lo, cudaStream_t stream) {
+    D2T_REQUIRE(in_hi && out_hi && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "d2t_maxpool3x3s2_nhwc: bad arguments");
+    // ceil((H - 3) / 2) + 1, and the last window must start inside the input (torch pooling rule)
+    int OH = (H - 3 + 1) / 2 + 1, OW = (W - 3 + 1) / 2 + 1;
+    if ((OH - 1) * 2 >= H) --OH;
+    if ((OW - 1) * 2 >= W) --OW;
+    D2T_REQUIRE(OH > 0 && OW > 0, "d2t_maxpool3x3s2_nhwc: input too small");
+    const size_t total = (size_t)N * OH * OW * (C / 4);
+    maxpool3x3s2_nhwc<<<grid_for(total), 256, 0, stream>>>(in_hi, in_lo, N, H, W, C, OH, OW, out_hi, out_lo);
+    D2T_CHECK_LAUNCH("maxpool3x3s2_nhwc");
+    return 1;
+}

@@ -56,15 +56,24 @@ _SIGS = {
     "d2t_proposal_decode": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_proposal_gather": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "d2t_proposal_write_rois": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
-    "d2t_psroi_vote_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _f, _i, _i, _p, _p, _sz, _p]),
-    "d2t_conv_workspace_bytes": (_sz, [_i] * 12),
-    "d2t_conv2d_forward": (_i, [_p, _p, _p, _p, _p] + [_i] * 12 + [_i, _i, _p, _sz, _p]),
-    "d2t_conv_pack_weights": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    # ---- convolution engine
+    "d2t_conv_plan_create": (_p, [_p] * 12),
+    "d2t_conv_plan_destroy": (None, [_p]),
+    "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),
+    "d2t_conv_plan_run": (_i, [_p, _p]),
+    "d2t_conv_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_nchw_to_nhwc_split": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_nhwc_split_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "d2t_maxpool3x3s2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
 }
 
-# symbols declared in the header that later milestones add; absent ones are skipped at bind
-# time and raise on use, so an older .so still loads for the ops it has.
-_OPTIONAL = {"d2t_psroi_vote_forward", "d2t_conv_workspace_bytes", "d2t_conv2d_forward", "d2t_conv_pack_weights"}
+_OPTIONAL = set()
+
+
+class ConvDesc(C.Structure):
+    """struct d2t_conv_desc (include/d2t_b200.h)"""
+    _fields_ = [(n, C.c_int) for n in ("N", "H", "W", "Cin", "in_cstride", "Cout", "R", "S", "stride", "pad", "dil",
+                                       "passes", "relu", "out_cstride", "out_coffset", "res_cstride")]
 
 _lib = None
 
@@ -101,6 +110,7 @@ def declared_symbols():
     import re
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct \w+ \{.*?\} \w+;", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)) - {"defined", "push", "visibility"})
 
 

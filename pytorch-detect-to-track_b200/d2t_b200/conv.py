@@ -1,0 +1,123 @@
+"""Tensor-level front end of the tcgen05 convolution engine (csrc/conv.cu, csrc/conv_util.cu).
+
+``SplitTensor`` is an NHWC fp32 activation kept as an exact two-term TF32 split (hi, lo);
+``ConvLayer`` owns packed weights, the folded BatchNorm / bias vectors, its output buffers and the
+C-ABI plan (TMA tensor maps) that runs it.  Nothing here computes on the CPU; everything is
+enqueued on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import ConvDesc, D2TError, check, lib
+from . import ops
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+class SplitTensor(object):
+    """[N, H, W, cstride] fp32 pair; channels [0, C) are meaningful, the rest are zero."""
+
+    def __init__(self, N, H, W, C_, cstride=None, device="cuda", lo=True):
+        self.N, self.H, self.W, self.C = N, H, W, C_
+        self.cstride = cstride if cstride is not None else (C_ + 3) // 4 * 4
+        self.hi = torch.zeros(N, H, W, self.cstride, device=device)
+        self.lo = torch.zeros(N, H, W, self.cstride, device=device) if lo else None
+
+    @staticmethod
+    def from_nchw(x, cstride=None, lo=True, out=None):
+        N, C_, H, W = x.shape
+        t = out if out is not None else SplitTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device, lo)
+        check(lib().d2t_nchw_to_nhwc_split(x.contiguous().data_ptr(), N, C_, H, W, t.cstride, t.hi.data_ptr(),
+                                           t.lo.data_ptr() if t.lo is not None else None, _stream()),
+              "d2t_nchw_to_nhwc_split")
+        ops._count(1)
+        return t
+
+    def to_nchw(self, C_=None, coffset=0):
+        C_ = self.C if C_ is None else C_
+        out = torch.empty(self.N, C_, self.H, self.W, device=self.hi.device)
+        check(lib().d2t_nhwc_split_to_nchw(self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None,
+                                           self.N, C_, self.H, self.W, self.cstride, coffset, out.data_ptr(), _stream()),
+              "d2t_nhwc_split_to_nchw")
+        ops._count(1)
+        return out
+
+
+def pack_weights(w, cin_pad=None, lo=True):
+    """OIHW -> ([O, R*S*cin_pad] hi, lo)"""
+    O, I, R, S = w.shape
+    cin_pad = cin_pad or _pad32(I)
+    w = w.detach().contiguous().float()
+    hi = torch.empty(O, R * S * cin_pad, device=w.device)
+    lo_t = torch.empty_like(hi) if lo else None
+    check(lib().d2t_conv_pack_weights(w.data_ptr(), O, I, R, S, cin_pad, hi.data_ptr(),
+                                      lo_t.data_ptr() if lo else None, _stream()), "d2t_conv_pack_weights")
+    return hi, lo_t
+
+
+class ConvLayer(object):
+    """out = relu?(scale * conv(x, w) + shift + residual) bound to fixed input / output buffers."""
+
+    def __init__(self, x, weight, scale=None, shift=None, stride=1, pad=0, dil=1, relu=False, residual=None,
+                 passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False):
+        O, I, R, S = weight.shape
+        if _pad32(I) > x.cstride:
+            raise ValueError("input buffer has %d channels per pixel, conv needs %d" % (x.cstride, _pad32(I)))
+        self.x, self.residual = x, residual
+        self.w_hi, self.w_lo = pack_weights(weight, _pad32(I), lo=(passes == 3))
+        dev = weight.device
+        self.scale = scale.detach().float().contiguous().to(dev) if scale is not None else None
+        self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
+        OH = (x.H + 2 * pad - dil * (R - 1) - 1) // stride + 1
+        OW = (x.W + 2 * pad - dil * (S - 1) - 1) // stride + 1
+        self.out = out if out is not None else (SplitTensor(x.N, OH, OW, O, device=dev) if want_nhwc else None)
+        self.out_nchw = torch.empty(x.N, O, OH, OW, device=dev) if want_nchw else None
+        d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=_pad32(I), in_cstride=x.cstride, Cout=O, R=R, S=S, stride=stride, pad=pad,
+                     dil=dil, passes=passes, relu=int(relu), out_cstride=self.out.cstride if self.out is not None else 0,
+                     out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0)
+        p = lambda t: t.data_ptr() if t is not None else None
+        self.plan = lib().d2t_conv_plan_create(
+            C.byref(d), p(x.hi), p(x.lo), p(self.w_hi), p(self.w_lo), p(self.scale), p(self.shift),
+            p(residual.hi) if residual is not None else None, p(residual.lo) if residual is not None else None,
+            p(self.out.hi) if self.out is not None else None, p(self.out.lo) if self.out is not None else None,
+            p(self.out_nchw))
+        if not self.plan:
+            raise D2TError("d2t_conv_plan_create failed: %s" % lib().d2t_last_error().decode())
+        info = (C.c_int * 8)()
+        lib().d2t_conv_plan_info(self.plan, info)
+        self.info = dict(zip(("OH", "OW", "tile_h", "tile_w", "BN", "m_tiles", "n_tiles", "grid"), list(info)))
+        self.flops = 2.0 * x.N * OH * OW * O * I * R * S
+
+    def run(self):
+        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
+        ops._count(1)
+        return self.out if self.out is not None else self.out_nchw
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                lib().d2t_conv_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+
+def maxpool3x3s2(x, out=None):
+    OH = -(-(x.H - 3) // 2) + 1
+    OW = -(-(x.W - 3) // 2) + 1
+    if (OH - 1) * 2 >= x.H:
+        OH -= 1
+    if (OW - 1) * 2 >= x.W:
+        OW -= 1
+    out = out if out is not None else SplitTensor(x.N, OH, OW, x.C, x.cstride, x.hi.device)
+    check(lib().d2t_maxpool3x3s2_nhwc(x.hi.data_ptr(), x.lo.data_ptr() if x.lo is not None else None, x.N, x.H, x.W,
+                                      x.cstride, out.hi.data_ptr(), out.lo.data_ptr(), _stream()), "d2t_maxpool3x3s2_nhwc")
+    ops._count(1)
+    return out
