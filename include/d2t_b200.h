@@ -220,9 +220,21 @@ int d2t_conv_plan_run(const d2t_conv_plan* plan, cudaStream_t stream);
 /* OIHW fp32 -> [Cout][R*S][cin_pad] hi / lo (lo may be NULL) */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
                           float* w_hi, float* w_lo, cudaStream_t stream);
-/* plain fp32 NCHW <-> split NHWC with c_stride channels per pixel (padding channels zeroed) */
-int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, float* hi,
-                           float* lo, cudaStream_t stream);
+/* The 7x7 stride-2 pad-3 stem conv (faster_rcnn/resnet.py:116) on the same kernel: the image is
+ * first packed by d2t_stem_pack_input into zero-bordered NHWC4 buffers [N, (H+7)&~1, W+8, 4] and
+ * the filter by d2t_stem_pack_weights into [Cout][7][32]; output is split NHWC [N, OH, OW, out_cstride]. */
+d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in_hi,
+                                         const float* in_lo, const float* w_hi, const float* w_lo,
+                                         const float* scale, const float* shift, int relu,
+                                         float* out_hi, float* out_lo, int out_cstride);
+int d2t_stem_pack_input(const float* x_nchw, int N, int C, int H, int W, float* hi, float* lo,
+                        cudaStream_t stream);
+int d2t_stem_pack_weights(const float* w_oihw, int Cout, int Cin, float* w_hi, float* w_lo,
+                          cudaStream_t stream);
+/* plain fp32 NCHW -> channels [c_offset, c_offset + c_width) of a split NHWC tensor with c_stride
+ * channels per pixel (the C source channels, then zeros); and back */
+int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, int c_offset,
+                           int c_width, float* hi, float* lo, cudaStream_t stream);
 int d2t_nhwc_split_to_nchw(const float* hi, const float* lo, int N, int C, int H, int W,
                            int c_stride, int c_offset, float* out, cudaStream_t stream);
 /* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on split NHWC (faster_rcnn/resnet.py:120) */

@@ -29,12 +29,12 @@
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
 //   warp 0   : TMA producer (one elected lane), NS-stage ring of {A_hi, A_lo, B_hi, B_lo}
 //   warp 1   : MMA issuer  (one elected lane), tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8
-//   warp 2   : TMEM allocation (2 accumulators of BN columns, so the epilogue of tile i overlaps
-//              the main loop of tile i+1)
-//   warps 4-7: epilogue, one TMEM lane (= one output pixel) per thread: tcgen05.ld -> scale/shift
-//              -> + residual -> ReLU -> re-split into hi/lo -> NHWC stores (and / or a plain fp32
-//              NCHW copy for the consumers that keep the reference's layout: correlation, PSRoI,
-//              the proposal step).
+//   warp 2   : TMEM allocation (two ping-pong chunk accumulators + two cross-term accumulators)
+//   warps 4-7: accumulate + epilogue, one TMEM lane (= one output pixel) per thread: every finished
+//              K chunk is pulled out of TMEM (tcgen05.ld) and added into fp32 registers, then
+//              scale/shift -> + residual -> ReLU -> re-split into hi/lo -> NHWC stores (and / or a
+//              plain fp32 NCHW copy for the consumers that keep the reference's layout: correlation,
+//              PSRoI, the proposal step) -- all while the tensor core is already on the next tile.
 #include <cuda.h>
 
 #include <new>
@@ -49,6 +49,7 @@ constexpr int kBlockK = 32;        // fp32 elements per K block = one 128-byte s
 constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA K step
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;       // warps 4..7 are the epilogue (warp % 4 = TMEM lane quarter)
+constexpr int kChunkK = 8;         // k-blocks accumulated in TMEM before the partial sum moves to registers
 
 struct ConvArgs {
     int N, OH, OW, Cout;
@@ -56,6 +57,7 @@ struct ConvArgs {
     int kc_blocks;                 // Cin / 32
     int TW_log2, TH;               // tile = TH x (1 << TW_log2) pixels
     int tiles_h, tiles_w, m_tiles, n_tiles;
+    int stem;                      // 1: A comes through the rank-5 "row window" map of the 7x7 stride-2 stem
     const float* scale;            // [Cout] or null (= 1)
     const float* shift;            // [Cout] or null (= 0)
     const float* res_hi;           // NHWC [N, OH, OW, res_cstride] or null
@@ -77,7 +79,8 @@ struct Cfg {
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two >= 32 (BN in {64,128,256})
+    // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
+    static constexpr int TMEM_COLS = (PASSES == 3 ? 4 : 2) * BN;      // power of two >= 32 for BN in {64,128}
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -86,6 +89,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -156,9 +166,10 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;                        // [STAGES]   TMA -> MMA
     uint64_t* empty = bars + C::STAGES;           // [STAGES]   MMA -> TMA
-    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue
-    uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue: chunk buffer complete
+    uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA: chunk buffer drained
+    uint64_t* xempty = tempty + 2;                // [2]        epilogue -> MMA: cross-term buffer read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.m_tiles * p.n_tiles;
@@ -180,6 +191,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4 * 32);
+            mbar_init(&xempty[i], 4 * 32);
         }
         fence_mbar_init();
     }
@@ -210,10 +222,20 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             uint8_t* st = smem + stage * C::STAGE_BYTES;
                             mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                             const int kcol = ((r * p.S + s) * p.kc_blocks + kc) * kBlockK;
-                            tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                            if (p.stem) {
+                                // filter row r of the stem: 32 consecutive floats (8 pixels x 4 channels) of padded
+                                // input row 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
+                                const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
+                                tma_load_5d(st, &tmA_hi, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
+                                if (PASSES == 3)
+                                    tma_load_5d(st + C::A_BYTES, &tmA_lo, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
+                            } else {
+                                tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                                if (PASSES == 3)
+                                    tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
+                                                ih0 + r * p.dil, img);
+                            }
                             if (PASSES == 3) {
-                                tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
-                                            ih0 + r * p.dil, img);
                                 tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
                                 tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
                             } else {
@@ -228,17 +250,31 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // fp32 accumulation inside the tensor core truncates on every add, a bias that grows with the
+        // number of accumulation steps (measured: ~2e-8 of the result per step).  So (1) the main
+        // hi*hi products are accumulated in TMEM only over a CHUNK of kChunkK k-blocks (32 steps);
+        // each finished chunk is drained by the epilogue warps into fp32 REGISTERS with
+        // round-to-nearest adds while the next chunk runs into the other TMEM buffer; (2) the two
+        // cross terms (2^-11 of the result, so their truncation is negligible) accumulate over the
+        // whole tile in their own TMEM buffer.  TMEM: main[2] | cross[2], BN columns each.
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc<BN>();
-            int stage = 0;
-            uint32_t phase = 0;
-            int local = 0;
+            int stage = 0, cbuf = 0, local = 0;
+            uint32_t phase = 0, cphase = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-                const int acc = local & 1;
-                mbar_wait_sleep(&tempty[acc], ((local >> 1) & 1) ^ 1);     // epilogue drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const int xacc = local & 1;
+                const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
+                if (PASSES == 3) {
+                    mbar_wait_sleep(&xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
+                    tc_fence_after();
+                }
                 for (int k = 0; k < k_iters; ++k) {
+                    const int kin = k % kChunkK;
+                    if (kin == 0) {
+                        mbar_wait_sleep(&tempty[cbuf], cphase ^ 1);          // epilogue drained this chunk buffer
+                        tc_fence_after();
+                    }
+                    const uint32_t d_main = tmem_base + cbuf * BN;
                     mbar_wait_sleep(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -248,22 +284,26 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         const uint64_t b_hi = make_smem_desc(st + 2 * C::A_BYTES);
                         const uint64_t b_lo = make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {      // small terms first
+                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (k | kk) != 0);
-                            umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1);
-                            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1);
+                            umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, (k | kk) != 0);
+                            umma_tf32(d_cross, a_hi + o, b_lo + o, idesc, 1);
+                            umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                         }
                     } else {
                         const uint64_t b_hi = make_smem_desc(st + C::A_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, (k | kk) != 0);
+                            umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                         }
                     }
                     umma_commit(&empty[stage]);                          // smem slot free once these MMAs retire
-                    if (k == k_iters - 1) umma_commit(&tfull[acc]);      // accumulator complete
+                    if (kin == kChunkK - 1 || k == k_iters - 1) {        // chunk complete (covers the cross MMAs too)
+                        umma_commit(&tfull[cbuf]);
+                        cbuf ^= 1;
+                        if (cbuf == 0) cphase ^= 1;
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -277,30 +317,59 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int m = q * 32 + lane;                       // tile row = TMEM lane = output pixel in the tile
         const int TW = 1 << p.TW_log2;
         const int hl = m >> p.TW_log2, wl = m & (TW - 1);
-        int local = 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nchunks = (k_iters + kChunkK - 1) / kChunkK;
+        int local = 0, cbuf = 0;
+        uint32_t cphase = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-            const int acc = local & 1;
+            const int xacc = local & 1;
             const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
             const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
             const int oh = th * p.TH + hl, ow = (tw << p.TW_log2) + wl;
             const bool pix_ok = oh < p.OH && ow < p.OW;
             const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
             const int n0 = n_tile * BN;
-            mbar_wait_sleep(&tfull[acc], (local >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+            float acc[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch) {          // drain finished chunks: fp32 round-to-nearest adds
+                mbar_wait_sleep(&tfull[cbuf], cphase);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < BN / 16; ++c) {
+                    float v[16];
+                    tmem_ld16(lane_base + cbuf * BN + c * 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[cbuf]);
+                cbuf ^= 1;
+                if (cbuf == 0) cphase ^= 1;
+            }
+            if (PASSES == 3) {                               // + the cross terms of the whole tile
+#pragma unroll
+                for (int c = 0; c < BN / 16; ++c) {
+                    float v[16];
+                    tmem_ld16(lane_base + (2 + xacc) * BN + c * 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
+                }
+                tc_fence_before();
+                mbar_arrive(&xempty[xacc]);
+            }
+            // ---- from here on the tile lives in registers; the tensor core is already on the next tile
+#pragma unroll
             for (int c = 0; c < BN / 16; ++c) {
-                float v[16];
-                tmem_ld16(taddr + c * 16, v);
+                float* v = acc + c * 16;
                 const int ch0 = n0 + c * 16;
                 if (ch0 >= p.Cout) continue;                 // (warp-uniform)
                 const bool full16 = ch0 + 16 <= p.Cout;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int ch = min(ch0 + j, p.Cout - 1);
-                    const float sc = p.scale ? __ldg(p.scale + ch) : 1.f;
-                    const float sh = p.shift ? __ldg(p.shift + ch) : 0.f;
+                    const int chn = min(ch0 + j, p.Cout - 1);
+                    const float sc = p.scale ? __ldg(p.scale + chn) : 1.f;
+                    const float sh = p.shift ? __ldg(p.shift + chn) : 0.f;
                     v[j] = fmaf(v[j], sc, sh);
                 }
                 if (p.res_hi && pix_ok) {
@@ -314,7 +383,9 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
                         }
                     } else {
-                        for (int j = 0; j < 16 && ch0 + j < p.Cout; ++j) v[j] += __ldg(rh + j) + __ldg(rl + j);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < p.Cout) v[j] += __ldg(rh + j) + __ldg(rl + j);
                     }
                 }
                 if (p.relu) {
@@ -343,16 +414,16 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             *reinterpret_cast<float4*>(ol_ + j) = l;
                         }
                     } else {
-                        for (int j = 0; j < 16 && ch0 + j < p.Cout; ++j) {
-                            const float h = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
-                            oh_[j] = h;
-                            ol_[j] = v[j] - h;
-                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < p.Cout) {
+                                const float h = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+                                oh_[j] = h;
+                                ol_[j] = v[j] - h;
+                            }
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
         }
     }
     tc_fence_before();
@@ -472,7 +543,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.N = d->N; a.OH = OH; a.OW = OW; a.Cout = d->Cout;
     a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
     a.kc_blocks = d->Cin / kBlockK;
-    a.TW_log2 = twl; a.TH = TH;
+    a.TW_log2 = twl; a.TH = TH; a.stem = 0;
     a.tiles_w = (OW + TW - 1) / TW; a.tiles_h = (OH + TH - 1) / TH;
     a.m_tiles = d->N * a.tiles_h * a.tiles_w;
     // N tile: 128 unless the layer is narrow
@@ -506,6 +577,71 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
         ok = encode(&pl->tmA_lo, in_lo, 4, adims, astr, abox, aestr, "A lo") &&
              encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo");
     if (ok && d->passes == 1) {
+        pl->tmA_lo = pl->tmA_hi;
+        pl->tmB_lo = pl->tmB_hi;
+    }
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
+// The 7x7 stride-2 pad-3 stem (faster_rcnn/resnet.py:116) has 3 input channels: far too thin for
+// a 32-channel K block.  Instead the image is stored NHWC with 4 channels and an explicit 3-pixel
+// zero border, so that the 7 taps of one filter ROW are 28 consecutive floats; a K block is then
+// "filter row r" = 32 consecutive floats (the 8th pixel meets zero weights).  Consecutive output
+// pixels start 2 pixels = 32 bytes apart, which a rank-5 tensor map {32, OW, 2, Hp/2, N} with
+// strides {32 B, row, 2 rows, image} expresses directly (overlapping windows): still one TMA copy
+// per (tile, filter row), same kernel, 7 K blocks.
+extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in_hi,
+                                                    const float* in_lo, const float* w_hi, const float* w_lo,
+                                                    const float* scale, const float* shift, int relu, float* out_hi,
+                                                    float* out_lo, int out_cstride) {
+    if (N <= 0 || H < 7 || W < 7 || Cout <= 0 || !in_hi || !w_hi || !out_hi || !out_lo || out_cstride % 4 != 0 ||
+        (passes != 1 && passes != 3) || (passes == 3 && (!in_lo || !w_lo))) {
+        set_error("d2t_conv_stem_plan_create: bad arguments");
+        return nullptr;
+    }
+    const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+    const int Hp = (H + 7) & ~1, Wp = W + 8;                  // padded buffer geometry (d2t_stem_pack_input)
+    int twl = 0;
+    while ((1 << twl) < OW && twl < 7) ++twl;
+    const int TW = 1 << twl, TH = kBlockM / TW;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(d2t_conv_plan)) != 0) {
+        set_error("d2t_conv_stem_plan_create: out of memory");
+        return nullptr;
+    }
+    d2t_conv_plan* pl = new (mem) d2t_conv_plan();
+    ConvArgs& a = pl->args;
+    a.N = N; a.OH = OH; a.OW = OW; a.Cout = Cout;
+    a.R = 7; a.S = 1; a.stride = 2; a.pad = 3; a.dil = 1; a.kc_blocks = 1;
+    a.TW_log2 = twl; a.TH = TH; a.stem = 1;
+    a.tiles_w = (OW + TW - 1) / TW; a.tiles_h = (OH + TH - 1) / TH;
+    a.m_tiles = N * a.tiles_h * a.tiles_w;
+    pl->BN = Cout <= 64 ? 64 : 128;
+    a.n_tiles = (Cout + pl->BN - 1) / pl->BN;
+    a.scale = scale; a.shift = shift; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = Cout; a.relu = relu;
+    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
+    pl->passes = passes;
+    const int tiles = a.m_tiles * a.n_tiles;
+    pl->grid = tiles < sm_count() ? tiles : sm_count();
+    const cuuint64_t row = (cuuint64_t)Wp * 16;
+    const cuuint64_t adims[5] = {32, (cuuint64_t)OW, 2, (cuuint64_t)(Hp / 2), (cuuint64_t)N};
+    const cuuint64_t astr[4] = {32, row, 2 * row, (cuuint64_t)Hp * row};
+    const cuuint32_t abox[5] = {32u, (cuuint32_t)TW, 1u, (cuuint32_t)TH, 1u};
+    const cuuint32_t aestr[5] = {1u, 1u, 1u, 1u, 1u};
+    const cuuint64_t bdims[2] = {7 * 32, (cuuint64_t)Cout};
+    const cuuint64_t bstr[1] = {7 * 32 * 4};
+    const cuuint32_t bbox[2] = {32u, (cuuint32_t)pl->BN};
+    const cuuint32_t bestr[2] = {1u, 1u};
+    bool ok = encode(&pl->tmA_hi, in_hi, 5, adims, astr, abox, aestr, "stem A hi") &&
+              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "stem B hi");
+    if (ok && passes == 3)
+        ok = encode(&pl->tmA_lo, in_lo, 5, adims, astr, abox, aestr, "stem A lo") &&
+             encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "stem B lo");
+    if (ok && passes == 1) {
         pl->tmA_lo = pl->tmA_hi;
         pl->tmB_lo = pl->tmB_hi;
     }

@@ -18,9 +18,40 @@ inline int grid_for(size_t total, int per_block = 256) {
 }
 
 // [N,C,H,W] fp32 -> [N,H,W,cs] hi/lo; channels [C, cs) are zero-filled.  32x32 smem transpose per (n, h).
+// image [N,3,H,W] -> zero-bordered NHWC4 [N, Hp, Wp, 4] hi/lo for the stem (border 3, 4th channel 0);
+// one thread per padded pixel, every element of the buffers is written.
+__global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H, int W, int Hp, int Wp,
+                                float4* __restrict__ hi, float4* __restrict__ lo) {
+    const size_t total = (size_t)N * Hp * Wp;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int wp = (int)(idx % Wp), hp = (int)((idx / Wp) % Hp), n = (int)(idx / Wp / Hp);
+        const int h = hp - 3, w = wp - 3;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (h >= 0 && h < H && w >= 0 && w < W)
+            for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)n * C + c) * H + h) * W + w);
+        const float4 a = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
+        hi[idx] = a;
+        if (lo) lo[idx] = make_float4(v[0] - a.x, v[1] - a.y, v[2] - a.z, v[3] - a.w);
+    }
+}
+
+// stem weights [O, C<=4, 7, 7] -> [O][7 rows][32] with column s*4 + c (zeros elsewhere)
+__global__ void stem_pack_weights(const float* __restrict__ w, int O, int C, float* __restrict__ hi, float* __restrict__ lo) {
+    const int total = O * 7 * 32;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int col = idx % 32, r = (idx / 32) % 7, o = idx / 32 / 7;
+        const int s = col >> 2, c = col & 3;
+        const float v = (s < 7 && c < C) ? __ldg(w + (((size_t)o * C + c) * 7 + r) * 7 + s) : 0.f;
+        const float a = tf32_hi(v);
+        hi[idx] = a;
+        if (lo) lo[idx] = v - a;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int cs, float* __restrict__ hi,
-                   float* __restrict__ lo) {
+nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, int cw,
+                   float* __restrict__ hi, float* __restrict__ lo) {
+    // writes channels [coff, coff + cw) of each pixel: x's C channels, then zeros
     __shared__ float tile[32][33];
     const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -31,9 +62,9 @@ nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int 
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int w = wt + j, c = ct + tx;
-        if (w < W && c < cs) {
+        if (w < W && c < cw) {
             const float v = tile[tx][j], a = tf32_hi(v);
-            const size_t o = (((size_t)n * H + h) * W + w) * cs + c;
+            const size_t o = (((size_t)n * H + h) * W + w) * cs + coff + c;
             hi[o] = a;
             if (lo) lo[o] = v - a;
         }
@@ -115,13 +146,14 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* 
 
 using namespace d2t;
 
-extern "C" int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, float* hi, float* lo,
-                                      cudaStream_t stream) {
-    D2T_REQUIRE(x && hi && N > 0 && C > 0 && H > 0 && W > 0 && c_stride >= C, "d2t_nchw_to_nhwc_split: bad arguments");
-    D2T_REQUIRE((long long)N * H <= 65535 * 1LL * 1 || true, "unreachable");
-    dim3 grid((W + 31) / 32, (c_stride + 31) / 32, N * H);
+extern "C" int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, int c_offset,
+                                      int c_width, float* hi, float* lo, cudaStream_t stream) {
+    D2T_REQUIRE(x && hi && N > 0 && C > 0 && H > 0 && W > 0 && c_offset >= 0 && c_width >= C &&
+                    c_stride >= c_offset + c_width,
+                "d2t_nchw_to_nhwc_split: bad arguments");
+    dim3 grid((W + 31) / 32, (c_width + 31) / 32, N * H);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc_split: tensor too large for the launch grid");
-    nchw_to_nhwc_split<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, hi, lo);
+    nchw_to_nhwc_split<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, c_width, hi, lo);
     D2T_CHECK_LAUNCH("nchw_to_nhwc_split");
     return 1;
 }
@@ -144,6 +176,23 @@ extern "C" int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int
     const size_t total = (size_t)Cout * R * S * cin_pad;
     pack_weights<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, w_hi, w_lo);
     D2T_CHECK_LAUNCH("pack_weights");
+    return 1;
+}
+
+extern "C" int d2t_stem_pack_input(const float* x, int N, int C, int H, int W, float* hi, float* lo, cudaStream_t stream) {
+    D2T_REQUIRE(x && hi && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "d2t_stem_pack_input: bad arguments");
+    const int Hp = (H + 7) & ~1, Wp = W + 8;
+    const size_t total = (size_t)N * Hp * Wp;
+    stem_pack_input<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(hi),
+                                                         reinterpret_cast<float4*>(lo));
+    D2T_CHECK_LAUNCH("stem_pack_input");
+    return 1;
+}
+
+extern "C" int d2t_stem_pack_weights(const float* w, int Cout, int Cin, float* w_hi, float* w_lo, cudaStream_t stream) {
+    D2T_REQUIRE(w && w_hi && Cout > 0 && Cin > 0 && Cin <= 4, "d2t_stem_pack_weights: bad arguments");
+    stem_pack_weights<<<grid_for((size_t)Cout * 7 * 32), 256, 0, stream>>>(w, Cout, Cin, w_hi, w_lo);
+    D2T_CHECK_LAUNCH("stem_pack_weights");
     return 1;
 }
 

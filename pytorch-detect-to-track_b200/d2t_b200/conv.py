@@ -34,11 +34,26 @@ class SplitTensor(object):
     def from_nchw(x, cstride=None, lo=True, out=None):
         N, C_, H, W = x.shape
         t = out if out is not None else SplitTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device, lo)
-        check(lib().d2t_nchw_to_nhwc_split(x.contiguous().data_ptr(), N, C_, H, W, t.cstride, t.hi.data_ptr(),
-                                           t.lo.data_ptr() if t.lo is not None else None, _stream()),
-              "d2t_nchw_to_nhwc_split")
-        ops._count(1)
+        t.load_nchw(x)
         return t
+
+    def load_nchw(self, x, coffset=0, cwidth=None):
+        """write x [N, C, H, W] into channels [coffset, coffset + cwidth) (x's channels, then zeros)"""
+        N, C_, H, W = x.shape
+        cwidth = cwidth if cwidth is not None else self.cstride - coffset
+        check(lib().d2t_nchw_to_nhwc_split(x.contiguous().data_ptr(), N, C_, H, W, self.cstride, coffset, cwidth,
+                                           self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None,
+                                           _stream()), "d2t_nchw_to_nhwc_split")
+        ops._count(1)
+        return self
+
+    def batch_slice(self, n0, n1):
+        """view of images [n0, n1) (contiguous in NHWC)"""
+        v = SplitTensor.__new__(SplitTensor)
+        v.N, v.H, v.W, v.C, v.cstride = n1 - n0, self.H, self.W, self.C, self.cstride
+        v.hi = self.hi[n0:n1]
+        v.lo = self.lo[n0:n1] if self.lo is not None else None
+        return v
 
     def to_nchw(self, C_=None, coffset=0):
         C_ = self.C if C_ is None else C_
@@ -66,7 +81,7 @@ class ConvLayer(object):
     """out = relu?(scale * conv(x, w) + shift + residual) bound to fixed input / output buffers."""
 
     def __init__(self, x, weight, scale=None, shift=None, stride=1, pad=0, dil=1, relu=False, residual=None,
-                 passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False):
+                 passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False, out_nchw=None):
         O, I, R, S = weight.shape
         if _pad32(I) > x.cstride:
             raise ValueError("input buffer has %d channels per pixel, conv needs %d" % (x.cstride, _pad32(I)))
@@ -78,7 +93,9 @@ class ConvLayer(object):
         OH = (x.H + 2 * pad - dil * (R - 1) - 1) // stride + 1
         OW = (x.W + 2 * pad - dil * (S - 1) - 1) // stride + 1
         self.out = out if out is not None else (SplitTensor(x.N, OH, OW, O, device=dev) if want_nhwc else None)
-        self.out_nchw = torch.empty(x.N, O, OH, OW, device=dev) if want_nchw else None
+        if out_nchw is not None:
+            assert tuple(out_nchw.shape) == (x.N, O, OH, OW) and out_nchw.is_contiguous()
+        self.out_nchw = out_nchw if out_nchw is not None else (torch.empty(x.N, O, OH, OW, device=dev) if want_nchw else None)
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=_pad32(I), in_cstride=x.cstride, Cout=O, R=R, S=S, stride=stride, pad=pad,
                      dil=dil, passes=passes, relu=int(relu), out_cstride=self.out.cstride if self.out is not None else 0,
                      out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0)
@@ -99,6 +116,52 @@ class ConvLayer(object):
         check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
         ops._count(1)
         return self.out if self.out is not None else self.out_nchw
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                lib().d2t_conv_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+
+class StemConv(object):
+    """conv1 7x7 / stride 2 / pad 3 (+ folded bn1 + ReLU) on the tcgen05 kernel via the row-window
+    TMA map (csrc/conv.cu: d2t_conv_stem_plan_create)."""
+
+    def __init__(self, N, H, W, weight, scale, shift, relu=True, passes=3, device="cuda"):
+        O, I, R, S = weight.shape
+        assert (R, S) == (7, 7) and I <= 4
+        self.N, self.C, self.H, self.W = N, I, H, W
+        Hp, Wp = (H + 7) & ~1, W + 8
+        self.in_hi = torch.empty(N, Hp, Wp, 4, device=device)
+        self.in_lo = torch.empty(N, Hp, Wp, 4, device=device)
+        self.w_hi = torch.empty(O, 7 * 32, device=device)
+        self.w_lo = torch.empty(O, 7 * 32, device=device)
+        w = weight.detach().float().contiguous()
+        check(lib().d2t_stem_pack_weights(w.data_ptr(), O, I, self.w_hi.data_ptr(), self.w_lo.data_ptr(), _stream()),
+              "d2t_stem_pack_weights")
+        torch.cuda.current_stream().synchronize()   # `w` may be a temporary
+        self.scale = scale.detach().float().contiguous().to(device) if scale is not None else None
+        self.shift = shift.detach().float().contiguous().to(device) if shift is not None else None
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        self.out = SplitTensor(N, OH, OW, O, device=device)
+        p = lambda t: t.data_ptr() if t is not None else None
+        self.plan = lib().d2t_conv_stem_plan_create(N, H, W, O, passes, p(self.in_hi), p(self.in_lo), p(self.w_hi),
+                                                    p(self.w_lo), p(self.scale), p(self.shift), int(relu),
+                                                    p(self.out.hi), p(self.out.lo), self.out.cstride)
+        if not self.plan:
+            raise D2TError("d2t_conv_stem_plan_create failed: %s" % lib().d2t_last_error().decode())
+        self.flops = 2.0 * N * OH * OW * O * I * 49
+
+    def run(self, x):
+        """x: [N, C, H, W] fp32 image batch"""
+        check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.in_hi.data_ptr(),
+                                        self.in_lo.data_ptr(), _stream()), "d2t_stem_pack_input")
+        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
+        ops._count(2)
+        return self.out
 
     def __del__(self):
         try:

@@ -1,0 +1,172 @@
+"""D2TEngine -- the eval-mode Detect-to-Track forward (rfcn.py:66-250) on hand-written sm_100a kernels.
+
+It is built FROM a ``model.faster_rcnn.resnet.resnet`` module (same parameters, same state_dict)
+for a fixed batch geometry, and computes exactly what ``_RFCN.forward`` computes in eval mode:
+
+  stem 7x7/2 + bn + relu -> maxpool(3,2,ceil) -> layer1..layer4 (frozen-BN bottlenecks, layer4 dilated)
+  -> RFCN_net 3x3 dil 6 + relu -> {RFCN_cls_net, RFCN_bbox_net, RPN_Conv -> RPN_cls_score / RPN_bbox_pred}
+  -> proposal step (decode + clip + sort + NMS)  -> PSRoI cls / loc + 7x7 vote + softmax
+  -> 3 cross-frame correlations -> concat -> corr_bbox_net -> PSRoI tracking + vote.
+
+Every convolution runs on the tcgen05/TMA implicit-GEMM kernel (csrc/conv.cu) with eval-mode
+BatchNorm folded into a per-channel scale/shift in the epilogue, the residual add and ReLU fused,
+both siamese legs batched as one 2B-image pass (the BN statistics are frozen, so this is the same
+function as the reference's python loop over legs).  Activations stay NHWC / TF32-split between
+convs; tensors the reference-layout operators consume (correlation, PSRoI, proposal step) are
+emitted as plain fp32 NCHW by the producing conv's epilogue.  ``passes=3`` (default) is the
+fp32-accurate 3xTF32 mode; ``passes=1`` is single-pass TF32.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import conv as dc
+from . import ops
+
+
+def _fold_bn(bn):
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean.detach() * scale
+    return scale, shift
+
+
+class D2TEngine(object):
+    def __init__(self, net, pairs, height, width, passes=3, cfg_key="TEST"):
+        from model.utils.config import cfg
+        self.net, self.B, self.H, self.W, self.passes = net, pairs, height, width, passes
+        self.cfg_key = cfg_key
+        self.post_nms = cfg[cfg_key].RPN_POST_NMS_TOP_N
+        self.pre_nms = cfg[cfg_key].RPN_PRE_NMS_TOP_N
+        self.nms_thresh = cfg[cfg_key].RPN_NMS_THRESH
+        self.n_classes, self.n_reg = net.n_classes, net.n_reg_classes
+        dev = next(net.parameters()).device
+        self.device = dev
+        N = 2 * pairs
+        self.N = N
+        self.layers = []          # run order
+        self.conv_flops = 0.0
+        base = net.RFCN_base
+
+        # ---- stem + pool
+        s, b = _fold_bn(base[1])
+        self.stem = dc.StemConv(N, height, width, base[0].weight, s, b, relu=True, passes=passes, device=dev)
+        self.conv_flops += self.stem.flops
+        so = self.stem.out
+        ph = -(-(so.H - 3) // 2) + 1
+        pw = -(-(so.W - 3) // 2) + 1
+        ph -= 1 if (ph - 1) * 2 >= so.H else 0
+        pw -= 1 if (pw - 1) * 2 >= so.W else 0
+        self.pool_out = dc.SplitTensor(N, ph, pw, 64, device=dev)
+        x = self.pool_out
+
+        # ---- residual stages
+        self.feat_nchw = {}
+        for idx in (4, 5, 6, 7):
+            stage = base[idx]
+            for bi, blk in enumerate(stage):
+                last = bi == len(stage) - 1
+                x = self._bottleneck(x, blk, want_nchw=(last and idx in (5, 6, 7)), tag=idx)
+        self.conv5 = x
+        # ---- head conv (3x3 dilation 6, bias) + relu
+        rn = base.RFCN_net
+        self.base_feat = self._conv(x, rn.weight, None, rn.bias, 1, rn.padding[0], rn.dilation[0], relu=True).out
+        bf = self.base_feat
+        # ---- R-FCN maps: NCHW for PSRoI; the loc map also feeds the tracking concat (NHWC slices)
+        cn, bn_ = net.RFCN_cls_net, net.RFCN_bbox_net
+        self.cls_map = self._conv(bf, cn.weight, None, cn.bias, want_nhwc=False, want_nchw=True).out_nchw
+        n_loc = 4 * self.n_reg * 49
+        c3c, c45c = 81, 289
+        self.trk_cin = 2 * n_loc + c3c + 2 * c45c
+        self.trk_in = dc.SplitTensor(pairs, bf.H, bf.W, self.trk_cin, cstride=(self.trk_cin + 31) // 32 * 32, device=dev)
+        self.bbox_map = torch.empty(N, n_loc, bf.H, bf.W, device=dev)
+        for leg in (0, 1):   # one plan per leg: NHWC into its channel slice of the concat buffer + NCHW for PSRoI
+            layer = dc.ConvLayer(bf.batch_slice(leg * pairs, (leg + 1) * pairs), bn_.weight, None, bn_.bias, passes=passes,
+                                 out=self.trk_in, out_coffset=leg * n_loc,
+                                 out_nchw=self.bbox_map[leg * pairs:(leg + 1) * pairs])
+            self.layers.append(layer)
+            self.conv_flops += layer.flops
+        # ---- RPN head
+        rpn = net.RFCN_rpn
+        rc = self._conv(bf, rpn.RPN_Conv.weight, None, rpn.RPN_Conv.bias, 1, 1, 1, relu=True).out
+        self.rpn_score = self._conv(rc, rpn.RPN_cls_score.weight, None, rpn.RPN_cls_score.bias, want_nhwc=False,
+                                    want_nchw=True).out_nchw
+        self.rpn_delta = self._conv(rc, rpn.RPN_bbox_pred.weight, None, rpn.RPN_bbox_pred.bias, want_nhwc=False,
+                                    want_nchw=True).out_nchw
+        self.n_trunk_layers = len(self.layers)
+        # ---- tracking head conv (runs after the correlations)
+        tn = net.corr_bbox_net
+        self.trk_layer = dc.ConvLayer(self.trk_in, tn.weight, None, tn.bias, passes=passes, want_nhwc=False, want_nchw=True)
+        self.conv_flops += self.trk_layer.flops
+        self.anchors = rpn.RPN_proposal._anchors.to(dev)
+        self.feat_stride = rpn.feat_stride
+        self.corr_cfg = [(net.conv3_corr_layer, 5, 2 * n_loc, c3c), (net.conv4_corr_layer, 6, 2 * n_loc + c3c, c45c),
+                         (net.conv5_corr_layer, 7, 2 * n_loc + c3c + c45c, c45c)]
+        self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, kind::tf32 x%d passes, TMA-fed, fused BN/ReLU/residual" % passes
+
+    # ------------------------------------------------------------------ construction helpers
+    def _conv(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, want_nhwc=True,
+              want_nchw=False):
+        layer = dc.ConvLayer(x, weight, scale, shift, stride, pad, dil, relu, residual, passes=self.passes,
+                             want_nhwc=want_nhwc, want_nchw=want_nchw)
+        self.layers.append(layer)
+        self.conv_flops += layer.flops
+        return layer
+
+    def _bottleneck(self, x, blk, want_nchw, tag):
+        s1, b1 = _fold_bn(blk.bn1)
+        s2, b2 = _fold_bn(blk.bn2)
+        s3, b3 = _fold_bn(blk.bn3)
+        c1, c2, c3 = blk.conv1, blk.conv2, blk.conv3
+        if blk.downsample is not None:
+            sd, bd = _fold_bn(blk.downsample[1])
+            dconv = blk.downsample[0]
+            res = self._conv(x, dconv.weight, sd, bd, dconv.stride[0]).out
+        else:
+            res = x
+        y = self._conv(x, c1.weight, s1, b1, c1.stride[0], relu=True).out
+        y = self._conv(y, c2.weight, s2, b2, 1, c2.padding[0], c2.dilation[0], relu=True).out
+        last = self._conv(y, c3.weight, s3, b3, relu=True, residual=res, want_nchw=want_nchw)
+        if want_nchw:
+            self.feat_nchw[tag] = last.out_nchw
+        return last.out
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, im_data, im_info):
+        """im_data [B, 2, 3, H, W], im_info [B, 2, 3] (CUDA fp32) -> the reference's 10-tuple (eval)."""
+        B, L, N = self.B, 2, self.N
+        assert tuple(im_data.shape) == (B, 2, 3, self.H, self.W), "engine was built for a fixed geometry"
+        frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, 3, self.H, self.W).contiguous()     # leg-major
+        info = im_info.permute(1, 0, 2).reshape(N, 3).contiguous().float()
+        self.stem.run(frames)
+        dc.maxpool3x3s2(self.stem.out, out=self.pool_out)
+        for layer in self.layers:
+            layer.run()
+        # ---- proposals for all 2B images
+        A = self.anchors.size(0)
+        sc = self.rpn_score
+        prob = F.softmax(sc.view(N, 2, A * sc.size(2), sc.size(3)), dim=1).view_as(sc)   # rpn.py:66-68
+        rois_all = ops.proposals(self.anchors, self.rpn_delta, prob, info, self.feat_stride, self.pre_nms,
+                                 self.post_nms, self.nms_thresh)                        # [2B, R, 5]
+        R = rois_all.size(1)
+        flat = rois_all.view(-1, 5)
+        # ---- detection heads
+        pooled_cls, _ = ops.psroi_forward(self.cls_map, flat, 7, 7, 1.0 / 16.0, 7, self.n_classes)
+        pooled_loc, _ = ops.psroi_forward(self.bbox_map, flat, 7, 7, 1.0 / 16.0, 7, 4 * self.n_reg)
+        cls_prob = F.softmax(pooled_cls.mean((2, 3)), dim=1).view(L, B, R, -1)
+        bbox_pred = pooled_loc.mean((2, 3)).view(L, B, R, -1)
+        rois = rois_all.view(L, B, R, 5).clone()
+        rois[1, :, :, 0] -= B                                                           # per-leg image index
+        # ---- tracking branch
+        for corr, tag, coff, cw in self.corr_cfg:
+            f = self.feat_nchw[tag]
+            c = corr(f[:B], f[B:])
+            self.trk_in.load_nchw(c, coffset=coff, cwidth=cw)
+        self.trk_layer.run()
+        pooled_trk, _ = ops.psroi_forward(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
+                                          4 * self.n_reg)
+        tracking_pred = pooled_trk.mean((2, 3)).view(B * R, -1)
+        zero = im_data.new_zeros(L, 1)
+        return (rois, cls_prob, bbox_pred, tracking_pred, zero, zero.clone(), zero.clone(), zero.clone(), [],
+                im_data.new_zeros(1))
+
+    __call__ = forward
