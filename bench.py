@@ -151,16 +151,21 @@ def op_microbench(flush, hbm_gbs):
                                       "corr_conv3": (512, 75, 125, (8, 1, 8, 2, 2), 2)}.items():
         a, b = torch.randn(Bc, C_, Hh, Ww, device="cuda"), torch.randn(Bc, C_, Hh, Ww, device="cuda")
         oc, oh, ow = ops.correlation_shape(Hh, Ww, *p)
+        from d2t_b200 import conv as dc
+        # tensor-core kernel on the engine's native layout (split NHWC in, NCHW out) ...
+        layer = dc.CorrLayer(dc.SplitTensor.from_nchw(a), dc.SplitTensor.from_nchw(b), p[0], p[2], p[3], passes=3, want_nchw=True)
+        ms = time_kernel(layer.run, 20, flush)
+        # ... through the reference-layout operator (adds the two NCHW -> split-NHWC re-layouts) ...
+        ms_api = time_kernel(lambda: ops.correlation_forward(a, b, *p), 10, flush)
+        # ... and the fp32 SIMT kernel it replaced
         o = torch.empty(Bc, oc, oh, ow, device="cuda")
-
-        def corr():
-            lib().d2t_correlation_forward(a.data_ptr(), b.data_ptr(), Bc, C_, Hh, Ww, *p, o.data_ptr(), st)
-        ms = time_kernel(corr, 20, flush)
+        ms_simt = time_kernel(lambda: lib().d2t_correlation_forward(a.data_ptr(), b.data_ptr(), Bc, C_, Hh, Ww, *p, o.data_ptr(), st), 5, flush)
         touched = (oh * ow) if p[3] > 1 else Hh * Ww      # stride-2 lattice reads 1/4 of the elements
         alg = 4.0 * (2 * C_ * touched + oc * oh * ow) * Bc
         flops = 2.0 * oc * oh * ow * C_ * Bc
         out[name] = {"batch": Bc, "ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6,
-                     "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_fp32": flops / ms / 1e9}
+                     "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_useful": flops / ms / 1e9,
+                     "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
     for n in (6000, 12000):
         dets = torch.from_numpy(np.stack([common.make_dets(n, seed=22 + i) for i in range(4)])).cuda()
         ms = time_kernel(lambda: ops.nms_batched(dets, 0.7, max_keep=300 if n == 6000 else 2000), 10, flush)

@@ -217,6 +217,16 @@ void d2t_conv_plan_destroy(d2t_conv_plan* plan);
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);
 int d2t_conv_plan_run(const d2t_conv_plan* plan, cudaStream_t stream);
 
+/* Cross-frame correlation (correlation/src/correlation_cuda_kernel.cu:34-106) for kernel_size 1,
+ * stride1 == stride2 = stride, 1 <= max_displacement/stride <= 8, on the same tensor-core pipeline:
+ * in1 / in2 are split NHWC [N, H, W, in_cstride] (C % 32 == 0 channels read, c_real of them
+ * meaningful: the divisor); the (2r+1)^2-channel result goes to
+ * channels [out_coffset, ...) of a split NHWC buffer and/or to a plain fp32 NCHW tensor. */
+d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int in_cstride, int pad, int max_displacement,
+                                    int stride, int passes, const float* in1_hi, const float* in1_lo,
+                                    const float* in2_hi, const float* in2_lo, float* out_hi, float* out_lo,
+                                    int out_cstride, int out_coffset, float* out_nchw);
+
 /* OIHW fp32 -> [Cout][R*S][cin_pad] hi / lo (lo may be NULL) */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
                           float* w_hi, float* w_lo, cudaStream_t stream);

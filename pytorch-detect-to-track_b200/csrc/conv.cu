@@ -68,6 +68,9 @@ struct ConvArgs {
     float* out_lo;
     int out_cstride, out_coffset;
     float* out_nchw;               // plain fp32 [N, Cout, OH, OW] or null
+    // correlation mode (CORR): B operand = halo rows of the second frame, see corr section below
+    int corr_r, corr_D;            // displacement radius (lattice units) and 2r+1
+    float corr_nelems;             // kernel_size^2 * C
 };
 
 template <int BN, int PASSES>
@@ -154,7 +157,14 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int PASSES>
+// CORR = true turns the same pipeline into the cross-frame correlation (correlation/src/
+// correlation_cuda_kernel.cu:34-106, kernel_size 1, stride1 == stride2): for a tile of 8x16 positions p of
+// frame t and a chunk of 4x32 "halo" positions q of frame t+tau, D[p, q] = sum_c in1[p, c] * in2[q, c] is
+// a Gram block -- a GEMM whose B operand is a second 4-D activation box instead of a weight tile.  The
+// (2r+1)^2 displacements of p are the q with |q - p| <= r in both axes; the epilogue keeps those (38 % of the
+// block for r = 8) and writes out[n, (tj+r)*D + (ti+r), y, x] = D / C.  Zero padding outside the frame is
+// again the TMA out-of-bounds fill; strided correlation (conv3: stride 2) is the TMA element stride.
+template <int BN, int PASSES, bool CORR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -235,7 +245,17 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                     tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
                                                 ih0 + r * p.dil, img);
                             }
-                            if (PASSES == 3) {
+                            if (CORR) {
+                                // chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
+                                const int bw0 = ((tw << p.TW_log2) - p.corr_r) * p.stride - p.pad;
+                                const int bh0 = (th * p.TH - p.corr_r + 4 * n_tile) * p.stride - p.pad;
+                                if (PASSES == 3) {
+                                    tma_load_4d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
+                                    tma_load_4d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kc * kBlockK, bw0, bh0, img);
+                                } else {
+                                    tma_load_4d(st + C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
+                                }
+                            } else if (PASSES == 3) {
                                 tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
                                 tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
                             } else {
@@ -359,6 +379,31 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 mbar_arrive(&xempty[xacc]);
             }
             // ---- from here on the tile lives in registers; the tensor core is already on the next tile
+            if constexpr (CORR) {
+                // tile row m = position (yl, xl) of the 8x16 tile; column n = halo (rl, cl) of this 4x32 chunk
+                const int r = p.corr_r, D = p.corr_D;
+#pragma unroll
+                for (int rl = 0; rl < BN / 32; ++rl) {
+                    const int tjr = 4 * n_tile + rl - hl;            // tj + r
+                    if (!pix_ok || tjr < 0 || tjr >= D) continue;
+                    const int tc0 = tjr * D - wl;                    // channel of column cl is tc0 + cl
+#pragma unroll
+                    for (int cl = 0; cl < 32; ++cl) {
+                        const int tir = cl - wl;                     // ti + r
+                        if (tir < 0 || tir >= D) continue;
+                        const float val = __fdiv_rn(acc[rl * 32 + cl], p.corr_nelems);   // kernel.cu:100
+                        if (p.out_nchw)
+                            p.out_nchw[(((size_t)img * D * D + tc0 + cl) * p.OH + oh) * p.OW + ow] = val;
+                        if (p.out_hi) {
+                            const size_t o = pix * p.out_cstride + p.out_coffset + tc0 + cl;
+                            const float h = __uint_as_float(__float_as_uint(val) & 0xffffe000u);
+                            p.out_hi[o] = h;
+                            p.out_lo[o] = val - h;
+                        }
+                    }
+                }
+                (void)r;
+            } else {
 #pragma unroll
             for (int c = 0; c < BN / 16; ++c) {
                 float* v = acc + c * 16;
@@ -424,6 +469,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                 }
             }
+            }   // !CORR
         }
     }
     tc_fence_before();
@@ -477,16 +523,16 @@ struct d2t_conv_plan {
     alignas(64) CUtensorMap tmB_hi;
     alignas(64) CUtensorMap tmB_lo;
     ConvArgs args;
-    int BN, passes, grid;
+    int BN, passes, grid, corr;
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool CORR>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     using C = Cfg<BN, PASSES>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm_tf32<BN, PASSES>, C::SMEM_BYTES, "conv smem attr")) return 0;
-    conv_igemm_tf32<BN, PASSES><<<pl->grid, kThreads, C::SMEM_BYTES, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                             pl->tmB_lo, pl->args);
+    if (!once.ensure(conv_igemm_tf32<BN, PASSES, CORR>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    conv_igemm_tf32<BN, PASSES, CORR><<<pl->grid, kThreads, C::SMEM_BYTES, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
+                                                                                   pl->tmB_lo, pl->args);
     D2T_CHECK_LAUNCH("conv_igemm_tf32");
     return 1;
 }
@@ -554,7 +600,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.relu = d->relu;
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
-    pl->passes = d->passes;
+    pl->passes = d->passes; pl->corr = 0;
     const int tiles = a.m_tiles * a.n_tiles;
     pl->grid = tiles < sm_count() ? tiles : sm_count();
 
@@ -624,7 +670,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.n_tiles = (Cout + pl->BN - 1) / pl->BN;
     a.scale = scale; a.shift = shift; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
-    pl->passes = passes;
+    pl->passes = passes; pl->corr = 0;
     const int tiles = a.m_tiles * a.n_tiles;
     pl->grid = tiles < sm_count() ? tiles : sm_count();
     const cuuint64_t row = (cuuint64_t)Wp * 16;
@@ -652,6 +698,68 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     return pl;
 }
 
+extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int in_cstride, int pad, int md, int stride,
+                                               int passes, const float* in1_hi, const float* in1_lo,
+                                               const float* in2_hi, const float* in2_lo, float* out_hi, float* out_lo,
+                                               int out_cstride, int out_coffset, float* out_nchw) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || md < 0 || stride <= 0 || !in1_hi || !in2_hi ||
+        (passes != 1 && passes != 3) || (passes == 3 && (!in1_lo || !in2_lo)) || (!out_hi && !out_nchw) ||
+        (out_hi && !out_lo)) {
+        set_error("d2t_corr_plan_create: bad arguments");
+        return nullptr;
+    }
+    const int r = md / stride;
+    if (C % kBlockK != 0 || in_cstride % 4 != 0 || in_cstride < C || r > 8 || r < 1) {
+        set_error("d2t_corr_plan_create: needs C %% 32 == 0, 16-byte pixel stride and 1 <= max_displacement/stride2 <= 8");
+        return nullptr;
+    }
+    const int nh = H + 2 * pad - 2 * md, nw = W + 2 * pad - 2 * md;   // correlation_cuda.c:33-34, kernel_size 1
+    if (nh <= 0 || nw <= 0) {
+        set_error("d2t_corr_plan_create: empty output");
+        return nullptr;
+    }
+    const int OH = (nh + stride - 1) / stride, OW = (nw + stride - 1) / stride;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(d2t_conv_plan)) != 0) {
+        set_error("d2t_corr_plan_create: out of memory");
+        return nullptr;
+    }
+    d2t_conv_plan* pl = new (mem) d2t_conv_plan();
+    ConvArgs& a = pl->args;
+    a.N = N; a.OH = OH; a.OW = OW; a.Cout = (2 * r + 1) * (2 * r + 1);
+    a.R = 1; a.S = 1; a.stride = stride; a.pad = pad - md; a.dil = 1;       // element = lattice*stride + (md - pad)
+    a.kc_blocks = C / kBlockK;
+    a.TW_log2 = 4; a.TH = 8; a.stem = 0;
+    a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 7) / 8;
+    a.m_tiles = N * a.tiles_h * a.tiles_w;
+    a.n_tiles = (8 + 2 * r + 3) / 4;                                         // halo chunks of 4 rows
+    a.scale = nullptr; a.shift = nullptr; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = 0; a.relu = 0;
+    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
+    a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
+    pl->BN = 128; pl->passes = passes; pl->corr = 1;
+    const int tiles = a.m_tiles * a.n_tiles;
+    pl->grid = tiles < sm_count() ? tiles : sm_count();
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t str[3] = {(cuuint64_t)in_cstride * 4, (cuuint64_t)W * in_cstride * 4, (cuuint64_t)H * W * in_cstride * 4};
+    const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(15 * stride + 1), (cuuint32_t)(7 * stride + 1), 1u};
+    const cuuint32_t bbox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(31 * stride + 1), (cuuint32_t)(3 * stride + 1), 1u};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    bool ok = encode(&pl->tmA_hi, in1_hi, 4, dims, str, abox, estr, "corr A hi") &&
+              encode(&pl->tmB_hi, in2_hi, 4, dims, str, bbox, estr, "corr B hi");
+    if (ok && passes == 3)
+        ok = encode(&pl->tmA_lo, in1_lo, 4, dims, str, abox, estr, "corr A lo") &&
+             encode(&pl->tmB_lo, in2_lo, 4, dims, str, bbox, estr, "corr B lo");
+    if (ok && passes == 1) {
+        pl->tmA_lo = pl->tmA_hi;
+        pl->tmB_lo = pl->tmB_hi;
+    }
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
 extern "C" void d2t_conv_plan_destroy(d2t_conv_plan* pl) {
     if (pl) free(pl);
 }
@@ -665,6 +773,7 @@ extern "C" int d2t_conv_plan_info(const d2t_conv_plan* pl, int* out8) {
 
 extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
     D2T_REQUIRE(pl, "d2t_conv_plan_run: null plan");
-    if (pl->passes == 3) return pl->BN == 64 ? launch_conv<64, 3>(pl, stream) : launch_conv<128, 3>(pl, stream);
-    return pl->BN == 64 ? launch_conv<64, 1>(pl, stream) : launch_conv<128, 1>(pl, stream);
+    if (pl->corr) return pl->passes == 3 ? launch_conv<128, 3, true>(pl, stream) : launch_conv<128, 1, true>(pl, stream);
+    if (pl->passes == 3) return pl->BN == 64 ? launch_conv<64, 3, false>(pl, stream) : launch_conv<128, 3, false>(pl, stream);
+    return pl->BN == 64 ? launch_conv<64, 1, false>(pl, stream) : launch_conv<128, 1, false>(pl, stream);
 }

@@ -59,6 +59,7 @@ _SIGS = {
     # ---- convolution engine
     "d2t_conv_plan_create": (_p, [_p] * 12),
     "d2t_conv_plan_destroy": (None, [_p]),
+    "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 6 + [_i, _i, _p]),
     "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),
     "d2t_conv_plan_run": (_i, [_p, _p]),
     "d2t_conv_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -172,6 +172,35 @@ class StemConv(object):
             pass
 
 
+class CorrLayer(object):
+    """Cross-frame correlation (kernel_size 1, stride1 == stride2) of two split NHWC tensors on the
+    tensor cores; writes a channel slice of `out` (split NHWC) and/or a plain NCHW tensor."""
+
+    def __init__(self, x1, x2, pad, md, stride, passes=3, out=None, out_coffset=0, want_nchw=False):
+        assert (x1.N, x1.H, x1.W, x1.cstride) == (x2.N, x2.H, x2.W, x2.cstride)
+        r = md // stride
+        self.D = 2 * r + 1
+        oh = -(-(x1.H + 2 * pad - 2 * md) // stride)
+        ow = -(-(x1.W + 2 * pad - 2 * md) // stride)
+        self.x1, self.x2, self.out = x1, x2, out
+        self.out_nchw = torch.empty(x1.N, self.D * self.D, oh, ow, device=x1.hi.device) if want_nchw else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        self.plan = lib().d2t_corr_plan_create(x1.N, _pad32(x1.C), x1.C, x1.H, x1.W, x1.cstride, pad, md, stride, passes,
+                                               p(x1.hi), p(x1.lo), p(x2.hi), p(x2.lo),
+                                               p(out.hi) if out is not None else None, p(out.lo) if out is not None else None,
+                                               out.cstride if out is not None else 0, out_coffset, p(self.out_nchw))
+        if not self.plan:
+            raise D2TError("d2t_corr_plan_create failed: %s" % lib().d2t_last_error().decode())
+        self.flops = 2.0 * x1.N * oh * ow * self.D * self.D * x1.C
+
+    def run(self):
+        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
+        ops._count(1)
+        return self.out_nchw if self.out_nchw is not None else self.out
+
+    __del__ = ConvLayer.__del__
+
+
 def maxpool3x3s2(x, out=None):
     OH = -(-(x.H - 3) // 2) + 1
     OW = -(-(x.W - 3) // 2) + 1

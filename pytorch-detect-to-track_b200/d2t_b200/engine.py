@@ -30,10 +30,11 @@ def _fold_bn(bn):
 
 
 class D2TEngine(object):
-    def __init__(self, net, pairs, height, width, passes=3, cfg_key="TEST"):
+    def __init__(self, net, pairs, height, width, passes=3, cfg_key="TEST", keep_features=False):
         from model.utils.config import cfg
         self.net, self.B, self.H, self.W, self.passes = net, pairs, height, width, passes
         self.cfg_key = cfg_key
+        self.keep_features = keep_features   # also emit conv3/4/5 as plain NCHW (tests / inspection)
         self.post_nms = cfg[cfg_key].RPN_POST_NMS_TOP_N
         self.pre_nms = cfg[cfg_key].RPN_PRE_NMS_TOP_N
         self.nms_thresh = cfg[cfg_key].RPN_NMS_THRESH
@@ -59,12 +60,12 @@ class D2TEngine(object):
         x = self.pool_out
 
         # ---- residual stages
-        self.feat_nchw = {}
+        self.feat_nchw, self.feat_nhwc = {}, {}
         for idx in (4, 5, 6, 7):
             stage = base[idx]
             for bi, blk in enumerate(stage):
                 last = bi == len(stage) - 1
-                x = self._bottleneck(x, blk, want_nchw=(last and idx in (5, 6, 7)), tag=idx)
+                x = self._bottleneck(x, blk, feature=(last and idx in (5, 6, 7)), tag=idx)
         self.conv5 = x
         # ---- head conv (3x3 dilation 6, bias) + relu
         rn = base.RFCN_net
@@ -98,8 +99,15 @@ class D2TEngine(object):
         self.conv_flops += self.trk_layer.flops
         self.anchors = rpn.RPN_proposal._anchors.to(dev)
         self.feat_stride = rpn.feat_stride
-        self.corr_cfg = [(net.conv3_corr_layer, 5, 2 * n_loc, c3c), (net.conv4_corr_layer, 6, 2 * n_loc + c3c, c45c),
-                         (net.conv5_corr_layer, 7, 2 * n_loc + c3c + c45c, c45c)]
+        # ---- correlations: straight from the NHWC split features of the two legs into the concat buffer
+        self.corr_layers = []
+        for corr, tag, coff in ((net.conv3_corr_layer, 5, 2 * n_loc), (net.conv4_corr_layer, 6, 2 * n_loc + c3c),
+                                (net.conv5_corr_layer, 7, 2 * n_loc + c3c + c45c)):
+            f = self.feat_nhwc[tag]
+            assert corr.kernel_size == 1 and corr.stride1 == corr.stride2
+            self.corr_layers.append(dc.CorrLayer(f.batch_slice(0, pairs), f.batch_slice(pairs, N), corr.pad_size,
+                                                 corr.max_displacement, corr.stride1, passes=passes, out=self.trk_in,
+                                                 out_coffset=coff))
         self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, kind::tf32 x%d passes, TMA-fed, fused BN/ReLU/residual" % passes
 
     # ------------------------------------------------------------------ construction helpers
@@ -111,7 +119,8 @@ class D2TEngine(object):
         self.conv_flops += layer.flops
         return layer
 
-    def _bottleneck(self, x, blk, want_nchw, tag):
+    def _bottleneck(self, x, blk, feature, tag):
+        want_nchw = feature and self.keep_features
         s1, b1 = _fold_bn(blk.bn1)
         s2, b2 = _fold_bn(blk.bn2)
         s3, b3 = _fold_bn(blk.bn3)
@@ -125,8 +134,10 @@ class D2TEngine(object):
         y = self._conv(x, c1.weight, s1, b1, c1.stride[0], relu=True).out
         y = self._conv(y, c2.weight, s2, b2, 1, c2.padding[0], c2.dilation[0], relu=True).out
         last = self._conv(y, c3.weight, s3, b3, relu=True, residual=res, want_nchw=want_nchw)
-        if want_nchw:
-            self.feat_nchw[tag] = last.out_nchw
+        if feature:
+            self.feat_nhwc[tag] = last.out
+            if want_nchw:
+                self.feat_nchw[tag] = last.out_nchw
         return last.out
 
     # ------------------------------------------------------------------ forward
@@ -157,10 +168,8 @@ class D2TEngine(object):
         rois = rois_all.view(L, B, R, 5).clone()
         rois[1, :, :, 0] -= B                                                           # per-leg image index
         # ---- tracking branch
-        for corr, tag, coff, cw in self.corr_cfg:
-            f = self.feat_nchw[tag]
-            c = corr(f[:B], f[B:])
-            self.trk_in.load_nchw(c, coffset=coff, cwidth=cw)
+        for layer in self.corr_layers:
+            layer.run()
         self.trk_layer.run()
         pooled_trk, _ = ops.psroi_forward(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
                                           4 * self.n_reg)

@@ -13,7 +13,7 @@ B, H, W = 2, 224, 320
 g = torch.Generator().manual_seed(1)
 im_data = (torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128).cuda()
 im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
-eng = D2TEngine(net, B, H, W, passes=3)
+eng = D2TEngine(net, B, H, W, passes=3, keep_features=True)
 out = eng(im_data, im_info)
 rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
 with torch.no_grad():

@@ -117,7 +117,7 @@ def test_engine_matches_torch_graph():
     g = torch.Generator().manual_seed(1)
     im_data = (torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128).cuda()
     im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
-    eng = D2TEngine(net, B, H, W, passes=3)
+    eng = D2TEngine(net, B, H, W, passes=3, keep_features=True)
     out = eng(im_data, im_info)
     with torch.no_grad():
         frames = im_data.permute(1, 0, 2, 3, 4).reshape(2 * B, 3, H, W)
@@ -142,3 +142,27 @@ def test_engine_matches_torch_graph():
     sel0 = same[0].reshape(-1)
     d = (out[3][sel0] - ref[3][sel0]).abs().max() / ref[3].abs().max()
     assert float(d) < 1e-4, float(d)
+
+
+@pytest.mark.parametrize("C,H,W,p,B", [(64, 20, 30, (8, 1, 8, 1, 1), 2), (1024, 38, 63, (8, 1, 8, 1, 1), 2),
+                                       (512, 75, 125, (8, 1, 8, 2, 2), 1), (2048, 38, 63, (8, 1, 8, 1, 1), 1),
+                                       (96, 21, 27, (4, 1, 4, 1, 1), 1), (40, 13, 50, (0, 1, 3, 1, 1), 1)])
+def test_tensor_core_correlation(C, H, W, p, B):
+    """CORR mode of the tcgen05 kernel against the reference kernel itself (or the fp32 SIMT kernel)."""
+    from d2t_b200 import ops
+    from oracle import ref_cuda
+    g = torch.Generator(device="cuda").manual_seed(77)
+    a = torch.randn(B, C, H, W, device="cuda", generator=g)
+    b = torch.randn(B, C, H, W, device="cuda", generator=g)
+    out = ops.correlation_forward(a, b, *p)
+    ops.TENSOR_CORE_CORRELATION = False
+    try:
+        simt = ops.correlation_forward(a, b, *p)
+    finally:
+        ops.TENSOR_CORE_CORRELATION = True
+    assert out.shape == simt.shape
+    ref = ref_cuda.correlation_forward(a, b, *p) if ref_cuda.available() else simt
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print("corr", (C, H, W, p), "max rel err vs reference kernel %.2e" % err)
+    assert err < 2e-5, err
+    assert float((simt - ref).abs().max() / ref.abs().max()) < 1e-4
