@@ -37,6 +37,7 @@
 //              PSRoI, the proposal step) -- all while the tensor core is already on the next tile.
 #include <cuda.h>
 
+#include <atomic>
 #include <new>
 
 #include "common.cuh"
@@ -47,8 +48,9 @@ namespace {
 constexpr int kBlockM = 128;       // output pixels per tile (TMEM lanes)
 constexpr int kBlockK = 32;        // fp32 elements per K block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA K step
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;       // warps 4..7 are the epilogue (warp % 4 = TMEM lane quarter)
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;       // warps 4..11 are the epilogue: two groups of 4 (warp % 4 = TMEM lane quarter),
+constexpr int kEpiThreads = 256;   // group g owns columns [g*BN/2, (g+1)*BN/2) of the tile
 constexpr int kChunkK = 8;         // k-blocks accumulated in TMEM before the partial sum moves to registers
 
 struct ConvArgs {
@@ -71,6 +73,58 @@ struct ConvArgs {
     // correlation mode (CORR): B operand = halo rows of the second frame, see corr section below
     int corr_r, corr_D;            // displacement radius (lattice units) and 2r+1
     float corr_nelems;             // kernel_size^2 * C
+    // stream-K fix-up (see Sched): per-CTA partial tiles [grid][BN][128] and their "published" flags
+    float* sk_scratch;
+    int* sk_flags;
+    int sk_epoch;
+};
+
+// Work distribution ("stream-K").  A layer is tiles x cpt units, a unit = one K chunk (kChunkK k-blocks) of
+// one output tile.  CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G): every CTA gets the same amount of
+// tensor-core work (+-1 chunk) whatever the tile count -- with whole tiles, 152 or 304 tiles on 148 SMs cost
+// 2 or 3 rounds for 1.03 or 2.05 rounds of work.  A tile split across CTAs is finished by the CTA holding its
+// LAST chunk: the others publish their fp32 partial tile (registers -> L2-resident scratch) and the finisher
+// adds them in k order (deterministic) before the fused epilogue.  A CTA runs its trailing partial tile
+// FIRST and its leading partial tile LAST, so a finisher never waits on a partial that is not long published,
+// and waits only ever point to lower CTA indices (all CTAs are co-resident: grid <= #SMs, 1 CTA/SM).
+struct Seg {
+    int tile, c0, c1, role;        // chunks [c0, c1) of `tile`; role 0 = whole tile, 1 = publish partial, 2 = finish
+};
+struct Sched {
+    int cpt, nseg, first_tile, tail_pub, head_fin;
+    long long u0, u1;
+    __device__ Sched(int tiles, int k_iters, int cta, int G) {
+        cpt = (k_iters + kChunkK - 1) / kChunkK;
+        const long long U = (long long)tiles * cpt;
+        u0 = U * cta / G;
+        u1 = U * (cta + 1) / G;
+        nseg = 0; first_tile = 0; tail_pub = 0; head_fin = 0;
+        if (u1 > u0) {
+            first_tile = (int)(u0 / cpt);
+            const int last_tile = (int)((u1 - 1) / cpt);
+            nseg = last_tile - first_tile + 1;
+            tail_pub = (u1 - (long long)last_tile * cpt) < cpt;
+            head_fin = (u0 - (long long)first_tile * cpt) > 0 && (nseg > 1 || !tail_pub);
+        }
+    }
+    __device__ Seg get(int e) const {          // e-th segment in EXECUTION order
+        int nat;
+        int e2 = e;
+        if (tail_pub && e == 0) {
+            nat = nseg - 1;
+        } else {
+            if (tail_pub) e2 = e - 1;
+            const int mid = (tail_pub ? nseg - 1 : nseg) - head_fin;
+            nat = e2 < mid ? e2 + head_fin : 0;
+        }
+        Seg g;
+        g.tile = first_tile + nat;
+        const long long base = (long long)g.tile * cpt;
+        g.c0 = (int)((u0 > base ? u0 : base) - base);
+        g.c1 = (int)((u1 < base + cpt ? u1 : base + cpt) - base);
+        g.role = g.c1 < cpt ? 1 : (g.c0 > 0 ? 2 : 0);
+        return g;
+    }
 };
 
 template <int BN, int PASSES>
@@ -81,7 +135,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int OUT_STAGE_BYTES = 2 * kBlockM * 128;        // one [128 x 32] fp32 slab per epilogue group (TMA store)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
     static constexpr int TMEM_COLS = (PASSES == 3 ? 4 : 2) * BN;      // power of two >= 32 for BN in {64,128}
 };
@@ -107,6 +162,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -168,12 +231,14 @@ template <int BN, int PASSES, bool CORR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                 const ConvArgs p) {
     using C = Cfg<BN, PASSES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;                   // [2 groups][128 rows][128 B], swizzled
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_STAGE_BYTES);
     uint64_t* full = bars;                        // [STAGES]   TMA -> MMA
     uint64_t* empty = bars + C::STAGES;           // [STAGES]   MMA -> TMA
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue: chunk buffer complete
@@ -192,6 +257,10 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             prefetch_tmap(&tmA_lo);
             prefetch_tmap(&tmB_lo);
         }
+        if (!CORR && p.out_hi) {
+            prefetch_tmap(&tmO_hi);
+            prefetch_tmap(&tmO_lo);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
@@ -200,8 +269,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4 * 32);
-            mbar_init(&xempty[i], 4 * 32);
+            mbar_init(&tempty[i], kEpiThreads);
+            mbar_init(&xempty[i], kEpiThreads);
         }
         fence_mbar_init();
     }
@@ -214,58 +283,61 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const Sched sched(tiles, k_iters, blockIdx.x, gridDim.x);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int e = 0; e < sched.nseg; ++e) {
+                const Seg sg = sched.get(e);
+                const int t = sg.tile;
                 const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
                 const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
                 const int iw0 = (tw << p.TW_log2) * p.stride - p.pad, ih0 = th * p.TH * p.stride - p.pad;
                 const int n0 = n_tile * BN;
-                for (int r = 0; r < p.R; ++r)
-                    for (int s = 0; s < p.S; ++s)
-                        for (int kc = 0; kc < p.kc_blocks; ++kc) {
-                            mbar_wait_sleep(&empty[stage], phase ^ 1);
-                            uint8_t* st = smem + stage * C::STAGE_BYTES;
-                            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                            const int kcol = ((r * p.S + s) * p.kc_blocks + kc) * kBlockK;
-                            if (p.stem) {
-                                // filter row r of the stem: 32 consecutive floats (8 pixels x 4 channels) of padded
-                                // input row 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
-                                const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
-                                tma_load_5d(st, &tmA_hi, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
-                                if (PASSES == 3)
-                                    tma_load_5d(st + C::A_BYTES, &tmA_lo, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
-                            } else {
-                                tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
-                                if (PASSES == 3)
-                                    tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
-                                                ih0 + r * p.dil, img);
-                            }
-                            if (CORR) {
-                                // chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
-                                const int bw0 = ((tw << p.TW_log2) - p.corr_r) * p.stride - p.pad;
-                                const int bh0 = (th * p.TH - p.corr_r + 4 * n_tile) * p.stride - p.pad;
-                                if (PASSES == 3) {
-                                    tma_load_4d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
-                                    tma_load_4d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kc * kBlockK, bw0, bh0, img);
-                                } else {
-                                    tma_load_4d(st + C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
-                                }
-                            } else if (PASSES == 3) {
-                                tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
-                                tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
-                            } else {
-                                tma_load_2d(st + C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
-                            }
-                            if (++stage == C::STAGES) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
+                const int k_end = min(sg.c1 * kChunkK, k_iters);
+                for (int k = sg.c0 * kChunkK; k < k_end; ++k) {
+                    const int kc = k % p.kc_blocks, rs = k / p.kc_blocks, s = rs % p.S, r = rs / p.S;
+                    mbar_wait_sleep(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    const int kcol = k * kBlockK;
+                    if (p.stem) {
+                        // filter row r of the stem: 32 consecutive floats (8 pixels x 4 channels) of padded
+                        // input row 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
+                        const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
+                        tma_load_5d(st, &tmA_hi, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
+                        if (PASSES == 3)
+                            tma_load_5d(st + C::A_BYTES, &tmA_lo, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
+                    } else {
+                        tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        if (PASSES == 3)
+                            tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
+                                        ih0 + r * p.dil, img);
+                    }
+                    if (CORR) {
+                        // chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
+                        const int bw0 = ((tw << p.TW_log2) - p.corr_r) * p.stride - p.pad;
+                        const int bh0 = (th * p.TH - p.corr_r + 4 * n_tile) * p.stride - p.pad;
+                        if (PASSES == 3) {
+                            tma_load_4d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
+                            tma_load_4d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kc * kBlockK, bw0, bh0, img);
+                        } else {
+                            tma_load_4d(st + C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
                         }
+                    } else if (PASSES == 3) {
+                        tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
+                        tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
+                    } else {
+                        tma_load_2d(st + C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
+                    }
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -281,14 +353,16 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             constexpr uint32_t idesc = make_idesc<BN>();
             int stage = 0, cbuf = 0, local = 0;
             uint32_t phase = 0, cphase = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+            for (; local < sched.nseg; ++local) {
+                const Seg sg = sched.get(local);
                 const int xacc = local & 1;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
                 if (PASSES == 3) {
                     mbar_wait_sleep(&xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
                     tc_fence_after();
                 }
-                for (int k = 0; k < k_iters; ++k) {
+                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                for (int k = k_beg; k < k_end; ++k) {
                     const int kin = k % kChunkK;
                     if (kin == 0) {
                         mbar_wait_sleep(&tempty[cbuf], cphase ^ 1);          // epilogue drained this chunk buffer
@@ -306,7 +380,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, (k | kk) != 0);
+                            umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                             umma_tf32(d_cross, a_hi + o, b_lo + o, idesc, 1);
                             umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                         }
@@ -319,7 +393,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         }
                     }
                     umma_commit(&empty[stage]);                          // smem slot free once these MMAs retire
-                    if (kin == kChunkK - 1 || k == k_iters - 1) {        // chunk complete (covers the cross MMAs too)
+                    if (kin == kChunkK - 1 || k == k_end - 1) {          // chunk complete (covers the cross MMAs too)
                         umma_commit(&tfull[cbuf]);
                         cbuf ^= 1;
                         if (cbuf == 0) cphase ^= 1;
@@ -333,15 +407,19 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue =====================
-        const int q = warp - kEpiWarp0;                    // TMEM lane quarter of this warp
+        const int q = (warp - kEpiWarp0) & 3;              // TMEM lane quarter of this warp
+        const int grp = (warp - kEpiWarp0) >> 2;           // column half of the tile this warp owns
+        constexpr int HN = BN / 2;                         // columns per thread
+        const int cofs = grp * HN;
         const int m = q * 32 + lane;                       // tile row = TMEM lane = output pixel in the tile
         const int TW = 1 << p.TW_log2;
         const int hl = m >> p.TW_log2, wl = m & (TW - 1);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int nchunks = (k_iters + kChunkK - 1) / kChunkK;
         int local = 0, cbuf = 0;
         uint32_t cphase = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+        for (; local < sched.nseg; ++local) {
+            const Seg sg = sched.get(local);
+            const int t = sg.tile, nchunks = sg.c1 - sg.c0;
             const int xacc = local & 1;
             const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
             const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
@@ -349,16 +427,16 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const bool pix_ok = oh < p.OH && ow < p.OW;
             const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
             const int n0 = n_tile * BN;
-            float acc[BN];
+            float acc[HN];
 #pragma unroll
-            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            for (int j = 0; j < HN; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchunks; ++ch) {          // drain finished chunks: fp32 round-to-nearest adds
                 mbar_wait_sleep(&tfull[cbuf], cphase);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < BN / 16; ++c) {
+                for (int c = 0; c < HN / 16; ++c) {
                     float v[16];
-                    tmem_ld16(lane_base + cbuf * BN + c * 16, v);
+                    tmem_ld16(lane_base + cbuf * BN + cofs + c * 16, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
                 }
@@ -369,21 +447,54 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
             if (PASSES == 3) {                               // + the cross terms of the whole tile
 #pragma unroll
-                for (int c = 0; c < BN / 16; ++c) {
+                for (int c = 0; c < HN / 16; ++c) {
                     float v[16];
-                    tmem_ld16(lane_base + (2 + xacc) * BN + c * 16, v);
+                    tmem_ld16(lane_base + (2 + xacc) * BN + cofs + c * 16, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
                 }
                 tc_fence_before();
                 mbar_arrive(&xempty[xacc]);
             }
-            // ---- from here on the tile lives in registers; the tensor core is already on the next tile
+            // ---- from here on the tile lives in registers; the tensor core is already on the next segment
+            if (sg.role == 1) {
+                // partial tile: publish registers -> scratch[cta][column][row] (coalesced across the warp)
+                float* dst = p.sk_scratch + ((size_t)blockIdx.x * BN + cofs) * kBlockM + m;
+#pragma unroll
+                for (int j = 0; j < HN; ++j) dst[j * kBlockM] = acc[j];
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps
+                if (m == 0 && grp == 0) {
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(p.sk_epoch) : "memory");
+                }
+                continue;
+            }
+            if (sg.role == 2) {
+                // finisher: add the partials of the CTAs that ran the earlier chunks of this tile, in k order
+                const long long ufirst = (long long)t * sched.cpt;
+                const long long U = (long long)tiles * sched.cpt;
+                const int c_first = (int)(((ufirst + 1) * gridDim.x + U - 1) / U) - 1;
+                for (int c = c_first; c < (int)blockIdx.x; ++c) {
+                    if (m == 0 && grp == 0) {
+                        int v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.sk_flags + c) : "memory");
+                            if (v != p.sk_epoch) __nanosleep(64);
+                        } while (v != p.sk_epoch);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    __threadfence();
+                    const float* src = p.sk_scratch + ((size_t)c * BN + cofs) * kBlockM + m;
+#pragma unroll
+                    for (int j = 0; j < HN; ++j) acc[j] += __ldcg(src + j * kBlockM);
+                }
+            }
             if constexpr (CORR) {
                 // tile row m = position (yl, xl) of the 8x16 tile; column n = halo (rl, cl) of this 4x32 chunk
                 const int r = p.corr_r, D = p.corr_D;
 #pragma unroll
-                for (int rl = 0; rl < BN / 32; ++rl) {
+                for (int rh = 0; rh < HN / 32; ++rh) {
+                    const int rl = grp * (HN / 32) + rh;             // halo row of the chunk (this group's half)
                     const int tjr = 4 * n_tile + rl - hl;            // tj + r
                     if (!pix_ok || tjr < 0 || tjr >= D) continue;
                     const int tc0 = tjr * D - wl;                    // channel of column cl is tc0 + cl
@@ -391,7 +502,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     for (int cl = 0; cl < 32; ++cl) {
                         const int tir = cl - wl;                     // ti + r
                         if (tir < 0 || tir >= D) continue;
-                        const float val = __fdiv_rn(acc[rl * 32 + cl], p.corr_nelems);   // kernel.cu:100
+                        const float val = __fdiv_rn(acc[rh * 32 + cl], p.corr_nelems);   // kernel.cu:100
                         if (p.out_nchw)
                             p.out_nchw[(((size_t)img * D * D + tc0 + cl) * p.OH + oh) * p.OW + ow] = val;
                         if (p.out_hi) {
@@ -405,17 +516,34 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 (void)r;
             } else {
 #pragma unroll
-            for (int c = 0; c < BN / 16; ++c) {
+            for (int c = 0; c < HN / 16; ++c) {
                 float* v = acc + c * 16;
-                const int ch0 = n0 + c * 16;
+                const int ch0 = n0 + cofs + c * 16;
                 if (ch0 >= p.Cout) continue;                 // (warp-uniform)
                 const bool full16 = ch0 + 16 <= p.Cout;
+                if (full16) {                                // per-channel affine (folded BN / bias): 128-bit loads
+                    if (p.scale) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int chn = min(ch0 + j, p.Cout - 1);
-                    const float sc = p.scale ? __ldg(p.scale + chn) : 1.f;
-                    const float sh = p.shift ? __ldg(p.shift + chn) : 0.f;
-                    v[j] = fmaf(v[j], sc, sh);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
+                            v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
+                        }
+                    }
+                    if (p.shift) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
+                            v[j] += sh.x; v[j + 1] += sh.y; v[j + 2] += sh.z; v[j + 3] += sh.w;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int chn = min(ch0 + j, p.Cout - 1);
+                        const float sc = p.scale ? __ldg(p.scale + chn) : 1.f;
+                        const float sh = p.shift ? __ldg(p.shift + chn) : 0.f;
+                        v[j] = v[j] * sc + sh;
+                    }
                 }
                 if (p.res_hi && pix_ok) {
                     const float* rh = p.res_hi + pix * p.res_cstride + ch0;
@@ -444,34 +572,43 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     for (int j = 0; j < 16; ++j)
                         if (full16 || ch0 + j < p.Cout) o[j * cs] = v[j];     // lanes = consecutive ow: coalesced
                 }
-                if (p.out_hi && pix_ok) {
-                    float* oh_ = p.out_hi + pix * p.out_cstride + p.out_coffset + ch0;
-                    float* ol_ = p.out_lo + pix * p.out_cstride + p.out_coffset + ch0;
-                    if (full16) {
+            }
+            if (p.out_hi) {
+                // NHWC output through shared memory + TMA store: the 128 threads of this group lay their rows
+                // (32 channels = 128 B each) into a SWIZZLE_128B slab, then ONE bulk tensor store writes the
+                // [TH x TW x 32] box as full lines; pixels / channels outside the tensor are clipped by the TMA.
+                uint8_t* slab = out_stage + grp * (kBlockM * 128);
+                const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)m & 7u;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 h, l;
-                            h.x = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);     l.x = v[j] - h.x;
-                            h.y = __uint_as_float(__float_as_uint(v[j + 1]) & 0xffffe000u); l.y = v[j + 1] - h.y;
-                            h.z = __uint_as_float(__float_as_uint(v[j + 2]) & 0xffffe000u); l.z = v[j + 2] - h.z;
-                            h.w = __uint_as_float(__float_as_uint(v[j + 3]) & 0xffffe000u); l.w = v[j + 3] - h.w;
-                            *reinterpret_cast<float4*>(oh_ + j) = h;
-                            *reinterpret_cast<float4*>(ol_ + j) = l;
+                for (int sl = 0; sl < HN / 32; ++sl) {
+                    const int chs = n0 + cofs + sl * 32;
+                    if (chs >= p.Cout) continue;              // (uniform over the group)
+                    const float* v = acc + sl * 32;
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {    // 0: hi, 1: lo
+                        if (m == 0) tma_store_wait_read();    // the previous store has read the slab
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float h0 = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+                            const float h1 = __uint_as_float(__float_as_uint(v[j + 1]) & 0xffffe000u);
+                            const float h2 = __uint_as_float(__float_as_uint(v[j + 2]) & 0xffffe000u);
+                            const float h3 = __uint_as_float(__float_as_uint(v[j + 3]) & 0xffffe000u);
+                            const float4 o = part == 0 ? make_float4(h0, h1, h2, h3)
+                                                       : make_float4(v[j] - h0, v[j + 1] - h1, v[j + 2] - h2, v[j + 3] - h3);
+                            *reinterpret_cast<float4*>(slab + row_off + ((((uint32_t)j >> 2) ^ sw) << 4)) = o;
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (ch0 + j < p.Cout) {
-                                const float h = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
-                                oh_[j] = h;
-                                ol_[j] = v[j] - h;
-                            }
+                        fence_proxy_async();
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                        if (m == 0)
+                            tma_store_4d(part == 0 ? &tmO_hi : &tmO_lo, slab, chs, tw << p.TW_log2, th * p.TH, img);
                     }
                 }
             }
             }   // !CORR
         }
     }
+    if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 2)
@@ -517,11 +654,71 @@ bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims
 
 using namespace d2t;
 
+namespace d2t {
+namespace {
+// Per-device stream-K scratch: one fp32 partial tile [128 x 128] and one flag per SM.  Allocated once, at the
+// first plan creation on a device (never on the launch path).  Plans on one device share it, so they must not
+// run concurrently on different streams (the engine runs everything on one stream).
+struct SkScratch {
+    float* partial = nullptr;
+    int* flags = nullptr;
+};
+SkScratch g_sk[64];
+std::mutex g_sk_mu;
+std::atomic<int> g_sk_epoch{0};
+
+bool sk_scratch(SkScratch* out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        set_error("stream-K scratch: bad device");
+        return false;
+    }
+    std::lock_guard<std::mutex> lock(g_sk_mu);
+    if (!g_sk[dev].partial) {
+        const size_t n = (size_t)sm_count();
+        cudaError_t e = cudaMalloc(&g_sk[dev].partial, n * kBlockM * 128 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&g_sk[dev].flags, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(g_sk[dev].flags, 0, n * sizeof(int));
+        if (e != cudaSuccess) {
+            set_error("stream-K scratch: %s", cudaGetErrorString(e));
+            g_sk[dev] = SkScratch();
+            return false;
+        }
+    }
+    *out = g_sk[dev];
+    return true;
+}
+
+// grid = one CTA per SM, fewer only when the layer has fewer K chunks than SMs
+int sk_grid(int tiles, int k_iters) {
+    const long long units = (long long)tiles * ((k_iters + kChunkK - 1) / kChunkK);
+    return (int)(units < sm_count() ? units : sm_count());
+}
+}  // namespace
+}  // namespace d2t
+
+namespace d2t {
+namespace {
+// split NHWC output [N, OH, OW, cstride], channels [coff, coff + Cout): box = one 32-channel slab of a tile
+bool encode_out_maps(CUtensorMap* hi, CUtensorMap* lo, float* out_hi, float* out_lo, int N, int OH, int OW, int Cout,
+                     int cstride, int coff, int TH, int TW) {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    const cuuint64_t str[3] = {(cuuint64_t)cstride * 4, (cuuint64_t)OW * cstride * 4, (cuuint64_t)OH * OW * cstride * 4};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)TW, (cuuint32_t)TH, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return encode(hi, out_hi + coff, 4, dims, str, box, estr, "out hi") &&
+           encode(lo, out_lo + coff, 4, dims, str, box, estr, "out lo");
+}
+}  // namespace
+}  // namespace d2t
+
 struct d2t_conv_plan {
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
     alignas(64) CUtensorMap tmB_hi;
     alignas(64) CUtensorMap tmB_lo;
+    alignas(64) CUtensorMap tmO_hi;
+    alignas(64) CUtensorMap tmO_lo;
     ConvArgs args;
     int BN, passes, grid, corr;
 };
@@ -531,8 +728,10 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     using C = Cfg<BN, PASSES>;
     static SmemAttrOnce once;
     if (!once.ensure(conv_igemm_tf32<BN, PASSES, CORR>, C::SMEM_BYTES, "conv smem attr")) return 0;
-    conv_igemm_tf32<BN, PASSES, CORR><<<pl->grid, kThreads, C::SMEM_BYTES, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                                   pl->tmB_lo, pl->args);
+    ConvArgs args = pl->args;
+    args.sk_epoch = ++g_sk_epoch;
+    conv_igemm_tf32<BN, PASSES, CORR><<<pl->grid, kThreads, C::SMEM_BYTES, stream>>>(
+        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, args);
     D2T_CHECK_LAUNCH("conv_igemm_tf32");
     return 1;
 }
@@ -601,8 +800,13 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
     pl->passes = d->passes; pl->corr = 0;
-    const int tiles = a.m_tiles * a.n_tiles;
-    pl->grid = tiles < sm_count() ? tiles : sm_count();
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks);
+    SkScratch sk;
+    if (!sk_scratch(&sk)) {
+        free(pl);
+        return nullptr;
+    }
+    a.sk_scratch = sk.partial; a.sk_flags = sk.flags; a.sk_epoch = 0;
 
     // A: NHWC activation, dims innermost first {C, W, H, N}
     const cuuint64_t adims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
@@ -625,6 +829,13 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     if (ok && d->passes == 1) {
         pl->tmA_lo = pl->tmA_hi;
         pl->tmB_lo = pl->tmB_hi;
+    }
+    if (ok && out_hi)
+        ok = encode_out_maps(&pl->tmO_hi, &pl->tmO_lo, out_hi, out_lo, d->N, OH, OW, d->Cout, d->out_cstride,
+                             d->out_coffset, TH, TW);
+    else if (ok) {
+        pl->tmO_hi = pl->tmA_hi;
+        pl->tmO_lo = pl->tmA_hi;
     }
     if (!ok) {
         free(pl);
@@ -671,8 +882,15 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.scale = scale; a.shift = shift; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0;
-    const int tiles = a.m_tiles * a.n_tiles;
-    pl->grid = tiles < sm_count() ? tiles : sm_count();
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7);
+    {
+        SkScratch sk;
+        if (!sk_scratch(&sk)) {
+            free(pl);
+            return nullptr;
+        }
+        a.sk_scratch = sk.partial; a.sk_flags = sk.flags; a.sk_epoch = 0;
+    }
     const cuuint64_t row = (cuuint64_t)Wp * 16;
     const cuuint64_t adims[5] = {32, (cuuint64_t)OW, 2, (cuuint64_t)(Hp / 2), (cuuint64_t)N};
     const cuuint64_t astr[4] = {32, row, 2 * row, (cuuint64_t)Hp * row};
@@ -691,6 +909,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
         pl->tmA_lo = pl->tmA_hi;
         pl->tmB_lo = pl->tmB_hi;
     }
+    if (ok) ok = encode_out_maps(&pl->tmO_hi, &pl->tmO_lo, out_hi, out_lo, N, OH, OW, Cout, out_cstride, 0, TH, TW);
     if (!ok) {
         free(pl);
         return nullptr;
@@ -737,8 +956,15 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
     pl->BN = 128; pl->passes = passes; pl->corr = 1;
-    const int tiles = a.m_tiles * a.n_tiles;
-    pl->grid = tiles < sm_count() ? tiles : sm_count();
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks);
+    {
+        SkScratch sk;
+        if (!sk_scratch(&sk)) {
+            free(pl);
+            return nullptr;
+        }
+        a.sk_scratch = sk.partial; a.sk_flags = sk.flags; a.sk_epoch = 0;
+    }
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t str[3] = {(cuuint64_t)in_cstride * 4, (cuuint64_t)W * in_cstride * 4, (cuuint64_t)H * W * in_cstride * 4};
     const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(15 * stride + 1), (cuuint32_t)(7 * stride + 1), 1u};
@@ -753,6 +979,8 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
         pl->tmA_lo = pl->tmA_hi;
         pl->tmB_lo = pl->tmB_hi;
     }
+    pl->tmO_hi = pl->tmA_hi;   // unused in correlation mode (direct stores)
+    pl->tmO_lo = pl->tmA_hi;
     if (!ok) {
         free(pl);
         return nullptr;
