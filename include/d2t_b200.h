@@ -187,9 +187,11 @@ int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
  * Replaces the cuDNN convolutions + eval-mode BatchNorm + ReLU the reference reaches through
  * torch.nn for the ResNet-101 trunk and the heads (faster_rcnn/resnet.py:66-129, 258-312, 333-344;
  * faster_rcnn/rfcn.py:49-53; rpn/rpn.py:28-36, 62-71).
- * Activations are NHWC fp32 "split" tensors x = hi + lo: hi = x with the low 13 mantissa bits
- * cleared (exactly a TF32 value), lo = x - hi (exact).  passes = 3 evaluates hi*hi + hi*lo + lo*hi
- * on the tensor cores (fp32-level accuracy); passes = 1 is a plain single TF32 pass. */
+ * Activations are NHWC fp32 "split" tensors: the pair (x, lo) with lo = x - trunc13(x), trunc13 =
+ * clearing the low 13 mantissa bits.  kind::tf32 reads x as hi = trunc13(x) (the hardware ignores
+ * those bits), so the arrays named *_hi below hold the plain fp32 values and *_lo the exact
+ * remainders.  passes = 3 evaluates hi*hi + hi*lo + lo*hi on the tensor cores (fp32-level
+ * accuracy); passes = 1 is a plain single TF32 pass on x alone. */
 typedef struct d2t_conv_desc {
     int N, H, W;              /* input [N, H, W, in_cstride] */
     int Cin;                  /* input channels read, a multiple of 32 (zero padded) */

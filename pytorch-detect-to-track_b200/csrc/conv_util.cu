@@ -1,7 +1,7 @@
 // conv_util.cu -- layout / precision-split helpers around the tcgen05 conv kernels (conv.cu).
 //
-// The conv engine keeps activations as NHWC "split" tensors x = hi + lo (hi = x with the low 13
-// mantissa bits cleared = exactly a TF32 value, lo = x - hi, exact).  These kernels move data
+// The conv engine keeps activations as NHWC "split" tensors: the pair (x, lo) with lo = x - trunc13(x)
+// (the tensor core reads x as hi = trunc13(x); see conv.cu).  The x array is called "hi" below.  These kernels move data
 // between that format and the reference's plain fp32 NCHW tensors, pack OIHW weights into the
 // [Cout, R*S*Cin_pad] K-major matrix the weight TMA reads, and implement the stem's
 // MaxPool2d(3, stride 2, padding 0, ceil_mode=True) (/root/reference/lib/model/faster_rcnn/resnet.py:120).
@@ -30,7 +30,7 @@ __global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H
         if (h >= 0 && h < H && w >= 0 && w < W)
             for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)n * C + c) * H + h) * W + w);
         const float4 a = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
-        hi[idx] = a;
+        hi[idx] = make_float4(v[0], v[1], v[2], v[3]);
         if (lo) lo[idx] = make_float4(v[0] - a.x, v[1] - a.y, v[2] - a.z, v[3] - a.w);
     }
 }
@@ -43,7 +43,7 @@ __global__ void stem_pack_weights(const float* __restrict__ w, int O, int C, flo
         const int s = col >> 2, c = col & 3;
         const float v = (s < 7 && c < C) ? __ldg(w + (((size_t)o * C + c) * 7 + r) * 7 + s) : 0.f;
         const float a = tf32_hi(v);
-        hi[idx] = a;
+        hi[idx] = v;
         if (lo) lo[idx] = v - a;
     }
 }
@@ -65,7 +65,7 @@ nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int 
         if (w < W && c < cw) {
             const float v = tile[tx][j], a = tf32_hi(v);
             const size_t o = (((size_t)n * H + h) * W + w) * cs + coff + c;
-            hi[o] = a;
+            hi[o] = v;
             if (lo) lo[o] = v - a;
         }
     }
@@ -83,7 +83,7 @@ nhwc_split_to_nchw(const float* __restrict__ hi, const float* __restrict__ lo, i
         float v = 0.f;
         if (w < W && c < C) {
             const size_t i = (((size_t)n * H + h) * W + w) * cs + coff + c;
-            v = __ldg(hi + i) + (lo ? __ldg(lo + i) : 0.f);
+            v = __ldg(hi + i);
         }
         tile[j][tx] = v;
     }
@@ -104,7 +104,7 @@ __global__ void pack_weights(const float* __restrict__ w, int O, int I, int R, i
         const int o = (int)(idx / cin_pad / (R * S));
         const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) : 0.f;
         const float a = tf32_hi(v);
-        hi[idx] = a;
+        hi[idx] = v;
         if (lo) lo[idx] = v - a;
     }
 }
@@ -127,16 +127,12 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* 
                 const int w = ow * 2 + s;
                 if (w >= W) break;
                 const size_t i = ((((size_t)n * H + h) * W + w) * C >> 2) + c4;
-                float4 v = __ldg(reinterpret_cast<const float4*>(in_hi) + i);
-                if (in_lo) {
-                    const float4 l = __ldg(reinterpret_cast<const float4*>(in_lo) + i);
-                    v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
-                }
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in_hi) + i);
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
         float4 a = make_float4(tf32_hi(m.x), tf32_hi(m.y), tf32_hi(m.z), tf32_hi(m.w));
-        reinterpret_cast<float4*>(out_hi)[idx] = a;
+        reinterpret_cast<float4*>(out_hi)[idx] = m;
         if (out_lo) reinterpret_cast<float4*>(out_lo)[idx] = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
     }
 }

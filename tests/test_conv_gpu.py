@@ -67,7 +67,8 @@ def test_conv_matches_torch(case, passes):
     assert err < tol, (err, layer.info)
     if layer.out is not None:
         assert torch.equal(layer.out.to_nchw(Cout), got)      # NHWC split output carries the same values
-        assert float((layer.out.hi.view(-1).view(torch.int32) & 0x1fff).abs().max()) == 0   # hi is a TF32 value
+        hi13 = (layer.out.hi.view(-1).view(torch.int32) & ~0x1fff).view(torch.float32)
+        assert torch.equal(layer.out.lo.view(-1), layer.out.hi.view(-1) - hi13)              # lo = x - trunc13(x)
 
 
 def test_maxpool_ceil_mode():
