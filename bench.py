@@ -216,6 +216,10 @@ def run_reference(args):
 
 
 def run_b200(args):
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner) go to stderr meanwhile
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     from d2t_b200 import ops
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,6 +229,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the d2t_b200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -357,7 +364,10 @@ def run_b200(args):
                 "gpu_launches": my_launches, "roofline": roofline, "roofline_psroi": roofline_psroi,
                 "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "ops": ops_bench}
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
