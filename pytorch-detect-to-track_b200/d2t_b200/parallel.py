@@ -46,3 +46,30 @@ def gather_pairs(part, dst=0):
     if dist.get_rank() != dst:
         return None
     return torch.cat([b[: int(s)] for b, s in zip(bufs, sizes)], 0)
+
+
+def allreduce_gradients(params, bucket_bytes=64 << 20):
+    """The ONE collective of the training step: mean of the gradients of the trainable
+    parameters over ranks, in a few flat buckets (reverse parameter order = the order backward produces
+    them).  Replaces nn.DataParallel's reduce-onto-GPU-0 (trainval_net.py:311); with equal shard sizes the
+    result equals the gradient of the mean loss over the global batch (trainval_net.py:367-368)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in reversed(list(params)) if p.requires_grad and p.grad is not None]
+    n_buckets, i = 0, 0
+    while i < len(grads):
+        j, size = i, 0
+        while j < len(grads) and (size == 0 or size + grads[j].numel() * grads[j].element_size() <= bucket_bytes):
+            size += grads[j].numel() * grads[j].element_size()
+            j += 1
+        flat = torch.cat([g.reshape(-1) for g in grads[i:j]])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for g in grads[i:j]:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        n_buckets += 1
+        i = j
+    return n_buckets

@@ -42,3 +42,44 @@ def clip_boxes(boxes, im_shape, batch_size=None):
     boxes[:, :, 2::4] = torch.min(torch.max(boxes[:, :, 2::4], zero), xmax)
     boxes[:, :, 3::4] = torch.min(torch.max(boxes[:, :, 3::4], zero), ymax)
     return boxes
+
+
+def bbox_transform_batch(ex_rois, gt_rois):
+    """Regression targets (dx, dy, dw, dh) of gt w.r.t. ex boxes, +1 width convention
+    (bbox_transform.py:38-75).  ex_rois [N,4] or [B,N,4]; gt_rois [B,N,4]."""
+    if ex_rois.dim() == 2:
+        ex_rois = ex_rois.unsqueeze(0).expand_as(gt_rois[..., :4])
+    ew = ex_rois[..., 2] - ex_rois[..., 0] + 1.0
+    eh = ex_rois[..., 3] - ex_rois[..., 1] + 1.0
+    ecx = ex_rois[..., 0] + 0.5 * ew
+    ecy = ex_rois[..., 1] + 0.5 * eh
+    gw = gt_rois[..., 2] - gt_rois[..., 0] + 1.0
+    gh = gt_rois[..., 3] - gt_rois[..., 1] + 1.0
+    gcx = gt_rois[..., 0] + 0.5 * gw
+    gcy = gt_rois[..., 1] + 0.5 * gh
+    return torch.stack(((gcx - ecx) / ew, (gcy - ecy) / eh, torch.log(gw / ew), torch.log(gh / eh)), -1)
+
+
+def bbox_overlaps_batch(anchors, gt_boxes):
+    """IoU (+1 convention) of anchors [N,4] / [B,N,4|5] against gt_boxes [B,K,>=4] -> [B,N,K]; all-zero
+    (padding) gt boxes give 0, degenerate anchors give -1 (bbox_transform.py:208-298)."""
+    B = gt_boxes.size(0)
+    if anchors.dim() == 2:
+        anchors = anchors.unsqueeze(0).expand(B, anchors.size(0), 4)
+    elif anchors.size(2) == 5:
+        anchors = anchors[:, :, 1:5]
+    gt = gt_boxes[:, :, :4]
+    gx = gt[:, :, 2] - gt[:, :, 0] + 1
+    gy = gt[:, :, 3] - gt[:, :, 1] + 1
+    ax = anchors[:, :, 2] - anchors[:, :, 0] + 1
+    ay = anchors[:, :, 3] - anchors[:, :, 1] + 1
+    g_area = (gx * gy).unsqueeze(1)
+    a_area = (ax * ay).unsqueeze(2)
+    a, g = anchors.unsqueeze(2), gt.unsqueeze(1)
+    iw = (torch.min(a[..., 2], g[..., 2]) - torch.max(a[..., 0], g[..., 0]) + 1).clamp(min=0)
+    ih = (torch.min(a[..., 3], g[..., 3]) - torch.max(a[..., 1], g[..., 1]) + 1).clamp(min=0)
+    inter = iw * ih
+    ov = inter / (a_area + g_area - inter)
+    ov = ov.masked_fill(((gx == 1) & (gy == 1)).unsqueeze(1), 0)
+    ov = ov.masked_fill(((ax == 1) & (ay == 1)).unsqueeze(2), -1)
+    return ov

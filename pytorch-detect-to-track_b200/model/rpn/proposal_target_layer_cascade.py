@@ -1,0 +1,107 @@
+"""Training-only RoI sampling (lib/model/rpn/proposal_target_layer_cascade.py:20-208) and the training branch
+of the D&T graph (lib/model/faster_rcnn/rfcn.py:113-160, 176-204), restated for Python 3 / current torch.
+Host-side training glue; sampling uses torch's generator on the device."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from model.utils.config import cfg
+from model.utils.net_utils import _smooth_l1_loss
+from .bbox_transform import bbox_overlaps_batch, bbox_transform_batch
+
+
+class _ProposalTargetLayer(nn.Module):
+    """Assign proposals to ground truth: labels + (normalised) regression targets for 128 sampled RoIs / image."""
+
+    def __init__(self, nclasses):
+        super(_ProposalTargetLayer, self).__init__()
+        self._num_classes = nclasses
+        self.generator = None
+
+    @torch.no_grad()
+    def forward(self, all_rois, gt_boxes, num_boxes):
+        means = gt_boxes.new_tensor(cfg.TRAIN.BBOX_NORMALIZE_MEANS)
+        stds = gt_boxes.new_tensor(cfg.TRAIN.BBOX_NORMALIZE_STDS)
+        inside = gt_boxes.new_tensor(cfg.TRAIN.BBOX_INSIDE_WEIGHTS)
+        gt_append = gt_boxes.new_zeros(gt_boxes.size(0), gt_boxes.size(1), 5)
+        gt_append[:, :, 1:5] = gt_boxes[:, :, :4]
+        all_rois = torch.cat([all_rois, gt_append], 1)                      # ground truth joins the candidates
+        rois_per_image = int(cfg.TRAIN.BATCH_SIZE)
+        fg_per_image = max(1, int(np.round(cfg.TRAIN.FG_FRACTION * rois_per_image)))
+        overlaps = bbox_overlaps_batch(all_rois, gt_boxes[:, :, :5])
+        max_ov, assign = overlaps.max(2)
+        B = overlaps.size(0)
+        labels = torch.gather(gt_boxes[:, :, 4], 1, assign)
+        labels_b = labels.new_zeros(B, rois_per_image)
+        rois_b = all_rois.new_zeros(B, rois_per_image, 5)
+        gt_b = all_rois.new_zeros(B, rois_per_image, gt_boxes.size(2))
+        for i in range(B):
+            fg = torch.nonzero(max_ov[i] >= cfg.TRAIN.FG_THRESH).view(-1)
+            bg = torch.nonzero((max_ov[i] < cfg.TRAIN.BG_THRESH_HI) & (max_ov[i] >= cfg.TRAIN.BG_THRESH_LO)).view(-1)
+            nf, nb = fg.numel(), bg.numel()
+            rnd = lambda n, m: torch.floor(torch.rand(n, device=fg.device, generator=self.generator) * m).long()
+            if nf > 0 and nb > 0:
+                n_fg = min(fg_per_image, nf)
+                fg = fg[torch.randperm(nf, device=fg.device, generator=self.generator)[:n_fg]]
+                bg = bg[rnd(rois_per_image - n_fg, nb)]
+            elif nf > 0:
+                fg, bg, n_fg = fg[rnd(rois_per_image, nf)], bg[:0], rois_per_image
+            elif nb > 0:
+                fg, bg, n_fg = fg[:0], bg[rnd(rois_per_image, nb)], 0
+            else:
+                raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+            keep = torch.cat([fg, bg], 0)
+            labels_b[i] = labels[i][keep]
+            labels_b[i][n_fg:] = 0                                          # background label
+            rois_b[i] = all_rois[i][keep]
+            rois_b[i, :, 0] = i
+            gt_b[i] = gt_boxes[i][assign[i][keep]]
+        targets = (bbox_transform_batch(rois_b[:, :, 1:5], gt_b[:, :, :4]) - means) / stds
+        fg_mask = (labels_b > 0).unsqueeze(2).float()
+        bbox_targets = targets * fg_mask
+        inside_w = inside.view(1, 1, 4) * fg_mask
+        outside_w = (inside_w > 0).float()
+        return rois_b, labels_b, bbox_targets, inside_w, outside_w
+
+
+def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, info, gt_boxes, num_boxes):
+    """Training branch of _RFCN.forward.  Tensors are leg-major over 2B images; gt_boxes [B,2,K,6],
+    num_boxes [B,2,1].  Returns the reference's 10-tuple (rfcn.py:248-250)."""
+    from .tracking_proposal_target_layer import _TrackingProposalTargetLayer
+    L = 2
+    if net.RFCN_proposal_target is None:
+        net.RFCN_proposal_target = _ProposalTargetLayer(net.n_classes)
+        net.RFCN_tracking_proposal_target = _TrackingProposalTargetLayer(net.n_classes)
+    gt = gt_boxes.permute(1, 0, 2, 3).contiguous()          # [2, B, K, 6]
+    nb = num_boxes.permute(1, 0, 2).contiguous()
+    rois, rois_label, cls_prob, bbox_pred = [], [], [], []
+    l_rpn_cls, l_rpn_box, l_cls, l_box = [], [], [], []
+    for leg in range(L):
+        sl = slice(leg * B, (leg + 1) * B)
+        leg_rois, lc, lb = net.RFCN_rpn(base_feat[sl], info[sl], gt[leg][:, :, :5], nb[leg])
+        l_rpn_cls.append(lc.view(1)), l_rpn_box.append(lb.view(1))
+        leg_rois, label, target, iw, ow = net.RFCN_proposal_target(leg_rois, gt[leg][:, :, :5], nb[leg])
+        label = label.view(-1).long()
+        flat = leg_rois.view(-1, 5)
+        pooled_cls = net.RFCN_psroi_cls_pool(rfcn_cls[sl].contiguous(), flat)
+        pooled_loc = net.RFCN_psroi_loc_pool(rfcn_bbox[sl].contiguous(), flat)
+        score = net.RFCN_cls_score(pooled_cls).view(flat.size(0), -1)
+        pred = net.RFCN_bbox_pred(pooled_loc).view(flat.size(0), -1)
+        if not net.class_agnostic:
+            pred = torch.gather(pred.view(pred.size(0), -1, 4), 1, label.view(-1, 1, 1).expand(-1, 1, 4)).squeeze(1)
+        l_cls.append(F.cross_entropy(score, label).view(1))
+        l_box.append(_smooth_l1_loss(pred, target.view(-1, target.size(2)), iw.view(-1, iw.size(2)),
+                                     ow.view(-1, ow.size(2))).view(1))
+        rois.append(leg_rois), rois_label.append(label)
+        cls_prob.append(F.softmax(score, dim=1).view(B, leg_rois.size(1), -1))
+        bbox_pred.append(pred.view(B, leg_rois.size(1), -1))
+    # ---- tracking branch
+    trk = net._tracking_maps(conv3, conv4, conv5, rfcn_bbox, B)
+    t_rois, t_label, t_target, t_iw, t_ow = net.RFCN_tracking_proposal_target(gt, nb)
+    pooled = net.RFCN_psroi_loc_pool(trk, t_rois.contiguous().view(-1, 5))
+    tracking_pred = net.RFCN_tracking_pred(pooled).view(-1, pooled.size(1))
+    l_trk = _smooth_l1_loss(tracking_pred, t_target.view(-1, t_target.size(2)), t_iw.view(-1, t_iw.size(2)),
+                            t_ow.view(-1, t_ow.size(2)))
+    return (torch.stack(rois), torch.stack(cls_prob), torch.stack(bbox_pred), tracking_pred, torch.stack(l_rpn_cls),
+            torch.stack(l_rpn_box), torch.stack(l_cls), torch.stack(l_box), torch.stack(rois_label).view(L, B, -1), l_trk)

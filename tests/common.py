@@ -70,3 +70,29 @@ def make_rpn_inputs(B, H, W, A=12, seed=30, im_h=None, im_w=None):
     deltas = (rng.standard_normal((B, 4 * A, H, W)) * 0.3).astype(np.float32)
     im_info = np.tile(np.array([[im_h or H * 16, im_w or W * 16, 1.0]], np.float32), (B, 1))
     return prob, deltas, im_info
+
+
+def make_gt_boxes(B, K=30, seed=2, height=600, width=1000):
+    """[B, 2, K, 6] = (x1, y1, x2, y2, cls, track_id): 1-5 boxes per frame, w,h ~ U[40, 400] (clipped),
+    same track ids in both frames with +-8 px jitter, one extra unmatched box in some frames."""
+    rng = np.random.RandomState(seed)
+    gt = np.zeros((B, 2, K, 6), np.float32)
+    for b in range(B):
+        n = rng.randint(1, 6)
+        w = rng.uniform(40, min(400, width * 0.6), n)
+        h = rng.uniform(40, min(400, height * 0.6), n)
+        x1 = rng.uniform(0, width - w - 1)
+        y1 = rng.uniform(0, height - h - 1)
+        cls = rng.randint(1, 31, n)
+        ids = rng.permutation(n) + 1
+        for leg in range(2):
+            j = rng.uniform(-8, 8, (n, 4)) if leg else np.zeros((n, 4))
+            box = np.stack([x1, y1, x1 + w, y1 + h], 1) + j
+            box[:, [0, 2]] = np.clip(box[:, [0, 2]], 0, width - 1)
+            box[:, [1, 3]] = np.clip(box[:, [1, 3]], 0, height - 1)
+            gt[b, leg, :n, :4] = box
+            gt[b, leg, :n, 4] = cls
+            gt[b, leg, :n, 5] = ids
+        if b % 2 == 1 and n < K:      # a track that ends: present in frame t only
+            gt[b, 0, n] = [10, 10, 90, 120, 7, 99]
+    return gt

@@ -35,9 +35,24 @@ SCRIPT = textwrap.dedent("""
     full = parallel.gather_pairs(part, dst=0)
     if rank == 0:
         assert torch.equal(full.view(-1), torch.arange(10, dtype=torch.float32))
-        print("OK", flush=True)
     else:
         assert full is None
+    # 5. gradient all-reduce == gradient of the mean loss over the concatenated global batch
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    data = torch.randn(10, 8)
+    target = torch.randn(10, 3)
+    loss = torch.nn.functional.mse_loss(model(data[lo:hi]), target[lo:hi])
+    loss.backward()
+    nb = parallel.allreduce_gradients(model.parameters(), bucket_bytes=256)
+    assert nb >= 2
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    ref.load_state_dict(model.state_dict())
+    torch.nn.functional.mse_loss(ref(data), target).backward()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    if rank == 0:
+        print("OK", flush=True)
     dist.destroy_process_group()
 """)
 
