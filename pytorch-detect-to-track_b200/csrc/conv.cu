@@ -129,10 +129,10 @@ struct Sched {
     }
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool PAIR = false>
 struct Cfg {
     static constexpr int A_BYTES = kBlockM * kBlockK * 4;             // 16 KB
-    static constexpr int B_BYTES = BN * kBlockK * 4;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * kBlockK * 4;   // per CTA: a CTA pair holds half of B each
     static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // hi (+ lo)
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
@@ -172,6 +172,32 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// ---- CTA-pair (cta_group::2) forms.  `mbar_leader` is the shared::cluster address of the LEADER CTA's barrier.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t mbar_leader, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t mbar_leader, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_leader), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -190,9 +216,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 // instruction descriptor: D = fp32, A = B = tf32, both K-major, M = 128, N = BN
-template <int BN>
+template <int BN, int M = kBlockM>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -206,6 +232,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// M = 256 across the CTA pair: rows 0..127 come from / go to the leader, 128..255 the peer; each CTA supplies N/2 rows of B
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {     // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -217,8 +257,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// mbarrier.try_wait already suspends the thread for a hardware-chosen interval, so the poll loop is a plain spin
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+    while (!mbar_try_wait(bar, parity)) {
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -229,13 +271,24 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // (2r+1)^2 displacements of p are the q with |q - p| <= r in both axes; the epilogue keeps those (38 % of the
 // block for r = 8) and writes out[n, (tj+r)*D + (ti+r), y, x] = D / C.  Zero padding outside the frame is
 // again the TMA out-of-bounds fill; strided correlation (conv3: stride 2) is the TMA element stride.
-template <int BN, int PASSES, bool CORR>
+//
+// PAIR = true runs the kernel as CTA pairs (2-CTA clusters, tcgen05 cta_group::2): one MMA covers 256 output
+// pixels (two adjacent pixel tiles, one per CTA) x BN channels; each CTA stages only its own A tile and HALF of
+// the weight tile, the tensor cores of the two SMs exchange the B halves: 25 % less TMA traffic per useful FLOP
+// and one more pipeline stage.  MEASURED on B200 (round 1): no faster than single-CTA mode on these layers
+// (head conv 0.89 vs 0.87 ms) -- the MMA pipe itself reaches ~95 % of the TF32 peak when fed (MMA-repeat
+// experiment), and the ~40 % main-loop overhead is additive per K block and insensitive to operand bytes (pair
+// mode) and to L2 reads (2x2 TMA-multicast clusters were tried too).  So pairs are OFF by default
+// (D2T_CONV_PAIR=1 enables them) and kept as the validated cta_group::2 path.  The leader CTA issues the MMAs and owns the
+// `full` / `tempty` / `xempty` barriers (both CTAs' TMA and epilogue warps signal them remotely); its commits
+// are multicast to both CTAs' `empty` / `tfull` barriers.
+template <int BN, int PASSES, bool CORR, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                 const ConvArgs p) {
-    using C = Cfg<BN, PASSES>;
+    using C = Cfg<BN, PASSES, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
@@ -249,7 +302,11 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles = p.m_tiles * p.n_tiles;
+    constexpr int CS = PAIR ? 2 : 1;               // CTAs per work unit
+    uint32_t crank = 0;                            // 0 = leader
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int unit_id = blockIdx.x / CS, n_units = gridDim.x / CS;
+    const int tiles = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;     // (pair-)tiles
     const int k_iters = p.R * p.S * p.kc_blocks;
 
     if (warp == 0 && lane == 0) {
@@ -266,26 +323,33 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
-            mbar_init(&full[i], 1);
+            mbar_init(&full[i], CS);                       // one producer arrival per CTA of the pair
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], kEpiThreads);
-            mbar_init(&xempty[i], kEpiThreads);
+            mbar_init(&tempty[i], CS * kEpiThreads);       // (leader's copy collects both CTAs' epilogue threads)
+            mbar_init(&xempty[i], CS * kEpiThreads);
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(C::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const Sched sched(tiles, k_iters, blockIdx.x, gridDim.x);
+    const Sched sched(tiles, k_iters, unit_id, n_units);
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
     // overlapped the tail of the previous layer; from here on we touch its output.
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -299,7 +363,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             for (int e = 0; e < sched.nseg; ++e) {
                 const Seg sg = sched.get(e);
                 const int t = sg.tile;
-                const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+                const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
                 const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
                 const int iw0 = (tw << p.TW_log2) * p.stride - p.pad, ih0 = th * p.TH * p.stride - p.pad;
                 const int n0 = n_tile * BN;
@@ -308,8 +372,28 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const int kc = k % p.kc_blocks, rs = k / p.kc_blocks, s = rs % p.S, r = rs / p.S;
                     mbar_wait_sleep(&empty[stage], phase ^ 1);
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     const int kcol = k * kBlockK;
+                    if (PAIR) {
+                        // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
+                        const uint32_t fb = map_to_cta(smem_u32(&full[stage]), 0);
+                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                        else mbar_arrive_remote(fb);
+                        tma_load_4d_pair(st, &tmA_hi, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        const int brow = n0 + (int)crank * (BN / 2);
+                        if (PASSES == 3) {
+                            tma_load_4d_pair(st + C::A_BYTES, &tmA_lo, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                            tma_load_2d_pair(st + 2 * C::A_BYTES, &tmB_hi, fb, kcol, brow);
+                            tma_load_2d_pair(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, kcol, brow);
+                        } else {
+                            tma_load_2d_pair(st + C::A_BYTES, &tmB_hi, fb, kcol, brow);
+                        }
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     if (p.stem) {
                         // filter row r of the stem: 32 consecutive floats (8 pixels x 4 channels) of padded
                         // input row 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
@@ -355,8 +439,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         // round-to-nearest adds while the next chunk runs into the other TMEM buffer; (2) the two
         // cross terms (2^-11 of the result, so their truncation is negligible) accumulate over the
         // whole tile in their own TMEM buffer.  TMEM: main[2] | cross[2], BN columns each.
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<BN>();
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : make_idesc<BN>();
             int stage = 0, cbuf = 0, local = 0;
             uint32_t phase = 0, cphase = 0;
             for (; local < sched.nseg; ++local) {
@@ -386,21 +470,31 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
-                            umma_tf32(d_cross, a_hi + o, b_lo + o, idesc, 1);
-                            umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            if (PAIR) {
+                                umma_tf32_pair(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
+                                umma_tf32_pair(d_cross, a_hi + o, b_lo + o, idesc, 1);
+                                umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            } else {
+                                umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
+                                umma_tf32(d_cross, a_hi + o, b_lo + o, idesc, 1);
+                                umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            }
                         }
                     } else {
                         const uint64_t b_hi = make_smem_desc(st + C::A_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            if (PAIR) umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            else umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                         }
                     }
-                    umma_commit(&empty[stage]);                          // smem slot free once these MMAs retire
+                    // smem slot free once these MMAs retire (in a pair: in BOTH CTAs)
+                    if (PAIR) umma_commit_pair(&empty[stage]);
+                    else umma_commit(&empty[stage]);
                     if (kin == kChunkK - 1 || k == k_end - 1) {          // chunk complete (covers the cross MMAs too)
-                        umma_commit(&tfull[cbuf]);
+                        if (PAIR) umma_commit_pair(&tfull[cbuf]);
+                        else umma_commit(&tfull[cbuf]);
                         cbuf ^= 1;
                         if (cbuf == 0) cphase ^= 1;
                     }
@@ -427,10 +521,10 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const Seg sg = sched.get(local);
             const int t = sg.tile, nchunks = sg.c1 - sg.c0;
             const int xacc = local & 1;
-            const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+            const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
             const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
             const int oh = th * p.TH + hl, ow = (tw << p.TW_log2) + wl;
-            const bool pix_ok = oh < p.OH && ow < p.OW;
+            const bool pix_ok = oh < p.OH && ow < p.OW && img < p.N;   // (a pair's second tile may not exist)
             const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
             const int n0 = n_tile * BN;
             float acc[HN];
@@ -447,7 +541,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
                 }
                 tc_fence_before();
-                mbar_arrive(&tempty[cbuf]);
+                if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(&tempty[cbuf]), 0));
+                else mbar_arrive(&tempty[cbuf]);
                 cbuf ^= 1;
                 if (cbuf == 0) cphase ^= 1;
             }
@@ -460,7 +555,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
                 }
                 tc_fence_before();
-                mbar_arrive(&xempty[xacc]);
+                if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(&xempty[xacc]), 0));
+                else mbar_arrive(&xempty[xacc]);
             }
             // ---- from here on the tile lives in registers; the tensor core is already on the next segment
             if (sg.role == 1) {
@@ -479,8 +575,9 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 // finisher: add the partials of the CTAs that ran the earlier chunks of this tile, in k order
                 const long long ufirst = (long long)t * sched.cpt;
                 const long long U = (long long)tiles * sched.cpt;
-                const int c_first = (int)(((ufirst + 1) * gridDim.x + U - 1) / U) - 1;
-                for (int c = c_first; c < (int)blockIdx.x; ++c) {
+                const int c_first = (int)(((ufirst + 1) * n_units + U - 1) / U) - 1;
+                for (int cc = c_first; cc < unit_id; ++cc) {
+                    const int c = cc * CS + (int)crank;    // the CTA of unit cc that ran my tile position
                     if (m == 0 && grp == 0) {
                         int v;
                         do {
@@ -615,8 +712,13 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
-    if (warp == 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    if (PAIR) cluster_sync_all();                  // the peer may still signal my barriers / feed my tensor core
+    if (warp == 2) {
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -725,13 +827,14 @@ struct d2t_conv_plan {
     alignas(64) CUtensorMap tmO_lo;
     ConvArgs args;
     int BN, passes, grid, corr;
+    int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
 };
 
-template <int BN, int PASSES, bool CORR>
+template <int BN, int PASSES, bool CORR, bool PAIR>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
-    using C = Cfg<BN, PASSES>;
+    using C = Cfg<BN, PASSES, PAIR>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm_tf32<BN, PASSES, CORR>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm_tf32<BN, PASSES, CORR, PAIR>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
@@ -739,15 +842,50 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_tf32<BN, PASSES, CORR>, pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo,
-                                   pl->tmO_hi, pl->tmO_lo, args),
+    cfg.numAttrs = PAIR ? 2 : 1;
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_tf32<BN, PASSES, CORR, PAIR>, pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
+                                   pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, args),
                 "conv_igemm_tf32 launch");
     return 1;
+}
+
+// how many CTA pairs of the kernel can be resident at once (the persistent grid must not exceed it)
+template <int BN, int PASSES>
+static int max_pairs() {
+    using C = Cfg<BN, PASSES, true>;
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev]) return cached[dev];
+    auto kern = conv_igemm_tf32<BN, PASSES, false, true>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 64);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    if (n <= 0) n = sm_count() / 2 * 3 / 4;       // conservative fallback
+    if (n > sm_count() / 2) n = sm_count() / 2;
+    cached[dev] = n;
+    return n;
 }
 
 extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const float* in_hi, const float* in_lo,
@@ -814,7 +952,17 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
     pl->passes = d->passes; pl->corr = 0;
-    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks);
+    // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
+    pl->pair = (a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
+    if (pl->pair) {
+        const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+        const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + kChunkK - 1) / kChunkK);
+        const int maxp = d->passes == 3 ? (pl->BN == 64 ? max_pairs<64, 3>() : max_pairs<128, 3>())
+                                        : (pl->BN == 64 ? max_pairs<64, 1>() : max_pairs<128, 1>());
+        pl->grid = 2 * (int)(units < maxp ? units : maxp);
+    } else {
+        pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks);
+    }
     SkScratch sk;
     if (!sk_scratch(&sk)) {
         free(pl);
@@ -833,7 +981,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     const cuuint64_t ktot = (cuuint64_t)d->R * d->S * d->Cin;
     const cuuint64_t bdims[2] = {ktot, (cuuint64_t)d->Cout};
     const cuuint64_t bstr[1] = {ktot * 4};
-    const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)pl->BN};
+    const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pl->pair ? pl->BN / 2 : pl->BN)};
     const cuuint32_t bestr[2] = {1u, 1u};
     bool ok = encode(&pl->tmA_hi, in_hi, 4, adims, astr, abox, aestr, "A hi") &&
               encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi");
@@ -895,7 +1043,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.n_tiles = (Cout + pl->BN - 1) / pl->BN;
     a.scale = scale; a.shift = shift; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
-    pl->passes = passes; pl->corr = 0;
+    pl->passes = passes; pl->corr = 0; pl->pair = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7);
     {
         SkScratch sk;
@@ -969,7 +1117,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.scale = nullptr; a.shift = nullptr; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = 0; a.relu = 0;
     a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
-    pl->BN = 128; pl->passes = passes; pl->corr = 1;
+    pl->BN = 128; pl->passes = passes; pl->corr = 1; pl->pair = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks);
     {
         SkScratch sk;
@@ -1009,13 +1157,16 @@ extern "C" void d2t_conv_plan_destroy(d2t_conv_plan* pl) {
 extern "C" int d2t_conv_plan_info(const d2t_conv_plan* pl, int* out8) {
     D2T_REQUIRE(pl && out8, "d2t_conv_plan_info: null");
     out8[0] = pl->args.OH; out8[1] = pl->args.OW; out8[2] = pl->args.TH; out8[3] = 1 << pl->args.TW_log2;
-    out8[4] = pl->BN; out8[5] = pl->args.m_tiles; out8[6] = pl->args.n_tiles; out8[7] = pl->grid;
+    out8[4] = pl->BN; out8[5] = pl->args.m_tiles; out8[6] = pl->args.n_tiles; out8[7] = pl->grid * 10 + pl->pair;
     return 1;
 }
 
 extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
     D2T_REQUIRE(pl, "d2t_conv_plan_run: null plan");
-    if (pl->corr) return pl->passes == 3 ? launch_conv<128, 3, true>(pl, stream) : launch_conv<128, 1, true>(pl, stream);
-    if (pl->passes == 3) return pl->BN == 64 ? launch_conv<64, 3, false>(pl, stream) : launch_conv<128, 3, false>(pl, stream);
-    return pl->BN == 64 ? launch_conv<64, 1, false>(pl, stream) : launch_conv<128, 1, false>(pl, stream);
+    if (pl->corr)
+        return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
+#define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))
+    if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);
+    return pl->BN == 64 ? D2T_RUN(64, 1) : D2T_RUN(128, 1);
+#undef D2T_RUN
 }

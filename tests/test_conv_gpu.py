@@ -167,3 +167,25 @@ def test_tensor_core_correlation(C, H, W, p, B):
     print("corr", (C, H, W, p), "max rel err vs reference kernel %.2e" % err)
     assert err < 2e-5, err
     assert float((simt - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+def test_cta_pair_mode_matches(monkeypatch):
+    """The cta_group::2 (CTA-pair) variant of the kernel gives the same result as single-CTA mode."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(2, 256, 38, 63, device="cuda", generator=g)
+    w = torch.randn(384, 256, 3, 3, device="cuda", generator=g) * 0.02
+    sc, sh = torch.rand(384, device="cuda", generator=g) + 0.5, torch.randn(384, device="cuda", generator=g)
+    res = dc.SplitTensor.from_nchw(torch.randn(2, 384, 38, 63, device="cuda", generator=g), cstride=384)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("D2T_CONV_PAIR", pair)
+        layer = dc.ConvLayer(dc.SplitTensor.from_nchw(x), w, sc, sh, 1, 1, 1, True, res, passes=3, want_nchw=True)
+        assert layer.info["grid"] % 10 == int(pair)
+        layer.run()
+        torch.cuda.synchronize()
+        outs.append((layer.out_nchw.clone(), layer.out.hi.clone(), layer.out.lo.clone()))
+    want = _ref(x, w, sc, sh, 1, 1, 1, True, res.to_nchw())
+    for o in outs:
+        assert float((o[0] - want).abs().max() / want.abs().max()) < 1e-5
+    assert float((outs[0][0] - outs[1][0]).abs().max() / want.abs().max()) < 2e-6
+    assert torch.equal(outs[1][1].permute(0, 3, 1, 2), outs[1][0])
