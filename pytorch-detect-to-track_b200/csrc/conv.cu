@@ -29,7 +29,7 @@
 // number.  (Argument names keep "hi" for the x array.)
 //
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
-//   warp 0   : TMA producer (one elected lane), NS-stage ring of {A_hi, A_lo, B_hi, B_lo}
+//   warp 0   : TMA producer (one lane per operand copy), NS-stage ring of {A x, A lo, B x, B lo}
 //   warp 1   : MMA issuer  (one elected lane), tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8
 //   warp 2   : TMEM allocation (two ping-pong chunk accumulators + two cross-term accumulators)
 //   warps 4-7: accumulate + epilogue, one TMEM lane (= one output pixel) per thread: every finished
@@ -357,7 +357,17 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // One lane per operand copy (A x, A lo, B x, B lo), all four walking the same K loop; (r, s, kc) advance
+        // incrementally -- no divisions in the loop.  Measured (round 1): the feed alone (no MMAs issued) runs at
+        // ~950 cycles per 64 KB K block with the 3-stage ring = TMA latency x bytes in flight, against ~870 cycles
+        // of 3xTF32 MMA work per K block; the two overlap only partly (1450 cycles per K block end to end).
+        constexpr int NL = PASSES == 3 ? 4 : 2;              // copies per stage
+        if (lane < NL) {
+            const bool is_a = PASSES == 3 ? lane < 2 : lane == 0;
+            const bool is_lo = PASSES == 3 && (lane & 1);
+            const CUtensorMap* map = is_a ? (is_lo ? &tmA_lo : &tmA_hi) : (is_lo ? &tmB_lo : &tmB_hi);
+            const int dst_off = PASSES == 3 ? (is_a ? (is_lo ? C::A_BYTES : 0) : 2 * C::A_BYTES + (is_lo ? C::B_BYTES : 0))
+                                            : (is_a ? 0 : C::A_BYTES);
             int stage = 0;
             uint32_t phase = 0;
             for (int e = 0; e < sched.nseg; ++e) {
@@ -365,67 +375,50 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const int t = sg.tile;
                 const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
                 const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
-                const int iw0 = (tw << p.TW_log2) * p.stride - p.pad, ih0 = th * p.TH * p.stride - p.pad;
+                const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
+                const int iw0 = ow0 * p.stride - p.pad, ih0 = oh0 * p.stride - p.pad;
                 const int n0 = n_tile * BN;
-                const int k_end = min(sg.c1 * kChunkK, k_iters);
-                for (int k = sg.c0 * kChunkK; k < k_end; ++k) {
-                    const int kc = k % p.kc_blocks, rs = k / p.kc_blocks, s = rs % p.S, r = rs / p.S;
+                // correlation: chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
+                const int bw0 = (ow0 - p.corr_r) * p.stride - p.pad;
+                const int bh0 = (oh0 - p.corr_r + 4 * n_tile) * p.stride - p.pad;
+                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                int kc = k_beg % p.kc_blocks, rs = k_beg / p.kc_blocks, s = rs % p.S, r = rs / p.S;
+                for (int k = k_beg; k < k_end; ++k) {
                     mbar_wait_sleep(&empty[stage], phase ^ 1);
-                    uint8_t* st = smem + stage * C::STAGE_BYTES;
-                    const int kcol = k * kBlockK;
+                    uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
+                    uint64_t* fbar = &full[stage];
                     if (PAIR) {
                         // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
-                        const uint32_t fb = map_to_cta(smem_u32(&full[stage]), 0);
-                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
-                        else mbar_arrive_remote(fb);
-                        tma_load_4d_pair(st, &tmA_hi, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
-                        const int brow = n0 + (int)crank * (BN / 2);
-                        if (PASSES == 3) {
-                            tma_load_4d_pair(st + C::A_BYTES, &tmA_lo, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
-                            tma_load_2d_pair(st + 2 * C::A_BYTES, &tmB_hi, fb, kcol, brow);
-                            tma_load_2d_pair(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, fb, kcol, brow);
-                        } else {
-                            tma_load_2d_pair(st + C::A_BYTES, &tmB_hi, fb, kcol, brow);
+                        const uint32_t fb = map_to_cta(smem_u32(fbar), 0);
+                        if (lane == 0) {
+                            if (crank == 0) mbar_expect_tx(fbar, 2 * C::STAGE_BYTES);
+                            else mbar_arrive_remote(fb);
                         }
-                        if (++stage == C::STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                        continue;
-                    }
-                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                    if (p.stem) {
-                        // filter row r of the stem: 32 consecutive floats (8 pixels x 4 channels) of padded
-                        // input row 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
-                        const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
-                        tma_load_5d(st, &tmA_hi, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
-                        if (PASSES == 3)
-                            tma_load_5d(st + C::A_BYTES, &tmA_lo, &full[stage], 0, ow0, r & 1, oh0 + (r >> 1), img);
+                        if (is_a) tma_load_4d_pair(dst, map, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        else tma_load_2d_pair(dst, map, fb, k * kBlockK, n0 + (int)crank * (BN / 2));
                     } else {
-                        tma_load_4d(st, &tmA_hi, &full[stage], kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
-                        if (PASSES == 3)
-                            tma_load_4d(st + C::A_BYTES, &tmA_lo, &full[stage], kc * kBlockK, iw0 + s * p.dil,
-                                        ih0 + r * p.dil, img);
-                    }
-                    if (CORR) {
-                        // chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
-                        const int bw0 = ((tw << p.TW_log2) - p.corr_r) * p.stride - p.pad;
-                        const int bh0 = (th * p.TH - p.corr_r + 4 * n_tile) * p.stride - p.pad;
-                        if (PASSES == 3) {
-                            tma_load_4d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
-                            tma_load_4d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kc * kBlockK, bw0, bh0, img);
+                        if (lane == 0) mbar_expect_tx(fbar, C::STAGE_BYTES);
+                        if (is_a) {
+                            // stem: filter row r = 32 consecutive floats (8 pixels x 4 channels) of padded input row
+                            // 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
+                            if (p.stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
+                            else tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        } else if (CORR) {
+                            tma_load_4d(dst, map, fbar, kc * kBlockK, bw0, bh0, img);
                         } else {
-                            tma_load_4d(st + C::A_BYTES, &tmB_hi, &full[stage], kc * kBlockK, bw0, bh0, img);
+                            tma_load_2d(dst, map, fbar, k * kBlockK, n0);
                         }
-                    } else if (PASSES == 3) {
-                        tma_load_2d(st + 2 * C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
-                        tma_load_2d(st + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full[stage], kcol, n0);
-                    } else {
-                        tma_load_2d(st + C::A_BYTES, &tmB_hi, &full[stage], kcol, n0);
                     }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
+                    }
+                    if (++kc == p.kc_blocks) {
+                        kc = 0;
+                        if (++s == p.S) {
+                            s = 0;
+                            ++r;
+                        }
                     }
                 }
             }
@@ -441,6 +434,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         // whole tile in their own TMEM buffer.  TMEM: main[2] | cross[2], BN columns each.
         if (lane == 0 && crank == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : make_idesc<BN>();
+            const uint64_t desc0 = make_smem_desc(smem_u32(smem));     // stage s / operand o: + (byte offset >> 4)
             int stage = 0, cbuf = 0, local = 0;
             uint32_t phase = 0, cphase = 0;
             for (; local < sched.nseg; ++local) {
@@ -461,12 +455,11 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const uint32_t d_main = tmem_base + cbuf * BN;
                     mbar_wait_sleep(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint64_t a_hi = make_smem_desc(st);
+                    const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
                     if (PASSES == 3) {
-                        const uint64_t a_lo = make_smem_desc(st + C::A_BYTES);
-                        const uint64_t b_hi = make_smem_desc(st + 2 * C::A_BYTES);
-                        const uint64_t b_lo = make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES);
+                        const uint64_t a_lo = a_hi + (C::A_BYTES >> 4);
+                        const uint64_t b_hi = a_hi + (2 * C::A_BYTES >> 4);
+                        const uint64_t b_lo = a_hi + ((2 * C::A_BYTES + C::B_BYTES) >> 4);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
@@ -481,7 +474,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             }
                         }
                     } else {
-                        const uint64_t b_hi = make_smem_desc(st + C::A_BYTES);
+                        const uint64_t b_hi = a_hi + (C::A_BYTES >> 4);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                             const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
