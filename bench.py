@@ -153,7 +153,7 @@ def op_microbench(flush, hbm_gbs):
         oc, oh, ow = ops.correlation_shape(Hh, Ww, *p)
         from d2t_b200 import conv as dc
         # tensor-core kernel on the engine's native layout (split NHWC in, NCHW out) ...
-        layer = dc.CorrLayer(dc.SplitTensor.from_nchw(a), dc.SplitTensor.from_nchw(b), p[0], p[2], p[3], passes=3, want_nchw=True)
+        layer = dc.CorrLayer(dc.ActTensor.from_nchw(a), dc.ActTensor.from_nchw(b), p[0], p[2], p[3], passes=3, want_nchw=True)
         ms = time_kernel(layer.run, 20, flush)
         # ... through the reference-layout operator (adds the two NCHW -> split-NHWC re-layouts) ...
         ms_api = time_kernel(lambda: ops.correlation_forward(a, b, *p), 10, flush)

@@ -187,11 +187,11 @@ int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
  * Replaces the cuDNN convolutions + eval-mode BatchNorm + ReLU the reference reaches through
  * torch.nn for the ResNet-101 trunk and the heads (faster_rcnn/resnet.py:66-129, 258-312, 333-344;
  * faster_rcnn/rfcn.py:49-53; rpn/rpn.py:28-36, 62-71).
- * Activations are NHWC fp32 "split" tensors: the pair (x, lo) with lo = x - trunc13(x), trunc13 =
- * clearing the low 13 mantissa bits.  kind::tf32 reads x as hi = trunc13(x) (the hardware ignores
- * those bits), so the arrays named *_hi below hold the plain fp32 values and *_lo the exact
- * remainders.  passes = 3 evaluates hi*hi + hi*lo + lo*hi on the tensor cores (fp32-level
- * accuracy); passes = 1 is a plain single TF32 pass on x alone. */
+ * Activations are plain fp32 NHWC tensors [N, H, W, cstride].  Weights are packed once by
+ * d2t_conv_pack_weights into the pair (w, w_lo), w_lo = w - trunc13(w) (trunc13 = low 13 mantissa
+ * bits cleared).  kind::tf32 reads an fp32 operand as its truncation, so passes = 3 evaluates
+ * hi*hi + hi*lo + lo*hi on the tensor cores (fp32-level accuracy; the activation lo tile is derived
+ * in shared memory); passes = 1 is a plain single TF32 pass. */
 typedef struct d2t_conv_desc {
     int N, H, W;              /* input [N, H, W, in_cstride] */
     int Cin;                  /* input channels read, a multiple of 32 (zero padded) */
@@ -200,58 +200,56 @@ typedef struct d2t_conv_desc {
     int stride, pad, dil;
     int passes;               /* 3 or 1 */
     int relu;
-    int out_cstride;          /* channels per pixel of the NHWC output buffers */
+    int out_cstride;          /* channels per pixel of the NHWC output buffer */
     int out_coffset;          /* this conv writes channels [out_coffset, out_coffset + Cout) */
-    int res_cstride;          /* channels per pixel of the residual buffers (0: = Cout) */
+    int res_cstride;          /* channels per pixel of the residual buffer (0: = Cout) */
 } d2t_conv_desc;
 typedef struct d2t_conv_plan d2t_conv_plan;
 
-/* out = relu?( scale[c] * conv(in, w) + shift[c] + (res_hi + res_lo) ).  scale / shift / res_* /
- * out_hi+out_lo / out_nchw may be NULL (at least one output is required); out_nchw is a plain
- * fp32 [N, Cout, OH, OW] copy for consumers that keep the reference's layout.  The plan captures
- * the pointers (TMA tensor maps); buffers must outlive it.  Returns NULL on error. */
-d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in_hi, const float* in_lo,
-                                    const float* w_hi, const float* w_lo, const float* scale,
-                                    const float* shift, const float* res_hi, const float* res_lo,
-                                    float* out_hi, float* out_lo, float* out_nchw);
+/* out = relu?( scale[c] * conv(in, w) + shift[c] + res ).  scale / shift / res / out / out_nchw may
+ * be NULL (at least one output is required); out_nchw is a plain fp32 [N, Cout, OH, OW] copy for
+ * consumers that keep the reference's layout.  The plan captures the pointers (TMA tensor maps);
+ * buffers must outlive it.  Plans of one device share a small stream-K scratch, so they must not
+ * run concurrently on different streams.  Returns NULL on error. */
+d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in, const float* w_hi,
+                                    const float* w_lo, const float* scale, const float* shift,
+                                    const float* res, float* out, float* out_nchw);
 void d2t_conv_plan_destroy(d2t_conv_plan* plan);
-/* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid} */
+/* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid*10 + pair_mode} */
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);
 int d2t_conv_plan_run(const d2t_conv_plan* plan, cudaStream_t stream);
 
-/* Cross-frame correlation (correlation/src/correlation_cuda_kernel.cu:34-106) for kernel_size 1,
- * stride1 == stride2 = stride, 1 <= max_displacement/stride <= 8, on the same tensor-core pipeline:
- * in1 / in2 are split NHWC [N, H, W, in_cstride] (C % 32 == 0 channels read, c_real of them
- * meaningful: the divisor); the (2r+1)^2-channel result goes to
- * channels [out_coffset, ...) of a split NHWC buffer and/or to a plain fp32 NCHW tensor. */
-d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int in_cstride, int pad, int max_displacement,
-                                    int stride, int passes, const float* in1_hi, const float* in1_lo,
-                                    const float* in2_hi, const float* in2_lo, float* out_hi, float* out_lo,
-                                    int out_cstride, int out_coffset, float* out_nchw);
-
-/* OIHW fp32 -> [Cout][R*S][cin_pad] hi / lo (lo may be NULL) */
-int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
-                          float* w_hi, float* w_lo, cudaStream_t stream);
 /* The 7x7 stride-2 pad-3 stem conv (faster_rcnn/resnet.py:116) on the same kernel: the image is
- * first packed by d2t_stem_pack_input into zero-bordered NHWC4 buffers [N, (H+7)&~1, W+8, 4] and
- * the filter by d2t_stem_pack_weights into [Cout][7][32]; output is split NHWC [N, OH, OW, out_cstride]. */
-d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in_hi,
-                                         const float* in_lo, const float* w_hi, const float* w_lo,
-                                         const float* scale, const float* shift, int relu,
-                                         float* out_hi, float* out_lo, int out_cstride);
-int d2t_stem_pack_input(const float* x_nchw, int N, int C, int H, int W, float* hi, float* lo,
-                        cudaStream_t stream);
+ * first packed by d2t_stem_pack_input into a zero-bordered NHWC4 buffer [N, (H+7)&~1, W+8, 4] and
+ * the filter by d2t_stem_pack_weights into [Cout][7][32] (w, w_lo); output NHWC [N, OH, OW, out_cstride]. */
+d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in,
+                                         const float* w_hi, const float* w_lo, const float* scale,
+                                         const float* shift, int relu, float* out, int out_cstride);
+int d2t_stem_pack_input(const float* x_nchw, int N, int C, int H, int W, float* packed, cudaStream_t stream);
 int d2t_stem_pack_weights(const float* w_oihw, int Cout, int Cin, float* w_hi, float* w_lo,
                           cudaStream_t stream);
-/* plain fp32 NCHW -> channels [c_offset, c_offset + c_width) of a split NHWC tensor with c_stride
- * channels per pixel (the C source channels, then zeros); and back */
-int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, int c_offset,
-                           int c_width, float* hi, float* lo, cudaStream_t stream);
-int d2t_nhwc_split_to_nchw(const float* hi, const float* lo, int N, int C, int H, int W,
-                           int c_stride, int c_offset, float* out, cudaStream_t stream);
-/* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on split NHWC (faster_rcnn/resnet.py:120) */
-int d2t_maxpool3x3s2_nhwc(const float* in_hi, const float* in_lo, int N, int H, int W, int C,
-                          float* out_hi, float* out_lo, cudaStream_t stream);
+
+/* Cross-frame correlation (correlation/src/correlation_cuda_kernel.cu:34-106) for kernel_size 1,
+ * stride1 == stride2 = stride, 1 <= max_displacement/stride <= 8, on the same tensor-core pipeline:
+ * in1 / in2 are NHWC [N, H, W, in_cstride] (C % 32 == 0 channels read, c_real of them meaningful:
+ * the divisor); the (2r+1)^2-channel result goes to channels [out_coffset, ...) of an NHWC buffer
+ * and/or to a plain fp32 NCHW tensor. */
+d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int in_cstride, int pad,
+                                    int max_displacement, int stride, int passes, const float* in1,
+                                    const float* in2, float* out, int out_cstride, int out_coffset,
+                                    float* out_nchw);
+
+/* OIHW fp32 -> [Cout][R*S][cin_pad] (w, w_lo); w_lo may be NULL */
+int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+                          float* w_hi, float* w_lo, cudaStream_t stream);
+/* plain fp32 NCHW -> channels [c_offset, c_offset + c_width) of an NHWC tensor with c_stride channels
+ * per pixel (the C source channels, then zeros); and back */
+int d2t_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,
+                     float* out, cudaStream_t stream);
+int d2t_nhwc_to_nchw(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, float* out,
+                     cudaStream_t stream);
+/* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on NHWC (faster_rcnn/resnet.py:120) */
+int d2t_maxpool3x3s2_nhwc(const float* in, int N, int H, int W, int C, float* out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

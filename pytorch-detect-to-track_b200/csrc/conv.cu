@@ -20,18 +20,22 @@
 //
 // Precision.  The reference computes these convolutions in fp32.  tcgen05 has no fp32 kind;
 // kind::tf32 reads fp32 containers and IGNORES the low 13 mantissa bits (verified on B200:
-// scripts/tf32_trunc_probe.py gives bit-identical results with those bits cleared or not).  Every
-// tensor is therefore kept as the pair (x, lo): x itself -- which the tensor core reads as
-// hi = trunc13(x) -- and lo = x - trunc13(x), exactly representable.  A K-block issues THREE MMAs,
+// scripts/tf32_trunc_probe.py gives bit-identical results with those bits cleared or not).  An
+// operand x is therefore used twice: as itself -- which the tensor core reads as hi = trunc13(x) --
+// and as lo = x - trunc13(x), exactly representable.  A K-block issues THREE MMAs,
 // hi*hi + hi*lo + lo*hi ("3xTF32"); the dropped lo*lo term is <= 2^-22 relative, i.e. fp32-level
-// accuracy at one third of the TF32 rate -- still ~5x the fp32 SIMT pipe.  PASSES = 1 runs the plain
-// single-pass TF32 conv on x alone (~1e-3 relative) and is reported separately, never as the parity
-// number.  (Argument names keep "hi" for the x array.)
+// accuracy at one third of the TF32 rate -- still ~5x the fp32 SIMT pipe.  Weights are packed once
+// as (w, w_lo) matrices; ACTIVATIONS ARE PLAIN fp32 NHWC TENSORS in HBM: only x travels through
+// the TMA, and two "converter" warps derive the lo tile in shared memory (same swizzled address,
+// elementwise) while the stage waits for its turn -- activation traffic is not doubled.
+// PASSES = 1 runs the plain single-pass TF32 conv (~1e-3 relative) and is reported separately,
+// never as the parity number.
 //
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
 //   warp 0   : TMA producer (one lane per operand copy), NS-stage ring of {A x, A lo, B x, B lo}
 //   warp 1   : MMA issuer  (one elected lane), tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8
 //   warp 2   : TMEM allocation (two ping-pong chunk accumulators + two cross-term accumulators)
+//   warps 2-3: converters (3-pass mode): lo = x - trunc13(x) for the activation tile(s) of each landed stage
 //   warps 4-7: accumulate + epilogue, one TMEM lane (= one output pixel) per thread: every finished
 //              K chunk is pulled out of TMEM (tcgen05.ld) and added into fp32 registers, then
 //              scale/shift -> + residual -> ReLU -> re-split into hi/lo -> NHWC stores (and / or a
@@ -54,6 +58,7 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;       // warps 4..11 are the epilogue: two groups of 4 (warp % 4 = TMEM lane quarter),
 constexpr int kEpiThreads = 256;   // group g owns columns [g*BN/2, (g+1)*BN/2) of the tile
 constexpr int kChunkK = 8;         // k-blocks accumulated in TMEM before the partial sum moves to registers
+constexpr int kCvtThreads = 64;    // warps 2-3 derive the lo tiles
 
 struct ConvArgs {
     int N, OH, OW, Cout;
@@ -64,12 +69,10 @@ struct ConvArgs {
     int stem;                      // 1: A comes through the rank-5 "row window" map of the 7x7 stride-2 stem
     const float* scale;            // [Cout] or null (= 1)
     const float* shift;            // [Cout] or null (= 0)
-    const float* res_hi;           // NHWC [N, OH, OW, res_cstride] or null
-    const float* res_lo;
+    const float* res;              // NHWC [N, OH, OW, res_cstride] or null
     int res_cstride;
     int relu;
-    float* out_hi;                 // NHWC [N, OH, OW, out_cstride], channels [out_coffset, +Cout); or null
-    float* out_lo;
+    float* out;                    // NHWC [N, OH, OW, out_cstride], channels [out_coffset, +Cout); or null
     int out_cstride, out_coffset;
     float* out_nchw;               // plain fp32 [N, Cout, OH, OW] or null
     // correlation mode (CORR): B operand = halo rows of the second frame, see corr section below
@@ -134,11 +137,11 @@ struct Cfg {
     static constexpr int A_BYTES = kBlockM * kBlockK * 4;             // 16 KB
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * kBlockK * 4;   // per CTA: a CTA pair holds half of B each
     static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // hi (+ lo)
-    static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);   // smem per stage: A x | A lo | B x | B lo
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int OUT_STAGE_BYTES = 2 * kBlockM * 128;        // one [128 x 32] fp32 slab per epilogue group (TMA store)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/;
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
     static constexpr int TMEM_COLS = (PASSES == 3 ? 4 : 2) * BN;      // power of two >= 32 for BN in {64,128}
 };
@@ -177,19 +180,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
-}
-__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t mbar_leader, int c0, int c1,
-                                                 int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t mbar_leader, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_leader), "r"(c0), "r"(c1)
-        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
@@ -284,9 +274,10 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // are multicast to both CTAs' `empty` / `tfull` barriers.
 template <int BN, int PASSES, bool CORR, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
+                const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
+                const __grid_constant__ CUtensorMap tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
+                const __grid_constant__ CUtensorMap tmO,      // NHWC output (TMA store)
                 const ConvArgs p) {
     using C = Cfg<BN, PASSES, PAIR>;
     extern __shared__ uint8_t smem_raw[];
@@ -299,7 +290,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue: chunk buffer complete
     uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA: chunk buffer drained
     uint64_t* xempty = tempty + 2;                // [2]        epilogue -> MMA: cross-term buffer read
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + 2);
+    uint64_t* cvt = xempty + 2;                   // [STAGES]   converters -> MMA: lo tile(s) of the stage written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cvt + C::STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CS = PAIR ? 2 : 1;               // CTAs per work unit
@@ -310,21 +302,16 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int k_iters = p.R * p.S * p.kc_blocks;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmA);
         prefetch_tmap(&tmB_hi);
-        if (PASSES == 3) {
-            prefetch_tmap(&tmA_lo);
-            prefetch_tmap(&tmB_lo);
-        }
-        if (!CORR && p.out_hi) {
-            prefetch_tmap(&tmO_hi);
-            prefetch_tmap(&tmO_lo);
-        }
+        if (PASSES == 3 && !CORR) prefetch_tmap(&tmB_lo);
+        if (!CORR && p.out) prefetch_tmap(&tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
-            mbar_init(&full[i], CS);                       // one producer arrival per CTA of the pair
+            mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
+            mbar_init(&cvt[i], CS * kCvtThreads);          // (leader's copy collects both CTAs' converters)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -361,13 +348,12 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         // incrementally -- no divisions in the loop.  Measured (round 1): the feed alone (no MMAs issued) runs at
         // ~950 cycles per 64 KB K block with the 3-stage ring = TMA latency x bytes in flight, against ~870 cycles
         // of 3xTF32 MMA work per K block; the two overlap only partly (1450 cycles per K block end to end).
-        constexpr int NL = PASSES == 3 ? 4 : 2;              // copies per stage
+        constexpr int NL = (PASSES == 3 && !CORR) ? 3 : 2;   // TMA copies per stage: A x, B x (, B lo: weights only)
+        constexpr int TMA_BYTES = C::A_BYTES + (NL - 1) * C::B_BYTES;
         if (lane < NL) {
-            const bool is_a = PASSES == 3 ? lane < 2 : lane == 0;
-            const bool is_lo = PASSES == 3 && (lane & 1);
-            const CUtensorMap* map = is_a ? (is_lo ? &tmA_lo : &tmA_hi) : (is_lo ? &tmB_lo : &tmB_hi);
-            const int dst_off = PASSES == 3 ? (is_a ? (is_lo ? C::A_BYTES : 0) : 2 * C::A_BYTES + (is_lo ? C::B_BYTES : 0))
-                                            : (is_a ? 0 : C::A_BYTES);
+            const bool is_a = lane == 0;
+            const CUtensorMap* map = is_a ? &tmA : (lane == 1 ? &tmB_hi : &tmB_lo);
+            const int dst_off = PASSES == 3 ? (is_a ? 0 : 2 * C::A_BYTES + (lane == 2 ? C::B_BYTES : 0)) : (is_a ? 0 : C::A_BYTES);
             int stage = 0;
             uint32_t phase = 0;
             for (int e = 0; e < sched.nseg; ++e) {
@@ -388,16 +374,12 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
                     uint64_t* fbar = &full[stage];
                     if (PAIR) {
-                        // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
-                        const uint32_t fb = map_to_cta(smem_u32(fbar), 0);
-                        if (lane == 0) {
-                            if (crank == 0) mbar_expect_tx(fbar, 2 * C::STAGE_BYTES);
-                            else mbar_arrive_remote(fb);
-                        }
-                        if (is_a) tma_load_4d_pair(dst, map, fb, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
-                        else tma_load_2d_pair(dst, map, fb, k * kBlockK, n0 + (int)crank * (BN / 2));
+                        // each CTA stages its own A tile and its half of the weight tile (completion: own barrier)
+                        if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
+                        if (is_a) tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        else tma_load_2d(dst, map, fbar, k * kBlockK, n0 + (int)crank * (BN / 2));
                     } else {
-                        if (lane == 0) mbar_expect_tx(fbar, C::STAGE_BYTES);
+                        if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
                         if (is_a) {
                             // stem: filter row r = 32 consecutive floats (8 pixels x 4 channels) of padded input row
                             // 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
@@ -454,6 +436,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                     const uint32_t d_main = tmem_base + cbuf * BN;
                     mbar_wait_sleep(&full[stage], phase);
+                    if (PASSES == 3 || PAIR) mbar_wait_sleep(&cvt[stage], phase);   // lo tiles written (pair: peer landed too)
                     tc_fence_after();
                     const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
                     if (PASSES == 3) {
@@ -498,7 +481,55 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 }
             }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp < kEpiWarp0) {
+        // ===================== converters (warps 2-3) =====================
+        // lo = x - trunc13(x) for the activation tile of every landed stage (and for the second frame's tile in
+        // correlation mode): same swizzled address in the stage's "lo" slot, so the layout needs no thought.
+        // In a CTA pair the converters also carry the "my copies have landed" signal to the leader: each CTA's TMA
+        // completes on its OWN `full` barrier, and the leader's MMA thread waits for both CTAs' cvt arrivals.
+        if (PASSES == 3 || PAIR) {
+            const int ct = threadIdx.x - 64;                       // 0..63
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int e = 0; e < sched.nseg; ++e) {
+                const Seg sg = sched.get(e);
+                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                for (int k = k_beg; k < k_end; ++k) {
+                    mbar_wait_sleep(&full[stage], phase);           // this CTA's copies of the stage have landed
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    const float4* ax = reinterpret_cast<const float4*>(st);
+                    float4* al = reinterpret_cast<float4*>(st + C::A_BYTES);
+#pragma unroll 4
+                    for (int i = ct; i < (PASSES == 3 ? C::A_BYTES / 16 : 0); i += kCvtThreads) {
+                        const float4 v = ax[i];
+                        al[i] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
+                                            v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                            v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
+                                            v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                    }
+                    if (CORR && PASSES == 3) {
+                        const float4* bx = reinterpret_cast<const float4*>(st + 2 * C::A_BYTES);
+                        float4* bl = reinterpret_cast<float4*>(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll 4
+                        for (int i = ct; i < C::B_BYTES / 16; i += kCvtThreads) {
+                            const float4 v = bx[i];
+                            bl[i] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
+                                                v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                                v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
+                                                v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                        }
+                    }
+                    fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                    if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(&cvt[stage]), 0));
+                    else mbar_arrive(&cvt[stage]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
         // ===================== epilogue =====================
         const int q = (warp - kEpiWarp0) & 3;              // TMEM lane quarter of this warp
         const int grp = (warp - kEpiWarp0) >> 2;           // column half of the tile this warp owns
@@ -601,12 +632,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         const float val = __fdiv_rn(acc[rh * 32 + cl], p.corr_nelems);   // kernel.cu:100
                         if (p.out_nchw)
                             p.out_nchw[(((size_t)img * D * D + tc0 + cl) * p.OH + oh) * p.OW + ow] = val;
-                        if (p.out_hi) {
-                            const size_t o = pix * p.out_cstride + p.out_coffset + tc0 + cl;
-                            const float h = __uint_as_float(__float_as_uint(val) & 0xffffe000u);
-                            p.out_hi[o] = val;
-                            p.out_lo[o] = val - h;
-                        }
+                        if (p.out) p.out[pix * p.out_cstride + p.out_coffset + tc0 + cl] = val;
                     }
                 }
                 (void)r;
@@ -641,8 +667,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         v[j] = v[j] * sc + sh;
                     }
                 }
-                if (p.res_hi && pix_ok) {
-                    const float* rh = p.res_hi + pix * p.res_cstride + ch0;     // the "hi" array is the full fp32 value
+                if (p.res && pix_ok) {
+                    const float* rh = p.res + pix * p.res_cstride + ch0;
                     if (full16) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
@@ -667,7 +693,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         if (full16 || ch0 + j < p.Cout) o[j * cs] = v[j];     // lanes = consecutive ow: coalesced
                 }
             }
-            if (p.out_hi) {
+            if (p.out) {
                 // NHWC output through shared memory + TMA store: the 128 threads of this group lay their rows
                 // (32 channels = 128 B each) into a SWIZZLE_128B slab, then ONE bulk tensor store writes the
                 // [TH x TW x 32] box as full lines; pixels / channels outside the tensor are clipped by the TMA.
@@ -678,25 +704,15 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const int chs = n0 + cofs + sl * 32;
                     if (chs >= p.Cout) continue;              // (uniform over the group)
                     const float* v = acc + sl * 32;
+                    if (m == 0) tma_store_wait_read();        // the previous store has read the slab
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {    // 0: hi, 1: lo
-                        if (m == 0) tma_store_wait_read();    // the previous store has read the slab
-                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float h0 = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
-                            const float h1 = __uint_as_float(__float_as_uint(v[j + 1]) & 0xffffe000u);
-                            const float h2 = __uint_as_float(__float_as_uint(v[j + 2]) & 0xffffe000u);
-                            const float h3 = __uint_as_float(__float_as_uint(v[j + 3]) & 0xffffe000u);
-                            const float4 o = part == 0 ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])
-                                                       : make_float4(v[j] - h0, v[j + 1] - h1, v[j + 2] - h2, v[j + 3] - h3);
-                            *reinterpret_cast<float4*>(slab + row_off + ((((uint32_t)j >> 2) ^ sw) << 4)) = o;
-                        }
-                        fence_proxy_async();
-                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-                        if (m == 0)
-                            tma_store_4d(part == 0 ? &tmO_hi : &tmO_lo, slab, chs, tw << p.TW_log2, th * p.TH, img);
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(slab + row_off + ((((uint32_t)j >> 2) ^ sw) << 4)) =
+                            make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                    if (m == 0) tma_store_4d(&tmO, slab, chs, tw << p.TW_log2, th * p.TH, img);
                 }
             }
             }   // !CORR
@@ -798,26 +814,23 @@ int sk_grid(int tiles, int k_iters) {
 
 namespace d2t {
 namespace {
-// split NHWC output [N, OH, OW, cstride], channels [coff, coff + Cout): box = one 32-channel slab of a tile
-bool encode_out_maps(CUtensorMap* hi, CUtensorMap* lo, float* out_hi, float* out_lo, int N, int OH, int OW, int Cout,
-                     int cstride, int coff, int TH, int TW) {
+// NHWC output [N, OH, OW, cstride], channels [coff, coff + Cout): box = one 32-channel slab of a tile
+bool encode_out_map(CUtensorMap* map, float* out, int N, int OH, int OW, int Cout, int cstride, int coff, int TH,
+                    int TW) {
     const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
     const cuuint64_t str[3] = {(cuuint64_t)cstride * 4, (cuuint64_t)OW * cstride * 4, (cuuint64_t)OH * OW * cstride * 4};
     const cuuint32_t box[4] = {32u, (cuuint32_t)TW, (cuuint32_t)TH, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    return encode(hi, out_hi + coff, 4, dims, str, box, estr, "out hi") &&
-           encode(lo, out_lo + coff, 4, dims, str, box, estr, "out lo");
+    return encode(map, out + coff, 4, dims, str, box, estr, "out");
 }
 }  // namespace
 }  // namespace d2t
 
 struct d2t_conv_plan {
-    alignas(64) CUtensorMap tmA_hi;
-    alignas(64) CUtensorMap tmA_lo;
+    alignas(64) CUtensorMap tmA;
     alignas(64) CUtensorMap tmB_hi;
     alignas(64) CUtensorMap tmB_lo;
-    alignas(64) CUtensorMap tmO_hi;
-    alignas(64) CUtensorMap tmO_lo;
+    alignas(64) CUtensorMap tmO;
     ConvArgs args;
     int BN, passes, grid, corr;
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
@@ -844,8 +857,8 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = PAIR ? 2 : 1;
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_tf32<BN, PASSES, CORR, PAIR>, pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                   pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, args),
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_tf32<BN, PASSES, CORR, PAIR>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
+                                   args),
                 "conv_igemm_tf32 launch");
     return 1;
 }
@@ -881,11 +894,10 @@ static int max_pairs() {
     return n;
 }
 
-extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const float* in_hi, const float* in_lo,
+extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const float* in,
                                                const float* w_hi, const float* w_lo, const float* scale,
-                                               const float* shift, const float* res_hi, const float* res_lo,
-                                               float* out_hi, float* out_lo, float* out_nchw) {
-    if (!d || !in_hi || !w_hi || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->R <= 0 ||
+                                               const float* shift, const float* res, float* out, float* out_nchw) {
+    if (!d || !in || !w_hi || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->R <= 0 ||
         d->S <= 0 || d->stride <= 0 || d->dil <= 0 || d->pad < 0) {
         set_error("d2t_conv_plan_create: bad descriptor");
         return nullptr;
@@ -898,16 +910,12 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
         set_error("d2t_conv_plan_create: passes must be 1 (TF32) or 3 (3xTF32, fp32-accurate)");
         return nullptr;
     }
-    if (d->passes == 3 && (!in_lo || !w_lo)) {
-        set_error("d2t_conv_plan_create: 3-pass mode needs the lo halves of input and weights");
+    if (d->passes == 3 && !w_lo) {
+        set_error("d2t_conv_plan_create: 3-pass mode needs the lo half of the packed weights");
         return nullptr;
     }
-    if ((out_hi && (!out_lo || d->out_cstride % 4 != 0 || d->out_coffset % 4 != 0)) || (!out_hi && !out_nchw)) {
-        set_error("d2t_conv_plan_create: need an output (NHWC hi+lo with 4-aligned channel stride/offset, and/or NCHW)");
-        return nullptr;
-    }
-    if (res_hi && !res_lo) {
-        set_error("d2t_conv_plan_create: residual needs both halves");
+    if ((out && (d->out_cstride % 4 != 0 || d->out_coffset % 4 != 0)) || (!out && !out_nchw)) {
+        set_error("d2t_conv_plan_create: need an output (NHWC with 4-aligned channel stride/offset, and/or NCHW)");
         return nullptr;
     }
     const int OH = (d->H + 2 * d->pad - d->dil * (d->R - 1) - 1) / d->stride + 1;
@@ -940,9 +948,9 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     pl->BN = d->Cout <= 64 ? 64 : 128;
     a.n_tiles = (d->Cout + pl->BN - 1) / pl->BN;
     a.scale = scale; a.shift = shift;
-    a.res_hi = res_hi; a.res_lo = res_lo; a.res_cstride = d->res_cstride > 0 ? d->res_cstride : d->Cout;
+    a.res = res; a.res_cstride = d->res_cstride > 0 ? d->res_cstride : d->Cout;
     a.relu = d->relu;
-    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
+    a.out = out; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
     pl->passes = d->passes; pl->corr = 0;
     // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
@@ -976,22 +984,12 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     const cuuint64_t bstr[1] = {ktot * 4};
     const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pl->pair ? pl->BN / 2 : pl->BN)};
     const cuuint32_t bestr[2] = {1u, 1u};
-    bool ok = encode(&pl->tmA_hi, in_hi, 4, adims, astr, abox, aestr, "A hi") &&
+    bool ok = encode(&pl->tmA, in, 4, adims, astr, abox, aestr, "A") &&
               encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi");
-    if (ok && d->passes == 3)
-        ok = encode(&pl->tmA_lo, in_lo, 4, adims, astr, abox, aestr, "A lo") &&
-             encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo");
-    if (ok && d->passes == 1) {
-        pl->tmA_lo = pl->tmA_hi;
-        pl->tmB_lo = pl->tmB_hi;
-    }
-    if (ok && out_hi)
-        ok = encode_out_maps(&pl->tmO_hi, &pl->tmO_lo, out_hi, out_lo, d->N, OH, OW, d->Cout, d->out_cstride,
-                             d->out_coffset, TH, TW);
-    else if (ok) {
-        pl->tmO_hi = pl->tmA_hi;
-        pl->tmO_lo = pl->tmA_hi;
-    }
+    if (ok && d->passes == 3) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo");
+    if (ok && d->passes == 1) pl->tmB_lo = pl->tmB_hi;
+    if (ok && out) ok = encode_out_map(&pl->tmO, out, d->N, OH, OW, d->Cout, d->out_cstride, d->out_coffset, TH, TW);
+    else if (ok) pl->tmO = pl->tmA;
     if (!ok) {
         free(pl);
         return nullptr;
@@ -1006,12 +1004,11 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
 // pixels start 2 pixels = 32 bytes apart, which a rank-5 tensor map {32, OW, 2, Hp/2, N} with
 // strides {32 B, row, 2 rows, image} expresses directly (overlapping windows): still one TMA copy
 // per (tile, filter row), same kernel, 7 K blocks.
-extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in_hi,
-                                                    const float* in_lo, const float* w_hi, const float* w_lo,
-                                                    const float* scale, const float* shift, int relu, float* out_hi,
-                                                    float* out_lo, int out_cstride) {
-    if (N <= 0 || H < 7 || W < 7 || Cout <= 0 || !in_hi || !w_hi || !out_hi || !out_lo || out_cstride % 4 != 0 ||
-        (passes != 1 && passes != 3) || (passes == 3 && (!in_lo || !w_lo))) {
+extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int passes, const float* in,
+                                                    const float* w_hi, const float* w_lo, const float* scale,
+                                                    const float* shift, int relu, float* out, int out_cstride) {
+    if (N <= 0 || H < 7 || W < 7 || Cout <= 0 || !in || !w_hi || !out || out_cstride % 4 != 0 ||
+        (passes != 1 && passes != 3) || (passes == 3 && !w_lo)) {
         set_error("d2t_conv_stem_plan_create: bad arguments");
         return nullptr;
     }
@@ -1034,8 +1031,8 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.m_tiles = N * a.tiles_h * a.tiles_w;
     pl->BN = Cout <= 64 ? 64 : 128;
     a.n_tiles = (Cout + pl->BN - 1) / pl->BN;
-    a.scale = scale; a.shift = shift; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = Cout; a.relu = relu;
-    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
+    a.scale = scale; a.shift = shift; a.res = nullptr; a.res_cstride = Cout; a.relu = relu;
+    a.out = out; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0; pl->pair = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7);
     {
@@ -1055,16 +1052,11 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     const cuuint64_t bstr[1] = {7 * 32 * 4};
     const cuuint32_t bbox[2] = {32u, (cuuint32_t)pl->BN};
     const cuuint32_t bestr[2] = {1u, 1u};
-    bool ok = encode(&pl->tmA_hi, in_hi, 5, adims, astr, abox, aestr, "stem A hi") &&
+    bool ok = encode(&pl->tmA, in, 5, adims, astr, abox, aestr, "stem A") &&
               encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "stem B hi");
-    if (ok && passes == 3)
-        ok = encode(&pl->tmA_lo, in_lo, 5, adims, astr, abox, aestr, "stem A lo") &&
-             encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "stem B lo");
-    if (ok && passes == 1) {
-        pl->tmA_lo = pl->tmA_hi;
-        pl->tmB_lo = pl->tmB_hi;
-    }
-    if (ok) ok = encode_out_maps(&pl->tmO_hi, &pl->tmO_lo, out_hi, out_lo, N, OH, OW, Cout, out_cstride, 0, TH, TW);
+    if (ok && passes == 3) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "stem B lo");
+    if (ok && passes == 1) pl->tmB_lo = pl->tmB_hi;
+    if (ok) ok = encode_out_map(&pl->tmO, out, N, OH, OW, Cout, out_cstride, 0, TH, TW);
     if (!ok) {
         free(pl);
         return nullptr;
@@ -1073,12 +1065,10 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
 }
 
 extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int in_cstride, int pad, int md, int stride,
-                                               int passes, const float* in1_hi, const float* in1_lo,
-                                               const float* in2_hi, const float* in2_lo, float* out_hi, float* out_lo,
+                                               int passes, const float* in1, const float* in2, float* out,
                                                int out_cstride, int out_coffset, float* out_nchw) {
-    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || md < 0 || stride <= 0 || !in1_hi || !in2_hi ||
-        (passes != 1 && passes != 3) || (passes == 3 && (!in1_lo || !in2_lo)) || (!out_hi && !out_nchw) ||
-        (out_hi && !out_lo)) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || md < 0 || stride <= 0 || !in1 || !in2 ||
+        (passes != 1 && passes != 3) || (!out && !out_nchw)) {
         set_error("d2t_corr_plan_create: bad arguments");
         return nullptr;
     }
@@ -1107,8 +1097,8 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 7) / 8;
     a.m_tiles = N * a.tiles_h * a.tiles_w;
     a.n_tiles = (8 + 2 * r + 3) / 4;                                         // halo chunks of 4 rows
-    a.scale = nullptr; a.shift = nullptr; a.res_hi = nullptr; a.res_lo = nullptr; a.res_cstride = 0; a.relu = 0;
-    a.out_hi = out_hi; a.out_lo = out_lo; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
+    a.scale = nullptr; a.shift = nullptr; a.res = nullptr; a.res_cstride = 0; a.relu = 0;
+    a.out = out; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
     pl->BN = 128; pl->passes = passes; pl->corr = 1; pl->pair = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks);
@@ -1125,17 +1115,10 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(15 * stride + 1), (cuuint32_t)(7 * stride + 1), 1u};
     const cuuint32_t bbox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(31 * stride + 1), (cuuint32_t)(3 * stride + 1), 1u};
     const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
-    bool ok = encode(&pl->tmA_hi, in1_hi, 4, dims, str, abox, estr, "corr A hi") &&
-              encode(&pl->tmB_hi, in2_hi, 4, dims, str, bbox, estr, "corr B hi");
-    if (ok && passes == 3)
-        ok = encode(&pl->tmA_lo, in1_lo, 4, dims, str, abox, estr, "corr A lo") &&
-             encode(&pl->tmB_lo, in2_lo, 4, dims, str, bbox, estr, "corr B lo");
-    if (ok && passes == 1) {
-        pl->tmA_lo = pl->tmA_hi;
-        pl->tmB_lo = pl->tmB_hi;
-    }
-    pl->tmO_hi = pl->tmA_hi;   // unused in correlation mode (direct stores)
-    pl->tmO_lo = pl->tmA_hi;
+    bool ok = encode(&pl->tmA, in1, 4, dims, str, abox, estr, "corr A") &&
+              encode(&pl->tmB_hi, in2, 4, dims, str, bbox, estr, "corr B");
+    pl->tmB_lo = pl->tmB_hi;   // unused: both lo tiles are derived in shared memory
+    pl->tmO = pl->tmA;         // unused in correlation mode (direct stores)
     if (!ok) {
         free(pl);
         return nullptr;

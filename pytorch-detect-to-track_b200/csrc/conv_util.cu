@@ -1,10 +1,10 @@
-// conv_util.cu -- layout / precision-split helpers around the tcgen05 conv kernels (conv.cu).
+// conv_util.cu -- layout helpers around the tcgen05 conv kernels (conv.cu).
 //
-// The conv engine keeps activations as NHWC "split" tensors: the pair (x, lo) with lo = x - trunc13(x)
-// (the tensor core reads x as hi = trunc13(x); see conv.cu).  The x array is called "hi" below.  These kernels move data
-// between that format and the reference's plain fp32 NCHW tensors, pack OIHW weights into the
-// [Cout, R*S*Cin_pad] K-major matrix the weight TMA reads, and implement the stem's
-// MaxPool2d(3, stride 2, padding 0, ceil_mode=True) (/root/reference/lib/model/faster_rcnn/resnet.py:120).
+// The conv engine keeps activations as plain fp32 NHWC tensors; these kernels move data between that layout and
+// the reference's NCHW tensors, pack OIHW weights into the [Cout, R*S*Cin_pad] K-major (w, w_lo) matrices the
+// weight TMA reads (w_lo = w - trunc13(w): the exact remainder of the tensor core's own TF32 truncation, see
+// conv.cu), and implement the stem's MaxPool2d(3, stride 2, padding 0, ceil_mode=True)
+// (/root/reference/lib/model/faster_rcnn/resnet.py:120).
 #include "common.cuh"
 
 namespace d2t {
@@ -17,11 +17,10 @@ inline int grid_for(size_t total, int per_block = 256) {
     return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
-// [N,C,H,W] fp32 -> [N,H,W,cs] hi/lo; channels [C, cs) are zero-filled.  32x32 smem transpose per (n, h).
-// image [N,3,H,W] -> zero-bordered NHWC4 [N, Hp, Wp, 4] hi/lo for the stem (border 3, 4th channel 0);
-// one thread per padded pixel, every element of the buffers is written.
+// image [N,C<=4,H,W] -> zero-bordered NHWC4 [N, Hp, Wp, 4] for the stem (border 3, unused channels 0);
+// one thread per padded pixel, every element of the buffer is written.
 __global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H, int W, int Hp, int Wp,
-                                float4* __restrict__ hi, float4* __restrict__ lo) {
+                                float4* __restrict__ out) {
     const size_t total = (size_t)N * Hp * Wp;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int wp = (int)(idx % Wp), hp = (int)((idx / Wp) % Hp), n = (int)(idx / Wp / Hp);
@@ -29,9 +28,7 @@ __global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (h >= 0 && h < H && w >= 0 && w < W)
             for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)n * C + c) * H + h) * W + w);
-        const float4 a = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
-        hi[idx] = make_float4(v[0], v[1], v[2], v[3]);
-        if (lo) lo[idx] = make_float4(v[0] - a.x, v[1] - a.y, v[2] - a.z, v[3] - a.w);
+        out[idx] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -42,16 +39,14 @@ __global__ void stem_pack_weights(const float* __restrict__ w, int O, int C, flo
         const int col = idx % 32, r = (idx / 32) % 7, o = idx / 32 / 7;
         const int s = col >> 2, c = col & 3;
         const float v = (s < 7 && c < C) ? __ldg(w + (((size_t)o * C + c) * 7 + r) * 7 + s) : 0.f;
-        const float a = tf32_hi(v);
         hi[idx] = v;
-        if (lo) lo[idx] = v - a;
+        if (lo) lo[idx] = v - tf32_hi(v);
     }
 }
 
+// [N,C,H,W] -> channels [coff, coff + cw) of [N,H,W,cs]: x's C channels, then zeros.  32x32 smem transpose per (n, h).
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, int cw,
-                   float* __restrict__ hi, float* __restrict__ lo) {
-    // writes channels [coff, coff + cw) of each pixel: x's C channels, then zeros
+nchw_to_nhwc(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, int cw, float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -62,30 +57,19 @@ nchw_to_nhwc_split(const float* __restrict__ x, int N, int C, int H, int W, int 
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int w = wt + j, c = ct + tx;
-        if (w < W && c < cw) {
-            const float v = tile[tx][j], a = tf32_hi(v);
-            const size_t o = (((size_t)n * H + h) * W + w) * cs + coff + c;
-            hi[o] = v;
-            if (lo) lo[o] = v - a;
-        }
+        if (w < W && c < cw) out[(((size_t)n * H + h) * W + w) * cs + coff + c] = tile[tx][j];
     }
 }
 
-// [N,H,W,cs] hi(+lo) -> [N,C,H,W] fp32
+// channels [coff, coff + C) of [N,H,W,cs] -> [N,C,H,W]
 __global__ void __launch_bounds__(256)
-nhwc_split_to_nchw(const float* __restrict__ hi, const float* __restrict__ lo, int N, int C, int H, int W, int cs,
-                   int coff, float* __restrict__ out) {
+nhwc_to_nchw(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int j = ty; j < 32; j += 8) {
         const int w = wt + j, c = ct + tx;
-        float v = 0.f;
-        if (w < W && c < C) {
-            const size_t i = (((size_t)n * H + h) * W + w) * cs + coff + c;
-            v = __ldg(hi + i);
-        }
-        tile[j][tx] = v;
+        tile[j][tx] = (w < W && c < C) ? __ldg(x + (((size_t)n * H + h) * W + w) * cs + coff + c) : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -94,7 +78,7 @@ nhwc_split_to_nchw(const float* __restrict__ hi, const float* __restrict__ lo, i
     }
 }
 
-// OIHW -> [O][R*S][cin_pad] hi/lo (zero pad)
+// OIHW -> [O][R*S][cin_pad] (w, w_lo), zero pad
 __global__ void pack_weights(const float* __restrict__ w, int O, int I, int R, int S, int cin_pad,
                              float* __restrict__ hi, float* __restrict__ lo) {
     const size_t total = (size_t)O * R * S * cin_pad;
@@ -103,15 +87,14 @@ __global__ void pack_weights(const float* __restrict__ w, int O, int I, int R, i
         const int rs = (int)((idx / cin_pad) % (R * S));
         const int o = (int)(idx / cin_pad / (R * S));
         const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) : 0.f;
-        const float a = tf32_hi(v);
         hi[idx] = v;
-        if (lo) lo[idx] = v - a;
+        if (lo) lo[idx] = v - tf32_hi(v);
     }
 }
 
-// MaxPool 3x3 stride 2, padding 0, ceil_mode (windows clipped at the border), NHWC: in hi(+lo) -> out hi/lo
-__global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int N, int H, int W,
-                                  int C, int OH, int OW, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+// MaxPool 3x3 stride 2, padding 0, ceil_mode (windows clipped at the border), NHWC, 4 channels per thread
+__global__ void maxpool3x3s2_nhwc(const float* __restrict__ in, int N, int H, int W, int C, int OH, int OW,
+                                  float* __restrict__ out) {
     const int C4 = C >> 2;
     const size_t total = (size_t)N * OH * OW * C4;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -126,14 +109,11 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* 
             for (int s = 0; s < 3; ++s) {
                 const int w = ow * 2 + s;
                 if (w >= W) break;
-                const size_t i = ((((size_t)n * H + h) * W + w) * C >> 2) + c4;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(in_hi) + i);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in) + ((((size_t)n * H + h) * W + w) * C >> 2) + c4);
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
-        float4 a = make_float4(tf32_hi(m.x), tf32_hi(m.y), tf32_hi(m.z), tf32_hi(m.w));
-        reinterpret_cast<float4*>(out_hi)[idx] = m;
-        if (out_lo) reinterpret_cast<float4*>(out_lo)[idx] = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
+        reinterpret_cast<float4*>(out)[idx] = m;
     }
 }
 
@@ -142,26 +122,25 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in_hi, const float* 
 
 using namespace d2t;
 
-extern "C" int d2t_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int c_stride, int c_offset,
-                                      int c_width, float* hi, float* lo, cudaStream_t stream) {
-    D2T_REQUIRE(x && hi && N > 0 && C > 0 && H > 0 && W > 0 && c_offset >= 0 && c_width >= C &&
+extern "C" int d2t_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,
+                                float* out, cudaStream_t stream) {
+    D2T_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0 && c_offset >= 0 && c_width >= C &&
                     c_stride >= c_offset + c_width,
-                "d2t_nchw_to_nhwc_split: bad arguments");
+                "d2t_nchw_to_nhwc: bad arguments");
     dim3 grid((W + 31) / 32, (c_width + 31) / 32, N * H);
-    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc_split: tensor too large for the launch grid");
-    nchw_to_nhwc_split<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, c_width, hi, lo);
-    D2T_CHECK_LAUNCH("nchw_to_nhwc_split");
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc: tensor too large for the launch grid");
+    nchw_to_nhwc<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, c_width, out);
+    D2T_CHECK_LAUNCH("nchw_to_nhwc");
     return 1;
 }
 
-extern "C" int d2t_nhwc_split_to_nchw(const float* hi, const float* lo, int N, int C, int H, int W, int c_stride,
-                                      int c_offset, float* out, cudaStream_t stream) {
-    D2T_REQUIRE(hi && out && N > 0 && C > 0 && H > 0 && W > 0 && c_stride >= c_offset + C,
-                "d2t_nhwc_split_to_nchw: bad arguments");
+extern "C" int d2t_nhwc_to_nchw(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, float* out,
+                                cudaStream_t stream) {
+    D2T_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0 && c_stride >= c_offset + C, "d2t_nhwc_to_nchw: bad arguments");
     dim3 grid((W + 31) / 32, (C + 31) / 32, N * H);
-    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nhwc_split_to_nchw: tensor too large for the launch grid");
-    nhwc_split_to_nchw<<<grid, 256, 0, stream>>>(hi, lo, N, C, H, W, c_stride, c_offset, out);
-    D2T_CHECK_LAUNCH("nhwc_split_to_nchw");
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nhwc_to_nchw: tensor too large for the launch grid");
+    nhwc_to_nchw<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, out);
+    D2T_CHECK_LAUNCH("nhwc_to_nchw");
     return 1;
 }
 
@@ -175,12 +154,11 @@ extern "C" int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int
     return 1;
 }
 
-extern "C" int d2t_stem_pack_input(const float* x, int N, int C, int H, int W, float* hi, float* lo, cudaStream_t stream) {
-    D2T_REQUIRE(x && hi && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "d2t_stem_pack_input: bad arguments");
+extern "C" int d2t_stem_pack_input(const float* x, int N, int C, int H, int W, float* packed, cudaStream_t stream) {
+    D2T_REQUIRE(x && packed && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "d2t_stem_pack_input: bad arguments");
     const int Hp = (H + 7) & ~1, Wp = W + 8;
     const size_t total = (size_t)N * Hp * Wp;
-    stem_pack_input<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(hi),
-                                                         reinterpret_cast<float4*>(lo));
+    stem_pack_input<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(packed));
     D2T_CHECK_LAUNCH("stem_pack_input");
     return 1;
 }
@@ -192,16 +170,15 @@ extern "C" int d2t_stem_pack_weights(const float* w, int Cout, int Cin, float* w
     return 1;
 }
 
-extern "C" int d2t_maxpool3x3s2_nhwc(const float* in_hi, const float* in_lo, int N, int H, int W, int C, float* out_hi,
-                                     float* out_lo, cudaStream_t stream) {
-    D2T_REQUIRE(in_hi && out_hi && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "d2t_maxpool3x3s2_nhwc: bad arguments");
+extern "C" int d2t_maxpool3x3s2_nhwc(const float* in, int N, int H, int W, int C, float* out, cudaStream_t stream) {
+    D2T_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "d2t_maxpool3x3s2_nhwc: bad arguments");
     // ceil((H - 3) / 2) + 1, and the last window must start inside the input (torch pooling rule)
     int OH = (H - 3 + 1) / 2 + 1, OW = (W - 3 + 1) / 2 + 1;
     if ((OH - 1) * 2 >= H) --OH;
     if ((OW - 1) * 2 >= W) --OW;
     D2T_REQUIRE(OH > 0 && OW > 0, "d2t_maxpool3x3s2_nhwc: input too small");
     const size_t total = (size_t)N * OH * OW * (C / 4);
-    maxpool3x3s2_nhwc<<<grid_for(total), 256, 0, stream>>>(in_hi, in_lo, N, H, W, C, OH, OW, out_hi, out_lo);
+    maxpool3x3s2_nhwc<<<grid_for(total), 256, 0, stream>>>(in, N, H, W, C, OH, OW, out);
     D2T_CHECK_LAUNCH("maxpool3x3s2_nhwc");
     return 1;
 }

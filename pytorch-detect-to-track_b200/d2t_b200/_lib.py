@@ -57,18 +57,18 @@ _SIGS = {
     "d2t_proposal_gather": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "d2t_proposal_write_rois": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     # ---- convolution engine
-    "d2t_conv_plan_create": (_p, [_p] * 12),
+    "d2t_conv_plan_create": (_p, [_p] * 9),
     "d2t_conv_plan_destroy": (None, [_p]),
-    "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 6 + [_i, _i, _p]),
+    "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 3 + [_i, _i, _p]),
     "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),
     "d2t_conv_plan_run": (_i, [_p, _p]),
     "d2t_conv_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "d2t_nchw_to_nhwc_split": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "d2t_conv_stem_plan_create": (_p, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i]),
-    "d2t_stem_pack_input": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "d2t_conv_stem_plan_create": (_p, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i]),
+    "d2t_stem_pack_input": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "d2t_stem_pack_weights": (_i, [_p, _i, _i, _p, _p, _p]),
-    "d2t_nhwc_split_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "d2t_maxpool3x3s2_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "d2t_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
 }
 
 _OPTIONAL = set()

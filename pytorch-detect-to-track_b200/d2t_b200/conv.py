@@ -1,9 +1,8 @@
 """Tensor-level front end of the tcgen05 convolution engine (csrc/conv.cu, csrc/conv_util.cu).
 
-``SplitTensor`` is an NHWC fp32 activation kept as an exact two-term TF32 split (hi, lo);
-``ConvLayer`` owns packed weights, the folded BatchNorm / bias vectors, its output buffers and the
-C-ABI plan (TMA tensor maps) that runs it.  Nothing here computes on the CPU; everything is
-enqueued on torch's current stream.
+``ActTensor`` is a plain fp32 NHWC activation buffer; ``ConvLayer`` / ``StemConv`` / ``CorrLayer`` own packed
+weights (w, w_lo), the folded BatchNorm / bias vectors, their output buffers and the C-ABI plan (TMA tensor maps)
+that runs them.  Nothing here computes on the CPU; everything is enqueued on torch's current stream.
 """
 import ctypes as C
 
@@ -21,63 +20,79 @@ def _pad32(c):
     return (c + 31) // 32 * 32
 
 
-class SplitTensor(object):
-    """[N, H, W, cstride] fp32 pair; channels [0, C) are meaningful, the rest are zero."""
+def _p(t):
+    return t.data_ptr() if t is not None else None
 
-    def __init__(self, N, H, W, C_, cstride=None, device="cuda", lo=True):
+
+class ActTensor(object):
+    """[N, H, W, cstride] fp32; channels [0, C) are meaningful, the rest are zero."""
+
+    def __init__(self, N, H, W, C_, cstride=None, device="cuda"):
         self.N, self.H, self.W, self.C = N, H, W, C_
         self.cstride = cstride if cstride is not None else (C_ + 3) // 4 * 4
-        self.hi = torch.zeros(N, H, W, self.cstride, device=device)
-        self.lo = torch.zeros(N, H, W, self.cstride, device=device) if lo else None
+        self.x = torch.zeros(N, H, W, self.cstride, device=device)
 
     @staticmethod
-    def from_nchw(x, cstride=None, lo=True, out=None):
+    def from_nchw(x, cstride=None):
         N, C_, H, W = x.shape
-        t = out if out is not None else SplitTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device, lo)
-        t.load_nchw(x)
-        return t
+        t = ActTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device)
+        return t.load_nchw(x)
 
     def load_nchw(self, x, coffset=0, cwidth=None):
         """write x [N, C, H, W] into channels [coffset, coffset + cwidth) (x's channels, then zeros)"""
         N, C_, H, W = x.shape
         cwidth = cwidth if cwidth is not None else self.cstride - coffset
-        check(lib().d2t_nchw_to_nhwc_split(x.contiguous().data_ptr(), N, C_, H, W, self.cstride, coffset, cwidth,
-                                           self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None,
-                                           _stream()), "d2t_nchw_to_nhwc_split")
+        check(lib().d2t_nchw_to_nhwc(x.contiguous().data_ptr(), N, C_, H, W, self.cstride, coffset, cwidth,
+                                     self.x.data_ptr(), _stream()), "d2t_nchw_to_nhwc")
         ops._count(1)
         return self
 
     def batch_slice(self, n0, n1):
         """view of images [n0, n1) (contiguous in NHWC)"""
-        v = SplitTensor.__new__(SplitTensor)
+        v = ActTensor.__new__(ActTensor)
         v.N, v.H, v.W, v.C, v.cstride = n1 - n0, self.H, self.W, self.C, self.cstride
-        v.hi = self.hi[n0:n1]
-        v.lo = self.lo[n0:n1] if self.lo is not None else None
+        v.x = self.x[n0:n1]
         return v
 
     def to_nchw(self, C_=None, coffset=0):
         C_ = self.C if C_ is None else C_
-        out = torch.empty(self.N, C_, self.H, self.W, device=self.hi.device)
-        check(lib().d2t_nhwc_split_to_nchw(self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None,
-                                           self.N, C_, self.H, self.W, self.cstride, coffset, out.data_ptr(), _stream()),
-              "d2t_nhwc_split_to_nchw")
+        out = torch.empty(self.N, C_, self.H, self.W, device=self.x.device)
+        check(lib().d2t_nhwc_to_nchw(self.x.data_ptr(), self.N, C_, self.H, self.W, self.cstride, coffset,
+                                     out.data_ptr(), _stream()), "d2t_nhwc_to_nchw")
         ops._count(1)
         return out
 
 
 def pack_weights(w, cin_pad=None, lo=True):
-    """OIHW -> ([O, R*S*cin_pad] hi, lo)"""
+    """OIHW -> ([O, R*S*cin_pad] w, w_lo)"""
     O, I, R, S = w.shape
     cin_pad = cin_pad or _pad32(I)
     w = w.detach().contiguous().float()
     hi = torch.empty(O, R * S * cin_pad, device=w.device)
     lo_t = torch.empty_like(hi) if lo else None
-    check(lib().d2t_conv_pack_weights(w.data_ptr(), O, I, R, S, cin_pad, hi.data_ptr(),
-                                      lo_t.data_ptr() if lo else None, _stream()), "d2t_conv_pack_weights")
+    check(lib().d2t_conv_pack_weights(w.data_ptr(), O, I, R, S, cin_pad, hi.data_ptr(), _p(lo_t), _stream()),
+          "d2t_conv_pack_weights")
+    torch.cuda.current_stream().synchronize()   # `w` may be a temporary
     return hi, lo_t
 
 
-class ConvLayer(object):
+class _Planned(object):
+    plan = None
+
+    def run(self):
+        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
+        ops._count(1)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                lib().d2t_conv_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+
+class ConvLayer(_Planned):
     """out = relu?(scale * conv(x, w) + shift + residual) bound to fixed input / output buffers."""
 
     def __init__(self, x, weight, scale=None, shift=None, stride=1, pad=0, dil=1, relu=False, residual=None,
@@ -92,19 +107,17 @@ class ConvLayer(object):
         self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
         OH = (x.H + 2 * pad - dil * (R - 1) - 1) // stride + 1
         OW = (x.W + 2 * pad - dil * (S - 1) - 1) // stride + 1
-        self.out = out if out is not None else (SplitTensor(x.N, OH, OW, O, device=dev) if want_nhwc else None)
+        self.out = out if out is not None else (ActTensor(x.N, OH, OW, O, device=dev) if want_nhwc else None)
         if out_nchw is not None:
             assert tuple(out_nchw.shape) == (x.N, O, OH, OW) and out_nchw.is_contiguous()
         self.out_nchw = out_nchw if out_nchw is not None else (torch.empty(x.N, O, OH, OW, device=dev) if want_nchw else None)
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=_pad32(I), in_cstride=x.cstride, Cout=O, R=R, S=S, stride=stride, pad=pad,
                      dil=dil, passes=passes, relu=int(relu), out_cstride=self.out.cstride if self.out is not None else 0,
                      out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0)
-        p = lambda t: t.data_ptr() if t is not None else None
         self.plan = lib().d2t_conv_plan_create(
-            C.byref(d), p(x.hi), p(x.lo), p(self.w_hi), p(self.w_lo), p(self.scale), p(self.shift),
-            p(residual.hi) if residual is not None else None, p(residual.lo) if residual is not None else None,
-            p(self.out.hi) if self.out is not None else None, p(self.out.lo) if self.out is not None else None,
-            p(self.out_nchw))
+            C.byref(d), _p(x.x), _p(self.w_hi), _p(self.w_lo), _p(self.scale), _p(self.shift),
+            _p(residual.x) if residual is not None else None, _p(self.out.x) if self.out is not None else None,
+            _p(self.out_nchw))
         if not self.plan:
             raise D2TError("d2t_conv_plan_create failed: %s" % lib().d2t_last_error().decode())
         info = (C.c_int * 8)()
@@ -113,30 +126,20 @@ class ConvLayer(object):
         self.flops = 2.0 * x.N * OH * OW * O * I * R * S
 
     def run(self):
-        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
-        ops._count(1)
+        _Planned.run(self)
         return self.out if self.out is not None else self.out_nchw
 
-    def __del__(self):
-        try:
-            if getattr(self, "plan", None):
-                lib().d2t_conv_plan_destroy(self.plan)
-                self.plan = None
-        except Exception:
-            pass
 
-
-class StemConv(object):
-    """conv1 7x7 / stride 2 / pad 3 (+ folded bn1 + ReLU) on the tcgen05 kernel via the row-window
-    TMA map (csrc/conv.cu: d2t_conv_stem_plan_create)."""
+class StemConv(_Planned):
+    """conv1 7x7 / stride 2 / pad 3 (+ folded bn1 + ReLU) on the tcgen05 kernel via the row-window TMA map
+    (csrc/conv.cu: d2t_conv_stem_plan_create)."""
 
     def __init__(self, N, H, W, weight, scale, shift, relu=True, passes=3, device="cuda"):
         O, I, R, S = weight.shape
         assert (R, S) == (7, 7) and I <= 4
         self.N, self.C, self.H, self.W = N, I, H, W
         Hp, Wp = (H + 7) & ~1, W + 8
-        self.in_hi = torch.empty(N, Hp, Wp, 4, device=device)
-        self.in_lo = torch.empty(N, Hp, Wp, 4, device=device)
+        self.packed = torch.empty(N, Hp, Wp, 4, device=device)
         self.w_hi = torch.empty(O, 7 * 32, device=device)
         self.w_lo = torch.empty(O, 7 * 32, device=device)
         w = weight.detach().float().contiguous()
@@ -146,35 +149,26 @@ class StemConv(object):
         self.scale = scale.detach().float().contiguous().to(device) if scale is not None else None
         self.shift = shift.detach().float().contiguous().to(device) if shift is not None else None
         OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        self.out = SplitTensor(N, OH, OW, O, device=device)
-        p = lambda t: t.data_ptr() if t is not None else None
-        self.plan = lib().d2t_conv_stem_plan_create(N, H, W, O, passes, p(self.in_hi), p(self.in_lo), p(self.w_hi),
-                                                    p(self.w_lo), p(self.scale), p(self.shift), int(relu),
-                                                    p(self.out.hi), p(self.out.lo), self.out.cstride)
+        self.out = ActTensor(N, OH, OW, O, device=device)
+        self.plan = lib().d2t_conv_stem_plan_create(N, H, W, O, passes, _p(self.packed), _p(self.w_hi), _p(self.w_lo),
+                                                    _p(self.scale), _p(self.shift), int(relu), _p(self.out.x),
+                                                    self.out.cstride)
         if not self.plan:
             raise D2TError("d2t_conv_stem_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * N * OH * OW * O * I * 49
 
     def run(self, x):
         """x: [N, C, H, W] fp32 image batch"""
-        check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.in_hi.data_ptr(),
-                                        self.in_lo.data_ptr(), _stream()), "d2t_stem_pack_input")
-        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
-        ops._count(2)
+        check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(), _stream()),
+              "d2t_stem_pack_input")
+        ops._count(1)
+        _Planned.run(self)
         return self.out
 
-    def __del__(self):
-        try:
-            if getattr(self, "plan", None):
-                lib().d2t_conv_plan_destroy(self.plan)
-                self.plan = None
-        except Exception:
-            pass
 
-
-class CorrLayer(object):
-    """Cross-frame correlation (kernel_size 1, stride1 == stride2) of two split NHWC tensors on the
-    tensor cores; writes a channel slice of `out` (split NHWC) and/or a plain NCHW tensor."""
+class CorrLayer(_Planned):
+    """Cross-frame correlation (kernel_size 1, stride1 == stride2) of two NHWC tensors on the tensor cores;
+    writes a channel slice of `out` (NHWC) and/or a plain NCHW tensor."""
 
     def __init__(self, x1, x2, pad, md, stride, passes=3, out=None, out_coffset=0, want_nchw=False):
         assert (x1.N, x1.H, x1.W, x1.cstride) == (x2.N, x2.H, x2.W, x2.cstride)
@@ -183,22 +177,17 @@ class CorrLayer(object):
         oh = -(-(x1.H + 2 * pad - 2 * md) // stride)
         ow = -(-(x1.W + 2 * pad - 2 * md) // stride)
         self.x1, self.x2, self.out = x1, x2, out
-        self.out_nchw = torch.empty(x1.N, self.D * self.D, oh, ow, device=x1.hi.device) if want_nchw else None
-        p = lambda t: t.data_ptr() if t is not None else None
+        self.out_nchw = torch.empty(x1.N, self.D * self.D, oh, ow, device=x1.x.device) if want_nchw else None
         self.plan = lib().d2t_corr_plan_create(x1.N, _pad32(x1.C), x1.C, x1.H, x1.W, x1.cstride, pad, md, stride, passes,
-                                               p(x1.hi), p(x1.lo), p(x2.hi), p(x2.lo),
-                                               p(out.hi) if out is not None else None, p(out.lo) if out is not None else None,
-                                               out.cstride if out is not None else 0, out_coffset, p(self.out_nchw))
+                                               _p(x1.x), _p(x2.x), _p(out.x) if out is not None else None,
+                                               out.cstride if out is not None else 0, out_coffset, _p(self.out_nchw))
         if not self.plan:
             raise D2TError("d2t_corr_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * x1.N * oh * ow * self.D * self.D * x1.C
 
     def run(self):
-        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
-        ops._count(1)
+        _Planned.run(self)
         return self.out_nchw if self.out_nchw is not None else self.out
-
-    __del__ = ConvLayer.__del__
 
 
 def maxpool3x3s2(x, out=None):
@@ -208,8 +197,8 @@ def maxpool3x3s2(x, out=None):
         OH -= 1
     if (OW - 1) * 2 >= x.W:
         OW -= 1
-    out = out if out is not None else SplitTensor(x.N, OH, OW, x.C, x.cstride, x.hi.device)
-    check(lib().d2t_maxpool3x3s2_nhwc(x.hi.data_ptr(), x.lo.data_ptr() if x.lo is not None else None, x.N, x.H, x.W,
-                                      x.cstride, out.hi.data_ptr(), out.lo.data_ptr(), _stream()), "d2t_maxpool3x3s2_nhwc")
+    out = out if out is not None else ActTensor(x.N, OH, OW, x.C, x.cstride, x.x.device)
+    check(lib().d2t_maxpool3x3s2_nhwc(x.x.data_ptr(), x.N, x.H, x.W, x.cstride, out.x.data_ptr(), _stream()),
+          "d2t_maxpool3x3s2_nhwc")
     ops._count(1)
     return out

@@ -56,7 +56,7 @@ class D2TEngine(object):
         pw = -(-(so.W - 3) // 2) + 1
         ph -= 1 if (ph - 1) * 2 >= so.H else 0
         pw -= 1 if (pw - 1) * 2 >= so.W else 0
-        self.pool_out = dc.SplitTensor(N, ph, pw, 64, device=dev)
+        self.pool_out = dc.ActTensor(N, ph, pw, 64, device=dev)
         x = self.pool_out
 
         # ---- residual stages
@@ -77,7 +77,7 @@ class D2TEngine(object):
         n_loc = 4 * self.n_reg * 49
         c3c, c45c = 81, 289
         self.trk_cin = 2 * n_loc + c3c + 2 * c45c
-        self.trk_in = dc.SplitTensor(pairs, bf.H, bf.W, self.trk_cin, cstride=(self.trk_cin + 31) // 32 * 32, device=dev)
+        self.trk_in = dc.ActTensor(pairs, bf.H, bf.W, self.trk_cin, cstride=(self.trk_cin + 31) // 32 * 32, device=dev)
         self.bbox_map = torch.empty(N, n_loc, bf.H, bf.W, device=dev)
         for leg in (0, 1):   # one plan per leg: NHWC into its channel slice of the concat buffer + NCHW for PSRoI
             layer = dc.ConvLayer(bf.batch_slice(leg * pairs, (leg + 1) * pairs), bn_.weight, None, bn_.bias, passes=passes,

@@ -49,7 +49,7 @@ rows, tot_mine, tot_cudnn, tot_tf32 = [], 0.0, 0.0, 0.0
 for name, N, Cin, H, W, Cout, k, stride, pad, dil, cnt in SHAPES:
     x = torch.randn(N, Cin, H, W, device="cuda")
     w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
-    xs = dc.SplitTensor.from_nchw(x)
+    xs = dc.ActTensor.from_nchw(x)
     layer = dc.ConvLayer(xs, w, None, None, stride, pad, dil, True, None, passes=passes, want_nhwc=(Cout % 4 == 0), want_nchw=(Cout % 4 != 0))
     ms = timeit(layer.run)
     xl = x.contiguous(memory_format=torch.channels_last)

@@ -14,8 +14,8 @@ N, Cin, H, W, Cout, k, stride, pad, dil, relu, use_res = CASES[idx]
 g = torch.Generator(device="cuda").manual_seed(7)
 x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
 w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
-xs = dc.SplitTensor.from_nchw(x)
-print("split exact:", torch.equal(xs.to_nchw(Cin), x), flush=True)
+xs = dc.ActTensor.from_nchw(x)
+print("layout round trip exact:", torch.equal(xs.to_nchw(Cin), x), flush=True)
 layer = dc.ConvLayer(xs, w, None, None, stride, pad, dil, False, None, passes=passes, want_nhwc=(Cout % 4 == 0), want_nchw=True)
 print("plan:", layer.info, flush=True)
 layer.run()

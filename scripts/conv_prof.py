@@ -10,7 +10,7 @@ for (N, Cin, H, W, Cout, k, stride, pad, dil) in [(4, 2048, 38, 63, 512, 3, 1, 6
                                                     (4, 256, 38, 63, 256, 3, 1, 1, 1), (4, 64, 150, 250, 256, 1, 1, 0, 1)]:
     x = torch.randn(N, Cin, H, W, device="cuda")
     w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
-    layer = dc.ConvLayer(dc.SplitTensor.from_nchw(x), w, None, None, stride, pad, dil, True, None, passes=passes)
+    layer = dc.ConvLayer(dc.ActTensor.from_nchw(x), w, None, None, stride, pad, dil, True, None, passes=passes)
     for _ in range(3):
         layer.run()
     torch.cuda.synchronize()

@@ -9,7 +9,7 @@ N, Cin, H, W, Cout, k, stride, pad, dil, passes = [int(a) for a in sys.argv[1:11
 x = torch.randn(N, Cin, H, W, device="cuda")
 w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
 sc, sh = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
-layer = dc.ConvLayer(dc.SplitTensor.from_nchw(x), w, sc, sh, stride, pad, dil, True, None, passes=passes)
+layer = dc.ConvLayer(dc.ActTensor.from_nchw(x), w, sc, sh, stride, pad, dil, True, None, passes=passes)
 for _ in range(4):
     layer.run()
 torch.cuda.synchronize()

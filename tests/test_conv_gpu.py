@@ -50,10 +50,9 @@ def test_conv_matches_torch(case, passes):
     OH = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     OW = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
     res = torch.randn(N, Cout, OH, OW, device="cuda", generator=g) if use_res else None
-    xs = dc.SplitTensor.from_nchw(x, lo=True)
-    # the split is exact
+    xs = dc.ActTensor.from_nchw(x)
     assert torch.equal(xs.to_nchw(Cin), x)
-    rs = dc.SplitTensor.from_nchw(res, cstride=Cout) if use_res else None
+    rs = dc.ActTensor.from_nchw(res, cstride=Cout) if use_res else None
     layer = dc.ConvLayer(xs, w, scale, shift, stride, pad, dil, relu, rs, passes=passes, want_nhwc=(Cout % 4 == 0),
                          want_nchw=True)
     out = layer.run()
@@ -66,19 +65,17 @@ def test_conv_matches_torch(case, passes):
     tol = 1e-5 if passes == 3 else 3e-3
     assert err < tol, (err, layer.info)
     if layer.out is not None:
-        assert torch.equal(layer.out.to_nchw(Cout), got)      # NHWC split output carries the same values
-        hi13 = (layer.out.hi.view(-1).view(torch.int32) & ~0x1fff).view(torch.float32)
-        assert torch.equal(layer.out.lo.view(-1), layer.out.hi.view(-1) - hi13)              # lo = x - trunc13(x)
+        assert torch.equal(layer.out.to_nchw(Cout), got)      # the NHWC output carries the same values
 
 
 def test_maxpool_ceil_mode():
     x = torch.randn(2, 64, 37, 50, device="cuda")
-    xs = dc.SplitTensor.from_nchw(x)
+    xs = dc.ActTensor.from_nchw(x)
     out = dc.maxpool3x3s2(xs).to_nchw()
     want = F.max_pool2d(x, 3, 2, 0, ceil_mode=True)
     assert out.shape == want.shape and torch.equal(out, want)
     x = torch.randn(1, 64, 300, 500, device="cuda")
-    out = dc.maxpool3x3s2(dc.SplitTensor.from_nchw(x)).to_nchw()
+    out = dc.maxpool3x3s2(dc.ActTensor.from_nchw(x)).to_nchw()
     want = F.max_pool2d(x, 3, 2, 0, ceil_mode=True)
     assert out.shape == want.shape == (1, 64, 150, 250) and torch.equal(out, want)
 
@@ -175,15 +172,15 @@ def test_cta_pair_mode_matches(monkeypatch):
     x = torch.randn(2, 256, 38, 63, device="cuda", generator=g)
     w = torch.randn(384, 256, 3, 3, device="cuda", generator=g) * 0.02
     sc, sh = torch.rand(384, device="cuda", generator=g) + 0.5, torch.randn(384, device="cuda", generator=g)
-    res = dc.SplitTensor.from_nchw(torch.randn(2, 384, 38, 63, device="cuda", generator=g), cstride=384)
+    res = dc.ActTensor.from_nchw(torch.randn(2, 384, 38, 63, device="cuda", generator=g), cstride=384)
     outs = []
     for pair in ("0", "1"):
         monkeypatch.setenv("D2T_CONV_PAIR", pair)
-        layer = dc.ConvLayer(dc.SplitTensor.from_nchw(x), w, sc, sh, 1, 1, 1, True, res, passes=3, want_nchw=True)
+        layer = dc.ConvLayer(dc.ActTensor.from_nchw(x), w, sc, sh, 1, 1, 1, True, res, passes=3, want_nchw=True)
         assert layer.info["grid"] % 10 == int(pair)
         layer.run()
         torch.cuda.synchronize()
-        outs.append((layer.out_nchw.clone(), layer.out.hi.clone(), layer.out.lo.clone()))
+        outs.append((layer.out_nchw.clone(), layer.out.x.clone()))
     want = _ref(x, w, sc, sh, 1, 1, 1, True, res.to_nchw())
     for o in outs:
         assert float((o[0] - want).abs().max() / want.abs().max()) < 1e-5
