@@ -352,15 +352,18 @@ def run_b200(args):
         conv_flops = sum(l.flops for l in engine.layers)
         n_conv = len(engine.layers)
         tf_useful = conv_flops / conv_ms / 1e9
-        mma_per_flop = 3 if args.passes == 3 else 1
-        roofline = {"kernel": "conv_igemm_tf32 (tcgen05 kind::tf32 implicit GEMM, %d launches/step)" % n_conv,
+        mma_per_flop = 1 if args.passes == 1 else 3
+        kind = "f16" if args.passes == 16 else "tf32"
+        kind_peak = _tf if args.passes == 16 else _tf / 2.0
+        roofline = {"kernel": "conv_igemm (tcgen05 kind::%s implicit GEMM, %d launches/step)" % (kind, n_conv),
                     "bound": "tensor", "achieved": tf_useful, "peak": _tf, "unit": "TFLOP/s", "frac": tf_useful / _tf,
-                    "traffic": None, "peak_source": peak_src + " (cuBLAS bf16 sustained; the TF32 kind peaks at half of it)",
+                    "traffic": None, "peak_source": peak_src + " (cuBLAS bf16 sustained = the kind::f16 peak; kind::tf32 peaks at half of it)",
                     "algorithmic_flops_per_launch": conv_flops / n_conv, "avg_launch_ms": conv_ms / n_conv,
                     "conv_ms_per_step": conv_ms,
                     "issued_tensor_tflops": tf_useful * mma_per_flop,
-                    "frac_of_tf32_peak_issued": tf_useful * mma_per_flop / (_tf / 2.0),
-                    "note": "achieved = useful fp32-equivalent conv FLOPs; 3xTF32 issues 3 tensor-core MMAs per useful FLOP"}
+                    "frac_of_kind_peak_issued": tf_useful * mma_per_flop / kind_peak,
+                    "note": "achieved = useful fp32-equivalent conv FLOPs; the fp32-accurate split modes (3xFP16 / 3xTF32) "
+                            "issue 3 tensor-core MMAs per useful FLOP"}
         ops_bench = op_microbench(flush, hbm_gbs)
         ps = ops_bench["psroi_fwd"]
         roofline_psroi = {"kernel": "psroi_fwd_sat<7> (+ psroi_prep) via d2t_psroi_forward", "bound": "hbm",
@@ -378,7 +381,8 @@ def run_b200(args):
         line = {"metric": METRIC, "value": parallel.throughput(pairs, ms_per_step, world), "unit": "frame-pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32 (3xTF32 tensor-core convs, fp32 accumulate)" if args.passes == 3 else "tf32", "data": "synthetic",
+                "dtype": {16: "fp32 (3xFP16 split tensor-core convs: hi/lo fp16 operand pairs, fp32 accumulate, <= 1e-5 of fp64)",
+                          3: "fp32 (3xTF32 tensor-core convs, fp32 accumulate)", 1: "tf32"}[args.passes], "data": "synthetic",
                 "config": {"workload": "Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation "
                                        "(BASELINE.json configs[1])",
                            "pairs_per_gpu": pairs, "global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
@@ -405,8 +409,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--passes", type=int, default=3, choices=[1, 3],
-                    help="3 = fp32-accurate 3xTF32 convolutions (the parity mode, default); 1 = single-pass TF32")
+    ap.add_argument("--passes", type=int, default=16, choices=[1, 3, 16],
+                    help="16 = fp32-accurate fp16-split convolutions (3xFP16, the parity mode, default); "
+                         "3 = fp32-accurate 3xTF32; 1 = single-pass TF32")
     ap.add_argument("--ops-only", action="store_true", help="only the per-op microbench (configs[3], [4]); for ncu")
     args = ap.parse_args()
     if args.ops_only:

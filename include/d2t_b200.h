@@ -191,18 +191,25 @@ int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
  * d2t_conv_pack_weights into the pair (w, w_lo), w_lo = w - trunc13(w) (trunc13 = low 13 mantissa
  * bits cleared).  kind::tf32 reads an fp32 operand as its truncation, so passes = 3 evaluates
  * hi*hi + hi*lo + lo*hi on the tensor cores (fp32-level accuracy; the activation lo tile is derived
- * in shared memory); passes = 1 is a plain single TF32 pass. */
+ * in shared memory); passes = 1 is a plain single TF32 pass.
+ * passes = 16 ("3xFP16") evaluates the same three products on kind::f16 -- twice the TF32 rate --
+ * with fp16 (hi, lo) operand pairs.  fp16 lacks fp32's range, so operands carry power-of-two scales:
+ * weights are packed by d2t_conv_pack_weights_f16 with 2^w_exp; every activation tensor owns one
+ * float in device memory holding a running max |x| ("amax": written by the producing plan's epilogue
+ * with atomicMax, zeroed by the caller before the producer runs), from which the consuming kernel
+ * derives its scale.  The fp32 activation tile is split in shared memory; HBM tensors stay fp32. */
 typedef struct d2t_conv_desc {
     int N, H, W;              /* input [N, H, W, in_cstride] */
     int Cin;                  /* input channels read, a multiple of 32 (zero padded) */
     int in_cstride;           /* channels per pixel of the input buffer, a multiple of 4 */
     int Cout, R, S;           /* filter [Cout, R, S, Cin] packed by d2t_conv_pack_weights */
     int stride, pad, dil;
-    int passes;               /* 3 or 1 */
+    int passes;               /* 3, 1 or 16 (see above) */
     int relu;
     int out_cstride;          /* channels per pixel of the NHWC output buffer */
     int out_coffset;          /* this conv writes channels [out_coffset, out_coffset + Cout) */
     int res_cstride;          /* channels per pixel of the residual buffer (0: = Cout) */
+    int w_exp;                /* passes = 16: the packed weights are w * 2^w_exp (d2t_conv_pack_weights_f16) */
 } d2t_conv_desc;
 typedef struct d2t_conv_plan d2t_conv_plan;
 
@@ -211,9 +218,13 @@ typedef struct d2t_conv_plan d2t_conv_plan;
  * consumers that keep the reference's layout.  The plan captures the pointers (TMA tensor maps);
  * buffers must outlive it.  Plans of one device share a small stream-K scratch, so they must not
  * run concurrently on different streams.  Returns NULL on error. */
-d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in, const float* w_hi,
-                                    const float* w_lo, const float* scale, const float* shift,
+d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in, const void* w_hi,
+                                    const void* w_lo, const float* scale, const float* shift,
                                     const float* res, float* out, float* out_nchw);
+/* Attach the per-tensor running max |x| scalars (device pointers, one float each): amax_in belongs to
+ * the plan's input tensor (required for passes = 16), amax_out to its NHWC output (optional: the
+ * epilogue folds max |out| into it).  Works for stem and correlation plans too (amax_out). */
+int d2t_conv_plan_set_amax(d2t_conv_plan* plan, const float* amax_in, float* amax_out);
 void d2t_conv_plan_destroy(d2t_conv_plan* plan);
 /* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid*10 + pair_mode} */
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);
@@ -242,6 +253,10 @@ d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int 
 /* OIHW fp32 -> [Cout][R*S][cin_pad] (w, w_lo); w_lo may be NULL */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
                           float* w_hi, float* w_lo, cudaStream_t stream);
+/* OIHW fp32 -> [Cout][R*S][cin_pad] fp16 pair (hi, lo) of w * 2^w_exp, cin_pad a multiple of 64:
+ * hi = fp16(w * 2^w_exp), lo = fp16(w * 2^w_exp - hi).  Choose w_exp so that max |w| * 2^w_exp < 2^15. */
+int d2t_conv_pack_weights_f16(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+                              int w_exp, void* w_hi, void* w_lo, cudaStream_t stream);
 /* plain fp32 NCHW -> channels [c_offset, c_offset + c_width) of an NHWC tensor with c_stride channels
  * per pixel (the C source channels, then zeros); and back */
 int d2t_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,

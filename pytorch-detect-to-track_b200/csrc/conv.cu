@@ -31,6 +31,17 @@
 // PASSES = 1 runs the plain single-pass TF32 conv (~1e-3 relative) and is reported separately,
 // never as the parity number.
 //
+// PASSES = 16 ("3xFP16") is the same three-product scheme on kind::f16, which runs at TWICE the TF32 rate:
+// x*sa = hi + lo with hi = the top 11 significant bits and lo the rounded remainder, both fp16.  fp16 has
+// fp32's precision budget for such a pair (11 + 11 bits) but not its range, so every operand tensor carries a
+// power-of-two scale: weights are packed once with sw = 2^w_exp (max |w| * sw in [2^14, 2^15)); activations
+// keep a per-tensor running max |x| (one float in HBM, written by the producing kernel's epilogue with one
+// atomicMax per warp and tile) from which the consumer derives sa = 2^ea the same way.  Scaling by a power of
+// two is exact, the epilogue multiplies the fp32 accumulator by 2^-(ea + w_exp) before the folded BatchNorm.
+// The fp32 activation tile travels through the TMA unchanged (two 32-channel sub-tiles per 64-channel K block);
+// four converter warps rewrite it IN PLACE as the (hi | lo) fp16 operand tiles -- 4 bytes per element either
+// way, and a thread pair owns one pixel row, so no second buffer is needed.
+//
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
 //   warp 0   : TMA producer (one lane per operand copy), NS-stage ring of {A x, A lo, B x, B lo}
 //   warp 1   : MMA issuer  (one elected lane), tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8
@@ -42,6 +53,7 @@
 //              plain fp32 NCHW copy for the consumers that keep the reference's layout: correlation,
 //              PSRoI, the proposal step) -- all while the tensor core is already on the next tile.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <atomic>
 #include <new>
@@ -52,13 +64,14 @@ namespace d2t {
 namespace {
 
 constexpr int kBlockM = 128;       // output pixels per tile (TMEM lanes)
-constexpr int kBlockK = 32;        // fp32 elements per K block = one 128-byte swizzle row
-constexpr int kUmmaK = 8;          // tf32: 32 bytes per MMA K step
-constexpr int kThreads = 384;
+constexpr int kBoxC = 32;          // fp32 channels per activation TMA box = one 128-byte swizzle row
 constexpr int kEpiWarp0 = 4;       // warps 4..11 are the epilogue: two groups of 4 (warp % 4 = TMEM lane quarter),
 constexpr int kEpiThreads = 256;   // group g owns columns [g*BN/2, (g+1)*BN/2) of the tile
-constexpr int kChunkK = 8;         // k-blocks accumulated in TMEM before the partial sum moves to registers
-constexpr int kCvtThreads = 64;    // warps 2-3 derive the lo tiles
+constexpr int kChunkC = 256;       // channels (x taps) accumulated in TMEM before the partial sum moves to registers
+
+// channels per K block / K blocks per TMEM chunk for a given operand mode (PASSES: 1 = TF32, 3 = 3xTF32, 16 = 3xFP16)
+__host__ __device__ constexpr int kblk_of(int passes) { return passes == 16 ? 64 : 32; }
+__host__ __device__ constexpr int chunk_of(int passes) { return kChunkC / kblk_of(passes); }
 
 struct ConvArgs {
     int N, OH, OW, Cout;
@@ -82,9 +95,25 @@ struct ConvArgs {
     float* sk_scratch;
     int* sk_flags;
     int sk_epoch;
+    // per-tensor running max |x| (one float each): amax_in scales the fp16-split activation operand, amax_out
+    // collects this layer's output for its consumers; w_exp = log2 of the packed weights' scale (3xFP16 only)
+    const float* amax_in;
+    float* amax_out;
+    int w_exp;
 };
 
-// Work distribution ("stream-K").  A layer is tiles x cpt units, a unit = one K chunk (kChunkK k-blocks) of
+// activation scale exponent: sa = 2^ea puts the tensor's max |x| into [2^14, 2^15)
+__device__ __forceinline__ int act_exp(const float* amax) {
+    int eb = (int)((__float_as_uint(__ldcg(amax)) >> 23) & 0xffu);
+    eb = eb < 15 ? 15 : (eb > 254 ? 254 : eb);
+    return 141 - eb;
+}
+__device__ __forceinline__ float pow2f(int e) {
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
+// Work distribution ("stream-K").  A layer is tiles x cpt units, a unit = one K chunk (256 channels x taps) of
 // one output tile.  CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G): every CTA gets the same amount of
 // tensor-core work (+-1 chunk) whatever the tile count -- with whole tiles, 152 or 304 tiles on 148 SMs cost
 // 2 or 3 rounds for 1.03 or 2.05 rounds of work.  A tile split across CTAs is finished by the CTA holding its
@@ -98,8 +127,8 @@ struct Seg {
 struct Sched {
     int cpt, nseg, first_tile, tail_pub, head_fin;
     long long u0, u1;
-    __device__ Sched(int tiles, int k_iters, int cta, int G) {
-        cpt = (k_iters + kChunkK - 1) / kChunkK;
+    __device__ Sched(int tiles, int k_iters, int chunk, int cta, int G) {
+        cpt = (k_iters + chunk - 1) / chunk;
         const long long U = (long long)tiles * cpt;
         u0 = U * cta / G;
         u1 = U * (cta + 1) / G;
@@ -134,16 +163,27 @@ struct Sched {
 
 template <int BN, int PASSES, bool PAIR = false>
 struct Cfg {
-    static constexpr int A_BYTES = kBlockM * kBlockK * 4;             // 16 KB
-    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * kBlockK * 4;   // per CTA: a CTA pair holds half of B each
-    static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // hi (+ lo)
-    static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);   // smem per stage: A x | A lo | B x | B lo
+    static constexpr bool F16 = PASSES == 16;
+    static constexpr bool SPLIT = PASSES != 1;                        // three products per K step
+    static constexpr int KBLK = kblk_of(PASSES);                      // channels per K block
+    static constexpr int CHUNK = chunk_of(PASSES);                    // K blocks per TMEM chunk
+    static constexpr int THREADS = F16 ? 448 : 384;                   // 3xFP16: warps 12-13 are two more converters
+    static constexpr int CVT_THREADS = F16 ? 128 : 64;
+    // 3xFP16: A = two fp32 [128 x 32] sub-tiles as loaded, rewritten in place as fp16 [128 x 64] hi | lo
+    static constexpr int A_BYTES = kBlockM * KBLK * 4;                // 16 KB (32 KB)
+    static constexpr int B_BYTES = F16 ? BN * KBLK * 2 : (PAIR ? BN / 2 : BN) * KBLK * 4;   // (a CTA pair holds half of B each)
+    static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // TF32: hi (+ lo) copies of each operand
+    // smem per stage -- TF32: A x | A lo | B x | B lo;  FP16: A (hi | lo) | B hi | B lo
+    static constexpr int STAGE_BYTES = F16 ? A_BYTES + 2 * B_BYTES : NOPER * (A_BYTES + B_BYTES);
+    static constexpr int OFF_ALO = F16 ? A_BYTES / 2 : A_BYTES;
+    static constexpr int OFF_BHI = F16 ? A_BYTES : NOPER * A_BYTES;
+    static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int OUT_STAGE_BYTES = 2 * kBlockM * 128;        // one [128 x 32] fp32 slab per epilogue group (TMA store)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/;
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
-    static constexpr int TMEM_COLS = (PASSES == 3 ? 4 : 2) * BN;      // power of two >= 32 for BN in {64,128}
+    static constexpr int TMEM_COLS = (SPLIT ? 4 : 2) * BN;            // power of two >= 32 for BN in {64,128}
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -218,6 +258,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D = fp32, A = B = fp16, both K-major
+template <int BN, int M = kBlockM>
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
+    return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -273,13 +326,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // `full` / `tempty` / `xempty` barriers (both CTAs' TMA and epilogue warps signal them remotely); its commits
 // are multicast to both CTAs' `empty` / `tfull` barriers.
 template <int BN, int PASSES, bool CORR, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
+__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR>::THREADS), 1)
+conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
                 const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
                 const __grid_constant__ CUtensorMap tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
                 const __grid_constant__ CUtensorMap tmO,      // NHWC output (TMA store)
                 const ConvArgs p) {
     using C = Cfg<BN, PASSES, PAIR>;
+    constexpr bool F16 = C::F16, SPLIT = C::SPLIT;
+    constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
+    static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
@@ -304,7 +360,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB_hi);
-        if (PASSES == 3 && !CORR) prefetch_tmap(&tmB_lo);
+        if (SPLIT && !CORR) prefetch_tmap(&tmB_lo);
         if (!CORR && p.out) prefetch_tmap(&tmO);
     }
     if (warp == 1 && lane == 0) {
@@ -336,7 +392,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
     if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const Sched sched(tiles, k_iters, unit_id, n_units);
+    const Sched sched(tiles, k_iters, kChunkK, unit_id, n_units);
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
     // overlapped the tail of the previous layer; from here on we touch its output.
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -348,12 +404,15 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
         // incrementally -- no divisions in the loop.  Measured (round 1): the feed alone (no MMAs issued) runs at
         // ~950 cycles per 64 KB K block with the 3-stage ring = TMA latency x bytes in flight, against ~870 cycles
         // of 3xTF32 MMA work per K block; the two overlap only partly (1450 cycles per K block end to end).
-        constexpr int NL = (PASSES == 3 && !CORR) ? 3 : 2;   // TMA copies per stage: A x, B x (, B lo: weights only)
-        constexpr int TMA_BYTES = C::A_BYTES + (NL - 1) * C::B_BYTES;
+        // TMA copies per stage: A x (3xFP16: its two 32-channel sub-tiles), B x (, B lo: weights only)
+        constexpr int NA = F16 ? 2 : 1;
+        constexpr int NL = NA + ((SPLIT && !CORR) ? 2 : 1);
+        constexpr int TMA_BYTES = C::A_BYTES + (NL - NA) * C::B_BYTES;
         if (lane < NL) {
-            const bool is_a = lane == 0;
-            const CUtensorMap* map = is_a ? &tmA : (lane == 1 ? &tmB_hi : &tmB_lo);
-            const int dst_off = PASSES == 3 ? (is_a ? 0 : 2 * C::A_BYTES + (lane == 2 ? C::B_BYTES : 0)) : (is_a ? 0 : C::A_BYTES);
+            const bool is_a = lane < NA;
+            const CUtensorMap* map = is_a ? &tmA : (lane == NA ? &tmB_hi : &tmB_lo);
+            const int dst_off = is_a ? lane * (kBlockM * kBoxC * 4) : (lane == NA ? C::OFF_BHI : C::OFF_BLO);
+            const int a_c0 = is_a ? lane * kBoxC : 0;            // first channel of this lane's sub-tile in the K block
             int stage = 0;
             uint32_t phase = 0;
             for (int e = 0; e < sched.nseg; ++e) {
@@ -384,7 +443,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                             // stem: filter row r = 32 consecutive floats (8 pixels x 4 channels) of padded input row
                             // 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
                             if (p.stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
-                            else tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                            else tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * p.dil, ih0 + r * p.dil, img);
                         } else if (CORR) {
                             tma_load_4d(dst, map, fbar, kc * kBlockK, bw0, bh0, img);
                         } else {
@@ -415,7 +474,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
         // cross terms (2^-11 of the result, so their truncation is negligible) accumulate over the
         // whole tile in their own TMEM buffer.  TMEM: main[2] | cross[2], BN columns each.
         if (lane == 0 && crank == 0) {
-            constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : make_idesc<BN>();
+            constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : (F16 ? make_idesc_f16<BN>() : make_idesc<BN>());
             const uint64_t desc0 = make_smem_desc(smem_u32(smem));     // stage s / operand o: + (byte offset >> 4)
             int stage = 0, cbuf = 0, local = 0;
             uint32_t phase = 0, cphase = 0;
@@ -423,7 +482,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                 const Seg sg = sched.get(local);
                 const int xacc = local & 1;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
-                if (PASSES == 3) {
+                if (SPLIT) {
                     mbar_wait_sleep(&xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
                     tc_fence_after();
                 }
@@ -436,17 +495,21 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                     }
                     const uint32_t d_main = tmem_base + cbuf * BN;
                     mbar_wait_sleep(&full[stage], phase);
-                    if (PASSES == 3 || PAIR) mbar_wait_sleep(&cvt[stage], phase);   // lo tiles written (pair: peer landed too)
+                    if (SPLIT || PAIR) mbar_wait_sleep(&cvt[stage], phase);   // lo tiles written (pair: peer landed too)
                     tc_fence_after();
                     const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
-                    if (PASSES == 3) {
-                        const uint64_t a_lo = a_hi + (C::A_BYTES >> 4);
-                        const uint64_t b_hi = a_hi + (2 * C::A_BYTES >> 4);
-                        const uint64_t b_lo = a_hi + ((2 * C::A_BYTES + C::B_BYTES) >> 4);
+                    if (SPLIT) {
+                        const uint64_t a_lo = a_hi + (C::OFF_ALO >> 4);
+                        const uint64_t b_hi = a_hi + (C::OFF_BHI >> 4);
+                        const uint64_t b_lo = a_hi + (C::OFF_BLO >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
-                            const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
-                            if (PAIR) {
+                        for (int kk = 0; kk < 4; ++kk) {                  // 4 K steps of 32 bytes per 128-byte row
+                            const uint64_t o = (uint64_t)(kk * 32 >> 4);
+                            if (F16) {
+                                umma_f16(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
+                                umma_f16(d_cross, a_hi + o, b_lo + o, idesc, 1);
+                                umma_f16(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            } else if (PAIR) {
                                 umma_tf32_pair(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                                 umma_tf32_pair(d_cross, a_hi + o, b_lo + o, idesc, 1);
                                 umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
@@ -457,10 +520,10 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                             }
                         }
                     } else {
-                        const uint64_t b_hi = a_hi + (C::A_BYTES >> 4);
+                        const uint64_t b_hi = a_hi + (C::OFF_BHI >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
-                            const uint64_t o = (uint64_t)(kk * kUmmaK * 4 >> 4);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t o = (uint64_t)(kk * 32 >> 4);
                             if (PAIR) umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                             else umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
                         }
@@ -481,13 +544,69 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                 }
             }
         }
-    } else if (warp < kEpiWarp0) {
-        // ===================== converters (warps 2-3) =====================
+    } else if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
+        // ===================== converters (warps 2-3; 3xFP16: + warps 12-13) =====================
         // lo = x - trunc13(x) for the activation tile of every landed stage (and for the second frame's tile in
         // correlation mode): same swizzled address in the stage's "lo" slot, so the layout needs no thought.
         // In a CTA pair the converters also carry the "my copies have landed" signal to the leader: each CTA's TMA
         // completes on its OWN `full` barrier, and the leader's MMA thread waits for both CTAs' cvt arrivals.
-        if (PASSES == 3 || PAIR) {
+        if constexpr (F16) {
+            // 3xFP16: the landed activation tile is two fp32 [128 rows x 32 channels] sub-tiles (128-byte rows,
+            // SWIZZLE_128B).  Row m of the fp16 operand tiles is again 128 bytes: 64 channels of hi (same place as
+            // sub-tile 0) and of lo (sub-tile 1), same swizzle.  Lanes l and l + 16 of a warp own one row: each reads
+            // its sub-tile's 32 floats, scales by sa (exact), splits x*sa = hi + lo (hi = top 11 significant bits,
+            // lo = the remainder rounded to fp16), and after a __syncwarp writes its 32 channels of both rows.  A
+            // quarter warp touches 8 consecutive rows of one sub-tile, so every 16-byte access is conflict-free.
+            const int cw = warp < kEpiWarp0 ? warp - 2 : warp - (kEpiWarp0 + 8) + 2;      // converter warp 0..3
+            const int sub = lane >> 4;
+            const float sa = pow2f(act_exp(p.amax_in));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int e = 0; e < sched.nseg; ++e) {
+                const Seg sg = sched.get(e);
+                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                for (int k = k_beg; k < k_end; ++k) {
+                    mbar_wait_sleep(&full[stage], phase);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int m = pass * 64 + cw * 16 + (lane & 15);
+                        const uint32_t sw = (uint32_t)m & 7u;
+                        const uint8_t* src = st + sub * (kBlockM * kBoxC * 4) + m * 128;
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
+                            const float a0 = v.x * sa, a1 = v.y * sa, a2 = v.z * sa, a3 = v.w * sa;
+                            const float h0 = __uint_as_float(__float_as_uint(a0) & 0xffffe000u);
+                            const float h1 = __uint_as_float(__float_as_uint(a1) & 0xffffe000u);
+                            const float h2 = __uint_as_float(__float_as_uint(a2) & 0xffffe000u);
+                            const float h3 = __uint_as_float(__float_as_uint(a3) & 0xffffe000u);
+                            __half2 t;
+                            t = __floats2half2_rn(h0, h1); hi[2 * c] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(h2, h3); hi[2 * c + 1] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(a0 - h0, a1 - h1); lo[2 * c] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(a2 - h2, a3 - h3); lo[2 * c + 1] = *reinterpret_cast<uint32_t*>(&t);
+                        }
+                        __syncwarp();                                  // both lanes of every row have read it
+                        uint8_t* dh = st + m * 128;
+                        uint8_t* dl = st + C::OFF_ALO + m * 128;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8) of the K block
+                            const uint32_t off = (((uint32_t)(4 * sub + jj)) ^ sw) << 4;
+                            *reinterpret_cast<uint4*>(dh + off) = make_uint4(hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3]);
+                            *reinterpret_cast<uint4*>(dl + off) = make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
+                        }
+                    }
+                    fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                    mbar_arrive(&cvt[stage]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (PASSES == 3 || PAIR) {
             const int ct = threadIdx.x - 64;                       // 0..63
             int stage = 0;
             uint32_t phase = 0;
@@ -508,8 +627,8 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                                             v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
                     }
                     if (CORR && PASSES == 3) {
-                        const float4* bx = reinterpret_cast<const float4*>(st + 2 * C::A_BYTES);
-                        float4* bl = reinterpret_cast<float4*>(st + 2 * C::A_BYTES + C::B_BYTES);
+                        const float4* bx = reinterpret_cast<const float4*>(st + C::OFF_BHI);
+                        float4* bl = reinterpret_cast<float4*>(st + C::OFF_BLO);
 #pragma unroll 4
                         for (int i = ct; i < C::B_BYTES / 16; i += kCvtThreads) {
                             const float4 v = bx[i];
@@ -539,9 +658,12 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
         const int TW = 1 << p.TW_log2;
         const int hl = m >> p.TW_log2, wl = m & (TW - 1);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        // 3xFP16: the accumulator holds (x * 2^ea) . (w * 2^w_exp); undo both (exact) ahead of the affine
+        const float descale = F16 ? pow2f(-(act_exp(p.amax_in) + p.w_exp)) : 1.f;
         int local = 0, cbuf = 0;
         uint32_t cphase = 0;
         for (; local < sched.nseg; ++local) {
+            float tmax = 0.f;                               // max |value| this thread wrote for this tile
             const Seg sg = sched.get(local);
             const int t = sg.tile, nchunks = sg.c1 - sg.c0;
             const int xacc = local & 1;
@@ -570,7 +692,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                 cbuf ^= 1;
                 if (cbuf == 0) cphase ^= 1;
             }
-            if (PASSES == 3) {                               // + the cross terms of the whole tile
+            if (SPLIT) {                                     // + the cross terms of the whole tile
 #pragma unroll
                 for (int c = 0; c < HN / 16; ++c) {
                     float v[16];
@@ -630,6 +752,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                         const int tir = cl - wl;                     // ti + r
                         if (tir < 0 || tir >= D) continue;
                         const float val = __fdiv_rn(acc[rh * 32 + cl], p.corr_nelems);   // kernel.cu:100
+                        tmax = fmaxf(tmax, fabsf(val));
                         if (p.out_nchw)
                             p.out_nchw[(((size_t)img * D * D + tc0 + cl) * p.OH + oh) * p.OW + ow] = val;
                         if (p.out) p.out[pix * p.out_cstride + p.out_coffset + tc0 + cl] = val;
@@ -648,8 +771,15 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
-                            v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
+                            if (F16) {
+                                v[j] *= sc.x * descale; v[j + 1] *= sc.y * descale; v[j + 2] *= sc.z * descale; v[j + 3] *= sc.w * descale;
+                            } else {
+                                v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
+                            }
                         }
+                    } else if (F16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] *= descale;
                     }
                     if (p.shift) {
 #pragma unroll
@@ -662,7 +792,7 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int chn = min(ch0 + j, p.Cout - 1);
-                        const float sc = p.scale ? __ldg(p.scale + chn) : 1.f;
+                        const float sc = (p.scale ? __ldg(p.scale + chn) : 1.f) * descale;
                         const float sh = p.shift ? __ldg(p.shift + chn) : 0.f;
                         v[j] = v[j] * sc + sh;
                     }
@@ -684,6 +814,11 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.amax_out && pix_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full16 || ch0 + j < p.Cout) tmax = fmaxf(tmax, fabsf(v[j]));
                 }
                 if (p.out_nchw && pix_ok) {
                     float* o = p.out_nchw + (((size_t)img * p.Cout + ch0) * p.OH + oh) * p.OW + ow;
@@ -716,6 +851,10 @@ conv_igemm_tf32(const __grid_constant__ CUtensorMap tmA,      // activation (A o
                 }
             }
             }   // !CORR
+            if (p.amax_out) {                               // running max |x| of the output tensor (values are >= 0: integer order)
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));
+                if (lane == 0 && wmax != 0u) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
+            }
         }
     }
     if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
@@ -748,13 +887,13 @@ EncodeTiledFn encode_fn() {
 }
 
 bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+            const cuuint32_t* box, const cuuint32_t* estr, const char* what, bool f16 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
         return false;
     }
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -805,8 +944,9 @@ bool sk_scratch(SkScratch* out) {
 }
 
 // grid = one CTA per SM, fewer only when the layer has fewer K chunks than SMs
-int sk_grid(int tiles, int k_iters) {
-    const long long units = (long long)tiles * ((k_iters + kChunkK - 1) / kChunkK);
+int sk_grid(int tiles, int k_iters, int passes) {
+    const int chunk = chunk_of(passes);
+    const long long units = (long long)tiles * ((k_iters + chunk - 1) / chunk);
     return (int)(units < sm_count() ? units : sm_count());
 }
 }  // namespace
@@ -840,12 +980,12 @@ template <int BN, int PASSES, bool CORR, bool PAIR>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     using C = Cfg<BN, PASSES, PAIR>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm_tf32<BN, PASSES, CORR, PAIR>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl->grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -857,9 +997,10 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = PAIR ? 2 : 1;
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_tf32<BN, PASSES, CORR, PAIR>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
+    D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
                                    args),
-                "conv_igemm_tf32 launch");
+                "conv_igemm launch");
     return 1;
 }
 
@@ -871,12 +1012,12 @@ static int max_pairs() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
     if (cached[dev]) return cached[dev];
-    auto kern = conv_igemm_tf32<BN, PASSES, false, true>;
+    auto kern = conv_igemm<BN, PASSES, false, true>;
     int n = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * 64);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(C::THREADS);
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -895,22 +1036,24 @@ static int max_pairs() {
 }
 
 extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const float* in,
-                                               const float* w_hi, const float* w_lo, const float* scale,
+                                               const void* w_hi, const void* w_lo, const float* scale,
                                                const float* shift, const float* res, float* out, float* out_nchw) {
     if (!d || !in || !w_hi || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->R <= 0 ||
         d->S <= 0 || d->stride <= 0 || d->dil <= 0 || d->pad < 0) {
         set_error("d2t_conv_plan_create: bad descriptor");
         return nullptr;
     }
-    if (d->Cin % kBlockK != 0 || d->in_cstride % 4 != 0 || d->in_cstride < d->Cin) {
+    if (d->Cin % kBoxC != 0 || d->in_cstride % 4 != 0 || d->in_cstride < d->Cin) {
         set_error("d2t_conv_plan_create: Cin must be a multiple of 32 (zero-pad) and in_cstride a multiple of 4");
         return nullptr;
     }
-    if (d->passes != 1 && d->passes != 3) {
-        set_error("d2t_conv_plan_create: passes must be 1 (TF32) or 3 (3xTF32, fp32-accurate)");
+    if (d->passes != 1 && d->passes != 3 && d->passes != 16) {
+        set_error("d2t_conv_plan_create: passes must be 1 (TF32), 3 (3xTF32, fp32-accurate) or 16 (3xFP16, fp32-accurate)");
         return nullptr;
     }
-    if (d->passes == 3 && !w_lo) {
+    const bool f16 = d->passes == 16;
+    const int kblk = kblk_of(d->passes);
+    if (d->passes != 1 && !w_lo) {
         set_error("d2t_conv_plan_create: 3-pass mode needs the lo half of the packed weights");
         return nullptr;
     }
@@ -940,7 +1083,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     ConvArgs& a = pl->args;
     a.N = d->N; a.OH = OH; a.OW = OW; a.Cout = d->Cout;
     a.R = d->R; a.S = d->S; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
-    a.kc_blocks = d->Cin / kBlockK;
+    a.kc_blocks = (d->Cin + kblk - 1) / kblk;         // (3xFP16: a trailing half block reads zeros past Cin)
     a.TW_log2 = twl; a.TH = TH; a.stem = 0;
     a.tiles_w = (OW + TW - 1) / TW; a.tiles_h = (OH + TH - 1) / TH;
     a.m_tiles = d->N * a.tiles_h * a.tiles_w;
@@ -952,17 +1095,18 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.relu = d->relu;
     a.out = out; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp;
     pl->passes = d->passes; pl->corr = 0;
     // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
-    pl->pair = (a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
+    pl->pair = (!f16 && a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
     if (pl->pair) {
         const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
-        const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + kChunkK - 1) / kChunkK);
+        const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + chunk_of(3) - 1) / chunk_of(3));
         const int maxp = d->passes == 3 ? (pl->BN == 64 ? max_pairs<64, 3>() : max_pairs<128, 3>())
                                         : (pl->BN == 64 ? max_pairs<64, 1>() : max_pairs<128, 1>());
         pl->grid = 2 * (int)(units < maxp ? units : maxp);
     } else {
-        pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks);
+        pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks, d->passes);
     }
     SkScratch sk;
     if (!sk_scratch(&sk)) {
@@ -975,18 +1119,18 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     const cuuint64_t adims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     const cuuint64_t astr[3] = {(cuuint64_t)d->in_cstride * 4, (cuuint64_t)d->W * d->in_cstride * 4,
                                 (cuuint64_t)d->H * d->W * d->in_cstride * 4};
-    const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)((TW - 1) * d->stride + 1),
+    const cuuint32_t abox[4] = {(cuuint32_t)kBoxC, (cuuint32_t)((TW - 1) * d->stride + 1),
                                 (cuuint32_t)((TH - 1) * d->stride + 1), 1u};
     const cuuint32_t aestr[4] = {1u, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1u};
-    // B: packed weights [Cout, R*S*Cin]
-    const cuuint64_t ktot = (cuuint64_t)d->R * d->S * d->Cin;
+    // B: packed weights [Cout, R*S*cin_pad], cin_pad = kc_blocks * (channels per K block); fp32 or fp16 elements
+    const cuuint64_t ktot = (cuuint64_t)d->R * d->S * a.kc_blocks * kblk;
     const cuuint64_t bdims[2] = {ktot, (cuuint64_t)d->Cout};
-    const cuuint64_t bstr[1] = {ktot * 4};
-    const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pl->pair ? pl->BN / 2 : pl->BN)};
+    const cuuint64_t bstr[1] = {ktot * (f16 ? 2 : 4)};
+    const cuuint32_t bbox[2] = {(cuuint32_t)kblk, (cuuint32_t)(pl->pair ? pl->BN / 2 : pl->BN)};
     const cuuint32_t bestr[2] = {1u, 1u};
     bool ok = encode(&pl->tmA, in, 4, adims, astr, abox, aestr, "A") &&
-              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi");
-    if (ok && d->passes == 3) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo");
+              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi", f16);
+    if (ok && d->passes != 1) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo", f16);
     if (ok && d->passes == 1) pl->tmB_lo = pl->tmB_hi;
     if (ok && out) ok = encode_out_map(&pl->tmO, out, d->N, OH, OW, d->Cout, d->out_cstride, d->out_coffset, TH, TW);
     else if (ok) pl->tmO = pl->tmA;
@@ -1034,7 +1178,8 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.scale = scale; a.shift = shift; a.res = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0; pl->pair = 0;
-    pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7);
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0;
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7, passes);
     {
         SkScratch sk;
         if (!sk_scratch(&sk)) {
@@ -1073,7 +1218,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
         return nullptr;
     }
     const int r = md / stride;
-    if (C % kBlockK != 0 || in_cstride % 4 != 0 || in_cstride < C || r > 8 || r < 1) {
+    if (C % kBoxC != 0 || in_cstride % 4 != 0 || in_cstride < C || r > 8 || r < 1) {
         set_error("d2t_corr_plan_create: needs C %% 32 == 0, 16-byte pixel stride and 1 <= max_displacement/stride2 <= 8");
         return nullptr;
     }
@@ -1092,7 +1237,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     ConvArgs& a = pl->args;
     a.N = N; a.OH = OH; a.OW = OW; a.Cout = (2 * r + 1) * (2 * r + 1);
     a.R = 1; a.S = 1; a.stride = stride; a.pad = pad - md; a.dil = 1;       // element = lattice*stride + (md - pad)
-    a.kc_blocks = C / kBlockK;
+    a.kc_blocks = C / kBoxC;
     a.TW_log2 = 4; a.TH = 8; a.stem = 0;
     a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 7) / 8;
     a.m_tiles = N * a.tiles_h * a.tiles_w;
@@ -1101,7 +1246,8 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
     pl->BN = 128; pl->passes = passes; pl->corr = 1; pl->pair = 0;
-    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks);
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0;
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks, passes);
     {
         SkScratch sk;
         if (!sk_scratch(&sk)) {
@@ -1112,8 +1258,8 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     }
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t str[3] = {(cuuint64_t)in_cstride * 4, (cuuint64_t)W * in_cstride * 4, (cuuint64_t)H * W * in_cstride * 4};
-    const cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(15 * stride + 1), (cuuint32_t)(7 * stride + 1), 1u};
-    const cuuint32_t bbox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(31 * stride + 1), (cuuint32_t)(3 * stride + 1), 1u};
+    const cuuint32_t abox[4] = {(cuuint32_t)kBoxC, (cuuint32_t)(15 * stride + 1), (cuuint32_t)(7 * stride + 1), 1u};
+    const cuuint32_t bbox[4] = {(cuuint32_t)kBoxC, (cuuint32_t)(31 * stride + 1), (cuuint32_t)(3 * stride + 1), 1u};
     const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
     bool ok = encode(&pl->tmA, in1, 4, dims, str, abox, estr, "corr A") &&
               encode(&pl->tmB_hi, in2, 4, dims, str, bbox, estr, "corr B");
@@ -1124,6 +1270,13 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
         return nullptr;
     }
     return pl;
+}
+
+extern "C" int d2t_conv_plan_set_amax(d2t_conv_plan* pl, const float* amax_in, float* amax_out) {
+    D2T_REQUIRE(pl, "d2t_conv_plan_set_amax: null plan");
+    pl->args.amax_in = amax_in;
+    pl->args.amax_out = amax_out;
+    return 1;
 }
 
 extern "C" void d2t_conv_plan_destroy(d2t_conv_plan* pl) {
@@ -1142,6 +1295,8 @@ extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->corr)
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))
+    if (pl->passes == 16)
+        return pl->BN == 64 ? launch_conv<64, 16, false, false>(pl, stream) : launch_conv<128, 16, false, false>(pl, stream);
     if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);
     return pl->BN == 64 ? D2T_RUN(64, 1) : D2T_RUN(128, 1);
 #undef D2T_RUN

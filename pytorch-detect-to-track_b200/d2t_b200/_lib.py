@@ -59,6 +59,8 @@ _SIGS = {
     # ---- convolution engine
     "d2t_conv_plan_create": (_p, [_p] * 9),
     "d2t_conv_plan_destroy": (None, [_p]),
+    "d2t_conv_plan_set_amax": (_i, [_p, _p, _p]),
+    "d2t_conv_pack_weights_f16": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 3 + [_i, _i, _p]),
     "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),
     "d2t_conv_plan_run": (_i, [_p, _p]),
@@ -77,7 +79,7 @@ _OPTIONAL = set()
 class ConvDesc(C.Structure):
     """struct d2t_conv_desc (include/d2t_b200.h)"""
     _fields_ = [(n, C.c_int) for n in ("N", "H", "W", "Cin", "in_cstride", "Cout", "R", "S", "stride", "pad", "dil",
-                                       "passes", "relu", "out_cstride", "out_coffset", "res_cstride")]
+                                       "passes", "relu", "out_cstride", "out_coffset", "res_cstride", "w_exp")]
 
 _lib = None
 

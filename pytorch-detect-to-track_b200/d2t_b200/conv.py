@@ -1,10 +1,15 @@
 """Tensor-level front end of the tcgen05 convolution engine (csrc/conv.cu, csrc/conv_util.cu).
 
-``ActTensor`` is a plain fp32 NHWC activation buffer; ``ConvLayer`` / ``StemConv`` / ``CorrLayer`` own packed
-weights (w, w_lo), the folded BatchNorm / bias vectors, their output buffers and the C-ABI plan (TMA tensor maps)
-that runs them.  Nothing here computes on the CPU; everything is enqueued on torch's current stream.
+``ActTensor`` is a plain fp32 NHWC activation buffer plus one device float, ``amax`` -- a running max |x| that the
+producing kernel's epilogue maintains and the fp16-split conv mode (``passes=16``) turns into its power-of-two
+operand scale; ``ConvLayer`` / ``StemConv`` / ``CorrLayer`` own packed weights (hi, lo), the folded BatchNorm / bias
+vectors, their output buffers and the C-ABI plan (TMA tensor maps) that runs them.  Nothing here computes on the CPU;
+everything is enqueued on torch's current stream.
+
+``passes``: 3 = 3xTF32, 16 = 3xFP16 (both fp32-accurate), 1 = single-pass TF32.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -20,6 +25,38 @@ def _pad32(c):
     return (c + 31) // 32 * 32
 
 
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class AmaxArena(object):
+    """One device buffer for the amax scalars of every ActTensor created inside ``with arena:`` -- an engine zeroes
+    them all with a single memset per forward instead of one per tensor."""
+    _active = None
+
+    def __init__(self, slots, device="cuda"):
+        self.buf = torch.zeros(slots, device=device)
+        self.used = 0
+
+    def take(self):
+        if self.used >= self.buf.numel():
+            raise D2TError("AmaxArena exhausted")
+        self.used += 1
+        return self.buf[self.used - 1:self.used]
+
+    def zero(self):
+        self.buf.zero_()
+        ops._count(1)
+
+    def __enter__(self):
+        self._prev, AmaxArena._active = AmaxArena._active, self
+        return self
+
+    def __exit__(self, *exc):
+        AmaxArena._active = self._prev
+        return False
+
+
 def _p(t):
     return t.data_ptr() if t is not None else None
 
@@ -27,24 +64,29 @@ def _p(t):
 class ActTensor(object):
     """[N, H, W, cstride] fp32; channels [0, C) are meaningful, the rest are zero."""
 
-    def __init__(self, N, H, W, C_, cstride=None, device="cuda"):
+    def __init__(self, N, H, W, C_, cstride=None, device="cuda", amax=None):
         self.N, self.H, self.W, self.C = N, H, W, C_
         self.cstride = cstride if cstride is not None else (C_ + 3) // 4 * 4
         self.x = torch.zeros(N, H, W, self.cstride, device=device)
+        arena = AmaxArena._active
+        self.arena_owned = amax is None and arena is not None      # an engine zeroes it once per forward
+        self.amax = amax if amax is not None else (arena.take() if arena is not None else torch.zeros(1, device=device))
 
     @staticmethod
-    def from_nchw(x, cstride=None):
+    def from_nchw(x, cstride=None, amax=True):
         N, C_, H, W = x.shape
         t = ActTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device)
-        return t.load_nchw(x)
+        return t.load_nchw(x, amax=amax)
 
-    def load_nchw(self, x, coffset=0, cwidth=None):
+    def load_nchw(self, x, coffset=0, cwidth=None, amax=True):
         """write x [N, C, H, W] into channels [coffset, coffset + cwidth) (x's channels, then zeros)"""
         N, C_, H, W = x.shape
         cwidth = cwidth if cwidth is not None else self.cstride - coffset
         check(lib().d2t_nchw_to_nhwc(x.contiguous().data_ptr(), N, C_, H, W, self.cstride, coffset, cwidth,
                                      self.x.data_ptr(), _stream()), "d2t_nchw_to_nhwc")
         ops._count(1)
+        if amax:   # (not on the engine path; only a 3xFP16 consumer needs it)
+            torch.maximum(self.amax, x.detach().abs().max().reshape(1).float(), out=self.amax)
         return self
 
     def batch_slice(self, n0, n1):
@@ -52,6 +94,7 @@ class ActTensor(object):
         v = ActTensor.__new__(ActTensor)
         v.N, v.H, v.W, v.C, v.cstride = n1 - n0, self.H, self.W, self.C, self.cstride
         v.x = self.x[n0:n1]
+        v.amax, v.arena_owned = self.amax, self.arena_owned       # (a bound for the whole tensor bounds the slice)
         return v
 
     def to_nchw(self, C_=None, coffset=0):
@@ -76,10 +119,37 @@ def pack_weights(w, cin_pad=None, lo=True):
     return hi, lo_t
 
 
+def pack_weights_f16(w, cin_pad=None):
+    """OIHW -> ([O, R*S*cin_pad] fp16 hi, lo, w_exp): the pair splits w * 2^w_exp, max |w| * 2^w_exp in [2^14, 2^15)"""
+    O, I, R, S = w.shape
+    cin_pad = cin_pad or _pad64(I)
+    w = w.detach().contiguous().float()
+    wmax = float(w.abs().max())
+    w_exp = 15 - math.frexp(wmax)[1] if wmax > 0 and math.isfinite(wmax) else 0
+    w_exp = max(-100, min(100, w_exp))
+    hi = torch.empty(O, R * S * cin_pad, device=w.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    check(lib().d2t_conv_pack_weights_f16(w.data_ptr(), O, I, R, S, cin_pad, w_exp, hi.data_ptr(), lo.data_ptr(), _stream()),
+          "d2t_conv_pack_weights_f16")
+    torch.cuda.current_stream().synchronize()   # `w` may be a temporary
+    return hi, lo, w_exp
+
+
 class _Planned(object):
     plan = None
+    zero_amax = None      # the output's amax scalar when this layer owns zeroing it (stand-alone use)
+
+    def _bind_amax(self, x, out):
+        """attach the input's / output's amax scalars; outside an engine arena the layer zeroes its output's before
+        each run (inside one, several producers may share an output buffer and the engine zeroes all at once)"""
+        check(lib().d2t_conv_plan_set_amax(self.plan, _p(x.amax) if x is not None else None,
+                                           _p(out.amax) if out is not None else None), "d2t_conv_plan_set_amax")
+        if out is not None and not out.arena_owned:
+            self.zero_amax = out.amax
 
     def run(self):
+        if self.zero_amax is not None:
+            self.zero_amax.zero_()
         check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
         ops._count(1)
 
@@ -101,7 +171,11 @@ class ConvLayer(_Planned):
         if _pad32(I) > x.cstride:
             raise ValueError("input buffer has %d channels per pixel, conv needs %d" % (x.cstride, _pad32(I)))
         self.x, self.residual = x, residual
-        self.w_hi, self.w_lo = pack_weights(weight, _pad32(I), lo=(passes == 3))
+        w_exp = 0
+        if passes == 16:
+            self.w_hi, self.w_lo, w_exp = pack_weights_f16(weight, _pad64(I))
+        else:
+            self.w_hi, self.w_lo = pack_weights(weight, _pad32(I), lo=(passes == 3))
         dev = weight.device
         self.scale = scale.detach().float().contiguous().to(dev) if scale is not None else None
         self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
@@ -113,7 +187,7 @@ class ConvLayer(_Planned):
         self.out_nchw = out_nchw if out_nchw is not None else (torch.empty(x.N, O, OH, OW, device=dev) if want_nchw else None)
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=_pad32(I), in_cstride=x.cstride, Cout=O, R=R, S=S, stride=stride, pad=pad,
                      dil=dil, passes=passes, relu=int(relu), out_cstride=self.out.cstride if self.out is not None else 0,
-                     out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0)
+                     out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0, w_exp=w_exp)
         self.plan = lib().d2t_conv_plan_create(
             C.byref(d), _p(x.x), _p(self.w_hi), _p(self.w_lo), _p(self.scale), _p(self.shift),
             _p(residual.x) if residual is not None else None, _p(self.out.x) if self.out is not None else None,
@@ -124,6 +198,7 @@ class ConvLayer(_Planned):
         lib().d2t_conv_plan_info(self.plan, info)
         self.info = dict(zip(("OH", "OW", "tile_h", "tile_w", "BN", "m_tiles", "n_tiles", "grid"), list(info)))
         self.flops = 2.0 * x.N * OH * OW * O * I * R * S
+        self._bind_amax(x, self.out)
 
     def run(self):
         _Planned.run(self)
@@ -156,6 +231,7 @@ class StemConv(_Planned):
         if not self.plan:
             raise D2TError("d2t_conv_stem_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * N * OH * OW * O * I * 49
+        self._bind_amax(None, self.out)
 
     def run(self, x):
         """x: [N, C, H, W] fp32 image batch"""
@@ -184,6 +260,7 @@ class CorrLayer(_Planned):
         if not self.plan:
             raise D2TError("d2t_corr_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * x1.N * oh * ow * self.D * self.D * x1.C
+        self._bind_amax(None, out)
 
     def run(self):
         _Planned.run(self)
@@ -197,7 +274,8 @@ def maxpool3x3s2(x, out=None):
         OH -= 1
     if (OW - 1) * 2 >= x.W:
         OW -= 1
-    out = out if out is not None else ActTensor(x.N, OH, OW, x.C, x.cstride, x.x.device)
+    # (the pooled tensor shares its input's amax: max-pooling cannot raise max |x|)
+    out = out if out is not None else ActTensor(x.N, OH, OW, x.C, x.cstride, x.x.device, amax=x.amax)
     check(lib().d2t_maxpool3x3s2_nhwc(x.x.data_ptr(), x.N, x.H, x.W, x.cstride, out.x.data_ptr(), _stream()),
           "d2t_maxpool3x3s2_nhwc")
     ops._count(1)

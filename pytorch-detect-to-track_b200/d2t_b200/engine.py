@@ -11,10 +11,12 @@ for a fixed batch geometry, and computes exactly what ``_RFCN.forward`` computes
 Every convolution runs on the tcgen05/TMA implicit-GEMM kernel (csrc/conv.cu) with eval-mode
 BatchNorm folded into a per-channel scale/shift in the epilogue, the residual add and ReLU fused,
 both siamese legs batched as one 2B-image pass (the BN statistics are frozen, so this is the same
-function as the reference's python loop over legs).  Activations stay NHWC / TF32-split between
+function as the reference's python loop over legs).  Activations stay fp32 NHWC between
 convs; tensors the reference-layout operators consume (correlation, PSRoI, proposal step) are
-emitted as plain fp32 NCHW by the producing conv's epilogue.  ``passes=3`` (default) is the
-fp32-accurate 3xTF32 mode; ``passes=1`` is single-pass TF32.
+emitted as plain fp32 NCHW by the producing conv's epilogue.  ``passes=16`` (default) is the
+fp32-accurate fp16-split mode ("3xFP16": hi/lo fp16 operands with per-tensor power-of-two scales,
+twice the TF32 tensor rate; the stem and the correlations stay on 3xTF32), ``passes=3`` the
+fp32-accurate 3xTF32 mode, ``passes=1`` single-pass TF32.
 """
 import torch
 import torch.nn.functional as F
@@ -30,9 +32,16 @@ def _fold_bn(bn):
 
 
 class D2TEngine(object):
-    def __init__(self, net, pairs, height, width, passes=3, cfg_key="TEST", keep_features=False):
+    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False):
+        dev = next(net.parameters()).device
+        self.amax = dc.AmaxArena(1024, dev)       # every activation tensor's running max |x|, zeroed once per forward
+        with self.amax:
+            self._build(net, pairs, height, width, passes, cfg_key, keep_features)
+
+    def _build(self, net, pairs, height, width, passes, cfg_key, keep_features):
         from model.utils.config import cfg
         self.net, self.B, self.H, self.W, self.passes = net, pairs, height, width, passes
+        tf32_passes = 3 if passes == 16 else passes     # stem (3 input channels) and correlations: TF32 kinds only
         self.cfg_key = cfg_key
         self.keep_features = keep_features   # also emit conv3/4/5 as plain NCHW (tests / inspection)
         self.post_nms = cfg[cfg_key].RPN_POST_NMS_TOP_N
@@ -49,14 +58,14 @@ class D2TEngine(object):
 
         # ---- stem + pool
         s, b = _fold_bn(base[1])
-        self.stem = dc.StemConv(N, height, width, base[0].weight, s, b, relu=True, passes=passes, device=dev)
+        self.stem = dc.StemConv(N, height, width, base[0].weight, s, b, relu=True, passes=tf32_passes, device=dev)
         self.conv_flops += self.stem.flops
         so = self.stem.out
         ph = -(-(so.H - 3) // 2) + 1
         pw = -(-(so.W - 3) // 2) + 1
         ph -= 1 if (ph - 1) * 2 >= so.H else 0
         pw -= 1 if (pw - 1) * 2 >= so.W else 0
-        self.pool_out = dc.ActTensor(N, ph, pw, 64, device=dev)
+        self.pool_out = dc.ActTensor(N, ph, pw, 64, device=dev, amax=so.amax)
         x = self.pool_out
 
         # ---- residual stages
@@ -106,9 +115,11 @@ class D2TEngine(object):
             f = self.feat_nhwc[tag]
             assert corr.kernel_size == 1 and corr.stride1 == corr.stride2
             self.corr_layers.append(dc.CorrLayer(f.batch_slice(0, pairs), f.batch_slice(pairs, N), corr.pad_size,
-                                                 corr.max_displacement, corr.stride1, passes=passes, out=self.trk_in,
+                                                 corr.max_displacement, corr.stride1, passes=tf32_passes, out=self.trk_in,
                                                  out_coffset=coff))
-        self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, kind::tf32 x%d passes, TMA-fed, fused BN/ReLU/residual" % passes
+        kind = {16: "kind::f16 x3 passes (fp16 hi/lo split, per-tensor 2^k scales)", 3: "kind::tf32 x3 passes",
+                1: "kind::tf32 x1 pass"}[passes]
+        self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, %s, TMA-fed, fused BN/ReLU/residual" % kind
 
     # ------------------------------------------------------------------ construction helpers
     def _conv(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, want_nhwc=True,
@@ -148,6 +159,7 @@ class D2TEngine(object):
         assert tuple(im_data.shape) == (B, 2, 3, self.H, self.W), "engine was built for a fixed geometry"
         frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, 3, self.H, self.W).contiguous()     # leg-major
         info = im_info.permute(1, 0, 2).reshape(N, 3).contiguous().float()
+        self.amax.zero()
         self.stem.run(frames)
         dc.maxpool3x3s2(self.stem.out, out=self.pool_out)
         for layer in self.layers:

@@ -137,7 +137,7 @@ def correlation_forward(in1, in2, pad, k, md, s1, s2):
         # fp32-accurate 3xTF32; the NCHW operands are first re-laid out as split NHWC
         from . import conv as dc
         with torch.cuda.device_of(in1):
-            x1, x2 = dc.ActTensor.from_nchw(in1), dc.ActTensor.from_nchw(in2)
+            x1, x2 = dc.ActTensor.from_nchw(in1, amax=False), dc.ActTensor.from_nchw(in2, amax=False)
             return dc.CorrLayer(x1, x2, pad, md, s1, passes=3, want_nchw=True).run()
     with torch.cuda.device_of(in1):
         out = torch.empty(B, oc, oh, ow, device=in1.device)
