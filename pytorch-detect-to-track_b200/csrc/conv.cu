@@ -100,7 +100,14 @@ struct ConvArgs {
     const float* amax_in;
     float* amax_out;
     int w_exp;
+    long long* trace;              // debug builds only (D2T_CONV_TRACE): per-CTA wait-cycle counters
+    int exp;                       // debug builds only: experiment bit mask (env D2T_CONV_EXP)
 };
+#ifdef D2T_CONV_TRACE
+#define EXP(bit) (p.exp & (bit))
+#else
+#define EXP(bit) false
+#endif
 
 // activation scale exponent: sa = 2^ea puts the tensor's max |x| into [2^14, 2^15)
 __device__ __forceinline__ int act_exp(const float* amax) {
@@ -161,13 +168,15 @@ struct Sched {
     }
 };
 
-template <int BN, int PASSES, bool PAIR = false>
+template <int BN, int PASSES, bool PAIR = false, bool EPI2 = false>
 struct Cfg {
     static constexpr bool F16 = PASSES == 16;
     static constexpr bool SPLIT = PASSES != 1;                        // three products per K step
     static constexpr int KBLK = kblk_of(PASSES);                      // channels per K block
     static constexpr int CHUNK = chunk_of(PASSES);                    // K blocks per TMEM chunk
-    static constexpr int THREADS = F16 ? 448 : 384;                   // 3xFP16: warps 12-13 are two more converters
+    // 3xFP16: 16 warps -- warps 12-13 are two more converters (14-15 idle) -- so that the register file can be
+    // re-split by warpgroup (setmaxnreg): 80 registers for the TMA / MMA / converter warps, 176 for the epilogue
+    static constexpr int THREADS = F16 ? 512 : 384;
     static constexpr int CVT_THREADS = F16 ? 128 : 64;
     // 3xFP16: A = two fp32 [128 x 32] sub-tiles as loaded, rewritten in place as fp16 [128 x 64] hi | lo
     static constexpr int A_BYTES = kBlockM * KBLK * 4;                // 16 KB (32 KB)
@@ -178,10 +187,15 @@ struct Cfg {
     static constexpr int OFF_ALO = F16 ? A_BYTES / 2 : A_BYTES;
     static constexpr int OFF_BHI = F16 ? A_BYTES : NOPER * A_BYTES;
     static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
-    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    // output staging: [128 x 32] fp32 slabs (TMA store; EPI2: also the TMA-loaded residual).  Default: one slab per
+    // epilogue group, reused by the BN/64 slabs of a tile.  EPI2 (layers whose time is the epilogue, not the K loop: short
+    // K, residual): one buffer for EVERY slab of the tile, paid for with one pipeline stage.
+    static constexpr int OUT_SLABS = EPI2 ? BN / 64 : 1;             // buffers per group
+    static constexpr int OUT_STAGE_BYTES = 2 * OUT_SLABS * kBlockM * 128;
+    static constexpr int STAGES_RAW = (228 * 1024 - OUT_STAGE_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int OUT_STAGE_BYTES = 2 * kBlockM * 128;        // one [128 x 32] fp32 slab per epilogue group (TMA store)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/ +
+                                      1024 /*scale | shift of the current n tile*/;
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
     static constexpr int TMEM_COLS = (SPLIT ? 4 : 2) * BN;            // power of two >= 32 for BN in {64,128}
 };
@@ -212,6 +226,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_4d_nocommit(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -305,6 +324,31 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Debug builds (make trace: -DD2T_CONV_TRACE, libd2t_b200_trace.so) account the cycles every role spends in each of its
+// waits; slot layout in scripts/conv_trace.py.  Compiled out of the product library.
+#ifdef D2T_CONV_TRACE
+#define TRACE_DECL long long trace_t0__ = 0, trace_acc__[4] = {0, 0, 0, 0}
+#define TRACED_WAIT(slot, bar, parity)            \
+    do {                                          \
+        const long long t__ = clock64();          \
+        mbar_wait_sleep(bar, parity);             \
+        trace_acc__[slot] += clock64() - t__;     \
+    } while (0)
+#define TRACE_BEGIN() trace_t0__ = clock64()
+#define TRACE_FLUSH(role)                                                                        \
+    do {                                                                                         \
+        if (p.trace && lane == 0) {                                                              \
+            long long* d__ = p.trace + ((size_t)blockIdx.x * 8 + (role)) * 8;                    \
+            d__[0] = clock64() - trace_t0__;                                                     \
+            d__[1] = trace_acc__[0]; d__[2] = trace_acc__[1]; d__[3] = trace_acc__[2]; d__[4] = trace_acc__[3]; \
+        }                                                                                        \
+    } while (0)
+#else
+#define TRACE_DECL
+#define TRACED_WAIT(slot, bar, parity) mbar_wait_sleep(bar, parity)
+#define TRACE_BEGIN()
+#define TRACE_FLUSH(role)
+#endif
 
 // ------------------------------------------------------------------ the kernel
 // CORR = true turns the same pipeline into the cross-frame correlation (correlation/src/
@@ -325,14 +369,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // (D2T_CONV_PAIR=1 enables them) and kept as the validated cta_group::2 path.  The leader CTA issues the MMAs and owns the
 // `full` / `tempty` / `xempty` barriers (both CTAs' TMA and epilogue warps signal them remotely); its commits
 // are multicast to both CTAs' `empty` / `tfull` barriers.
-template <int BN, int PASSES, bool CORR, bool PAIR>
-__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR>::THREADS), 1)
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2>
+__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
 conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
                 const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
                 const __grid_constant__ CUtensorMap tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
                 const __grid_constant__ CUtensorMap tmO,      // NHWC output (TMA store)
+                const __grid_constant__ CUtensorMap tmR,      // NHWC residual (EPI2: TMA load into the output slabs)
                 const ConvArgs p) {
-    using C = Cfg<BN, PASSES, PAIR>;
+    using C = Cfg<BN, PASSES, PAIR, EPI2>;
+    static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
     static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
@@ -347,7 +393,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA: chunk buffer drained
     uint64_t* xempty = tempty + 2;                // [2]        epilogue -> MMA: cross-term buffer read
     uint64_t* cvt = xempty + 2;                   // [STAGES]   converters -> MMA: lo tile(s) of the stage written
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cvt + C::STAGES);
+    uint64_t* rfull = cvt + C::STAGES;            // [2]        TMA -> epilogue group: residual slabs landed (EPI2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CS = PAIR ? 2 : 1;               // CTAs per work unit
@@ -362,6 +409,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         prefetch_tmap(&tmB_hi);
         if (SPLIT && !CORR) prefetch_tmap(&tmB_lo);
         if (!CORR && p.out) prefetch_tmap(&tmO);
+        if (EPI2 && p.res) prefetch_tmap(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
@@ -373,6 +421,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], CS * kEpiThreads);       // (leader's copy collects both CTAs' epilogue threads)
             mbar_init(&xempty[i], CS * kEpiThreads);
+            mbar_init(&rfull[i], 1);
         }
         fence_mbar_init();
     }
@@ -398,6 +447,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
 
+    if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
+    // ---- warpgroups 0 (and 3 in 3xFP16 mode): TMA producer, MMA issuer, converters
+    if constexpr (F16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 0) {
         // ===================== TMA producer =====================
         // One lane per operand copy (A x, A lo, B x, B lo), all four walking the same K loop; (r, s, kc) advance
@@ -415,6 +467,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const int a_c0 = is_a ? lane * kBoxC : 0;            // first channel of this lane's sub-tile in the K block
             int stage = 0;
             uint32_t phase = 0;
+            TRACE_DECL;
+            TRACE_BEGIN();
             for (int e = 0; e < sched.nseg; ++e) {
                 const Seg sg = sched.get(e);
                 const int t = sg.tile;
@@ -429,7 +483,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
                 int kc = k_beg % p.kc_blocks, rs = k_beg / p.kc_blocks, s = rs % p.S, r = rs / p.S;
                 for (int k = k_beg; k < k_end; ++k) {
-                    mbar_wait_sleep(&empty[stage], phase ^ 1);
+                    TRACED_WAIT(0, &empty[stage], phase ^ 1);
                     uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
                     uint64_t* fbar = &full[stage];
                     if (PAIR) {
@@ -463,6 +517,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     }
                 }
             }
+            TRACE_FLUSH(0);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -478,24 +533,26 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const uint64_t desc0 = make_smem_desc(smem_u32(smem));     // stage s / operand o: + (byte offset >> 4)
             int stage = 0, cbuf = 0, local = 0;
             uint32_t phase = 0, cphase = 0;
+            TRACE_DECL;
+            TRACE_BEGIN();
             for (; local < sched.nseg; ++local) {
                 const Seg sg = sched.get(local);
                 const int xacc = local & 1;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
                 if (SPLIT) {
-                    mbar_wait_sleep(&xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
+                    TRACED_WAIT(0, &xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
                     tc_fence_after();
                 }
                 const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
                     const int kin = k % kChunkK;
                     if (kin == 0) {
-                        mbar_wait_sleep(&tempty[cbuf], cphase ^ 1);          // epilogue drained this chunk buffer
+                        TRACED_WAIT(1, &tempty[cbuf], cphase ^ 1);          // epilogue drained this chunk buffer
                         tc_fence_after();
                     }
                     const uint32_t d_main = tmem_base + cbuf * BN;
-                    mbar_wait_sleep(&full[stage], phase);
-                    if (SPLIT || PAIR) mbar_wait_sleep(&cvt[stage], phase);   // lo tiles written (pair: peer landed too)
+                    TRACED_WAIT(2, &full[stage], phase);
+                    if (SPLIT || PAIR) TRACED_WAIT(3, &cvt[stage], phase);   // lo tiles written (pair: peer landed too)
                     tc_fence_after();
                     const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
                     if (SPLIT) {
@@ -543,8 +600,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     }
                 }
             }
+            TRACE_FLUSH(1);
         }
-    } else if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
+    } else if (warp < kEpiWarp0 || warp == kEpiWarp0 + 8 || warp == kEpiWarp0 + 9) {
         // ===================== converters (warps 2-3; 3xFP16: + warps 12-13) =====================
         // lo = x - trunc13(x) for the activation tile of every landed stage (and for the second frame's tile in
         // correlation mode): same swizzled address in the stage's "lo" slot, so the layout needs no thought.
@@ -562,11 +620,13 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const float sa = pow2f(act_exp(p.amax_in));
             int stage = 0;
             uint32_t phase = 0;
+            TRACE_DECL;
+            TRACE_BEGIN();
             for (int e = 0; e < sched.nseg; ++e) {
                 const Seg sg = sched.get(e);
                 const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
-                    mbar_wait_sleep(&full[stage], phase);
+                    TRACED_WAIT(0, &full[stage], phase);
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
 #pragma unroll 1
                     for (int pass = 0; pass < 2; ++pass) {
@@ -606,6 +666,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     }
                 }
             }
+            TRACE_FLUSH(2 + cw);
         } else if (PASSES == 3 || PAIR) {
             const int ct = threadIdx.x - 64;                       // 0..63
             int stage = 0;
@@ -648,8 +709,11 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 }
             }
         }
+    }
     } else {
-        // ===================== epilogue =====================
+        // ===================== epilogue (warpgroups 1-2) =====================
+        // 3xFP16: these warps hold a 64-column accumulator row AND the prefetched residual row in registers
+        if constexpr (F16) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         const int q = (warp - kEpiWarp0) & 3;              // TMEM lane quarter of this warp
         const int grp = (warp - kEpiWarp0) >> 2;           // column half of the tile this warp owns
         constexpr int HN = BN / 2;                         // columns per thread
@@ -658,13 +722,31 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         const int TW = 1 << p.TW_log2;
         const int hl = m >> p.TW_log2, wl = m & (TW - 1);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        // 3xFP16: the accumulator holds (x * 2^ea) . (w * 2^w_exp); undo both (exact) ahead of the affine
+        // 3xFP16: the accumulator holds (x * 2^ea) . (w * 2^w_exp); the drain undoes both (exact: fma by a power of two)
         const float descale = F16 ? pow2f(-(act_exp(p.amax_in) + p.w_exp)) : 1.f;
         int local = 0, cbuf = 0;
-        uint32_t cphase = 0;
+        uint32_t cphase = 0, rphase = 0;
+        TRACE_DECL;
+        TRACE_BEGIN();
+        float tmax = 0.f;                                   // max |value| this thread wrote (all its tiles)
+        // Folded BatchNorm / bias of the current n tile live in shared memory ([BN] scale | [BN] shift): every thread needs
+        // all of its 64 channels' values every tile, and as global loads they paid an L2 round trip per 16 channels
+        // (measured: the affine loop was 5-7k cycles per tile).  Thread et fetches ONE value a tile ahead (register),
+        // so the latency hides behind the previous tile; channels past Cout read a clamped index and are never stored.
+        float* scsh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
+        const int et = (warp - kEpiWarp0) * 32 + lane;     // 0..255
+        auto fetch_scsh = [&](int tile) -> float {
+            if (CORR || et >= 2 * BN) return 0.f;
+            const bool is_shift = et >= BN;
+            const float* src = is_shift ? p.shift : p.scale;
+            const int chn = min((tile % p.n_tiles) * BN + (is_shift ? et - BN : et), p.Cout - 1);
+            return src ? __ldg(src + chn) : (is_shift ? 0.f : 1.f);
+        };
+        float scsh_next = sched.nseg > 0 ? fetch_scsh(sched.get(0).tile) : 0.f;
         for (; local < sched.nseg; ++local) {
-            float tmax = 0.f;                               // max |value| this thread wrote for this tile
             const Seg sg = sched.get(local);
+            const float scsh_cur = scsh_next;
+            if (local + 1 < sched.nseg) scsh_next = fetch_scsh(sched.get(local + 1).tile);
             const int t = sg.tile, nchunks = sg.c1 - sg.c0;
             const int xacc = local & 1;
             const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
@@ -673,18 +755,39 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const bool pix_ok = oh < p.OH && ow < p.OW && img < p.N;   // (a pair's second tile may not exist)
             const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
             const int n0 = n_tile * BN;
+            // EPI2: the residual tile is requested NOW -- before the accumulator is even complete -- as bulk tensor
+            // loads straight into this group's output slabs (the epilogue then adds and overwrites in place, each thread
+            // its own row): 64 KB per SM in flight on the TMA engine, which plain loads cannot sustain (the LSU keeps
+            // ~16 KB in flight per SM: measured ~10 B/clk/SM for register-prefetched residual rows)
+            const bool res_tma = EPI2 && !CORR && p.res != nullptr && sg.role != 1;
+            if constexpr (EPI2) {
+                if (res_tma && m == 0) {
+                    tma_store_wait_read();                  // the previous tile's stores have read the slabs
+                    int nsl = 0;
+#pragma unroll
+                    for (int sl = 0; sl < HN / 32; ++sl) nsl += (n0 + cofs + sl * 32 < p.Cout) ? 1 : 0;
+                    mbar_expect_tx(&rfull[grp], nsl * (kBlockM * 128));
+#pragma unroll
+                    for (int sl = 0; sl < HN / 32; ++sl) {
+                        const int chs = n0 + cofs + sl * 32;
+                        if (chs < p.Cout)
+                            tma_load_4d(out_stage + (grp * C::OUT_SLABS + sl) * (kBlockM * 128), &tmR, &rfull[grp], chs,
+                                        tw << p.TW_log2, th * p.TH, img);
+                    }
+                }
+            }
             float acc[HN];
 #pragma unroll
             for (int j = 0; j < HN; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchunks; ++ch) {          // drain finished chunks: fp32 round-to-nearest adds
-                mbar_wait_sleep(&tfull[cbuf], cphase);
+                TRACED_WAIT(0, &tfull[cbuf], cphase);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < HN / 16; ++c) {
                     float v[16];
                     tmem_ld16(lane_base + cbuf * BN + cofs + c * 16, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] = F16 ? fmaf(v[j], descale, acc[c * 16 + j]) : acc[c * 16 + j] + v[j];
                 }
                 tc_fence_before();
                 if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(&tempty[cbuf]), 0));
@@ -698,13 +801,16 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     float v[16];
                     tmem_ld16(lane_base + (2 + xacc) * BN + cofs + c * 16, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] = F16 ? fmaf(v[j], descale, acc[c * 16 + j]) : acc[c * 16 + j] + v[j];
                 }
                 tc_fence_before();
                 if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(&xempty[xacc]), 0));
                 else mbar_arrive(&xempty[xacc]);
             }
             // ---- from here on the tile lives in registers; the tensor core is already on the next segment
+#ifdef D2T_CONV_TRACE
+            const long long t_post__ = clock64();
+#endif
             if (sg.role == 1) {
                 // partial tile: publish registers -> scratch[cta][column][row] (coalesced across the warp)
                 float* dst = p.sk_scratch + ((size_t)blockIdx.x * BN + cofs) * kBlockM + m;
@@ -760,44 +866,40 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 }
                 (void)r;
             } else {
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue thread is done with the previous tile's values
+            if (et < 2 * BN) scsh[et] = scsh_cur;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if constexpr (EPI2) {
+                if (res_tma) {                               // the residual slabs of this group have landed
+                    TRACED_WAIT(2, &rfull[grp], rphase);
+                    rphase ^= 1;
+                }
+            }
 #pragma unroll
             for (int c = 0; c < HN / 16; ++c) {
                 float* v = acc + c * 16;
                 const int ch0 = n0 + cofs + c * 16;
                 if (ch0 >= p.Cout) continue;                 // (warp-uniform)
                 const bool full16 = ch0 + 16 <= p.Cout;
-                if (full16) {                                // per-channel affine (folded BN / bias): 128-bit loads
-                    if (p.scale) {
+                {                                            // per-channel affine (folded BN / bias) from shared memory
+                    const float4* sc4 = reinterpret_cast<const float4*>(scsh + cofs + c * 16);
+                    const float4* sh4 = reinterpret_cast<const float4*>(scsh + BN + cofs + c * 16);
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
-                            if (F16) {
-                                v[j] *= sc.x * descale; v[j + 1] *= sc.y * descale; v[j + 2] *= sc.z * descale; v[j + 3] *= sc.w * descale;
-                            } else {
-                                v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
-                            }
-                        }
-                    } else if (F16) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] *= descale;
-                    }
-                    if (p.shift) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
-                            v[j] += sh.x; v[j + 1] += sh.y; v[j + 2] += sh.z; v[j + 3] += sh.w;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int chn = min(ch0 + j, p.Cout - 1);
-                        const float sc = (p.scale ? __ldg(p.scale + chn) : 1.f) * descale;
-                        const float sh = p.shift ? __ldg(p.shift + chn) : 0.f;
-                        v[j] = v[j] * sc + sh;
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 sc = sc4[j >> 2], sh = sh4[j >> 2];
+                        v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                        v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
                     }
                 }
-                if (p.res && pix_ok) {
+                if (res_tma) {
+                    // (channels / pixels outside the tensor were zero-filled by the TMA)
+                    const uint8_t* rrow = out_stage + (grp * C::OUT_SLABS + (c >> 1)) * (kBlockM * 128) + (uint32_t)m * 128u;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(rrow + (((uint32_t)((c & 1) * 4 + (j >> 2)) ^ ((uint32_t)m & 7u)) << 4));
+                        v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                    }
+                } else if (p.res && pix_ok) {
                     const float* rh = p.res + pix * p.res_cstride + ch0;
                     if (full16) {
 #pragma unroll
@@ -816,9 +918,15 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (p.amax_out && pix_ok) {
+                    if (full16) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full16 || ch0 + j < p.Cout) tmax = fmaxf(tmax, fabsf(v[j]));
+                        for (int j = 0; j < 16; j += 4)
+                            tmax = fmaxf(fmaxf(tmax, fmaxf(fabsf(v[j]), fabsf(v[j + 1]))), fmaxf(fabsf(v[j + 2]), fabsf(v[j + 3])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < p.Cout) tmax = fmaxf(tmax, fabsf(v[j]));
+                    }
                 }
                 if (p.out_nchw && pix_ok) {
                     float* o = p.out_nchw + (((size_t)img * p.Cout + ch0) * p.OH + oh) * p.OW + ow;
@@ -828,12 +936,45 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         if (full16 || ch0 + j < p.Cout) o[j * cs] = v[j];     // lanes = consecutive ow: coalesced
                 }
             }
+#ifdef D2T_CONV_TRACE
+            trace_acc__[3] += clock64() - t_post__;          // affine / residual / relu / amax part
+#endif
             if (p.out) {
                 // NHWC output through shared memory + TMA store: the 128 threads of this group lay their rows
                 // (32 channels = 128 B each) into a SWIZZLE_128B slab, then ONE bulk tensor store writes the
                 // [TH x TW x 32] box as full lines; pixels / channels outside the tensor are clipped by the TMA.
-                uint8_t* slab = out_stage + grp * (kBlockM * 128);
+                // EPI2: every slab of the tile has its own buffer, so the stores of a whole tile are issued back to back
+                // and their smem reads are only waited for one tile later (with a residual: before its loads above).
                 const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)m & 7u;
+                if constexpr (EPI2) {
+                    if (!res_tma) {
+                        if (m == 0) tma_store_wait_read();    // the previous tile's stores have read the slabs
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < HN / 32; ++sl) {
+                        if (n0 + cofs + sl * 32 >= p.Cout) continue;   // (uniform over the group)
+                        uint8_t* slab = out_stage + (grp * C::OUT_SLABS + sl) * (kBlockM * 128);
+                        const float* v = acc + sl * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(slab + row_off + ((((uint32_t)j >> 2) ^ sw) << 4)) =
+                                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                    if (m == 0) {
+#pragma unroll
+                        for (int sl = 0; sl < HN / 32; ++sl) {
+                            const int chs = n0 + cofs + sl * 32;
+                            if (chs < p.Cout)
+                                tma_store_4d_nocommit(&tmO, out_stage + (grp * C::OUT_SLABS + sl) * (kBlockM * 128), chs,
+                                                      tw << p.TW_log2, th * p.TH, img);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else {
+                uint8_t* slab = out_stage + grp * (kBlockM * 128);
 #pragma unroll
                 for (int sl = 0; sl < HN / 32; ++sl) {
                     const int chs = n0 + cofs + sl * 32;
@@ -849,12 +990,26 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
                     if (m == 0) tma_store_4d(&tmO, slab, chs, tw << p.TW_log2, th * p.TH, img);
                 }
+                }
             }
             }   // !CORR
-            if (p.amax_out) {                               // running max |x| of the output tensor (values are >= 0: integer order)
-                const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));
-                if (lane == 0 && wmax != 0u) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
-            }
+#ifdef D2T_CONV_TRACE
+            trace_acc__[1] += clock64() - t_post__;
+#endif
+        }
+#ifdef D2T_CONV_TRACE
+        if ((warp - kEpiWarp0) % 4 == 0) TRACE_FLUSH(6 + (warp - kEpiWarp0) / 4);
+#endif
+        if (p.amax_out) {
+            // running max |x| of the output tensor: ONE atomic per CTA and layer (values are >= 0, so unsigned integer
+            // order is float order) -- same-address atomics serialise in the L2 slice and would back up the store path
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));
+            uint32_t* red = tmem_slot + 1;                    // spare word next to the TMEM address
+            if (warp == kEpiWarp0 && lane == 0) *red = 0u;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (lane == 0) atomicMax(red, wmax);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == kEpiWarp0 && lane == 0 && *red != 0u && !EXP(8)) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), *red);
         }
     }
     if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
@@ -971,16 +1126,18 @@ struct d2t_conv_plan {
     alignas(64) CUtensorMap tmB_hi;
     alignas(64) CUtensorMap tmB_lo;
     alignas(64) CUtensorMap tmO;
+    alignas(64) CUtensorMap tmR;
     ConvArgs args;
     int BN, passes, grid, corr;
+    int epi2;                  // 3xFP16, BN = 128: the full-tile output staging / TMA residual variant
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
 };
 
-template <int BN, int PASSES, bool CORR, bool PAIR>
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
-    using C = Cfg<BN, PASSES, PAIR>;
+    using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
@@ -998,8 +1155,8 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = PAIR ? 2 : 1;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
-                                   args),
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
+                                   pl->tmR, args),
                 "conv_igemm launch");
     return 1;
 }
@@ -1012,7 +1169,7 @@ static int max_pairs() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
     if (cached[dev]) return cached[dev];
-    auto kern = conv_igemm<BN, PASSES, false, true>;
+    auto kern = conv_igemm<BN, PASSES, false, true, false>;
     int n = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
@@ -1057,8 +1214,12 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
         set_error("d2t_conv_plan_create: 3-pass mode needs the lo half of the packed weights");
         return nullptr;
     }
-    if ((out && (d->out_cstride % 4 != 0 || d->out_coffset % 4 != 0)) || (!out && !out_nchw)) {
-        set_error("d2t_conv_plan_create: need an output (NHWC with 4-aligned channel stride/offset, and/or NCHW)");
+    if ((out && (d->out_cstride % 4 != 0 || d->out_coffset % 4 != 0 || d->Cout % 4 != 0)) || (!out && !out_nchw)) {
+        set_error("d2t_conv_plan_create: need an output (NHWC with Cout and the channel stride/offset multiples of 4, and/or NCHW)");
+        return nullptr;
+    }
+    if (res && ((d->res_cstride > 0 ? d->res_cstride : d->Cout) % 4 != 0 || d->Cout % 4 != 0)) {
+        set_error("d2t_conv_plan_create: the residual needs Cout and its channel stride to be multiples of 4");
         return nullptr;
     }
     const int OH = (d->H + 2 * d->pad - d->dil * (d->R - 1) - 1) / d->stride + 1;
@@ -1095,7 +1256,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.relu = d->relu;
     a.out = out; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp; a.trace = nullptr; a.exp = 0;
     pl->passes = d->passes; pl->corr = 0;
     // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
     pl->pair = (!f16 && a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
@@ -1134,6 +1295,14 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     if (ok && d->passes == 1) pl->tmB_lo = pl->tmB_hi;
     if (ok && out) ok = encode_out_map(&pl->tmO, out, d->N, OH, OW, d->Cout, d->out_cstride, d->out_coffset, TH, TW);
     else if (ok) pl->tmO = pl->tmA;
+    // EPI2 variant (3xFP16, BN = 128, NHWC output): layers whose time is the epilogue rather than the K loop -- a residual
+    // to add, or at most two K chunks per tile -- trade one pipeline stage for full-tile output staging and take the
+    // residual through the TMA.  D2T_CONV_EPI2=0/1 forces the choice (experiments).
+    pl->epi2 = (f16 && pl->BN == 128 && out && (res || a.R * a.S * a.kc_blocks <= 2 * chunk_of(16))) ? 1 : 0;
+    if (f16 && pl->BN == 128 && out && getenv("D2T_CONV_EPI2")) pl->epi2 = atoi(getenv("D2T_CONV_EPI2")) ? 1 : 0;
+    pl->tmR = pl->tmA;
+    if (ok && pl->epi2 && res)
+        ok = encode_out_map(&pl->tmR, const_cast<float*>(res), d->N, OH, OW, d->Cout, a.res_cstride, 0, TH, TW);
     if (!ok) {
         free(pl);
         return nullptr;
@@ -1178,7 +1347,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.scale = scale; a.shift = shift; a.res = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0; pl->pair = 0;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7, passes);
     {
         SkScratch sk;
@@ -1246,7 +1415,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
     pl->BN = 128; pl->passes = passes; pl->corr = 1; pl->pair = 0;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks, passes);
     {
         SkScratch sk;
@@ -1279,6 +1448,15 @@ extern "C" int d2t_conv_plan_set_amax(d2t_conv_plan* pl, const float* amax_in, f
     return 1;
 }
 
+#ifdef D2T_CONV_TRACE
+// debug builds only: [grid][8 roles][8] cycle counters (scripts/conv_trace.py)
+extern "C" __attribute__((visibility("default"))) int d2t_conv_plan_set_trace(d2t_conv_plan* pl, long long* trace) {
+    pl->args.trace = trace;
+    pl->args.exp = getenv("D2T_CONV_EXP") ? atoi(getenv("D2T_CONV_EXP")) : 0;
+    return pl->grid;
+}
+#endif
+
 extern "C" void d2t_conv_plan_destroy(d2t_conv_plan* pl) {
     if (pl) free(pl);
 }
@@ -1295,8 +1473,10 @@ extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->corr)
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))
-    if (pl->passes == 16)
-        return pl->BN == 64 ? launch_conv<64, 16, false, false>(pl, stream) : launch_conv<128, 16, false, false>(pl, stream);
+    if (pl->passes == 16) {
+        if (pl->BN == 64) return launch_conv<64, 16, false, false>(pl, stream);
+        return pl->epi2 ? launch_conv<128, 16, false, false, true>(pl, stream) : launch_conv<128, 16, false, false>(pl, stream);
+    }
     if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);
     return pl->BN == 64 ? D2T_RUN(64, 1) : D2T_RUN(128, 1);
 #undef D2T_RUN

@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libd2t_b200.so")
+SO_PATH = os.environ.get("D2T_B200_LIB") or os.path.join(_HERE, "libd2t_b200.so")   # (override: debug builds only)
 CSRC_DIR = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 HEADER = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "d2t_b200.h"))
 
