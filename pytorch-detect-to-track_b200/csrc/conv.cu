@@ -377,6 +377,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const __grid_constant__ CUtensorMap tmO,      // NHWC output (TMA store)
                 const __grid_constant__ CUtensorMap tmR,      // NHWC residual (EPI2: TMA load into the output slabs)
                 const ConvArgs p) {
+#ifdef D2T_CONV_TRACE
+    const long long t_entry__ = clock64();
+#endif
     using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT;
@@ -444,8 +447,14 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     const Sched sched(tiles, k_iters, kChunkK, unit_id, n_units);
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
     // overlapped the tail of the previous layer; from here on we touch its output.
+#ifdef D2T_CONV_TRACE
+    const long long t_prol__ = clock64();
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+#ifdef D2T_CONV_TRACE
+    const long long t_dep__ = clock64();
+#endif
 
     if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
     // ---- warpgroups 0 (and 3 in 3xFP16 mode): TMA producer, MMA issuer, converters
@@ -1012,15 +1021,38 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             if (warp == kEpiWarp0 && lane == 0 && *red != 0u && !EXP(8)) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), *red);
         }
     }
+#ifdef D2T_CONV_TRACE
+    const long long t_w0__ = clock64();
+#endif
     if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
+#ifdef D2T_CONV_TRACE
+    if (p.trace && warp == kEpiWarp0 && lane == 0) {
+        p.trace[(size_t)blockIdx.x * 64 + 16 + 5] = clock64() - t_w0__;     // role 2 value 5: the final store wait
+        p.trace[(size_t)blockIdx.x * 64 + 16 + 6] = t_w0__ - t_entry__;     // role 2 value 6: epilogue warp 0 done (from entry)
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();                  // the peer may still signal my barriers / feed my tensor core
+#ifdef D2T_CONV_TRACE
+    const long long t_sync__ = clock64();
+#endif
     if (warp == 2) {
         if (PAIR)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+#ifdef D2T_CONV_TRACE
+        const long long t_de__ = clock64();
+        if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 64 + 16 + 7] = t_de__ - t_sync__;   // role 2 value 7: the dealloc itself
+        if (p.trace && lane == 0) {     // kernel-level timeline of this CTA: role slot 0 (producer), values 5..7 and role 1 value 5
+            long long* d__ = p.trace + (size_t)blockIdx.x * 64;
+            d__[5] = t_prol__ - t_entry__;      // entry -> prologue done (barriers, TMEM, descriptors)
+            d__[6] = t_dep__ - t_entry__;       // entry -> the previous grid is complete
+            d__[7] = t_sync__ - t_entry__;      // entry -> every role done (stores waited for)
+            d__[8 + 5] = clock64() - t_entry__; // entry -> TMEM released
+        }
+#endif
     }
 }
 

@@ -20,15 +20,19 @@ fn = lib().d2t_conv_plan_set_trace
 fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_void_p]
 grid = fn(layer.plan, trace.data_ptr())
 flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+layer.zero_amax = None
 for _ in range(3):
     flush.add_(1.0)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); layer.run(); b.record()
+    a.record(); layer.run(); layer.run(); layer.run(); b.record()      # (the trace is the last launch's)
     torch.cuda.synchronize()
-print("layer", sys.argv[1:], "info", layer.info, "time %.1f us" % (a.elapsed_time(b) * 1e3))
+print("layer", sys.argv[1:], "info", layer.info, "time %.1f us per launch (3 back to back)" % (a.elapsed_time(b) * 1e3 / 3))
 t = trace.view(148, 8, 8)[:grid].double().cpu()
 names = ["producer  [total, wait empty]", "mma       [total, wait xempty, wait tempty, wait full, wait cvt]",
          "cvt0      [total, wait full]", "cvt1", "cvt2", "cvt3", "epilogue0 [total, wait tfull, post-accumulate part, of which wait residual, post up to the end of the affine loop]", "epilogue1"]
+print("kernel timeline (cycles from CTA entry): prologue done %d, previous grid complete %d, all roles done %d, TMEM released %d" %
+      (t[:, 0, 5].mean(), t[:, 0, 6].mean(), t[:, 0, 7].mean(), t[:, 1, 5].mean()))
+print("   epilogue warp 0 done at %d, final store wait %d cycles, dealloc %d cycles" % (t[:, 2, 6].mean(), t[:, 2, 5].mean(), t[:, 2, 7].mean()))
 for r in range(8):
     m = t[:, r, :5]
     print("%-70s mean %s   max-total %d" % (names[r], [int(v) for v in m.mean(0)], int(m[:, 0].max())))
