@@ -197,7 +197,16 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/ +
                                       1024 /*scale | shift of the current n tile*/;
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
-    static constexpr int TMEM_COLS = (SPLIT ? 4 : 2) * BN;            // power of two >= 32 for BN in {64,128}
+    // TMEM columns.  TF32: main[2] chunk accumulators (+ cross[2] whole-tile accumulators in 3-pass mode), BN each.
+    // 3xFP16: main[2] only (the cross terms join the chunk accumulator) + the A OPERAND RING: per pipeline stage 32 columns
+    // of hi and 32 of lo (128 lanes = pixel rows x 64 channels of packed fp16), written by the converter warps with
+    // tcgen05.st and read by tcgen05.mma directly -- the tensor core's A reads leave shared memory altogether.
+    static constexpr bool ATMEM = F16;
+    static constexpr int A_TMEM_COLS = 64;
+    static constexpr int A_TMEM_BASE = 2 * BN;
+    static constexpr int TMEM_USED = ATMEM ? 2 * BN + STAGES * A_TMEM_COLS : (SPLIT ? 4 : 2) * BN;
+    static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
+    static_assert(TMEM_USED <= 512, "tensor memory budget");
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -282,12 +291,20 @@ template <int BN, int M = kBlockM>
 __device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
     return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
+// kind::f16 MMA with the A operand in tensor memory (lane = row, 2 fp16 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -382,7 +399,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 #endif
     using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
-    constexpr bool F16 = C::F16, SPLIT = C::SPLIT;
+    constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
     static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
     extern __shared__ uint8_t smem_raw[];
@@ -458,7 +475,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 
     if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
     // ---- warpgroups 0 (and 3 in 3xFP16 mode): TMA producer, MMA issuer, converters
-    if constexpr (F16) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if constexpr (F16) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0) {
         // ===================== TMA producer =====================
         // One lane per operand copy (A x, A lo, B x, B lo), all four walking the same K loop; (r, s, kc) advance
@@ -548,7 +565,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const Seg sg = sched.get(local);
                 const int xacc = local & 1;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
-                if (SPLIT) {
+                if (SPLIT && !ATMEM) {
                     TRACED_WAIT(0, &xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
                     tc_fence_after();
                 }
@@ -572,9 +589,12 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         for (int kk = 0; kk < 4; ++kk) {                  // 4 K steps of 32 bytes per 128-byte row
                             const uint64_t o = (uint64_t)(kk * 32 >> 4);
                             if (F16) {
-                                umma_f16(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
-                                umma_f16(d_cross, a_hi + o, b_lo + o, idesc, 1);
-                                umma_f16(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                                // A from tensor memory (8 columns = 16 fp16 per K step); all three products of the K step
+                                // go to the chunk accumulator (48 accumulation steps per 256-channel chunk)
+                                const uint32_t at_hi = tmem_base + C::A_TMEM_BASE + stage * C::A_TMEM_COLS + kk * 8;
+                                umma_f16_ts(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
+                                umma_f16_ts(d_main, at_hi, b_lo + o, idesc, 1);
+                                umma_f16_ts(d_main, at_hi + 32, b_hi + o, idesc, 1);
                             } else if (PAIR) {
                                 umma_tf32_pair(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                                 umma_tf32_pair(d_cross, a_hi + o, b_lo + o, idesc, 1);
@@ -619,13 +639,15 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         // completes on its OWN `full` barrier, and the leader's MMA thread waits for both CTAs' cvt arrivals.
         if constexpr (F16) {
             // 3xFP16: the landed activation tile is two fp32 [128 rows x 32 channels] sub-tiles (128-byte rows,
-            // SWIZZLE_128B).  Row m of the fp16 operand tiles is again 128 bytes: 64 channels of hi (same place as
-            // sub-tile 0) and of lo (sub-tile 1), same swizzle.  Lanes l and l + 16 of a warp own one row: each reads
-            // its sub-tile's 32 floats, scales by sa (exact), splits x*sa = hi + lo (hi = top 11 significant bits,
-            // lo = the remainder rounded to fp16), and after a __syncwarp writes its 32 channels of both rows.  A
-            // quarter warp touches 8 consecutive rows of one sub-tile, so every 16-byte access is conflict-free.
-            const int cw = warp < kEpiWarp0 ? warp - 2 : warp - (kEpiWarp0 + 8) + 2;      // converter warp 0..3
-            const int sub = lane >> 4;
+            // SWIZZLE_128B).  A converter thread owns ONE pixel row -- the row whose TMEM lane its warp may address (warps
+            // 2, 3, 12, 13 = lane quarters 2, 3, 0, 1) -- reads its 64 floats (quarter warps touch 8 consecutive rows: every
+            // 16-byte access is conflict-free), scales by sa (exact), splits x*sa = hi + lo (hi = top 11 significant bits,
+            // lo = the remainder rounded to fp16) and stores the packed pairs into the stage's A slot in tensor memory.
+            const int cw = warp < kEpiWarp0 ? warp - 2 : warp - (kEpiWarp0 + 8) + 2;      // converter warp 0..3 (trace slot)
+            (void)cw;
+            const int m = (warp & 3) * 32 + lane;
+            const uint32_t sw = (uint32_t)m & 7u;
+            const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_TMEM_BASE;
             const float sa = pow2f(act_exp(p.amax_in));
             int stage = 0;
             uint32_t phase = 0;
@@ -635,13 +657,13 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const Seg sg = sched.get(e);
                 const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
+                    // (the slot's previous MMAs have retired: the TMA refilled this stage only after their commit)
                     TRACED_WAIT(0, &full[stage], phase);
-                    uint8_t* st = smem + stage * C::STAGE_BYTES;
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int m = pass * 64 + cw * 16 + (lane & 15);
-                        const uint32_t sw = (uint32_t)m & 7u;
-                        const uint8_t* src = st + sub * (kBlockM * kBoxC * 4) + m * 128;
+                    tc_fence_after();
+                    const uint8_t* row = smem + stage * C::STAGE_BYTES + m * 128;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {             // sub-tile = channels [32 half, 32 half + 32)
+                        const uint8_t* src = row + half * (kBlockM * kBoxC * 4);
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -657,17 +679,12 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                             t = __floats2half2_rn(a0 - h0, a1 - h1); lo[2 * c] = *reinterpret_cast<uint32_t*>(&t);
                             t = __floats2half2_rn(a2 - h2, a3 - h3); lo[2 * c + 1] = *reinterpret_cast<uint32_t*>(&t);
                         }
-                        __syncwarp();                                  // both lanes of every row have read it
-                        uint8_t* dh = st + m * 128;
-                        uint8_t* dl = st + C::OFF_ALO + m * 128;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8) of the K block
-                            const uint32_t off = (((uint32_t)(4 * sub + jj)) ^ sw) << 4;
-                            *reinterpret_cast<uint4*>(dh + off) = make_uint4(hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3]);
-                            *reinterpret_cast<uint4*>(dl + off) = make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
-                        }
+                        const uint32_t slot = a_lane + stage * C::A_TMEM_COLS + half * 16;
+                        tmem_st16(slot, hi);
+                        tmem_st16(slot + 32, lo);
                     }
-                    fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
                     mbar_arrive(&cvt[stage]);
                     if (++stage == C::STAGES) {
                         stage = 0;
@@ -722,7 +739,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     } else {
         // ===================== epilogue (warpgroups 1-2) =====================
         // 3xFP16: these warps hold a 64-column accumulator row AND the prefetched residual row in registers
-        if constexpr (F16) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+        if constexpr (F16) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int q = (warp - kEpiWarp0) & 3;              // TMEM lane quarter of this warp
         const int grp = (warp - kEpiWarp0) >> 2;           // column half of the tile this warp owns
         constexpr int HN = BN / 2;                         // columns per thread
@@ -804,7 +821,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 cbuf ^= 1;
                 if (cbuf == 0) cphase ^= 1;
             }
-            if (SPLIT) {                                     // + the cross terms of the whole tile
+            if (SPLIT && !ATMEM) {                           // + the cross terms of the whole tile
 #pragma unroll
                 for (int c = 0; c < HN / 16; ++c) {
                     float v[16];
