@@ -39,6 +39,15 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch from the committed ncu captures (profiles/r01_traffic.json); bench.py cannot run ncu itself."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
+
+
 def make_inputs(pairs, seed):
     g = torch.Generator().manual_seed(seed)
     im_data = torch.rand(pairs, 2, 3, H, W, generator=g) * 256.0 - 128.0     # mean-subtracted-image-like
@@ -357,7 +366,10 @@ def run_b200(args):
         kind_peak = _tf if args.passes == 16 else _tf / 2.0
         roofline = {"kernel": "conv_igemm (tcgen05 kind::%s implicit GEMM, %d launches/step)" % (kind, n_conv),
                     "bound": "tensor", "achieved": tf_useful, "peak": _tf, "unit": "TFLOP/s", "frac": tf_useful / _tf,
-                    "traffic": None, "peak_source": peak_src + " (cuBLAS bf16 sustained = the kind::f16 peak; kind::tf32 peaks at half of it)",
+                    "traffic": ncu_traffic().get("conv_igemm", {}).get("dram_bytes_per_launch") if args.passes == 16 else None,
+                    "traffic_note": "dram__bytes_read + write per launch, mean over the step's conv launches, ncu (cold cache, "
+                                    "serialised: every layer re-reads its input from DRAM); profiles/r01_traffic.json",
+                    "peak_source": peak_src + " (cuBLAS bf16 sustained = the kind::f16 peak; kind::tf32 peaks at half of it)",
                     "algorithmic_flops_per_launch": conv_flops / n_conv, "avg_launch_ms": conv_ms / n_conv,
                     "conv_ms_per_step": conv_ms,
                     "issued_tensor_tflops": tf_useful * mma_per_flop,
@@ -368,7 +380,9 @@ def run_b200(args):
         ps = ops_bench["psroi_fwd"]
         roofline_psroi = {"kernel": "psroi_fwd_sat<7> (+ psroi_prep) via d2t_psroi_forward", "bound": "hbm",
                           "achieved": ps["gbs"], "peak": hbm_gbs, "unit": "GB/s", "frac": ps["frac_hbm"],
-                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ps["algorithmic_bytes"],
+                          "traffic": ncu_traffic().get("psroi_fwd_sat", {}).get("dram_bytes_per_launch"),
+                          "traffic_note": "ncu: the features cross HBM once; the 23.5 MB of outputs stay in L2 within the capture",
+                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ps["algorithmic_bytes"],
                           "avg_launch_ms": ps["ms"]}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
