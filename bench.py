@@ -175,6 +175,23 @@ def op_microbench(flush, hbm_gbs):
         out[name] = {"batch": Bc, "ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6,
                      "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_useful": flops / ms / 1e9,
                      "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
+    # detection decode + per-class NMS after the network (test_net.py:232-301), 4 frames x 30 classes
+    from d2t_b200 import detect
+    g = torch.Generator().manual_seed(50)
+    L_, B_, R_, C_ = 2, 2, 300, 31
+    xy = torch.rand(L_, B_, R_, 2, generator=g) * torch.tensor([800.0, 480.0])
+    wh = 40 + torch.rand(L_, B_, R_, 2, generator=g) * 200
+    d_rois = torch.cat([torch.zeros(L_, B_, R_, 1), xy, (xy + wh).clamp(max=599.0)], -1).cuda()
+    d_prob = torch.softmax(torch.randn(L_, B_, R_, C_, generator=g) * 3.0, -1).cuda()
+    d_pred = torch.randn(L_, B_, R_, 4, generator=g).cuda()
+    d_info = torch.tensor([600.0, 1000.0, 1.0]).view(1, 1, 3).expand(B_, L_, 3).contiguous().cuda()
+    ms_b = time_kernel(lambda: detect.per_class_detections(d_rois, d_prob, d_pred, d_info, thresh=0.05), 10, flush)
+    t0 = time.time()
+    common.detect_reference_loop(d_rois, d_prob, d_pred, d_info, 0.05, 0.3, 0)
+    torch.cuda.synchronize()
+    out["detect_postproc_4frames_x30classes"] = {"ms_batched_device": ms_b, "ms_per_class_loop_wall": (time.time() - t0) * 1e3,
+                                                 "note": "batched = one sort + gather + d2t_nms_batched over the (frame, class) axis; "
+                                                         "loop = the reference's class-by-class nms with a host round trip each"}
     for n in (6000, 12000):
         dets = torch.from_numpy(np.stack([common.make_dets(n, seed=22 + i) for i in range(4)])).cuda()
         ms = time_kernel(lambda: ops.nms_batched(dets, 0.7, max_keep=300 if n == 6000 else 2000), 10, flush)

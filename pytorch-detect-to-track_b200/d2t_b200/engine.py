@@ -191,3 +191,14 @@ class D2TEngine(object):
                 im_data.new_zeros(1))
 
     __call__ = forward
+
+    @torch.no_grad()
+    def detect(self, im_data, im_info, thresh=0.0, nms_thresh=None):
+        """forward + the reference's post-processing (test_net.py:232-301) for every frame and class in one batched
+        pass: returns (forward outputs, d2t_b200.detect.Detections)."""
+        from model.utils.config import cfg
+        from . import detect as det
+        out = self.forward(im_data, im_info)
+        nms_t = cfg.TEST.NMS if nms_thresh is None else nms_thresh
+        return out, det.per_class_detections(out[0], out[1], out[2], im_info, thresh, nms_t, class_agnostic=(self.n_reg == 1),
+                                             stds=cfg.TRAIN.BBOX_NORMALIZE_STDS, means=cfg.TRAIN.BBOX_NORMALIZE_MEANS)
