@@ -225,6 +225,11 @@ d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in, 
  * the plan's input tensor (required for passes = 16), amax_out to its NHWC output (optional: the
  * epilogue folds max |out| into it).  Works for stem and correlation plans too (amax_out). */
 int d2t_conv_plan_set_amax(d2t_conv_plan* plan, const float* amax_in, float* amax_out);
+/* Stream-K scratch.  By default the plans of a device share one scratch (partial tiles + flags), which is why they must
+ * not run concurrently.  A caller that runs several chains of plans on different streams gives each chain its own
+ * zero-initialised device buffer of d2t_conv_scratch_bytes() bytes. */
+size_t d2t_conv_scratch_bytes(void);
+int d2t_conv_plan_set_scratch(d2t_conv_plan* plan, void* scratch, size_t bytes);
 void d2t_conv_plan_destroy(d2t_conv_plan* plan);
 /* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid*10 + pair_mode} */
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);

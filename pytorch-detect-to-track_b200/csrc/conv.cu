@@ -1490,6 +1490,18 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     return pl;
 }
 
+extern "C" size_t d2t_conv_scratch_bytes(void) {
+    return (size_t)sm_count() * kBlockM * 128 * sizeof(float) + (size_t)sm_count() * sizeof(int);
+}
+
+extern "C" int d2t_conv_plan_set_scratch(d2t_conv_plan* pl, void* scratch, size_t bytes) {
+    D2T_REQUIRE(pl && scratch && ((uintptr_t)scratch & 15) == 0 && bytes >= d2t_conv_scratch_bytes(),
+                "d2t_conv_plan_set_scratch: need a 16-byte aligned, zero-initialised buffer of d2t_conv_scratch_bytes()");
+    pl->args.sk_scratch = reinterpret_cast<float*>(scratch);
+    pl->args.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (size_t)sm_count() * kBlockM * 128 * sizeof(float));
+    return 1;
+}
+
 extern "C" int d2t_conv_plan_set_amax(d2t_conv_plan* pl, const float* amax_in, float* amax_out) {
     D2T_REQUIRE(pl, "d2t_conv_plan_set_amax: null plan");
     pl->args.amax_in = amax_in;

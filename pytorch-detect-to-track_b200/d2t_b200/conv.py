@@ -139,6 +139,12 @@ class _Planned(object):
     plan = None
     zero_amax = None      # the output's amax scalar when this layer owns zeroing it (stand-alone use)
 
+    def set_scratch(self, scratch):
+        """give this plan a private stream-K scratch (uint8 CUDA tensor of d2t_conv_scratch_bytes(), zero-initialised)
+        so that its chain may run concurrently with other chains on another stream"""
+        check(lib().d2t_conv_plan_set_scratch(self.plan, scratch.data_ptr(), scratch.numel()), "d2t_conv_plan_set_scratch")
+        self._scratch = scratch
+
     def _bind_amax(self, x, out):
         """attach the input's / output's amax scalars; outside an engine arena the layer zeroes its output's before
         each run (inside one, several producers may share an output buffer and the engine zeroes all at once)"""

@@ -32,11 +32,16 @@ def _fold_bn(bn):
 
 
 class D2TEngine(object):
-    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False):
+    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=False):
         dev = next(net.parameters()).device
         self.amax = dc.AmaxArena(1024, dev)       # every activation tensor's running max |x|, zeroed once per forward
         with self.amax:
             self._build(net, pairs, height, width, passes, cfg_key, keep_features)
+        if private_scratch:    # this engine's conv chain may then overlap another engine's on a different stream
+            from ._lib import lib
+            self.scratch = torch.zeros(lib().d2t_conv_scratch_bytes(), dtype=torch.uint8, device=dev)
+            for layer in [self.stem, self.trk_layer] + self.layers + self.corr_layers:
+                layer.set_scratch(self.scratch)
 
     def _build(self, net, pairs, height, width, passes, cfg_key, keep_features):
         from model.utils.config import cfg

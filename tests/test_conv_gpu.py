@@ -210,3 +210,32 @@ def test_cta_pair_mode_matches(monkeypatch):
         assert float((o[0] - want).abs().max() / want.abs().max()) < 1e-5
     assert float((outs[0][0] - outs[1][0]).abs().max() / want.abs().max()) < 2e-6
     assert torch.equal(outs[1][1].permute(0, 3, 1, 2), outs[1][0])
+
+
+def test_two_engines_on_two_streams_with_private_scratch():
+    """Two conv chains may overlap on different streams only with their own stream-K scratch (partial tiles + flags):
+    results must equal the sequential runs (sharing the device-wide scratch would deadlock a finisher on a clobbered flag)."""
+    from model.faster_rcnn.resnet import resnet
+    from d2t_b200.engine import D2TEngine
+    torch.manual_seed(3)
+    net = resnet(tuple(range(31)), 50, class_agnostic=True).create_architecture().cuda().eval()
+    H, W = 160, 224
+    g = torch.Generator().manual_seed(2)
+    ims = [(torch.rand(1, 2, 3, H, W, generator=g) * 256 - 128).cuda() for _ in range(2)]
+    info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(1, 2, 3).contiguous().cuda()
+    engines = [D2TEngine(net, 1, H, W, private_scratch=True) for _ in range(2)]
+    want = [[t.clone() for t in e(im, info)[:4]] for e, im in zip(engines, ims)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):
+        outs = []
+        for e, im, st in zip(engines, ims, streams):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                outs.append([t.clone() for t in e(im, info)[:4]])
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for o, w_ in zip(outs, want):
+            for a, b in zip(o, w_):
+                assert torch.equal(a, b)
