@@ -433,6 +433,87 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Secondary number: one data-parallel TRAINING step per iteration -- forward in training mode
+    (target layers, five losses), backward through the PSRoI / correlation backward kernels, the gradient all-reduce over
+    NCCL (the path's one collective) and the SGD update -- on 2 frame-pairs per GPU.  The trunk convolutions of this
+    mode still run through torch.nn (cuDNN fp32, TF32 off): the tcgen05 engine has no dgrad / wgrad yet, which is why this
+    is not the headline metric."""
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch.distributed as dist
+    import common
+    from d2t_b200 import ops, parallel
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the d2t_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    net = build_net(101).cuda()
+    net.train()
+    pairs = PAIRS_PER_GPU
+    g = torch.Generator().manual_seed(1 + rank)
+    im = (torch.rand(pairs, 2, 3, H, W, generator=g) * 2.0 - 1.0).cuda()
+    info = torch.tensor([float(H), float(W), 1.0]).view(1, 1, 3).expand(pairs, 2, 3).contiguous().cuda()
+    gt = torch.from_numpy(common.make_gt_boxes(pairs, 30, seed=2 + rank, height=H, width=W)).cuda()
+    nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-7, momentum=0.9)
+    n_grad = sum(p.numel() for p in params)
+
+    def step():
+        out = net(im, info, gt, nb)
+        loss = out[4].mean() + out[5].mean() + out[6].mean() + out[7].mean() + out[9].mean()    # trainval_net.py:367-368
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        nbk = parallel.allreduce_gradients(params)
+        opt.step()
+        return loss, nbk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss, nbk = step()
+    barrier()
+    launches0 = ops.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss, nbk = step()
+    b.record()
+    barrier()
+    ms = float(parallel.max_over_ranks(torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64))[0]) / args.steps
+    if rank == 0:
+        line = {"metric": "training frame-pairs/sec (Res-101 D&T, 600px; fwd + bwd + gradient all-reduce + SGD)",
+                "value": parallel.throughput(pairs, ms, world), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic", "mode": "train",
+                "config": {"workload": "Res-101 D&T training step, 600x1000 frame-pairs, 128 RoIs/frame (BASELINE.json configs[2] shape)",
+                           "pairs_per_gpu": pairs, "global_pairs": world * pairs,
+                           "parallelism": "dp%d, one collective: mean all-reduce of %d trainable fp32 gradients in %d buckets (NCCL)" % (world, n_grad, nbk),
+                           "convs": "torch.nn / cuDNN fp32 (TF32 off); PSRoI, correlation, NMS, proposal step: d2t_b200 kernels (forward and backward)"},
+                "loss_finite": bool(torch.isfinite(loss)), "gpu_launches": ops.LAUNCHES - launches0}
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -444,6 +525,8 @@ def main():
                     help="16 = fp32-accurate fp16-split convolutions (3xFP16, the parity mode, default); "
                          "3 = fp32-accurate 3xTF32; 1 = single-pass TF32")
     ap.add_argument("--ops-only", action="store_true", help="only the per-op microbench (configs[3], [4]); for ncu")
+    ap.add_argument("--train", action="store_true",
+                    help="secondary number: the data-parallel training step (fwd + bwd + NCCL gradient all-reduce + SGD)")
     args = ap.parse_args()
     if args.ops_only:
         torch.cuda.set_device(0)
@@ -451,6 +534,8 @@ def main():
         print(json.dumps({"ops": op_microbench(flush, peaks()[0])}), flush=True)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_b200(args)
 
