@@ -131,6 +131,10 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
  * Part 2 -- stream-ordered surface used by the Python host layer
  * ==================================================================================== */
 
+/* Opt-in (environment D2T_NMS_PREFIX=1): d2t_nms_batched with max_keep > 0 first decides a prefix of the (sorted) lists --
+ * greedy NMS never looks ahead -- and runs the full pass only for the lists that did not reach max_keep inside it.
+ * Returns the prefix length that would be used (0: no prefix pass). */
+int d2t_nms_prefix(int N, int max_keep);
 /* ---- NMS: B independent, caller-sorted box lists in one launch pair ----
  * boxes   [B, N, box_dim] fp32 (x1,y1,x2,y2,...), n_valid [B] int32 or NULL (= N each)
  * keep    [B, keep_stride] int32, num_keep [B] int32; at most max_keep (<= keep_stride)

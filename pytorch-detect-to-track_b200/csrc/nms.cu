@@ -23,6 +23,8 @@
 //     rows of the chunk are then OR-ed into the shared-memory `removed` bitmap by the whole CTA
 //     with every load in flight at once.  Early exit once max_keep boxes are kept.
 //   No cudaMalloc, no host round trip, stream-ordered.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace d2t {
@@ -51,44 +53,53 @@ __device__ __forceinline__ float4 load_box(const float* p) {
     return make_float4(p[0], p[1], p[2], p[3]);
 }
 
-// grid (cb, cb, B); blocks below the diagonal exit.
+// grid (G, B): a block walks the 64x64 tiles t = r * cb + c of its image with stride G and skips the ones below the
+// diagonal.  `limit` (a multiple of 64, or >= N) restricts the problem to the first `limit` boxes of every list -- greedy
+// NMS on a sorted list decides a prefix without looking past it -- `skip_cb` skips the tiles an earlier prefix pass
+// already wrote, and images whose `done` flag is set leave at once (see d2t_nms_batched).
 __global__ void __launch_bounds__(64)
 nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N, int box_dim, int cb,
-         float thresh, u64* __restrict__ mask, u64* __restrict__ diag) {
-    const int r = blockIdx.y, c = blockIdx.x, img = blockIdx.z;
-    if (c < r) return;
-    const int n = n_valid ? min(n_valid[img], N) : N;
-    if (r * 64 >= n || c * 64 >= n) return;
+         float thresh, u64* __restrict__ mask, u64* __restrict__ diag, int limit, int skip_cb,
+         const int* __restrict__ done) {
+    const int img = blockIdx.y;
+    if (done && done[img]) return;
+    const int n = min(n_valid ? min(n_valid[img], N) : N, limit);
+    const int nb = (n + 63) >> 6;                     // tiles per side that hold boxes
     const float* bx = boxes + (size_t)img * N * box_dim;
     const int tid = threadIdx.x;
     const bool fast = thresh >= 0.f;
-
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
-    const int col_size = min(n - c * 64, 64), row_size = min(n - r * 64, 64);
-    if (tid < col_size) {
-        float4 b = load_box(bx + (size_t)(c * 64 + tid) * box_dim);
-        cbox[tid] = b;
-        carea[tid] = box_area(b);
-    }
-    __syncthreads();
-    if (tid >= row_size) return;
-    const int row = r * 64 + tid;
-    const float4 a = (r == c) ? cbox[tid] : load_box(bx + (size_t)row * box_dim);
-    const float Sa = (r == c) ? carea[tid] : box_area(a);
-    u64 bits = 0;
-    if (r == c) {
-        for (int j = 0; j < col_size; ++j) {
-            if (j == tid) continue;
-            bool s = (j > tid) ? iou_gt(a, Sa, cbox[j], thresh, fast) : iou_gt(cbox[j], carea[j], a, thresh, fast);
-            if (s) bits |= 1ull << j;
+    for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
+        const int r = t / nb, c = t - r * nb;
+        if (c < r || (r < skip_cb && c < skip_cb)) continue;
+        const int col_size = min(n - c * 64, 64), row_size = min(n - r * 64, 64);
+        __syncthreads();                               // the previous tile's column boxes are no longer read
+        if (tid < col_size) {
+            float4 b = load_box(bx + (size_t)(c * 64 + tid) * box_dim);
+            cbox[tid] = b;
+            carea[tid] = box_area(b);
         }
-        diag[(size_t)img * N + row] = bits;
-    } else {
+        __syncthreads();
+        if (tid < row_size) {
+            const int row = r * 64 + tid;
+            const float4 a = (r == c) ? cbox[tid] : load_box(bx + (size_t)row * box_dim);
+            const float Sa = (r == c) ? carea[tid] : box_area(a);
+            u64 bits = 0;
+            if (r == c) {
+                for (int j = 0; j < col_size; ++j) {
+                    if (j == tid) continue;
+                    bool sp = (j > tid) ? iou_gt(a, Sa, cbox[j], thresh, fast) : iou_gt(cbox[j], carea[j], a, thresh, fast);
+                    if (sp) bits |= 1ull << j;
+                }
+                diag[(size_t)img * N + row] = bits;
+            } else {
 #pragma unroll 4
-        for (int j = 0; j < col_size; ++j)
-            if (iou_gt(a, Sa, cbox[j], thresh, fast)) bits |= 1ull << j;
-        mask[((size_t)img * N + row) * cb + c] = bits;
+                for (int j = 0; j < col_size; ++j)
+                    if (iou_gt(a, Sa, cbox[j], thresh, fast)) bits |= 1ull << j;
+                mask[((size_t)img * N + row) * cb + c] = bits;
+            }
+        }
     }
 }
 
@@ -96,12 +107,15 @@ constexpr int kSweepThreads = 512;
 
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep(const u64* __restrict__ mask, const u64* __restrict__ diag, const int* __restrict__ n_valid, int N,
-          int cb, int max_keep, int* __restrict__ keep, int keep_stride, int* __restrict__ num_keep) {
+          int cb, int max_keep, int* __restrict__ keep, int keep_stride, int* __restrict__ num_keep, int limit,
+          int* __restrict__ done, int set_done) {
     extern __shared__ u64 removed[];  // [cb]
     __shared__ int s_list[64];
     __shared__ int s_nk, s_count;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = n_valid ? min(n_valid[img], N) : N;
+    if (done && !set_done && done[img]) return;       // the prefix pass already produced this image's answer
+    const int n_full = n_valid ? min(n_valid[img], N) : N;
+    const int n = min(n_full, limit);
     const int nchunks = (n + 63) >> 6;
     const u64* dg = diag + (size_t)img * N;
     const u64* mk = mask + (size_t)img * N * cb;
@@ -161,7 +175,11 @@ nms_sweep(const u64* __restrict__ mask, const u64* __restrict__ diag, const int*
         }
         __syncthreads();
     }
-    if (tid == 0) num_keep[img] = s_count;
+    if (tid == 0) {
+        num_keep[img] = s_count;
+        // prefix pass: final iff it already holds max_keep boxes or the prefix was the whole list
+        if (set_done) done[img] = (s_count >= cap || limit >= n_full) ? 1 : 0;
+    }
 }
 
 }  // namespace
@@ -171,7 +189,20 @@ using namespace d2t;
 
 extern "C" size_t d2t_nms_workspace_bytes(int B, int N) {
     size_t cb = ((size_t)N + 63) / 64;
-    return align_up((size_t)B * N * cb * 8 + (size_t)B * N * 8, 256);
+    return align_up((size_t)B * N * cb * 8 + (size_t)B * N * 8 + (size_t)B * 4, 256);
+}
+
+// boxes decided by the prefix pass of d2t_nms_batched (0: no prefix pass); a multiple of 64
+extern "C" int d2t_nms_prefix(int N, int max_keep) {
+    if (max_keep <= 0) return 0;
+    // Opt-in (D2T_NMS_PREFIX=1).  Measured on B200: 12.5 instead of 36.8 us/image at N = 6000 / keep 300 when the survivors sit
+    // in the prefix (spread boxes), +17 % when they do not and both passes run (heavily clustered boxes) -- and the
+    // synthetic random-weight model of bench.py is of the second kind (5.95 vs 5.92 ms/step), so it is off by default.
+    const char* env = getenv("D2T_NMS_PREFIX");
+    if (!env || atoi(env) == 0) return 0;
+    int p = ((4 * max_keep + 63) / 64) * 64;
+    if (p < 1024) p = 1024;
+    return 2 * p <= N ? p : 0;
 }
 
 extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int box_dim, float thresh,
@@ -192,14 +223,34 @@ extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, in
     D2T_REQUIRE((size_t)cb * 8 <= 200 * 1024, "d2t_nms_batched: N too large for the sweep bitmap");
     u64* mask = reinterpret_cast<u64*>(workspace);
     u64* diag = mask + (size_t)B * N * cb;
-    nms_mask<<<dim3(cb, cb, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask, diag);
-    D2T_CHECK_LAUNCH("nms_mask");
+    int* done = reinterpret_cast<int*>(diag + (size_t)B * N);
     size_t smem = (size_t)cb * 8;
     if (smem > 40 * 1024) {
         static SmemAttrOnce once;
         if (!once.ensure(nms_sweep, 200 * 1024, "nms_sweep smem attr")) return 0;
     }
-    nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep);
+    const int gx_cap = sm_count() * 8;
+    // Keeping only the first max_keep survivors (the proposal step: 300 of 6000) may not need the whole list: an optional
+    // first pass (d2t_nms_prefix) decides the prefix of 4 * max_keep boxes (exact: greedy NMS never looks ahead) and marks
+    // the images it finished; the full pass then runs only for the others and reuses the prefix tiles.
+    const int prefix = d2t_nms_prefix(N, max_keep);
+    int skip_cb = 0;
+    if (prefix > 0) {
+        const int pcb = prefix / 64;
+        nms_mask<<<dim3(pcb * pcb < gx_cap ? pcb * pcb : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask,
+                                                                                       diag, prefix, 0, nullptr);
+        D2T_CHECK_LAUNCH("nms_mask (prefix)");
+        nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep, prefix,
+                                                      done, 1);
+        D2T_CHECK_LAUNCH("nms_sweep (prefix)");
+        skip_cb = pcb;
+    }
+    const int* done_c = prefix > 0 ? done : nullptr;
+    nms_mask<<<dim3(cb * cb < gx_cap ? cb * cb : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask, diag,
+                                                                             0x7fffffff, skip_cb, done_c);
+    D2T_CHECK_LAUNCH("nms_mask");
+    nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep, 0x7fffffff,
+                                                  prefix > 0 ? done : nullptr, 0);
     D2T_CHECK_LAUNCH("nms_sweep");
     return 1;
 }

@@ -191,6 +191,35 @@ def test_nms_batched_ragged_and_capped(oracle):
         np.testing.assert_array_equal(npy(keep[b, : len(want)]), want)
 
 
+def test_nms_prefix_pass_and_fallback(oracle, monkeypatch):
+    """max_keep > 0 on long lists with D2T_NMS_PREFIX=1: d2t_nms_batched first decides a prefix (4 * max_keep boxes); lists
+    that reach max_keep inside it are final, the others take the full pass.  One batch mixes short / empty / long lists."""
+    from d2t_b200._lib import lib
+    assert lib().d2t_nms_prefix(6000, 300) == 0           # opt-in
+    monkeypatch.setenv("D2T_NMS_PREFIX", "1")
+    B, N, K = 5, 6000, 300
+    assert lib().d2t_nms_prefix(N, K) == 1216 and lib().d2t_nms_prefix(N, 0) == 0 and lib().d2t_nms_prefix(2000, K) == 0
+    dets = np.stack([common.make_dets(N, seed=300), common.make_clustered_dets(N, seed=301), common.make_dets(N, seed=302),
+                     common.make_clustered_dets(N, seed=303), common.make_clustered_dets(N, seed=304)])
+    n_valid = np.array([6000, 6000, 1000, 5000, 0], np.int32)
+    keep, num = ops.nms_batched(cu(dets), 0.7, max_keep=K, n_valid=cu(n_valid))
+    keep, num = npy(keep), npy(num)
+    in_prefix = []
+    for b in range(B):
+        full = oracle.nms(dets[b, : n_valid[b]], 0.7)
+        want = full[:K]
+        assert num[b] == len(want), (b, num[b], len(want))
+        np.testing.assert_array_equal(keep[b, : num[b]], want)
+        in_prefix.append(len(want) == K and want[-1] < 1216)
+    assert in_prefix[0]                                # (spread boxes: final after the prefix pass)
+    # a threshold that suppresses almost everything: fewer than max_keep survivors inside the prefix, so the full pass
+    # runs and must find the late ones
+    keep, num = ops.nms_batched(cu(dets[1:2]), 0.05, max_keep=K)
+    want = oracle.nms(dets[1], 0.05)[:K]
+    assert int(num[0]) == len(want) and (len(want) < K or want[-1] >= 1216)
+    np.testing.assert_array_equal(npy(keep)[0, : len(want)], want)
+
+
 def test_nms_degenerate_boxes(oracle):
     rng = np.random.RandomState(9)
     dets = common.make_dets(200, seed=9)
