@@ -70,9 +70,15 @@ nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N
     const bool fast = thresh >= 0.f;
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
-    for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
-        const int r = t / nb, c = t - r * nb;
-        if (c < r || (r < skip_cb && c < skip_cb)) continue;
+    // upper-triangle tiles only, row-major: row r starts at t0(r) = r * nb - r (r - 1) / 2
+    const int ntri = nb * (nb + 1) / 2;
+    for (int t = blockIdx.x; t < ntri; t += gridDim.x) {
+        int r = (int)(((float)(2 * nb + 1) - sqrtf((float)(2 * nb + 1) * (float)(2 * nb + 1) - 8.f * (float)t)) * 0.5f);
+        r = max(0, min(r, nb - 1));
+        while (r > 0 && r * nb - r * (r - 1) / 2 > t) --r;                     // (float rounding)
+        while ((r + 1) * nb - (r + 1) * r / 2 <= t) ++r;
+        const int c = r + (t - (r * nb - r * (r - 1) / 2));
+        if (r < skip_cb && c < skip_cb) continue;
         const int col_size = min(n - c * 64, 64), row_size = min(n - r * 64, 64);
         __syncthreads();                               // the previous tile's column boxes are no longer read
         if (tid < col_size) {
@@ -229,7 +235,7 @@ extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, in
         static SmemAttrOnce once;
         if (!once.ensure(nms_sweep, 200 * 1024, "nms_sweep smem attr")) return 0;
     }
-    const int gx_cap = sm_count() * 8;
+    const int gx_cap = sm_count() * 32;   // 64-thread blocks: 32 resident per SM
     // Keeping only the first max_keep survivors (the proposal step: 300 of 6000) may not need the whole list: an optional
     // first pass (d2t_nms_prefix) decides the prefix of 4 * max_keep boxes (exact: greedy NMS never looks ahead) and marks
     // the images it finished; the full pass then runs only for the others and reuses the prefix tiles.
@@ -237,7 +243,7 @@ extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, in
     int skip_cb = 0;
     if (prefix > 0) {
         const int pcb = prefix / 64;
-        nms_mask<<<dim3(pcb * pcb < gx_cap ? pcb * pcb : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask,
+        nms_mask<<<dim3(pcb * (pcb + 1) / 2 < gx_cap ? pcb * (pcb + 1) / 2 : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask,
                                                                                        diag, prefix, 0, nullptr);
         D2T_CHECK_LAUNCH("nms_mask (prefix)");
         nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep, prefix,
@@ -246,7 +252,7 @@ extern "C" int d2t_nms_batched(const float* boxes, const int* n_valid, int B, in
         skip_cb = pcb;
     }
     const int* done_c = prefix > 0 ? done : nullptr;
-    nms_mask<<<dim3(cb * cb < gx_cap ? cb * cb : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask, diag,
+    nms_mask<<<dim3(cb * (cb + 1) / 2 < gx_cap ? cb * (cb + 1) / 2 : gx_cap, B), 64, 0, stream>>>(boxes, n_valid, N, box_dim, cb, thresh, mask, diag,
                                                                              0x7fffffff, skip_cb, done_c);
     D2T_CHECK_LAUNCH("nms_mask");
     nms_sweep<<<B, kSweepThreads, smem, stream>>>(mask, diag, n_valid, N, cb, max_keep, keep, keep_stride, num_keep, 0x7fffffff,
