@@ -869,6 +869,14 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 #pragma unroll
                     for (int j = 0; j < HN; ++j) acc[j] += __ldcg(src + j * kBlockM);
                 }
+                // the consumer clears the flags it used (each publisher has exactly one finisher), so a launch never
+                // finds its own epoch left over from an earlier launch with the same argument: a captured CUDA graph
+                // replays the same epochs.  The next writer of these flags starts after this grid has completed.
+                if (c_first < unit_id) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");        // every partial of this tile has been read
+                    if (m == 0 && grp == 0)
+                        for (int cc = c_first; cc < unit_id; ++cc) p.sk_flags[cc * CS + (int)crank] = 0;
+                }
             }
             if constexpr (CORR) {
                 // tile row m = position (yl, xl) of the 8x16 tile; column n = halo (rl, cl) of this 4x32 chunk
@@ -1194,15 +1202,25 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
+    // D2T_CONV_PDL=0 (experiments): plain stream order -- the next launch of a chain is not resident (holding an SM at
+    // griddepcontrol.wait) while another stream's kernel could use that SM
+    static const bool pdl = [] { const char* e = getenv("D2T_CONV_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = PAIR ? 2 : 1;
+    cfg.numAttrs = na;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
     D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
                                    pl->tmR, args),

@@ -54,12 +54,13 @@ struct PsroiWs {
     int* chunk;            // [Rp/32] min | max << 16 of the valid image indices among rois [32k, 32k+32)
     unsigned short* bh;    // [PH][Rp] hstart | hend << 8   (transposed: one ph is contiguous over n)
     unsigned short* bw;    // [Rp][PW] wstart | wend << 8
+    unsigned int* bhb;     // [PH][Rp] hstart | hend << 8 | image << 16 (0xffff: none) -- bh and rb in one load
 };
 
 __host__ __device__ inline int psroi_rp(int R) { return (R + 31) / 32 * 32; }
 __host__ __device__ inline size_t psroi_ws_bytes(int R, int PH, int PW) {
     const size_t Rp = (size_t)psroi_rp(R);
-    return Rp * 4 + Rp / 32 * 4 + Rp * PH * 2 + Rp * PW * 2;
+    return Rp * 4 + Rp / 32 * 4 + Rp * PH * 2 + Rp * PW * 2 + Rp * PH * 4;
 }
 
 // One thread per roi: image index, the PH + PW integer windows (psroi_pooling_kernel.cu:31-61,
@@ -83,6 +84,7 @@ psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, in
         for (int p = 0; p < PH; ++p) {
             int2 w = psroi_window(ah, p, H);
             ws.bh[(size_t)p * Rp + n] = (unsigned short)(w.x | (w.y << 8));
+            ws.bhb[(size_t)p * Rp + n] = (unsigned)(w.x | (w.y << 8)) | ((unsigned)(b < 0 ? 0xffff : b) << 16);
         }
         for (int p = 0; p < PW; ++p) {
             int2 w = psroi_window(aw, p, W);
@@ -94,6 +96,8 @@ psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, in
         }
     }
     ws.rb[n] = b;
+    if (n >= R)
+        for (int p = 0; p < PH; ++p) ws.bhb[(size_t)p * Rp + n] = 0xffff0000u;
     int lo = b < 0 ? 0xffff : b, hi = b < 0 ? 0 : b;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -464,6 +468,358 @@ psroi_fwd_isat(const float* __restrict__ feat, int B, int C, int H, int W, int D
     if (!waited_for_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// ---- forward, planes of width <= 64: integer tables, ONE item per CTA, several CTAs per SM ----
+// Same arithmetic as psroi_fwd_isat (per-plane power-of-two fixed point, 2-D inclusive prefix sum in place in the TMA
+// buffer, exact integer window sums), different execution shape.  The two kernels above run one 1024-thread CTA per SM
+// and walk through load -> norm -> row scan -> column scan -> lookups with a block-wide barrier between phases: every
+// phase is latency-bound on its own (ncu / phase trace), so the SM idles through most of each.  Here a
+// CTA is THREADS wide, owns one 67 KB buffer and CTAS of them are resident per SM: while one CTA waits for its planes or
+// sits in a scan, the others' lookups use the issue slots, the shared-memory pipe and the store path -- the hardware
+// overlaps the phases of different items without any warp-role choreography, and the work granularity drops from
+// 1/148 to 1/(148 CTAS) of the device (420 items of BASELINE config 5 on 444 slots: one wave).
+// Lookups: the 32-roi chunks of the item's image form the range [c_lo, c_hi] (found once per item from the chunk
+// descriptors, all loads in flight together -- no dependent load per chunk); inside the range the per-lane image test
+// alone decides, so unsorted roi lists stay correct; the windows of a warp's next chunk are fetched while it works on
+// the current one.
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+constexpr int kMcMaxRows = 320;    // TROW: per-row |f| sums of one item (launcher: G * H <= kMcMaxRows)
+
+template <int G, int THREADS, int CTAS, bool LROI, bool TROW = false>
+__global__ void __launch_bounds__(THREADS, CTAS)
+psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, int D, int R, PsroiWs ws,
+                  float* __restrict__ top, int* __restrict__ mapping) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    __shared__ uint64_t bar;
+    __shared__ float l1w[NW][2];   // per warp: sum |f| over its rows of plane p0 / of plane p0 + 1
+    __shared__ int wp0s[NW];       // first plane of each warp's row block
+    __shared__ float scl[G], inv[G];
+    __shared__ int crange[2];      // chunk range [lo, hi] holding the rois of the item's image
+    __shared__ float stage_w[LROI ? NW * 16 * G : 1];   // LROI: per-warp [16 rois][G] output transposition area
+    __shared__ float rowsum[TROW ? kMcMaxRows : 1];     // TROW: sum |f| of every plane row of the item
+    const int HW = H * W, n_el = G * HW;
+    float* buf = reinterpret_cast<float*>(smem4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int items = B * D * G;
+    const int Rp = psroi_rp(R), nchunks = Rp >> 5;
+    const int per_roi = D * G * G;
+    // lane j = k*32 + lane of pass k works on (roi j / G, pw j % G); recomputed where needed (two integer ops) rather
+    // than held in 3 G registers: three CTAs per SM leave 56 registers per thread
+    auto nl_of = [&](int k) { return (k * 32 + lane) / G; };
+    auto pw_of = [&](int k) { return (k * 32 + lane) % G; };
+    // rows [r_begin, r_end) of the item's G*H plane rows belong to this warp: at most two planes (launcher: rw <= H)
+    const int rows = G * H;
+    const int rw = (rows + NW - 1) / NW;
+    const int r_begin = min(warp * rw, rows), r_end = min(rows, r_begin + rw);
+    const int p0 = min(r_begin / H, G - 1), r_split = min(r_end, (p0 + 1) * H);
+    if (lane == 0) wp0s[warp] = p0;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    uint32_t phase = 0;
+    bool waited_for_prep = false;
+
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
+        if (tid == 0) {
+            crange[0] = 0x3fffffff;          // (+ warp index must not overflow)
+            crange[1] = -1;
+        }
+        fence_proxy_async();           // my generic-proxy accesses to the buffer are ordered before the next bulk copy into it
+        __syncthreads();               // mbarrier initialised; previous item's lookups are done with the buffer and crange
+        const float* src = feat + ((size_t)b * C + (size_t)cg * G) * HW;
+        float* pl = buf + (int)(stage_issue(buf, src, n_el, &bar) - buf);
+        int* S = reinterpret_cast<int*>(pl);
+        if (!waited_for_prep) {        // windows / chunk descriptors come from psroi_prep (programmatic dependent launch)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited_for_prep = true;
+        }
+        {   // chunk range of image b, while the planes are in flight
+            int lo = 0x3fffffff, hi = -1;
+            for (int ck = tid; ck < nchunks; ck += THREADS) {
+                const int mm = __ldg(ws.chunk + ck);
+                if (b >= (mm & 0xffff) && b <= (mm >> 16)) {
+                    lo = min(lo, ck);
+                    hi = max(hi, ck);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0 && hi >= 0) {
+                atomicMin(&crange[0], lo);
+                atomicMax(&crange[1], hi);
+            }
+        }
+        if (warp == 0) mbar_wait(&bar, phase);   // one warp polls; the others sleep at the barrier
+        phase ^= 1;
+        __syncthreads();               // planes landed, head/tail scalar stores of stage_issue visible, crange complete
+        const int c_lo = crange[0], c_hi = crange[1];   // (read here: three barriers separate it from the next item's reset)
+        // TROW (odd W only: thread r walks row r, the row pitch W is odd, so a warp's 32 rows hit 32 different banks): one
+        // thread per plane row for the norm and for the quantise + row scan -- 5 instructions per ELEMENT of one thread
+        // instead of ~45 warp instructions per row for the shuffle scan (the kernel is issue-bound).
+        const bool trow = TROW && (W & 1);
+        // ---- (1) L1 norm of every plane -> per-plane power-of-two scale
+        if (trow) {
+            for (int r = tid; r < rows; r += THREADS) {
+                const float* row = pl + r * W;
+                float a = 0.f;
+#pragma unroll 9
+                for (int x = 0; x < W; ++x) a += fabsf(row[x]);
+                rowsum[r] = a;
+            }
+        } else {
+            float s0 = 0.f, s1 = 0.f;
+            for (int r = r_begin; r < r_end; ++r) {
+                const float* row = pl + r * W;
+                float a = 0.f;
+                if (2 * lane < W) a = fabsf(row[2 * lane]);
+                if (2 * lane + 1 < W) a += fabsf(row[2 * lane + 1]);
+                if (r < r_split) s0 += a; else s1 += a;
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                l1w[warp][0] = s0;
+                l1w[warp][1] = s1;
+            }
+        }
+        __syncthreads();
+        if (tid < G) {
+            float l1 = 0.f;
+            if (trow) {
+                for (int h = 0; h < H; ++h) l1 += rowsum[tid * H + h];      // fixed order: the scale is deterministic
+            } else {
+                for (int w = 0; w < NW; ++w) {
+                    const int wp0 = wp0s[w];
+                    l1 += (wp0 == tid ? l1w[w][0] : 0.f) + (wp0 + 1 == tid ? l1w[w][1] : 0.f);
+                }
+            }
+            // l1 < 2^(eb - 126) for the biased exponent eb of l1  =>  k = 30 - (eb - 126); powers of two built from bits
+            const int eb = (int)((__float_as_uint(l1) >> 23) & 0xffu);
+            int k = (eb > 0 && eb < 255) ? 156 - eb : 0;
+            k = k < -96 ? -96 : (k > 120 ? 120 : k);
+            scl[tid] = __uint_as_float((uint32_t)(127 + k) << 23);
+            inv[tid] = __uint_as_float((uint32_t)(127 - k) << 23);
+        }
+        __syncthreads();
+        // ---- (2) quantise + inclusive row scan, written back in place as int32
+        if (trow) {
+            for (int r = tid; r < rows; r += THREADS) {
+                const float sc = scl[r / H];
+                const float* row = pl + r * W;
+                int* irow = S + r * W;
+                int acc = 0;
+                for (int x0 = 0; x0 < W; x0 += 9) {          // 9 loads in flight, then 9 dependent adds + stores (in place)
+                    float v[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) v[j] = x0 + j < W ? row[x0 + j] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        acc += __float2int_rn(v[j] * sc);
+                        if (x0 + j < W) irow[x0 + j] = acc;
+                    }
+                }
+            }
+        } else {
+            const float sc0 = scl[p0], sc1 = scl[min(p0 + 1, G - 1)];
+            for (int r = r_begin; r < r_end; ++r) {
+                const float sc = r < r_split ? sc0 : sc1;
+                const float* row = pl + r * W;
+                const float va = 2 * lane < W ? row[2 * lane] : 0.f;
+                const float vb = 2 * lane + 1 < W ? row[2 * lane + 1] : 0.f;
+                const int qa = __float2int_rn(va * sc), qb = __float2int_rn(vb * sc);
+                const int sum2 = qa + qb;
+                int scan = sum2;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, scan, o);
+                    if (lane >= o) scan += t;
+                }
+                const int excl = scan - sum2;
+                int* irow = S + r * W;
+                if (2 * lane < W) irow[2 * lane] = excl + qa;
+                if (2 * lane + 1 < W) irow[2 * lane + 1] = excl + sum2;
+            }
+        }
+        __syncthreads();
+        // ---- (3) column scan: one thread per (plane, column)
+        for (int i = tid; i < G * W; i += THREADS) {
+            const int p = i / W;
+            int* col = S + p * HW + (i - p * W);
+            int acc = 0;
+#pragma unroll 19
+            for (int h = 0; h < H; ++h) {
+                acc += col[h * W];
+                col[h * W] = acc;
+            }
+        }
+        __syncthreads();
+        if constexpr (!LROI) {
+            // ---- (4) lookups: warp per 32-roi chunk of the image's range, lane j -> (roi j / G, pw j % G), G passes
+            const unsigned int* __restrict__ bhb = ws.bhb + (size_t)ph * Rp;
+            const int c0 = (ctop * G + ph) * G;
+            const int obase = ctop * (G * G) + ph * G;
+            int ck = c_lo + warp;
+            unsigned hbn[G], wbn[G];       // windows of the NEXT chunk, in flight while the current one is looked up
+            if (ck <= c_hi) {
+    #pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    hbn[k] = __ldg(bhb + ck * 32 + nl_of(k));
+                    wbn[k] = __ldg(ws.bw + (size_t)ck * 32 * G + k * 32 + lane);
+                }
+            }
+            for (; ck <= c_hi; ck += NW) {
+                unsigned hbv[G], wbv[G];
+    #pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    hbv[k] = hbn[k];
+                    wbv[k] = wbn[k];
+                }
+                const int cn = ck + NW;
+                if (cn <= c_hi) {
+    #pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        hbn[k] = __ldg(bhb + cn * 32 + nl_of(k));
+                        wbn[k] = __ldg(ws.bw + (size_t)cn * 32 * G + k * 32 + lane);
+                    }
+                }
+    #pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    if ((int)(hbv[k] >> 16) != b) continue;
+                    const int pw = pw_of(k);
+                    const int n = ck * 32 + nl_of(k);
+                    const int hs = hbv[k] & 0xff, he = (hbv[k] >> 8) & 0xff, wsx = wbv[k] & 0xff, we = wbv[k] >> 8;
+                    float o = 0.f;
+                    if (he > hs && we > wsx) {
+                        const int* P = S + pw * HW;
+                        const int r1 = (he - 1) * W, r0 = (hs - 1) * W;
+                        // the four corners, index -1 (first row / column of the plane) contributing 0: clamp the address,
+                        // mask the value -- straight-line code, four independent loads
+                        const int m0 = hs > 0 ? -1 : 0, n0 = wsx > 0 ? -1 : 0;
+                        const int a11 = P[r1 + we - 1];
+                        const int a01 = P[max(r0, 0) + we - 1] & m0;
+                        const int a10 = P[r1 + max(wsx - 1, 0)] & n0;
+                        const int a00 = P[max(r0, 0) + max(wsx - 1, 0)] & (m0 & n0);
+                        const int sum = (a11 - a01) - (a10 - a00);
+                        o = __fdividef(__int2float_rn(sum) * inv[pw], (float)((he - hs) * (we - wsx)));
+                    }
+                    const int idx = n * per_roi + obase + pw;
+                    top[idx] = o;
+                    if (mapping) mapping[idx] = c0 + pw;
+                }
+            }
+        } else {
+            // ---- (4') lookups, lane -> roi: the per-roi row arithmetic (window rows, masks, height) is done once per roi
+            // instead of once per (roi, pw), the G bins of a roi are looked up in turn, and the outputs are transposed
+            // through a per-warp staging area (16 rois at a time) so that the stores stay [roi][pw]-contiguous.
+            const unsigned int* __restrict__ bhb = ws.bhb + (size_t)ph * Rp;
+            const int c0 = (ctop * G + ph) * G;
+            const int obase = ctop * (G * G) + ph * G;
+            float* stg = stage_w + warp * (16 * G);
+            float invp[G];
+#pragma unroll
+            for (int pw = 0; pw < G; ++pw) invp[pw] = inv[pw];
+            // store side: lane j of round q writes element j = q*32 + lane of the [16][G] staging area
+            constexpr int NQ = (16 * G + 31) / 32;
+            int soff[NQ], srl[NQ];                  // output offset rl * per_roi + pw, source roi rl (-1: no element)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int j = q * 32 + lane, rl = j / G;
+                soff[q] = rl * per_roi + (j - rl * G);
+                srl[q] = j < 16 * G ? rl : -1;
+            }
+            int ck = c_lo + warp;
+            unsigned hbn = 0xffff0000u, wbn[G];      // the NEXT chunk's windows, in flight while this one is looked up
+            if (ck <= c_hi) {
+                hbn = __ldg(bhb + ck * 32 + lane);
+#pragma unroll
+                for (int pw = 0; pw < G; ++pw) wbn[pw] = __ldg(ws.bw + ((size_t)ck * 32 + lane) * G + pw);
+            }
+            for (; ck <= c_hi; ck += NW) {
+                const unsigned hb = hbn;
+                unsigned wbv[G];
+#pragma unroll
+                for (int pw = 0; pw < G; ++pw) wbv[pw] = wbn[pw];
+                const int cn = ck + NW;
+                if (cn <= c_hi) {
+                    hbn = __ldg(bhb + cn * 32 + lane);
+#pragma unroll
+                    for (int pw = 0; pw < G; ++pw) wbn[pw] = __ldg(ws.bw + ((size_t)cn * 32 + lane) * G + pw);
+                }
+                const bool mine = (int)(hb >> 16) == b;
+                const unsigned mine_mask = __ballot_sync(0xffffffffu, mine);
+                if (mine_mask == 0u) continue;
+                // Branch-free from here to the stores, so that the 4 G table reads of a roi are all in flight together
+                // (with a branch per bin they were issued bin after bin: the kernel is latency-bound, not issue-bound).
+                // Lanes whose roi belongs to another image / is padding work on an all-zero window; an EMPTY window
+                // (he == hs or we == ws, possibly 0) reads up to W + 1 cells BELOW the table -- static shared memory of
+                // this CTA (stage_w alone is > 3 KB), a legal address whose value is discarded by the select below.
+                const unsigned mm = mine ? 0xffffffffu : 0u;
+                const int hs = hb & mm & 0xff, he = ((hb & mm) >> 8) & 0xff, hgt = he - hs;
+                const int m0 = hs > 0 ? -1 : 0;
+                // shared-memory byte addresses of row he-1 / row max(hs-1, 0) of plane 0 (a corner = one add + one LDS)
+                uint32_t a1 = smem_u32(S) + (uint32_t)((he - 1) * W) * 4u;
+                uint32_t a0 = smem_u32(S) + (uint32_t)(max(hs - 1, 0) * W) * 4u;
+                const float fh = (float)hgt;
+                float o[G];
+#pragma unroll
+                for (int pw = 0; pw < G; ++pw) {
+                    const unsigned wb = wbv[pw] & mm;
+                    const int wsx = wb & 0xff, we = wb >> 8;
+                    const uint32_t c1 = (uint32_t)(we - 1) * 4u, cz = (uint32_t)max(wsx - 1, 0) * 4u;
+                    const int n0 = wsx > 0 ? -1 : 0;
+                    const int a11 = lds_s32(a1 + c1), a01 = lds_s32(a0 + c1);
+                    const int a10 = lds_s32(a1 + cz), a00 = lds_s32(a0 + cz);
+                    // columns ws-1 / row hs-1 "before the plane" contribute 0: mask the values
+                    const int sum = (a11 - (a10 & n0)) - ((a01 - (a00 & n0)) & m0);
+                    float rcp;                                // 1 / area, area an integer in [1, H*W]: one MUFU
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(fh * (float)(we - wsx)));
+                    const float v = __int2float_rn(sum) * invp[pw] * rcp;
+                    o[pw] = (hgt > 0 && we > wsx) ? v : 0.f;  // empty bin -> 0 (psroi_pooling_kernel.cu:63,76)
+                    a1 += (uint32_t)HW * 4u;
+                    a0 += (uint32_t)HW * 4u;
+                }
+                int ibase = ck * 32 * per_roi + obase;         // (launcher: num_rois * per_roi < 2^31)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if ((lane >> 4) == half) {
+#pragma unroll
+                        for (int pw = 0; pw < G; ++pw) stg[(lane & 15) * G + pw] = o[pw];
+                    }
+                    __syncwarp();
+                    const unsigned hm = (mine_mask >> (half * 16)) & 0xffffu;
+                    if (mapping) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            if (srl[q] >= 0 && ((hm >> srl[q]) & 1u)) {
+                                const int idx = ibase + soff[q];
+                                top[idx] = stg[q * 32 + lane];
+                                mapping[idx] = c0 + (q * 32 + lane) % G;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            if (srl[q] >= 0 && ((hm >> srl[q]) & 1u)) top[ibase + soff[q]] = stg[q * 32 + lane];
+                        }
+                    }
+                    __syncwarp();
+                    ibase += 16 * per_roi;
+                }
+            }
+        }
+    }
+    if (!waited_for_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- backward: the adjoint of the summed-area-table forward ----
 // d(out)/d(f[h][w]) is dv = top_diff / area on the window and 0 elsewhere, so the gradient plane is
 // the 2-D prefix sum of a difference array holding +dv, -dv, -dv, +dv at the window's four
@@ -649,6 +1005,7 @@ PsroiWs carve(void* workspace, int R, int PH, int PW) {
     ws.chunk = ws.rb + Rp;
     ws.bh = reinterpret_cast<unsigned short*>(ws.chunk + Rp / 32);
     ws.bw = ws.bh + Rp * PH;
+    ws.bhb = reinterpret_cast<unsigned int*>(ws.bw + Rp * PW);      // Rp is a multiple of 32: 4-byte aligned
     return ws;
 }
 
@@ -706,10 +1063,11 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
         // to 4.9 M, but the kernel is bound by its five barrier-separated phases (per item, cycles: load + L1 norm 3.8 k, row
         // scan 4.5 k, column scan 2.2 k, lookups 13.7 k) at 2.84 items per CTA, not by the gathers; the exactly-rounded fp64
         // kernel therefore stays the product path.
+        const char* int_env1 = getenv("D2T_PSROI_INT");
         const size_t buf_bytes = (((size_t)group * height * width + 4 + 3) & ~(size_t)3) * sizeof(float);
         const int nbuf = (int)(kMaxDynSmem / buf_bytes) >= 3 ? 3 : (int)(kMaxDynSmem / buf_bytes);
         if (width <= 64 && group * height <= 32 * 12 && nbuf >= 2 &&
-            (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31) && getenv("D2T_PSROI_INT")) {
+            (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31) && int_env1 && atoi(int_env1) == 1) {
             const int rw = (group * height + 31) / 32;
             auto kern = rw <= 3 ? psroi_fwd_isat<7, 3> : (rw <= 6 ? psroi_fwd_isat<7, 6> : (rw <= 9 ? psroi_fwd_isat<7, 9> : psroi_fwd_isat<7, 12>));
             static SmemAttrOnce once_i[4];
@@ -727,6 +1085,63 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
             D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bottom, batch, channels, height, width, out_dim,
                                            num_rois, ws, top, mapping, nbuf),
                         "psroi_fwd_isat launch");
+            return 1;
+        }
+        // D2T_PSROI_INT=2: the same integer tables, one item per 384-thread CTA, three CTAs per SM (psroi_fwd_isat_mc).
+        constexpr int kMcCtas = 3;
+        constexpr int kMcDefaultThreads = 256;
+        constexpr size_t kMcSmem = 70 * 1024;      // 3 x (70 KB + 4 KB static + 1 KB reserved) <= 227 KB per SM
+        // Path selection.  D2T_PSROI_INT unset: the integer-table multi-CTA kernel (mode 4) whenever the geometry fits and
+        // there is more than one item per SM (with fewer, a 1024-thread CTA finishes its single item sooner: measured
+        // 15.3 against 17.4 us for 84 items); D2T_PSROI_INT=0: always the exactly-rounded fp64 tables; 1..4: force a variant.
+        const char* int_env = getenv("D2T_PSROI_INT");
+        const bool mc_fits = width <= 64 && buf_bytes <= kMcSmem && group * height <= kMcMaxRows &&
+                             (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31);
+        const int mode_sel = int_env ? atoi(int_env) : ((mc_fits && items > sm_count()) ? 4 : 0);
+        if (mc_fits && mode_sel >= 2) {
+            const int mode = mode_sel;
+            const int lroi = mode >= 3;     // 3: lane -> roi lookups, 4: + thread-per-row scans (see the kernel)
+            const int thr_env = getenv("D2T_PSROI_THREADS") ? atoi(getenv("D2T_PSROI_THREADS")) : kMcDefaultThreads;
+            const int wide = thr_env == 384;
+            int kMcThreads = wide ? 384 : 256;
+            using Kern = void (*)(const float*, int, int, int, int, int, int, PsroiWs, float*, int*);
+            static const Kern kerns[2][2] = {{psroi_fwd_isat_mc<7, 256, kMcCtas, false>, psroi_fwd_isat_mc<7, 384, kMcCtas, false>},
+                                             {psroi_fwd_isat_mc<7, 256, kMcCtas, true>, psroi_fwd_isat_mc<7, 384, kMcCtas, true>}};
+            Kern kern = kerns[lroi][wide];
+            int slot = lroi;
+            if (mode == 4 && group * height <= kMcMaxRows) {
+                kern = wide ? psroi_fwd_isat_mc<7, 384, kMcCtas, true, true> : psroi_fwd_isat_mc<7, 256, kMcCtas, true, true>;
+                slot = 2;
+                if (thr_env == 320) {
+                    kern = psroi_fwd_isat_mc<7, 320, kMcCtas, true, true>;
+                    kMcThreads = 320;
+                    slot = 3;
+                }
+            }
+            static SmemAttrOnce once_mc[4][2];
+            static bool carveout_set[4][2][64] = {};
+            if (!once_mc[slot][wide].ensure(kern, kMcSmem, "psroi_fwd_isat_mc smem attr")) return 0;
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+            if (!carveout_set[slot][wide][dev]) {
+                D2T_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared), "psroi_fwd_isat_mc carveout");
+                carveout_set[slot][wide][dev] = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            const int slots = kMcCtas * sm_count();
+            cfg.gridDim = dim3(items < slots ? items : slots);
+            cfg.blockDim = dim3(kMcThreads);
+            cfg.dynamicSmemBytes = buf_bytes;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap with psroi_prep
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bottom, batch, channels, height, width, out_dim, num_rois, ws, top,
+                                           mapping),
+                        "psroi_fwd_isat_mc launch");
             return 1;
         }
         static SmemAttrOnce once;

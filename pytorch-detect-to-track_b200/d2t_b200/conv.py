@@ -153,10 +153,11 @@ class _Planned(object):
         if out is not None and not out.arena_owned:
             self.zero_amax = out.amax
 
-    def run(self):
+    def run(self, stream=None):
+        """enqueue on `stream` (a raw cudaStream_t handle) or, by default, on torch's current stream"""
         if self.zero_amax is not None:
             self.zero_amax.zero_()
-        check(lib().d2t_conv_plan_run(self.plan, _stream()), "d2t_conv_plan_run")
+        check(lib().d2t_conv_plan_run(self.plan, _stream() if stream is None else stream), "d2t_conv_plan_run")
         ops._count(1)
 
     def __del__(self):
@@ -206,8 +207,8 @@ class ConvLayer(_Planned):
         self.flops = 2.0 * x.N * OH * OW * O * I * R * S
         self._bind_amax(x, self.out)
 
-    def run(self):
-        _Planned.run(self)
+    def run(self, stream=None):
+        _Planned.run(self, stream)
         return self.out if self.out is not None else self.out_nchw
 
 
@@ -268,8 +269,8 @@ class CorrLayer(_Planned):
         self.flops = 2.0 * x1.N * oh * ow * self.D * self.D * x1.C
         self._bind_amax(None, out)
 
-    def run(self):
-        _Planned.run(self)
+    def run(self, stream=None):
+        _Planned.run(self, stream)
         return self.out_nchw if self.out_nchw is not None else self.out
 
 

@@ -160,15 +160,25 @@ class D2TEngine(object):
     @torch.no_grad()
     def forward(self, im_data, im_info):
         """im_data [B, 2, 3, H, W], im_info [B, 2, 3] (CUDA fp32) -> the reference's 10-tuple (eval)."""
-        B, L, N = self.B, 2, self.N
-        assert tuple(im_data.shape) == (B, 2, 3, self.H, self.W), "engine was built for a fixed geometry"
+        info = self._begin(im_data, im_info)
+        for layer in self.layers:
+            layer.run()
+        return self._tail(im_data, info)
+
+    def _begin(self, im_data, im_info):
+        """input re-layout, stem conv and max-pool; returns the per-frame im_info [2B, 3]"""
+        N = self.N
+        assert tuple(im_data.shape) == (self.B, 2, 3, self.H, self.W), "engine was built for a fixed geometry"
         frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, 3, self.H, self.W).contiguous()     # leg-major
         info = im_info.permute(1, 0, 2).reshape(N, 3).contiguous().float()
         self.amax.zero()
         self.stem.run(frames)
         dc.maxpool3x3s2(self.stem.out, out=self.pool_out)
-        for layer in self.layers:
-            layer.run()
+        return info
+
+    def _tail(self, im_data, info):
+        """everything after the trunk / head convs: proposal step, PSRoI heads, correlations, tracking head"""
+        B, L, N = self.B, 2, self.N
         # ---- proposals for all 2B images
         A = self.anchors.size(0)
         sc = self.rpn_score
@@ -207,3 +217,97 @@ class D2TEngine(object):
         nms_t = cfg.TEST.NMS if nms_thresh is None else nms_thresh
         return out, det.per_class_detections(out[0], out[1], out[2], im_info, thresh, nms_t, class_agnostic=(self.n_reg == 1),
                                              stds=cfg.TRAIN.BBOX_NORMALIZE_STDS, means=cfg.TRAIN.BBOX_NORMALIZE_MEANS)
+
+
+class D2TEngineStreams(object):
+    """The same forward as ``D2TEngine(net, pairs, ...)`` run as ``chains`` independent sub-engines (contiguous groups
+    of frame-pairs, SURVEY 8e: pairs are independent units) on their own CUDA streams, ENQUEUED LAYER BY LAYER IN TURN.
+    Every conv launch of one chain depends on the launch before it, and that dependency costs a fixed ~7.5 us of idle
+    SMs per launch (finding 4); with two chains in flight the gap of one hides behind the other's
+    kernel.  Each sub-engine owns a private stream-K scratch.  The outputs are concatenated in the reference's layout
+    with the image index in column 0 of ``rois`` counted over the whole batch, exactly as ``D2TEngine`` returns them."""
+
+    def __init__(self, net, pairs, height, width, chains=2, **kw):
+        assert pairs % chains == 0, "pairs must split evenly over the chains"
+        self.B, self.chains, self.per = pairs, chains, pairs // chains
+        self.engines = [D2TEngine(net, self.per, height, width, private_scratch=True, **kw) for _ in range(chains)]
+        self.streams = [torch.cuda.Stream() for _ in range(chains)]
+        e0 = self.engines[0]
+        self.conv_flops = sum(e.conv_flops for e in self.engines)
+        self.conv_backend = e0.conv_backend + ", %d interleaved chains" % chains
+        self.layers = [l for e in self.engines for l in e.layers]
+        self.n_classes, self.n_reg = e0.n_classes, e0.n_reg
+
+    @torch.no_grad()
+    def forward(self, im_data, im_info):
+        cur = torch.cuda.current_stream()
+        per = self.per
+        infos, outs = [], []
+        for i, (e, s) in enumerate(zip(self.engines, self.streams)):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                infos.append(e._begin(im_data[i * per:(i + 1) * per], im_info[i * per:(i + 1) * per]))
+        handles = [s.cuda_stream for s in self.streams]
+        for layers in zip(*[e.layers for e in self.engines]):
+            for layer, h in zip(layers, handles):
+                layer.run(h)
+        for i, (e, s) in enumerate(zip(self.engines, self.streams)):
+            with torch.cuda.stream(s):
+                o = e._tail(im_data[i * per:(i + 1) * per], infos[i])
+                if i:
+                    o[0][..., 0] += i * per          # image index inside the whole batch
+                outs.append(o)
+        for s in self.streams:
+            cur.wait_stream(s)
+        rois = torch.cat([o[0] for o in outs], 1)
+        cls_prob = torch.cat([o[1] for o in outs], 1)
+        bbox_pred = torch.cat([o[2] for o in outs], 1)
+        tracking_pred = torch.cat([o[3] for o in outs], 0)
+        o0 = outs[0]
+        return (rois, cls_prob, bbox_pred, tracking_pred) + tuple(o0[4:])
+
+    __call__ = forward
+
+
+class GraphedEngine(object):
+    """One forward of a ``D2TEngine`` / ``D2TEngineStreams`` captured as a CUDA graph (streams forked inside the capture
+    become parallel branches) and replayed per call: no per-launch host work, and the branches' kernels are released by
+    the device, not by the order in which Python reached them.  Inputs are copied into static buffers; the returned
+    tensors are the graph's static outputs and are overwritten by the next call.  Safe to replay because the conv
+    kernel's stream-K hand-shake is self-cleaning (csrc/conv.cu: the finisher clears the flags it consumed)."""
+
+    def __init__(self, engine, pairs, height, width, device="cuda", warmup=3):
+        self.engine = engine
+        self.im_data = torch.zeros(pairs, 2, 3, height, width, device=device)
+        self.im_info = torch.tensor([float(height), float(width), 1.0], device=device).view(1, 1, 3).repeat(pairs, 2, 1)
+        self.graph = None
+        self.warmup = warmup
+        self.conv_flops = engine.conv_flops
+        self.conv_backend = engine.conv_backend + ", CUDA-graph replay"
+        self.layers = engine.layers
+
+    def _capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self.engine(self.im_data, self.im_info)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        count = ops.LAUNCHES
+        with torch.cuda.graph(self.graph):
+            self.out = self.engine(self.im_data, self.im_info)
+        self.launches_per_replay = ops.LAUNCHES - count
+
+    @torch.no_grad()
+    def forward(self, im_data, im_info):
+        self.im_data.copy_(im_data, non_blocking=True)
+        self.im_info.copy_(im_info, non_blocking=True)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        ops._count(self.launches_per_replay)
+        return self.out
+
+    __call__ = forward

@@ -166,6 +166,47 @@ def test_engine_matches_torch_graph(passes):
     assert float(d) < 1e-4, float(d)
 
 
+def test_engine_chains_and_graph_replay():
+    """D2TEngineStreams (independent frame-pair chains on their own streams, enqueued in turn) computes what one
+    D2TEngine per chain computes -- bit for bit, the kernels and their inputs are the same -- and agrees with the
+    whole-batch engine to the fp32 bar; GraphedEngine replays it bit-identically, replay after replay (the stream-K
+    hand-shake leaves no stale flag behind)."""
+    from model.faster_rcnn.resnet import resnet
+    from d2t_b200.engine import D2TEngine, D2TEngineStreams, GraphedEngine
+    torch.manual_seed(3)
+    net = resnet(tuple(range(31)), 50, class_agnostic=True).create_architecture().cuda().eval()
+    B, H, W = 2, 224, 320
+    g = torch.Generator().manual_seed(1)
+    im_data = (torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128).cuda()
+    im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
+    whole = D2TEngine(net, B, H, W)(im_data, im_info)
+    chains = D2TEngineStreams(net, B, H, W, chains=2)
+    out = chains(im_data, im_info)
+    torch.cuda.synchronize()
+    single = D2TEngine(net, 1, H, W)
+    for i in range(B):
+        one = single(im_data[i:i + 1], im_info[i:i + 1])
+        assert torch.equal(one[0][..., 1:], out[0][:, i:i + 1, :, 1:])          # rois (image index aside)
+        assert float((out[0][:, i, :, 0] - i).abs().max()) == 0.0               # image index inside the whole batch
+        assert torch.equal(one[1], out[1][:, i:i + 1])
+        assert torch.equal(one[2], out[2][:, i:i + 1])
+        R = one[3].size(0)
+        assert torch.equal(one[3], out[3][i * R:(i + 1) * R])
+    same = (out[0] - whole[0]).abs().amax(-1) < 1e-2
+    assert float(same.float().mean()) > 0.98
+    assert float((out[1][same] - whole[1][same]).abs().max()) < 1e-4
+    graphed = GraphedEngine(chains, B, H, W)
+    first = [t.clone() for t in graphed(im_data, im_info)[:4]]
+    torch.cuda.synchronize()
+    for a, b in zip(first, out[:4]):
+        assert torch.equal(a, b)
+    for _ in range(5):
+        again = graphed(im_data, im_info)
+        torch.cuda.synchronize()
+        for a, b in zip(first, again[:4]):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("C,H,W,p,B", [(64, 20, 30, (8, 1, 8, 1, 1), 2), (1024, 38, 63, (8, 1, 8, 1, 1), 2),
                                        (512, 75, 125, (8, 1, 8, 2, 2), 1), (2048, 38, 63, (8, 1, 8, 1, 1), 1),
                                        (96, 21, 27, (4, 1, 4, 1, 1), 1), (40, 13, 50, (0, 1, 3, 1, 1), 1)])
