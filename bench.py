@@ -152,6 +152,23 @@ def op_microbench(flush, hbm_gbs):
     alg = 4.0 * (D * 49 * 2394 + 5 * R + R * D * 49) * B
     out["psroi_fwd"] = {"shape": "feat[%d,%d,38,63] rois %d/img D=%d" % (B, D * 49, R, D), "ms": ms,
                         "algorithmic_bytes": alg, "gbs": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / hbm_gbs}
+    # batch sweep of config 5 (same generator): the integer-table kernel keeps 3 CTAs per SM busy once there are more
+    # items (image, class, bin row) than CTA slots
+    for Bs in (8, 32):
+        f_s = torch.randn(Bs, D * 49, 38, 63, device="cuda")
+        r_s = torch.from_numpy(common.make_rois(R, Bs, seed=21)).cuda()
+        t_s = torch.empty(Bs * R, D, 7, 7, device="cuda")
+        w_s = torch.empty(lib().d2t_psroi_workspace_bytes(Bs * R, Bs, 7, 7), dtype=torch.uint8, device="cuda")
+        ms_s = time_kernel(lambda: lib().d2t_psroi_forward(f_s.data_ptr(), Bs, D * 49, 38, 63, r_s.data_ptr(), Bs * R, 1 / 16., 7,
+                                                           7, 7, D, t_s.data_ptr(), None, w_s.data_ptr(), w_s.numel(), st), 10, flush)
+        alg_s = alg / B * Bs
+        out["psroi_fwd_b%d" % Bs] = {"ms": ms_s, "algorithmic_bytes": alg_s, "gbs": alg_s / ms_s / 1e6,
+                                     "frac_hbm": alg_s / ms_s / 1e6 / hbm_gbs}
+        del f_s, r_s, t_s, w_s
+    os.environ["D2T_PSROI_INT"] = "0"          # the exactly-rounded fp64-table kernel, for comparison (read per launch)
+    ms_x = time_kernel(psroi, 10, flush)
+    del os.environ["D2T_PSROI_INT"]
+    out["psroi_fwd_fp64_tables"] = {"ms": ms_x, "gbs": alg / ms_x / 1e6, "frac_hbm": alg / ms_x / 1e6 / hbm_gbs}
     gt = torch.randn_like(top)
     grad = torch.empty_like(feat)
 
@@ -277,8 +294,13 @@ def run_b200(args):
     im_dev, info_dev = im_pin.cuda(non_blocking=True), info_pin.cuda(non_blocking=True)
     flush = torch.zeros(128 * 1024 * 1024, device="cuda")          # 512 MB
 
+    runner = engine
+    if args.graph:
+        from d2t_b200.engine import GraphedEngine
+        runner = GraphedEngine(engine, pairs, H, W)
+
     def step(im, info):
-        return engine(im, info)
+        return runner(im, info)
 
     def barrier():
         if world > 1:
@@ -400,9 +422,9 @@ def run_b200(args):
                             "issue 3 tensor-core MMAs per useful FLOP"}
         ops_bench = op_microbench(flush, hbm_gbs)
         ps = ops_bench["psroi_fwd"]
-        roofline_psroi = {"kernel": "psroi_fwd_sat<7> (+ psroi_prep) via d2t_psroi_forward", "bound": "hbm",
+        roofline_psroi = {"kernel": "psroi_fwd_isat_mc<7, 256 threads, 3 CTAs/SM> (+ psroi_prep) via d2t_psroi_forward", "bound": "hbm",
                           "achieved": ps["gbs"], "peak": hbm_gbs, "unit": "GB/s", "frac": ps["frac_hbm"],
-                          "traffic": ncu_traffic().get("psroi_fwd_sat", {}).get("dram_bytes_per_launch"),
+                          "traffic": ncu_traffic().get("psroi_fwd_isat_mc", {}).get("dram_bytes_per_launch"),
                           "traffic_note": "ncu: the features cross HBM once; the 23.5 MB of outputs stay in L2 within the capture",
                           "peak_source": peak_src, "algorithmic_bytes_per_launch": ps["algorithmic_bytes"],
                           "avg_launch_ms": ps["ms"]}
@@ -423,7 +445,7 @@ def run_b200(args):
                                        "(BASELINE.json configs[1])",
                            "pairs_per_gpu": pairs, "global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
                            "l2": "512 MB buffer rewritten between timed steps",
-                           "convs": engine.conv_backend, "conv_gflop_per_step": engine.conv_flops / 1e9},
+                           "convs": runner.conv_backend, "conv_gflop_per_step": engine.conv_flops / 1e9},
                 "e2e": {"value": world * pairs / (e2e_ms / args.steps / 1e3), "unit": "frame-pairs/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": my_launches, "roofline": roofline, "roofline_psroi": roofline_psroi,
@@ -526,6 +548,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the forward as a CUDA graph (d2t_b200.engine.GraphedEngine; measured 5.85 vs 5.93 ms/step)")
     ap.add_argument("--passes", type=int, default=16, choices=[1, 3, 16],
                     help="16 = fp32-accurate fp16-split convolutions (3xFP16, the parity mode, default); "
                          "3 = fp32-accurate 3xTF32; 1 = single-pass TF32")

@@ -96,8 +96,10 @@ psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, in
         }
     }
     ws.rb[n] = b;
-    if (n >= R)
+    if (n >= R) {                      // padding up to a multiple of 32: no image, all-zero (legal) windows
         for (int p = 0; p < PH; ++p) ws.bhb[(size_t)p * Rp + n] = 0xffff0000u;
+        for (int p = 0; p < PW; ++p) ws.bw[(size_t)n * PW + p] = 0;
+    }
     int lo = b < 0 ? 0xffff : b, hi = b < 0 ? 0 : b;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -558,7 +560,9 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 atomicMax(&crange[1], hi);
             }
         }
-        if (warp == 0) mbar_wait(&bar, phase);   // one warp polls; the others sleep at the barrier
+        if (warp == 0) {               // one warp polls (with back-off: a spinning warp takes issue slots from the two
+            while (!mbar_try_wait(&bar, phase)) __nanosleep(64);   // other CTAs of the SM); the others sleep at the barrier
+        }
         phase ^= 1;
         __syncthreads();               // planes landed, head/tail scalar stores of stage_issue visible, crange complete
         const int c_lo = crange[0], c_hi = crange[1];   // (read here: three barriers separate it from the next item's reset)
@@ -616,16 +620,20 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 const float sc = scl[r / H];
                 const float* row = pl + r * W;
                 int* irow = S + r * W;
-                int acc = 0;
-                for (int x0 = 0; x0 < W; x0 += 9) {          // 9 loads in flight, then 9 dependent adds + stores (in place)
+                int acc = 0, x0 = 0;
+                for (; x0 + 9 <= W; x0 += 9) {               // 9 loads in flight, then 9 dependent adds + stores (in place)
                     float v[9];
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) v[j] = x0 + j < W ? row[x0 + j] : 0.f;
+                    for (int j = 0; j < 9; ++j) v[j] = row[x0 + j];
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {
                         acc += __float2int_rn(v[j] * sc);
-                        if (x0 + j < W) irow[x0 + j] = acc;
+                        irow[x0 + j] = acc;
                     }
+                }
+                for (; x0 < W; ++x0) {
+                    acc += __float2int_rn(row[x0] * sc);
+                    irow[x0] = acc;
                 }
             }
         } else {
@@ -655,10 +663,23 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             const int p = i / W;
             int* col = S + p * HW + (i - p * W);
             int acc = 0;
-#pragma unroll 19
-            for (int h = 0; h < H; ++h) {
-                acc += col[h * W];
-                col[h * W] = acc;
+            // 19 loads in flight, then 19 dependent adds + stores: with load / add / store per step the compiler keeps the
+            // in-place accesses in order and every step pays the full shared-memory latency (ncu: 19 % of the kernel's
+            // stall samples sat in this loop)
+            int h0 = 0;
+            for (; h0 + 19 <= H; h0 += 19) {
+                int v[19];
+#pragma unroll
+                for (int j = 0; j < 19; ++j) v[j] = col[(h0 + j) * W];
+#pragma unroll
+                for (int j = 0; j < 19; ++j) {
+                    acc += v[j];
+                    col[(h0 + j) * W] = acc;
+                }
+            }
+            for (; h0 < H; ++h0) {
+                acc += col[h0 * W];
+                col[h0 * W] = acc;
             }
         }
         __syncthreads();
@@ -759,11 +780,11 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 if (mine_mask == 0u) continue;
                 // Branch-free from here to the stores, so that the 4 G table reads of a roi are all in flight together
                 // (with a branch per bin they were issued bin after bin: the kernel is latency-bound, not issue-bound).
-                // Lanes whose roi belongs to another image / is padding work on an all-zero window; an EMPTY window
-                // (he == hs or we == ws, possibly 0) reads up to W + 1 cells BELOW the table -- static shared memory of
-                // this CTA (stage_w alone is > 3 KB), a legal address whose value is discarded by the select below.
-                const unsigned mm = mine ? 0xffffffffu : 0u;
-                const int hs = hb & mm & 0xff, he = ((hb & mm) >> 8) & 0xff, hgt = he - hs;
+                // Lanes whose roi belongs to another image (or is padding: all-zero windows from psroi_prep) look up their
+                // own, equally legal, windows and are masked at the store.  An EMPTY window (he == hs or we == ws, possibly
+                // 0) reads up to W + 1 cells BELOW the table -- static shared memory of this CTA (stage_w alone is > 3 KB),
+                // a legal address whose value is discarded by the select below.
+                const int hs = hb & 0xff, he = (hb >> 8) & 0xff, hgt = he - hs;
                 const int m0 = hs > 0 ? -1 : 0;
                 // shared-memory byte addresses of row he-1 / row max(hs-1, 0) of plane 0 (a corner = one add + one LDS)
                 uint32_t a1 = smem_u32(S) + (uint32_t)((he - 1) * W) * 4u;
@@ -772,7 +793,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 float o[G];
 #pragma unroll
                 for (int pw = 0; pw < G; ++pw) {
-                    const unsigned wb = wbv[pw] & mm;
+                    const unsigned wb = wbv[pw];
                     const int wsx = wb & 0xff, we = wb >> 8;
                     const uint32_t c1 = (uint32_t)(we - 1) * 4u, cz = (uint32_t)max(wsx - 1, 0) * 4u;
                     const int n0 = wsx > 0 ? -1 : 0;

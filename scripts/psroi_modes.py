@@ -68,8 +68,9 @@ def run_shape(B, D, R, shuffle=False, modes=MODES, iters=20, want_mapping=False)
 
 
 if __name__ == "__main__":
-    run_shape(2, 30, 2000)                                     # BASELINE config 5 at B = 2 (bench.py's shape)
-    fast = [m for m in MODES if m[0] in ("fp64", "auto", "int4_256", "int4_320", "int4_384")]
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    fast = [m for m in MODES if m[0] in (("fp64", "auto", "int4_320") if quick else ("fp64", "auto", "int4_256", "int4_320", "int4_384"))]
+    run_shape(2, 30, 2000, modes=fast if quick else MODES)     # BASELINE config 5 at B = 2 (bench.py's shape)
     run_shape(2, 30, 2000, shuffle=True, modes=fast, iters=5, want_mapping=True)   # unsorted rois + mapping output
     run_shape(3, 4, 77, modes=fast, iters=5, want_mapping=True)     # ragged: R not a multiple of 32, D = 4
     run_shape(4, 31, 300, modes=fast, iters=10)                # the model's cls head: 4 frames x 300 rois, D = 31

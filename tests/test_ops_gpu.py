@@ -96,6 +96,32 @@ def test_psroi_full_size_vs_reference_kernel(D, B, R):
     close(g, rg, rtol=1e-4, atol=1e-5)
 
 
+def test_psroi_integer_tables_against_exact_tables(monkeypatch):
+    """The forward has two table kernels (csrc/psroi.cu): fp64 summed-area tables (exactly rounded bin means,
+    D2T_PSROI_INT=0) and, chosen by default when there is more than one item per SM, per-plane fixed-point int32 tables
+    (window sums exact in integers; the only error is the quantisation, <= 2^-30 of the plane's L1 norm per cell).  Same
+    bins, same mapping; values within that bound -- also for large-magnitude features, unsorted rois, ragged counts."""
+    for B, D, R, shuffle, amp in ((2, 30, 2000, False, 1.0), (2, 30, 500, True, 300.0), (3, 8, 77, True, 1e-3),
+                                  (4, 31, 300, False, 1.0)):
+        torch.manual_seed(20 + R)
+        feat = torch.randn(B, D * 49, 38, 63, device="cuda") * amp
+        feat[0, 5] += 3.0 * amp                                        # a plane with a large mean (no cancellation)
+        rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
+        monkeypatch.setenv("D2T_PSROI_INT", "0")
+        exact, map_x = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D, want_mapping=True)
+        monkeypatch.setenv("D2T_PSROI_INT", "4")
+        fixed, map_i = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D, want_mapping=True)
+        monkeypatch.delenv("D2T_PSROI_INT")
+        auto, _ = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+        assert torch.equal(map_x, map_i)
+        l1 = feat.abs().sum((2, 3))[:, :D * 49].max()                   # largest plane L1 norm
+        bound = float(l1) * 2.0 ** -30 * 1.05 + 3e-7 * float(exact.abs().max())   # quantisation + fp32 rounding of the mean
+        err = float((fixed - exact).abs().max())
+        assert err <= bound, (err, bound, B, D, R)
+        # the default is one of the two
+        assert torch.equal(auto, fixed) or torch.equal(auto, exact)
+
+
 def test_psroi_edge_cases(oracle):
     feat = torch.randn(2, 196, 9, 11, device="cuda")
     # empty roi list
