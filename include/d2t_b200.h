@@ -146,7 +146,12 @@ int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int bo
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- PSRoI with explicit workspace; mapping may be NULL; accumulate=0 overwrites the
- * touched planes of bottom_diff (no pre-zeroing needed for channels < D*G*G). ---- */
+ * touched planes of bottom_diff (no pre-zeroing needed for channels < D*G*G).
+ * Replaces PSROIPoolForwardLauncher / PSROIPoolBackwardLauncher (psroi_pooling/src/psroi_pooling_kernel.h:8-14) for
+ * callers that know the batch size.  Forward, 7x7 bins: bins are the reference's bit for bit; values come from 2-D
+ * prefix-sum tables -- per-plane fixed-point int32 tables (|error| <= 2^-30 * L1 norm of the plane) when
+ * batch * out_dim * 7 exceeds the SM count and width <= 64, exactly rounded fp64 tables otherwise or when the
+ * environment has D2T_PSROI_INT=0.  The workspace must hold d2t_psroi_workspace_bytes() bytes, 4-byte aligned. ---- */
 size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w);
 int d2t_psroi_forward(const float* bottom, int batch, int channels, int height, int width,
                       const float* rois, int num_rois, float scale, int pooled_h, int pooled_w,

@@ -17,9 +17,14 @@
 //   * the planes are turned into fp64 summed-area tables, after which every bin is 4 table reads
 //     whatever its size (forward), or 4 atomics into a difference array followed by two scans
 //     (backward).  Features / gradients cross HBM exactly once.
-// Pooled values are the correctly rounded exact bin means; they differ from the reference's
-// sequential fp32 sums by the reference's own rounding (<= ~1e-6 relative).  The generic kernels
-// below keep the reference's summation order bit for bit and serve every other geometry and the
+// Two table kernels share that plan (selection: d2t_psroi_forward below; measurements: DESIGN.md section 6):
+//   * psroi_fwd_isat_mc -- the default whenever there is more than one item per SM and the plane is <= 64 wide: one item
+//     per 256-thread CTA, three CTAs per SM; per-plane fixed-point int32 tables built in place in the TMA buffer (window
+//     sums exact in integers, quantisation <= 2^-30 of the plane's L1 norm per cell), lane-per-roi branch-free lookups;
+//   * psroi_fwd_sat -- fp64 tables, one 1024-thread CTA per SM: pooled values are the correctly rounded exact bin means
+//     (they differ from the reference's sequential fp32 sums by the reference's own rounding, <= ~1e-6 relative);
+//     D2T_PSROI_INT=0 forces it.
+// The generic kernels below keep the reference's summation order bit for bit and serve every other geometry and the
 // reference-named launcher, which is not told the batch size.
 #include "common.cuh"
 
@@ -1108,7 +1113,9 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
                         "psroi_fwd_isat launch");
             return 1;
         }
-        // D2T_PSROI_INT=2: the same integer tables, one item per 384-thread CTA, three CTAs per SM (psroi_fwd_isat_mc).
+        // psroi_fwd_isat_mc: the same integer tables, one item per CTA, three CTAs per SM.  Modes 2 / 3 / 4 are the steps of
+        // its development (lane -> (roi, pw) lookups / lane -> roi lookups / + thread-per-row scans), kept for A/B runs
+        // (scripts/psroi_modes.py); D2T_PSROI_THREADS = 256 (default, measured best) | 320 | 384.
         constexpr int kMcCtas = 3;
         constexpr int kMcDefaultThreads = 256;
         constexpr size_t kMcSmem = 70 * 1024;      // 3 x (70 KB + 4 KB static + 1 KB reserved) <= 227 KB per SM

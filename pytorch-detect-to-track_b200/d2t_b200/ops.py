@@ -55,7 +55,9 @@ def psroi_mapping_channel(num_rois, pooled_h, pooled_w, group, out_dim, device):
 
 def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, want_mapping=False):
     """psroi_pooling/functions/psroi_pool.py:18-33 -> d2t_psroi_forward.  Returns (top, mapping);
-    mapping is None unless want_mapping (then the kernel writes it, as the reference's does)."""
+    mapping is None unless want_mapping (then the kernel writes it, as the reference's does).
+    The library picks the table kernel (csrc/psroi.cu): per-plane fixed-point int32 tables when there is more than one
+    (image, class, bin-row) item per SM, fp64 tables otherwise or when the environment has D2T_PSROI_INT=0."""
     _req(features, "features"), _req(rois, "rois")
     if rois.dim() != 2 or rois.size(1) != 5:
         raise ValueError("rois must be [R, 5]")   # the reference returns 0 silently (psroi_pooling_cuda.c:17-20)
