@@ -1115,7 +1115,7 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
         }
         // psroi_fwd_isat_mc: the same integer tables, one item per CTA, three CTAs per SM.  Modes 2 / 3 / 4 are the steps of
         // its development (lane -> (roi, pw) lookups / lane -> roi lookups / + thread-per-row scans), kept for A/B runs
-        // (scripts/psroi_modes.py); D2T_PSROI_THREADS = 256 (default, measured best) | 320 | 384.
+        // (scripts/psroi_modes.py); D2T_PSROI_THREADS = 256 (default, measured best) | 288 | 320 | 384.
         constexpr int kMcCtas = 3;
         constexpr int kMcDefaultThreads = 256;
         constexpr size_t kMcSmem = 70 * 1024;      // 3 x (70 KB + 4 KB static + 1 KB reserved) <= 227 KB per SM
@@ -1140,14 +1140,14 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
             if (mode == 4 && group * height <= kMcMaxRows) {
                 kern = wide ? psroi_fwd_isat_mc<7, 384, kMcCtas, true, true> : psroi_fwd_isat_mc<7, 256, kMcCtas, true, true>;
                 slot = 2;
-                if (thr_env == 320) {
-                    kern = psroi_fwd_isat_mc<7, 320, kMcCtas, true, true>;
-                    kMcThreads = 320;
-                    slot = 3;
+                if (thr_env == 288 || thr_env == 320) {        // 288: every plane row of a 7 x 38-row item has its own thread
+                    kern = thr_env == 288 ? psroi_fwd_isat_mc<7, 288, kMcCtas, true, true> : psroi_fwd_isat_mc<7, 320, kMcCtas, true, true>;
+                    kMcThreads = thr_env;
+                    slot = thr_env == 288 ? 4 : 3;
                 }
             }
-            static SmemAttrOnce once_mc[4][2];
-            static bool carveout_set[4][2][64] = {};
+            static SmemAttrOnce once_mc[5][2];
+            static bool carveout_set[5][2][64] = {};
             if (!once_mc[slot][wide].ensure(kern, kMcSmem, "psroi_fwd_isat_mc smem attr")) return 0;
             int dev = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;

@@ -21,7 +21,7 @@ torch.cuda.set_device(0)
 flush = torch.zeros(128 * 1024 * 1024, device="cuda")
 HBM = bench.peaks()[0]
 MODES = [("fp64", "0", None), ("auto", None, None), ("int1", "1", None), ("int2_256", "2", "256"), ("int2_384", "2", "384"),
-         ("int3_256", "3", "256"), ("int3_384", "3", "384"), ("int4_256", "4", "256"), ("int4_320", "4", "320"),
+         ("int3_256", "3", "256"), ("int3_384", "3", "384"), ("int4_256", "4", "256"), ("int4_288", "4", "288"), ("int4_320", "4", "320"),
          ("int4_384", "4", "384")]
 
 
@@ -69,7 +69,7 @@ def run_shape(B, D, R, shuffle=False, modes=MODES, iters=20, want_mapping=False)
 
 if __name__ == "__main__":
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-    fast = [m for m in MODES if m[0] in (("fp64", "auto", "int4_320") if quick else ("fp64", "auto", "int4_256", "int4_320", "int4_384"))]
+    fast = [m for m in MODES if m[0] in (("fp64", "auto", "int4_288") if quick else ("fp64", "auto", "int4_256", "int4_320", "int4_384"))]
     run_shape(2, 30, 2000, modes=fast if quick else MODES)     # BASELINE config 5 at B = 2 (bench.py's shape)
     run_shape(2, 30, 2000, shuffle=True, modes=fast, iters=5, want_mapping=True)   # unsorted rois + mapping output
     run_shape(3, 4, 77, modes=fast, iters=5, want_mapping=True)     # ragged: R not a multiple of 32, D = 4
