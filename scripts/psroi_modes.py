@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "pytorch-detect-to-track_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
+ARGS = sys.argv[1:]
 sys.argv = ["bench.py"]
 import bench
 import common
@@ -68,7 +69,7 @@ def run_shape(B, D, R, shuffle=False, modes=MODES, iters=20, want_mapping=False)
 
 
 if __name__ == "__main__":
-    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    quick = bool(ARGS) and ARGS[0] == "quick"
     fast = [m for m in MODES if m[0] in (("fp64", "auto", "int4_288") if quick else ("fp64", "auto", "int4_256", "int4_320", "int4_384"))]
     run_shape(2, 30, 2000, modes=fast if quick else MODES)     # BASELINE config 5 at B = 2 (bench.py's shape)
     run_shape(2, 30, 2000, shuffle=True, modes=fast, iters=5, want_mapping=True)   # unsorted rois + mapping output
