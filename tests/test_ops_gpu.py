@@ -122,6 +122,30 @@ def test_psroi_integer_tables_against_exact_tables(monkeypatch):
         assert torch.equal(auto, fixed) or torch.equal(auto, exact)
 
 
+@pytest.mark.parametrize("B,D,H,W", [(2, 2, 10, 12), (1, 3, 5, 7), (2, 2, 30, 64), (3, 1, 45, 33), (2, 4, 19, 63),
+                                     (1, 2, 1, 1), (2, 31, 24, 40)])
+def test_psroi_integer_tables_other_geometries(oracle, monkeypatch, B, D, H, W):
+    """The integer-table kernel is selected for any 7x7 geometry with planes up to 64 wide once there is more than one
+    item per SM; its scans have separate code for odd widths (thread per row), even widths (warp shuffles), rows / columns
+    shorter than one batch.  Forced here (D2T_PSROI_INT=4) on small planes and compared with the CPU oracle: bins and
+    mapping bit-exact, values within the quantisation bound; the last case is selected by the library on its own."""
+    torch.manual_seed(H * 100 + W)
+    feat = torch.randn(B, D * 49, H, W, device="cuda")
+    rois = common.make_rois(40, B, height=H * 16, width=W * 16, seed=H + W, lo=8, hi=max(64.0, 12.0 * min(H, W)),
+                            shuffle=True)
+    if B * D * 7 <= 148:
+        monkeypatch.setenv("D2T_PSROI_INT", "4")
+    top, mapping = ops.psroi_forward(feat, cu(rois), 7, 7, 1 / 16., 7, D, want_mapping=True)
+    monkeypatch.delenv("D2T_PSROI_INT", raising=False)
+    want, wmap = oracle.psroi_forward(npy(feat), rois, 1 / 16., 7, 7, 7, D)
+    np.testing.assert_array_equal(npy(mapping), wmap)
+    l1 = float(feat.abs().sum((2, 3)).max())
+    np.testing.assert_allclose(npy(top), want, rtol=PS_RTOL, atol=PS_ATOL + l1 * 2.0 ** -30)
+    monkeypatch.setenv("D2T_PSROI_INT", "0")
+    exact, _ = ops.psroi_forward(feat, cu(rois), 7, 7, 1 / 16., 7, D)
+    assert float((top - exact).abs().max()) <= l1 * 2.0 ** -30 * 1.05 + 3e-7 * float(exact.abs().max())
+
+
 def test_psroi_edge_cases(oracle):
     feat = torch.randn(2, 196, 9, 11, device="cuda")
     # empty roi list
