@@ -239,6 +239,12 @@ int d2t_conv_plan_set_amax(d2t_conv_plan* plan, const float* amax_in, float* ama
  * zero-initialised device buffer of d2t_conv_scratch_bytes() bytes. */
 size_t d2t_conv_scratch_bytes(void);
 int d2t_conv_plan_set_scratch(d2t_conv_plan* plan, void* scratch, size_t bytes);
+/* Optional completion hand-shake for CONSECUTIVE launches of one chain on one stream (experiment, off unless called):
+ * every CTA of `plan` adds 1 to *self_counter once its outputs are globally visible; if prev_counter is given (the
+ * self_counter of `prev`, the plan launched immediately before on the same stream), the kernel polls it up to prev's grid
+ * size instead of executing griddepcontrol.wait.  The caller zeroes the counters before each pass over the chain (the
+ * engine keeps them in the arena its per-forward memset clears).  Null pointers restore the default. */
+int d2t_conv_plan_set_done(d2t_conv_plan* plan, const d2t_conv_plan* prev, const int* prev_counter, int* self_counter);
 void d2t_conv_plan_destroy(d2t_conv_plan* plan);
 /* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid*10 + pair_mode} */
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);

@@ -100,6 +100,13 @@ struct ConvArgs {
     const float* amax_in;
     float* amax_out;
     int w_exp;
+    // optional completion hand-shake between consecutive launches of one chain (d2t_conv_plan_set_done): every CTA adds
+    // 1 to *done_self when all its outputs are globally visible; a launch whose done_prev is set polls that counter up
+    // to done_target (= the previous launch's grid) INSTEAD of griddepcontrol.wait, i.e. it does not sit through the
+    // hardware's grid-completion latency (~3.4 us per dependent launch, DESIGN section 6 finding 4)
+    const int* done_prev;
+    int done_target;
+    int* done_self;
     long long* trace;              // debug builds only (D2T_CONV_TRACE): per-CTA wait-cycle counters
     int exp;                       // debug builds only: experiment bit mask (env D2T_CONV_EXP)
 };
@@ -467,7 +474,22 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 #ifdef D2T_CONV_TRACE
     const long long t_prol__ = clock64();
 #endif
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.done_prev) {
+        // the previous launch of this chain counts its finished CTAs (see the end of this kernel): poll instead of waiting
+        // for the hardware's notion of grid completion; everything older in the stream was complete before that launch
+        // could finish (it waited the same way, or with griddepcontrol.wait)
+        if (threadIdx.x == 0) {
+            int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.done_prev) : "memory");
+                if (v < p.done_target) __nanosleep(40);
+            } while (v < p.done_target);
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");      // my TMA loads come after the acquire
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     asm volatile("griddepcontrol.launch_dependents;");
 #ifdef D2T_CONV_TRACE
     const long long t_dep__ = clock64();
@@ -1049,7 +1071,13 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 #ifdef D2T_CONV_TRACE
     const long long t_w0__ = clock64();
 #endif
-    if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) tma_store_wait_all();
+    if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) {
+        tma_store_wait_all();
+        if (p.done_self) {                                    // my bulk stores are complete: order them before the count below
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+        }
+    }
 #ifdef D2T_CONV_TRACE
     if (p.trace && warp == kEpiWarp0 && lane == 0) {
         p.trace[(size_t)blockIdx.x * 64 + 16 + 5] = clock64() - t_w0__;     // role 2 value 5: the final store wait
@@ -1058,6 +1086,10 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 #endif
     tc_fence_before();
     __syncthreads();
+    if (p.done_self && threadIdx.x == 0) {         // every thread's stores (and the flag resets above) precede the barrier
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done_self) : "memory");
+    }
     if (PAIR) cluster_sync_all();                  // the peer may still signal my barriers / feed my tensor core
 #ifdef D2T_CONV_TRACE
     const long long t_sync__ = clock64();
@@ -1323,7 +1355,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.relu = d->relu;
     a.out = out; a.out_cstride = d->out_cstride; a.out_coffset = d->out_coffset;
     a.out_nchw = out_nchw;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp; a.trace = nullptr; a.exp = 0;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp; a.trace = nullptr; a.exp = 0; a.done_prev = nullptr; a.done_target = 0; a.done_self = nullptr;
     pl->passes = d->passes; pl->corr = 0;
     // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
     pl->pair = (!f16 && a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
@@ -1414,7 +1446,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.scale = scale; a.shift = shift; a.res = nullptr; a.res_cstride = Cout; a.relu = relu;
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0; pl->pair = 0;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0; a.done_prev = nullptr; a.done_target = 0; a.done_self = nullptr;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7, passes);
     {
         SkScratch sk;
@@ -1482,7 +1514,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = out_nchw;
     a.corr_r = r; a.corr_D = 2 * r + 1; a.corr_nelems = (float)(c_real > 0 ? c_real : C);
     pl->BN = 128; pl->passes = passes; pl->corr = 1; pl->pair = 0;
-    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0;
+    a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0; a.done_prev = nullptr; a.done_target = 0; a.done_self = nullptr;
     pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.kc_blocks, passes);
     {
         SkScratch sk;
@@ -1524,6 +1556,15 @@ extern "C" int d2t_conv_plan_set_amax(d2t_conv_plan* pl, const float* amax_in, f
     D2T_REQUIRE(pl, "d2t_conv_plan_set_amax: null plan");
     pl->args.amax_in = amax_in;
     pl->args.amax_out = amax_out;
+    return 1;
+}
+
+extern "C" int d2t_conv_plan_set_done(d2t_conv_plan* pl, const d2t_conv_plan* prev, const int* prev_counter,
+                                      int* self_counter) {
+    D2T_REQUIRE(pl && (!prev_counter || prev), "d2t_conv_plan_set_done: a counter to wait on needs the plan that fills it");
+    pl->args.done_prev = prev_counter;
+    pl->args.done_target = prev_counter ? prev->grid : 0;
+    pl->args.done_self = self_counter;
     return 1;
 }
 

@@ -145,6 +145,16 @@ class _Planned(object):
         check(lib().d2t_conv_plan_set_scratch(self.plan, scratch.data_ptr(), scratch.numel()), "d2t_conv_plan_set_scratch")
         self._scratch = scratch
 
+    def set_done(self, prev, self_counter):
+        """completion hand-shake with the layer launched immediately before this one on the same stream (csrc/conv.cu,
+        d2t_conv_plan_set_done): `self_counter` is a one-element int32 CUDA tensor this layer's CTAs count into, `prev` the
+        previous layer (whose counter this one polls instead of griddepcontrol.wait) or None.  The caller zeroes the
+        counters before every pass over the chain."""
+        self.done_counter = self_counter
+        check(lib().d2t_conv_plan_set_done(self.plan, prev.plan if prev is not None else None,
+                                           _p(prev.done_counter) if prev is not None else None, _p(self_counter)),
+              "d2t_conv_plan_set_done")
+
     def _bind_amax(self, x, out):
         """attach the input's / output's amax scalars; outside an engine arena the layer zeroes its output's before
         each run (inside one, several producers may share an output buffer and the engine zeroes all at once)"""

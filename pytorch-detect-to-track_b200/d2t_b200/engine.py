@@ -18,6 +18,8 @@ fp32-accurate fp16-split mode ("3xFP16": hi/lo fp16 operands with per-tensor pow
 twice the TF32 tensor rate; the stem and the correlations stay on 3xTF32), ``passes=3`` the
 fp32-accurate 3xTF32 mode, ``passes=1`` single-pass TF32.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -37,6 +39,14 @@ class D2TEngine(object):
         self.amax = dc.AmaxArena(1024, dev)       # every activation tensor's running max |x|, zeroed once per forward
         with self.amax:
             self._build(net, pairs, height, width, passes, cfg_key, keep_features)
+        if os.environ.get("D2T_CONV_DONE") == "1":
+            # EXPERIMENT: consecutive conv launches hand over through per-layer completion counters instead of
+            # griddepcontrol.wait.  The counters live in the amax arena, so the per-forward memset clears them too.
+            for chain in (self.layers, self.corr_layers + [self.trk_layer]):
+                prev = None
+                for layer in chain:
+                    layer.set_done(prev, self.amax.take().view(torch.int32))
+                    prev = layer
         if private_scratch:    # this engine's conv chain may then overlap another engine's on a different stream
             from ._lib import lib
             self.scratch = torch.zeros(lib().d2t_conv_scratch_bytes(), dtype=torch.uint8, device=dev)
