@@ -221,12 +221,17 @@ class D2TEngine(object):
     def detect(self, im_data, im_info, thresh=0.0, nms_thresh=None):
         """forward + the reference's post-processing (test_net.py:232-301) for every frame and class in one batched
         pass: returns (forward outputs, d2t_b200.detect.Detections)."""
-        from model.utils.config import cfg
-        from . import detect as det
-        out = self.forward(im_data, im_info)
-        nms_t = cfg.TEST.NMS if nms_thresh is None else nms_thresh
-        return out, det.per_class_detections(out[0], out[1], out[2], im_info, thresh, nms_t, class_agnostic=(self.n_reg == 1),
-                                             stds=cfg.TRAIN.BBOX_NORMALIZE_STDS, means=cfg.TRAIN.BBOX_NORMALIZE_MEANS)
+        return _detect(self, self.n_reg, im_data, im_info, thresh, nms_thresh)
+
+
+@torch.no_grad()
+def _detect(engine, n_reg, im_data, im_info, thresh, nms_thresh):
+    from model.utils.config import cfg
+    from . import detect as det
+    out = engine(im_data, im_info)
+    nms_t = cfg.TEST.NMS if nms_thresh is None else nms_thresh
+    return out, det.per_class_detections(out[0], out[1], out[2], im_info, thresh, nms_t, class_agnostic=(n_reg == 1),
+                                         stds=cfg.TRAIN.BBOX_NORMALIZE_STDS, means=cfg.TRAIN.BBOX_NORMALIZE_MEANS)
 
 
 class D2TEngineStreams(object):
@@ -278,6 +283,9 @@ class D2TEngineStreams(object):
 
     __call__ = forward
 
+    def detect(self, im_data, im_info, thresh=0.0, nms_thresh=None):
+        return _detect(self, self.n_reg, im_data, im_info, thresh, nms_thresh)
+
 
 class GraphedEngine(object):
     """One forward of a ``D2TEngine`` / ``D2TEngineStreams`` captured as a CUDA graph (streams forked inside the capture
@@ -321,3 +329,7 @@ class GraphedEngine(object):
         return self.out
 
     __call__ = forward
+
+    def detect(self, im_data, im_info, thresh=0.0, nms_thresh=None):
+        """graph replay + the batched post-processing of D2TEngine.detect (eager: its output sizes depend on the data)"""
+        return _detect(self, self.engine.n_reg, im_data, im_info, thresh, nms_thresh)
