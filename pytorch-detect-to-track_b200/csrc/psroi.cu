@@ -941,6 +941,175 @@ psroi_bwd_sat(const float* __restrict__ top_diff, int B, int C, int H, int W, in
     }
 }
 
+// ---- backward on integer difference tables, one item per CTA, several CTAs per SM (EXPERIMENT: D2T_PSROI_BWD_INT=1) ----
+// The execution shape of psroi_fwd_isat_mc applied to the adjoint: a 256-thread CTA owns one item (image, ctop, ph) and a
+// [G][H+1][W+2] int32 difference table (71 KB: three CTAs per SM), so the phases of different items overlap on the SM.
+//   pass A: sum |dv| over the item's bins (dv = top_diff / area, the reference's fp32 division, kernel.cu:161) -> one
+//           power-of-two scale 2^k per item with sum |round(dv 2^k)| < 2^31: no cell of the finished gradient plane can
+//           leave int32, and intermediate wrap-around is harmless (the adds are exact modulo 2^32);
+//   pass B: the four corner updates of every bin as int32 shared-memory atomics (order-independent: integer adds);
+//   scans : thread per table row (odd pitch W + 2 for even W + 1 ... see Wp), then thread per column;
+//   write : planes * 2^-k to HBM, one warp per row (coalesced), exactly once (or += when `accumulate`).
+// Error: each dv is rounded to a multiple of 2^-k (<= 2^-(k+1) off), so a gradient cell covered by n bins is within
+// n 2^-(k+1) <= n 2^-30 sum|dv| of the exact sum -- about 1e-6 absolute for BASELINE config 5 (n ~ 5), against gradients of
+// a few tenths; the fp64 kernel above stays the default until this one has been measured.
+template <int G, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+psroi_bwd_isat_mc(const float* __restrict__ top_diff, int B, int C, int H, int W, int D, int R, PsroiWs ws,
+                  float* __restrict__ bottom_diff, int accumulate) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    __shared__ float red[NW];
+    __shared__ float scl_s[2];     // 2^k, 2^-k of the item
+    __shared__ int crange[2];
+    int* T = reinterpret_cast<int*>(smem4);                 // [G][H + 1][Wp]
+    const int HW = H * W;
+    const int Wp = (W + 1) | 1, Hp = H + 1, plane = Hp * Wp;   // odd pitch: thread-per-row accesses spread over the banks
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int items = B * D * G;
+    const int Rp = psroi_rp(R), nchunks = Rp >> 5;
+    const int per_roi = D * G * G;
+
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
+        if (tid == 0) {
+            crange[0] = 0x3fffffff;
+            crange[1] = -1;
+        }
+        __syncthreads();               // previous item's write-out is done with the table, crange and scl_s
+        for (int i = tid; i < G * plane; i += THREADS) T[i] = 0;
+        {   // chunk range of image b
+            int lo = 0x3fffffff, hi = -1;
+            for (int ck = tid; ck < nchunks; ck += THREADS) {
+                const int mm = __ldg(ws.chunk + ck);
+                if (b >= (mm & 0xffff) && b <= (mm >> 16)) {
+                    lo = min(lo, ck);
+                    hi = max(hi, ck);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0 && hi >= 0) {
+                atomicMin(&crange[0], lo);
+                atomicMax(&crange[1], hi);
+            }
+        }
+        __syncthreads();
+        const int c_lo = crange[0], c_hi = crange[1];
+        const unsigned int* __restrict__ bhb = ws.bhb + (size_t)ph * Rp;
+        const int obase = ctop * (G * G) + ph * G;
+        // ---- pass A: sum |dv| of my chunks (lane -> roi, its G bins in turn)
+        float part = 0.f;
+        for (int ck = c_lo + warp; ck <= c_hi; ck += NW) {
+            const int n = ck * 32 + lane;
+            const unsigned hb = __ldg(bhb + n);
+            if ((int)(hb >> 16) != b) continue;
+            const int hgt = (int)((hb >> 8) & 0xff) - (int)(hb & 0xff);
+            if (hgt <= 0) continue;
+            const float* g = top_diff + (size_t)n * per_roi + obase;
+#pragma unroll
+            for (int pw = 0; pw < G; ++pw) {
+                const unsigned wb = __ldg(ws.bw + (size_t)n * G + pw);
+                const int wid = (int)(wb >> 8) - (int)(wb & 0xff);
+                if (wid > 0) part += fabsf(__fdiv_rn(__ldg(g + pw), (float)(hgt * wid)));
+            }
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();               // table zeroed, partial sums in place
+        if (tid == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < NW; ++w) tot += red[w];          // fixed order: the scale is deterministic
+            // tot < 2^(eb - 126)  =>  k = 30 - (eb - 126), as in the forward kernel; tot = 0: any scale will do
+            const int eb = (int)((__float_as_uint(tot) >> 23) & 0xffu);
+            int k = (eb > 0 && eb < 255) ? 156 - eb : 0;
+            k = k < -96 ? -96 : (k > 120 ? 120 : k);
+            scl_s[0] = __uint_as_float((uint32_t)(127 + k) << 23);
+            scl_s[1] = __uint_as_float((uint32_t)(127 - k) << 23);
+        }
+        __syncthreads();
+        const float sc = scl_s[0], isc = scl_s[1];
+        // ---- pass B: corner updates
+        for (int ck = c_lo + warp; ck <= c_hi; ck += NW) {
+            const int n = ck * 32 + lane;
+            const unsigned hb = __ldg(bhb + n);
+            if ((int)(hb >> 16) != b) continue;
+            const int hs = hb & 0xff, he = (hb >> 8) & 0xff, hgt = he - hs;
+            if (hgt <= 0) continue;
+            const float* g = top_diff + (size_t)n * per_roi + obase;
+#pragma unroll
+            for (int pw = 0; pw < G; ++pw) {
+                const unsigned wb = __ldg(ws.bw + (size_t)n * G + pw);
+                const int wsx = wb & 0xff, we = wb >> 8, wid = we - wsx;
+                if (wid <= 0) continue;
+                const int q = __float2int_rn(__fdiv_rn(__ldg(g + pw), (float)(hgt * wid)) * sc);
+                int* P = T + pw * plane;
+                atomicAdd(P + hs * Wp + wsx, q);
+                atomicAdd(P + hs * Wp + we, -q);
+                atomicAdd(P + he * Wp + wsx, -q);
+                atomicAdd(P + he * Wp + we, q);
+            }
+        }
+        __syncthreads();
+        // ---- row scans (rows 0..H-1 of every plane; row H and column W only ever receive closing corners)
+        for (int r = tid; r < G * H; r += THREADS) {
+            const int p = r / H, h = r - p * H;
+            int* row = T + p * plane + h * Wp;
+            int acc = 0, x0 = 0;
+            for (; x0 + 9 <= W; x0 += 9) {
+                int v[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) v[j] = row[x0 + j];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    acc += v[j];
+                    row[x0 + j] = acc;
+                }
+            }
+            for (; x0 < W; ++x0) {
+                acc += row[x0];
+                row[x0] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- column scans
+        for (int i = tid; i < G * W; i += THREADS) {
+            const int p = i / W;
+            int* col = T + p * plane + (i - p * W);
+            int acc = 0, h0 = 0;
+            for (; h0 + 19 <= H; h0 += 19) {
+                int v[19];
+#pragma unroll
+                for (int j = 0; j < 19; ++j) v[j] = col[(h0 + j) * Wp];
+#pragma unroll
+                for (int j = 0; j < 19; ++j) {
+                    acc += v[j];
+                    col[(h0 + j) * Wp] = acc;
+                }
+            }
+            for (; h0 < H; ++h0) {
+                acc += col[h0 * Wp];
+                col[h0 * Wp] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- write-out: one warp per plane row, coalesced
+        float* dst = bottom_diff + ((size_t)b * C + (size_t)cg * G) * HW;
+        for (int r = warp; r < G * H; r += NW) {
+            const int p = r / H, h = r - p * H;
+            const int* row = T + p * plane + h * Wp;
+            float* o = dst + (size_t)r * W;
+            for (int x = lane; x < W; x += 32) {
+                const float v = __int2float_rn(row[x]) * isc;
+                o[x] = accumulate ? o[x] + v : v;
+            }
+        }
+    }
+}
+
 // Generic fallbacks (any PH/PW/G, any plane size): one thread per output element.
 __global__ void psroi_fwd_generic(const float* __restrict__ feat, int B, int C, int H, int W,
                                   const float* __restrict__ rois, int R, float scale, int PH, int PW, int G,
@@ -1222,6 +1391,29 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
                             "psroi_bwd tail memset");
         }
         const int items = batch * out_dim * group;
+        {   // EXPERIMENT, off unless D2T_PSROI_BWD_INT=1: integer difference tables, three CTAs per SM (psroi_bwd_isat_mc)
+            const size_t tbytes = (size_t)group * (height + 1) * ((width + 1) | 1) * sizeof(int);
+            constexpr size_t kBwdSmem = 72 * 1024;     // 3 x (72 KB + static + 1 KB reserved) <= 227 KB per SM
+            const char* e = getenv("D2T_PSROI_BWD_INT");
+            if (e && atoi(e) == 1 && tbytes <= kBwdSmem) {
+                auto kern = psroi_bwd_isat_mc<7, 256, 3>;
+                static SmemAttrOnce once_b;
+                static bool carve_b[64] = {};
+                if (!once_b.ensure(kern, kBwdSmem, "psroi_bwd_isat_mc smem attr")) return 0;
+                int dev = 0;
+                if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+                if (!carve_b[dev]) {
+                    D2T_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                     cudaSharedmemCarveoutMaxShared), "psroi_bwd_isat_mc carveout");
+                    carve_b[dev] = true;
+                }
+                const int slots = 3 * sm_count();
+                kern<<<items < slots ? items : slots, 256, tbytes, stream>>>(top_diff, batch, channels, height, width, out_dim,
+                                                                          num_rois, ws, bottom_diff, accumulate);
+                D2T_CHECK_LAUNCH("psroi_bwd_isat_mc");
+                return 1;
+            }
+        }
         psroi_bwd_sat<7><<<items < sm_count() ? items : sm_count(), 1024, smem, stream>>>(
             top_diff, batch, channels, height, width, out_dim, num_rois, ws, bottom_diff, accumulate);
         D2T_CHECK_LAUNCH("psroi_bwd_sat");

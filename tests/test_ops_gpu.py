@@ -4,6 +4,7 @@ sm_100a (oracle/_ref/libref_oracle.so) on identical inputs, (iii) the committed 
 Bars: integer outputs (bins, mapping channels, argmax, NMS keep sets) bit-exact; floating point
 within the tolerance written at each assert (north star: 1e-4 relative)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -144,6 +145,26 @@ def test_psroi_integer_tables_other_geometries(oracle, monkeypatch, B, D, H, W):
     monkeypatch.setenv("D2T_PSROI_INT", "0")
     exact, _ = ops.psroi_forward(feat, cu(rois), 7, 7, 1 / 16., 7, D)
     assert float((top - exact).abs().max()) <= l1 * 2.0 ** -30 * 1.05 + 3e-7 * float(exact.abs().max())
+
+
+@pytest.mark.skipif(os.environ.get("D2T_TEST_EXPERIMENTS") != "1",
+                    reason="unmeasured experiment (integer-table backward); run with D2T_TEST_EXPERIMENTS=1")
+def test_psroi_backward_integer_tables_experiment(monkeypatch):
+    """D2T_PSROI_BWD_INT=1 (csrc/psroi.cu, psroi_bwd_isat_mc) against the default fp64 difference tables: every dv is
+    rounded to a multiple of 2^-k with sum |dv| 2^k < 2^30, so a cell covered by n bins is within n 2^-30 sum|dv|."""
+    for B, D, R, shuffle in ((2, 30, 2000, False), (3, 4, 77, True), (1, 2, 5, False)):
+        torch.manual_seed(R)
+        rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
+        gt = torch.randn(rois.size(0), D, 7, 7, device="cuda")
+        shape = (B, D * 49 + 3, 38, 63)
+        monkeypatch.delenv("D2T_PSROI_BWD_INT", raising=False)
+        want = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+        monkeypatch.setenv("D2T_PSROI_BWD_INT", "1")
+        got = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+        monkeypatch.delenv("D2T_PSROI_BWD_INT")
+        assert float(got[:, D * 49:].abs().max()) == 0.0
+        err = float((got - want).abs().max())
+        assert err <= 2e-5 * max(1.0, float(want.abs().max())), err
 
 
 def test_psroi_edge_cases(oracle):
