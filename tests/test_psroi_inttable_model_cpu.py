@@ -77,3 +77,49 @@ def test_integer_table_wraparound_is_harmless():
         hs, ws = rng.randint(1, 30), rng.randint(1, 50)
         he, we = hs + rng.randint(1, 8), ws + rng.randint(1, 12)
         assert lookup(wrapped, hs, he, ws, we) == int(q[hs:he, ws:we].sum())
+
+
+def test_integer_difference_table_backward_model(oracle):
+    """CPU model of psroi_bwd_isat_mc (the opt-in integer-table backward): per item one scale 2^k from sum |dv|, the four
+    corner updates of every bin on a [H+1][Wp] int32 table, row scan over x < W, column scan over h < H, planes * 2^-k.
+    Against the C oracle's backward (the reference's per-cell accumulation): within n 2^-30 sum|dv| for n covering bins."""
+    rng = np.random.RandomState(7)
+    G, D, H, W, B = 7, 2, 38, 63, 2
+    feat_shape = (B, D * G * G, H, W)
+    rois = common.make_rois(40, B, seed=13, shuffle=True)
+    gtop = rng.randn(rois.shape[0], D, G, G).astype(np.float32)
+    want = oracle.psroi_backward(gtop, rois, feat_shape, 1 / 16., G, G, G, D)
+    _, _, bins = oracle.psroi_forward(np.zeros(feat_shape, np.float32), rois, 1 / 16., G, G, G, D, want_bins=True)
+    Wp = (W + 1) | 1
+    got = np.zeros(feat_shape, np.float32)
+    for b in range(B):
+        mine = np.nonzero(rois[:, 0].astype(int) == b)[0]
+        for ctop in range(D):
+            for ph in range(G):
+                dvs = []
+                for n in mine:
+                    for pw in range(G):
+                        hs, he, ws, we = [int(v) for v in bins[n, ph, pw]]
+                        if he > hs and we > ws:
+                            dv = np.float32(gtop[n, ctop, ph, pw]) / np.float32((he - hs) * (we - ws))
+                            dvs.append((pw, hs, he, ws, we, np.float32(dv)))
+                tot = np.float32(sum(abs(float(d[5])) for d in dvs))
+                eb = (np.float32(tot).view(np.uint32) >> 23) & 0xff
+                k = int(156 - int(eb)) if 0 < eb < 255 else 0
+                k = max(-96, min(120, k))
+                T = np.zeros((G, H + 1, Wp), np.int64)
+                for pw, hs, he, ws, we, dv in dvs:
+                    q = int(np.rint(np.float32(dv * np.float32(2.0 ** k))))
+                    T[pw, hs, ws] += q
+                    T[pw, hs, we] -= q
+                    T[pw, he, ws] -= q
+                    T[pw, he, we] += q
+                assert sum(abs(int(np.rint(np.float32(d[5] * np.float32(2.0 ** k))))) for d in dvs) < 2 ** 31
+                T = ((T + 2 ** 31) % 2 ** 32) - 2 ** 31                       # int32 storage
+                P = np.cumsum(np.cumsum(T[:, :H, :W], axis=2), axis=1)       # row scan over x < W, column scan over h < H
+                P = ((P + 2 ** 31) % 2 ** 32) - 2 ** 31
+                c0 = (ctop * G + ph) * G
+                got[b, c0:c0 + G] = (P.astype(np.float32) * np.float32(2.0 ** -k))
+                bound = max(len(dvs), 1) * 2.0 ** -30 * max(float(tot), 1e-30) + 1e-6 * float(np.abs(want[b, c0:c0 + G]).max())
+                assert float(np.abs(got[b, c0:c0 + G] - want[b, c0:c0 + G]).max()) <= bound
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
