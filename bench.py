@@ -18,7 +18,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "pytorch-detect-to-track_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "pytorch-detect-to-track_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -29,6 +29,17 @@ METRIC = "frame-pairs/sec (Res-101 D&T, 600px)"
 H, W = 600, 1000
 PAIRS_PER_GPU = 2
 CLASSES = tuple(range(31))
+
+
+WORKLOAD = ("Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation "
+            "(BASELINE.json configs[1])")
+
+
+def shared_config():
+    """`config` of the JSON line: the same literal dict in both arms (this repo's path and --impl reference)"""
+    return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU,
+            "parallelism": "frame-pairs sharded over ranks, no data-path collective in the eval forward",
+            "l2": "GPU arm: 512 MB buffer rewritten between timed steps (> 126 MB L2); CPU arm: not applicable"}
 
 
 def peaks():
@@ -133,8 +144,8 @@ def time_kernel(fn, iters, flush):
 def op_microbench(flush, hbm_gbs):
     """BASELINE configs[3] and [4] at a fixed batch: PSRoI (the roofline kernel of the metric),
     conv4 correlation, proposal-size NMS.  Algorithmic bytes: SURVEY.md section 8d / DESIGN.md."""
-    import common
     from d2t_b200 import ops
+    from d2t_b200 import synth as common
     from d2t_b200._lib import lib
     out = {}
     B, D, R = 2, 30, 2000
@@ -208,7 +219,7 @@ def op_microbench(flush, hbm_gbs):
     d_info = torch.tensor([600.0, 1000.0, 1.0]).view(1, 1, 3).expand(B_, L_, 3).contiguous().cuda()
     ms_b = time_kernel(lambda: detect.per_class_detections(d_rois, d_prob, d_pred, d_info, thresh=0.05), 10, flush)
     t0 = time.time()
-    common.detect_reference_loop(d_rois, d_prob, d_pred, d_info, 0.05, 0.3, 0)
+    detect.detect_reference_loop(d_rois, d_prob, d_pred, d_info, 0.05, 0.3, 0)
     torch.cuda.synchronize()
     out["detect_postproc_4frames_x30classes"] = {"ms_batched_device": ms_b, "ms_per_class_loop_wall": (time.time() - t0) * 1e3,
                                                  "note": "batched = one sort + gather + d2t_nms_batched over the (frame, class) axis; "
@@ -220,14 +231,14 @@ def op_microbench(flush, hbm_gbs):
     return out
 
 
-def cpu_path_pairs_per_sec(threads, steps, warmup, budget_s=240.0):
-    """The reference's CPU path (oracle/cpu_graph.py) on ONE 600x1000 frame-pair per step."""
+def cpu_path_pairs_per_sec(threads, steps, warmup, budget_s=240.0, pairs=1):
+    """The reference's CPU path (oracle/cpu_graph.py) on `pairs` 600x1000 frame-pairs per step."""
     from oracle import cpu as oracle
     from oracle import cpu_graph
     torch.set_num_threads(threads)
     oracle.lib().oracle_set_threads(threads)
     net = build_net(101)
-    im_data, im_info = make_inputs(1, seed=1)
+    im_data, im_info = make_inputs(pairs, seed=1)
     t0 = time.time()
     cpu_graph.forward_eval(net, im_data, im_info)
     first = time.time() - t0
@@ -241,7 +252,7 @@ def cpu_path_pairs_per_sec(threads, steps, warmup, budget_s=240.0):
         cpu_graph.forward_eval(net, im_data, im_info)
         times.append(time.time() - t0)
     sec = float(np.mean(times))
-    return 1.0 / sec, sec, k_run, w_run + 1
+    return pairs / sec, sec, k_run, w_run + 1
 
 
 def run_reference(args):
@@ -249,17 +260,48 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    value, sec, k_run, w_run = cpu_path_pairs_per_sec(threads, args.steps, args.warmup)
-    sample = "1 frame-pair (2 frames 600x1000) per step, full eval graph on host cores; %d timed steps" % k_run
+    value, sec, k_run, w_run = cpu_path_pairs_per_sec(threads, args.steps, args.warmup, pairs=PAIRS_PER_GPU)
+    sample = "%d frame-pairs (%d frames 600x1000) per step, full eval graph on host cores; %d timed steps" % (
+        PAIRS_PER_GPU, 2 * PAIRS_PER_GPU, k_run)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": args.gpus,
             "steps": k_run, "warmup": w_run, "steps_requested": args.steps, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation",
-                       "pairs_per_step": 1},
+            "config": shared_config(),
             "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def check_finite(outs, what):
+    """a timing of NaN/Inf is not a measurement: fail the run (rc != 0) instead of printing a line"""
+    bad = [i for i, t in enumerate(outs) if isinstance(t, torch.Tensor) and t.is_floating_point() and not bool(torch.isfinite(t).all())]
+    if bad:
+        raise SystemExit("bench.py: non-finite values in %s (outputs %s) -- refusing to report a throughput" % (what, bad))
+
+
+def parity_vs_torch(net, engine, im_dev, info_dev):
+    """One forward of the SAME nn.Module by torch (cuDNN fp32, TF32 off) on the bench inputs, outside every timed region,
+    against the engine's outputs: the line carries the error of the numbers it timed (tests/test_model_gpu.py holds the
+    full check, float64 included)."""
+    N = 2 * im_dev.size(0)
+    out = engine(im_dev, info_dev)
+    frames = im_dev.permute(1, 0, 2, 3, 4).reshape(N, 3, H, W).contiguous()
+    with torch.no_grad():
+        base = net._im_to_head(frames)[3]
+        ref = net(im_dev, info_dev)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    same = (out[0] - ref[0]).abs().amax(-1) < 1e-2
+    sel = same.view(-1)
+    res = {"comparator": "the same nn.Module run by torch (cuDNN fp32, allow_tf32=False) on the bench inputs",
+           "base_feat_max_rel_err": rel(engine.base_feat.to_nchw(), base),
+           "identical_proposals_frac": float(same.float().mean()),
+           "cls_prob_max_abs_err": float((out[1].reshape(-1, out[1].size(-1))[sel] - ref[1].reshape(-1, ref[1].size(-1))[sel]).abs().max()),
+           "bbox_pred_max_rel_err": float((out[2].reshape(-1, 4)[sel] - ref[2].reshape(-1, 4)[sel]).abs().max() / ref[2].abs().max()),
+           "tolerance": 1e-4}
+    res["ok"] = bool(res["base_feat_max_rel_err"] < 1e-4 and res["identical_proposals_frac"] >= 0.98 and
+                     res["cls_prob_max_abs_err"] < 1e-4 and res["bbox_pred_max_rel_err"] < 1e-4)
+    return res
 
 
 def run_b200(args):
@@ -276,9 +318,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the d2t_b200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL_DEBUG is left as the caller set it: fd 1 points at stderr until the JSON line is printed, so NCCL's log
+        # lines cannot land on stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -338,6 +379,7 @@ def run_b200(args):
     barrier()
     my_launches = ops.LAUNCHES - launches0
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    check_finite(step(im_dev, info_dev)[:4], "the eval forward's outputs")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API: every step copies ITS inputs pinned host -> device, runs the forward and
@@ -446,17 +488,20 @@ def run_b200(args):
             cpu_baseline = {"value": v, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
                             "sample": "1 frame-pair (2 frames 600x1000) eval forward x %d on host cores "
                                       "(torch.nn fp32 convs + oracle/ C restatements)" % k_run}
+        parity = parity_vs_torch(net, engine, im_dev, info_dev)
+        if not parity["ok"]:
+            print("bench.py: WARNING parity object outside tolerance: %r" % (parity,), file=sys.stderr)
         ms_per_step = total_ms / args.steps
+        config = shared_config()
         line = {"metric": METRIC, "value": parallel.throughput(pairs, ms_per_step, world), "unit": "frame-pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {16: "fp32 (3xFP16 split tensor-core convs: hi/lo fp16 operand pairs, fp32 accumulate, <= 1e-5 of fp64)",
                           3: "fp32 (3xTF32 tensor-core convs, fp32 accumulate)", 1: "tf32"}[args.passes], "data": "synthetic",
-                "config": {"workload": "Res-101 D&T eval forward, 600x1000 frame-pairs, 300 RoIs/frame, PSRoI + correlation "
-                                       "(BASELINE.json configs[1])",
-                           "pairs_per_gpu": pairs, "global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
-                           "l2": "512 MB buffer rewritten between timed steps",
+                "config": config,
+                "detail": {"global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
                            "convs": engine.conv_backend, "launch": graph_note, "conv_gflop_per_step": engine.conv_flops / 1e9},
+                "parity": parity,
                 "e2e": {"value": world * pairs / (e2e_ms / args.steps / 1e3), "unit": "frame-pairs/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": my_launches, "roofline": roofline, "roofline_psroi": roofline_psroi,
@@ -481,8 +526,8 @@ def run_train(args):
     _saved_stdout = os.dup(1)
     os.dup2(2, 1)
     import torch.distributed as dist
-    import common
     from d2t_b200 import ops, parallel
+    from d2t_b200 import synth as common
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -490,18 +535,18 @@ def run_train(args):
         raise SystemExit("bench.py: no CUDA device; the d2t_b200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     net = build_net(101).cuda()
-    net.train()
     pairs = PAIRS_PER_GPU
-    g = torch.Generator().manual_seed(1 + rank)
-    im = (torch.rand(pairs, 2, 3, H, W, generator=g) * 2.0 - 1.0).cuda()
-    info = torch.tensor([float(H), float(W), 1.0]).view(1, 1, 3).expand(pairs, 2, 3).contiguous().cuda()
+    im, info = make_inputs(pairs, seed=1 + rank)
+    im, info = im.cuda(), info.cuda()
+    # a trained trunk's BatchNorm statistics (the reference fine-tunes a pretrained Res-101, resnet.py:304-309): with the
+    # identity BN of the random init the activations reach 1e7 after 33 residual blocks and the losses overflow
+    common.calibrate_batchnorm(net, make_inputs(1, seed=1)[0].view(2, 3, H, W).cuda())
+    net.train()
     gt = torch.from_numpy(common.make_gt_boxes(pairs, 30, seed=2 + rank, height=H, width=W)).cuda()
     nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
     params = [p for p in net.parameters() if p.requires_grad]
@@ -533,6 +578,7 @@ def run_train(args):
     b.record()
     barrier()
     ms = float(parallel.max_over_ranks(torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64))[0]) / args.steps
+    check_finite([loss.detach()], "the training loss")
     if rank == 0:
         line = {"metric": "training frame-pairs/sec (Res-101 D&T, 600px; fwd + bwd + gradient all-reduce + SGD)",
                 "value": parallel.throughput(pairs, ms, world), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,

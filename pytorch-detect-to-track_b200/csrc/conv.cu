@@ -1154,12 +1154,18 @@ using namespace d2t;
 
 namespace d2t {
 namespace {
-// Per-device stream-K scratch: one fp32 partial tile [128 x 128] and one flag per SM.  Allocated once, at the
-// first plan creation on a device (never on the launch path).  Plans on one device share it, so they must not
-// run concurrently on different streams (the engine runs everything on one stream).
+// Per-device DEFAULT stream-K scratch: one fp32 partial tile [128 x 128] and one flag per SM.  Allocated once, at the
+// first plan creation on a device (never on the launch path).  Plans that were not given a private scratch
+// (d2t_conv_plan_set_scratch; D2TEngine allocates one per engine) share it, and two launches that share it must not
+// overlap: d2t_conv_plan_run therefore keeps the launches on the default scratch STREAM-ORDERED -- when such a plan
+// arrives on another stream than the previous one, the new stream first waits (event) for the previous stream's work,
+// and the whole guard + launch runs under a mutex so that host threads cannot interleave.
 struct SkScratch {
     float* partial = nullptr;
     int* flags = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+    cudaEvent_t ev = nullptr;
 };
 SkScratch g_sk[64];
 std::mutex g_sk_mu;
@@ -1177,6 +1183,7 @@ bool sk_scratch(SkScratch* out) {
         cudaError_t e = cudaMalloc(&g_sk[dev].partial, n * kBlockM * 128 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&g_sk[dev].flags, n * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(g_sk[dev].flags, 0, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_sk[dev].ev, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             set_error("stream-K scratch: %s", cudaGetErrorString(e));
             g_sk[dev] = SkScratch();
@@ -1184,6 +1191,26 @@ bool sk_scratch(SkScratch* out) {
         }
     }
     *out = g_sk[dev];
+    return true;
+}
+
+// (g_sk_mu held) order a launch that uses the device's default scratch after the previous such launch
+bool sk_serialize(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    SkScratch& g = g_sk[dev];
+    if (g.used && g.last_stream != stream && g.ev) {
+        cudaError_t e = cudaEventRecord(g.ev, g.last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, g.ev, 0);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            set_error("conv: cannot order the shared stream-K scratch across streams (%s); give the plan a private scratch "
+                      "(d2t_conv_plan_set_scratch)", cudaGetErrorString(e));
+            return false;
+        }
+    }
+    g.last_stream = stream;
+    g.used = true;
     return true;
 }
 
@@ -1220,6 +1247,7 @@ struct d2t_conv_plan {
     int BN, passes, grid, corr;
     int epi2;                  // 3xFP16, BN = 128: the full-tile output staging / TMA residual variant
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
+    int private_scratch;       // 1: the caller supplied the stream-K scratch (no cross-stream guard needed)
 };
 
 template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false>
@@ -1549,6 +1577,7 @@ extern "C" int d2t_conv_plan_set_scratch(d2t_conv_plan* pl, void* scratch, size_
                 "d2t_conv_plan_set_scratch: need a 16-byte aligned, zero-initialised buffer of d2t_conv_scratch_bytes()");
     pl->args.sk_scratch = reinterpret_cast<float*>(scratch);
     pl->args.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (size_t)sm_count() * kBlockM * 128 * sizeof(float));
+    pl->private_scratch = 1;
     return 1;
 }
 
@@ -1588,8 +1617,17 @@ extern "C" int d2t_conv_plan_info(const d2t_conv_plan* pl, int* out8) {
     return 1;
 }
 
+static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream);
+
 extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
     D2T_REQUIRE(pl, "d2t_conv_plan_run: null plan");
+    if (pl->private_scratch) return conv_plan_dispatch(pl, stream);
+    std::lock_guard<std::mutex> lock(g_sk_mu);       // default scratch: launches stay stream-ordered (see SkScratch)
+    if (!sk_serialize(stream)) return 0;
+    return conv_plan_dispatch(pl, stream);
+}
+
+static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->corr)
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))

@@ -83,3 +83,38 @@ def per_class_detections(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thr
     dets = torch.cat([b, torch.gather(scores, 2, order).unsqueeze(-1)], -1).contiguous()  # [F, C-1, R, 5]
     keep, num = ops.nms_batched(dets.reshape(F * (C - 1), R, 5), float(nms_thresh), n_valid=n_valid.reshape(-1).contiguous())
     return Detections(dets, n_valid, keep.reshape(F, C - 1, -1), num.reshape(F, C - 1), L, B)
+
+
+def detect_reference_loop(rois, cls_prob, bbox_pred, im_info, thresh, nms_thresh, max_per_image):
+    """test_net.py:232-294, frame by frame and class by class (one host round trip per class, like the reference)."""
+    L, B, R, C = cls_prob.shape
+    stds = torch.tensor((0.1, 0.1, 0.2, 0.2), device=rois.device)
+    deltas = (bbox_pred.view(-1, 4) * stds).view(L, B, R, 4)
+    pred = bbox_transform_inv_legs(rois[..., 1:5], deltas)
+    info_lb = im_info.permute(1, 0, 2)
+    for l in range(L):
+        pred[l] = clip_boxes(pred[l], info_lb[l])
+    pred = pred / info_lb[..., 2].reshape(L, B, 1, 1)
+    out = []
+    for l in range(L):
+        for b in range(B):
+            per = [np.zeros((0, 5), np.float32)]
+            for j in range(1, C):
+                inds = torch.nonzero(cls_prob[l, b, :, j] > thresh).view(-1)
+                if inds.numel() > 0:
+                    cls_scores = cls_prob[l, b][inds][:, j]
+                    _, order = torch.sort(cls_scores, dim=0, descending=True, stable=True)
+                    cls_dets = torch.cat([pred[l, b][inds, :], cls_scores.contiguous().view(-1, 1)], 1)[order]
+                    keep = ops.nms(cls_dets.contiguous(), nms_thresh)
+                    per.append(cls_dets[keep.view(-1).long()].cpu().numpy())
+                else:
+                    per.append(np.zeros((0, 5), np.float32))
+            if max_per_image > 0:
+                scores = np.hstack([p[:, -1] for p in per[1:]])
+                if len(scores) > max_per_image:
+                    t = np.sort(scores)[-max_per_image]
+                    per = [p[p[:, -1] >= t] if i else p for i, p in enumerate(per)]
+            out.append(per)
+    return out
+
+

@@ -34,7 +34,7 @@ def _fold_bn(bn):
 
 
 class D2TEngine(object):
-    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=False):
+    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=True):
         dev = next(net.parameters()).device
         self.amax = dc.AmaxArena(1024, dev)       # every activation tensor's running max |x|, zeroed once per forward
         with self.amax:
@@ -47,7 +47,8 @@ class D2TEngine(object):
                 for layer in chain:
                     layer.set_done(prev, self.amax.take().view(torch.int32))
                     prev = layer
-        if private_scratch:    # this engine's conv chain may then overlap another engine's on a different stream
+        if private_scratch:    # (default) this engine's conv chain may overlap any other conv work on a different stream;
+            # plans WITHOUT a private scratch share one per device and are kept stream-ordered by d2t_conv_plan_run
             from ._lib import lib
             self.scratch = torch.zeros(lib().d2t_conv_scratch_bytes(), dtype=torch.uint8, device=dev)
             for layer in [self.stem, self.trk_layer] + self.layers + self.corr_layers:
