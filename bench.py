@@ -434,6 +434,16 @@ def run_b200(args):
     t = parallel.max_over_ranks(torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64))
     total_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- the training step of configs[2] (data-parallel, the path's one collective) on every rank, after the eval numbers
+    train = None
+    if not args.no_train:
+        try:
+            train = train_measure(world, rank, steps=5, warmup=3)
+        except SystemExit:
+            raise
+        except Exception as exc:   # noqa: BLE001 -- the eval line must not be lost to the secondary measurement
+            train = {"error": repr(exc)[:300]}
+
     if rank == 0:
         # ---- the dominant kernel: conv_igemm_tf32 (~85 % of the step, profiles/).  All conv launches of one step
         # (trunk + heads, the engine's own layer list) timed together with CUDA events on the launching stream.
@@ -501,7 +511,7 @@ def run_b200(args):
                 "config": config,
                 "detail": {"global_pairs": world * pairs, "parallelism": "dp%d (pairs sharded, no collective)" % world,
                            "convs": engine.conv_backend, "launch": graph_note, "conv_gflop_per_step": engine.conv_flops / 1e9},
-                "parity": parity,
+                "parity": parity, "train": train,
                 "e2e": {"value": world * pairs / (e2e_ms / args.steps / 1e3), "unit": "frame-pairs/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": my_launches, "roofline": roofline, "roofline_psroi": roofline_psroi,
@@ -516,18 +526,91 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def train_measure(world, rank, steps, warmup):
+    """one data-parallel TRAINING step per iteration on 2 frame-pairs per GPU -- forward in
+    training mode on the tcgen05 engine, target layers + five losses, backward through DgradConv / WgradLayer (tcgen05) and
+    the PSRoI / correlation backward kernels, the bucketed gradient all-reduce (NCCL, the path's one collective) overlapped
+    with backward on a side stream, SGD, on-device weight re-pack (d2t_b200.train.D2TTrainEngine).  Returns the `train`
+    object of the JSON line (device time, max over ranks)."""
+    import torch.distributed as dist
+    from d2t_b200 import ops, parallel
+    from d2t_b200 import synth
+    from d2t_b200.train import D2TTrainEngine
+    net = build_net(101).cuda()
+    pairs = PAIRS_PER_GPU
+    im, info = make_inputs(pairs, seed=1 + rank)
+    im, info = im.cuda(), info.cuda()
+    # a trained trunk's BatchNorm statistics (the reference fine-tunes a pretrained Res-101, resnet.py:304-309): with the
+    # identity BN of the random init the activations reach 1e7 after 33 residual blocks and the losses overflow
+    synth.calibrate_batchnorm(net, make_inputs(1, seed=1)[0].view(2, 3, H, W).cuda())
+    net.train()
+    gt = torch.from_numpy(synth.make_gt_boxes(pairs, 30, seed=2 + rank, height=H, width=W)).cuda()
+    nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
+    engine = D2TTrainEngine(net, pairs, H, W)
+    opt = torch.optim.SGD(engine.params, lr=1e-5, momentum=0.9, weight_decay=1e-4)
+    n_grad = engine.flat.numel()
+
+    def step():
+        out, loss = engine.forward_backward(im, info, gt, nb)
+        opt.step()
+        engine.refresh_weights()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        loss = step()
+    barrier()
+    launches0 = ops.LAUNCHES
+    comm, exposed = [], []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / steps
+    c_ms, e_ms = engine.comm_stats()                               # the last step's buckets
+    t = parallel.max_over_ranks(torch.tensor([ms, c_ms, e_ms], device="cuda", dtype=torch.float64))
+    ms, c_ms, e_ms = float(t[0]), float(t[1]), float(t[2])
+    check_finite([loss.detach()], "the training loss")
+    # phase split (rank-local, one extra step with synchronisation points; not part of the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    with torch.no_grad():
+        i2 = engine._begin(im, info)
+        for layer in engine.layers + engine.corr_layers + [engine.trk_layer]:
+            layer.run()
+    ev[1].record()
+    engine._run_backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    fwd_ms, bwd_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    conv_flops = sum(l.flops for l in engine.layers) + engine.trk_layer.flops
+    return {"metric": "training frame-pairs/sec (Res-101 D&T, 600px; fwd + bwd + gradient all-reduce + SGD)",
+            "value": parallel.throughput(pairs, ms, world), "unit": "frame-pairs/s", "ms_per_step": ms, "steps": steps,
+            "nranks": world, "pairs_per_gpu": pairs, "loss": float(loss), "loss_finite": bool(torch.isfinite(loss)),
+            "collective": "mean all-reduce of %d trainable fp32 gradients (%.0f MB) in %d buckets, NCCL, side stream, issued "
+                          "as each bucket's weight gradients are enqueued" % (n_grad, n_grad * 4 / 1e6, len(engine.buckets)),
+            "allreduce_ms": c_ms, "allreduce_exposed_ms": e_ms,
+            "overlap_frac": (1.0 - e_ms / c_ms) if c_ms > 0 else None,
+            "engine_forward_ms": fwd_ms, "engine_backward_ms": bwd_ms,
+            "heads_losses_optimizer_ms": max(0.0, ms - fwd_ms - bwd_ms),
+            "conv_tflops_useful_fwd": conv_flops / fwd_ms / 1e9,
+            "conv_tflops_useful_bwd": (engine.dgrad_flops + engine.wgrad_flops) / bwd_ms / 1e9,
+            "convs": "d2t_b200 tcgen05 3xFP16: forward, backward-data (DgradConv) and weight-gradient (WgradLayer); PSRoI, "
+                     "correlation, NMS, proposal step: d2t_b200 kernels (forward and backward); losses / target layers / SGD: torch",
+            "bn": "calibrated (trained-looking) BatchNorm statistics, frozen", "gpu_launches": ops.LAUNCHES - launches0}
+
+
 def run_train(args):
-    """Secondary number: one data-parallel TRAINING step per iteration -- forward in training mode
-    (target layers, five losses), backward through the PSRoI / correlation backward kernels, the gradient all-reduce over
-    NCCL (the path's one collective) and the SGD update -- on 2 frame-pairs per GPU.  The trunk convolutions of this
-    mode still run through torch.nn (cuDNN fp32, TF32 off): the tcgen05 engine has no dgrad / wgrad yet, which is why this
-    is not the headline metric."""
     sys.stdout.flush()
     _saved_stdout = os.dup(1)
     os.dup2(2, 1)
     import torch.distributed as dist
-    from d2t_b200 import ops, parallel
-    from d2t_b200 import synth as common
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -538,57 +621,13 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
-    net = build_net(101).cuda()
-    pairs = PAIRS_PER_GPU
-    im, info = make_inputs(pairs, seed=1 + rank)
-    im, info = im.cuda(), info.cuda()
-    # a trained trunk's BatchNorm statistics (the reference fine-tunes a pretrained Res-101, resnet.py:304-309): with the
-    # identity BN of the random init the activations reach 1e7 after 33 residual blocks and the losses overflow
-    common.calibrate_batchnorm(net, make_inputs(1, seed=1)[0].view(2, 3, H, W).cuda())
-    net.train()
-    gt = torch.from_numpy(common.make_gt_boxes(pairs, 30, seed=2 + rank, height=H, width=W)).cuda()
-    nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
-    params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.SGD(params, lr=1e-7, momentum=0.9)
-    n_grad = sum(p.numel() for p in params)
-
-    def step():
-        out = net(im, info, gt, nb)
-        loss = out[4].mean() + out[5].mean() + out[6].mean() + out[7].mean() + out[9].mean()    # trainval_net.py:367-368
-        opt.zero_grad(set_to_none=False)
-        loss.backward()
-        nbk = parallel.allreduce_gradients(params)
-        opt.step()
-        return loss, nbk
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        loss, nbk = step()
-    barrier()
-    launches0 = ops.LAUNCHES
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        loss, nbk = step()
-    b.record()
-    barrier()
-    ms = float(parallel.max_over_ranks(torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64))[0]) / args.steps
-    check_finite([loss.detach()], "the training loss")
+    tr = train_measure(world, rank, args.steps, args.warmup)
     if rank == 0:
-        line = {"metric": "training frame-pairs/sec (Res-101 D&T, 600px; fwd + bwd + gradient all-reduce + SGD)",
-                "value": parallel.throughput(pairs, ms, world), "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32", "data": "synthetic", "mode": "train",
-                "config": {"workload": "Res-101 D&T training step, 600x1000 frame-pairs, 128 RoIs/frame (BASELINE.json configs[2] shape)",
-                           "pairs_per_gpu": pairs, "global_pairs": world * pairs,
-                           "parallelism": "dp%d, one collective: mean all-reduce of %d trainable fp32 gradients in %d buckets (NCCL)" % (world, n_grad, nbk),
-                           "convs": "torch.nn / cuDNN fp32 (TF32 off); PSRoI, correlation, NMS, proposal step: d2t_b200 kernels (forward and backward)"},
-                "loss_finite": bool(torch.isfinite(loss)), "gpu_launches": ops.LAUNCHES - launches0}
+        line = dict(tr)
+        line.update({"n_gpus": world, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "fp32 (3xFP16 split tensor-core convs)", "data": "synthetic", "mode": "train",
+                     "config": {"workload": "Res-101 D&T training step, 600x1000 frame-pairs, 128 RoIs/frame (BASELINE.json "
+                                            "configs[2] shape)", "pairs_per_gpu": PAIRS_PER_GPU}})
         sys.stdout.flush()
         os.dup2(_saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -605,6 +644,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train` object)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the forward's kernels one by one instead of replaying them as a CUDA graph "
                          "(d2t_b200.engine.GraphedEngine; measured 5.82 vs 5.89 ms/step)")

@@ -225,8 +225,9 @@ typedef struct d2t_conv_plan d2t_conv_plan;
 /* out = relu?( scale[c] * conv(in, w) + shift[c] + res ).  scale / shift / res / out / out_nchw may
  * be NULL (at least one output is required); out_nchw is a plain fp32 [N, Cout, OH, OW] copy for
  * consumers that keep the reference's layout.  The plan captures the pointers (TMA tensor maps);
- * buffers must outlive it.  Plans of one device share a small stream-K scratch, so they must not
- * run concurrently on different streams.  Returns NULL on error. */
+ * buffers must outlive it.  Plans of one device share a small stream-K scratch unless given their own
+ * (d2t_conv_plan_set_scratch); d2t_conv_plan_run keeps launches on the shared scratch stream-ordered
+ * (a launch arriving on another stream first waits for the previous one).  Returns NULL on error. */
 d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* desc, const float* in, const void* w_hi,
                                     const void* w_lo, const float* scale, const float* shift,
                                     const float* res, float* out, float* out_nchw);
@@ -269,6 +270,44 @@ d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int 
                                     int max_displacement, int stride, int passes, const float* in1,
                                     const float* in2, float* out, int out_cstride, int out_coffset,
                                     float* out_nchw);
+
+/* ---- Training path of the convolution engine: backward-data and weight-gradient on the same tcgen05 kernel ----
+ * Replaces the cuDNN dgrad / wgrad calls autograd makes for the trainable convolutions of the reference's training step
+ * (trainval_net.py:365-373 over faster_rcnn/resnet.py:66-109, 279-295, rfcn.py:49-53, rpn/rpn.py:28-36); 3xFP16 like
+ * the forward pass (fp32-accurate).
+ *
+ * Backward-data of  y = scale * conv(x, w)  (stride 1) is itself a convolution of dy with the transposed, flipped
+ * filter  wt[ci][r'][s'][co] = w[co][ci][R-1-r'][S-1-s'] * scale[co]  and padding dil*(R-1) - pad:
+ * d2t_conv_pack_weights_f16_dgrad builds wt in the engine's packed format and d2t_conv_plan_create runs it (the
+ * residual input adds the gradient arriving over the skip connection, in place if res == out).
+ * d2t_conv_plan_set_mask fuses the ReLU backward of the tensor whose gradient the plan produces.  A stride-2 1x1
+ * convolution's backward-data runs at the output resolution and is scattered by d2t_upsample2_add_mask.
+ * Packed weights whose scale changes every optimizer step take it from a device scalar (max |w|):
+ * d2t_conv_pack_weights_f16_dev / _dgrad read it, d2t_conv_plan_set_weight_amax makes the kernel read it. */
+int d2t_conv_plan_set_mask(d2t_conv_plan* plan, const float* mask_nhwc, int mask_cstride);
+int d2t_conv_plan_set_weight_amax(d2t_conv_plan* plan, const float* amax_w);
+int d2t_conv_pack_weights_f16_dev(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+                                  const float* amax_w, void* w_hi, void* w_lo, cudaStream_t stream);
+/* (rows >= Cin: rows [Cin, rows) of wt are zero -- the backward-data output may be wider than the forward input) */
+int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float* scale, int Cout, int Cin, int rows, int R, int S,
+                                    int cout_pad, const float* amax_wt, void* wt_hi, void* wt_lo, cudaStream_t stream);
+/* out[n,y,x,:] = mask > 0 ? (y, x even ? low[n,y/2,x/2,:] : 0) + extra[n,y,x,:] : 0  (NHWC, C % 4 == 0, one channel
+ * stride = C; extra / mask / amax_out may be NULL); max |out| is folded into *amax_out */
+int d2t_upsample2_add_mask(const float* low, int LH, int LW, const float* extra, const float* mask, int N, int H,
+                           int W, int C, float* out, float* amax_out, cudaStream_t stream);
+/* Weight gradient  dw[co][ci][r][s] = scale[co] * sum_{n,oy,ox} x[n, ci, oy + r*dil - pad, ox + s*dil - pad] * g[n, co, oy, ox]
+ * as a GEMM with K over the output pixels: both operands are read from channel-major PLANES so that K is contiguous.
+ * d2t_wgrad_pack_input: channels [0, C) of the NHWC input sampled at (oy*stride, ox*stride) -> fp32 planes
+ * [N][C][OH][pitch] (a stride-2 1x1 convolution is a stride-1 one on the sampled positions); d2t_wgrad_pack_grad: the
+ * NHWC gradient -> fp16 planes (hi, lo) of g * 2^k, k from *amax_g.  Pitches in elements (% 4 / % 8). */
+int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
+                         int pitch, float* xt, cudaStream_t stream);
+int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, const float* amax_g,
+                        void* g_hi, void* g_lo, cudaStream_t stream);
+d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, int xt_pitch, int OH, int OW,
+                                     int g_pitch, int R, int S, int pad, int dil, const float* xt,
+                                     const void* g_hi, const void* g_lo, const float* amax_x,
+                                     const float* amax_g, const float* scale, float* dw);
 
 /* OIHW fp32 -> [Cout][R*S][cin_pad] (w, w_lo); w_lo may be NULL */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,

@@ -114,6 +114,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+// 3xFP16 operand scale (conv.cu): sa = 2^ea puts a tensor's max |x| (`amax`, one float in device memory) into
+// [2^14, 2^15) -- the fp16 (hi, lo) split of x * sa then neither overflows nor loses its low bits
+__device__ __forceinline__ int act_exp(const float* amax) {
+    int eb = (int)((__float_as_uint(__ldcg(amax)) >> 23) & 0xffu);
+    eb = eb < 15 ? 15 : (eb > 254 ? 254 : eb);
+    return 141 - eb;
+}
+__device__ __forceinline__ float pow2f(int e) {
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

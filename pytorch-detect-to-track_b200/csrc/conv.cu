@@ -100,6 +100,16 @@ struct ConvArgs {
     const float* amax_in;
     float* amax_out;
     int w_exp;
+    // 3xFP16 with a B operand whose scale lives on the device (weights re-packed every training step, or -- WGRAD -- the
+    // pre-split gradient planes): its max |b| (one float); the packer and this kernel derive the same 2^k from it
+    const float* amax_b;
+    // backward-data: ReLU mask -- out = mask[pixel, channel] > 0 ? value : 0, applied after the residual add (the mask
+    // tensor is the forward activation whose gradient this launch produces; same geometry as the output)
+    const float* mask;
+    int mask_cstride;
+    // WGRAD (see the kernel comment): K blocks per output row, K blocks in total, input channels, OIHW gradient
+    int wg_xblocks, wg_kiters, wg_cin;
+    float* wg_out;
     // optional completion hand-shake between consecutive launches of one chain (d2t_conv_plan_set_done): every CTA adds
     // 1 to *done_self when all its outputs are globally visible; a launch whose done_prev is set polls that counter up
     // to done_target (= the previous launch's grid) INSTEAD of griddepcontrol.wait, i.e. it does not sit through the
@@ -115,17 +125,6 @@ struct ConvArgs {
 #else
 #define EXP(bit) false
 #endif
-
-// activation scale exponent: sa = 2^ea puts the tensor's max |x| into [2^14, 2^15)
-__device__ __forceinline__ int act_exp(const float* amax) {
-    int eb = (int)((__float_as_uint(__ldcg(amax)) >> 23) & 0xffu);
-    eb = eb < 15 ? 15 : (eb > 254 ? 254 : eb);
-    return 141 - eb;
-}
-__device__ __forceinline__ float pow2f(int e) {
-    e = e < -126 ? -126 : (e > 127 ? 127 : e);
-    return __uint_as_float((uint32_t)(e + 127) << 23);
-}
 
 // Work distribution ("stream-K").  A layer is tiles x cpt units, a unit = one K chunk (256 channels x taps) of
 // one output tile.  CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G): every CTA gets the same amount of
@@ -393,7 +392,18 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // (D2T_CONV_PAIR=1 enables them) and kept as the validated cta_group::2 path.  The leader CTA issues the MMAs and owns the
 // `full` / `tempty` / `xempty` barriers (both CTAs' TMA and epilogue warps signal them remotely); its commits
 // are multicast to both CTAs' `empty` / `tfull` barriers.
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2>
+//
+// WGRAD = true (3xFP16 only) is the weight gradient of a stride-1 convolution on the same pipeline,
+//   dW[co, ci, r, s] = scale[co] * sum over (image, oy, ox) of  X[image, ci, oy + r*dil - pad, ox + s*dil - pad] * G[image, co, oy, ox]
+// as the GEMM  D[m = ci, n = co] per filter tap with K running over the output PIXELS.  Both operands are read from
+// PLANAR copies (channel-major planes, row pitch a multiple of 16 bytes) so that K is the contiguous axis, exactly the
+// K-major SWIZZLE_128B tiles the forward pass uses: A = a [128 channels x 64 pixels] fp32 box of X (two 32-pixel TMA
+// boxes; the tap is the box's start coordinate, zero padding the TMA's out-of-bounds fill), split into fp16 (hi, lo) by
+// the converter warps into tensor memory like a forward activation tile; B = [BN channels x 64 pixels] boxes of the
+// gradient's pre-split fp16 (hi, lo) planes (d2t_wgrad_pack).  A K block is 64 consecutive pixels of one output row;
+// tiles are (128 input channels, tap) x (BN output channels); stream-K and the drain are unchanged; the epilogue
+// scales column co by the folded BatchNorm scale and writes the OIHW gradient.
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false>
 __global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
 conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
                 const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
@@ -409,6 +419,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
     static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
+    static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
@@ -429,7 +440,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int unit_id = blockIdx.x / CS, n_units = gridDim.x / CS;
     const int tiles = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;     // (pair-)tiles
-    const int k_iters = p.R * p.S * p.kc_blocks;
+    const int k_iters = WGRAD ? p.wg_kiters : p.R * p.S * p.kc_blocks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -521,6 +532,34 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const Seg sg = sched.get(e);
                 const int t = sg.tile;
                 const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
+                if constexpr (WGRAD) {
+                    // tile = (tap, 128 input channels) x (BN output channels); K block k = 64 pixels of output row
+                    // (image, oy) starting at column 64 * xb
+                    const int RS = p.R * p.S, tap = m_tile % RS, ci0 = (m_tile / RS) * kBlockM;
+                    const int dy = (tap / p.S) * p.dil - p.pad, dx = (tap % p.S) * p.dil - p.pad;
+                    const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                    int xb = k_beg % p.wg_xblocks, oy = (k_beg / p.wg_xblocks) % p.OH, im = k_beg / (p.wg_xblocks * p.OH);
+                    for (int k = k_beg; k < k_end; ++k) {
+                        TRACED_WAIT(0, &empty[stage], phase ^ 1);
+                        uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
+                        uint64_t* fbar = &full[stage];
+                        if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
+                        if (is_a) tma_load_4d(dst, map, fbar, xb * kBlockK + a_c0 + dx, oy + dy, ci0, im);
+                        else tma_load_4d(dst, map, fbar, xb * kBlockK, oy, n_tile * BN, im);
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        if (++xb == p.wg_xblocks) {
+                            xb = 0;
+                            if (++oy == p.OH) {
+                                oy = 0;
+                                ++im;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
                 const int ow0 = tw << p.TW_log2, oh0 = th * p.TH;
                 const int iw0 = ow0 * p.stride - p.pad, ih0 = oh0 * p.stride - p.pad;
@@ -771,7 +810,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         const int hl = m >> p.TW_log2, wl = m & (TW - 1);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         // 3xFP16: the accumulator holds (x * 2^ea) . (w * 2^w_exp); the drain undoes both (exact: fma by a power of two)
-        const float descale = F16 ? pow2f(-(act_exp(p.amax_in) + p.w_exp)) : 1.f;
+        const float descale = F16 ? pow2f(-(act_exp(p.amax_in) + (p.amax_b ? act_exp(p.amax_b) : p.w_exp))) : 1.f;
         int local = 0, cbuf = 0;
         uint32_t cphase = 0, rphase = 0;
         TRACE_DECL;
@@ -800,7 +839,10 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
             const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
             const int oh = th * p.TH + hl, ow = (tw << p.TW_log2) + wl;
-            const bool pix_ok = oh < p.OH && ow < p.OW && img < p.N;   // (a pair's second tile may not exist)
+            // WGRAD: tile row m = input channel ci0 + m of filter tap `tap` (tiles_w = tiles_h = 1 there)
+            const int wg_rs = WGRAD ? p.R * p.S : 1, wg_tap = m_tile % wg_rs, wg_ci = (m_tile / wg_rs) * kBlockM + m;
+            const bool pix_ok = WGRAD ? wg_ci < p.wg_cin
+                                      : (oh < p.OH && ow < p.OW && img < p.N);   // (a pair's second tile may not exist)
             const size_t pix = ((size_t)img * p.OH + oh) * p.OW + ow;
             const int n0 = n_tile * BN;
             // EPI2: the residual tile is requested NOW -- before the accumulator is even complete -- as bulk tensor
@@ -972,6 +1014,31 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if constexpr (WGRAD) {
+                    if (pix_ok) {       // dW[co][ci][tap], co = ch0 + j
+                        const size_t cs = (size_t)p.wg_cin * wg_rs;
+                        float* o = p.wg_out + ((size_t)ch0 * p.wg_cin + wg_ci) * wg_rs + wg_tap;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (full16 || ch0 + j < p.Cout) o[j * cs] = v[j];
+                    }
+                    continue;
+                }
+                if (p.mask && pix_ok) {                      // backward-data: ReLU mask of the forward activation
+                    const float* mr = p.mask + pix * p.mask_cstride + ch0;
+                    if (full16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(mr + j));
+                            v[j] = a.x > 0.f ? v[j] : 0.f; v[j + 1] = a.y > 0.f ? v[j + 1] : 0.f;
+                            v[j + 2] = a.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = a.w > 0.f ? v[j + 3] : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < p.Cout) v[j] = __ldg(mr + j) > 0.f ? v[j] : 0.f;
+                    }
                 }
                 if (p.amax_out && pix_ok) {
                     if (full16) {
@@ -1248,13 +1315,14 @@ struct d2t_conv_plan {
     int epi2;                  // 3xFP16, BN = 128: the full-tile output staging / TMA residual variant
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
     int private_scratch;       // 1: the caller supplied the stream-K scratch (no cross-stream guard needed)
+    int wgrad;                 // weight-gradient plan (d2t_wgrad_plan_create)
 };
 
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false>
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false, bool WGRAD = false>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
@@ -1282,7 +1350,7 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
                                    pl->tmR, args),
                 "conv_igemm launch");
     return 1;
@@ -1568,6 +1636,90 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     return pl;
 }
 
+
+// Weight gradient of a stride-1 convolution (see the WGRAD kernel comment).  xt: planar fp32 [N][Cin][xh][xt_pitch] (the
+// forward input; for a strided 1x1 conv the caller packs the sub-sampled positions, d2t_wgrad_pack_input); g_hi / g_lo:
+// planar fp16 [N][Cout][OH][g_pitch] = the (hi, lo) split of G * 2^k, k derived from *amax_g (d2t_wgrad_pack_grad);
+// dw: OIHW fp32 [Cout][Cin][R][S], every element written (no accumulation).  Pitches in elements: xt_pitch % 4 == 0,
+// g_pitch % 8 == 0.  amax_x / amax_g: the device scalars holding max |X| and max |G|.
+extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, int xt_pitch, int OH, int OW,
+                                                int g_pitch, int R, int S, int pad, int dil, const float* xt,
+                                                const void* g_hi, const void* g_lo, const float* amax_x,
+                                                const float* amax_g, const float* scale, float* dw) {
+    if (N <= 0 || Cin <= 0 || Cout <= 0 || xh <= 0 || xw <= 0 || OH <= 0 || OW <= 0 || R <= 0 || S <= 0 || pad < 0 ||
+        dil <= 0 || !xt || !g_hi || !g_lo || !amax_x || !amax_g || !dw || xt_pitch % 4 != 0 || xt_pitch < xw ||
+        g_pitch % 8 != 0 || g_pitch < OW) {
+        set_error("d2t_wgrad_plan_create: bad arguments");
+        return nullptr;
+    }
+    if (OH != xh + 2 * pad - dil * (R - 1) || OW != xw + 2 * pad - dil * (S - 1)) {
+        set_error("d2t_wgrad_plan_create: output geometry does not match a stride-1 convolution of the input");
+        return nullptr;
+    }
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(d2t_conv_plan)) != 0) {
+        set_error("d2t_wgrad_plan_create: out of memory");
+        return nullptr;
+    }
+    d2t_conv_plan* pl = new (mem) d2t_conv_plan();
+    ConvArgs& a = pl->args;
+    constexpr int KB = kblk_of(16);                          // 64 pixels per K block
+    a.N = N; a.OH = OH; a.OW = OW; a.Cout = Cout;
+    a.R = R; a.S = S; a.stride = 1; a.pad = pad; a.dil = dil;
+    a.kc_blocks = 1; a.TW_log2 = 7; a.TH = 1; a.stem = 0;
+    a.tiles_w = 1; a.tiles_h = 1;
+    a.m_tiles = ((Cin + kBlockM - 1) / kBlockM) * R * S;
+    pl->BN = Cout <= 64 ? 64 : 128;
+    a.n_tiles = (Cout + pl->BN - 1) / pl->BN;
+    a.scale = scale; a.shift = nullptr; a.res = nullptr; a.res_cstride = 0; a.relu = 0;
+    a.out = nullptr; a.out_nchw = nullptr; a.out_cstride = 0; a.out_coffset = 0;
+    a.amax_in = amax_x; a.amax_b = amax_g; a.amax_out = nullptr; a.w_exp = 0;
+    a.wg_xblocks = (OW + KB - 1) / KB;
+    a.wg_kiters = N * OH * a.wg_xblocks;
+    a.wg_cin = Cin; a.wg_out = dw;
+    pl->passes = 16; pl->corr = 0; pl->pair = 0; pl->epi2 = 0; pl->wgrad = 1;
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.wg_kiters, 16);
+    SkScratch sk;
+    if (!sk_scratch(&sk)) {
+        free(pl);
+        return nullptr;
+    }
+    a.sk_scratch = sk.partial; a.sk_flags = sk.flags; a.sk_epoch = 0;
+    // A: planes of X, dims innermost first {x, y, channel, image}; box = 32 pixels of one row x 128 channels
+    const cuuint64_t adims[4] = {(cuuint64_t)xw, (cuuint64_t)xh, (cuuint64_t)Cin, (cuuint64_t)N};
+    const cuuint64_t astr[3] = {(cuuint64_t)xt_pitch * 4, (cuuint64_t)xh * xt_pitch * 4, (cuuint64_t)Cin * xh * xt_pitch * 4};
+    const cuuint32_t abox[4] = {(cuuint32_t)kBoxC, 1u, (cuuint32_t)kBlockM, 1u};
+    // B: planes of G (fp16), box = 64 pixels of one row x BN channels
+    const cuuint64_t bdims[4] = {(cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)Cout, (cuuint64_t)N};
+    const cuuint64_t bstr[3] = {(cuuint64_t)g_pitch * 2, (cuuint64_t)OH * g_pitch * 2, (cuuint64_t)Cout * OH * g_pitch * 2};
+    const cuuint32_t bbox[4] = {(cuuint32_t)KB, 1u, (cuuint32_t)pl->BN, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    bool ok = encode(&pl->tmA, xt, 4, adims, astr, abox, estr, "wgrad A") &&
+              encode(&pl->tmB_hi, g_hi, 4, bdims, bstr, bbox, estr, "wgrad B hi", true) &&
+              encode(&pl->tmB_lo, g_lo, 4, bdims, bstr, bbox, estr, "wgrad B lo", true);
+    pl->tmO = pl->tmA;
+    pl->tmR = pl->tmA;
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
+extern "C" int d2t_conv_plan_set_mask(d2t_conv_plan* pl, const float* mask, int mask_cstride) {
+    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && (!mask || (mask_cstride % 4 == 0 && mask_cstride >= pl->args.Cout)),
+                "d2t_conv_plan_set_mask: needs a convolution plan and a mask with a channel stride that is a multiple of 4");
+    pl->args.mask = mask;
+    pl->args.mask_cstride = mask_cstride;
+    return 1;
+}
+
+extern "C" int d2t_conv_plan_set_weight_amax(d2t_conv_plan* pl, const float* amax_w) {
+    D2T_REQUIRE(pl && pl->passes == 16 && !pl->corr, "d2t_conv_plan_set_weight_amax: needs a 3xFP16 convolution plan");
+    pl->args.amax_b = amax_w;
+    return 1;
+}
+
 extern "C" size_t d2t_conv_scratch_bytes(void) {
     return (size_t)sm_count() * kBlockM * 128 * sizeof(float) + (size_t)sm_count() * sizeof(int);
 }
@@ -1628,6 +1780,9 @@ extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
 }
 
 static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
+    if (pl->wgrad)
+        return pl->BN == 64 ? launch_conv<64, 16, false, false, false, true>(pl, stream)
+                            : launch_conv<128, 16, false, false, false, true>(pl, stream);
     if (pl->corr)
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))

@@ -134,6 +134,111 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in, int N, int H, in
     }
 }
 
+
+// ---------------------------------------------------------------- training-path helpers (backward-data / weight-gradient)
+// OIHW -> forward layout [O][R*S][cin_pad] fp16 (hi, lo) of w * 2^k, k derived on the device from *amax (= max |w|, kept
+// by the caller): the per-step re-pack of a weight that the optimizer has just changed needs no host round trip
+__global__ void pack_weights_f16_dev(const float* __restrict__ w, int O, int I, int R, int S, int cin_pad,
+                                     const float* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float sw = pow2f(act_exp(amax));
+    const size_t total = (size_t)O * R * S * cin_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cin_pad);
+        const int rs = (int)((idx / cin_pad) % (R * S));
+        const int o = (int)(idx / cin_pad / (R * S));
+        const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) * sw : 0.f;
+        const __half h = __float2half_rn(v);
+        hi[idx] = h;
+        lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+// OIHW -> the backward-data operand [I][R*S][cout_pad]: the transposed, spatially flipped filter with the folded
+// BatchNorm scale of the OUTPUT channel multiplied in,  wt[ci][r'][s'][co] = w[co][ci][R-1-r'][S-1-s'] * scale[co],
+// fp16 (hi, lo) of wt * 2^k with k from *amax (an upper bound of max |wt|)
+__global__ void pack_weights_f16_dgrad(const float* __restrict__ w, const float* __restrict__ scale, int O, int I, int rows,
+                                       int R, int S, int cout_pad, const float* __restrict__ amax,
+                                       __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float sw = pow2f(act_exp(amax));
+    const size_t total = (size_t)rows * R * S * cout_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx % cout_pad);
+        const int rs = (int)((idx / cout_pad) % (R * S));
+        const int i = (int)(idx / cout_pad / (R * S));
+        float v = 0.f;
+        if (o < O && i < I) {
+            v = __ldg(w + ((size_t)o * I + i) * R * S + (R * S - 1 - rs)) * sw;
+            if (scale) v *= __ldg(scale + o);
+        }
+        const __half h = __float2half_rn(v);
+        hi[idx] = h;
+        lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+// channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> planes [N][C][OH][pitch] (columns
+// [OW, pitch) zero): the K-contiguous operand layout of the weight-gradient GEMM.  SPLIT: fp16 (hi, lo) planes of
+// x * 2^k (k from *amax) instead of fp32.  32 x 32 shared-memory transpose per (image, output row).
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, int stride, int OH, int OW, int pitch,
+               const float* __restrict__ amax, float* __restrict__ out, __half* __restrict__ out_hi,
+               __half* __restrict__ out_lo) {
+    __shared__ float tile[32][33];
+    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float sa = SPLIT ? pow2f(act_exp(amax)) : 1.f;
+    for (int j = ty; j < 32; j += 8) {
+        const int xo = wt + j, c = ct + tx;
+        tile[j][tx] = (xo < OW && c < C) ? __ldg(x + (((size_t)n * H + (size_t)oy * stride) * W + (size_t)xo * stride) * cs + c) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = ct + j, xo = wt + tx;
+        if (c < C && xo < pitch) {
+            const size_t o = (((size_t)n * C + c) * OH + oy) * pitch + xo;
+            const float v = tile[tx][j] * sa;
+            if (SPLIT) {
+                const __half h = __float2half_rn(v);
+                out_hi[o] = h;
+                out_lo[o] = __float2half_rn(v - __half2float(h));
+            } else {
+                out[o] = v;
+            }
+        }
+    }
+}
+
+// backward of a stride-2 1x1 convolution's input + ReLU:  out[n, y, x, :] = mask > 0 ? (even(y, x) ? low[n, y/2, x/2, :] : 0)
+// + extra[n, y, x, :] : 0, all NHWC with the same channel stride; max |out| folded into *amax
+__global__ void upsample2_add_mask(const float4* __restrict__ low, int LH, int LW, const float4* __restrict__ extra,
+                                   const float4* __restrict__ mask, int N, int H, int W, int C4, float4* __restrict__ out,
+                                   float* __restrict__ amax) {
+    const size_t total = (size_t)N * H * W * C4;
+    float m = 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        const int x = (int)((idx / C4) % W), y = (int)((idx / C4 / W) % H), n = (int)(idx / C4 / W / H);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(x & 1) && !(y & 1) && (y >> 1) < LH && (x >> 1) < LW)
+            v = __ldg(low + (((size_t)n * LH + (y >> 1)) * LW + (x >> 1)) * C4 + c4);
+        if (extra) {
+            const float4 e = __ldg(extra + idx);
+            v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        }
+        if (mask) {
+            const float4 k = __ldg(mask + idx);
+            v.x = k.x > 0.f ? v.x : 0.f; v.y = k.y > 0.f ? v.y : 0.f; v.z = k.z > 0.f ? v.z : 0.f; v.w = k.w > 0.f ? v.w : 0.f;
+        }
+        out[idx] = v;
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (amax) {
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if ((threadIdx.x & 31) == 0 && wm != 0u) atomicMax(reinterpret_cast<unsigned int*>(amax), wm);
+    }
+}
+
 }  // namespace
 }  // namespace d2t
 
@@ -180,6 +285,72 @@ extern "C" int d2t_conv_pack_weights_f16(const float* w_oihw, int Cout, int Cin,
     pack_weights_f16<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, ldexpf(1.f, w_exp),
                                                           reinterpret_cast<__half*>(w_hi), reinterpret_cast<__half*>(w_lo));
     D2T_CHECK_LAUNCH("pack_weights_f16");
+    return 1;
+}
+
+
+extern "C" int d2t_conv_pack_weights_f16_dev(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+                                             const float* amax_w, void* w_hi, void* w_lo, cudaStream_t stream) {
+    D2T_REQUIRE(w_oihw && w_hi && w_lo && amax_w && Cout > 0 && Cin > 0 && R > 0 && S > 0 && cin_pad >= Cin && cin_pad % 64 == 0,
+                "d2t_conv_pack_weights_f16_dev: bad arguments");
+    const size_t total = (size_t)Cout * R * S * cin_pad;
+    pack_weights_f16_dev<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, amax_w,
+                                                              reinterpret_cast<__half*>(w_hi), reinterpret_cast<__half*>(w_lo));
+    D2T_CHECK_LAUNCH("pack_weights_f16_dev");
+    return 1;
+}
+
+extern "C" int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float* scale, int Cout, int Cin, int rows, int R,
+                                               int S, int cout_pad, const float* amax_wt, void* wt_hi, void* wt_lo,
+                                               cudaStream_t stream) {
+    D2T_REQUIRE(w_oihw && wt_hi && wt_lo && amax_wt && Cout > 0 && Cin > 0 && rows >= Cin && R > 0 && S > 0 &&
+                    cout_pad >= Cout && cout_pad % 64 == 0,
+                "d2t_conv_pack_weights_f16_dgrad: bad arguments");
+    const size_t total = (size_t)rows * R * S * cout_pad;
+    pack_weights_f16_dgrad<<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, Cout, Cin, rows, R, S, cout_pad, amax_wt,
+                                                                reinterpret_cast<__half*>(wt_hi), reinterpret_cast<__half*>(wt_lo));
+    D2T_CHECK_LAUNCH("pack_weights_f16_dgrad");
+    return 1;
+}
+
+static int planes_launch(bool split, const float* x, int N, int H, int W, int cs, int C, int stride, int OH, int OW, int pitch,
+                         const float* amax, float* out, void* hi, void* lo, cudaStream_t stream) {
+    D2T_REQUIRE(x && N > 0 && H > 0 && W > 0 && C > 0 && cs >= C && stride > 0 && OH > 0 && OW > 0 && pitch >= OW &&
+                    (OH - 1) * stride < H && (OW - 1) * stride < W,
+                "d2t_wgrad_pack: bad arguments");
+    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack: tensor too large for the launch grid");
+    if (split)
+        nhwc_to_planes<true><<<grid, 256, 0, stream>>>(x, N, H, W, cs, C, stride, OH, OW, pitch, amax, nullptr,
+                                                       reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo));
+    else
+        nhwc_to_planes<false><<<grid, 256, 0, stream>>>(x, N, H, W, cs, C, stride, OH, OW, pitch, nullptr, out, nullptr, nullptr);
+    D2T_CHECK_LAUNCH("nhwc_to_planes");
+    return 1;
+}
+
+extern "C" int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
+                                    int pitch, float* xt, cudaStream_t stream) {
+    D2T_REQUIRE(xt && pitch % 4 == 0, "d2t_wgrad_pack_input: needs an output buffer and a row pitch that is a multiple of 4");
+    return planes_launch(false, x, N, H, W, c_stride, C, stride, OH, OW, pitch, nullptr, xt, nullptr, nullptr, stream);
+}
+
+extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, const float* amax_g,
+                                   void* g_hi, void* g_lo, cudaStream_t stream) {
+    D2T_REQUIRE(g_hi && g_lo && amax_g && pitch % 8 == 0, "d2t_wgrad_pack_grad: needs output planes, amax and a row pitch that is a multiple of 8");
+    return planes_launch(true, g, N, OH, OW, c_stride, C, 1, OH, OW, pitch, amax_g, nullptr, g_hi, g_lo, stream);
+}
+
+extern "C" int d2t_upsample2_add_mask(const float* low, int LH, int LW, const float* extra, const float* mask, int N, int H,
+                                      int W, int C, float* out, float* amax_out, cudaStream_t stream) {
+    D2T_REQUIRE(low && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && LH == (H + 1) / 2 && LW == (W + 1) / 2,
+                "d2t_upsample2_add_mask: bad arguments (C % 4 == 0, low = ceil(full / 2))");
+    const size_t total = (size_t)N * H * W * (C / 4);
+    upsample2_add_mask<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<const float4*>(low), LH, LW,
+                                                            reinterpret_cast<const float4*>(extra),
+                                                            reinterpret_cast<const float4*>(mask), N, H, W, C / 4,
+                                                            reinterpret_cast<float4*>(out), amax_out);
+    D2T_CHECK_LAUNCH("upsample2_add_mask");
     return 1;
 }
 

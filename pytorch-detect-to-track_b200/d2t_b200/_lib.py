@@ -75,6 +75,15 @@ _SIGS = {
     "d2t_stem_pack_weights": (_i, [_p, _i, _i, _p, _p, _p]),
     "d2t_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "d2t_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    # ---- training path (backward-data / weight-gradient)
+    "d2t_conv_plan_set_mask": (_i, [_p, _p, _i]),
+    "d2t_conv_plan_set_weight_amax": (_i, [_p, _p]),
+    "d2t_conv_pack_weights_f16_dev": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "d2t_conv_pack_weights_f16_dgrad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "d2t_upsample2_add_mask": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_wgrad_pack_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "d2t_wgrad_pack_grad": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "d2t_wgrad_plan_create": (_p, [_i] * 13 + [_p] * 7),
 }
 
 _OPTIONAL = set()

@@ -183,17 +183,31 @@ class ConvLayer(_Planned):
     """out = relu?(scale * conv(x, w) + shift + residual) bound to fixed input / output buffers."""
 
     def __init__(self, x, weight, scale=None, shift=None, stride=1, pad=0, dil=1, relu=False, residual=None,
-                 passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False, out_nchw=None):
+                 passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False, out_nchw=None, amax_w=None,
+                 packed=None, mask=None):
+        """amax_w: one-element CUDA float tensor holding max |weight| -- the weights are then (re)packed on the device from
+        it (``repack()``, no host round trip: a training loop calls it after every optimizer step) and the kernel reads the
+        scale from the same scalar.  packed = (hi, lo): operand matrices packed by the caller (backward-data, with amax_w);
+        `weight` then only gives the geometry [O, I, R, S].  mask: ActTensor shaped like the output; out = mask > 0 ? . : 0."""
         O, I, R, S = weight.shape
         if _pad32(I) > x.cstride:
             raise ValueError("input buffer has %d channels per pixel, conv needs %d" % (x.cstride, _pad32(I)))
-        self.x, self.residual = x, residual
+        self.x, self.residual, self.mask = x, residual, mask
+        self.weight, self.amax_w = weight, amax_w
         w_exp = 0
-        if passes == 16:
+        if packed is not None:
+            assert passes == 16 and amax_w is not None
+            self.w_hi, self.w_lo = packed
+        elif amax_w is not None:
+            assert passes == 16, "device-side weight scales are a 3xFP16 feature"
+            self.w_hi = torch.empty(O, R * S * _pad64(I), device=weight.device, dtype=torch.float16)
+            self.w_lo = torch.empty_like(self.w_hi)
+            self.repack()
+        elif passes == 16:
             self.w_hi, self.w_lo, w_exp = pack_weights_f16(weight, _pad64(I))
         else:
             self.w_hi, self.w_lo = pack_weights(weight, _pad32(I), lo=(passes == 3))
-        dev = weight.device
+        dev = x.x.device
         self.scale = scale.detach().float().contiguous().to(dev) if scale is not None else None
         self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
         OH = (x.H + 2 * pad - dil * (R - 1) - 1) // stride + 1
@@ -216,10 +230,115 @@ class ConvLayer(_Planned):
         self.info = dict(zip(("OH", "OW", "tile_h", "tile_w", "BN", "m_tiles", "n_tiles", "grid"), list(info)))
         self.flops = 2.0 * x.N * OH * OW * O * I * R * S
         self._bind_amax(x, self.out)
+        if amax_w is not None:
+            check(lib().d2t_conv_plan_set_weight_amax(self.plan, _p(amax_w)), "d2t_conv_plan_set_weight_amax")
+        if mask is not None:
+            assert (mask.N, mask.H, mask.W) == (x.N, OH, OW) and mask.cstride >= O
+            check(lib().d2t_conv_plan_set_mask(self.plan, _p(mask.x), mask.cstride), "d2t_conv_plan_set_mask")
+
+    def repack(self):
+        """re-derive the packed fp16 operand pair from the current values of `weight` (scale from *amax_w)"""
+        O, I, R, S = self.weight.shape
+        w = self.weight.detach()
+        assert w.is_contiguous() and w.dtype == torch.float32
+        check(lib().d2t_conv_pack_weights_f16_dev(w.data_ptr(), O, I, R, S, _pad64(I), _p(self.amax_w), _p(self.w_hi),
+                                                  _p(self.w_lo), _stream()), "d2t_conv_pack_weights_f16_dev")
+        ops._count(1)
 
     def run(self, stream=None):
         _Planned.run(self, stream)
         return self.out if self.out is not None else self.out_nchw
+
+
+class DgradConv(ConvLayer):
+    """Backward-data of  y = scale * conv(x, weight)  (stride 1: a strided 1x1 convolution is run at the output
+    resolution and scattered by ``upsample2_add_mask``):  out = mask > 0 ? conv(g, wt) + residual : 0  with
+    wt[ci][r'][s'][co] = weight[co][ci][R-1-r'][S-1-s'] * scale[co], padding dil * (R - 1) - pad, on the same tcgen05
+    kernel.  `amax_wt`: one-element CUDA float tensor >= max |wt| (the caller keeps it current); ``repack()`` after
+    every optimizer step.  `out_channels` >= Cin widens the output with zero channels (a padded forward input)."""
+
+    def __init__(self, g, weight, scale, pad, dil, amax_wt, out=None, residual=None, mask=None, out_channels=None):
+        O, I, R, S = weight.shape
+        rows = out_channels if out_channels is not None else I
+        self.fwd_weight, self.fwd_scale, self.rows = weight, (scale.detach().float().contiguous() if scale is not None else None), rows
+        self.amax_w = amax_wt
+        hi = torch.empty(rows, R * S * _pad64(O), device=weight.device, dtype=torch.float16)
+        lo = torch.empty_like(hi)
+        self.w_hi, self.w_lo = hi, lo
+        self.repack()
+        geom = torch.empty(rows, O, R, S, device="meta")              # [O', I', R, S] of the equivalent forward conv
+        ConvLayer.__init__(self, g, geom, None, None, 1, dil * (R - 1) - pad, dil, False, residual, passes=16, out=out,
+                           amax_w=amax_wt, packed=(hi, lo), mask=mask)
+
+    def repack(self):
+        O, I, R, S = self.fwd_weight.shape
+        w = self.fwd_weight.detach()
+        check(lib().d2t_conv_pack_weights_f16_dgrad(w.data_ptr(), _p(self.fwd_scale), O, I, self.rows, R, S, _pad64(O),
+                                                    _p(self.amax_w), _p(self.w_hi), _p(self.w_lo), _stream()),
+              "d2t_conv_pack_weights_f16_dgrad")
+        ops._count(1)
+
+
+class WgradScratch(object):
+    """The weight-gradient GEMM reads both operands from channel-major planes (csrc/conv.cu, WGRAD): one reusable pair of
+    plane buffers, sized for the largest layer, shared by every WgradLayer of an engine (plans run one after another)."""
+
+    def __init__(self, x_floats, g_halfs, device="cuda"):
+        self.xt = torch.zeros(x_floats, device=device)
+        self.g_hi = torch.zeros(g_halfs, device=device, dtype=torch.float16)
+        self.g_lo = torch.zeros(g_halfs, device=device, dtype=torch.float16)
+
+    @staticmethod
+    def need(x, g, stride):
+        return x.N * x.C * g.H * _pad32(g.W), g.N * g.C * g.H * _pad32(g.W)
+
+
+class WgradLayer(_Planned):
+    """grad_w [O, I, R, S] = scale[o] * sum_pixels x (*) g  for  y = scale * conv(x, w, stride, pad, dil):  x the forward
+    input (ActTensor), g the gradient w.r.t. the convolution's pre-activation output (ActTensor, amax current).  Three
+    launches: plane packs of x and g, then the tcgen05 GEMM, which writes every element of `grad_w`."""
+
+    def __init__(self, x, g, grad_w, scale, stride, pad, dil, scratch, cin=None):
+        O, I, R, S = grad_w.shape
+        assert grad_w.is_contiguous() and grad_w.dtype == torch.float32
+        assert stride == 1 or (R == 1 and S == 1 and pad == 0), "strided convolutions: 1x1 only"
+        self.x, self.g, self.grad_w, self.stride = x, g, grad_w, stride
+        self.scale = scale.detach().float().contiguous() if scale is not None else None
+        self.xh, self.xw = (g.H, g.W) if stride > 1 else (x.H, x.W)
+        self.xp, self.gp = _pad32(self.xw), _pad32(g.W)
+        self.scratch = scratch
+        nx, ng = x.N * I * self.xh * self.xp, g.N * O * g.H * self.gp
+        if nx > scratch.xt.numel() or ng > scratch.g_hi.numel():
+            raise ValueError("WgradScratch too small: need %d floats / %d halfs" % (nx, ng))
+        self.plan = lib().d2t_wgrad_plan_create(x.N, I, O, self.xh, self.xw, self.xp, g.H, g.W, self.gp, R, S, pad, dil,
+                                                _p(scratch.xt), _p(scratch.g_hi), _p(scratch.g_lo), _p(x.amax), _p(g.amax),
+                                                _p(self.scale), _p(grad_w))
+        if not self.plan:
+            raise D2TError("d2t_wgrad_plan_create failed: %s" % lib().d2t_last_error().decode())
+        self.flops = 2.0 * g.N * g.H * g.W * O * I * R * S
+
+    def run(self, stream=None):
+        x, g, sc = self.x, self.g, self.scratch
+        O, I = self.grad_w.shape[:2]
+        st = _stream() if stream is None else stream
+        check(lib().d2t_wgrad_pack_input(_p(x.x), x.N, x.H, x.W, x.cstride, I, self.stride, self.xh, self.xw, self.xp,
+                                         _p(sc.xt), st), "d2t_wgrad_pack_input")
+        check(lib().d2t_wgrad_pack_grad(_p(g.x), g.N, g.H, g.W, g.cstride, O, self.gp, _p(g.amax), _p(sc.g_hi), _p(sc.g_lo),
+                                        st), "d2t_wgrad_pack_grad")
+        check(lib().d2t_conv_plan_run(self.plan, st), "d2t_conv_plan_run")
+        ops._count(3)
+        return self.grad_w
+
+
+def upsample2_add_mask(low, out, extra=None, mask=None):
+    """out = mask > 0 ? (even positions: low) + extra : 0; max |out| -> out.amax (csrc/conv_util.cu)"""
+    assert out.cstride == out.C == low.cstride and (extra is None or extra.cstride == out.cstride)
+    assert mask is None or mask.cstride == out.cstride
+    check(lib().d2t_upsample2_add_mask(_p(low.x), low.H, low.W, _p(extra.x) if extra is not None else None,
+                                       _p(mask.x) if mask is not None else None, out.N, out.H, out.W, out.C, _p(out.x),
+                                       _p(out.amax), _stream()), "d2t_upsample2_add_mask")
+    ops._count(1)
+    return out
 
 
 class StemConv(_Planned):

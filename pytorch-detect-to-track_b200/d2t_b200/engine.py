@@ -34,9 +34,11 @@ def _fold_bn(bn):
 
 
 class D2TEngine(object):
+    AMAX_SLOTS = 1024
+
     def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=True):
         dev = next(net.parameters()).device
-        self.amax = dc.AmaxArena(1024, dev)       # every activation tensor's running max |x|, zeroed once per forward
+        self.amax = dc.AmaxArena(self.AMAX_SLOTS, dev)       # every activation tensor's running max |x|, zeroed once per forward
         with self.amax:
             self._build(net, pairs, height, width, passes, cfg_key, keep_features)
         if os.environ.get("D2T_CONV_DONE") == "1":
@@ -105,11 +107,8 @@ class D2TEngine(object):
         self.trk_in = dc.ActTensor(pairs, bf.H, bf.W, self.trk_cin, cstride=(self.trk_cin + 31) // 32 * 32, device=dev)
         self.bbox_map = torch.empty(N, n_loc, bf.H, bf.W, device=dev)
         for leg in (0, 1):   # one plan per leg: NHWC into its channel slice of the concat buffer + NCHW for PSRoI
-            layer = dc.ConvLayer(bf.batch_slice(leg * pairs, (leg + 1) * pairs), bn_.weight, None, bn_.bias, passes=passes,
-                                 out=self.trk_in, out_coffset=leg * n_loc,
-                                 out_nchw=self.bbox_map[leg * pairs:(leg + 1) * pairs])
-            self.layers.append(layer)
-            self.conv_flops += layer.flops
+            self._conv(bf.batch_slice(leg * pairs, (leg + 1) * pairs), bn_.weight, None, bn_.bias, out=self.trk_in,
+                       out_coffset=leg * n_loc, out_nchw=self.bbox_map[leg * pairs:(leg + 1) * pairs])
         # ---- RPN head
         rpn = net.RFCN_rpn
         rc = self._conv(bf, rpn.RPN_Conv.weight, None, rpn.RPN_Conv.bias, 1, 1, 1, relu=True).out
@@ -120,7 +119,7 @@ class D2TEngine(object):
         self.n_trunk_layers = len(self.layers)
         # ---- tracking head conv (runs after the correlations)
         tn = net.corr_bbox_net
-        self.trk_layer = dc.ConvLayer(self.trk_in, tn.weight, None, tn.bias, passes=passes, want_nhwc=False, want_nchw=True)
+        self.trk_layer = self._make_layer(self.trk_in, tn.weight, None, tn.bias, want_nhwc=False, want_nchw=True)
         self.conv_flops += self.trk_layer.flops
         self.anchors = rpn.RPN_proposal._anchors.to(dev)
         self.feat_stride = rpn.feat_stride
@@ -138,10 +137,12 @@ class D2TEngine(object):
         self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, %s, TMA-fed, fused BN/ReLU/residual" % kind
 
     # ------------------------------------------------------------------ construction helpers
-    def _conv(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, want_nhwc=True,
-              want_nchw=False):
-        layer = dc.ConvLayer(x, weight, scale, shift, stride, pad, dil, relu, residual, passes=self.passes,
-                             want_nhwc=want_nhwc, want_nchw=want_nchw)
+    def _make_layer(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, **kw):
+        """the one place a convolution plan is created (the training engine overrides it)"""
+        return dc.ConvLayer(x, weight, scale, shift, stride, pad, dil, relu, residual, passes=self.passes, **kw)
+
+    def _conv(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, **kw):
+        layer = self._make_layer(x, weight, scale, shift, stride, pad, dil, relu, residual, **kw)
         self.layers.append(layer)
         self.conv_flops += layer.flops
         return layer

@@ -65,9 +65,13 @@ class _ProposalTargetLayer(nn.Module):
         return rois_b, labels_b, bbox_targets, inside_w, outside_w
 
 
-def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, info, gt_boxes, num_boxes):
+def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, info, gt_boxes, num_boxes, rpn_maps=None,
+                trk_map=None):
     """Training branch of _RFCN.forward.  Tensors are leg-major over 2B images; gt_boxes [B,2,K,6],
-    num_boxes [B,2,1].  Returns the reference's 10-tuple (rfcn.py:248-250)."""
+    num_boxes [B,2,1].  Returns the reference's 10-tuple (rfcn.py:248-250).
+    rpn_maps = (rpn_cls_score, rpn_bbox_pred) [2B, ...] and trk_map [B, 4*n_reg*49, H, W]: the outputs of the RPN /
+    tracking-head convolutions when the caller has already run them (d2t_b200.train: the tcgen05 engine); base_feat and
+    conv3/4/5 are then unused."""
     from .tracking_proposal_target_layer import _TrackingProposalTargetLayer
     L = 2
     if net.RFCN_proposal_target is None:
@@ -79,7 +83,11 @@ def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, inf
     l_rpn_cls, l_rpn_box, l_cls, l_box = [], [], [], []
     for leg in range(L):
         sl = slice(leg * B, (leg + 1) * B)
-        leg_rois, lc, lb = net.RFCN_rpn(base_feat[sl], info[sl], gt[leg][:, :, :5], nb[leg])
+        if rpn_maps is not None:
+            leg_rois, lc, lb = net.RFCN_rpn.forward_from_maps(rpn_maps[0][sl], rpn_maps[1][sl], info[sl], gt[leg][:, :, :5],
+                                                              nb[leg])
+        else:
+            leg_rois, lc, lb = net.RFCN_rpn(base_feat[sl], info[sl], gt[leg][:, :, :5], nb[leg])
         l_rpn_cls.append(lc.view(1)), l_rpn_box.append(lb.view(1))
         leg_rois, label, target, iw, ow = net.RFCN_proposal_target(leg_rois, gt[leg][:, :, :5], nb[leg])
         label = label.view(-1).long()
@@ -97,7 +105,7 @@ def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, inf
         cls_prob.append(F.softmax(score, dim=1).view(B, leg_rois.size(1), -1))
         bbox_pred.append(pred.view(B, leg_rois.size(1), -1))
     # ---- tracking branch
-    trk = net._tracking_maps(conv3, conv4, conv5, rfcn_bbox, B)
+    trk = trk_map if trk_map is not None else net._tracking_maps(conv3, conv4, conv5, rfcn_bbox, B)
     t_rois, t_label, t_target, t_iw, t_ow = net.RFCN_tracking_proposal_target(gt, nb)
     pooled = net.RFCN_psroi_loc_pool(trk, t_rois.contiguous().view(-1, 5))
     tracking_pred = net.RFCN_tracking_pred(pooled).view(-1, pooled.size(1))

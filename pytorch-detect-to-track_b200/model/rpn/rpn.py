@@ -41,9 +41,13 @@ class _RPN(nn.Module):
 
     def forward(self, base_feat, im_info, gt_boxes=None, num_boxes=None):
         rpn_conv1 = F.relu(self.RPN_Conv(base_feat), inplace=True)
-        rpn_cls_score = self.RPN_cls_score(rpn_conv1)
+        return self.forward_from_maps(self.RPN_cls_score(rpn_conv1), self.RPN_bbox_pred(rpn_conv1), im_info, gt_boxes,
+                                      num_boxes)
+
+    def forward_from_maps(self, rpn_cls_score, rpn_bbox_pred, im_info, gt_boxes=None, num_boxes=None):
+        """rpn.py:66-105 after the three convolutions (the training engine runs those on the tcgen05 kernel and hands
+        their outputs in as autograd leaves)."""
         rpn_cls_prob = self.cls_prob_from_score(rpn_cls_score, self.nc_score_out)
-        rpn_bbox_pred = self.RPN_bbox_pred(rpn_conv1)
         cfg_key = 'TRAIN' if self.training else 'TEST'
         rois = self.RPN_proposal((rpn_cls_prob.detach(), rpn_bbox_pred.detach(), im_info, cfg_key))
         self.rpn_loss_cls = 0

@@ -1,0 +1,102 @@
+"""The training step on the native kernels (d2t_b200.train.D2TTrainEngine): forward on the tcgen05 engine, heads +
+losses through autograd, explicit backward through DgradConv / WgradLayer / the correlation + PSRoI backward kernels.
+Checked against torch autograd over the same nn.Module (cuDNN fp32, TF32 off) FED THE SAME head gradients, so the
+comparison does not depend on the target layers' random sampling."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(layers, B, H, W):
+    from model.faster_rcnn.resnet import resnet
+    from d2t_b200.synth import calibrate_batchnorm
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    net = resnet(tuple(range(31)), layers, class_agnostic=True).create_architecture().cuda()
+    g = torch.Generator().manual_seed(1)
+    im_data = (torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128).cuda()
+    im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
+    calibrate_batchnorm(net, im_data.view(2 * B, 3, H, W), chunk=0)
+    net.train()
+    gt = torch.from_numpy(common.make_gt_boxes(B, 30, seed=2, height=H, width=W)).cuda()
+    nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
+    return net, im_data, im_info, gt, nb
+
+
+def _torch_param_grads(net, im_data, B, leaf_grads):
+    """d(sum_i <map_i, leaf_grad_i>)/d(params) by torch autograd through the nn.Module's own convolutions"""
+    N = 2 * B
+    frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, *im_data.shape[2:]).contiguous()
+    conv3, conv4, conv5, base = net._im_to_head(frames)
+    cls_map, bbox_map = net.RFCN_cls_net(base), net.RFCN_bbox_net(base)
+    rpn = net.RFCN_rpn
+    rc = F.relu(rpn.RPN_Conv(base))
+    score, delta = rpn.RPN_cls_score(rc), rpn.RPN_bbox_pred(rc)
+    trk = net._tracking_maps(conv3, conv4, conv5, bbox_map, B)
+    torch.autograd.backward([cls_map, bbox_map, score, delta, trk], leaf_grads)
+
+
+@pytest.mark.parametrize("layers,B,H,W", [(50, 2, 224, 320), (50, 1, 160, 224)])
+def test_train_engine_gradients_match_autograd(layers, B, H, W):
+    from d2t_b200.train import D2TTrainEngine
+    net, im_data, im_info, gt, nb = _setup(layers, B, H, W)
+    eng = D2TTrainEngine(net, B, H, W)
+    out, loss = eng.forward_backward(im_data, im_info, gt, nb)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss))
+    assert out[0].shape == (2, B, 128, 5) and out[1].shape == (2, B, 128, 31)
+    mine = eng.flat.clone()
+    assert bool(torch.isfinite(mine).all())
+    eng.flat.zero_()
+    _torch_param_grads(net, im_data, B, [g.clone() for g in eng.leaf_grads])      # accumulates into the same .grad views
+    torch.cuda.synchronize()
+    ref = eng.flat.clone()
+    worst = ("", 0.0)
+    names = {id(p): n for n, p in net.named_parameters()}
+    for p in eng.params:
+        a = mine[p.grad.storage_offset():p.grad.storage_offset() + p.numel()]
+        b = ref[p.grad.storage_offset():p.grad.storage_offset() + p.numel()]
+        scale = float(b.abs().max())
+        assert scale > 0, names[id(p)]
+        err = float((a - b).abs().max()) / scale
+        if err > worst[1]:
+            worst = (names[id(p)], err)
+        assert err < 2e-3, (names[id(p)], err)
+    print("train engine vs autograd: worst per-parameter max-norm rel err %.2e (%s)" % (worst[1], worst[0]))
+    assert net.RFCN_base[4][0].conv1.weight.grad is None                           # frozen stem / layer1 (resnet.py:279-289)
+
+
+def test_train_engine_learns():
+    """three SGD steps through the engine (weights re-packed on the device after each) lower the loss on a fixed batch"""
+    from d2t_b200.train import D2TTrainEngine
+    B, H, W = 2, 224, 320
+    net, im_data, im_info, gt, nb = _setup(50, B, H, W)
+    eng = D2TTrainEngine(net, B, H, W)
+    opt = torch.optim.SGD(eng.params, lr=1e-3, momentum=0.9)
+    losses = []
+    for it in range(4):
+        torch.manual_seed(100)                     # the same RoI / anchor samples every step
+        out, loss = eng.forward_backward(im_data, im_info, gt, nb)
+        assert bool(torch.isfinite(loss))
+        opt.step()
+        eng.refresh_weights()
+        losses.append(float(loss))
+    print("losses", losses)
+    assert losses[-1] < losses[0], losses
+    # the engine's forward after the updates == the nn.Module's forward with the updated parameters
+    net.eval()
+    with torch.no_grad():
+        frames = im_data.permute(1, 0, 2, 3, 4).reshape(2 * B, 3, H, W).contiguous()
+        base = net._im_to_head(frames)[3]
+        info = eng._begin(im_data, im_info)
+        for layer in eng.layers:
+            layer.run()
+    err = float((eng.base_feat.to_nchw() - base).abs().max() / base.abs().max())
+    assert err < 1e-4, err
