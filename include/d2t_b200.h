@@ -299,11 +299,13 @@ int d2t_upsample2_add_mask(const float* low, int LH, int LW, const float* extra,
  * as a GEMM with K over the output pixels: both operands are read from channel-major PLANES so that K is contiguous.
  * d2t_wgrad_pack_input: channels [0, C) of the NHWC input sampled at (oy*stride, ox*stride) -> fp32 planes
  * [N][C][OH][pitch] (a stride-2 1x1 convolution is a stride-1 one on the sampled positions); d2t_wgrad_pack_grad: the
- * NHWC gradient -> fp16 planes (hi, lo) of g * 2^k, k from *amax_g.  Pitches in elements (% 4 / % 8). */
+ * NHWC gradient -> S copies [S][N][C][OH][pitch] of fp16 planes (hi, lo) of g * 2^k (k from *amax_g), copy s shifted
+ * right by s*dil - pad columns: a TMA box must start on a 16-byte boundary of the contiguous axis, so the filter column's
+ * offset is materialised by the packer (the row offset is a box coordinate).  Pitches in elements (% 4 / % 8). */
 int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
                          int pitch, float* xt, cudaStream_t stream);
-int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, const float* amax_g,
-                        void* g_hi, void* g_lo, cudaStream_t stream);
+int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, int S, int dil, int pad,
+                        const float* amax_g, void* g_hi, void* g_lo, cudaStream_t stream);
 d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, int xt_pitch, int OH, int OW,
                                      int g_pitch, int R, int S, int pad, int dil, const float* xt,
                                      const void* g_hi, const void* g_lo, const float* amax_x,

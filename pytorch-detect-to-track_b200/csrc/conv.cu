@@ -398,9 +398,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // as the GEMM  D[m = ci, n = co] per filter tap with K running over the output PIXELS.  Both operands are read from
 // PLANAR copies (channel-major planes, row pitch a multiple of 16 bytes) so that K is the contiguous axis, exactly the
 // K-major SWIZZLE_128B tiles the forward pass uses: A = a [128 channels x 64 pixels] fp32 box of X (two 32-pixel TMA
-// boxes; the tap is the box's start coordinate, zero padding the TMA's out-of-bounds fill), split into fp16 (hi, lo) by
-// the converter warps into tensor memory like a forward activation tile; B = [BN channels x 64 pixels] boxes of the
-// gradient's pre-split fp16 (hi, lo) planes (d2t_wgrad_pack).  A K block is 64 consecutive pixels of one output row;
+// boxes), split into fp16 (hi, lo) by the converter warps into tensor memory like a forward activation tile; B =
+// [BN channels x 64 pixels] boxes of the gradient's pre-split fp16 (hi, lo) planes (d2t_wgrad_pack_grad).  The filter
+// tap's ROW offset is the start coordinate of the A box in y (zero padding = the TMA's out-of-bounds fill); its COLUMN
+// offset cannot be a start coordinate -- a box must start on a 16-byte boundary of the contiguous axis (an odd start
+// raises an illegal-instruction fault, measured) -- so the packer writes one copy of the gradient planes per filter
+// column, shifted by that column's offset, and K runs over the columns u = ox + dx of X.  A K block is 64 consecutive
+// columns of one row;
 // tiles are (128 input channels, tap) x (BN output channels); stream-K and the drain are unchanged; the epilogue
 // scales column co by the folded BatchNorm scale and writes the OIHW gradient.
 template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false>
@@ -536,7 +540,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     // tile = (tap, 128 input channels) x (BN output channels); K block k = 64 pixels of output row
                     // (image, oy) starting at column 64 * xb
                     const int RS = p.R * p.S, tap = m_tile % RS, ci0 = (m_tile / RS) * kBlockM;
-                    const int dy = (tap / p.S) * p.dil - p.pad, dx = (tap % p.S) * p.dil - p.pad;
+                    const int dy = (tap / p.S) * p.dil - p.pad, sx = tap % p.S;     // (column shift sx: pre-shifted B planes)
                     const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
                     int xb = k_beg % p.wg_xblocks, oy = (k_beg / p.wg_xblocks) % p.OH, im = k_beg / (p.wg_xblocks * p.OH);
                     for (int k = k_beg; k < k_end; ++k) {
@@ -544,8 +548,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
                         uint64_t* fbar = &full[stage];
                         if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
-                        if (is_a) tma_load_4d(dst, map, fbar, xb * kBlockK + a_c0 + dx, oy + dy, ci0, im);
-                        else tma_load_4d(dst, map, fbar, xb * kBlockK, oy, n_tile * BN, im);
+                        if (is_a) tma_load_4d(dst, map, fbar, xb * kBlockK + a_c0, oy + dy, ci0, im);
+                        else tma_load_5d(dst, map, fbar, xb * kBlockK, oy, n_tile * BN, im, sx);
                         if (++stage == C::STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -1639,7 +1643,8 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
 
 // Weight gradient of a stride-1 convolution (see the WGRAD kernel comment).  xt: planar fp32 [N][Cin][xh][xt_pitch] (the
 // forward input; for a strided 1x1 conv the caller packs the sub-sampled positions, d2t_wgrad_pack_input); g_hi / g_lo:
-// planar fp16 [N][Cout][OH][g_pitch] = the (hi, lo) split of G * 2^k, k derived from *amax_g (d2t_wgrad_pack_grad);
+// planar fp16 [S][N][Cout][OH][g_pitch] = the (hi, lo) split of G * 2^k, k derived from *amax_g, copy s shifted right by
+// s*dil - pad columns (d2t_wgrad_pack_grad);
 // dw: OIHW fp32 [Cout][Cin][R][S], every element written (no accumulation).  Pitches in elements: xt_pitch % 4 == 0,
 // g_pitch % 8 == 0.  amax_x / amax_g: the device scalars holding max |X| and max |G|.
 extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, int xt_pitch, int OH, int OW,
@@ -1652,7 +1657,7 @@ extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh
         set_error("d2t_wgrad_plan_create: bad arguments");
         return nullptr;
     }
-    if (OH != xh + 2 * pad - dil * (R - 1) || OW != xw + 2 * pad - dil * (S - 1)) {
+    if (OH != xh + 2 * pad - dil * (R - 1) || OW != xw + 2 * pad - dil * (S - 1) || g_pitch < xw) {
         set_error("d2t_wgrad_plan_create: output geometry does not match a stride-1 convolution of the input");
         return nullptr;
     }
@@ -1674,7 +1679,7 @@ extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh
     a.scale = scale; a.shift = nullptr; a.res = nullptr; a.res_cstride = 0; a.relu = 0;
     a.out = nullptr; a.out_nchw = nullptr; a.out_cstride = 0; a.out_coffset = 0;
     a.amax_in = amax_x; a.amax_b = amax_g; a.amax_out = nullptr; a.w_exp = 0;
-    a.wg_xblocks = (OW + KB - 1) / KB;
+    a.wg_xblocks = (xw + KB - 1) / KB;                       // K runs over the columns of X
     a.wg_kiters = N * OH * a.wg_xblocks;
     a.wg_cin = Cin; a.wg_out = dw;
     pl->passes = 16; pl->corr = 0; pl->pair = 0; pl->epi2 = 0; pl->wgrad = 1;
@@ -1689,14 +1694,15 @@ extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh
     const cuuint64_t adims[4] = {(cuuint64_t)xw, (cuuint64_t)xh, (cuuint64_t)Cin, (cuuint64_t)N};
     const cuuint64_t astr[3] = {(cuuint64_t)xt_pitch * 4, (cuuint64_t)xh * xt_pitch * 4, (cuuint64_t)Cin * xh * xt_pitch * 4};
     const cuuint32_t abox[4] = {(cuuint32_t)kBoxC, 1u, (cuuint32_t)kBlockM, 1u};
-    // B: planes of G (fp16), box = 64 pixels of one row x BN channels
-    const cuuint64_t bdims[4] = {(cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)Cout, (cuuint64_t)N};
-    const cuuint64_t bstr[3] = {(cuuint64_t)g_pitch * 2, (cuuint64_t)OH * g_pitch * 2, (cuuint64_t)Cout * OH * g_pitch * 2};
-    const cuuint32_t bbox[4] = {(cuuint32_t)KB, 1u, (cuuint32_t)pl->BN, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    // B: the S column-shifted copies of the planes of G (fp16), indexed by X's columns; box = 64 columns of one row x BN channels
+    const cuuint64_t bdims[5] = {(cuuint64_t)xw, (cuuint64_t)OH, (cuuint64_t)Cout, (cuuint64_t)N, (cuuint64_t)S};
+    const cuuint64_t bstr[4] = {(cuuint64_t)g_pitch * 2, (cuuint64_t)OH * g_pitch * 2, (cuuint64_t)Cout * OH * g_pitch * 2,
+                                (cuuint64_t)N * Cout * OH * g_pitch * 2};
+    const cuuint32_t bbox[5] = {(cuuint32_t)KB, 1u, (cuuint32_t)pl->BN, 1u, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
     bool ok = encode(&pl->tmA, xt, 4, adims, astr, abox, estr, "wgrad A") &&
-              encode(&pl->tmB_hi, g_hi, 4, bdims, bstr, bbox, estr, "wgrad B hi", true) &&
-              encode(&pl->tmB_lo, g_lo, 4, bdims, bstr, bbox, estr, "wgrad B lo", true);
+              encode(&pl->tmB_hi, g_hi, 5, bdims, bstr, bbox, estr, "wgrad B hi", true) &&
+              encode(&pl->tmB_lo, g_lo, 5, bdims, bstr, bbox, estr, "wgrad B lo", true);
     pl->tmO = pl->tmA;
     pl->tmR = pl->tmA;
     if (!ok) {

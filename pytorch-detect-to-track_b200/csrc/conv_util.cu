@@ -176,18 +176,15 @@ __global__ void pack_weights_f16_dgrad(const float* __restrict__ w, const float*
     }
 }
 
-// channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> planes [N][C][OH][pitch] (columns
-// [OW, pitch) zero): the K-contiguous operand layout of the weight-gradient GEMM.  SPLIT: fp16 (hi, lo) planes of
-// x * 2^k (k from *amax) instead of fp32.  32 x 32 shared-memory transpose per (image, output row).
-template <bool SPLIT>
+// channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> fp32 planes [N][C][OH][pitch]
+// (columns [OW, pitch) zero): the K-contiguous A operand of the weight-gradient GEMM.  32 x 32 shared-memory transpose
+// per (image, output row).
 __global__ void __launch_bounds__(256)
 nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, int stride, int OH, int OW, int pitch,
-               const float* __restrict__ amax, float* __restrict__ out, __half* __restrict__ out_hi,
-               __half* __restrict__ out_lo) {
+               float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float sa = SPLIT ? pow2f(act_exp(amax)) : 1.f;
     for (int j = ty; j < 32; j += 8) {
         const int xo = wt + j, c = ct + tx;
         tile[j][tx] = (xo < OW && c < C) ? __ldg(x + (((size_t)n * H + (size_t)oy * stride) * W + (size_t)xo * stride) * cs + c) : 0.f;
@@ -195,15 +192,37 @@ nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, 
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int c = ct + j, xo = wt + tx;
-        if (c < C && xo < pitch) {
-            const size_t o = (((size_t)n * C + c) * OH + oy) * pitch + xo;
-            const float v = tile[tx][j] * sa;
-            if (SPLIT) {
+        if (c < C && xo < pitch) out[(((size_t)n * C + c) * OH + oy) * pitch + xo] = tile[tx][j];
+    }
+}
+
+// gradient NHWC [N, OH, OW, cs] -> the B operand of the weight-gradient GEMM: S copies of fp16 (hi, lo) planes
+// [S][N][C][OH][pitch] of g * 2^k (k from *amax), copy s shifted by dx_s = s * dil - pad columns:
+// plane_s[u] = g[u - dx_s] (zero outside [0, OW)) -- the filter column's offset cannot be a TMA start coordinate (see
+// conv.cu, WGRAD), so it is materialised here.  The tile is loaded with an 8-column halo on both sides (|dx| <= 8).
+__global__ void __launch_bounds__(256)
+nhwc_to_planes_split(const float* __restrict__ g, int N, int OH, int OW, int cs, int C, int pitch, int S, int dil, int pad,
+                     const float* __restrict__ amax, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    __shared__ float tile[48][33];
+    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float sa = pow2f(act_exp(amax));
+    for (int j = ty; j < 48; j += 8) {
+        const int xo = wt - 8 + j, c = ct + tx;
+        tile[j][tx] = (xo >= 0 && xo < OW && c < C) ? __ldg(g + (((size_t)n * OH + oy) * OW + xo) * cs + c) * sa : 0.f;
+    }
+    __syncthreads();
+    const size_t copy = (size_t)N * C * OH * pitch;
+    for (int s = 0; s < S; ++s) {
+        const int dx = s * dil - pad;
+        for (int j = ty; j < 32; j += 8) {
+            const int c = ct + j, u = wt + tx;
+            if (c < C && u < pitch) {
+                const float v = tile[tx + 8 - dx][j];
+                const size_t o = s * copy + (((size_t)n * C + c) * OH + oy) * pitch + u;
                 const __half h = __float2half_rn(v);
                 out_hi[o] = h;
                 out_lo[o] = __float2half_rn(v - __half2float(h));
-            } else {
-                out[o] = v;
             }
         }
     }
@@ -313,32 +332,29 @@ extern "C" int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float*
     return 1;
 }
 
-static int planes_launch(bool split, const float* x, int N, int H, int W, int cs, int C, int stride, int OH, int OW, int pitch,
-                         const float* amax, float* out, void* hi, void* lo, cudaStream_t stream) {
-    D2T_REQUIRE(x && N > 0 && H > 0 && W > 0 && C > 0 && cs >= C && stride > 0 && OH > 0 && OW > 0 && pitch >= OW &&
-                    (OH - 1) * stride < H && (OW - 1) * stride < W,
-                "d2t_wgrad_pack: bad arguments");
+extern "C" int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
+                                    int pitch, float* xt, cudaStream_t stream) {
+    D2T_REQUIRE(x && xt && N > 0 && H > 0 && W > 0 && C > 0 && c_stride >= C && stride > 0 && OH > 0 && OW > 0 &&
+                    pitch >= OW && pitch % 4 == 0 && (OH - 1) * stride < H && (OW - 1) * stride < W,
+                "d2t_wgrad_pack_input: bad arguments (row pitch a multiple of 4)");
     dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
-    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack: tensor too large for the launch grid");
-    if (split)
-        nhwc_to_planes<true><<<grid, 256, 0, stream>>>(x, N, H, W, cs, C, stride, OH, OW, pitch, amax, nullptr,
-                                                       reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo));
-    else
-        nhwc_to_planes<false><<<grid, 256, 0, stream>>>(x, N, H, W, cs, C, stride, OH, OW, pitch, nullptr, out, nullptr, nullptr);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_input: tensor too large for the launch grid");
+    nhwc_to_planes<<<grid, 256, 0, stream>>>(x, N, H, W, c_stride, C, stride, OH, OW, pitch, xt);
     D2T_CHECK_LAUNCH("nhwc_to_planes");
     return 1;
 }
 
-extern "C" int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
-                                    int pitch, float* xt, cudaStream_t stream) {
-    D2T_REQUIRE(xt && pitch % 4 == 0, "d2t_wgrad_pack_input: needs an output buffer and a row pitch that is a multiple of 4");
-    return planes_launch(false, x, N, H, W, c_stride, C, stride, OH, OW, pitch, nullptr, xt, nullptr, nullptr, stream);
-}
-
-extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, const float* amax_g,
-                                   void* g_hi, void* g_lo, cudaStream_t stream) {
-    D2T_REQUIRE(g_hi && g_lo && amax_g && pitch % 8 == 0, "d2t_wgrad_pack_grad: needs output planes, amax and a row pitch that is a multiple of 8");
-    return planes_launch(true, g, N, OH, OW, c_stride, C, 1, OH, OW, pitch, amax_g, nullptr, g_hi, g_lo, stream);
+extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_stride, int C, int pitch, int S, int dil,
+                                   int pad, const float* amax_g, void* g_hi, void* g_lo, cudaStream_t stream) {
+    D2T_REQUIRE(g && g_hi && g_lo && amax_g && N > 0 && OH > 0 && OW > 0 && C > 0 && c_stride >= C && pitch >= OW &&
+                    pitch % 8 == 0 && S >= 1 && dil >= 1 && pad >= 0 && pad <= 8 && (S - 1) * dil - pad <= 8,
+                "d2t_wgrad_pack_grad: bad arguments (row pitch a multiple of 8, column shifts within +-8)");
+    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_grad: tensor too large for the launch grid");
+    nhwc_to_planes_split<<<grid, 256, 0, stream>>>(g, N, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
+                                                   reinterpret_cast<__half*>(g_hi), reinterpret_cast<__half*>(g_lo));
+    D2T_CHECK_LAUNCH("nhwc_to_planes_split");
+    return 1;
 }
 
 extern "C" int d2t_upsample2_add_mask(const float* low, int LH, int LW, const float* extra, const float* mask, int N, int H,

@@ -82,7 +82,7 @@ _SIGS = {
     "d2t_conv_pack_weights_f16_dgrad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_upsample2_add_mask": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_wgrad_pack_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "d2t_wgrad_pack_grad": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "d2t_wgrad_pack_grad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_wgrad_plan_create": (_p, [_i] * 13 + [_p] * 7),
 }
 

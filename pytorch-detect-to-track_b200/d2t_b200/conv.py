@@ -289,8 +289,9 @@ class WgradScratch(object):
         self.g_lo = torch.zeros(g_halfs, device=device, dtype=torch.float16)
 
     @staticmethod
-    def need(x, g, stride):
-        return x.N * x.C * g.H * _pad32(g.W), g.N * g.C * g.H * _pad32(g.W)
+    def need(x, g, stride, S=1):
+        """(floats of input planes, halfs of gradient planes: one column-shifted copy per filter column)"""
+        return x.N * x.C * g.H * _pad32(g.W), S * g.N * g.C * g.H * _pad32(g.W)
 
 
 class WgradLayer(_Planned):
@@ -307,7 +308,8 @@ class WgradLayer(_Planned):
         self.xh, self.xw = (g.H, g.W) if stride > 1 else (x.H, x.W)
         self.xp, self.gp = _pad32(self.xw), _pad32(g.W)
         self.scratch = scratch
-        nx, ng = x.N * I * self.xh * self.xp, g.N * O * g.H * self.gp
+        self.S, self.pad, self.dil = S, pad, dil
+        nx, ng = x.N * I * self.xh * self.xp, S * g.N * O * g.H * self.gp
         if nx > scratch.xt.numel() or ng > scratch.g_hi.numel():
             raise ValueError("WgradScratch too small: need %d floats / %d halfs" % (nx, ng))
         self.plan = lib().d2t_wgrad_plan_create(x.N, I, O, self.xh, self.xw, self.xp, g.H, g.W, self.gp, R, S, pad, dil,
@@ -323,8 +325,8 @@ class WgradLayer(_Planned):
         st = _stream() if stream is None else stream
         check(lib().d2t_wgrad_pack_input(_p(x.x), x.N, x.H, x.W, x.cstride, I, self.stride, self.xh, self.xw, self.xp,
                                          _p(sc.xt), st), "d2t_wgrad_pack_input")
-        check(lib().d2t_wgrad_pack_grad(_p(g.x), g.N, g.H, g.W, g.cstride, O, self.gp, _p(g.amax), _p(sc.g_hi), _p(sc.g_lo),
-                                        st), "d2t_wgrad_pack_grad")
+        check(lib().d2t_wgrad_pack_grad(_p(g.x), g.N, g.H, g.W, g.cstride, O, self.gp, self.S, self.dil, self.pad,
+                                        _p(g.amax), _p(sc.g_hi), _p(sc.g_lo), st), "d2t_wgrad_pack_grad")
         check(lib().d2t_conv_plan_run(self.plan, st), "d2t_conv_plan_run")
         ops._count(3)
         return self.grad_w

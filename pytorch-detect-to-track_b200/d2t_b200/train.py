@@ -109,7 +109,7 @@ class D2TTrainEngine(D2TEngine):
             oh, ow = l.info["OH"], l.info["OW"]
             nimg = N if l is not self.trk_layer else B
             need_x = max(need_x, nimg * I * (oh if m["stride"] > 1 else l.x.H) * dc._pad32(ow if m["stride"] > 1 else l.x.W))
-            need_g = max(need_g, nimg * O * oh * dc._pad32(ow))
+            need_g = max(need_g, S * nimg * O * oh * dc._pad32(ow))
         self.wscratch = dc.WgradScratch(need_x, need_g, dev)
 
         # ---- gradient leaves coming out of the autograd part (NCHW -> NHWC each step)

@@ -59,7 +59,7 @@ def test_wgrad_matches_autograd(case):
     _, gw_ref = _ref_grads(x, w, scale, gy, stride, pad, dil)
     xs = dc.ActTensor.from_nchw(x)
     gs = dc.ActTensor.from_nchw(gy)
-    nx, ng = dc.WgradScratch.need(xs, gs, stride)
+    nx, ng = dc.WgradScratch.need(xs, gs, stride, k)
     scratch = dc.WgradScratch(nx, ng)
     gw = torch.full_like(w, float("nan"))
     layer = dc.WgradLayer(xs, gs, gw, scale, stride, pad, dil, scratch)
