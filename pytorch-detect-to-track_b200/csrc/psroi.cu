@@ -498,7 +498,7 @@ constexpr int kMcMaxRows = 320;    // TROW: per-row |f| sums of one item (launch
 template <int G, int THREADS, int CTAS, bool LROI, bool TROW = false>
 __global__ void __launch_bounds__(THREADS, CTAS)
 psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, int D, int R, PsroiWs ws,
-                  float* __restrict__ top, int* __restrict__ mapping) {
+                  float* __restrict__ top, int* __restrict__ mapping, float* __restrict__ vpart) {
     constexpr int NW = THREADS / 32;
     extern __shared__ float4 smem4[];
     __shared__ uint64_t bar;
@@ -508,6 +508,9 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
     __shared__ int crange[2];      // chunk range [lo, hi] holding the rois of the item's image
     __shared__ float stage_w[LROI ? NW * 16 * G : 1];   // LROI: per-warp [16 rois][G] output transposition area
     __shared__ float rowsum[TROW ? kMcMaxRows : 1];     // TROW: sum |f| of every plane row of the item
+    __shared__ float rowmax[TROW ? kMcMaxRows : 1];     // TROW: max |f| of every plane row
+    __shared__ float lmw[NW][2];                        // per warp: max |f| over its rows of plane p0 / p0 + 1
+    __shared__ int unsafe_p[G];                         // plane p must not be quantised (see the guard below)
     const int HW = H * W, n_el = G * HW;
     float* buf = reinterpret_cast<float*>(smem4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -579,38 +582,65 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
         if (trow) {
             for (int r = tid; r < rows; r += THREADS) {
                 const float* row = pl + r * W;
-                float a = 0.f;
+                float a = 0.f, mx = 0.f;
 #pragma unroll 9
-                for (int x = 0; x < W; ++x) a += fabsf(row[x]);
+                for (int x = 0; x < W; ++x) {
+                    const float v = fabsf(row[x]);
+                    a += v;
+                    mx = fmaxf(mx, v);
+                }
                 rowsum[r] = a;
+                rowmax[r] = mx;
             }
         } else {
-            float s0 = 0.f, s1 = 0.f;
+            float s0 = 0.f, s1 = 0.f, m0 = 0.f, m1 = 0.f;
             for (int r = r_begin; r < r_end; ++r) {
                 const float* row = pl + r * W;
-                float a = 0.f;
-                if (2 * lane < W) a = fabsf(row[2 * lane]);
-                if (2 * lane + 1 < W) a += fabsf(row[2 * lane + 1]);
-                if (r < r_split) s0 += a; else s1 += a;
+                float a = 0.f, mx = 0.f;
+                if (2 * lane < W) a = mx = fabsf(row[2 * lane]);
+                if (2 * lane + 1 < W) {
+                    const float v = fabsf(row[2 * lane + 1]);
+                    a += v;
+                    mx = fmaxf(mx, v);
+                }
+                if (r < r_split) { s0 += a; m0 = fmaxf(m0, mx); } else { s1 += a; m1 = fmaxf(m1, mx); }
             }
             s0 = warp_sum(s0);
             s1 = warp_sum(s1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            }
             if (lane == 0) {
                 l1w[warp][0] = s0;
                 l1w[warp][1] = s1;
+                lmw[warp][0] = m0;
+                lmw[warp][1] = m1;
             }
         }
         __syncthreads();
         if (tid < G) {
-            float l1 = 0.f;
+            float l1 = 0.f, mx = 0.f;
             if (trow) {
-                for (int h = 0; h < H; ++h) l1 += rowsum[tid * H + h];      // fixed order: the scale is deterministic
+                for (int h = 0; h < H; ++h) {
+                    l1 += rowsum[tid * H + h];                               // fixed order: the scale is deterministic
+                    mx = fmaxf(mx, rowmax[tid * H + h]);
+                }
             } else {
                 for (int w = 0; w < NW; ++w) {
                     const int wp0 = wp0s[w];
                     l1 += (wp0 == tid ? l1w[w][0] : 0.f) + (wp0 + 1 == tid ? l1w[w][1] : 0.f);
+                    mx = fmaxf(mx, fmaxf(wp0 == tid ? lmw[w][0] : 0.f, wp0 + 1 == tid ? lmw[w][1] : 0.f));
                 }
             }
+            // GUARD.  The fixed-point error of a bin mean is <= 2^-31 of the plane's L1 norm -- relative to the PLANE, not to
+            // the bin.  A plane whose largest |f| dwarfs the rest (one outlier > 2^14 x the mean of the others) would push
+            // quiet bins past ~1e-5 relative, and a NaN / Inf cannot be quantised at all (the reference propagates it).  Such
+            // an item is pooled by direct summation in the reference's own order instead (bit-identical to
+            // psroi_pooling_kernel.cu:62-76): rare, slower, exact.
+            const float rest = l1 - mx;
+            unsafe_p[tid] = (!(l1 < 3.0e38f) || mx * (float)(HW - 1) > 16384.f * rest) ? 1 : 0;
             // l1 < 2^(eb - 126) for the biased exponent eb of l1  =>  k = 30 - (eb - 126); powers of two built from bits
             const int eb = (int)((__float_as_uint(l1) >> 23) & 0xffu);
             int k = (eb > 0 && eb < 255) ? 156 - eb : 0;
@@ -619,8 +649,13 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             inv[tid] = __uint_as_float((uint32_t)(127 - k) << 23);
         }
         __syncthreads();
+        bool direct = false;
+#pragma unroll
+        for (int pq = 0; pq < G; ++pq) direct |= unsafe_p[pq] != 0;          // (block-uniform)
         // ---- (2) quantise + inclusive row scan, written back in place as int32
-        if (trow) {
+        if (direct) {
+            // guard tripped: the planes stay fp32, the lookups below sum the windows directly
+        } else if (trow) {
             for (int r = tid; r < rows; r += THREADS) {
                 const float sc = scl[r / H];
                 const float* row = pl + r * W;

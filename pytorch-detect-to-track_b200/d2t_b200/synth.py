@@ -89,11 +89,14 @@ def make_gt_boxes(B, K=30, seed=2, height=600, width=1000):
     return gt
 
 
-def calibrate_batchnorm(net, frames, chunk=2):
+def calibrate_batchnorm(net, frames, chunk=2, var_floor=0.1):
     """Give a randomly initialised trunk the BatchNorm statistics a trained one has: running_mean / running_var := the
     statistics of `frames` [N, 3, H, W] at every BatchNorm (one forward with momentum 1), so activations stay O(1)
     through ~100 layers instead of growing to 1e7 (Kaiming weights with identity BN).  The reference always starts
-    from a pretrained trunk (resnet.py:304-309); there are no checkpoints offline.  BN stays frozen afterwards."""
+    from a pretrained trunk (resnet.py:304-309); there are no checkpoints offline.  BN stays frozen afterwards.
+    Channels that are (nearly) constant on the calibration frames would get a folded scale of up to 1/sqrt(eps) = 316,
+    which only amplifies every implementation's rounding noise: their variance is floored at `var_floor` x the layer's
+    median variance."""
     import torch
     bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
     saved = [(m.momentum, m.training) for m in bns]
@@ -102,6 +105,9 @@ def calibrate_batchnorm(net, frames, chunk=2):
         m.train()
     with torch.no_grad():
         net._im_to_head(frames[:chunk] if chunk else frames)
+        for m in bns:
+            if m.num_batches_tracked is not None and int(m.num_batches_tracked) > 0:
+                m.running_var.clamp_(min=float(m.running_var.median()) * var_floor)
     for m, (mom, tr) in zip(bns, saved):
         m.momentum = mom
         m.train(tr)

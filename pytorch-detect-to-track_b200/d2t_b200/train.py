@@ -131,18 +131,18 @@ class D2TTrainEngine(D2TEngine):
         self._wgrad(layer_of(bn_.weight), bf, self.g_bbox)
         self._wgrad(layer_of(rpn.RPN_cls_score.weight), rc, self.g_score)
         self._wgrad(layer_of(rpn.RPN_bbox_pred.weight), rc, self.g_delta)
-        g_rc = self._G(rc)
+        g_rc = self.g_rc = self._G(rc)
         self._dgrad(layer_of(rpn.RPN_cls_score.weight), self.g_score, g_rc, mask=rc)
         self._dgrad(layer_of(rpn.RPN_bbox_pred.weight), self.g_delta, g_rc, residual=g_rc, mask=rc)
         self._wgrad(layer_of(rpn.RPN_Conv.weight), bf, g_rc)
-        g_base = self._G(bf)
+        g_base = self.g_base = self._G(bf)
         self._dgrad(layer_of(cn.weight), self.g_cls, g_base, mask=bf)
         self._dgrad(layer_of(bn_.weight), self.g_bbox, g_base, residual=g_base, mask=bf)
         self._dgrad(layer_of(rpn.RPN_Conv.weight), g_rc, g_base, residual=g_base, mask=bf)
         # ---- head conv on conv5
         head = layer_of(net.RFCN_base.RFCN_net.weight)
         self._wgrad(head, self.conv5, g_base)
-        g = self._G(self.conv5)
+        g = self.g_conv5 = self._G(self.conv5)
         self._dgrad(head, g_base, g, residual=self.extra[7], mask=self.conv5)
         # ---- residual stages, last block first
         for bi in range(len(self._blocks) - 1, -1, -1):

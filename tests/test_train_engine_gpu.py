@@ -14,16 +14,24 @@ pytestmark = pytest.mark.gpu
 
 
 def _setup(layers, B, H, W):
+    """a WELL-CONDITIONED synthetic net: non-trivial frozen BatchNorm statistics (so the folding is exercised) without
+    per-layer re-normalisation -- fp32 and fp64 forwards of this net agree to 1e-6, so two fp32 implementations can be
+    compared tightly.  (With BatchNorm calibrated on two small frames the same random net amplifies rounding noise
+    ~100x from layer to layer: torch's own fp32 and fp64 forwards then differ by 1e-4, scripts/r02_train_debug2.py.)"""
     from model.faster_rcnn.resnet import resnet
-    from d2t_b200.synth import calibrate_batchnorm
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(3)
     net = resnet(tuple(range(31)), layers, class_agnostic=True).create_architecture().cuda()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
     g = torch.Generator().manual_seed(1)
-    im_data = (torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128).cuda()
+    im_data = ((torch.rand(B, 2, 3, H, W, generator=g) * 256 - 128) * 0.01).cuda()     # (keeps the un-normalised trunk ~1e3)
     im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
-    calibrate_batchnorm(net, im_data.view(2 * B, 3, H, W), chunk=0)
     net.train()
     gt = torch.from_numpy(common.make_gt_boxes(B, 30, seed=2, height=H, width=W)).cuda()
     nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
@@ -79,7 +87,7 @@ def test_train_engine_learns():
     B, H, W = 2, 224, 320
     net, im_data, im_info, gt, nb = _setup(50, B, H, W)
     eng = D2TTrainEngine(net, B, H, W)
-    opt = torch.optim.SGD(eng.params, lr=1e-3, momentum=0.9)
+    opt = torch.optim.SGD(eng.params, lr=1e-6, momentum=0.9)
     losses = []
     for it in range(4):
         torch.manual_seed(100)                     # the same RoI / anchor samples every step
