@@ -125,7 +125,7 @@ class D2TTrainEngine(D2TEngine):
         # ---- tracking head conv
         self._wgrad(self.trk_layer, self.trk_in, self.g_trk)
         self._dgrad(self.trk_layer, self.g_trk, self.g_trk_in, out_channels=self.trk_in.cstride)
-        self.bwd.append((self._tracking_split, None))
+        self.bwd.append((self._tracking_split, None, 'tracking split + correlation backward'))
         # ---- heads on base_feat
         self._wgrad(layer_of(cn.weight), bf, self.g_cls)
         self._wgrad(layer_of(bn_.weight), bf, self.g_bbox)
@@ -156,7 +156,7 @@ class D2TTrainEngine(D2TEngine):
         assert self._flat_used == self.flat.numel(), (self._flat_used, self.flat.numel())
         # ---- buckets: contiguous ranges of the flat gradient buffer, closed in backward order
         self.buckets, start = [], 0
-        for k, (_, off) in enumerate(self.bwd):
+        for k, (_, off, _l) in enumerate(self.bwd):
             if off is not None and ((off - start) * 4 >= self.bucket_bytes or off == self.flat.numel()):
                 self.buckets.append((k, start, off))
                 start = off
@@ -195,7 +195,7 @@ class D2TTrainEngine(D2TEngine):
             flat2d = g.x.view(-1, g.cstride)
             steps.append(lambda: torch.sum(flat2d[:, :C_], 0, out=gb))
         off = self._flat_used
-        self.bwd.append((lambda: [s() for s in steps], off))
+        self.bwd.append((lambda: [s() for s in steps], off, 'wgrad %dx%d %d->%d @%dx%d' % (gw.shape[2], gw.shape[3], gw.shape[1], gw.shape[0], g.H, g.W)))
 
     def _dgrad(self, layer, g, out, residual=None, mask=None, out_channels=None):
         m = layer.meta
@@ -205,7 +205,7 @@ class D2TTrainEngine(D2TEngine):
         d.set_scratch(self.scratch)
         self.dgrads.append(d)
         self.dgrad_flops = getattr(self, "dgrad_flops", 0.0) + d.flops
-        self.bwd.append((d.run, None))
+        self.bwd.append((d.run, None, 'dgrad %dx%d %d->%d @%dx%d' % (m['weight'].shape[2], m['weight'].shape[3], m['weight'].shape[0], m['weight'].shape[1], g.H, g.W)))
         return d
 
     def _bottleneck_bwd(self, rec, g_out, need_dx, extra):
@@ -237,7 +237,7 @@ class D2TTrainEngine(D2TEngine):
             self._dgrad(c1, g1, low)
             self._dgrad(ds, g_out, low, residual=low)
             assert gx.cstride == x.cstride == x.C, "the scatter kernel wants one channel stride"
-            self.bwd.append((lambda: dc.upsample2_add_mask(low, gx, extra=extra, mask=x), None))
+            self.bwd.append((lambda: dc.upsample2_add_mask(low, gx, extra=extra, mask=x), None, 'upsample2_add_mask'))
         return gx
 
     # ------------------------------------------------------------------ per-step pieces
@@ -307,7 +307,7 @@ class D2TTrainEngine(D2TEngine):
         main = torch.cuda.current_stream()
         nb = 0
         self._comm_events = []
-        for k, (step, _) in enumerate(self.bwd):
+        for k, (step, _, _l) in enumerate(self.bwd):
             step()
             if world > 1 and nb < len(self.buckets) and self.buckets[nb][0] == k:
                 _, a, b = self.buckets[nb]

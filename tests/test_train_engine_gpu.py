@@ -38,7 +38,26 @@ def _setup(layers, B, H, W):
     return net, im_data, im_info, gt, nb
 
 
-def _torch_param_grads(net, im_data, B, leaf_grads):
+def _corr_torch(a, b, pad, md, s1, s2):
+    """correlation_cuda_kernel.cu:34-106 for kernel_size 1, pad == max_displacement, in plain torch (any dtype):
+    out[n, (tj+r)D + (ti+r), y, x] = mean_c a[n, c, y s1, x s1] * b[n, c, y s1 + tj s2, x s1 + ti s2]  (zero outside)"""
+    assert pad == md
+    r = md // s2
+    H, W = a.shape[2:]
+    oh, ow = -(-H // s1), -(-W // s1)
+    bp = F.pad(b, (md, md, md, md))
+    a_s = a[:, :, ::s1, ::s1]
+    outs = []
+    for tj in range(-r, r + 1):
+        for ti in range(-r, r + 1):
+            win = bp[:, :, md + tj * s2: md + tj * s2 + H: s1, md + ti * s2: md + ti * s2 + W: s1]
+            outs.append((a_s * win).mean(1, keepdim=True))
+    out = torch.cat(outs, 1)
+    assert out.shape[2:] == (oh, ow)
+    return out
+
+
+def _torch_param_grads(net, im_data, B, leaf_grads, pure_torch_corr=False):
     """d(sum_i <map_i, leaf_grad_i>)/d(params) by torch autograd through the nn.Module's own convolutions"""
     N = 2 * B
     frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, *im_data.shape[2:]).contiguous()
@@ -47,12 +66,22 @@ def _torch_param_grads(net, im_data, B, leaf_grads):
     rpn = net.RFCN_rpn
     rc = F.relu(rpn.RPN_Conv(base))
     score, delta = rpn.RPN_cls_score(rc), rpn.RPN_bbox_pred(rc)
-    trk = net._tracking_maps(conv3, conv4, conv5, bbox_map, B)
+    if pure_torch_corr:
+        c3 = _corr_torch(conv3[:B], conv3[B:], 8, 8, 2, 2)
+        c4 = _corr_torch(conv4[:B], conv4[B:], 8, 8, 1, 1)
+        c5 = _corr_torch(conv5[:B], conv5[B:], 8, 8, 1, 1)
+        trk = net.corr_bbox_net(torch.cat([bbox_map[:B], bbox_map[B:], c3, c4, c5], 1))
+    else:
+        trk = net._tracking_maps(conv3, conv4, conv5, bbox_map, B)
     torch.autograd.backward([cls_map, bbox_map, score, delta, trk], leaf_grads)
 
 
 @pytest.mark.parametrize("layers,B,H,W", [(50, 2, 224, 320), (50, 1, 160, 224)])
 def test_train_engine_gradients_match_autograd(layers, B, H, W):
+    """every trainable parameter's gradient from the engine's explicit backward against (a) torch autograd in float64 with
+    a pure-torch correlation -- the ground truth -- and (b) torch autograd in fp32 through cuDNN and this repo's
+    correlation op: the engine must be as close to the truth as a small multiple of what cuDNN fp32 is (ReLU masks that
+    flip on 1e-6-level forward differences put a floor of ~1e-3 of max |grad| under any two fp32 implementations here)"""
     from d2t_b200.train import D2TTrainEngine
     net, im_data, im_info, gt, nb = _setup(layers, B, H, W)
     eng = D2TTrainEngine(net, B, H, W)
@@ -65,19 +94,30 @@ def test_train_engine_gradients_match_autograd(layers, B, H, W):
     eng.flat.zero_()
     _torch_param_grads(net, im_data, B, [g.clone() for g in eng.leaf_grads])      # accumulates into the same .grad views
     torch.cuda.synchronize()
-    ref = eng.flat.clone()
-    worst = ("", 0.0)
+    ref32 = eng.flat.clone()
+    net64 = copy.deepcopy(net).double()
+    for p in net64.parameters():
+        p.grad = None
+    _torch_param_grads(net64, im_data.double(), B, [g.double() for g in eng.leaf_grads], pure_torch_corr=True)
+    truth = {n: p.grad for n, p in net64.named_parameters() if p.grad is not None}
     names = {id(p): n for n, p in net.named_parameters()}
+    worst, errs = ("", 0.0, 0.0), []
     for p in eng.params:
-        a = mine[p.grad.storage_offset():p.grad.storage_offset() + p.numel()]
-        b = ref[p.grad.storage_offset():p.grad.storage_offset() + p.numel()]
-        scale = float(b.abs().max())
+        o = p.grad.storage_offset()
+        a, b = mine[o:o + p.numel()].double(), ref32[o:o + p.numel()].double()
+        t = truth[names[id(p)]].reshape(-1)
+        scale = float(t.abs().max())
         assert scale > 0, names[id(p)]
-        err = float((a - b).abs().max()) / scale
-        if err > worst[1]:
-            worst = (names[id(p)], err)
-        assert err < 2e-3, (names[id(p)], err)
-    print("train engine vs autograd: worst per-parameter max-norm rel err %.2e (%s)" % (worst[1], worst[0]))
+        e_eng, e_ref = float((a - t).abs().max()) / scale, float((b - t).abs().max()) / scale
+        errs.append(e_eng)
+        if e_eng > worst[1]:
+            worst = (names[id(p)], e_eng, e_ref)
+        assert e_eng < max(8 * e_ref, 3e-4), (names[id(p)], e_eng, e_ref)
+        assert e_eng < 2e-2, (names[id(p)], e_eng)
+    errs.sort()
+    print("train engine vs float64 autograd: median %.2e, worst %.2e (%s; cuDNN fp32 there: %.2e)" % (
+        errs[len(errs) // 2], worst[1], worst[0], worst[2]))
+    assert errs[len(errs) // 2] < 2e-4
     assert net.RFCN_base[4][0].conv1.weight.grad is None                           # frozen stem / layer1 (resnet.py:279-289)
 
 
