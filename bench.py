@@ -176,9 +176,9 @@ def op_microbench(flush, hbm_gbs):
         out["psroi_fwd_b%d" % Bs] = {"ms": ms_s, "algorithmic_bytes": alg_s, "gbs": alg_s / ms_s / 1e6,
                                      "frac_hbm": alg_s / ms_s / 1e6 / hbm_gbs}
         del f_s, r_s, t_s, w_s
-    os.environ["D2T_PSROI_INT"] = "0"          # the exactly-rounded fp64-table kernel, for comparison (read per launch)
+    lib().d2t_psroi_set_mode(0, 0)             # the exactly-rounded fp64-table kernel, for comparison
     ms_x = time_kernel(psroi, 10, flush)
-    del os.environ["D2T_PSROI_INT"]
+    lib().d2t_psroi_set_mode(-1, 0)
     out["psroi_fwd_fp64_tables"] = {"ms": ms_x, "gbs": alg / ms_x / 1e6, "frac_hbm": alg / ms_x / 1e6 / hbm_gbs}
     gt = torch.randn_like(top)
     grad = torch.empty_like(feat)

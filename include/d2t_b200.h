@@ -145,6 +145,20 @@ int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int bo
                     float thresh, int max_keep, int* keep, int keep_stride, int* num_keep,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Kernel variant of d2t_psroi_forward / _backward, process-wide (tests and A/B measurements; the defaults are the product):
+ * forward_mode -1 = chosen by the geometry alone (integer tables when the plane fits, never by batch size or SM count),
+ * 0 = exactly-rounded fp64 tables, 1..4 = development variants of the integer tables; backward_mode 0 = fp64 difference
+ * tables, 1 = integer difference tables. */
+int d2t_psroi_set_mode(int forward_mode, int backward_mode);
+/* Fused PSRoI pooling + 7x7 vote (+ softmax) -- rfcn.py:62-64, 133-140, 194-196: vote[n][d] = the mean of the 49
+ * pooled bins of (roi n, output channel d), optionally followed by the softmax over d, without the [R, D, 7, 7] tensor
+ * reaching memory.  Same windows / tables as d2t_psroi_forward; pooled size 7x7, planes at most 64 wide (returns 0
+ * otherwise: use d2t_psroi_forward + a mean). */
+size_t d2t_psroi_vote_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w, int out_dim);
+int d2t_psroi_vote_forward(const float* bottom, int batch, int channels, int height, int width,
+                           const float* rois, int num_rois, float scale, int pooled_h, int pooled_w, int group,
+                           int out_dim, int softmax, float* vote, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
 /* ---- PSRoI with explicit workspace; mapping may be NULL; accumulate=0 overwrites the
  * touched planes of bottom_diff (no pre-zeroing needed for channels < D*G*G).
  * Replaces PSROIPoolForwardLauncher / PSROIPoolBackwardLauncher (psroi_pooling/src/psroi_pooling_kernel.h:8-14) for
@@ -310,6 +324,24 @@ d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, i
                                      int g_pitch, int R, int S, int pad, int dil, const float* xt,
                                      const void* g_hi, const void* g_lo, const float* amax_x,
                                      const float* amax_g, const float* scale, float* dw);
+
+/* Correlation backward on the tensor cores (replaces Correlation_backward_input1 / _input2,
+ * correlation/src/correlation_cuda_kernel.cu:108-290, for kernel_size 1, stride1 == stride2, pad == max_displacement):
+ *   g1[n, y, x, c] = (1/C) sum_t gO[n, y, x, t] * in2[n, (y, x) + t, c]          (lattice coordinates; t = (tj, ti), |.| <= r)
+ *   g2[n, y, x, c] = (1/C) sum_t gO[n, (y, x) - t, t] * in1[n, (y, x) - t, c]
+ * as the GEMM  [positions] x [halo positions] x [channels]  with a banded A operand: d2t_corrb_pack_band expands gO
+ * (channels [c_offset, c_offset + D*D) of an NHWC buffer; flipped = 1 builds the band of g2) to fp16 (hi, lo)
+ * [N][H][W][D][64]; d2t_corrb_pack_other writes the other frame's features, sampled on the correlation lattice, as
+ * fp16 (hi, lo) planes [N][C][OH][pitch]; the plan's output is NHWC [N, OH, OW, out_cstride] channels
+ * [out_coffset, out_coffset + C), every element written, multiplied by scale[c] (pass 1/C). */
+int d2t_corrb_pack_band(const float* g, int N, int H, int W, int c_stride, int c_offset, int r, int flipped,
+                        const float* amax_g, void* e_hi, void* e_lo, cudaStream_t stream);
+int d2t_corrb_pack_other(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
+                         int pitch, const float* amax_x, void* o_hi, void* o_lo, cudaStream_t stream);
+d2t_conv_plan* d2t_corrb_plan_create(int N, int C, int H, int W, int r, const void* e_hi, const void* e_lo,
+                                     const void* o_hi, const void* o_lo, int o_pitch, const float* amax_e,
+                                     const float* amax_o, const float* scale, float* out, int out_cstride,
+                                     int out_coffset);
 
 /* OIHW fp32 -> [Cout][R*S][cin_pad] (w, w_lo); w_lo may be NULL */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,

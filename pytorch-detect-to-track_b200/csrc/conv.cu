@@ -407,7 +407,17 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // columns of one row;
 // tiles are (128 input channels, tap) x (BN output channels); stream-K and the drain are unchanged; the epilogue
 // scales column co by the folded BatchNorm scale and writes the OIHW gradient.
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false>
+//
+// CORRB = true (3xFP16 only) is the BACKWARD of the cross-frame correlation (correlation_cuda_kernel.cu:108-290) on the
+// same pipeline.  With t = (tj, ti) a displacement,  g1[p, c] = (1/C) sum_t gO[p, t] * in2[p + t, c]  is, for a tile of
+// 4 x 32 positions p, the GEMM  D[p, c] = sum_q Band[p, q] * in2[q, c]  over the halo positions q (K = one 64-wide halo
+// row per K block, 4 + 2r of them), where Band[p, q] = gO[p, q - p] inside the (2r+1)^2 window and 0 outside.  Both
+// operands arrive pre-split as fp16 (hi, lo): B = boxes of the other frame's channel-major planes (like WGRAD); A = the
+// band, expanded by d2t_corrb_pack_band to [pixel][tj + r][64 halo columns] so that a tile row's K block is ONE TMA box
+// whose displacement-row coordinate is (halo row - tile row) -- rows outside the window are the TMA's zero fill.  The
+// converter warps only move the landed A tile into tensor memory.  The gradient w.r.t. the second frame is the same GEMM
+// on the flipped band  gO[p + t, -t]  and the first frame's planes.  Epilogue: the ordinary NHWC output path.
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false, bool CORRB = false>
 __global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
 conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
                 const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
@@ -424,6 +434,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
     static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
     static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
+    static_assert(!CORRB || (F16 && !EPI2 && !WGRAD && BN == 128), "the correlation-backward mode is a plain 3xFP16 variant");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
@@ -444,14 +455,14 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int unit_id = blockIdx.x / CS, n_units = gridDim.x / CS;
     const int tiles = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;     // (pair-)tiles
-    const int k_iters = WGRAD ? p.wg_kiters : p.R * p.S * p.kc_blocks;
+    const int k_iters = WGRAD ? p.wg_kiters : (CORRB ? p.TH + 2 * p.corr_r : p.R * p.S * p.kc_blocks);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB_hi);
         if (SPLIT && !CORR) prefetch_tmap(&tmB_lo);
         if (!CORR && p.out) prefetch_tmap(&tmO);
-        if (EPI2 && p.res) prefetch_tmap(&tmR);
+        if ((EPI2 && p.res) || CORRB) prefetch_tmap(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
@@ -523,6 +534,38 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         constexpr int NA = F16 ? 2 : 1;
         constexpr int NL = NA + ((SPLIT && !CORR) ? 2 : 1);
         constexpr int TMA_BYTES = C::A_BYTES + (NL - NA) * C::B_BYTES;
+        if constexpr (CORRB) {
+            // ten copies per stage: the band's (hi, lo) boxes of the four tile rows (32 pixels x 64 halo columns each),
+            // the other frame's (hi, lo) planes (BN channels x 64 halo columns of one halo row)
+            if (lane < 10) {
+                const bool is_a = lane < 8;
+                const int yl = lane & 3;
+                const CUtensorMap* map = lane < 4 ? &tmA : (lane < 8 ? &tmR : (lane == 8 ? &tmB_hi : &tmB_lo));
+                const int dst_off = lane < 4 ? yl * 4096 : (lane < 8 ? C::OFF_ALO + yl * 4096 : (lane == 8 ? C::OFF_BHI : C::OFF_BLO));
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int e = 0; e < sched.nseg; ++e) {
+                    const Seg sg = sched.get(e);
+                    const int t = sg.tile;
+                    const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+                    const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
+                    const int x0 = tw << p.TW_log2, y0 = th * p.TH;
+                    const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                    for (int hr = k_beg; hr < k_end; ++hr) {        // K block = halo row y0 - r + hr
+                        mbar_wait_sleep(&empty[stage], phase ^ 1);
+                        uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
+                        uint64_t* fbar = &full[stage];
+                        if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
+                        if (is_a) tma_load_5d(dst, map, fbar, 0, hr - yl, x0, y0 + yl, img);
+                        else tma_load_4d(dst, map, fbar, x0 - 16, y0 - p.corr_r + hr, n_tile * BN, img);
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else
         if (lane < NL) {
             const bool is_a = lane < NA;
             const CUtensorMap* map = is_a ? &tmA : (lane == NA ? &tmB_hi : &tmB_lo);
@@ -726,6 +769,23 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     TRACED_WAIT(0, &full[stage], phase);
                     tc_fence_after();
                     const uint8_t* row = smem + stage * C::STAGE_BYTES + m * 128;
+                    if constexpr (CORRB) {
+                        // the A tile landed as fp16 already: [128 rows x 64 halves] hi, then lo -- move it to tensor memory
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {         // 0 = hi, 1 = lo
+                            const uint8_t* src = row + part * C::OFF_ALO;
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {     // K elements [32 half, 32 half + 32)
+                                uint32_t w[16];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const uint4 v = *reinterpret_cast<const uint4*>(src + (((uint32_t)(half * 4 + c) ^ sw) << 4));
+                                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                                }
+                                tmem_st16(a_lane + stage * C::A_TMEM_COLS + part * 32 + half * 16, w);
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {             // sub-tile = channels [32 half, 32 half + 32)
                         const uint8_t* src = row + half * (kBlockM * kBoxC * 4);
@@ -1320,13 +1380,14 @@ struct d2t_conv_plan {
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
     int private_scratch;       // 1: the caller supplied the stream-K scratch (no cross-stream guard needed)
     int wgrad;                 // weight-gradient plan (d2t_wgrad_plan_create)
+    int corrb;                 // correlation-backward plan (d2t_corrb_plan_create)
 };
 
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false, bool WGRAD = false>
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false, bool WGRAD = false, bool CORRB = false>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
@@ -1354,7 +1415,7 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
                                    pl->tmR, args),
                 "conv_igemm launch");
     return 1;
@@ -1712,8 +1773,70 @@ extern "C" d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh
     return pl;
 }
 
+
+// Correlation backward (see the CORRB kernel comment): out[n, y, x, c] (+= nothing: every element written) =
+// scale[c] * sum over the (2r+1)^2 window of band * other.  e_hi / e_lo: the expanded band [N][H][W][D][64] fp16
+// (d2t_corrb_pack_band); o_hi / o_lo: the other frame's planes [N][C][H][o_pitch] fp16 (d2t_corrb_pack_other);
+// amax_e / amax_o: the device scalars the two packers scaled with.
+extern "C" d2t_conv_plan* d2t_corrb_plan_create(int N, int C, int H, int W, int r, const void* e_hi, const void* e_lo,
+                                                const void* o_hi, const void* o_lo, int o_pitch, const float* amax_e,
+                                                const float* amax_o, const float* scale, float* out, int out_cstride,
+                                                int out_coffset) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || r < 1 || r > 8 || !e_hi || !e_lo || !o_hi || !o_lo || !amax_e || !amax_o ||
+        !out || o_pitch % 8 != 0 || o_pitch < W || out_cstride % 4 != 0 || out_coffset % 4 != 0 || C % 4 != 0) {
+        set_error("d2t_corrb_plan_create: bad arguments");
+        return nullptr;
+    }
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(d2t_conv_plan)) != 0) {
+        set_error("d2t_corrb_plan_create: out of memory");
+        return nullptr;
+    }
+    d2t_conv_plan* pl = new (mem) d2t_conv_plan();
+    ConvArgs& a = pl->args;
+    const int D = 2 * r + 1, TH = 4, TW = 32;
+    a.N = N; a.OH = H; a.OW = W; a.Cout = C;
+    a.R = 1; a.S = 1; a.stride = 1; a.pad = 0; a.dil = 1; a.kc_blocks = 1;
+    a.TW_log2 = 5; a.TH = TH; a.stem = 0;
+    a.tiles_w = (W + TW - 1) / TW; a.tiles_h = (H + TH - 1) / TH;
+    a.m_tiles = N * a.tiles_h * a.tiles_w;
+    pl->BN = 128;
+    a.n_tiles = (C + 127) / 128;
+    a.scale = scale; a.shift = nullptr; a.res = nullptr; a.res_cstride = C; a.relu = 0;
+    a.out = out; a.out_cstride = out_cstride; a.out_coffset = out_coffset; a.out_nchw = nullptr;
+    a.corr_r = r; a.corr_D = D;
+    a.amax_in = amax_e; a.amax_b = amax_o; a.amax_out = nullptr; a.w_exp = 0;
+    pl->passes = 16; pl->corrb = 1;
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, TH + 2 * r, 16);
+    SkScratch sk;
+    if (!sk_scratch(&sk)) {
+        free(pl);
+        return nullptr;
+    }
+    a.sk_scratch = sk.partial; a.sk_flags = sk.flags; a.sk_epoch = 0;
+    // A: expanded band, dims innermost first {halo column, displacement row, x, y, image}; box = 32 pixels of one tile row
+    const cuuint64_t edims[5] = {64, (cuuint64_t)D, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t estrd[4] = {128, (cuuint64_t)D * 128, (cuuint64_t)W * D * 128, (cuuint64_t)H * W * D * 128};
+    const cuuint32_t ebox[5] = {64u, 1u, (cuuint32_t)TW, 1u, 1u};
+    const cuuint32_t one5[5] = {1u, 1u, 1u, 1u, 1u};
+    // B: planes of the other frame, box = 64 halo columns of one halo row x 128 channels
+    const cuuint64_t odims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
+    const cuuint64_t ostrd[3] = {(cuuint64_t)o_pitch * 2, (cuuint64_t)H * o_pitch * 2, (cuuint64_t)C * H * o_pitch * 2};
+    const cuuint32_t obox[4] = {64u, 1u, 128u, 1u};
+    bool ok = encode(&pl->tmA, e_hi, 5, edims, estrd, ebox, one5, "corrb band hi", true) &&
+              encode(&pl->tmR, e_lo, 5, edims, estrd, ebox, one5, "corrb band lo", true) &&
+              encode(&pl->tmB_hi, o_hi, 4, odims, ostrd, obox, one5, "corrb other hi", true) &&
+              encode(&pl->tmB_lo, o_lo, 4, odims, ostrd, obox, one5, "corrb other lo", true) &&
+              encode_out_map(&pl->tmO, out, N, H, W, C, out_cstride, out_coffset, TH, TW);
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
 extern "C" int d2t_conv_plan_set_mask(d2t_conv_plan* pl, const float* mask, int mask_cstride) {
-    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && (!mask || (mask_cstride % 4 == 0 && mask_cstride >= pl->args.Cout)),
+    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && !pl->corrb && (!mask || (mask_cstride % 4 == 0 && mask_cstride >= pl->args.Cout)),
                 "d2t_conv_plan_set_mask: needs a convolution plan and a mask with a channel stride that is a multiple of 4");
     pl->args.mask = mask;
     pl->args.mask_cstride = mask_cstride;
@@ -1789,6 +1912,7 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->wgrad)
         return pl->BN == 64 ? launch_conv<64, 16, false, false, false, true>(pl, stream)
                             : launch_conv<128, 16, false, false, false, true>(pl, stream);
+    if (pl->corrb) return launch_conv<128, 16, false, false, false, false, true>(pl, stream);
     if (pl->corr)
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))

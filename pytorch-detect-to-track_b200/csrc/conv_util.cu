@@ -201,15 +201,17 @@ nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, 
 // plane_s[u] = g[u - dx_s] (zero outside [0, OW)) -- the filter column's offset cannot be a TMA start coordinate (see
 // conv.cu, WGRAD), so it is materialised here.  The tile is loaded with an 8-column halo on both sides (|dx| <= 8).
 __global__ void __launch_bounds__(256)
-nhwc_to_planes_split(const float* __restrict__ g, int N, int OH, int OW, int cs, int C, int pitch, int S, int dil, int pad,
-                     const float* __restrict__ amax, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+nhwc_to_planes_split(const float* __restrict__ g, int N, int Hs, int Ws, int stride, int OH, int OW, int cs, int C, int pitch,
+                     int S, int dil, int pad, const float* __restrict__ amax, __half* __restrict__ out_hi,
+                     __half* __restrict__ out_lo) {
     __shared__ float tile[48][33];
     const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float sa = pow2f(act_exp(amax));
     for (int j = ty; j < 48; j += 8) {
         const int xo = wt - 8 + j, c = ct + tx;
-        tile[j][tx] = (xo >= 0 && xo < OW && c < C) ? __ldg(g + (((size_t)n * OH + oy) * OW + xo) * cs + c) * sa : 0.f;
+        tile[j][tx] = (xo >= 0 && xo < OW && c < C)
+                          ? __ldg(g + (((size_t)n * Hs + (size_t)oy * stride) * Ws + (size_t)xo * stride) * cs + c) * sa : 0.f;
     }
     __syncthreads();
     const size_t copy = (size_t)N * C * OH * pitch;
@@ -226,6 +228,46 @@ nhwc_to_planes_split(const float* __restrict__ g, int N, int OH, int OW, int cs,
             }
         }
     }
+}
+
+// correlation backward, A operand: the gradient of the correlation output gO [N, H, W, D*D] (channels [coff, coff + D*D)
+// of an NHWC buffer), expanded to [N][H][W][D][64] fp16 (hi, lo) of gO * 2^k:  row (pixel, tj + r) holds the D values
+// gO[pixel, (tj + r) D + ti + r] at halo columns hc = (x mod 32) + 16 + ti, zeros elsewhere -- the position the other
+// frame's pixel (x + ti) has inside the 64-column halo row [x0 - 16, x0 + 48) of the pixel's 32-wide tile, so that a
+// tile row's slice of the band matrix is one TMA box (conv.cu, CORRB).  flipped: the band of the gradient w.r.t. the
+// SECOND frame, E[p, t] = gO[p + t, -t] (zero where p + t leaves the map).  One warp per row, one half2 per lane.
+__global__ void __launch_bounds__(256)
+corr_band_pack(const float* __restrict__ g, int N, int H, int W, int cs, int coff, int r, int flipped,
+               const float* __restrict__ amax, __half2* __restrict__ e_hi, __half2* __restrict__ e_lo) {
+    const int D = 2 * r + 1;
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (size_t)N * H * W * D) return;
+    const int lane = threadIdx.x & 31;
+    const int tjr = (int)(row % D);
+    const size_t pix = row / D;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / W / H);
+    const float sa = pow2f(act_exp(amax));
+    const int hc0 = (x & 31) + 16 - r;                 // halo column of ti = -r
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int tir = 2 * lane + q - hc0;
+        float val = 0.f;
+        if (tir >= 0 && tir < D) {
+            if (!flipped) {
+                val = __ldg(g + (size_t)pix * cs + coff + tjr * D + tir);
+            } else {
+                const int ys = y + tjr - r, xs = x + tir - r;          // source pixel p + t
+                if (ys >= 0 && ys < H && xs >= 0 && xs < W)
+                    val = __ldg(g + (((size_t)n * H + ys) * W + xs) * cs + coff + (2 * r - tjr) * D + (2 * r - tir));
+            }
+        }
+        v[q] = val * sa;
+    }
+    const __half2 h = __floats2half2_rn(v[0], v[1]);
+    const float2 hf = __half22float2(h);
+    e_hi[row * 32 + lane] = h;
+    e_lo[row * 32 + lane] = __floats2half2_rn(v[0] - hf.x, v[1] - hf.y);
 }
 
 // backward of a stride-2 1x1 convolution's input + ReLU:  out[n, y, x, :] = mask > 0 ? (even(y, x) ? low[n, y/2, x/2, :] : 0)
@@ -351,9 +393,37 @@ extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_
                 "d2t_wgrad_pack_grad: bad arguments (row pitch a multiple of 8, column shifts within +-8)");
     dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_grad: tensor too large for the launch grid");
-    nhwc_to_planes_split<<<grid, 256, 0, stream>>>(g, N, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
+    nhwc_to_planes_split<<<grid, 256, 0, stream>>>(g, N, OH, OW, 1, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
                                                    reinterpret_cast<__half*>(g_hi), reinterpret_cast<__half*>(g_lo));
     D2T_CHECK_LAUNCH("nhwc_to_planes_split");
+    return 1;
+}
+
+// ---- correlation backward (conv.cu, CORRB): operand packers
+// the other frame's features, sampled on the correlation lattice (stride 2 for conv3), as fp16 (hi, lo) planes
+extern "C" int d2t_corrb_pack_other(const float* x, int N, int H, int W, int c_stride, int C, int stride, int OH, int OW,
+                                    int pitch, const float* amax_x, void* o_hi, void* o_lo, cudaStream_t stream) {
+    D2T_REQUIRE(x && o_hi && o_lo && amax_x && N > 0 && H > 0 && W > 0 && C > 0 && c_stride >= C && stride > 0 && OH > 0 &&
+                    OW > 0 && pitch >= OW && pitch % 8 == 0 && (OH - 1) * stride < H && (OW - 1) * stride < W,
+                "d2t_corrb_pack_other: bad arguments (row pitch a multiple of 8)");
+    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_corrb_pack_other: tensor too large for the launch grid");
+    nhwc_to_planes_split<<<grid, 256, 0, stream>>>(x, N, H, W, stride, OH, OW, c_stride, C, pitch, 1, 1, 0, amax_x,
+                                                   reinterpret_cast<__half*>(o_hi), reinterpret_cast<__half*>(o_lo));
+    D2T_CHECK_LAUNCH("nhwc_to_planes_split (corrb)");
+    return 1;
+}
+
+extern "C" int d2t_corrb_pack_band(const float* g, int N, int H, int W, int c_stride, int c_offset, int r, int flipped,
+                                   const float* amax_g, void* e_hi, void* e_lo, cudaStream_t stream) {
+    D2T_REQUIRE(g && e_hi && e_lo && amax_g && N > 0 && H > 0 && W > 0 && r >= 1 && r <= 8 && c_offset >= 0 &&
+                    c_stride >= c_offset + (2 * r + 1) * (2 * r + 1),
+                "d2t_corrb_pack_band: bad arguments");
+    const size_t rows = (size_t)N * H * W * (2 * r + 1);
+    D2T_REQUIRE(rows < ((size_t)1 << 31), "d2t_corrb_pack_band: tensor too large");
+    corr_band_pack<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(g, N, H, W, c_stride, c_offset, r, flipped, amax_g,
+                                                                 reinterpret_cast<__half2*>(e_hi), reinterpret_cast<__half2*>(e_lo));
+    D2T_CHECK_LAUNCH("corr_band_pack");
     return 1;
 }
 

@@ -26,6 +26,8 @@
 //     D2T_PSROI_INT=0 forces it.
 // The generic kernels below keep the reference's summation order bit for bit and serve every other geometry and the
 // reference-named launcher, which is not told the batch size.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace d2t {
@@ -640,7 +642,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             // an item is pooled by direct summation in the reference's own order instead (bit-identical to
             // psroi_pooling_kernel.cu:62-76): rare, slower, exact.
             const float rest = l1 - mx;
-            unsafe_p[tid] = (!(l1 < 3.0e38f) || mx * (float)(HW - 1) > 16384.f * rest) ? 1 : 0;
+            unsafe_p[tid] = (LROI && (!(l1 < 3.0e38f) || mx * (float)(HW - 1) > 16384.f * rest)) ? 1 : 0;
             // l1 < 2^(eb - 126) for the biased exponent eb of l1  =>  k = 30 - (eb - 126); powers of two built from bits
             const int eb = (int)((__float_as_uint(l1) >> 23) & 0xffu);
             int k = (eb > 0 && eb < 255) ? 156 - eb : 0;
@@ -699,7 +701,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
         }
         __syncthreads();
         // ---- (3) column scan: one thread per (plane, column)
-        for (int i = tid; i < G * W; i += THREADS) {
+        for (int i = tid; i < (direct ? 0 : G * W); i += THREADS) {
             const int p = i / W;
             int* col = S + p * HW + (i - p * W);
             int acc = 0;
@@ -831,6 +833,22 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 uint32_t a0 = smem_u32(S) + (uint32_t)(max(hs - 1, 0) * W) * 4u;
                 const float fh = (float)hgt;
                 float o[G];
+                if (direct) {
+                    // guard path: the planes are still fp32 -- sum every window cell by cell in the reference's order
+                    // (psroi_pooling_kernel.cu:62-76: h outer, w inner, fp32 adds, one IEEE division)
+#pragma unroll
+                    for (int pw = 0; pw < G; ++pw) {
+                        const unsigned wb = wbv[pw];
+                        const int wsx = wb & 0xff, we = wb >> 8;
+                        float sum = 0.f;
+                        if (mine) {
+                            const float* P = pl + pw * HW;
+                            for (int h = hs; h < he; ++h)
+                                for (int w = wsx; w < we; ++w) sum += P[h * W + w];
+                        }
+                        o[pw] = (hgt > 0 && we > wsx) ? __fdiv_rn(sum, (float)(hgt * (we - wsx))) : 0.f;
+                    }
+                } else
 #pragma unroll
                 for (int pw = 0; pw < G; ++pw) {
                     const unsigned wb = wbv[pw];
@@ -847,6 +865,16 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                     o[pw] = (hgt > 0 && we > wsx) ? v : 0.f;  // empty bin -> 0 (psroi_pooling_kernel.cu:63,76)
                     a1 += (uint32_t)HW * 4u;
                     a0 += (uint32_t)HW * 4u;
+                }
+                if (vpart) {
+                    // fused 7x7 vote (rfcn.py:136-140): this item's share of the RoI's class score is the sum of its G bins;
+                    // partial sums go out as [class][bin row][roi] -- one coalesced 128-byte store per warp instead of 32
+                    // scattered 28-byte runs -- and psroi_vote_finish adds the G rows in a fixed order
+                    float sum = 0.f;
+#pragma unroll
+                    for (int pw = 0; pw < G; ++pw) sum += o[pw];
+                    if (mine) vpart[(size_t)(ctop * G + ph) * Rp + ck * 32 + lane] = sum;
+                    continue;
                 }
                 int ibase = ck * 32 * per_roi + obase;         // (launcher: num_rois * per_roi < 2^31)
 #pragma unroll
@@ -879,6 +907,40 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
         }
     }
     if (!waited_for_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---- second half of the fused PSRoI + vote: vote[n][d] = (1 / G^2) * sum_ph vpart[d][ph][n] (fixed order), optionally
+// followed by the softmax over the D classes (rfcn.py:139: F.softmax(cls_score, 1)).  One thread per roi; reads are
+// coalesced over the rois, the [R][D] result is a few hundred KB.
+template <int G>
+__global__ void psroi_vote_finish(const float* __restrict__ vpart, const int* __restrict__ rb, int R, int Rp, int D,
+                                  int softmax, float* __restrict__ vote) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= R) return;
+    float* o = vote + (size_t)n * D;
+    if (__ldg(rb + n) < 0) {                       // roi of no image: zeros, like the pooled output (then softmax of zeros)
+        for (int d = 0; d < D; ++d) o[d] = softmax ? 1.f / (float)D : 0.f;
+        return;
+    }
+    float mx = -3.402823466e+38f;
+    for (int d = 0; d < D; ++d) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < G; ++ph) sum += __ldg(vpart + (size_t)(d * G + ph) * Rp + n);
+        const float v = sum * (1.f / (float)(G * G));
+        o[d] = v;
+        mx = fmaxf(mx, v);
+    }
+    if (softmax) {
+        float den = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float e = __expf(o[d] - mx);
+            o[d] = e;
+            den += e;
+        }
+        const float inv = 1.f / den;
+        for (int d = 0; d < D; ++d) o[d] *= inv;
+    }
 }
 
 // ---- backward: the adjoint of the summed-area-table forward ----
@@ -1266,6 +1328,20 @@ extern "C" __attribute__((visibility("default"))) int d2t_psroi_trace_read(long 
 }
 #endif
 
+// Kernel variant selection: process-wide, explicit (tests, A/B runs); the environment only seeds the initial value once.
+//   forward : -1 = by geometry (default), 0 = exactly-rounded fp64 tables, 1..4 = a development variant of the integer tables
+//   backward:  0 = fp64 difference tables (default), 1 = integer difference tables (measured slower: 144 vs 91 us, config 5)
+static std::atomic<int> g_psroi_fwd_mode{[] { const char* e = getenv("D2T_PSROI_INT"); return e ? atoi(e) : -1; }()};
+static std::atomic<int> g_psroi_bwd_mode{[] { const char* e = getenv("D2T_PSROI_BWD_INT"); return e ? atoi(e) : 0; }()};
+
+extern "C" int d2t_psroi_set_mode(int forward_mode, int backward_mode) {
+    D2T_REQUIRE(forward_mode >= -1 && forward_mode <= 4 && backward_mode >= 0 && backward_mode <= 1,
+                "d2t_psroi_set_mode: forward -1..4, backward 0..1");
+    g_psroi_fwd_mode = forward_mode;
+    g_psroi_bwd_mode = backward_mode;
+    return 1;
+}
+
 extern "C" size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w) {
     (void)batch;
     return align_up(psroi_ws_bytes(num_rois, pooled_h, pooled_w), 256);
@@ -1293,11 +1369,11 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
         // to 4.9 M, but the kernel is bound by its five barrier-separated phases (per item, cycles: load + L1 norm 3.8 k, row
         // scan 4.5 k, column scan 2.2 k, lookups 13.7 k) at 2.84 items per CTA, not by the gathers; the exactly-rounded fp64
         // kernel therefore stays the product path.
-        const char* int_env1 = getenv("D2T_PSROI_INT");
+        const int fwd_mode = g_psroi_fwd_mode.load();
         const size_t buf_bytes = (((size_t)group * height * width + 4 + 3) & ~(size_t)3) * sizeof(float);
         const int nbuf = (int)(kMaxDynSmem / buf_bytes) >= 3 ? 3 : (int)(kMaxDynSmem / buf_bytes);
         if (width <= 64 && group * height <= 32 * 12 && nbuf >= 2 &&
-            (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31) && int_env1 && atoi(int_env1) == 1) {
+            (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31) && fwd_mode == 1) {
             const int rw = (group * height + 31) / 32;
             auto kern = rw <= 3 ? psroi_fwd_isat<7, 3> : (rw <= 6 ? psroi_fwd_isat<7, 6> : (rw <= 9 ? psroi_fwd_isat<7, 9> : psroi_fwd_isat<7, 12>));
             static SmemAttrOnce once_i[4];
@@ -1323,20 +1399,22 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
         constexpr int kMcCtas = 3;
         constexpr int kMcDefaultThreads = 256;
         constexpr size_t kMcSmem = 70 * 1024;      // 3 x (70 KB + 4 KB static + 1 KB reserved) <= 227 KB per SM
-        // Path selection.  D2T_PSROI_INT unset: the integer-table multi-CTA kernel (mode 4) whenever the geometry fits and
-        // there is more than one item per SM (with fewer, a 1024-thread CTA finishes its single item sooner: measured
-        // 15.3 against 17.4 us for 84 items); D2T_PSROI_INT=0: always the exactly-rounded fp64 tables; 1..4: force a variant.
-        const char* int_env = getenv("D2T_PSROI_INT");
+        // Path selection.  D2T_PSROI_INT unset: the integer-table multi-CTA kernel (mode 4) whenever the geometry fits (for
+        // fewer items than SMs a 1024-thread fp64-table CTA would finish ~2 us sooner -- 15.3 against 17.4 us for 84 items --
+        // but results must not depend on the batch size); D2T_PSROI_INT=0: always the exactly-rounded fp64 tables; 1..4:
+        // force a variant.
+        // The choice depends on the GEOMETRY only (never on the batch size or the SM count), so the same (features, roi)
+        // pair gives the same bits in any batch on any device.
         const bool mc_fits = width <= 64 && buf_bytes <= kMcSmem && group * height <= kMcMaxRows &&
                              (size_t)num_rois * out_dim * group * group < ((size_t)1 << 31);
-        const int mode_sel = int_env ? atoi(int_env) : ((mc_fits && items > sm_count()) ? 4 : 0);
+        const int mode_sel = fwd_mode >= 0 ? fwd_mode : (mc_fits ? 4 : 0);
         if (mc_fits && mode_sel >= 2) {
             const int mode = mode_sel;
             const int lroi = mode >= 3;     // 3: lane -> roi lookups, 4: + thread-per-row scans (see the kernel)
-            const int thr_env = getenv("D2T_PSROI_THREADS") ? atoi(getenv("D2T_PSROI_THREADS")) : kMcDefaultThreads;
+            static const int thr_env = getenv("D2T_PSROI_THREADS") ? atoi(getenv("D2T_PSROI_THREADS")) : kMcDefaultThreads;
             const int wide = thr_env == 384;
             int kMcThreads = wide ? 384 : 256;
-            using Kern = void (*)(const float*, int, int, int, int, int, int, PsroiWs, float*, int*);
+            using Kern = void (*)(const float*, int, int, int, int, int, int, PsroiWs, float*, int*, float*);
             static const Kern kerns[2][2] = {{psroi_fwd_isat_mc<7, 256, kMcCtas, false>, psroi_fwd_isat_mc<7, 384, kMcCtas, false>},
                                              {psroi_fwd_isat_mc<7, 256, kMcCtas, true>, psroi_fwd_isat_mc<7, 384, kMcCtas, true>}};
             Kern kern = kerns[lroi][wide];
@@ -1372,7 +1450,7 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bottom, batch, channels, height, width, out_dim, num_rois, ws, top,
-                                           mapping),
+                                           mapping, (float*)nullptr),
                         "psroi_fwd_isat_mc launch");
             return 1;
         }
@@ -1397,6 +1475,70 @@ extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, i
     psroi_fwd_generic<<<grid_for(total), 256, 0, stream>>>(bottom, batch, channels, height, width, rois, num_rois,
                                                           scale, pooled_h, pooled_w, group, out_dim, top, mapping);
     D2T_CHECK_LAUNCH("psroi_fwd_generic");
+    return 1;
+}
+
+
+// ---- fused PSRoI pooling + 7x7 vote (+ softmax): SURVEY 8f rank 2; rfcn.py:62-64, 133-140, 194-196 ----
+// vote[n][d] = mean over the 49 bins of the pooled [n][d][7][7] block, i.e. AvgPool2d(7) of d2t_psroi_forward's output,
+// without the [R, D, 7, 7] tensor ever reaching memory.  Runs the integer-table multi-CTA kernel (with its dynamic-range
+// guard) for every problem size; geometries that kernel does not take (planes wider than 64, pooled size != 7) return 0.
+extern "C" size_t d2t_psroi_vote_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w, int out_dim) {
+    return d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w) +
+           align_up((size_t)psroi_rp(num_rois) * out_dim * pooled_h * sizeof(float), 256);
+}
+
+extern "C" int d2t_psroi_vote_forward(const float* bottom, int batch, int channels, int height, int width,
+                                      const float* rois, int num_rois, float scale, int pooled_h, int pooled_w, int group,
+                                      int out_dim, int softmax, float* vote, void* workspace, size_t workspace_bytes,
+                                      cudaStream_t stream) {
+    D2T_REQUIRE(batch > 0 && channels > 0 && height > 0 && width > 0 && pooled_h > 0 && pooled_w > 0 && group > 0 &&
+                    out_dim > 0 && num_rois >= 0,
+                "d2t_psroi_vote_forward: bad sizes");
+    if (num_rois == 0) return 1;
+    D2T_REQUIRE(bottom && rois && vote && workspace && ((uintptr_t)workspace & 3) == 0 &&
+                    workspace_bytes >= d2t_psroi_vote_workspace_bytes(num_rois, batch, pooled_h, pooled_w, out_dim),
+                "d2t_psroi_vote_forward: null pointer or workspace smaller than d2t_psroi_vote_workspace_bytes()");
+    size_t smem = 0;
+    constexpr int kCtas = 3;
+    constexpr size_t kSmem = 70 * 1024;
+    const size_t buf_bytes = (((size_t)group * height * width + 4 + 3) & ~(size_t)3) * sizeof(float);
+    D2T_REQUIRE(planes_path_ok(batch, channels, height, width, pooled_h, pooled_w, group, out_dim, true, &smem) &&
+                    width <= 64 && buf_bytes <= kSmem && group * height <= kMcMaxRows,
+                "d2t_psroi_vote_forward: geometry not covered by the fused kernel (7x7 bins, planes <= 64 wide)");
+    PsroiWs ws = carve(workspace, num_rois, pooled_h, pooled_w);
+    float* vpart = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
+                                            d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w));
+    if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, nullptr, out_dim, 0, stream)) return 0;
+    auto kern = psroi_fwd_isat_mc<7, 256, kCtas, true, true>;
+    static SmemAttrOnce once;
+    static bool carveout_set[64] = {};
+    if (!once.ensure(kern, kSmem, "psroi vote smem attr")) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!carveout_set[dev]) {
+        D2T_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                    "psroi vote carveout");
+        carveout_set[dev] = true;
+    }
+    const int items = batch * out_dim * group;
+    cudaLaunchConfig_t cfg = {};
+    const int slots = kCtas * sm_count();
+    cfg.gridDim = dim3(items < slots ? items : slots);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = buf_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap with psroi_prep
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bottom, batch, channels, height, width, out_dim, num_rois, ws,
+                                   (float*)nullptr, (int*)nullptr, vpart),
+                "psroi_fwd_isat_mc (vote) launch");
+    psroi_vote_finish<7><<<(num_rois + 127) / 128, 128, 0, stream>>>(vpart, ws.rb, num_rois, psroi_rp(num_rois), out_dim,
+                                                                     softmax, vote);
+    D2T_CHECK_LAUNCH("psroi_vote_finish");
     return 1;
 }
 
@@ -1429,8 +1571,7 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
         {   // EXPERIMENT, off unless D2T_PSROI_BWD_INT=1: integer difference tables, three CTAs per SM (psroi_bwd_isat_mc)
             const size_t tbytes = (size_t)group * (height + 1) * ((width + 1) | 1) * sizeof(int);
             constexpr size_t kBwdSmem = 72 * 1024;     // 3 x (72 KB + static + 1 KB reserved) <= 227 KB per SM
-            const char* e = getenv("D2T_PSROI_BWD_INT");
-            if (e && atoi(e) == 1 && tbytes <= kBwdSmem) {
+            if (g_psroi_bwd_mode.load() == 1 && tbytes <= kBwdSmem) {
                 auto kern = psroi_bwd_isat_mc<7, 256, 3>;
                 static SmemAttrOnce once_b;
                 static bool carve_b[64] = {};

@@ -332,6 +332,59 @@ class WgradLayer(_Planned):
         return self.grad_w
 
 
+class CorrBwdScratch(object):
+    """operand buffers of the correlation-backward GEMM (csrc/conv.cu, CORRB), reused by every CorrBwdLayer of an engine:
+    the expanded band [N][H][W][D][64] and the other frame's planes [N][C][H][pitch], fp16 (hi, lo) each"""
+
+    def __init__(self, band_halfs, other_halfs, device="cuda"):
+        self.e_hi = torch.zeros(band_halfs, device=device, dtype=torch.float16)
+        self.e_lo = torch.zeros(band_halfs, device=device, dtype=torch.float16)
+        self.o_hi = torch.zeros(other_halfs, device=device, dtype=torch.float16)
+        self.o_lo = torch.zeros(other_halfs, device=device, dtype=torch.float16)
+
+    @staticmethod
+    def need(N, C, H, W, r):
+        return N * H * W * (2 * r + 1) * 64, N * C * H * ((W + 7) // 8 * 8)
+
+
+class CorrBwdLayer(_Planned):
+    """Gradient of the cross-frame correlation (kernel_size 1, stride1 == stride2 = stride, pad == max_displacement) with
+    respect to ONE of its inputs, on the tensor cores:  which = 1: d/d(input1) from (gO, input2); which = 2: d/d(input2) from
+    (gO, input1).  `gout`: NHWC buffer holding gO in channels [coff, coff + D*D) (its amax current); `other`: the other
+    frame's NHWC features; `out`: NHWC gradient on the correlation LATTICE ([N, ceil(H/stride), ceil(W/stride), C]: for
+    stride 2 the gradient lives on the even positions only) -- every element written.  Three launches."""
+
+    def __init__(self, gout, coff, other, out, md, stride, which, scratch):
+        r = md // stride
+        self.r, self.D, self.which, self.stride = r, 2 * r + 1, which, stride
+        self.gout, self.coff, self.other, self.out, self.scratch = gout, coff, other, out, scratch
+        N, H, W, Cc = out.N, out.H, out.W, other.C
+        assert (gout.N, gout.H, gout.W) == (N, H, W) and other.N == N
+        assert H == -(-other.H // stride) and W == -(-other.W // stride)
+        self.pitch = (W + 7) // 8 * 8
+        nb, no = CorrBwdScratch.need(N, Cc, H, W, r)
+        if nb > scratch.e_hi.numel() or no > scratch.o_hi.numel():
+            raise ValueError("CorrBwdScratch too small")
+        self.inv = torch.full((Cc,), 1.0 / Cc, device=out.x.device)
+        self.plan = lib().d2t_corrb_plan_create(N, Cc, H, W, r, _p(scratch.e_hi), _p(scratch.e_lo), _p(scratch.o_hi),
+                                                _p(scratch.o_lo), self.pitch, _p(gout.amax), _p(other.amax), _p(self.inv),
+                                                _p(out.x), out.cstride, 0)
+        if not self.plan:
+            raise D2TError("d2t_corrb_plan_create failed: %s" % lib().d2t_last_error().decode())
+        self.flops = 2.0 * N * H * W * self.D * self.D * Cc
+
+    def run(self, stream=None):
+        g, o, sc, out = self.gout, self.other, self.scratch, self.out
+        st = _stream() if stream is None else stream
+        check(lib().d2t_corrb_pack_band(_p(g.x), g.N, g.H, g.W, g.cstride, self.coff, self.r, int(self.which == 2), _p(g.amax),
+                                        _p(sc.e_hi), _p(sc.e_lo), st), "d2t_corrb_pack_band")
+        check(lib().d2t_corrb_pack_other(_p(o.x), o.N, o.H, o.W, o.cstride, o.C, self.stride, out.H, out.W, self.pitch,
+                                         _p(o.amax), _p(sc.o_hi), _p(sc.o_lo), st), "d2t_corrb_pack_other")
+        check(lib().d2t_conv_plan_run(self.plan, st), "d2t_conv_plan_run")
+        ops._count(3)
+        return out
+
+
 def upsample2_add_mask(low, out, extra=None, mask=None):
     """out = mask > 0 ? (even positions: low) + extra : 0; max |out| -> out.amax (csrc/conv_util.cu)"""
     assert out.cstride == out.C == low.cstride and (extra is None or extra.cstride == out.cstride)

@@ -199,20 +199,17 @@ class D2TEngine(object):
                                  self.post_nms, self.nms_thresh)                        # [2B, R, 5]
         R = rois_all.size(1)
         flat = rois_all.view(-1, 5)
-        # ---- detection heads
-        pooled_cls, _ = ops.psroi_forward(self.cls_map, flat, 7, 7, 1.0 / 16.0, 7, self.n_classes)
-        pooled_loc, _ = ops.psroi_forward(self.bbox_map, flat, 7, 7, 1.0 / 16.0, 7, 4 * self.n_reg)
-        cls_prob = F.softmax(pooled_cls.mean((2, 3)), dim=1).view(L, B, R, -1)
-        bbox_pred = pooled_loc.mean((2, 3)).view(L, B, R, -1)
+        # ---- detection heads: PSRoI pooling + 7x7 vote (+ softmax) fused (rfcn.py:133-140)
+        cls_prob = ops.psroi_vote(self.cls_map, flat, 7, 7, 1.0 / 16.0, 7, self.n_classes, softmax=True).view(L, B, R, -1)
+        bbox_pred = ops.psroi_vote(self.bbox_map, flat, 7, 7, 1.0 / 16.0, 7, 4 * self.n_reg).view(L, B, R, -1)
         rois = rois_all.view(L, B, R, 5).clone()
         rois[1, :, :, 0] -= B                                                           # per-leg image index
         # ---- tracking branch
         for layer in self.corr_layers:
             layer.run()
         self.trk_layer.run()
-        pooled_trk, _ = ops.psroi_forward(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
-                                          4 * self.n_reg)
-        tracking_pred = pooled_trk.mean((2, 3)).view(B * R, -1)
+        tracking_pred = ops.psroi_vote(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
+                                       4 * self.n_reg).view(B * R, -1)                  # rfcn.py:192-196
         zero = im_data.new_zeros(L, 1)
         return (rois, cls_prob, bbox_pred, tracking_pred, zero, zero.clone(), zero.clone(), zero.clone(), [],
                 im_data.new_zeros(1))

@@ -57,7 +57,7 @@ def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, wan
     """psroi_pooling/functions/psroi_pool.py:18-33 -> d2t_psroi_forward.  Returns (top, mapping);
     mapping is None unless want_mapping (then the kernel writes it, as the reference's does).
     The library picks the table kernel (csrc/psroi.cu): per-plane fixed-point int32 tables when there is more than one
-    (image, class, bin-row) item per SM, fp64 tables otherwise or when the environment has D2T_PSROI_INT=0."""
+    (image, class, bin-row) item per SM, always for planes up to 64 wide (d2t_psroi_set_mode(0, 0) forces the exactly-rounded fp64 tables)."""
     _req(features, "features"), _req(rois, "rois")
     if rois.dim() != 2 or rois.size(1) != 5:
         raise ValueError("rois must be [R, 5]")   # the reference returns 0 silently (psroi_pooling_cuda.c:17-20)
@@ -73,6 +73,25 @@ def psroi_forward(features, rois, pooled_h, pooled_w, scale, group, out_dim, wan
                                       ws.data_ptr(), ws.numel(), _stream()), "d2t_psroi_forward")
         _count(2)
     return top, mapping
+
+
+def psroi_vote(features, rois, pooled_h, pooled_w, scale, group, out_dim, softmax=False):
+    """Fused PSRoI pooling + 7x7 vote (+ softmax over the classes): rfcn.py:133-140 / 194-196 in one pass -- what
+    ``AvgPool2d(7)(psroi(features, rois)).view(R, D)`` (then ``F.softmax(.., 1)``) returns, without the [R, D, 7, 7] tensor.
+    -> [R, out_dim].  Eval-path operator (no autograd)."""
+    _req(features, "features"), _req(rois, "rois")
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be [R, 5]")
+    B, Cc, H, W = features.shape
+    R = rois.size(0)
+    with torch.cuda.device_of(features):
+        vote = torch.empty(R, out_dim, device=features.device)
+        ws = _ws(lib().d2t_psroi_vote_workspace_bytes(R, B, pooled_h, pooled_w, out_dim), features.device)
+        check(lib().d2t_psroi_vote_forward(features.data_ptr(), B, Cc, H, W, rois.data_ptr(), R, scale, pooled_h, pooled_w,
+                                           group, out_dim, int(softmax), vote.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _stream()), "d2t_psroi_vote_forward")
+        _count(3)
+    return vote
 
 
 def psroi_backward(top_diff, rois, feature_size, pooled_h, pooled_w, scale, group, out_dim):

@@ -122,6 +122,32 @@ class D2TTrainEngine(D2TEngine):
         self.g_trk = dc.ActTensor(B, H, W, n_loc, cstride=dc._pad32(n_loc), device=dev)
         self.g_trk_in = dc.ActTensor(B, H, W, self.trk_in.cstride, cstride=self.trk_in.cstride, device=dev)
 
+        # ---- correlation backward: (gradient slice of the concat buffer, other frame's features) -> feature gradients
+        self.corr_bwd, self._extra = [], {}
+        coff = 2 * n_loc
+        specs = []
+        for corr, tag in ((net.conv3_corr_layer, 5), (net.conv4_corr_layer, 6), (net.conv5_corr_layer, 7)):
+            f = self.feat_nhwc[tag]
+            st, r = corr.stride1, corr.max_displacement // corr.stride2
+            assert corr.kernel_size == 1 and corr.stride1 == corr.stride2 and corr.pad_size == corr.max_displacement
+            specs.append((corr, tag, f, st, r, coff))
+            coff += (2 * r + 1) ** 2
+        nb_, no_ = 0, 0
+        for corr, tag, f, st, r, co in specs:
+            a, b_ = dc.CorrBwdScratch.need(B, f.C, -(-f.H // st), -(-f.W // st), r)
+            nb_, no_ = max(nb_, a), max(no_, b_)
+        self.cscratch = dc.CorrBwdScratch(nb_, no_, dev)
+        for corr, tag, f, st, r, co in specs:
+            # the gradient lives on the correlation lattice: for conv3 (stride 2) that is the even positions, a
+            # [N, 38, 63, C] tensor that joins the stride-2 backward-data of layer3's first block before the scatter
+            ex = dc.ActTensor(N, -(-f.H // st), -(-f.W // st), f.C, cstride=f.C, device=dev)
+            self._extra[tag] = ex
+            for which in (1, 2):
+                other = f.batch_slice(B, N) if which == 1 else f.batch_slice(0, B)
+                out = ex.batch_slice(0, B) if which == 1 else ex.batch_slice(B, N)
+                layer = dc.CorrBwdLayer(self.g_trk_in, co, other, out, corr.max_displacement, st, which, self.cscratch)
+                layer.set_scratch(self.scratch)
+                self.corr_bwd.append(layer)
         # ---- tracking head conv
         self._wgrad(self.trk_layer, self.trk_in, self.g_trk)
         self._dgrad(self.trk_layer, self.g_trk, self.g_trk_in, out_channels=self.trk_in.cstride)
@@ -165,9 +191,8 @@ class D2TTrainEngine(D2TEngine):
 
     @property
     def extra(self):
-        """gradients arriving at the conv3 / conv4 / conv5 features from the three correlations (tag -> ActTensor)"""
-        if not hasattr(self, "_extra"):
-            self._extra = {tag: self._G(self.feat_nhwc[tag]) for tag in (5, 6, 7)}
+        """gradients arriving at the conv3 / conv4 / conv5 features from the three correlations (tag -> ActTensor on the
+        correlation lattice)"""
         return self._extra
 
     def _grad_buf(self, p):
@@ -234,33 +259,24 @@ class D2TTrainEngine(D2TEngine):
         else:
             assert stride == 2 and ds is not None
             low = dc.ActTensor(g1.N, g1.H, g1.W, x.C, cstride=gx.cstride, device=self.device)
-            self._dgrad(c1, g1, low)
+            self._dgrad(c1, g1, low, residual=extra)                     # (the stride-2 correlation's gradient: same lattice)
             self._dgrad(ds, g_out, low, residual=low)
             assert gx.cstride == x.cstride == x.C, "the scatter kernel wants one channel stride"
-            self.bwd.append((lambda: dc.upsample2_add_mask(low, gx, extra=extra, mask=x), None, 'upsample2_add_mask'))
+            self.bwd.append((lambda: dc.upsample2_add_mask(low, gx, mask=x), None, 'upsample2_add_mask'))
         return gx
 
     # ------------------------------------------------------------------ per-step pieces
     def _tracking_split(self):
         """g_trk_in [B, H, W, 2*n_loc + 81 + 289 + 289] -> the two legs of the loc map's gradient and, through the
-        correlation backward kernels, the gradients of the conv3 / conv4 / conv5 features of both frames"""
-        B, N = self.B, self.N
+        tensor-core correlation backward (csrc/conv.cu, CORRB), the gradients of the conv3 / conv4 / conv5 features"""
+        B = self.B
         n_loc = 4 * self.n_reg * 49
         gi = self.g_trk_in
         self.g_bbox.x[:B, :, :, :n_loc] += gi.x[..., :n_loc]
         self.g_bbox.x[B:, :, :, :n_loc] += gi.x[..., n_loc:2 * n_loc]
         torch.amax(self.g_bbox.x.abs().view(-1), 0, keepdim=True, out=self.g_bbox.amax)
-        off = 2 * n_loc
-        for corr, tag in ((self.net.conv3_corr_layer, 5), (self.net.conv4_corr_layer, 6), (self.net.conv5_corr_layer, 7)):
-            D = (2 * (corr.max_displacement // corr.stride2) + 1) ** 2
-            go = gi.to_nchw(D, off)
-            off += D
-            f = self.feat_nchw[tag]
-            g1, g2 = ops.correlation_backward(f[:B], f[B:], go, corr.pad_size, corr.kernel_size, corr.max_displacement,
-                                              corr.stride1, corr.stride2)
-            ex = self.extra[tag]
-            ex.batch_slice(0, B).load_nchw(g1)
-            ex.batch_slice(B, N).load_nchw(g2)
+        for layer in self.corr_bwd:
+            layer.run()
 
     def refresh_weights(self):
         """after an optimizer step: new max |w| per weight (one fused norm), then the packed fp16 operand pairs of every

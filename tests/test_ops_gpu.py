@@ -108,11 +108,11 @@ def test_psroi_integer_tables_against_exact_tables(monkeypatch):
         feat = torch.randn(B, D * 49, 38, 63, device="cuda") * amp
         feat[0, 5] += 3.0 * amp                                        # a plane with a large mean (no cancellation)
         rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
-        monkeypatch.setenv("D2T_PSROI_INT", "0")
+        lib().d2t_psroi_set_mode(0, 0)
         exact, map_x = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D, want_mapping=True)
-        monkeypatch.setenv("D2T_PSROI_INT", "4")
+        lib().d2t_psroi_set_mode(4, 0)
         fixed, map_i = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D, want_mapping=True)
-        monkeypatch.delenv("D2T_PSROI_INT")
+        lib().d2t_psroi_set_mode(-1, 0)
         auto, _ = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
         assert torch.equal(map_x, map_i)
         l1 = feat.abs().sum((2, 3))[:, :D * 49].max()                   # largest plane L1 norm
@@ -134,21 +134,18 @@ def test_psroi_integer_tables_other_geometries(oracle, monkeypatch, B, D, H, W):
     feat = torch.randn(B, D * 49, H, W, device="cuda")
     rois = common.make_rois(40, B, height=H * 16, width=W * 16, seed=H + W, lo=8, hi=max(64.0, 12.0 * min(H, W)),
                             shuffle=True)
-    if B * D * 7 <= 148:
-        monkeypatch.setenv("D2T_PSROI_INT", "4")
     top, mapping = ops.psroi_forward(feat, cu(rois), 7, 7, 1 / 16., 7, D, want_mapping=True)
-    monkeypatch.delenv("D2T_PSROI_INT", raising=False)
+    lib().d2t_psroi_set_mode(-1, 0)
     want, wmap = oracle.psroi_forward(npy(feat), rois, 1 / 16., 7, 7, 7, D)
     np.testing.assert_array_equal(npy(mapping), wmap)
     l1 = float(feat.abs().sum((2, 3)).max())
     np.testing.assert_allclose(npy(top), want, rtol=PS_RTOL, atol=PS_ATOL + l1 * 2.0 ** -30)
-    monkeypatch.setenv("D2T_PSROI_INT", "0")
+    lib().d2t_psroi_set_mode(0, 0)
     exact, _ = ops.psroi_forward(feat, cu(rois), 7, 7, 1 / 16., 7, D)
+    lib().d2t_psroi_set_mode(-1, 0)
     assert float((top - exact).abs().max()) <= l1 * 2.0 ** -30 * 1.05 + 3e-7 * float(exact.abs().max())
 
 
-@pytest.mark.skipif(os.environ.get("D2T_TEST_EXPERIMENTS") != "1",
-                    reason="unmeasured experiment (integer-table backward); run with D2T_TEST_EXPERIMENTS=1")
 def test_psroi_backward_integer_tables_experiment(monkeypatch):
     """D2T_PSROI_BWD_INT=1 (csrc/psroi.cu, psroi_bwd_isat_mc) against the default fp64 difference tables: every dv is
     rounded to a multiple of 2^-k with sum |dv| 2^k < 2^30, so a cell covered by n bins is within n 2^-30 sum|dv|."""
@@ -157,11 +154,11 @@ def test_psroi_backward_integer_tables_experiment(monkeypatch):
         rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
         gt = torch.randn(rois.size(0), D, 7, 7, device="cuda")
         shape = (B, D * 49 + 3, 38, 63)
-        monkeypatch.delenv("D2T_PSROI_BWD_INT", raising=False)
+        lib().d2t_psroi_set_mode(-1, 0)
         want = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
-        monkeypatch.setenv("D2T_PSROI_BWD_INT", "1")
+        lib().d2t_psroi_set_mode(-1, 1)
         got = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
-        monkeypatch.delenv("D2T_PSROI_BWD_INT")
+        lib().d2t_psroi_set_mode(-1, 0)
         assert float(got[:, D * 49:].abs().max()) == 0.0
         err = float((got - want).abs().max())
         assert err <= 2e-5 * max(1.0, float(want.abs().max())), err
@@ -496,3 +493,49 @@ def test_proposal_decode_bit_exact_vs_torch_chain():
     want = clip_boxes(bbox_transform_inv(all_anchors, d, 2), cu(im_info), 2)
     assert torch.equal(boxes, want)
     assert torch.equal(scores, cu(prob)[:, A:].permute(0, 2, 3, 1).contiguous().view(2, -1))
+
+
+@pytest.mark.parametrize("B,D,R", [(2, 31, 300), (4, 4, 300), (1, 30, 2000), (3, 4, 77)])
+def test_psroi_vote_fused(B, D, R):
+    """fused PSRoI + 7x7 vote (+ softmax) against AvgPool2d(7) of the unfused operator (rfcn.py:133-140)"""
+    torch.manual_seed(R + D)
+    feat = torch.randn(B, D * 49, 38, 63, device="cuda")
+    rois = cu(common.make_rois(R, B, seed=21, shuffle=(R == 77)))
+    rois[5, 0] = 99.0                                   # a roi of no image: zeros like the unfused operator
+    top, _ = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+    want = top.mean((2, 3))
+    got = ops.psroi_vote(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+    assert got.shape == (rois.size(0), D)
+    assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    sm = ops.psroi_vote(feat, rois, 7, 7, 1.0 / 16.0, 7, D, softmax=True)
+    assert float((sm - torch.softmax(want, 1)).abs().max()) < 1e-5
+
+
+def test_psroi_integer_tables_outlier_guard():
+    """a plane with one huge value (or a NaN) must not cost the other bins their accuracy: the multi-CTA kernel detects
+    the dynamic range and pools such an item by direct summation in the reference's order (bit-identical to the oracle's
+    arithmetic); all other items keep the integer tables"""
+    from oracle import cpu as oracle_mod
+    B, D, R = 2, 30, 400
+    torch.manual_seed(5)
+    feat = torch.randn(B, D * 49, 38, 63, device="cuda")
+    feat[0, 7 * 49 + 3, 11, 20] = 1.0e9                  # one cell 1e9 x the rest of its plane
+    feat[1, 2 * 49 + 10, 5, 5] = -3.0e7
+    rois_np = common.make_rois(R, B, seed=21)
+    rois = cu(rois_np)
+    top, _ = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+    want, _ = oracle_mod.psroi_forward(feat.cpu().numpy(), rois_np, 1.0 / 16.0, 7, 7, 7, D)
+    want = torch.from_numpy(want).cuda()
+    # elementwise: bins that do not contain the outlier keep their own relative accuracy
+    err = (top - want).abs()
+    tol = 1e-5 * want.abs() + 2e-6
+    assert bool((err <= tol).all()), (float(err.max()), int((err > tol).sum()))
+    # the guarded items are bit-identical to the reference arithmetic
+    assert torch.equal(top[:R, 7, 0, 3], want[:R, 7, 0, 3])
+    feat[0, 3 * 49 + 1, 0, 0] = float("nan")
+    top, _ = ops.psroi_forward(feat, rois, 7, 7, 1.0 / 16.0, 7, D)
+    first = top[:R, 3, 0, 1]                              # bins of that plane covering cell (0, 0) are NaN, like the reference
+    bins = ops.psroi_bins(rois, 7, 7, 1.0 / 16.0, 38, 63)[:R, 0, 1]
+    covers = (bins[:, 0] == 0) & (bins[:, 2] == 0) & (bins[:, 1] > 0) & (bins[:, 3] > 0)
+    assert bool(torch.isnan(first[covers]).all()) and not bool(torch.isnan(first[~covers]).any())
+    assert not bool(torch.isnan(top[:, 4]).any())

@@ -160,3 +160,42 @@ def test_dynamic_weight_scale_repack():
         want = F.conv2d(x.double(), w.detach().double(), None, 1, 1, 1)
         err = float((layer.out_nchw.double() - want).abs().max() / want.abs().max())
         assert err < 1e-5, (scale, err)
+
+
+@pytest.mark.parametrize("C,H,W,md,stride,B", [(128, 38, 63, 8, 1, 2), (1024, 38, 63, 8, 1, 1), (512, 75, 125, 8, 2, 2),
+                                              (64, 20, 30, 8, 1, 1), (96, 21, 45, 4, 1, 1)])
+def test_correlation_backward_tensor_core(C, H, W, md, stride, B):
+    """CORRB mode of the tcgen05 kernel (banded GEMM over the halo positions) against the exact-adjoint fp32 SIMT kernels of
+    csrc/correlation.cu, both gradients, every D&T geometry; for stride 2 the gradient lives on the even positions"""
+    from d2t_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(55 + C)
+    in1 = torch.randn(B, C, H, W, device="cuda", generator=g)
+    in2 = torch.randn(B, C, H, W, device="cuda", generator=g)
+    r = md // stride
+    D2 = (2 * r + 1) ** 2
+    oh, ow = -(-H // stride), -(-W // stride)
+    go = torch.randn(B, D2, oh, ow, device="cuda", generator=g) * 1e-3
+    want1, want2 = ops.correlation_backward(in1, in2, go, md, 1, md, stride, stride)
+    coff = 12
+    gbuf = dc.ActTensor(B, oh, ow, coff + D2 + 5, cstride=(coff + D2 + 5 + 3) // 4 * 4)
+    gbuf.load_nchw(torch.cat([torch.randn(B, coff, oh, ow, device="cuda", generator=g), go,
+                              torch.randn(B, 5, oh, ow, device="cuda", generator=g)], 1))
+    x1, x2 = dc.ActTensor.from_nchw(in1), dc.ActTensor.from_nchw(in2)
+    nb, no = dc.CorrBwdScratch.need(B, C, oh, ow, r)
+    scratch = dc.CorrBwdScratch(nb, no)
+    for which, other, want in ((1, x2, want1), (2, x1, want2)):
+        out = dc.ActTensor(B, oh, ow, C, cstride=C)
+        out.x.fill_(float("nan"))
+        layer = dc.CorrBwdLayer(gbuf, coff, other, out, md, stride, which, scratch)
+        layer.run()
+        torch.cuda.synchronize()
+        got = out.to_nchw(C)
+        ref = want[:, :, ::stride, ::stride]
+        assert got.shape == ref.shape
+        err = float((got - ref).abs().max() / ref.abs().max())
+        print("corr bwd", (C, H, W, md, stride, B), "d/d(input%d)" % which, "max rel err %.2e" % err)
+        assert err < 2e-5, (which, err)
+        if stride > 1:      # nothing off the lattice
+            mask = torch.ones_like(want)
+            mask[:, :, ::stride, ::stride] = 0
+            assert float((want * mask).abs().max()) == 0.0

@@ -84,6 +84,7 @@ def test_train_engine_gradients_match_autograd(layers, B, H, W):
     flip on 1e-6-level forward differences put a floor of ~1e-3 of max |grad| under any two fp32 implementations here)"""
     from d2t_b200.train import D2TTrainEngine
     net, im_data, im_info, gt, nb = _setup(layers, B, H, W)
+    net64 = copy.deepcopy(net).double()             # (before the first forward: the modules then hold no graph tensors)
     eng = D2TTrainEngine(net, B, H, W)
     out, loss = eng.forward_backward(im_data, im_info, gt, nb)
     torch.cuda.synchronize()
@@ -95,7 +96,6 @@ def test_train_engine_gradients_match_autograd(layers, B, H, W):
     _torch_param_grads(net, im_data, B, [g.clone() for g in eng.leaf_grads])      # accumulates into the same .grad views
     torch.cuda.synchronize()
     ref32 = eng.flat.clone()
-    net64 = copy.deepcopy(net).double()
     for p in net64.parameters():
         p.grad = None
     _torch_param_grads(net64, im_data.double(), B, [g.double() for g in eng.leaf_grads], pure_torch_corr=True)
