@@ -1089,6 +1089,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     }
                     continue;
                 }
+#ifndef D2T_AB_NO_MASK                               // (A/B builds only: scripts/r02_ab_mask.sh)
                 if (p.mask && pix_ok) {                      // backward-data: ReLU mask of the forward activation
                     const float* mr = p.mask + pix * p.mask_cstride + ch0;
                     if (full16) {
@@ -1104,6 +1105,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                             if (ch0 + j < p.Cout) v[j] = __ldg(mr + j) > 0.f ? v[j] : 0.f;
                     }
                 }
+#endif
                 if (p.amax_out && pix_ok) {
                     if (full16) {
 #pragma unroll
