@@ -577,13 +577,14 @@ def train_measure(world, rank, steps, warmup):
     t = parallel.max_over_ranks(torch.tensor([ms, c_ms, e_ms], device="cuda", dtype=torch.float64))
     ms, c_ms, e_ms = float(t[0]), float(t[1]), float(t[2])
     check_finite([loss.detach()], "the training loss")
-    # phase split (rank-local, one extra step with synchronisation points; not part of the timed region)
+    # phase split (rank-local, one extra pass with events between the phases; not part of the timed region)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     with torch.no_grad():
-        i2 = engine._begin(im, info)
-        for layer in engine.layers + engine.corr_layers + [engine.trk_layer]:
-            layer.run()
+        if engine.g_fwd is not None:
+            engine.g_fwd.replay()
+        else:
+            engine._engine_forward(im, info)
     ev[1].record()
     engine._run_backward()
     ev[2].record()
@@ -603,6 +604,8 @@ def train_measure(world, rank, steps, warmup):
             "conv_tflops_useful_bwd": (engine.dgrad_flops + engine.wgrad_flops) / bwd_ms / 1e9,
             "convs": "d2t_b200 tcgen05 3xFP16: forward, backward-data (DgradConv) and weight-gradient (WgradLayer); PSRoI, "
                      "correlation, NMS, proposal step: d2t_b200 kernels (forward and backward); losses / target layers / SGD: torch",
+            "launch": ("CUDA-graph replays: forward, one graph per gradient bucket of the backward pass, weight re-pack; heads / "
+                       "losses / SGD eager" if engine.g_fwd is not None else "eager launches"),
             "bn": "calibrated (trained-looking) BatchNorm statistics, frozen", "gpu_launches": ops.LAUNCHES - launches0}
 
 

@@ -36,7 +36,8 @@ def _is_param(t):
 class D2TTrainEngine(D2TEngine):
     AMAX_SLOTS = 4096
 
-    def __init__(self, net, pairs, height, width, bucket_bytes=32 << 20):
+    def __init__(self, net, pairs, height, width, bucket_bytes=32 << 20, use_graphs=True):
+        self.use_graphs, self.g_fwd = use_graphs, None
         self._widx, self._blocks, self._meta = {}, [], {}
         dev = next(net.parameters()).device
         self.w_amax = torch.zeros(512, device=dev)          # max |w| per distinct conv weight (slot = _widx[id(w)])
@@ -281,6 +282,14 @@ class D2TTrainEngine(D2TEngine):
     def refresh_weights(self):
         """after an optimizer step: new max |w| per weight (one fused norm), then the packed fp16 operand pairs of every
         forward and backward-data plan -- all on the device, no host synchronisation"""
+        if self.g_fwd is not None:
+            self.g_refresh.replay()
+            ops._count(self._refresh_launches)
+        else:
+            with torch.no_grad():
+                self._refresh_weights()
+
+    def _refresh_weights(self):
         norms = torch._foreach_norm([w.detach() for w in self._weights], float("inf"))
         n = len(norms)
         torch.stack(norms, out=self.w_amax[:n])
@@ -291,19 +300,76 @@ class D2TTrainEngine(D2TEngine):
             d.repack()
 
     # ------------------------------------------------------------------ the step
+    def _engine_forward(self, im_data, im_info):
+        info = self._begin(im_data, im_info)
+        for layer in self.layers:
+            layer.run()
+        for layer in self.corr_layers:
+            layer.run()
+        self.trk_layer.run()
+        return info
+
+    def _load_leaf_grads(self, grads):
+        for buf, gr in zip((self.g_cls, self.g_bbox, self.g_score, self.g_delta, self.g_trk), grads):
+            buf.load_nchw(gr)
+
+    def _segments(self):
+        """backward steps grouped so that a gradient bucket closes at the end of each group"""
+        cuts = [k + 1 for k, _, _ in self.buckets]
+        if not cuts or cuts[-1] != len(self.bwd):
+            cuts.append(len(self.bwd))
+        return list(zip([0] + cuts[:-1], cuts))
+
+    def _capture(self, im_data, im_info):
+        """The engine's two halves as CUDA graphs (the geometry, every buffer and every plan are fixed): the forward, and
+        the backward in one graph per gradient bucket, so that the bucket's all-reduce can be issued between two replays.
+        Removes ~900 kernel launches of host work per step; the heads in between stay eager (data-dependent shapes)."""
+        self.im_static, self.info_static = im_data.clone(), im_info.clone()
+        self.grads_static = [torch.zeros_like(t) for t in (self.cls_map, self.bbox_map, self.rpn_score, self.rpn_delta,
+                                                            self.trk_layer.out_nchw)]
+        torch.cuda.synchronize()
+        count = ops.LAUNCHES
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            self.info_graph = self._engine_forward(self.im_static, self.info_static)
+        self._fwd_launches = ops.LAUNCHES - count
+        pool = self.g_fwd.pool()
+        self.g_bwd = []
+        for a, b in self._segments():
+            count = ops.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                if a == 0:
+                    self._load_leaf_grads(self.grads_static)
+                for k in range(a, b):
+                    self.bwd[k][0]()
+            self.g_bwd.append((g, ops.LAUNCHES - count))
+        count = ops.LAUNCHES
+        self.g_refresh = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_refresh, pool=pool):
+            self._refresh_weights()
+        self._refresh_launches = ops.LAUNCHES - count
+
     def forward_backward(self, im_data, im_info, gt_boxes, num_boxes):
         """forward (training mode) + losses + backward; fills param.grad (mean over ranks when torch.distributed is
         initialised).  Returns (the reference's 10-tuple, total loss)."""
         from model.rpn.proposal_target_layer_cascade import train_heads
         net, B = self.net, self.B
         assert net.training, "call net.train() first (the RPN picks its TRAIN configuration from it)"
+        self._calls = getattr(self, "_calls", 0) + 1
+        if self.use_graphs and self.g_fwd is None and self._calls > 2:       # (two eager steps first: every kernel variant
+            with torch.no_grad():                                            # has been launched once before the capture)
+                self._capture(im_data, im_info)
+        graphed = self.g_fwd is not None
         with torch.no_grad():
-            info = self._begin(im_data, im_info)
-            for layer in self.layers:
-                layer.run()
-            for layer in self.corr_layers:
-                layer.run()
-            self.trk_layer.run()
+            if graphed:
+                self.im_static.copy_(im_data, non_blocking=True)
+                self.info_static.copy_(im_info, non_blocking=True)
+                self.g_fwd.replay()
+                ops._count(self._fwd_launches)
+                info = self.info_graph
+            else:
+                info = self._engine_forward(im_data, im_info)
         leaves = [t.detach().requires_grad_() for t in (self.cls_map, self.bbox_map, self.rpn_score, self.rpn_delta,
                                                         self.trk_layer.out_nchw)]
         cls_map, bbox_map, score, delta, trk = leaves
@@ -313,26 +379,34 @@ class D2TTrainEngine(D2TEngine):
         grads = torch.autograd.grad(loss, leaves, allow_unused=True)
         self.leaf_grads = [gr if gr is not None else torch.zeros_like(leaf) for gr, leaf in zip(grads, leaves)]
         with torch.no_grad():
-            for buf, gr in zip((self.g_cls, self.g_bbox, self.g_score, self.g_delta, self.g_trk), self.leaf_grads):
-                buf.load_nchw(gr.contiguous())
+            if graphed:
+                for dst, gr in zip(self.grads_static, self.leaf_grads):
+                    dst.copy_(gr, non_blocking=True)
+            else:
+                self._load_leaf_grads([gr.contiguous() for gr in self.leaf_grads])
             self._run_backward()
         return out, loss
 
     def _run_backward(self):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         main = torch.cuda.current_stream()
-        nb = 0
         self._comm_events = []
-        for k, (step, _, _l) in enumerate(self.bwd):
-            step()
-            if world > 1 and nb < len(self.buckets) and self.buckets[nb][0] == k:
-                _, a, b = self.buckets[nb]
-                nb += 1
+        graphed = self.g_fwd is not None
+        for i, (a, b) in enumerate(self._segments()):
+            if graphed:
+                g, n = self.g_bwd[i]
+                g.replay()
+                ops._count(n)
+            else:
+                for k in range(a, b):
+                    self.bwd[k][0]()
+            if world > 1 and i < len(self.buckets):
+                _, lo, hi = self.buckets[i]
                 self.ready.record(main)
                 self.comm_stream.wait_event(self.ready)
                 with torch.cuda.stream(self.comm_stream):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    part = self.flat[a:b]
+                    part = self.flat[lo:hi]
                     e0.record(self.comm_stream)
                     if dist.get_backend() == "nccl":
                         dist.all_reduce(part, op=dist.ReduceOp.AVG)
