@@ -177,38 +177,45 @@ __global__ void pack_weights_f16_dgrad(const float* __restrict__ w, const float*
 }
 
 // channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> fp32 planes [N][C][OH][pitch]
-// (columns [OW, pitch) zero): the K-contiguous A operand of the weight-gradient GEMM.  32 x 32 shared-memory transpose
-// per (image, output row).
+// (columns [OW, pitch) zero): the K-contiguous A operand of the weight-gradient GEMM.  A CTA transposes 64 positions x
+// 32 channels of one output row through shared memory: 128-byte loads (32 channels of a pixel), 256-byte stores (a lane
+// writes two neighbouring positions of one channel).  pitch is even.
 __global__ void __launch_bounds__(256)
 nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, int stride, int OH, int OW, int pitch,
                float* __restrict__ out) {
-    __shared__ float tile[32][33];
-    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
+    __shared__ float tile[64][33];
+    const int wt = blockIdx.x * 64, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int j = ty; j < 32; j += 8) {
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
         const int xo = wt + j, c = ct + tx;
         tile[j][tx] = (xo < OW && c < C) ? __ldg(x + (((size_t)n * H + (size_t)oy * stride) * W + (size_t)xo * stride) * cs + c) : 0.f;
     }
     __syncthreads();
+#pragma unroll
     for (int j = ty; j < 32; j += 8) {
-        const int c = ct + j, xo = wt + tx;
-        if (c < C && xo < pitch) out[(((size_t)n * C + c) * OH + oy) * pitch + xo] = tile[tx][j];
+        const int c = ct + j, xo = wt + 2 * tx;
+        if (c < C && xo < pitch)
+            *reinterpret_cast<float2*>(out + (((size_t)n * C + c) * OH + oy) * pitch + xo) = make_float2(tile[2 * tx][j], tile[2 * tx + 1][j]);
     }
 }
 
 // gradient NHWC [N, OH, OW, cs] -> the B operand of the weight-gradient GEMM: S copies of fp16 (hi, lo) planes
 // [S][N][C][OH][pitch] of g * 2^k (k from *amax), copy s shifted by dx_s = s * dil - pad columns:
 // plane_s[u] = g[u - dx_s] (zero outside [0, OW)) -- the filter column's offset cannot be a TMA start coordinate (see
-// conv.cu, WGRAD), so it is materialised here.  The tile is loaded with an 8-column halo on both sides (|dx| <= 8).
+// conv.cu, WGRAD), so it is materialised here.  The 64-position tile is loaded with an 8-column halo on both sides
+// (|dx| <= 8); a lane writes two neighbouring positions (half2: 128-byte stores per warp).  Also used, with a source
+// stride, for the correlation backward's planes (S = 1).
 __global__ void __launch_bounds__(256)
 nhwc_to_planes_split(const float* __restrict__ g, int N, int Hs, int Ws, int stride, int OH, int OW, int cs, int C, int pitch,
                      int S, int dil, int pad, const float* __restrict__ amax, __half* __restrict__ out_hi,
                      __half* __restrict__ out_lo) {
-    __shared__ float tile[48][33];
-    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
+    __shared__ float tile[80][33];
+    const int wt = blockIdx.x * 64, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float sa = pow2f(act_exp(amax));
-    for (int j = ty; j < 48; j += 8) {
+#pragma unroll
+    for (int j = ty; j < 80; j += 8) {
         const int xo = wt - 8 + j, c = ct + tx;
         tile[j][tx] = (xo >= 0 && xo < OW && c < C)
                           ? __ldg(g + (((size_t)n * Hs + (size_t)oy * stride) * Ws + (size_t)xo * stride) * cs + c) * sa : 0.f;
@@ -217,14 +224,16 @@ nhwc_to_planes_split(const float* __restrict__ g, int N, int Hs, int Ws, int str
     const size_t copy = (size_t)N * C * OH * pitch;
     for (int s = 0; s < S; ++s) {
         const int dx = s * dil - pad;
+#pragma unroll
         for (int j = ty; j < 32; j += 8) {
-            const int c = ct + j, u = wt + tx;
+            const int c = ct + j, u = wt + 2 * tx;
             if (c < C && u < pitch) {
-                const float v = tile[tx + 8 - dx][j];
+                const float v0 = tile[2 * tx + 8 - dx][j], v1 = tile[2 * tx + 9 - dx][j];
                 const size_t o = s * copy + (((size_t)n * C + c) * OH + oy) * pitch + u;
-                const __half h = __float2half_rn(v);
-                out_hi[o] = h;
-                out_lo[o] = __float2half_rn(v - __half2float(h));
+                const __half2 h = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(h);
+                *reinterpret_cast<__half2*>(out_hi + o) = h;
+                *reinterpret_cast<__half2*>(out_lo + o) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
             }
         }
     }
@@ -379,7 +388,7 @@ extern "C" int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_s
     D2T_REQUIRE(x && xt && N > 0 && H > 0 && W > 0 && C > 0 && c_stride >= C && stride > 0 && OH > 0 && OW > 0 &&
                     pitch >= OW && pitch % 4 == 0 && (OH - 1) * stride < H && (OW - 1) * stride < W,
                 "d2t_wgrad_pack_input: bad arguments (row pitch a multiple of 4)");
-    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    dim3 grid((pitch + 63) / 64, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_input: tensor too large for the launch grid");
     nhwc_to_planes<<<grid, 256, 0, stream>>>(x, N, H, W, c_stride, C, stride, OH, OW, pitch, xt);
     D2T_CHECK_LAUNCH("nhwc_to_planes");
@@ -391,7 +400,7 @@ extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_
     D2T_REQUIRE(g && g_hi && g_lo && amax_g && N > 0 && OH > 0 && OW > 0 && C > 0 && c_stride >= C && pitch >= OW &&
                     pitch % 8 == 0 && S >= 1 && dil >= 1 && pad >= 0 && pad <= 8 && (S - 1) * dil - pad <= 8,
                 "d2t_wgrad_pack_grad: bad arguments (row pitch a multiple of 8, column shifts within +-8)");
-    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    dim3 grid((pitch + 63) / 64, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_grad: tensor too large for the launch grid");
     nhwc_to_planes_split<<<grid, 256, 0, stream>>>(g, N, OH, OW, 1, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
                                                    reinterpret_cast<__half*>(g_hi), reinterpret_cast<__half*>(g_lo));
@@ -406,7 +415,7 @@ extern "C" int d2t_corrb_pack_other(const float* x, int N, int H, int W, int c_s
     D2T_REQUIRE(x && o_hi && o_lo && amax_x && N > 0 && H > 0 && W > 0 && C > 0 && c_stride >= C && stride > 0 && OH > 0 &&
                     OW > 0 && pitch >= OW && pitch % 8 == 0 && (OH - 1) * stride < H && (OW - 1) * stride < W,
                 "d2t_corrb_pack_other: bad arguments (row pitch a multiple of 8)");
-    dim3 grid((pitch + 31) / 32, (C + 31) / 32, N * OH);
+    dim3 grid((pitch + 63) / 64, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_corrb_pack_other: tensor too large for the launch grid");
     nhwc_to_planes_split<<<grid, 256, 0, stream>>>(x, N, H, W, stride, OH, OW, c_stride, C, pitch, 1, 1, 0, amax_x,
                                                    reinterpret_cast<__half*>(o_hi), reinterpret_cast<__half*>(o_lo));
