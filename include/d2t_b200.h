@@ -237,7 +237,7 @@ typedef struct d2t_conv_desc {
 typedef struct d2t_conv_plan d2t_conv_plan;
 
 /* out = relu?( scale[c] * conv(in, w) + shift[c] + res ).  scale / shift / res / out / out_nchw may
- * be NULL (at least one output is required); out_nchw is a plain fp32 [N, Cout, OH, OW] copy for
+ * be NULL (at least one output is required; passes = 16: scale must be NULL -- fold it into the packed weights); out_nchw is a plain fp32 [N, Cout, OH, OW] copy for
  * consumers that keep the reference's layout.  The plan captures the pointers (TMA tensor maps);
  * buffers must outlive it.  Plans of one device share a small stream-K scratch unless given their own
  * (d2t_conv_plan_set_scratch); d2t_conv_plan_run keeps launches on the shared scratch stream-ordered
@@ -300,7 +300,7 @@ d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int 
  * d2t_conv_pack_weights_f16_dev / _dgrad read it, d2t_conv_plan_set_weight_amax makes the kernel read it. */
 int d2t_conv_plan_set_mask(d2t_conv_plan* plan, const float* mask_nhwc, int mask_cstride);
 int d2t_conv_plan_set_weight_amax(d2t_conv_plan* plan, const float* amax_w);
-int d2t_conv_pack_weights_f16_dev(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+int d2t_conv_pack_weights_f16_dev(const float* w_oihw, const float* scale, int Cout, int Cin, int R, int S, int cin_pad,
                                   const float* amax_w, void* w_hi, void* w_lo, cudaStream_t stream);
 /* (rows >= Cin: rows [Cin, rows) of wt are zero -- the backward-data output may be wider than the forward input) */
 int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float* scale, int Cout, int Cin, int rows, int R, int S,
@@ -346,9 +346,11 @@ d2t_conv_plan* d2t_corrb_plan_create(int N, int C, int H, int W, int r, const vo
 /* OIHW fp32 -> [Cout][R*S][cin_pad] (w, w_lo); w_lo may be NULL */
 int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
                           float* w_hi, float* w_lo, cudaStream_t stream);
-/* OIHW fp32 -> [Cout][R*S][cin_pad] fp16 pair (hi, lo) of w * 2^w_exp, cin_pad a multiple of 64:
- * hi = fp16(w * 2^w_exp), lo = fp16(w * 2^w_exp - hi).  Choose w_exp so that max |w| * 2^w_exp < 2^15. */
-int d2t_conv_pack_weights_f16(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
+/* OIHW fp32 -> [Cout][R*S][cin_pad] fp16 pair (hi, lo) of w * scale[cout] * 2^w_exp, cin_pad a multiple of 64:
+ * hi = fp16(.), lo = fp16(. - hi).  scale (may be NULL) is the per-output-channel factor of the convolution -- the folded
+ * BatchNorm scale: a 3xFP16 plan has no epilogue scale, it lives in the packed weights.  Choose w_exp so that
+ * max |w * scale| * 2^w_exp < 2^15. */
+int d2t_conv_pack_weights_f16(const float* w_oihw, const float* scale, int Cout, int Cin, int R, int S, int cin_pad,
                               int w_exp, void* w_hi, void* w_lo, cudaStream_t stream);
 /* plain fp32 NCHW -> channels [c_offset, c_offset + c_width) of an NHWC tensor with c_stride channels
  * per pixel (the C source channels, then zeros); and back */

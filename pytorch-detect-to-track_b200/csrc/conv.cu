@@ -888,11 +888,17 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         // all of its 64 channels' values every tile, and as global loads they paid an L2 round trip per 16 channels
         // (measured: the affine loop was 5-7k cycles per tile).  Thread et fetches ONE value a tile ahead (register),
         // so the latency hides behind the previous tile; channels past Cout read a clamped index and are never stored.
+        // 3xFP16 convolutions (forward and backward-data): the per-channel scale lives in the PACKED WEIGHTS (folded by the
+        // packers) and the shift INITIALISES the accumulator, so a finished tile needs no affine pass at all -- the traced
+        // epilogue spent 3.4 k of its 8.5 k cycles per tile there on the residual 1x1 layers (profiles/r02_conv_trace.txt).
+        // Every other variant (TF32 kinds, WGRAD's column scale, CORRB's 1/C) keeps the scale / shift loop below.
+        constexpr bool FOLDED = F16 && !WGRAD && !CORRB;
         float* scsh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
         const int et = (warp - kEpiWarp0) * 32 + lane;     // 0..255
         auto fetch_scsh = [&](int tile) -> float {
             if (CORR || et >= 2 * BN) return 0.f;
             const bool is_shift = et >= BN;
+            if (FOLDED && !is_shift) return 1.f;
             const float* src = is_shift ? p.shift : p.scale;
             const int chn = min((tile % p.n_tiles) * BN + (is_shift ? et - BN : et), p.Cout - 1);
             return src ? __ldg(src + chn) : (is_shift ? 0.f : 1.f);
@@ -935,8 +941,25 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 }
             }
             float acc[HN];
+            if constexpr (FOLDED) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue thread has read the previous tile's shifts
+                if (et >= BN && et < 2 * BN) scsh[et] = scsh_cur;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (sg.role != 1) {                              // (a published partial tile must not carry the shift)
+                    const float4* sh4 = reinterpret_cast<const float4*>(scsh + BN + cofs);
 #pragma unroll
-            for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+                    for (int j = 0; j < HN; j += 4) {
+                        const float4 sh = sh4[j >> 2];
+                        acc[j] = sh.x; acc[j + 1] = sh.y; acc[j + 2] = sh.z; acc[j + 3] = sh.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+            }
             for (int ch = 0; ch < nchunks; ++ch) {          // drain finished chunks: fp32 round-to-nearest adds
                 TRACED_WAIT(0, &tfull[cbuf], cphase);
                 tc_fence_after();
@@ -1032,9 +1055,11 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 }
                 (void)r;
             } else {
+            if constexpr (!FOLDED) {
             asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue thread is done with the previous tile's values
             if (et < 2 * BN) scsh[et] = scsh_cur;
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             if constexpr (EPI2) {
                 if (res_tma) {                               // the residual slabs of this group have landed
                     TRACED_WAIT(2, &rfull[grp], rphase);
@@ -1047,7 +1072,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const int ch0 = n0 + cofs + c * 16;
                 if (ch0 >= p.Cout) continue;                 // (warp-uniform)
                 const bool full16 = ch0 + 16 <= p.Cout;
-                {                                            // per-channel affine (folded BN / bias) from shared memory
+                if constexpr (!FOLDED) {                     // per-channel affine (folded BN / bias) from shared memory
                     const float4* sc4 = reinterpret_cast<const float4*>(scsh + cofs + c * 16);
                     const float4* sh4 = reinterpret_cast<const float4*>(scsh + BN + cofs + c * 16);
 #pragma unroll
@@ -1111,7 +1136,11 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 }
                 }
                 if (p.amax_out && pix_ok) {
-                    if (full16) {
+                    if (full16 && p.relu) {                  // (after a ReLU the values are their own magnitudes)
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            tmax = fmaxf(fmaxf(tmax, fmaxf(v[j], v[j + 1])), fmaxf(v[j + 2], v[j + 3]));
+                    } else if (full16) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4)
                             tmax = fmaxf(fmaxf(tmax, fmaxf(fabsf(v[j]), fabsf(v[j + 1]))), fmaxf(fabsf(v[j + 2]), fabsf(v[j + 3])));
@@ -1476,6 +1505,11 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     }
     const bool f16 = d->passes == 16;
     const int kblk = kblk_of(d->passes);
+    if (f16 && scale) {
+        set_error("d2t_conv_plan_create: a 3xFP16 plan takes its per-channel scale folded into the packed weights "
+                  "(d2t_conv_pack_weights_f16 / _dev with `scale`), not as an epilogue vector");
+        return nullptr;
+    }
     if (d->passes != 1 && !w_lo) {
         set_error("d2t_conv_plan_create: 3-pass mode needs the lo half of the packed weights");
         return nullptr;

@@ -95,14 +95,15 @@ __global__ void pack_weights(const float* __restrict__ w, int O, int I, int R, i
 }
 
 // OIHW -> [O][R*S][cin_pad] fp16 (hi, lo) of w * 2^w_exp (the 3xFP16 operand format, conv.cu), zero pad
-__global__ void pack_weights_f16(const float* __restrict__ w, int O, int I, int R, int S, int cin_pad, float sw,
-                                 __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void pack_weights_f16(const float* __restrict__ w, const float* __restrict__ scale, int O, int I, int R, int S,
+                                 int cin_pad, float sw, __half* __restrict__ hi, __half* __restrict__ lo) {
     const size_t total = (size_t)O * R * S * cin_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cin_pad);
         const int rs = (int)((idx / cin_pad) % (R * S));
         const int o = (int)(idx / cin_pad / (R * S));
-        const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) * sw : 0.f;
+        float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) * sw : 0.f;
+        if (scale) v *= __ldg(scale + o);
         const __half h = __float2half_rn(v);
         hi[idx] = h;
         lo[idx] = __float2half_rn(v - __half2float(h));
@@ -138,15 +139,17 @@ __global__ void maxpool3x3s2_nhwc(const float* __restrict__ in, int N, int H, in
 // ---------------------------------------------------------------- training-path helpers (backward-data / weight-gradient)
 // OIHW -> forward layout [O][R*S][cin_pad] fp16 (hi, lo) of w * 2^k, k derived on the device from *amax (= max |w|, kept
 // by the caller): the per-step re-pack of a weight that the optimizer has just changed needs no host round trip
-__global__ void pack_weights_f16_dev(const float* __restrict__ w, int O, int I, int R, int S, int cin_pad,
-                                     const float* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void pack_weights_f16_dev(const float* __restrict__ w, const float* __restrict__ scale, int O, int I, int R, int S,
+                                     int cin_pad, const float* __restrict__ amax, __half* __restrict__ hi,
+                                     __half* __restrict__ lo) {
     const float sw = pow2f(act_exp(amax));
     const size_t total = (size_t)O * R * S * cin_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cin_pad);
         const int rs = (int)((idx / cin_pad) % (R * S));
         const int o = (int)(idx / cin_pad / (R * S));
-        const float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) * sw : 0.f;
+        float v = c < I ? __ldg(w + ((size_t)o * I + c) * R * S + rs) * sw : 0.f;
+        if (scale) v *= __ldg(scale + o);
         const __half h = __float2half_rn(v);
         hi[idx] = h;
         lo[idx] = __float2half_rn(v - __half2float(h));
@@ -346,25 +349,25 @@ extern "C" int d2t_conv_pack_weights(const float* w_oihw, int Cout, int Cin, int
     return 1;
 }
 
-extern "C" int d2t_conv_pack_weights_f16(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad, int w_exp,
-                                         void* w_hi, void* w_lo, cudaStream_t stream) {
+extern "C" int d2t_conv_pack_weights_f16(const float* w_oihw, const float* scale, int Cout, int Cin, int R, int S, int cin_pad,
+                                         int w_exp, void* w_hi, void* w_lo, cudaStream_t stream) {
     D2T_REQUIRE(w_oihw && w_hi && w_lo && Cout > 0 && Cin > 0 && R > 0 && S > 0 && cin_pad >= Cin && cin_pad % 64 == 0 &&
                     w_exp >= -126 && w_exp <= 127,
                 "d2t_conv_pack_weights_f16: bad arguments");
     const size_t total = (size_t)Cout * R * S * cin_pad;
-    pack_weights_f16<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, ldexpf(1.f, w_exp),
+    pack_weights_f16<<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, Cout, Cin, R, S, cin_pad, ldexpf(1.f, w_exp),
                                                           reinterpret_cast<__half*>(w_hi), reinterpret_cast<__half*>(w_lo));
     D2T_CHECK_LAUNCH("pack_weights_f16");
     return 1;
 }
 
 
-extern "C" int d2t_conv_pack_weights_f16_dev(const float* w_oihw, int Cout, int Cin, int R, int S, int cin_pad,
-                                             const float* amax_w, void* w_hi, void* w_lo, cudaStream_t stream) {
+extern "C" int d2t_conv_pack_weights_f16_dev(const float* w_oihw, const float* scale, int Cout, int Cin, int R, int S,
+                                             int cin_pad, const float* amax_w, void* w_hi, void* w_lo, cudaStream_t stream) {
     D2T_REQUIRE(w_oihw && w_hi && w_lo && amax_w && Cout > 0 && Cin > 0 && R > 0 && S > 0 && cin_pad >= Cin && cin_pad % 64 == 0,
                 "d2t_conv_pack_weights_f16_dev: bad arguments");
     const size_t total = (size_t)Cout * R * S * cin_pad;
-    pack_weights_f16_dev<<<grid_for(total), 256, 0, stream>>>(w_oihw, Cout, Cin, R, S, cin_pad, amax_w,
+    pack_weights_f16_dev<<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, Cout, Cin, R, S, cin_pad, amax_w,
                                                               reinterpret_cast<__half*>(w_hi), reinterpret_cast<__half*>(w_lo));
     D2T_CHECK_LAUNCH("pack_weights_f16_dev");
     return 1;

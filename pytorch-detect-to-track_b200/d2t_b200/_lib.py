@@ -64,7 +64,7 @@ _SIGS = {
     "d2t_conv_scratch_bytes": (_sz, []),
     "d2t_conv_plan_set_scratch": (_i, [_p, _p, _sz]),
     "d2t_conv_plan_set_done": (_i, [_p, _p, _p, _p]),
-    "d2t_conv_pack_weights_f16": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_conv_pack_weights_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 3 + [_i, _i, _p]),
     "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),
     "d2t_conv_plan_run": (_i, [_p, _p]),
@@ -78,7 +78,7 @@ _SIGS = {
     # ---- training path (backward-data / weight-gradient)
     "d2t_conv_plan_set_mask": (_i, [_p, _p, _i]),
     "d2t_conv_plan_set_weight_amax": (_i, [_p, _p]),
-    "d2t_conv_pack_weights_f16_dev": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "d2t_conv_pack_weights_f16_dev": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_conv_pack_weights_f16_dgrad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_upsample2_add_mask": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_wgrad_pack_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

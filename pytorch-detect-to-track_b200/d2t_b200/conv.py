@@ -119,18 +119,20 @@ def pack_weights(w, cin_pad=None, lo=True):
     return hi, lo_t
 
 
-def pack_weights_f16(w, cin_pad=None):
-    """OIHW -> ([O, R*S*cin_pad] fp16 hi, lo, w_exp): the pair splits w * 2^w_exp, max |w| * 2^w_exp in [2^14, 2^15)"""
+def pack_weights_f16(w, cin_pad=None, scale=None):
+    """OIHW -> ([O, R*S*cin_pad] fp16 hi, lo, w_exp): the pair splits w * scale[o] * 2^w_exp, max |.| * 2^w_exp in
+    [2^14, 2^15).  `scale`: the convolution's per-output-channel factor (folded BatchNorm), carried by the weights."""
     O, I, R, S = w.shape
     cin_pad = cin_pad or _pad64(I)
     w = w.detach().contiguous().float()
-    wmax = float(w.abs().max())
+    scale = scale.detach().float().contiguous() if scale is not None else None
+    wmax = float((w * scale.view(-1, 1, 1, 1)).abs().max()) if scale is not None else float(w.abs().max())
     w_exp = 15 - math.frexp(wmax)[1] if wmax > 0 and math.isfinite(wmax) else 0
     w_exp = max(-100, min(100, w_exp))
     hi = torch.empty(O, R * S * cin_pad, device=w.device, dtype=torch.float16)
     lo = torch.empty_like(hi)
-    check(lib().d2t_conv_pack_weights_f16(w.data_ptr(), O, I, R, S, cin_pad, w_exp, hi.data_ptr(), lo.data_ptr(), _stream()),
-          "d2t_conv_pack_weights_f16")
+    check(lib().d2t_conv_pack_weights_f16(w.data_ptr(), _p(scale), O, I, R, S, cin_pad, w_exp, hi.data_ptr(), lo.data_ptr(),
+                                          _stream()), "d2t_conv_pack_weights_f16")
     torch.cuda.current_stream().synchronize()   # `w` may be a temporary
     return hi, lo, w_exp
 
@@ -185,7 +187,9 @@ class ConvLayer(_Planned):
     def __init__(self, x, weight, scale=None, shift=None, stride=1, pad=0, dil=1, relu=False, residual=None,
                  passes=3, out=None, out_coffset=0, want_nhwc=True, want_nchw=False, out_nchw=None, amax_w=None,
                  packed=None, mask=None):
-        """amax_w: one-element CUDA float tensor holding max |weight| -- the weights are then (re)packed on the device from
+        """passes = 16: `scale` (the folded BatchNorm factor) is multiplied into the packed weights and `shift` initialises
+        the accumulator -- the kernel's epilogue has no affine pass.
+        amax_w: one-element CUDA float tensor >= max |weight * scale| -- the weights are then (re)packed on the device from
         it (``repack()``, no host round trip: a training loop calls it after every optimizer step) and the kernel reads the
         scale from the same scalar.  packed = (hi, lo): operand matrices packed by the caller (backward-data, with amax_w);
         `weight` then only gives the geometry [O, I, R, S].  mask: ActTensor shaped like the output; out = mask > 0 ? . : 0."""
@@ -194,6 +198,9 @@ class ConvLayer(_Planned):
             raise ValueError("input buffer has %d channels per pixel, conv needs %d" % (x.cstride, _pad32(I)))
         self.x, self.residual, self.mask = x, residual, mask
         self.weight, self.amax_w = weight, amax_w
+        dev = x.x.device
+        self.scale = scale.detach().float().contiguous().to(dev) if scale is not None else None
+        self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
         w_exp = 0
         if packed is not None:
             assert passes == 16 and amax_w is not None
@@ -204,12 +211,10 @@ class ConvLayer(_Planned):
             self.w_lo = torch.empty_like(self.w_hi)
             self.repack()
         elif passes == 16:
-            self.w_hi, self.w_lo, w_exp = pack_weights_f16(weight, _pad64(I))
+            self.w_hi, self.w_lo, w_exp = pack_weights_f16(weight, _pad64(I), self.scale)
         else:
             self.w_hi, self.w_lo = pack_weights(weight, _pad32(I), lo=(passes == 3))
-        dev = x.x.device
-        self.scale = scale.detach().float().contiguous().to(dev) if scale is not None else None
-        self.shift = shift.detach().float().contiguous().to(dev) if shift is not None else None
+        plan_scale = None if passes == 16 else self.scale          # 3xFP16: the scale is in the packed weights
         OH = (x.H + 2 * pad - dil * (R - 1) - 1) // stride + 1
         OW = (x.W + 2 * pad - dil * (S - 1) - 1) // stride + 1
         self.out = out if out is not None else (ActTensor(x.N, OH, OW, O, device=dev) if want_nhwc else None)
@@ -220,7 +225,7 @@ class ConvLayer(_Planned):
                      dil=dil, passes=passes, relu=int(relu), out_cstride=self.out.cstride if self.out is not None else 0,
                      out_coffset=out_coffset, res_cstride=residual.cstride if residual is not None else 0, w_exp=w_exp)
         self.plan = lib().d2t_conv_plan_create(
-            C.byref(d), _p(x.x), _p(self.w_hi), _p(self.w_lo), _p(self.scale), _p(self.shift),
+            C.byref(d), _p(x.x), _p(self.w_hi), _p(self.w_lo), _p(plan_scale), _p(self.shift),
             _p(residual.x) if residual is not None else None, _p(self.out.x) if self.out is not None else None,
             _p(self.out_nchw))
         if not self.plan:
@@ -241,8 +246,8 @@ class ConvLayer(_Planned):
         O, I, R, S = self.weight.shape
         w = self.weight.detach()
         assert w.is_contiguous() and w.dtype == torch.float32
-        check(lib().d2t_conv_pack_weights_f16_dev(w.data_ptr(), O, I, R, S, _pad64(I), _p(self.amax_w), _p(self.w_hi),
-                                                  _p(self.w_lo), _stream()), "d2t_conv_pack_weights_f16_dev")
+        check(lib().d2t_conv_pack_weights_f16_dev(w.data_ptr(), _p(self.scale), O, I, R, S, _pad64(I), _p(self.amax_w),
+                                                  _p(self.w_hi), _p(self.w_lo), _stream()), "d2t_conv_pack_weights_f16_dev")
         ops._count(1)
 
     def run(self, stream=None):

@@ -67,7 +67,7 @@ class D2TTrainEngine(D2TEngine):
     def _make_layer(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, **kw):
         i = self._slot(weight, scale)
         layer = dc.ConvLayer(x, weight, scale, shift, stride, pad, dil, relu, residual, passes=16,
-                             amax_w=self.w_amax[i:i + 1], **kw)
+                             amax_w=self.wt_amax[i:i + 1], **kw)          # (bound of |w * scale|: the forward pack folds it too)
         layer.meta = dict(weight=weight, scale=scale, bias=shift if _is_param(shift) else None, stride=stride, pad=pad,
                           dil=dil, relu=relu, slot=i)
         self._meta.setdefault(id(weight), []).append(layer)
