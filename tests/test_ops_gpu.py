@@ -539,3 +539,32 @@ def test_psroi_integer_tables_outlier_guard():
     covers = (bins[:, 0] == 0) & (bins[:, 2] == 0) & (bins[:, 1] > 0) & (bins[:, 3] > 0)
     assert bool(torch.isnan(first[covers]).all()) and not bool(torch.isnan(first[~covers]).any())
     assert not bool(torch.isnan(top[:, 4]).any())
+
+
+def test_correlation_backward_legacy_launcher_symbol():
+    """Correlation_backward_cuda_kernel with the reference's own 40-argument order (correlation_cuda_kernel.h:47-88)
+    against the reference kernel itself compiled unmodified (oracle/_ref), for the D&T stride-1 geometry where the
+    reference backward is the adjoint of its forward."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_oracle.so not built (needs /root/reference at build time)")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, Cc, H, W, pad, k, md, s1, s2 = 2, 64, 20, 30, 8, 1, 8, 1, 1
+    a = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+    b = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+    gout = torch.randn(B, 289, H, W, device="cuda", generator=g)
+    want1, want2 = ref_cuda.correlation_backward(a, b, gout, pad, k, md, s1, s2)
+    g1, g2 = torch.full_like(a, float("nan")), torch.full_like(a, float("nan"))      # (the replacement needs no pre-zeroing)
+    ok = lib().Correlation_backward_cuda_kernel(
+        gout.data_ptr(), *gout.shape, *gout.stride(), a.data_ptr(), Cc, H, W, *a.stride(), b.data_ptr(), *b.stride(),
+        g1.data_ptr(), *g1.stride(), g2.data_ptr(), Cc, *g2.stride(), None, None, pad, k, md, s1, s2, 1,
+        torch.cuda.current_stream().cuda_stream)
+    assert ok == 1
+    torch.cuda.synchronize()
+    for got, want in ((g1, want1), (g2, want2)):
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    # non-contiguous strides are refused with a message
+    ok = lib().Correlation_backward_cuda_kernel(
+        gout.data_ptr(), *gout.shape, *gout.stride(), a.data_ptr(), Cc, H, W, 1, 2, 3, 4, b.data_ptr(), *b.stride(),
+        g1.data_ptr(), *g1.stride(), g2.data_ptr(), Cc, *g2.stride(), None, None, pad, k, md, s1, s2, 1,
+        torch.cuda.current_stream().cuda_stream)
+    assert ok == 0 and b"contiguous" in lib().d2t_last_error()
