@@ -194,8 +194,10 @@ def op_microbench(flush, hbm_gbs):
         oc, oh, ow = ops.correlation_shape(Hh, Ww, *p)
         from d2t_b200 import conv as dc
         # tensor-core kernel on the engine's native layout (split NHWC in, NCHW out) ...
-        layer = dc.CorrLayer(dc.ActTensor.from_nchw(a), dc.ActTensor.from_nchw(b), p[0], p[2], p[3], passes=3, want_nchw=True)
+        layer = dc.CorrLayer(dc.ActTensor.from_nchw(a), dc.ActTensor.from_nchw(b), p[0], p[2], p[3], passes=16, want_nchw=True)
         ms = time_kernel(layer.run, 20, flush)
+        layer3 = dc.CorrLayer(dc.ActTensor.from_nchw(a), dc.ActTensor.from_nchw(b), p[0], p[2], p[3], passes=3, want_nchw=True)
+        ms_tf32 = time_kernel(layer3.run, 10, flush)
         # ... through the reference-layout operator (adds the two NCHW -> split-NHWC re-layouts) ...
         ms_api = time_kernel(lambda: ops.correlation_forward(a, b, *p), 10, flush)
         # ... and the fp32 SIMT kernel it replaced
@@ -206,7 +208,8 @@ def op_microbench(flush, hbm_gbs):
         flops = 2.0 * oc * oh * ow * C_ * Bc
         out[name] = {"batch": Bc, "ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6,
                      "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_useful": flops / ms / 1e9,
-                     "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
+                     "kernel": "conv_igemm CORR mode, 3xFP16 (kind::f16); 3xTF32 variant: %.4f ms" % ms_tf32,
+                     "ms_3xtf32": ms_tf32, "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
     # detection decode + per-class NMS after the network (test_net.py:232-301), 4 frames x 30 classes
     from d2t_b200 import detect
     g = torch.Generator().manual_seed(50)

@@ -436,7 +436,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
-    static_assert(!(F16 && (CORR || PAIR)), "3xFP16 is a single-CTA convolution mode");
+    static_assert(!(F16 && PAIR), "3xFP16 is a single-CTA mode");
     static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
     static_assert(!CORRB || (F16 && !EPI2 && !WGRAD && BN == 128), "the correlation-backward mode is a plain 3xFP16 variant");
     extern __shared__ uint8_t smem_raw[];
@@ -536,7 +536,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         // of 3xTF32 MMA work per K block; the two overlap only partly (1450 cycles per K block end to end).
         // TMA copies per stage: A x (3xFP16: its two 32-channel sub-tiles), B x (, B lo: weights only)
         constexpr int NA = F16 ? 2 : 1;
-        constexpr int NL = NA + ((SPLIT && !CORR) ? 2 : 1);
+        // B copies: weights (hi, lo); correlation: the second frame's tile -- ONE fp32 box in the TF32 kinds, two 32-channel
+        // sub-tiles in 3xFP16 (they land in the B hi / B lo slots and are rewritten there as the fp16 pair, see the converters)
+        constexpr int NL = NA + ((SPLIT && !CORR) || (CORR && F16) ? 2 : 1);
         constexpr int TMA_BYTES = C::A_BYTES + (NL - NA) * C::B_BYTES;
         if constexpr (CORRB) {
             // ten copies per stage: the band's (hi, lo) boxes of the four tile rows (32 pixels x 64 halo columns each),
@@ -637,7 +639,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                             if (p.stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
                             else tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * p.dil, ih0 + r * p.dil, img);
                         } else if (CORR) {
-                            tma_load_4d(dst, map, fbar, kc * kBlockK, bw0, bh0, img);
+                            tma_load_4d(dst, map, fbar, kc * kBlockK + (F16 ? (lane - NA) * kBoxC : 0), bw0, bh0, img);
                         } else {
                             tma_load_2d(dst, map, fbar, k * kBlockK, n0);
                         }
@@ -761,6 +763,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             const uint32_t sw = (uint32_t)m & 7u;
             const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_TMEM_BASE;
             const float sa = pow2f(act_exp(p.amax_in));
+            const float sb = CORR ? pow2f(act_exp(p.amax_b)) : 1.f;
+            (void)sb;
             int stage = 0;
             uint32_t phase = 0;
             TRACE_DECL;
@@ -811,6 +815,41 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         const uint32_t slot = a_lane + stage * C::A_TMEM_COLS + half * 16;
                         tmem_st16(slot, hi);
                         tmem_st16(slot + 32, lo);
+                    }
+                    if constexpr (CORR) {
+                        // correlation: the B operand is an activation tile too.  Its two fp32 sub-tiles sit in the B hi / B lo
+                        // slots; row m's 64 values are split like A's and written back IN PLACE as row m of the fp16 hi tile
+                        // (first slot) and of the lo tile (second slot): the same 2 x 128 bytes the thread has just read.
+                        uint8_t* b0 = smem + stage * C::STAGE_BYTES + C::OFF_BHI + m * 128;
+                        uint8_t* b1 = smem + stage * C::STAGE_BYTES + C::OFF_BLO + m * 128;
+                        uint4 bh[8], bl[8];
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint8_t* src = half ? b1 : b0;
+#pragma unroll
+                            for (int c = 0; c < 8; c += 2) {
+                                const float4 v0 = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
+                                const float4 v1 = *reinterpret_cast<const float4*>(src + (((uint32_t)(c + 1) ^ sw) << 4));
+                                const float a[8] = {v0.x * sb, v0.y * sb, v0.z * sb, v0.w * sb, v1.x * sb, v1.y * sb, v1.z * sb, v1.w * sb};
+                                uint32_t wh[4], wl[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const __half2 h = __floats2half2_rn(a[2 * q], a[2 * q + 1]);
+                                    const float2 hf = __half22float2(h);
+                                    const __half2 l = __floats2half2_rn(a[2 * q] - hf.x, a[2 * q + 1] - hf.y);
+                                    wh[q] = *reinterpret_cast<const uint32_t*>(&h);
+                                    wl[q] = *reinterpret_cast<const uint32_t*>(&l);
+                                }
+                                bh[half * 4 + (c >> 1)] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                                bl[half * 4 + (c >> 1)] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            *reinterpret_cast<uint4*>(b0 + (((uint32_t)j ^ sw) << 4)) = bh[j];
+                            *reinterpret_cast<uint4*>(b1 + (((uint32_t)j ^ sw) << 4)) = bl[j];
+                        }
+                        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
@@ -892,7 +931,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         // packers) and the shift INITIALISES the accumulator, so a finished tile needs no affine pass at all -- the traced
         // epilogue spent 3.4 k of its 8.5 k cycles per tile there on the residual 1x1 layers (profiles/r02_conv_trace.txt).
         // Every other variant (TF32 kinds, WGRAD's column scale, CORRB's 1/C) keeps the scale / shift loop below.
-        constexpr bool FOLDED = F16 && !WGRAD && !CORRB;
+        constexpr bool FOLDED = F16 && !WGRAD && !CORRB && !CORR;
         float* scsh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
         const int et = (warp - kEpiWarp0) * 32 + lane;     // 0..255
         auto fetch_scsh = [&](int tile) -> float {
@@ -1682,7 +1721,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
                                                int passes, const float* in1, const float* in2, float* out,
                                                int out_cstride, int out_coffset, float* out_nchw) {
     if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || md < 0 || stride <= 0 || !in1 || !in2 ||
-        (passes != 1 && passes != 3) || (!out && !out_nchw)) {
+        (passes != 1 && passes != 3 && passes != 16) || (!out && !out_nchw)) {
         set_error("d2t_corr_plan_create: bad arguments");
         return nullptr;
     }
@@ -1706,7 +1745,7 @@ extern "C" d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, 
     ConvArgs& a = pl->args;
     a.N = N; a.OH = OH; a.OW = OW; a.Cout = (2 * r + 1) * (2 * r + 1);
     a.R = 1; a.S = 1; a.stride = stride; a.pad = pad - md; a.dil = 1;       // element = lattice*stride + (md - pad)
-    a.kc_blocks = C / kBoxC;
+    a.kc_blocks = (C + kblk_of(passes) - 1) / kblk_of(passes);   // (3xFP16: a trailing half block reads zeros past C)
     a.TW_log2 = 4; a.TH = 8; a.stem = 0;
     a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 7) / 8;
     a.m_tiles = N * a.tiles_h * a.tiles_w;
@@ -1884,7 +1923,8 @@ extern "C" int d2t_conv_plan_set_mask(d2t_conv_plan* pl, const float* mask, int 
 }
 
 extern "C" int d2t_conv_plan_set_weight_amax(d2t_conv_plan* pl, const float* amax_w) {
-    D2T_REQUIRE(pl && pl->passes == 16 && !pl->corr, "d2t_conv_plan_set_weight_amax: needs a 3xFP16 convolution plan");
+    D2T_REQUIRE(pl && pl->passes == 16, "d2t_conv_plan_set_weight_amax: needs a 3xFP16 plan (convolution: max |packed weights|; "
+                                        "correlation: max |second input|)");
     pl->args.amax_b = amax_w;
     return 1;
 }
@@ -1953,8 +1993,13 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
         return pl->BN == 64 ? launch_conv<64, 16, false, false, false, true>(pl, stream)
                             : launch_conv<128, 16, false, false, false, true>(pl, stream);
     if (pl->corrb) return launch_conv<128, 16, false, false, false, false, true>(pl, stream);
-    if (pl->corr)
+    if (pl->corr) {
+        if (pl->passes == 16) {
+            D2T_REQUIRE(pl->args.amax_b, "correlation plan: the fp16-split mode needs both inputs' amax (d2t_conv_plan_set_weight_amax for the second)");
+            return launch_conv<128, 16, true, false>(pl, stream);
+        }
         return pl->passes == 3 ? launch_conv<128, 3, true, false>(pl, stream) : launch_conv<128, 1, true, false>(pl, stream);
+    }
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))
     if (pl->passes == 16) {
         if (pl->args.mask) {        // backward-data plans: the epilogue with the ReLU mask compiled in

@@ -440,7 +440,8 @@ class StemConv(_Planned):
 
 class CorrLayer(_Planned):
     """Cross-frame correlation (kernel_size 1, stride1 == stride2) of two NHWC tensors on the tensor cores;
-    writes a channel slice of `out` (NHWC) and/or a plain NCHW tensor."""
+    writes a channel slice of `out` (NHWC) and/or a plain NCHW tensor.  passes = 16: 3xFP16 (kind::f16, twice the TF32
+    rate; both inputs' amax scalars must be current), 3: 3xTF32, 1: single-pass TF32."""
 
     def __init__(self, x1, x2, pad, md, stride, passes=3, out=None, out_coffset=0, want_nchw=False):
         assert (x1.N, x1.H, x1.W, x1.cstride) == (x2.N, x2.H, x2.W, x2.cstride)
@@ -456,7 +457,9 @@ class CorrLayer(_Planned):
         if not self.plan:
             raise D2TError("d2t_corr_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * x1.N * oh * ow * self.D * self.D * x1.C
-        self._bind_amax(None, out)
+        self._bind_amax(x1 if passes == 16 else None, out)
+        if passes == 16:      # 3xFP16: both operands are activations, each scaled by its own tensor's amax
+            check(lib().d2t_conv_plan_set_weight_amax(self.plan, _p(x2.amax)), "d2t_conv_plan_set_weight_amax")
 
     def run(self, stream=None):
         _Planned.run(self, stream)

@@ -15,7 +15,7 @@ function as the reference's python loop over legs).  Activations stay fp32 NHWC 
 convs; tensors the reference-layout operators consume (correlation, PSRoI, proposal step) are
 emitted as plain fp32 NCHW by the producing conv's epilogue.  ``passes=16`` (default) is the
 fp32-accurate fp16-split mode ("3xFP16": hi/lo fp16 operands with per-tensor power-of-two scales,
-twice the TF32 tensor rate; the stem and the correlations stay on 3xTF32), ``passes=3`` the
+twice the TF32 tensor rate, correlations included; only the 3-channel stem stays on 3xTF32), ``passes=3`` the
 fp32-accurate 3xTF32 mode, ``passes=1`` single-pass TF32.
 """
 import os
@@ -130,7 +130,7 @@ class D2TEngine(object):
             f = self.feat_nhwc[tag]
             assert corr.kernel_size == 1 and corr.stride1 == corr.stride2
             self.corr_layers.append(dc.CorrLayer(f.batch_slice(0, pairs), f.batch_slice(pairs, N), corr.pad_size,
-                                                 corr.max_displacement, corr.stride1, passes=tf32_passes, out=self.trk_in,
+                                                 corr.max_displacement, corr.stride1, passes=passes, out=self.trk_in,
                                                  out_coffset=coff))
         kind = {16: "kind::f16 x3 passes (fp16 hi/lo split, per-tensor 2^k scales)", 3: "kind::tf32 x3 passes",
                 1: "kind::tf32 x1 pass"}[passes]

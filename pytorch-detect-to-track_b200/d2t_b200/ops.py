@@ -14,6 +14,8 @@ from ._lib import check, lib
 
 # False routes every correlation through the fp32 SIMT kernels of csrc/correlation.cu
 TENSOR_CORE_CORRELATION = True
+# operand split of the tensor-core correlation: 16 = 3xFP16 (default), 3 = 3xTF32 (both fp32-accurate)
+CORRELATION_PASSES = 16
 
 # kernels of libd2t_b200.so enqueued since import (bench.py reports the delta as gpu_launches)
 LAUNCHES = 0
@@ -155,11 +157,11 @@ def correlation_forward(in1, in2, pad, k, md, s1, s2):
     oc, oh, ow = correlation_shape(H, W, pad, k, md, s1, s2)
     if k == 1 and s1 == s2 and 1 <= md // s2 <= 8 and Cc >= 32 and TENSOR_CORE_CORRELATION:
         # every D&T configuration (rfcn.py:58-60): Gram tiles on the tensor cores (csrc/conv.cu, CORR mode),
-        # fp32-accurate 3xTF32; the NCHW operands are first re-laid out as split NHWC
+        # fp32-accurate 3xFP16; the NCHW operands are first re-laid out as NHWC (+ each tensor's max |x| for its scale)
         from . import conv as dc
         with torch.cuda.device_of(in1):
-            x1, x2 = dc.ActTensor.from_nchw(in1, amax=False), dc.ActTensor.from_nchw(in2, amax=False)
-            return dc.CorrLayer(x1, x2, pad, md, s1, passes=3, want_nchw=True).run()
+            x1, x2 = dc.ActTensor.from_nchw(in1), dc.ActTensor.from_nchw(in2)
+            return dc.CorrLayer(x1, x2, pad, md, s1, passes=CORRELATION_PASSES, want_nchw=True).run()
     with torch.cuda.device_of(in1):
         out = torch.empty(B, oc, oh, ow, device=in1.device)
         check(lib().d2t_correlation_forward(in1.data_ptr(), in2.data_ptr(), B, Cc, H, W, pad, k, md, s1, s2,

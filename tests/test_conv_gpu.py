@@ -210,13 +210,16 @@ def test_engine_chains_and_graph_replay():
 @pytest.mark.parametrize("C,H,W,p,B", [(64, 20, 30, (8, 1, 8, 1, 1), 2), (1024, 38, 63, (8, 1, 8, 1, 1), 2),
                                        (512, 75, 125, (8, 1, 8, 2, 2), 1), (2048, 38, 63, (8, 1, 8, 1, 1), 1),
                                        (96, 21, 27, (4, 1, 4, 1, 1), 1), (40, 13, 50, (0, 1, 3, 1, 1), 1)])
-def test_tensor_core_correlation(C, H, W, p, B):
-    """CORR mode of the tcgen05 kernel against the reference kernel itself (or the fp32 SIMT kernel)."""
+@pytest.mark.parametrize("passes", [16, 3])
+def test_tensor_core_correlation(C, H, W, p, B, passes, monkeypatch):
+    """CORR mode of the tcgen05 kernel (3xFP16 and 3xTF32) against the reference kernel itself (or the fp32 SIMT kernel);
+    inputs of different magnitudes: each operand carries its own scale in the fp16 split."""
     from d2t_b200 import ops
     from oracle import ref_cuda
+    monkeypatch.setattr(ops, "CORRELATION_PASSES", passes)
     g = torch.Generator(device="cuda").manual_seed(77)
-    a = torch.randn(B, C, H, W, device="cuda", generator=g)
-    b = torch.randn(B, C, H, W, device="cuda", generator=g)
+    a = torch.randn(B, C, H, W, device="cuda", generator=g) * 37.0
+    b = torch.randn(B, C, H, W, device="cuda", generator=g) * 2.0e-3
     out = ops.correlation_forward(a, b, *p)
     ops.TENSOR_CORE_CORRELATION = False
     try:
