@@ -260,10 +260,37 @@ int d2t_conv_plan_set_scratch(d2t_conv_plan* plan, void* scratch, size_t bytes);
  * size instead of executing griddepcontrol.wait.  The caller zeroes the counters before each pass over the chain (the
  * engine keeps them in the arena its per-forward memset clears).  Null pointers restore the default. */
 int d2t_conv_plan_set_done(d2t_conv_plan* plan, const d2t_conv_plan* prev, const int* prev_counter, int* self_counter);
+/* Let a stand-alone launch of the plan fetch its first weight tiles BEFORE it waits for the previous launch on the stream
+ * (programmatic dependent launch): the first touch of a layer's weights is a DRAM miss that otherwise sits in front of the
+ * first MMA.  Only for weights that no kernel up to and including the launch immediately before this one writes (an
+ * inference engine with weights packed once; NOT a training loop that re-packs them right before the layer).  Off by default. */
+int d2t_conv_plan_set_early_weights(d2t_conv_plan* plan, int on);
 void d2t_conv_plan_destroy(d2t_conv_plan* plan);
 /* out8 = {OH, OW, tile_h, tile_w, BN, m_tiles, n_tiles, grid*10 + pair_mode} */
 int d2t_conv_plan_info(const d2t_conv_plan* plan, int* out8);
 int d2t_conv_plan_run(const d2t_conv_plan* plan, cudaStream_t stream);
+
+/* ---- Layer chains: a LIST of 3xFP16 convolution plans run by ONE persistent launch ----
+ * The reference's trunk is ~110 dependent cuDNN calls (faster_rcnn/resnet.py:66-109, 258-312; rfcn.py:49-53; rpn/rpn.py:62-71);
+ * launched one by one, every kernel boundary idles the SMs for several microseconds.  A chain keeps one CTA per SM
+ * resident over the whole list (tensor memory and barriers stay allocated, the tensor maps of layer i are read from a
+ * descriptor array) and separates DEPENDENT layers by a grid-wide barrier instead of a kernel boundary.
+ *   d2t_conv_plan_chainable: 1 if the plan can be a chain layer (plain 3xFP16 convolution with its input amax set: no
+ *                            stem / correlation / weight-gradient / mask / completion-counter plans).
+ *   d2t_conv_chain_create:   plans[i] becomes layer i.  sync_before[i] != 0 (or sync_before == NULL): layer i reads -- as
+ *                            input or residual -- what a layer since the last such mark writes, so the CTAs meet at a
+ *                            barrier before it; independent neighbours run back to back.  dev_buf: d2t_conv_chain_bytes(n)
+ *                            bytes of device memory, 256-byte aligned, owned by the caller for the life of the chain.
+ *                            The plans' tensor maps and arguments are COPIED: create the chain after every
+ *                            d2t_conv_plan_set_* call; all plans must share one stream-K scratch.
+ *   d2t_conv_chain_run:      one cooperative launch on `stream`; results are bit-identical to running the plans one by one. */
+typedef struct d2t_conv_chain d2t_conv_chain;
+int d2t_conv_plan_chainable(const d2t_conv_plan* plan);
+size_t d2t_conv_chain_bytes(int n_layers);
+d2t_conv_chain* d2t_conv_chain_create(const d2t_conv_plan* const* plans, const int* sync_before, int n_layers,
+                                      void* dev_buf, size_t bytes);
+int d2t_conv_chain_run(const d2t_conv_chain* chain, cudaStream_t stream);
+void d2t_conv_chain_destroy(d2t_conv_chain* chain);
 
 /* The 7x7 stride-2 pad-3 stem conv (faster_rcnn/resnet.py:116) on the same kernel: the image is
  * first packed by d2t_stem_pack_input into a zero-bordered NHWC4 buffer [N, (H+7)&~1, W+8, 4] and

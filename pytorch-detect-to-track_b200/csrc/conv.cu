@@ -56,6 +56,8 @@
 #include <cuda_fp16.h>
 
 #include <atomic>
+#include <cstddef>
+#include <cstring>
 #include <new>
 
 #include "common.cuh"
@@ -117,6 +119,10 @@ struct ConvArgs {
     const int* done_prev;
     int done_target;
     int* done_self;
+    // stand-alone launches: the weight (B operand) copies of the first pipeline stages are issued BEFORE griddepcontrol.wait --
+    // packed weights do not depend on the previous launch, and their first touch per forward is a DRAM miss that otherwise
+    // sits in front of the first MMA (d2t_conv_plan_set_early_weights; never for plans whose B operand is produced upstream)
+    int early_b;
     long long* trace;              // debug builds only (D2T_CONV_TRACE): per-CTA wait-cycle counters
     int exp;                       // debug builds only: experiment bit mask (env D2T_CONV_EXP)
 };
@@ -421,17 +427,19 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // MASK = true compiles the backward-data epilogue (ReLU mask of the forward activation, d2t_conv_plan_set_mask) in.  It is
 // a template parameter, not a run-time test, because the forward pass pays for the extra code in its hottest loop even
 // when the pointer is null: measured on one B200 box, 5.27 ms against 4.98 ms for the 110 forward launches of the step.
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false, bool CORRB = false, bool MASK = false>
-__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
-conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operand)
-                const __grid_constant__ CUtensorMap tmB_hi,   // weights w (CORR: the second frame's activation)
-                const __grid_constant__ CUtensorMap tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
-                const __grid_constant__ CUtensorMap tmO,      // NHWC output (TMA store)
-                const __grid_constant__ CUtensorMap tmR,      // NHWC residual (EPI2: TMA load into the output slabs)
-                const ConvArgs p) {
-#ifdef D2T_CONV_TRACE
-    const long long t_entry__ = clock64();
-#endif
+// CHAIN = true compiles the body for the multi-layer persistent kernel (conv_chain below): the pipeline barriers are
+// (re)initialised here, per layer; tensors written by earlier layers of the same launch are only read through the TMA or
+// with L2-coherent loads; a publisher waits for its stream-K flag to be consumed before it reuses its scratch slot (layers
+// that do not depend on each other run without a grid-wide barrier between them); no setmaxnreg.
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD, bool CORRB, bool MASK, bool CHAIN>
+__device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activation (A operand)
+                                          const CUtensorMap& tmB_hi,   // weights w (CORR: the second frame's activation)
+                                          const CUtensorMap& tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
+                                          const CUtensorMap& tmO,      // NHWC output (TMA store)
+                                          const CUtensorMap& tmR,      // NHWC residual (EPI2: TMA load into the output slabs)
+                                          const ConvArgs& p, uint8_t* smem /*1024-B aligned*/, uint64_t* bars,
+                                          const uint32_t tmem_base, const uint32_t crank, const int prev_nbars,
+                                          const Sched* pre_sched = nullptr) {
     using C = Cfg<BN, PASSES, PAIR, EPI2>;
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
@@ -439,11 +447,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
     static_assert(!(F16 && PAIR), "3xFP16 is a single-CTA mode");
     static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
     static_assert(!CORRB || (F16 && !EPI2 && !WGRAD && BN == 128), "the correlation-backward mode is a plain 3xFP16 variant");
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_u32 = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
+    static_assert(!CHAIN || (F16 && !CORR && !PAIR && !WGRAD && !CORRB), "the chain kernel runs 3xFP16 convolutions");
     uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;                   // [2 groups][128 rows][128 B], swizzled
-    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_STAGE_BYTES);
     uint64_t* full = bars;                        // [STAGES]   TMA -> MMA
     uint64_t* empty = bars + C::STAGES;           // [STAGES]   MMA -> TMA
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue: chunk buffer complete
@@ -455,75 +460,50 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CS = PAIR ? 2 : 1;               // CTAs per work unit
-    uint32_t crank = 0;                            // 0 = leader
-    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int unit_id = blockIdx.x / CS, n_units = gridDim.x / CS;
     const int tiles = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;     // (pair-)tiles
     const int k_iters = WGRAD ? p.wg_kiters : (CORRB ? p.TH + 2 * p.corr_r : p.R * p.S * p.kc_blocks);
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB_hi);
-        if (SPLIT && !CORR) prefetch_tmap(&tmB_lo);
-        if (!CORR && p.out) prefetch_tmap(&tmO);
-        if ((EPI2 && p.res) || CORRB) prefetch_tmap(&tmR);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < C::STAGES; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
-            mbar_init(&cvt[i], CS * kCvtThreads);          // (leader's copy collects both CTAs' converters)
+    // the stream-K split needs every participating CTA to own at least one unit (a finisher waits for ALL CTAs between the
+    // tile's first chunk and itself): the stand-alone launch sizes its grid accordingly (sk_grid), a chain layer with fewer
+    // units than CTAs leaves the surplus CTAs idle
+    const long long units_total = (long long)tiles * ((k_iters + kChunkK - 1) / kChunkK);
+    const int unit_id = blockIdx.x / CS;
+    const int n_units = CHAIN ? (int)(units_total < (long long)gridDim.x ? units_total : (long long)gridDim.x) : gridDim.x / CS;
+    if constexpr (CHAIN) {
+        // per-layer pipeline reset: every role has left the previous layer (the caller's __syncthreads), no arrival is
+        // pending on any barrier (the MMA thread waited for its last commits), so the barriers restart at phase 0
+        if (warp == 1 && lane == 0) {
+            for (int i = 0; i < prev_nbars; ++i)          // (the previous layer's variant may have laid out more or fewer)
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bars + i)) : "memory");
+            for (int i = 0; i < C::STAGES; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+                mbar_init(&cvt[i], kCvtThreads);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tfull[i], 1);
+                mbar_init(&tempty[i], kEpiThreads);
+                mbar_init(&xempty[i], kEpiThreads);
+                mbar_init(&rfull[i], 1);
+            }
+            fence_mbar_init();
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], CS * kEpiThreads);       // (leader's copy collects both CTAs' epilogue threads)
-            mbar_init(&xempty[i], CS * kEpiThreads);
-            mbar_init(&rfull[i], 1);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "n"(C::TMEM_COLS));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "n"(C::TMEM_COLS));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone signals them
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const Sched sched(tiles, k_iters, kChunkK, unit_id, n_units);
-    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
-    // overlapped the tail of the previous layer; from here on we touch its output.
-#ifdef D2T_CONV_TRACE
-    const long long t_prol__ = clock64();
-#endif
-    if (p.done_prev) {
-        // the previous launch of this chain counts its finished CTAs (see the end of this kernel): poll instead of waiting
-        // for the hardware's notion of grid completion; everything older in the stream was complete before that launch
-        // could finish (it waited the same way, or with griddepcontrol.wait)
-        if (threadIdx.x == 0) {
-            int v;
-            do {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.done_prev) : "memory");
-                if (v < p.done_target) __nanosleep(40);
-            } while (v < p.done_target);
+        if (warp == 0 && lane == 0) {
+            prefetch_tmap(&tmA);
+            prefetch_tmap(&tmB_hi);
+            prefetch_tmap(&tmB_lo);
+            if (p.out) prefetch_tmap(&tmO);
+            if (EPI2 && p.res) prefetch_tmap(&tmR);
         }
         __syncthreads();
-        asm volatile("fence.proxy.async;" ::: "memory");      // my TMA loads come after the acquire
-    } else {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-    }
-    asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("fence.proxy.async;" ::: "memory");      // TMA reads of this layer come after the caller's acquire
+        tc_fence_after();
 #ifdef D2T_CONV_TRACE
-    const long long t_dep__ = clock64();
+        if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 64 + 5] = clock64();          // role 0 value 5: body start
 #endif
+    }
+    // (a stand-alone launch computes its schedule -- 64-bit divisions -- before griddepcontrol.wait and hands it in)
+    Sched sched = pre_sched ? *pre_sched : Sched(tiles, k_iters, kChunkK, CHAIN && unit_id >= n_units ? 0 : unit_id, n_units);
+    if (CHAIN && unit_id >= n_units) sched.nseg = 0;
 
     if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
     // ---- warpgroups 0 (and 3 in 3xFP16 mode): TMA producer, MMA issuer, converters
@@ -621,7 +601,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 const int bw0 = (ow0 - p.corr_r) * p.stride - p.pad;
                 const int bh0 = (oh0 - p.corr_r + 4 * n_tile) * p.stride - p.pad;
                 const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
-                int kc = k_beg % p.kc_blocks, rs = k_beg / p.kc_blocks, s = rs % p.S, r = rs / p.S;
+                const int kcb = p.kc_blocks, fS = p.S, dil = p.dil, stem = p.stem;
+                int kc = k_beg % kcb, rs = k_beg / kcb, s = rs % fS, r = rs / fS;
                 for (int k = k_beg; k < k_end; ++k) {
                     TRACED_WAIT(0, &empty[stage], phase ^ 1);
                     uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
@@ -629,15 +610,15 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     if (PAIR) {
                         // each CTA stages its own A tile and its half of the weight tile (completion: own barrier)
                         if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
-                        if (is_a) tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                        if (is_a) tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * dil, ih0 + r * dil, img);
                         else tma_load_2d(dst, map, fbar, k * kBlockK, n0 + (int)crank * (BN / 2));
                     } else {
                         if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
                         if (is_a) {
                             // stem: filter row r = 32 consecutive floats (8 pixels x 4 channels) of padded input row
                             // 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
-                            if (p.stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
-                            else tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * p.dil, ih0 + r * p.dil, img);
+                            if (stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
+                            else tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * dil, ih0 + r * dil, img);
                         } else if (CORR) {
                             tma_load_4d(dst, map, fbar, kc * kBlockK + (F16 ? (lane - NA) * kBoxC : 0), bw0, bh0, img);
                         } else {
@@ -648,9 +629,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         stage = 0;
                         phase ^= 1;
                     }
-                    if (++kc == p.kc_blocks) {
+                    if (++kc == kcb) {
                         kc = 0;
-                        if (++s == p.S) {
+                        if (++s == fS) {
                             s = 0;
                             ++r;
                         }
@@ -671,13 +652,14 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         if (lane == 0 && crank == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : (F16 ? make_idesc_f16<BN>() : make_idesc<BN>());
             const uint64_t desc0 = make_smem_desc(smem_u32(smem));     // stage s / operand o: + (byte offset >> 4)
-            int stage = 0, cbuf = 0, local = 0;
+            int stage = 0, cbuf = 0, local = 0, issued = 0;
             uint32_t phase = 0, cphase = 0;
             TRACE_DECL;
             TRACE_BEGIN();
             for (; local < sched.nseg; ++local) {
                 const Seg sg = sched.get(local);
                 const int xacc = local & 1;
+                issued += min(sg.c1 * kChunkK, k_iters) - sg.c0 * kChunkK;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
                 if (SPLIT && !ATMEM) {
                     TRACED_WAIT(0, &xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
@@ -694,6 +676,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     TRACED_WAIT(2, &full[stage], phase);
                     if (SPLIT || PAIR) TRACED_WAIT(3, &cvt[stage], phase);   // lo tiles written (pair: peer landed too)
                     tc_fence_after();
+#ifdef D2T_CONV_TRACE
+                    if (CHAIN && p.trace && local == 0 && k == k_beg) p.trace[(size_t)blockIdx.x * 64 + 8 + 5] = clock64();   // role 1 value 5: first MMA
+#endif
                     const uint64_t a_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
                     if (SPLIT) {
                         const uint64_t a_lo = a_hi + (C::OFF_ALO >> 4);
@@ -742,6 +727,11 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                         phase ^= 1;
                     }
                 }
+            }
+            if constexpr (CHAIN) {
+                // the barriers are re-initialised for the next layer: no commit may still be on its way to `empty`
+                for (int s = 0; s < C::STAGES; ++s)
+                    if (issued > s) mbar_wait_sleep(&empty[s], (uint32_t)(((issued - s - 1) / C::STAGES) & 1));
             }
             TRACE_FLUSH(1);
         }
@@ -1034,6 +1024,18 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             if (sg.role == 1) {
                 // partial tile: publish registers -> scratch[cta][column][row] (coalesced across the warp)
                 float* dst = p.sk_scratch + ((size_t)blockIdx.x * BN + cofs) * kBlockM + m;
+                if constexpr (CHAIN) {
+                    // no grid-wide barrier separates independent layers: the finisher of my previous partial clears the flag
+                    // once it has read the slot
+                    if (m == 0 && grp == 0) {
+                        int v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.sk_flags + blockIdx.x) : "memory");
+                            if (v != 0) __nanosleep(64);
+                        } while (v != 0);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
 #pragma unroll
                 for (int j = 0; j < HN; ++j) dst[j * kBlockM] = acc[j];
                 __threadfence();
@@ -1069,7 +1071,10 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                 if (c_first < unit_id) {
                     asm volatile("bar.sync 1, 256;" ::: "memory");        // every partial of this tile has been read
                     if (m == 0 && grp == 0)
-                        for (int cc = c_first; cc < unit_id; ++cc) p.sk_flags[cc * CS + (int)crank] = 0;
+                        for (int cc = c_first; cc < unit_id; ++cc) {
+                            if constexpr (CHAIN) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + cc), "r"(0) : "memory");
+                            else p.sk_flags[cc * CS + (int)crank] = 0;
+                        }
                 }
             }
             if constexpr (CORR) {
@@ -1134,13 +1139,13 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
                     if (full16) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(rh + j));
+                            const float4 a = CHAIN ? __ldcg(reinterpret_cast<const float4*>(rh + j)) : __ldg(reinterpret_cast<const float4*>(rh + j));
                             v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (ch0 + j < p.Cout) v[j] += __ldg(rh + j);
+                            if (ch0 + j < p.Cout) v[j] += CHAIN ? __ldcg(rh + j) : __ldg(rh + j);
                     }
                 }
                 if (p.relu) {
@@ -1260,6 +1265,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         }
 #ifdef D2T_CONV_TRACE
         if ((warp - kEpiWarp0) % 4 == 0) TRACE_FLUSH(6 + (warp - kEpiWarp0) / 4);
+        if (CHAIN && p.trace && warp == kEpiWarp0 && lane == 0) p.trace[(size_t)blockIdx.x * 64 + 48 + 5] = clock64();   // role 6 value 5: epilogue done
 #endif
         if (p.amax_out) {
             // running max |x| of the output tensor: ONE atomic per CTA and layer (values are >= 0, so unsigned integer
@@ -1273,23 +1279,116 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
             if (warp == kEpiWarp0 && lane == 0 && *red != 0u && !EXP(8)) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), *red);
         }
     }
-#ifdef D2T_CONV_TRACE
-    const long long t_w0__ = clock64();
-#endif
     if (warp >= kEpiWarp0 && lane == 0 && ((warp - kEpiWarp0) & 3) == 0) {
         tma_store_wait_all();
-        if (p.done_self) {                                    // my bulk stores are complete: order them before the count below
+        if (CHAIN || p.done_self) {                           // my bulk stores are complete: order them before the count / barrier
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
         }
     }
-#ifdef D2T_CONV_TRACE
-    if (p.trace && warp == kEpiWarp0 && lane == 0) {
-        p.trace[(size_t)blockIdx.x * 64 + 16 + 5] = clock64() - t_w0__;     // role 2 value 5: the final store wait
-        p.trace[(size_t)blockIdx.x * 64 + 16 + 6] = t_w0__ - t_entry__;     // role 2 value 6: epilogue warp 0 done (from entry)
-    }
-#endif
     tc_fence_before();
+}
+
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false, bool CORRB = false, bool MASK = false>
+__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
+conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
+           const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO,
+           const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvArgs p) {
+#ifdef D2T_CONV_TRACE
+    const long long t_entry__ = clock64();
+#endif
+    using C = Cfg<BN, PASSES, PAIR, EPI2>;
+    constexpr bool SPLIT = C::SPLIT;
+    constexpr int kCvtThreads = C::CVT_THREADS;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
+    uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* xempty = tempty + 2;
+    uint64_t* cvt = xempty + 2;
+    uint64_t* rfull = cvt + C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CS = PAIR ? 2 : 1;
+    uint32_t crank = 0;                            // 0 = leader
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB_hi);
+        if (SPLIT && !CORR) prefetch_tmap(&tmB_lo);
+        if (!CORR && p.out) prefetch_tmap(&tmO);
+        if ((EPI2 && p.res) || CORRB) prefetch_tmap(&tmR);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+            mbar_init(&cvt[i], CS * kCvtThreads);          // (leader's copy collects both CTAs' converters)
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], CS * kEpiThreads);       // (leader's copy collects both CTAs' epilogue threads)
+            mbar_init(&xempty[i], CS * kEpiThreads);
+            mbar_init(&rfull[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const Sched sched(((p.m_tiles + CS - 1) / CS) * p.n_tiles,
+                      WGRAD ? p.wg_kiters : (CORRB ? p.TH + 2 * p.corr_r : p.R * p.S * p.kc_blocks), C::CHUNK,
+                      (int)blockIdx.x / CS, (int)gridDim.x / CS);
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+    // overlapped the tail of the previous layer; from here on we touch its output.
+#ifdef D2T_CONV_TRACE
+    const long long t_prol__ = clock64();
+#endif
+    if (p.done_prev) {
+        // the previous launch of this chain counts its finished CTAs (see the end of this kernel): poll instead of waiting
+        // for the hardware's notion of grid completion; everything older in the stream was complete before that launch
+        // could finish (it waited the same way, or with griddepcontrol.wait)
+        if (threadIdx.x == 0) {
+            int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.done_prev) : "memory");
+                if (v < p.done_target) __nanosleep(40);
+            } while (v < p.done_target);
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");      // my TMA loads come after the acquire
+    } else {
+        // (the weight lanes of the producer warp run ahead when the plan allows it: see ConvArgs::early_b)
+        constexpr int NA_ = C::F16 ? 2 : 1, NL_ = NA_ + ((SPLIT && !CORR) || (CORR && C::F16) ? 2 : 1);
+        const bool runs_ahead = !CORR && !PAIR && !WGRAD && !CORRB && p.early_b && warp == 0 && lane >= NA_ && lane < NL_;
+        if (!runs_ahead) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.launch_dependents;");
+#ifdef D2T_CONV_TRACE
+    const long long t_dep__ = clock64();
+#endif
+
+    conv_body<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK, false>(tmA, tmB_hi, tmB_lo, tmO, tmR, p, smem, bars, tmem_base,
+                                                                        crank, 0, &sched);
     __syncthreads();
     if (p.done_self && threadIdx.x == 0) {         // every thread's stores (and the flag resets above) precede the barrier
         __threadfence();
@@ -1316,6 +1415,114 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA,      // activation (A operan
         }
 #endif
     }
+}
+
+// ------------------------------------------------------------------ the multi-layer persistent kernel
+// Every dependent launch of the layer chain costs ~6 us in which the SMs idle (the next grid's CTAs become
+// resident as this grid's exit, then sit in griddepcontrol.wait until the LAST CTA is done and its writes are flushed) on top
+// of the prologue (barrier init, TMEM allocation).  conv_chain runs a LIST of 3xFP16 convolution layers in one launch: one
+// CTA per SM stays resident, keeps its tensor memory, and walks the list; each layer is the same conv_body, with its tensor
+// maps and arguments read from a descriptor array in global memory.  Where layer l reads what an earlier layer of the launch
+// wrote, the CTAs meet at a grid-wide barrier (self-resetting counter + generation word: safe under CUDA-graph replay);
+// independent neighbours (the four heads on base_feat, a block's downsample branch next to its first 1x1) run back to back.
+// Launched cooperatively, so all CTAs are co-resident by construction.
+struct alignas(128) ChainLayer {
+    CUtensorMap tmA, tmB_hi, tmB_lo, tmO, tmR;
+    ConvArgs args;
+    int variant;                   // 0: BN = 128, 1: BN = 128 with full-tile output staging (EPI2), 2: BN = 64
+    int sync_before;               // grid-wide barrier before this layer
+};
+constexpr int kChainBarsOff = 224 * 1024;     // the largest variant layout: 3 x 64 KB stages + 32 KB output staging
+constexpr int kChainSmem = kChainBarsOff + 1024 /*align slack*/ + 384 /*barriers*/ + 1024 /*shift of the current n tile*/ +
+                           2 * 288 /*ConvArgs + variant + sync_before of the current and the next layer*/;
+static_assert(sizeof(ConvArgs) + 8 <= 288 && sizeof(ConvArgs) % 4 == 0 && offsetof(ChainLayer, variant) == offsetof(ChainLayer, args) + sizeof(ConvArgs) &&
+              offsetof(ChainLayer, sync_before) == offsetof(ChainLayer, variant) + 4 && kChainSmem <= 227 * 1024, "chain shared-memory budget");
+static_assert(Cfg<128, 16, false, false>::STAGES * Cfg<128, 16, false, false>::STAGE_BYTES + Cfg<128, 16, false, false>::OUT_STAGE_BYTES <= kChainBarsOff &&
+              Cfg<128, 16, false, true>::STAGES * Cfg<128, 16, false, true>::STAGE_BYTES + Cfg<128, 16, false, true>::OUT_STAGE_BYTES <= kChainBarsOff &&
+              Cfg<64, 16, false, false>::STAGES * Cfg<64, 16, false, false>::STAGE_BYTES + Cfg<64, 16, false, false>::OUT_STAGE_BYTES <= kChainBarsOff,
+              "chain shared-memory layout");
+static_assert(3 * Cfg<64, 16, false, false>::STAGES + 8 <= 40, "chain barrier block");
+
+__device__ __forceinline__ void grid_barrier(int* gsync, int nblocks) {      // one thread per CTA
+    __threadfence();
+    int gen, old;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gen) : "l"(gsync + 1) : "memory");     // BEFORE arriving
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(gsync) : "memory");
+    if (old == nblocks - 1) {
+        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(gsync), "r"(0) : "memory");          // ready for the next barrier
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(gsync + 1) : "memory");
+    } else {
+        int g;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(g) : "l"(gsync + 1) : "memory");
+            if (g == gen) __nanosleep(32);
+        } while (g == gen);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) conv_chain(const ChainLayer* __restrict__ layers, const int n_layers, int* gsync) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChainBarsOff);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 44);          // past every variant's barriers (and its spare words)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+    // The arguments of a layer (ConvArgs | variant | sync_before) are read from shared memory -- as kernel parameters they
+    // would sit in the constant bank, a register copy spills -- and they are fetched ONE LAYER AHEAD into the other of two
+    // slots, so that no global-memory round trip sits between two layers.
+    constexpr int kArgWords = (int)(sizeof(ConvArgs) + 8) / 4;
+    uint8_t* argbuf = reinterpret_cast<uint8_t*>(bars) + 384 + 1024;
+    if (threadIdx.x < kArgWords)
+        reinterpret_cast<uint32_t*>(argbuf)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(&layers[0].args) + threadIdx.x);
+    __syncthreads();
+    int prev_nbars = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const ChainLayer* L = layers + l;
+        const ConvArgs* sp = reinterpret_cast<const ConvArgs*>(argbuf + (l & 1) * 288);
+        const int variant = reinterpret_cast<const int*>(sp + 1)[0], sync_before = reinterpret_cast<const int*>(sp + 1)[1];
+        if (l > 0) {
+            __syncthreads();                   // every role of this CTA has left layer l - 1: stores complete, fences done
+#ifdef D2T_CONV_TRACE
+            if (sp->trace && threadIdx.x == 0) sp->trace[(size_t)blockIdx.x * 64 + 6] = clock64();   // role 0 value 6: previous layer left
+#endif
+            if (sync_before && warp == 0) {
+                if (lane == 0) grid_barrier(gsync, (int)gridDim.x);
+                __syncwarp();
+            }
+#ifdef D2T_CONV_TRACE
+            if (sp->trace && threadIdx.x == 0) sp->trace[(size_t)blockIdx.x * 64 + 7] = clock64();   // role 0 value 7: barrier passed
+#endif
+            // (the body's barrier after its pipeline reset releases the other warps)
+        }
+        if (l + 1 < n_layers && threadIdx.x >= 128 && threadIdx.x < 128 + kArgWords)      // (epilogue warps: idle at a layer's start)
+            reinterpret_cast<uint32_t*>(argbuf + ((l + 1) & 1) * 288)[threadIdx.x - 128] =
+                __ldg(reinterpret_cast<const uint32_t*>(&L[1].args) + (threadIdx.x - 128));
+        if (warp == 3 && lane == 0 && l + 1 < n_layers) {       // the next layer's descriptors: fetched while this one runs
+            prefetch_tmap(&L[1].tmA);
+            prefetch_tmap(&L[1].tmB_hi);
+            prefetch_tmap(&L[1].tmB_lo);
+            prefetch_tmap(&L[1].tmO);
+            prefetch_tmap(&L[1].tmR);
+        }
+        const ConvArgs& p = *sp;
+        if (variant == 0)
+            conv_body<128, 16, false, false, false, false, false, false, true>(L->tmA, L->tmB_hi, L->tmB_lo, L->tmO, L->tmR, p, smem, bars, tmem_base, 0u, prev_nbars);
+        else if (variant == 1)
+            conv_body<128, 16, false, false, true, false, false, false, true>(L->tmA, L->tmB_hi, L->tmB_lo, L->tmO, L->tmR, p, smem, bars, tmem_base, 0u, prev_nbars);
+        else
+            conv_body<64, 16, false, false, false, false, false, false, true>(L->tmA, L->tmB_hi, L->tmB_lo, L->tmO, L->tmR, p, smem, bars, tmem_base, 0u, prev_nbars);
+        prev_nbars = 3 * (variant == 0 ? Cfg<128, 16, false, false>::STAGES : (variant == 1 ? Cfg<128, 16, false, true>::STAGES : Cfg<64, 16, false, false>::STAGES)) + 8;
+    }
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
 // ------------------------------------------------------------------ host side
@@ -1929,6 +2136,13 @@ extern "C" int d2t_conv_plan_set_weight_amax(d2t_conv_plan* pl, const float* ama
     return 1;
 }
 
+extern "C" int d2t_conv_plan_set_early_weights(d2t_conv_plan* pl, int on) {
+    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && !pl->corrb && !pl->pair,
+                "d2t_conv_plan_set_early_weights: needs a convolution plan (its B operand must be the packed weights)");
+    pl->args.early_b = on ? 1 : 0;
+    return 1;
+}
+
 extern "C" size_t d2t_conv_scratch_bytes(void) {
     return (size_t)sm_count() * kBlockM * 128 * sizeof(float) + (size_t)sm_count() * sizeof(int);
 }
@@ -2013,4 +2227,103 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);
     return pl->BN == 64 ? D2T_RUN(64, 1) : D2T_RUN(128, 1);
 #undef D2T_RUN
+}
+
+// ------------------------------------------------------------------ layer chains (conv_chain)
+struct d2t_conv_chain {
+    ChainLayer* dev;
+    int* gsync;
+    int n;
+    int private_scratch;
+};
+
+extern "C" int d2t_conv_plan_chainable(const d2t_conv_plan* pl) {
+    return pl && pl->passes == 16 && !pl->corr && !pl->pair && !pl->wgrad && !pl->corrb && !pl->args.mask && !pl->args.stem &&
+           !pl->args.done_prev && !pl->args.done_self && pl->args.amax_in && (pl->BN == 128 || (pl->BN == 64 && !pl->epi2)) ? 1 : 0;
+}
+
+extern "C" size_t d2t_conv_chain_bytes(int n_layers) {
+    return 256 + (size_t)(n_layers > 0 ? n_layers : 0) * sizeof(ChainLayer);
+}
+
+// plans[i] runs as layer i.  sync_before[i] != 0: layer i reads (input, residual) what one of the layers since the last such
+// mark writes -- the CTAs meet at a grid-wide barrier first.  dev_buf: d2t_conv_chain_bytes(n) bytes of device memory,
+// 256-byte aligned, owned by the caller for the life of the chain.  The plans' tensor maps and arguments are COPIED: build
+// the chain after every d2t_conv_plan_set_* call.  All plans must use the same stream-K scratch.
+extern "C" d2t_conv_chain* d2t_conv_chain_create(const d2t_conv_plan* const* plans, const int* sync_before, int n, void* dev_buf,
+                                                 size_t bytes) {
+    if (!plans || n <= 0 || !dev_buf || ((uintptr_t)dev_buf & 255) != 0 || bytes < d2t_conv_chain_bytes(n)) {
+        set_error("d2t_conv_chain_create: bad arguments");
+        return nullptr;
+    }
+    ChainLayer* host = nullptr;
+    if (posix_memalign(reinterpret_cast<void**>(&host), 128, sizeof(ChainLayer) * (size_t)n) != 0) {
+        set_error("d2t_conv_chain_create: out of memory");
+        return nullptr;
+    }
+    for (int i = 0; i < n; ++i) {
+        const d2t_conv_plan* pl = plans[i];
+        if (!d2t_conv_plan_chainable(pl) || pl->args.sk_scratch != plans[0]->args.sk_scratch) {
+            set_error("d2t_conv_chain_create: layer %d is not a plain 3xFP16 convolution plan on the chain's scratch", i);
+            free(host);
+            return nullptr;
+        }
+        ChainLayer& L = host[i];
+        memset(&L, 0, sizeof(L));
+        L.tmA = pl->tmA; L.tmB_hi = pl->tmB_hi; L.tmB_lo = pl->tmB_lo; L.tmO = pl->tmO; L.tmR = pl->tmR;
+        L.args = pl->args;
+        L.args.sk_epoch = i + 1;            // unique per layer: un-barriered neighbours must not mistake each other's partials
+        L.variant = pl->BN == 64 ? 2 : (pl->epi2 ? 1 : 0);
+        L.sync_before = sync_before ? (sync_before[i] != 0) : 1;
+        if (getenv("D2T_CHAIN_NOSYNC") && atoi(getenv("D2T_CHAIN_NOSYNC")) == 1) L.sync_before = 0;    // timing experiments only (wrong results)
+    }
+    d2t_conv_chain* ch = new (std::nothrow) d2t_conv_chain();
+    if (!ch) {
+        free(host);
+        set_error("d2t_conv_chain_create: out of memory");
+        return nullptr;
+    }
+    ch->gsync = reinterpret_cast<int*>(dev_buf);
+    ch->dev = reinterpret_cast<ChainLayer*>(reinterpret_cast<char*>(dev_buf) + 256);
+    ch->n = n;
+    ch->private_scratch = plans[0]->private_scratch;
+    cudaError_t e = cudaMemset(dev_buf, 0, 256);
+    if (e == cudaSuccess) e = cudaMemcpy(ch->dev, host, sizeof(ChainLayer) * (size_t)n, cudaMemcpyHostToDevice);
+    free(host);
+    if (e != cudaSuccess) {
+        set_error("d2t_conv_chain_create: %s", cudaGetErrorString(e));
+        delete ch;
+        return nullptr;
+    }
+    return ch;
+}
+
+extern "C" int d2t_conv_chain_run(const d2t_conv_chain* ch, cudaStream_t stream) {
+    D2T_REQUIRE(ch, "d2t_conv_chain_run: null chain");
+    static SmemAttrOnce once;
+    if (!once.ensure(conv_chain, kChainSmem, "conv chain smem attr")) return 0;
+    std::unique_lock<std::mutex> lock(g_sk_mu, std::defer_lock);
+    if (!ch->private_scratch) {                       // default scratch: launches stay stream-ordered (see SkScratch)
+        lock.lock();
+        if (!sk_serialize(stream)) return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count());                   // one CTA per SM: the grid-wide barrier needs every CTA resident
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = kChainSmem;
+    cfg.stream = stream;
+    // D2T_CHAIN_COOP=0 (experiments): plain launch -- co-residency then rests on nothing else occupying the SMs
+    static const bool coop = [] { const char* e = getenv("D2T_CHAIN_COOP"); return !(e && e[0] == '0'); }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = coop ? 1 : 0;
+    const ChainLayer* layers = ch->dev;
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_chain, layers, ch->n, ch->gsync), "conv_chain launch");
+    return 1;
+}
+
+extern "C" void d2t_conv_chain_destroy(d2t_conv_chain* ch) {
+    delete ch;
 }

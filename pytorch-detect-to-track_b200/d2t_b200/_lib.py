@@ -64,6 +64,12 @@ _SIGS = {
     "d2t_conv_scratch_bytes": (_sz, []),
     "d2t_conv_plan_set_scratch": (_i, [_p, _p, _sz]),
     "d2t_conv_plan_set_done": (_i, [_p, _p, _p, _p]),
+    "d2t_conv_plan_set_early_weights": (_i, [_p, _i]),
+    "d2t_conv_plan_chainable": (_i, [_p]),
+    "d2t_conv_chain_bytes": (_sz, [_i]),
+    "d2t_conv_chain_create": (_p, [_p, _p, _i, _p, _sz]),
+    "d2t_conv_chain_run": (_i, [_p, _p]),
+    "d2t_conv_chain_destroy": (None, [_p]),
     "d2t_conv_pack_weights_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_corr_plan_create": (_p, [_i] * 10 + [_p] * 3 + [_i, _i, _p]),
     "d2t_conv_plan_info": (_i, [_p, C.POINTER(_i)]),

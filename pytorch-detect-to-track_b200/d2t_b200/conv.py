@@ -147,6 +147,11 @@ class _Planned(object):
         check(lib().d2t_conv_plan_set_scratch(self.plan, scratch.data_ptr(), scratch.numel()), "d2t_conv_plan_set_scratch")
         self._scratch = scratch
 
+    def set_early_weights(self, on=True):
+        """fetch the first weight tiles before the launch waits for its predecessor (d2t_conv_plan_set_early_weights):
+        for layers whose packed weights are not rewritten by the launch immediately before them"""
+        check(lib().d2t_conv_plan_set_early_weights(self.plan, int(on)), "d2t_conv_plan_set_early_weights")
+
     def set_done(self, prev, self_counter):
         """completion hand-shake with the layer launched immediately before this one on the same stream (csrc/conv.cu,
         d2t_conv_plan_set_done): `self_counter` is a one-element int32 CUDA tensor this layer's CTAs count into, `prev` the
@@ -253,6 +258,78 @@ class ConvLayer(_Planned):
     def run(self, stream=None):
         _Planned.run(self, stream)
         return self.out if self.out is not None else self.out_nchw
+
+
+class ConvChain(object):
+    """Consecutive ConvLayers run by ONE persistent launch (csrc/conv.cu: conv_chain; include/d2t_b200.h "Layer chains").
+    The layers' plans are copied at construction -- build the chain after every set_scratch / set_done / amax binding.
+    A grid-wide barrier separates a layer from the ones before it only where it reads (input or residual) a buffer that a
+    layer since the previous barrier writes; results are bit-identical to ``for l in layers: l.run()``."""
+
+    def __init__(self, layers):
+        assert len(layers) > 0 and all(ConvChain.chainable(l) for l in layers)
+        self.layers = list(layers)
+        n = len(layers)
+
+        def store(t):
+            return t.untyped_storage().data_ptr() if t is not None else None
+
+        written, sync = set(), []
+        for l in layers:
+            reads = {store(l.x.x), store(l.residual.x) if l.residual is not None else None} - {None}
+            need = bool(reads & written)
+            if need:
+                written = set()
+            sync.append(int(need))
+            written |= {store(l.out.x) if l.out is not None else None, store(l.out_nchw)} - {None}
+        sync[0] = 0
+        self.sync_before = sync
+        dev = layers[0].x.x.device
+        self.buf = torch.zeros(lib().d2t_conv_chain_bytes(n) + 256, dtype=torch.uint8, device=dev)
+        off = (-self.buf.data_ptr()) % 256
+        plans = (C.c_void_p * n)(*[l.plan for l in layers])
+        syncs = (C.c_int * n)(*sync)
+        self.chain = lib().d2t_conv_chain_create(plans, syncs, n, self.buf.data_ptr() + off, self.buf.numel() - off)
+        if not self.chain:
+            raise D2TError("d2t_conv_chain_create failed: %s" % lib().d2t_last_error().decode())
+        self.flops = sum(l.flops for l in layers)
+
+    @staticmethod
+    def chainable(layer):
+        return isinstance(layer, ConvLayer) and layer.zero_amax is None and bool(lib().d2t_conv_plan_chainable(layer.plan))
+
+    def run(self, stream=None):
+        check(lib().d2t_conv_chain_run(self.chain, _stream() if stream is None else stream), "d2t_conv_chain_run")
+        ops._count(1)
+
+    def __del__(self):
+        try:
+            if self.chain:
+                lib().d2t_conv_chain_destroy(self.chain)
+                self.chain = None
+        except Exception:
+            pass
+
+
+def build_chains(layers, min_len=2):
+    """run list for `layers`: maximal runs of chainable ConvLayers become ConvChains, everything else stays as it is"""
+    out, run = [], []
+
+    def flush():
+        if len(run) >= min_len:
+            out.append(ConvChain(run))
+        else:
+            out.extend(run)
+        del run[:]
+
+    for l in layers:
+        if ConvChain.chainable(l):
+            run.append(l)
+        else:
+            flush()
+            out.append(l)
+    flush()
+    return out
 
 
 class DgradConv(ConvLayer):

@@ -36,7 +36,11 @@ def _fold_bn(bn):
 class D2TEngine(object):
     AMAX_SLOTS = 1024
 
-    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=True):
+    def __init__(self, net, pairs, height, width, passes=16, cfg_key="TEST", keep_features=False, private_scratch=True,
+                 chain=None):
+        """chain: run the trunk / head convolutions as persistent multi-layer launches (dc.ConvChain; 3xFP16 only).
+        Bit-identical, but MEASURED SLOWER than per-layer launches with programmatic dependent launch (DESIGN section 6:
+        112 against 98 us per layer3 bottleneck), so it is off unless asked for (chain=True or D2T_CONV_CHAIN=1)."""
         dev = next(net.parameters()).device
         self.amax = dc.AmaxArena(self.AMAX_SLOTS, dev)       # every activation tensor's running max |x|, zeroed once per forward
         with self.amax:
@@ -55,6 +59,14 @@ class D2TEngine(object):
             self.scratch = torch.zeros(lib().d2t_conv_scratch_bytes(), dtype=torch.uint8, device=dev)
             for layer in [self.stem, self.trk_layer] + self.layers + self.corr_layers:
                 layer.set_scratch(self.scratch)
+        if os.environ.get("D2T_CONV_EARLY_B", "1") != "0" and type(self) is D2TEngine:
+            for layer in self.layers + [self.trk_layer]:       # weights packed once at build time: nothing upstream writes them
+                layer.set_early_weights(True)
+        if chain is None:
+            chain = os.environ.get("D2T_CONV_CHAIN", "0") == "1"
+        # the launch list of forward(): with chains, maximal runs of plain 3xFP16 layers collapse into one launch each
+        self.run_list = dc.build_chains(self.layers) if (chain and passes == 16 and os.environ.get("D2T_CONV_DONE") != "1") \
+            else list(self.layers)
 
     def _build(self, net, pairs, height, width, passes, cfg_key, keep_features):
         from model.utils.config import cfg
@@ -173,8 +185,8 @@ class D2TEngine(object):
     def forward(self, im_data, im_info):
         """im_data [B, 2, 3, H, W], im_info [B, 2, 3] (CUDA fp32) -> the reference's 10-tuple (eval)."""
         info = self._begin(im_data, im_info)
-        for layer in self.layers:
-            layer.run()
+        for item in self.run_list:
+            item.run()
         return self._tail(im_data, info)
 
     def _begin(self, im_data, im_info):

@@ -320,3 +320,82 @@ def test_random_geometries_fp16_split_and_determinism():
         case = (N, Cin, H, W, Cout, k, stride, pad, dil, relu, use_res, mag)
         assert err < 1e-5, (case, err, layer.info)
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), case
+
+
+def test_conv_chain_bit_identical():
+    """ConvChain (one persistent launch over a list of layers, grid-wide barriers only between dependent layers) computes
+    bit for bit what the same plans compute launched one by one: a bottleneck with a downsample branch (independent
+    neighbours, EPI2 residual layer, BN = 64 and BN = 128 variants, stream-K splits), repeated launches included."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+
+    def w(o, i, k):
+        return torch.randn(o, i, k, k, device="cuda", generator=g) * (2.0 / (i * k * k)) ** 0.5
+
+    def bn(c):
+        return torch.rand(c, device="cuda", generator=g) + 0.5, torch.randn(c, device="cuda", generator=g) * 0.1
+
+    for (N, H, W, cin, mid, cout) in [(2, 38, 63, 256, 64, 256), (4, 38, 63, 1024, 256, 1024), (1, 75, 125, 128, 128, 512)]:
+        x = dc.ActTensor.from_nchw(torch.randn(N, cin, H, W, device="cuda", generator=g))
+
+        def build():
+            layers = []
+            layers.append(dc.ConvLayer(x, w(cout, cin, 1), *bn(cout), passes=16))          # downsample-style branch
+            res = layers[-1].out
+            layers.append(dc.ConvLayer(x, w(mid, cin, 1), *bn(mid), relu=True, passes=16))
+            layers.append(dc.ConvLayer(layers[-1].out, w(mid, mid, 3), *bn(mid), pad=2, dil=2, relu=True, passes=16))
+            layers.append(dc.ConvLayer(layers[-1].out, w(cout, mid, 1), *bn(cout), relu=True, residual=res, passes=16))
+            layers.append(dc.ConvLayer(layers[-1].out, w(mid, cout, 1), *bn(mid), relu=True, passes=16))
+            layers.append(dc.ConvLayer(layers[-1].out, w(24, mid, 1), None, torch.randn(24, device="cuda", generator=g),
+                                       passes=16, want_nhwc=False, want_nchw=True))
+            return layers
+
+        st = g.get_state()
+        a = build()
+        g.set_state(st)
+        b = build()
+        for l in a + b:                      # stand-alone layers zero their own amax; a chain leaves that to its owner
+            l.zero_amax = None
+        for l in a:
+            l.run()
+        chain = dc.ConvChain(b)
+        assert chain.sync_before == [0, 0, 1, 1, 1, 1], chain.sync_before
+        for rep in range(3):
+            for l in b:
+                if l.out is not None:
+                    l.out.x.fill_(-7.0)
+            chain.run()
+            torch.cuda.synchronize()
+            for la, lb in zip(a, b):
+                if la.out is not None:
+                    assert torch.equal(la.out.x, lb.out.x), (N, H, W, cin, rep)
+                    assert torch.equal(la.out.amax, lb.out.amax)
+                else:
+                    assert torch.equal(la.out_nchw, lb.out_nchw)
+
+
+def test_engine_chain_bit_identical():
+    """D2TEngine with its layers collapsed into persistent chain launches == the layer-by-layer engine, bit for bit,
+    eager and as a CUDA-graph replay."""
+    from model.faster_rcnn.resnet import resnet
+    from d2t_b200.engine import D2TEngine, GraphedEngine
+    torch.manual_seed(3)
+    net = resnet(tuple(range(31)), 50, class_agnostic=True).create_architecture().cuda().eval()
+    B, H, W = 2, 224, 320
+    gen = torch.Generator().manual_seed(1)
+    im_data = (torch.rand(B, 2, 3, H, W, generator=gen) * 256 - 128).cuda()
+    im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
+    plain = D2TEngine(net, B, H, W, chain=False)
+    chained = D2TEngine(net, B, H, W, chain=True)
+    assert len(chained.run_list) < len(plain.run_list) // 4
+    want = [t.clone() for t in plain(im_data, im_info)[:4]]
+    got = chained(im_data, im_info)[:4]
+    torch.cuda.synchronize()
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    assert torch.equal(plain.base_feat.x, chained.base_feat.x)
+    graphed = GraphedEngine(chained, B, H, W)
+    for _ in range(3):
+        out = graphed(im_data, im_info)[:4]
+        torch.cuda.synchronize()
+        for a, b in zip(want, out):
+            assert torch.equal(a, b)
