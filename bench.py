@@ -607,8 +607,11 @@ def train_measure(world, rank, steps, warmup):
             "conv_tflops_useful_bwd": (engine.dgrad_flops + engine.wgrad_flops) / bwd_ms / 1e9,
             "convs": "d2t_b200 tcgen05 3xFP16: forward, backward-data (DgradConv) and weight-gradient (WgradLayer); PSRoI, "
                      "correlation, NMS, proposal step: d2t_b200 kernels (forward and backward); losses / target layers / SGD: torch",
-            "launch": ("CUDA-graph replays: forward, one graph per gradient bucket of the backward pass, weight re-pack; heads / "
-                       "losses / SGD eager" if engine.g_fwd is not None else "eager launches"),
+            "launch": ("CUDA-graph replays: forward, heads (proposal step + target layers + PSRoI heads + losses + their autograd "
+                       "backward, no host round trip), one graph per gradient bucket of the backward pass, weight re-pack; SGD "
+                       "eager" if engine.g_heads is not None else
+                       ("CUDA-graph replays: forward, backward, weight re-pack; heads eager" if engine.g_fwd is not None
+                        else "eager launches")),
             "bn": "calibrated (trained-looking) BatchNorm statistics, frozen", "gpu_launches": ops.LAUNCHES - launches0}
 
 

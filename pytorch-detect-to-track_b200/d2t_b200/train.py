@@ -36,8 +36,8 @@ def _is_param(t):
 class D2TTrainEngine(D2TEngine):
     AMAX_SLOTS = 4096
 
-    def __init__(self, net, pairs, height, width, bucket_bytes=32 << 20, use_graphs=True):
-        self.use_graphs, self.g_fwd = use_graphs, None
+    def __init__(self, net, pairs, height, width, bucket_bytes=32 << 20, use_graphs=True, graph_heads=True):
+        self.use_graphs, self.g_fwd, self.g_heads, self.graph_heads = use_graphs, None, None, graph_heads
         self._widx, self._blocks, self._meta = {}, [], {}
         dev = next(net.parameters()).device
         self.w_amax = torch.zeros(512, device=dev)          # max |w| per distinct conv weight (slot = _widx[id(w)])
@@ -350,16 +350,49 @@ class D2TTrainEngine(D2TEngine):
             self._refresh_weights()
         self._refresh_launches = ops.LAUNCHES - count
 
+    def _heads(self, info, gt_boxes, num_boxes):
+        """proposal step, target layers, PSRoI heads and the five losses on autograd LEAVES of the five convolution outputs
+        they consume, then d(loss)/d(leaves) (trainval_net.py:367-368).  No device->host round trip anywhere in here, so
+        the whole thing -- forward and autograd backward -- replays as one CUDA graph."""
+        from model.rpn.proposal_target_layer_cascade import train_heads
+        leaves = [t.detach().requires_grad_() for t in (self.cls_map, self.bbox_map, self.rpn_score, self.rpn_delta,
+                                                        self.trk_layer.out_nchw)]
+        cls_map, bbox_map, score, delta, trk = leaves
+        out = train_heads(self.net, self.B, None, None, None, None, cls_map, bbox_map, info, gt_boxes, num_boxes,
+                          rpn_maps=(score, delta), trk_map=trk)
+        loss = out[4].mean() + out[5].mean() + out[6].mean() + out[7].mean() + out[9].mean()   # trainval_net.py:367-368
+        grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+        grads = [gr if gr is not None else torch.zeros_like(leaf) for gr, leaf in zip(grads, leaves)]
+        return out, loss, grads
+
+    def _capture_heads(self, gt_boxes, num_boxes):
+        """the heads as a CUDA graph of their own (private memory pool: it is captured after, but replayed between, the
+        forward and backward graphs)"""
+        self.gt_static, self.nb_static = gt_boxes.clone(), num_boxes.clone()
+        torch.cuda.synchronize()
+        count = ops.LAUNCHES
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out, loss, grads = self._heads(self.info_graph, self.gt_static, self.nb_static)
+            with torch.no_grad():
+                for dst, gr in zip(self.grads_static, grads):
+                    dst.copy_(gr)
+        self._heads_static = (tuple(t.detach() if torch.is_tensor(t) else t for t in out), loss.detach())
+        self._heads_launches = ops.LAUNCHES - count
+        self.g_heads = g
+
     def forward_backward(self, im_data, im_info, gt_boxes, num_boxes):
         """forward (training mode) + losses + backward; fills param.grad (mean over ranks when torch.distributed is
-        initialised).  Returns (the reference's 10-tuple, total loss)."""
-        from model.rpn.proposal_target_layer_cascade import train_heads
+        initialised).  Returns (the reference's 10-tuple, total loss); with CUDA graphs (the default, from the third call
+        on) these are the graphs' static output tensors, overwritten by the next call."""
         net, B = self.net, self.B
         assert net.training, "call net.train() first (the RPN picks its TRAIN configuration from it)"
         self._calls = getattr(self, "_calls", 0) + 1
         if self.use_graphs and self.g_fwd is None and self._calls > 2:       # (two eager steps first: every kernel variant
             with torch.no_grad():                                            # has been launched once before the capture)
                 self._capture(im_data, im_info)
+            if self.graph_heads:
+                self._capture_heads(gt_boxes, num_boxes)
         graphed = self.g_fwd is not None
         with torch.no_grad():
             if graphed:
@@ -370,14 +403,18 @@ class D2TTrainEngine(D2TEngine):
                 info = self.info_graph
             else:
                 info = self._engine_forward(im_data, im_info)
-        leaves = [t.detach().requires_grad_() for t in (self.cls_map, self.bbox_map, self.rpn_score, self.rpn_delta,
-                                                        self.trk_layer.out_nchw)]
-        cls_map, bbox_map, score, delta, trk = leaves
-        out = train_heads(net, B, None, None, None, None, cls_map, bbox_map, info, gt_boxes, num_boxes,
-                          rpn_maps=(score, delta), trk_map=trk)
-        loss = out[4].mean() + out[5].mean() + out[6].mean() + out[7].mean() + out[9].mean()   # trainval_net.py:367-368
-        grads = torch.autograd.grad(loss, leaves, allow_unused=True)
-        self.leaf_grads = [gr if gr is not None else torch.zeros_like(leaf) for gr, leaf in zip(grads, leaves)]
+        if graphed and self.g_heads is not None:
+            with torch.no_grad():
+                self.gt_static.copy_(gt_boxes, non_blocking=True)
+                self.nb_static.copy_(num_boxes, non_blocking=True)
+            self.g_heads.replay()                                            # (fills grads_static)
+            ops._count(self._heads_launches)
+            out, loss = self._heads_static
+            self.leaf_grads = self.grads_static
+            with torch.no_grad():
+                self._run_backward()
+            return out, loss
+        out, loss, self.leaf_grads = self._heads(info, gt_boxes, num_boxes)
         with torch.no_grad():
             if graphed:
                 for dst, gr in zip(self.grads_static, self.leaf_grads):

@@ -1,18 +1,23 @@
 """Training-only RoI sampling (lib/model/rpn/proposal_target_layer_cascade.py:20-208) and the training branch
 of the D&T graph (lib/model/faster_rcnn/rfcn.py:113-160, 176-204), restated for Python 3 / current torch.
-Host-side training glue; sampling uses torch's generator on the device."""
+Host-side training glue; sampling uses torch's generator on the device; no device->host round trip."""
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from model.utils.config import cfg
-from model.utils.net_utils import _smooth_l1_loss
+from model.utils.net_utils import _smooth_l1_loss, device_const
 from .bbox_transform import bbox_overlaps_batch, bbox_transform_batch
 
 
 class _ProposalTargetLayer(nn.Module):
-    """Assign proposals to ground truth: labels + (normalised) regression targets for 128 sampled RoIs / image."""
+    """Assign proposals to ground truth: labels + (normalised) regression targets for 128 sampled RoIs / image.
+    Static shapes, no device->host round trip (the head of the training step replays as a CUDA graph): the reference's
+    per-image ``nonzero`` / ``randperm`` / python branches (proposal_target_layer_cascade.py:129-187) become batched sorts
+    -- foreground: a random order of the candidates (random keys, non-candidates last), the first min(32, n_fg) taken;
+    background (and foreground when there is no background): drawn WITH replacement from the compacted candidate list,
+    floor(u * n) like the reference."""
 
     def __init__(self, nclasses):
         super(_ProposalTargetLayer, self).__init__()
@@ -21,46 +26,43 @@ class _ProposalTargetLayer(nn.Module):
 
     @torch.no_grad()
     def forward(self, all_rois, gt_boxes, num_boxes):
-        means = gt_boxes.new_tensor(cfg.TRAIN.BBOX_NORMALIZE_MEANS)
-        stds = gt_boxes.new_tensor(cfg.TRAIN.BBOX_NORMALIZE_STDS)
-        inside = gt_boxes.new_tensor(cfg.TRAIN.BBOX_INSIDE_WEIGHTS)
+        means = device_const(cfg.TRAIN.BBOX_NORMALIZE_MEANS, gt_boxes)
+        stds = device_const(cfg.TRAIN.BBOX_NORMALIZE_STDS, gt_boxes)
+        inside = device_const(cfg.TRAIN.BBOX_INSIDE_WEIGHTS, gt_boxes)
         gt_append = gt_boxes.new_zeros(gt_boxes.size(0), gt_boxes.size(1), 5)
         gt_append[:, :, 1:5] = gt_boxes[:, :, :4]
         all_rois = torch.cat([all_rois, gt_append], 1)                      # ground truth joins the candidates
-        rois_per_image = int(cfg.TRAIN.BATCH_SIZE)
-        fg_per_image = max(1, int(np.round(cfg.TRAIN.FG_FRACTION * rois_per_image)))
+        R = int(cfg.TRAIN.BATCH_SIZE)
+        fg_per_image = max(1, int(np.round(cfg.TRAIN.FG_FRACTION * R)))
         overlaps = bbox_overlaps_batch(all_rois, gt_boxes[:, :, :5])
         max_ov, assign = overlaps.max(2)
-        B = overlaps.size(0)
+        B, N = max_ov.shape
+        dev = max_ov.device
         labels = torch.gather(gt_boxes[:, :, 4], 1, assign)
-        labels_b = labels.new_zeros(B, rois_per_image)
-        rois_b = all_rois.new_zeros(B, rois_per_image, 5)
-        gt_b = all_rois.new_zeros(B, rois_per_image, gt_boxes.size(2))
-        for i in range(B):
-            fg = torch.nonzero(max_ov[i] >= cfg.TRAIN.FG_THRESH).view(-1)
-            bg = torch.nonzero((max_ov[i] < cfg.TRAIN.BG_THRESH_HI) & (max_ov[i] >= cfg.TRAIN.BG_THRESH_LO)).view(-1)
-            nf, nb = fg.numel(), bg.numel()
-            rnd = lambda n, m: torch.floor(torch.rand(n, device=fg.device, generator=self.generator) * m).long()
-            if nf > 0 and nb > 0:
-                n_fg = min(fg_per_image, nf)
-                fg = fg[torch.randperm(nf, device=fg.device, generator=self.generator)[:n_fg]]
-                bg = bg[rnd(rois_per_image - n_fg, nb)]
-            elif nf > 0:
-                fg, bg, n_fg = fg[rnd(rois_per_image, nf)], bg[:0], rois_per_image
-            elif nb > 0:
-                fg, bg, n_fg = fg[:0], bg[rnd(rois_per_image, nb)], 0
-            else:
-                raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
-            keep = torch.cat([fg, bg], 0)
-            labels_b[i] = labels[i][keep]
-            labels_b[i][n_fg:] = 0                                          # background label
-            rois_b[i] = all_rois[i][keep]
-            rois_b[i, :, 0] = i
-            gt_b[i] = gt_boxes[i][assign[i][keep]]
+        fg_mask = max_ov >= cfg.TRAIN.FG_THRESH
+        bg_mask = (max_ov < cfg.TRAIN.BG_THRESH_HI) & (max_ov >= cfg.TRAIN.BG_THRESH_LO)
+        nf, nb = fg_mask.sum(1), bg_mask.sum(1)                             # [B]
+        # (the reference raises when an image has neither; that cannot be tested without a host round trip: such a row
+        # falls through to index 0 with background labels)
+        keys = torch.rand(B, N, device=dev, generator=self.generator)
+        fg_order = torch.sort(torch.where(fg_mask, keys, torch.full_like(keys, 2.0)), dim=1)[1]      # random order, candidates first
+        fg_list = torch.sort((~fg_mask).to(torch.uint8), dim=1, stable=True)[1]                      # index order, candidates first
+        bg_list = torch.sort((~bg_mask).to(torch.uint8), dim=1, stable=True)[1]
+        u = torch.rand(B, R, device=dev, generator=self.generator)
+        pick = lambda lst, n: lst.gather(1, torch.floor(u * n.view(B, 1).float()).long().clamp(min=0, max=N - 1))
+        has_f, has_b = (nf > 0).view(B, 1), (nb > 0).view(B, 1)
+        n_fg = torch.where(has_b.view(B), nf.clamp(max=fg_per_image), torch.full_like(nf, R)) * has_f.view(B).long()
+        fg_rows = torch.where(has_b, fg_order[:, :R], pick(fg_list, nf))    # without replacement / (no background) with
+        keep = torch.where(torch.arange(R, device=dev).view(1, R) < n_fg.view(B, 1), fg_rows, pick(bg_list, nb))
+        is_fg_row = torch.arange(R, device=dev).view(1, R) < n_fg.view(B, 1)
+        labels_b = labels.gather(1, keep) * is_fg_row.to(labels.dtype)      # background label 0
+        rois_b = all_rois.gather(1, keep.unsqueeze(2).expand(B, R, 5)).clone()
+        rois_b[:, :, 0] = torch.arange(B, device=dev, dtype=rois_b.dtype).view(B, 1)
+        gt_b = gt_boxes.gather(1, assign.gather(1, keep).unsqueeze(2).expand(B, R, gt_boxes.size(2)))
         targets = (bbox_transform_batch(rois_b[:, :, 1:5], gt_b[:, :, :4]) - means) / stds
-        fg_mask = (labels_b > 0).unsqueeze(2).float()
-        bbox_targets = targets * fg_mask
-        inside_w = inside.view(1, 1, 4) * fg_mask
+        fg_m = (labels_b > 0).unsqueeze(2).float()
+        bbox_targets = targets * fg_m
+        inside_w = inside.view(1, 1, 4) * fg_m
         outside_w = (inside_w > 0).float()
         return rois_b, labels_b, bbox_targets, inside_w, outside_w
 

@@ -13,3 +13,16 @@ def _smooth_l1_loss(bbox_pred, bbox_targets, bbox_inside_weights, bbox_outside_w
     for i in sorted(dim, reverse=True):
         loss = loss.sum(i)
     return loss.mean()
+
+
+_CONST_CACHE = {}
+
+
+def device_const(values, like):
+    """a small constant tensor on `like`'s device / dtype, uploaded once (a host->device copy per call would be a
+    synchronising operation inside the training step -- and is illegal while a CUDA graph is being captured)"""
+    key = (tuple(float(v) for v in values), like.device, like.dtype)
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = _CONST_CACHE[key] = torch.tensor(list(key[0]), device=like.device, dtype=like.dtype)
+    return t

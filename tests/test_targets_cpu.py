@@ -85,3 +85,39 @@ def test_proposal_target_layer_invariants(gold):
         assert torch.allclose(targets[b][fg], want[fg], rtol=1e-5, atol=1e-6)
         assert float(targets[b][~fg].abs().max()) == 0.0
     assert torch.equal(ow, (iw > 0).float())
+
+
+def test_anchor_target_layer_quota_with_many_positives():
+    """More than 128 positives per image: the positives are cut to 128 and the negatives' quota is RPN_BATCHSIZE minus the
+    number of positives BEFORE that cut (reference anchor_target_layer.py:119-137: `num_bg = RPN_BATCHSIZE - sum_fg[i]`),
+    i.e. fewer than 128 negatives -- none at all once there were 256 positives."""
+    H, W = 19, 32
+    rng = np.random.RandomState(3)
+
+    def boxes(n, size):
+        x = rng.uniform(0, 500 - size, n)
+        y = rng.uniform(0, 300 - size, n)
+        return np.stack([x, y, x + size, y + size, np.ones(n)], 1).astype(np.float32)
+
+    gt = np.zeros((2, 200, 5), np.float32)
+    gt[0, :12] = boxes(12, 128)           # a handful of anchor-sized boxes: a few dozen positives
+    gt[1, :200] = boxes(200, 128)         # crowded image: several hundred positives
+    layer = _AnchorTargetLayer(16, cfg.ANCHOR_SCALES, cfg.ANCHOR_RATIOS)
+    layer.generator = torch.Generator().manual_seed(0)
+    g = torch.from_numpy(gt)
+    info = torch.tensor([[300., 500., 1.], [300., 500., 1.]])
+    lab = layer((torch.zeros(2, 24, H, W), g, info, None))[0].view(2, -1)
+    # the positives / negatives before subsampling: the same rules with an unlimited quota
+    saved = cfg.TRAIN.RPN_BATCHSIZE
+    try:
+        cfg.TRAIN.RPN_BATCHSIZE = 10 ** 6                      # no quota: every positive / negative survives
+        full = layer((torch.zeros(2, 24, H, W), g, info, None))[0].view(2, -1)
+    finally:
+        cfg.TRAIN.RPN_BATCHSIZE = saved
+    for b in range(2):
+        n_pos_before = int((full[b] == 1).sum())
+        n_pos, n_neg = int((lab[b] == 1).sum()), int((lab[b] == 0).sum())
+        assert n_pos == min(128, n_pos_before)
+        assert n_neg == max(0, 256 - n_pos_before), (n_pos_before, n_neg)
+        assert bool(((lab[b] == 1) <= (full[b] == 1)).all()) and bool(((lab[b] == 0) <= (full[b] == 0)).all())   # subsets
+    assert int((full[1] == 1).sum()) > 128                      # the fixture does exercise the cut

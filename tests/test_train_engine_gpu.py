@@ -129,7 +129,7 @@ def test_train_engine_learns():
     from d2t_b200.train import D2TTrainEngine
     B, H, W = 2, 224, 320
     net, im_data, im_info, gt, nb = _setup(50, B, H, W)
-    eng = D2TTrainEngine(net, B, H, W)
+    eng = D2TTrainEngine(net, B, H, W, graph_heads=False)     # (eager heads: torch.manual_seed below then fixes the samples)
     opt = torch.optim.SGD(eng.params, lr=1e-6, momentum=0.9)
     losses = []
     for it in range(4):
@@ -151,3 +151,45 @@ def test_train_engine_learns():
             layer.run()
     err = float((eng.base_feat.to_nchw() - base).abs().max() / base.abs().max())
     assert err < 1e-4, err
+
+
+def test_train_engine_graphed_heads():
+    """From the third step on the heads -- proposal step, target layers, PSRoI heads, five losses AND their autograd backward
+    down to the five convolution outputs -- replay as one CUDA graph (no device->host round trip in the target layers).
+    The graph's random samples differ from an eager run's by construction, so it is checked through what it returns: the
+    sampled RoIs / labels satisfy the samplers' invariants, the classification loss recomputed eagerly from the returned
+    samples equals the returned loss, and autograd's gradient of that recomputed loss w.r.t. the class map equals the
+    gradient the graph handed to the engine's backward pass."""
+    from d2t_b200.train import D2TTrainEngine
+    B, H, W = 2, 224, 320
+    net, im_data, im_info, gt, nb = _setup(50, B, H, W)
+    eng = D2TTrainEngine(net, B, H, W)
+    losses = []
+    for it in range(5):
+        out, loss = eng.forward_backward(im_data, im_info, gt, nb)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(loss)) and bool(torch.isfinite(eng.flat).all())
+        losses.append(float(loss))
+    assert eng.g_fwd is not None and eng.g_heads is not None
+    assert max(losses) < 1.5 * min(losses), losses                 # eager and replayed steps see the same problem
+    rois, labels = out[0], out[8]
+    assert rois.shape == (2, B, 128, 5) and labels.shape == (2, B, 128)
+    for leg in range(2):
+        for b in range(B):
+            assert bool((rois[leg, b, :, 0] == b).all())
+            fg = labels[leg, b] > 0
+            assert 1 <= int(fg.sum()) <= 32
+            assert bool(torch.isin(labels[leg, b][fg], gt[b, leg, :, 4]).all())
+    cls_map = eng.cls_map.detach().clone().requires_grad_()
+    total = 0
+    for leg in range(2):
+        flat = rois[leg].reshape(-1, 5).contiguous()
+        pooled = net.RFCN_psroi_cls_pool(cls_map[leg * B:(leg + 1) * B].contiguous(), flat)
+        score = net.RFCN_cls_score(pooled).view(flat.size(0), -1)
+        l = F.cross_entropy(score, labels[leg].reshape(-1).long())
+        assert abs(float(l) - float(out[6][leg])) <= 1e-5 * max(1.0, abs(float(l))), (float(l), float(out[6][leg]))
+        total = total + l
+    g, = torch.autograd.grad(total / 2, [cls_map])
+    got = eng.grads_static[0]
+    err = float((g - got).abs().max() / g.abs().max())
+    assert err < 1e-5, err
