@@ -135,6 +135,15 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
  * greedy NMS never looks ahead -- and runs the full pass only for the lists that did not reach max_keep inside it.
  * Returns the prefix length that would be used (0: no prefix pass). */
 int d2t_nms_prefix(int N, int max_keep);
+/* Lists capped at 0 < max_keep <= 2048 (the proposal step: proposal_layer.py:149-156 keeps the first post_nms_topN survivors)
+ * can take a mask-free kernel: one CTA per list keeps the survivors in shared memory and tests each candidate only against
+ * them (6000 x 300 IoUs instead of the 18 M of the mask's upper triangle, one launch, same keep-set bit for bit).  Faster
+ * when the cap is reached early (6.7 against 37 us per image on spread boxes), slower on heavily clustered lists where one
+ * SM meets a long kept list for every chunk -- so it is opt-in: d2t_nms_set_mode(1) or D2T_NMS_GREEDY=1; (0) forces the
+ * mask + sweep pair, (-1) restores the environment default.  d2t_nms_launch_count: kernels d2t_nms_batched launches for
+ * (N, max_keep) under the current mode. */
+int d2t_nms_set_mode(int greedy);
+int d2t_nms_launch_count(int N, int max_keep);
 /* ---- NMS: B independent, caller-sorted box lists in one launch pair ----
  * boxes   [B, N, box_dim] fp32 (x1,y1,x2,y2,...), n_valid [B] int32 or NULL (= N each)
  * keep    [B, keep_stride] int32, num_keep [B] int32; at most max_keep (<= keep_stride)

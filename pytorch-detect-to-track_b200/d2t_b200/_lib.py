@@ -46,6 +46,8 @@ _SIGS = {
     # ---- Part 2: stream-ordered surface
     "d2t_nms_workspace_bytes": (_sz, [_i, _i]),
     "d2t_nms_prefix": (_i, [_i, _i]),
+    "d2t_nms_set_mode": (_i, [_i]),
+    "d2t_nms_launch_count": (_i, [_i, _i]),
     "d2t_nms_batched": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _i, _p, _p, _sz, _p]),
     "d2t_psroi_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "d2t_psroi_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _f, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),

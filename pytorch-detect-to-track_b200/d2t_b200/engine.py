@@ -67,6 +67,13 @@ class D2TEngine(object):
         # the launch list of forward(): with chains, maximal runs of plain 3xFP16 layers collapse into one launch each
         self.run_list = dc.build_chains(self.layers) if (chain and passes == 16 and os.environ.get("D2T_CONV_DONE") != "1") \
             else list(self.layers)
+        # Two branches after the RPN head (D2T_ENGINE_FORK=0: one stream): the proposal step (decode, sort, NMS mask + sweep:
+        # ~0.25 ms of small kernels that leave the device almost empty) on the caller's stream, the remaining convolutions
+        # (R-FCN maps, correlations, tracking head) on a side stream; they join at the PSRoI heads.  Captured by
+        # GraphedEngine as parallel graph branches.
+        self.fork = (os.environ.get("D2T_ENGINE_FORK", "1") != "0" and self.run_list == list(self.layers)
+                     and os.environ.get("D2T_CONV_DONE") != "1")
+        self.side = torch.cuda.Stream(device=dev) if self.fork else None
 
     def _build(self, net, pairs, height, width, passes, cfg_key, keep_features):
         from model.utils.config import cfg
@@ -110,6 +117,15 @@ class D2TEngine(object):
         rn = base.RFCN_net
         self.base_feat = self._conv(x, rn.weight, None, rn.bias, 1, rn.padding[0], rn.dilation[0], relu=True).out
         bf = self.base_feat
+        # ---- RPN head (first: the proposal step that consumes it is a chain of small latency-bound kernels, which forward()
+        # overlaps with everything below)
+        rpn = net.RFCN_rpn
+        rc = self._conv(bf, rpn.RPN_Conv.weight, None, rpn.RPN_Conv.bias, 1, 1, 1, relu=True).out
+        self.rpn_score = self._conv(rc, rpn.RPN_cls_score.weight, None, rpn.RPN_cls_score.bias, want_nhwc=False,
+                                    want_nchw=True).out_nchw
+        self.rpn_delta = self._conv(rc, rpn.RPN_bbox_pred.weight, None, rpn.RPN_bbox_pred.bias, want_nhwc=False,
+                                    want_nchw=True).out_nchw
+        self.n_main_layers = len(self.layers)     # layers[:n_main_layers] feed the proposal step; the rest only the PSRoI heads
         # ---- R-FCN maps: NCHW for PSRoI; the loc map also feeds the tracking concat (NHWC slices)
         cn, bn_ = net.RFCN_cls_net, net.RFCN_bbox_net
         self.cls_map = self._conv(bf, cn.weight, None, cn.bias, want_nhwc=False, want_nchw=True).out_nchw
@@ -121,13 +137,6 @@ class D2TEngine(object):
         for leg in (0, 1):   # one plan per leg: NHWC into its channel slice of the concat buffer + NCHW for PSRoI
             self._conv(bf.batch_slice(leg * pairs, (leg + 1) * pairs), bn_.weight, None, bn_.bias, out=self.trk_in,
                        out_coffset=leg * n_loc, out_nchw=self.bbox_map[leg * pairs:(leg + 1) * pairs])
-        # ---- RPN head
-        rpn = net.RFCN_rpn
-        rc = self._conv(bf, rpn.RPN_Conv.weight, None, rpn.RPN_Conv.bias, 1, 1, 1, relu=True).out
-        self.rpn_score = self._conv(rc, rpn.RPN_cls_score.weight, None, rpn.RPN_cls_score.bias, want_nhwc=False,
-                                    want_nchw=True).out_nchw
-        self.rpn_delta = self._conv(rc, rpn.RPN_bbox_pred.weight, None, rpn.RPN_bbox_pred.bias, want_nhwc=False,
-                                    want_nchw=True).out_nchw
         self.n_trunk_layers = len(self.layers)
         # ---- tracking head conv (runs after the correlations)
         tn = net.corr_bbox_net
@@ -185,9 +194,18 @@ class D2TEngine(object):
     def forward(self, im_data, im_info):
         """im_data [B, 2, 3, H, W], im_info [B, 2, 3] (CUDA fp32) -> the reference's 10-tuple (eval)."""
         info = self._begin(im_data, im_info)
-        for item in self.run_list:
-            item.run()
-        return self._tail(im_data, info)
+        if not self.fork:
+            for item in self.run_list:
+                item.run()
+            return self._tail(im_data, info)
+        for layer in self.layers[:self.n_main_layers]:
+            layer.run()
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        h = self.side.cuda_stream
+        for layer in self.layers[self.n_main_layers:] + self.corr_layers + [self.trk_layer]:
+            layer.run(h)
+        return self._tail(im_data, info, joined=self.side)
 
     def _begin(self, im_data, im_info):
         """input re-layout, stem conv and max-pool; returns the per-frame im_info [2B, 3]"""
@@ -200,8 +218,10 @@ class D2TEngine(object):
         dc.maxpool3x3s2(self.stem.out, out=self.pool_out)
         return info
 
-    def _tail(self, im_data, info):
-        """everything after the trunk / head convs: proposal step, PSRoI heads, correlations, tracking head"""
+    def _tail(self, im_data, info, joined=None):
+        """everything after the trunk / head convs: proposal step, PSRoI heads, correlations, tracking head.
+        joined: the side stream on which forward() has already enqueued the R-FCN map convolutions, the correlations and
+        the tracking head; it is waited for before the first PSRoI head."""
         B, L, N = self.B, 2, self.N
         # ---- proposals for all 2B images
         A = self.anchors.size(0)
@@ -211,15 +231,18 @@ class D2TEngine(object):
                                  self.post_nms, self.nms_thresh)                        # [2B, R, 5]
         R = rois_all.size(1)
         flat = rois_all.view(-1, 5)
+        if joined is not None:
+            torch.cuda.current_stream().wait_stream(joined)
         # ---- detection heads: PSRoI pooling + 7x7 vote (+ softmax) fused (rfcn.py:133-140)
         cls_prob = ops.psroi_vote(self.cls_map, flat, 7, 7, 1.0 / 16.0, 7, self.n_classes, softmax=True).view(L, B, R, -1)
         bbox_pred = ops.psroi_vote(self.bbox_map, flat, 7, 7, 1.0 / 16.0, 7, 4 * self.n_reg).view(L, B, R, -1)
         rois = rois_all.view(L, B, R, 5).clone()
         rois[1, :, :, 0] -= B                                                           # per-leg image index
         # ---- tracking branch
-        for layer in self.corr_layers:
-            layer.run()
-        self.trk_layer.run()
+        if joined is None:
+            for layer in self.corr_layers:
+                layer.run()
+            self.trk_layer.run()
         tracking_pred = ops.psroi_vote(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
                                        4 * self.n_reg).view(B * R, -1)                  # rfcn.py:192-196
         zero = im_data.new_zeros(L, 1)

@@ -216,7 +216,7 @@ def nms_batched(dets, thresh, max_keep=0, n_valid=None):
         check(lib().d2t_nms_batched(dets.data_ptr(), n_valid.data_ptr() if n_valid is not None else None, B, N, dim,
                                     thresh, max_keep, keep.data_ptr(), stride, num.data_ptr(), ws.data_ptr(),
                                     ws.numel(), _stream()), "d2t_nms_batched")
-        _count(4 if lib().d2t_nms_prefix(N, max_keep) > 0 else 2)
+        _count(lib().d2t_nms_launch_count(N, max_keep))
     return keep, num
 
 

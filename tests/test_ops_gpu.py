@@ -259,12 +259,44 @@ def test_nms_batched_ragged_and_capped(oracle):
         np.testing.assert_array_equal(npy(keep[b, : len(want)]), want)
 
 
+@pytest.mark.parametrize("N,K,thresh", [(6000, 300, 0.7), (12000, 2000, 0.7), (6000, 300, 0.05), (700, 40, 0.3), (130, 2048, 0.7),
+                                        (6000, 64, 1.0), (6000, 300, 0.0)])
+def test_nms_capped_mask_free_kernel(oracle, N, K, thresh):
+    """capped lists (the proposal step) run on nms_greedy -- no N x N mask, one CTA per list, candidates tested against the
+    kept boxes only -- and must give the keep-sets of the oracle and of the mask + sweep pair, bit for bit: spread and
+    clustered boxes, ragged / empty lists, degenerate boxes, caps that are and are not reached."""
+    from d2t_b200._lib import lib
+    dets = np.stack([common.make_dets(N, seed=400), common.make_clustered_dets(N, seed=401), common.make_dets(N, seed=402),
+                     common.make_clustered_dets(N, seed=403), common.make_clustered_dets(N, seed=404)])
+    dets[2, 10:20, 2] = dets[2, 10:20, 0] - 5          # inverted boxes
+    dets[2, 30:40, :4] = dets[2, 30, :4]               # exact duplicates
+    dets[2, 50:60, :4] = 0.0                           # zero boxes
+    dets[2, 60:64, :4] = np.array([5, 5, 4, 4])        # 0/0 IoU = NaN, never suppresses
+    n_valid = np.array([N, N, min(N, 1000), N - 37, 0], np.int32)
+    outs = []
+    try:
+        for mode in (1, 0):
+            lib().d2t_nms_set_mode(mode)
+            assert lib().d2t_nms_launch_count(N, K) == (1 if mode else 2)
+            keep, num = ops.nms_batched(cu(dets), thresh, max_keep=K, n_valid=cu(n_valid))
+            outs.append((npy(keep), npy(num)))
+    finally:
+        lib().d2t_nms_set_mode(-1)
+    for b in range(5):
+        want = oracle.nms(dets[b, : n_valid[b]], thresh)[:K]
+        for keep, num in outs:
+            assert num[b] == len(want), (b, num[b], len(want))
+            np.testing.assert_array_equal(keep[b, : num[b]], want)
+
+
 def test_nms_prefix_pass_and_fallback(oracle, monkeypatch):
     """max_keep > 0 on long lists with D2T_NMS_PREFIX=1: d2t_nms_batched first decides a prefix (4 * max_keep boxes); lists
     that reach max_keep inside it are final, the others take the full pass.  One batch mixes short / empty / long lists."""
     from d2t_b200._lib import lib
     assert lib().d2t_nms_prefix(6000, 300) == 0           # opt-in
     monkeypatch.setenv("D2T_NMS_PREFIX", "1")
+    lib().d2t_nms_set_mode(0)                             # (the mask + sweep pair: capped lists default to the mask-free kernel)
+    monkeypatch.setattr(ops, "_nms_mode_restore", lib().d2t_nms_set_mode, raising=False)
     B, N, K = 5, 6000, 300
     assert lib().d2t_nms_prefix(N, K) == 1216 and lib().d2t_nms_prefix(N, 0) == 0 and lib().d2t_nms_prefix(2000, K) == 0
     dets = np.stack([common.make_dets(N, seed=300), common.make_clustered_dets(N, seed=301), common.make_dets(N, seed=302),
@@ -286,6 +318,7 @@ def test_nms_prefix_pass_and_fallback(oracle, monkeypatch):
     want = oracle.nms(dets[1], 0.05)[:K]
     assert int(num[0]) == len(want) and (len(want) < K or want[-1] >= 1216)
     np.testing.assert_array_equal(npy(keep)[0, : len(want)], want)
+    lib().d2t_nms_set_mode(-1)
 
 
 def test_nms_degenerate_boxes(oracle):
