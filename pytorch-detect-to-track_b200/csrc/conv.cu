@@ -192,7 +192,7 @@ struct Cfg {
     static constexpr int CVT_THREADS = F16 ? 128 : 64;
     // 3xFP16: A = two fp32 [128 x 32] sub-tiles as loaded, rewritten in place as fp16 [128 x 64] hi | lo
     static constexpr int A_BYTES = kBlockM * KBLK * 4;                // 16 KB (32 KB)
-    static constexpr int B_BYTES = F16 ? BN * KBLK * 2 : (PAIR ? BN / 2 : BN) * KBLK * 4;   // (a CTA pair holds half of B each)
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KBLK * (F16 ? 2 : 4);   // (a CTA pair holds half of B each)
     static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // TF32: hi (+ lo) copies of each operand
     // smem per stage -- TF32: A x | A lo | B x | B lo;  FP16: A (hi | lo) | B hi | B lo
     static constexpr int STAGE_BYTES = F16 ? A_BYTES + 2 * B_BYTES : NOPER * (A_BYTES + B_BYTES);
@@ -262,7 +262,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -310,6 +310,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same across a CTA pair: M = 256 (each CTA's tensor memory holds its own 128 rows of A and of D), each CTA's shared
+// memory holds N/2 rows of B
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -444,7 +454,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
-    static_assert(!(F16 && PAIR), "3xFP16 is a single-CTA mode");
+    static_assert(!(F16 && PAIR) || (BN == 128 && !CORR && !WGRAD && !CORRB && !MASK), "3xFP16 pairs: plain forward convolutions");
     static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
     static_assert(!CORRB || (F16 && !EPI2 && !WGRAD && BN == 128), "the correlation-backward mode is a plain 3xFP16 variant");
     static_assert(!CHAIN || (F16 && !CORR && !PAIR && !WGRAD && !CORRB), "the chain kernel runs 3xFP16 convolutions");
@@ -610,7 +620,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                     if (PAIR) {
                         // each CTA stages its own A tile and its half of the weight tile (completion: own barrier)
                         if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
-                        if (is_a) tma_load_4d(dst, map, fbar, kc * kBlockK, iw0 + s * dil, ih0 + r * dil, img);
+                        if (is_a) tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * dil, ih0 + r * dil, img);
                         else tma_load_2d(dst, map, fbar, k * kBlockK, n0 + (int)crank * (BN / 2));
                     } else {
                         if (lane == 0) mbar_expect_tx(fbar, TMA_BYTES);
@@ -650,7 +660,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
         // cross terms (2^-11 of the result, so their truncation is negligible) accumulate over the
         // whole tile in their own TMEM buffer.  TMEM: main[2] | cross[2], BN columns each.
         if (lane == 0 && crank == 0) {
-            constexpr uint32_t idesc = PAIR ? make_idesc<BN, 256>() : (F16 ? make_idesc_f16<BN>() : make_idesc<BN>());
+            constexpr uint32_t idesc = F16 ? (PAIR ? make_idesc_f16<BN, 256>() : make_idesc_f16<BN>())
+                                           : (PAIR ? make_idesc<BN, 256>() : make_idesc<BN>());
             const uint64_t desc0 = make_smem_desc(smem_u32(smem));     // stage s / operand o: + (byte offset >> 4)
             int stage = 0, cbuf = 0, local = 0, issued = 0;
             uint32_t phase = 0, cphase = 0;
@@ -691,9 +702,15 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                                 // A from tensor memory (8 columns = 16 fp16 per K step); all three products of the K step
                                 // go to the chunk accumulator (48 accumulation steps per 256-channel chunk)
                                 const uint32_t at_hi = tmem_base + C::A_TMEM_BASE + stage * C::A_TMEM_COLS + kk * 8;
-                                umma_f16_ts(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
-                                umma_f16_ts(d_main, at_hi, b_lo + o, idesc, 1);
-                                umma_f16_ts(d_main, at_hi + 32, b_hi + o, idesc, 1);
+                                if (PAIR) {
+                                    umma_f16_ts_pair(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
+                                    umma_f16_ts_pair(d_main, at_hi, b_lo + o, idesc, 1);
+                                    umma_f16_ts_pair(d_main, at_hi + 32, b_hi + o, idesc, 1);
+                                } else {
+                                    umma_f16_ts(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
+                                    umma_f16_ts(d_main, at_hi, b_lo + o, idesc, 1);
+                                    umma_f16_ts(d_main, at_hi + 32, b_hi + o, idesc, 1);
+                                }
                             } else if (PAIR) {
                                 umma_tf32_pair(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                                 umma_tf32_pair(d_cross, a_hi + o, b_lo + o, idesc, 1);
@@ -843,7 +860,18 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
-                    mbar_arrive(&cvt[stage]);
+                    if (PAIR) {
+                        // the leader issues the pair's MMAs.  ONE arrival per CTA (128 remote arrivals per K block measured
+                        // ~40 % slower than single-CTA mode): the four converter warps meet at a named barrier first
+                        asm volatile("bar.sync 4, 128;" ::: "memory");
+                        if ((warp & 3) == 2 && warp < kEpiWarp0 && lane == 0) {
+                            tc_fence_after();
+                            tc_fence_before();
+                            mbar_arrive_remote(map_to_cta(smem_u32(&cvt[stage]), 0));
+                        }
+                    } else {
+                        mbar_arrive(&cvt[stage]);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -1329,7 +1357,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
-            mbar_init(&cvt[i], CS * kCvtThreads);          // (leader's copy collects both CTAs' converters)
+            mbar_init(&cvt[i], (PAIR && C::F16) ? 2 : CS * kCvtThreads);   // (leader's copy collects both CTAs' converters; 3xFP16 pairs: one elected arrival per CTA)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -1655,7 +1683,10 @@ struct d2t_conv_plan {
     alignas(64) CUtensorMap tmB_lo;
     alignas(64) CUtensorMap tmO;
     alignas(64) CUtensorMap tmR;
+    alignas(64) CUtensorMap tmBh_hi;   // pair mode: boxes of BN / 2 weight rows (each CTA of a pair stages half of the tile)
+    alignas(64) CUtensorMap tmBh_lo;
     ConvArgs args;
+    int grid_single;                   // grid of the single-CTA kernel (a pair plan falls back to it: d2t_conv_plan_set_mask)
     int BN, passes, grid, corr;
     int epi2;                  // 3xFP16, BN = 128: the full-tile output staging / TMA residual variant
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
@@ -1672,7 +1703,7 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl->grid);
+    cfg.gridDim = dim3(PAIR || pl->grid_single <= 0 ? pl->grid : pl->grid_single);
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
@@ -1696,8 +1727,8 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK>, pl->tmA, pl->tmB_hi, pl->tmB_lo, pl->tmO,
-                                   pl->tmR, args),
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK>, pl->tmA,
+                                   PAIR ? pl->tmBh_hi : pl->tmB_hi, PAIR ? pl->tmBh_lo : pl->tmB_lo, pl->tmO, pl->tmR, args),
                 "conv_igemm launch");
     return 1;
 }
@@ -1805,16 +1836,24 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = d->w_exp; a.trace = nullptr; a.exp = 0; a.done_prev = nullptr; a.done_target = 0; a.done_self = nullptr;
     pl->passes = d->passes; pl->corr = 0;
     // CTA pairs (cta_group::2) are opt-in: measured no faster than single-CTA mode (see the kernel comment)
-    pl->pair = (!f16 && a.m_tiles >= 2 && getenv("D2T_CONV_PAIR") && atoi(getenv("D2T_CONV_PAIR")) == 1) ? 1 : 0;
+    // 3xFP16 pairs (plain BN = 128 forward layers): D2T_CONV_PAIR=1 every eligible layer, =2 only the K-loop-bound ones
+    // (more than two K chunks per tile and no residual: the layers that do not take the EPI2 variant)
+    const int pair_env = getenv("D2T_CONV_PAIR") ? atoi(getenv("D2T_CONV_PAIR")) : 0;
+    const bool pair_f16_ok = f16 && pl->BN == 128 && out && d->Cout >= 128 &&
+                             (pair_env == 1 || (pair_env == 2 && !res && a.R * a.S * a.kc_blocks > 2 * chunk_of(16)));
+    pl->pair = (a.m_tiles >= 2 && ((!f16 && pair_env == 1) || pair_f16_ok)) ? 1 : 0;
     if (pl->pair) {
         const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
-        const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + chunk_of(3) - 1) / chunk_of(3));
-        const int maxp = d->passes == 3 ? (pl->BN == 64 ? max_pairs<64, 3>() : max_pairs<128, 3>())
-                                        : (pl->BN == 64 ? max_pairs<64, 1>() : max_pairs<128, 1>());
+        const int ch = chunk_of(d->passes);
+        const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + ch - 1) / ch);
+        const int maxp = f16 ? max_pairs<128, 16>()
+                             : (d->passes == 3 ? (pl->BN == 64 ? max_pairs<64, 3>() : max_pairs<128, 3>())
+                                               : (pl->BN == 64 ? max_pairs<64, 1>() : max_pairs<128, 1>()));
         pl->grid = 2 * (int)(units < maxp ? units : maxp);
     } else {
         pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks, d->passes);
     }
+    pl->grid_single = sk_grid(a.m_tiles * a.n_tiles, a.R * a.S * a.kc_blocks, d->passes);
     SkScratch sk;
     if (!sk_scratch(&sk)) {
         free(pl);
@@ -1833,12 +1872,20 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     const cuuint64_t ktot = (cuuint64_t)d->R * d->S * a.kc_blocks * kblk;
     const cuuint64_t bdims[2] = {ktot, (cuuint64_t)d->Cout};
     const cuuint64_t bstr[1] = {ktot * (f16 ? 2 : 4)};
-    const cuuint32_t bbox[2] = {(cuuint32_t)kblk, (cuuint32_t)(pl->pair ? pl->BN / 2 : pl->BN)};
+    const cuuint32_t bbox[2] = {(cuuint32_t)kblk, (cuuint32_t)pl->BN};
+    const cuuint32_t bbox_half[2] = {(cuuint32_t)kblk, (cuuint32_t)(pl->BN / 2)};
     const cuuint32_t bestr[2] = {1u, 1u};
     bool ok = encode(&pl->tmA, in, 4, adims, astr, abox, aestr, "A") &&
               encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "B hi", f16);
     if (ok && d->passes != 1) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "B lo", f16);
     if (ok && d->passes == 1) pl->tmB_lo = pl->tmB_hi;
+    pl->tmBh_hi = pl->tmB_hi;
+    pl->tmBh_lo = pl->tmB_lo;
+    if (ok && pl->pair) {
+        ok = encode(&pl->tmBh_hi, w_hi, 2, bdims, bstr, bbox_half, bestr, "B hi (pair)", f16);
+        if (ok && d->passes != 1) ok = encode(&pl->tmBh_lo, w_lo, 2, bdims, bstr, bbox_half, bestr, "B lo (pair)", f16);
+        if (ok && d->passes == 1) pl->tmBh_lo = pl->tmBh_hi;
+    }
     if (ok && out) ok = encode_out_map(&pl->tmO, out, d->N, OH, OW, d->Cout, d->out_cstride, d->out_coffset, TH, TW);
     else if (ok) pl->tmO = pl->tmA;
     // EPI2 variant (3xFP16, BN = 128, NHWC output): layers whose time is the epilogue rather than the K loop -- a residual
@@ -1846,6 +1893,8 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     // residual through the TMA.  D2T_CONV_EPI2=0/1 forces the choice (experiments).
     pl->epi2 = (f16 && pl->BN == 128 && out && (res || a.R * a.S * a.kc_blocks <= 2 * chunk_of(16))) ? 1 : 0;
     if (f16 && pl->BN == 128 && out && getenv("D2T_CONV_EPI2")) pl->epi2 = atoi(getenv("D2T_CONV_EPI2")) ? 1 : 0;
+    // (a pair plan that later receives a ReLU mask falls back to the single-CTA kernel, d2t_conv_plan_set_mask: EPI2 is
+    // decided as if it had never been a pair)
     pl->tmR = pl->tmA;
     if (ok && pl->epi2 && res)
         ok = encode_out_map(&pl->tmR, const_cast<float*>(res), d->N, OH, OW, d->Cout, a.res_cstride, 0, TH, TW);
@@ -2126,6 +2175,7 @@ extern "C" int d2t_conv_plan_set_mask(d2t_conv_plan* pl, const float* mask, int 
                 "d2t_conv_plan_set_mask: needs a convolution plan and a mask with a channel stride that is a multiple of 4");
     pl->args.mask = mask;
     pl->args.mask_cstride = mask_cstride;
+    if (mask) pl->pair = 0;             // the backward-data epilogue is a single-CTA variant
     return 1;
 }
 
@@ -2137,7 +2187,7 @@ extern "C" int d2t_conv_plan_set_weight_amax(d2t_conv_plan* pl, const float* ama
 }
 
 extern "C" int d2t_conv_plan_set_early_weights(d2t_conv_plan* pl, int on) {
-    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && !pl->corrb && !pl->pair,
+    D2T_REQUIRE(pl && !pl->corr && !pl->wgrad && !pl->corrb,
                 "d2t_conv_plan_set_early_weights: needs a convolution plan (its B operand must be the packed weights)");
     pl->args.early_b = on ? 1 : 0;
     return 1;
@@ -2216,12 +2266,13 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
     }
 #define D2T_RUN(bn, ps) (pl->pair ? launch_conv<bn, ps, false, true>(pl, stream) : launch_conv<bn, ps, false, false>(pl, stream))
     if (pl->passes == 16) {
-        if (pl->args.mask) {        // backward-data plans: the epilogue with the ReLU mask compiled in
+        if (pl->args.mask) {        // backward-data plans: the epilogue with the ReLU mask compiled in (never pairs)
             if (pl->BN == 64) return launch_conv<64, 16, false, false, false, false, false, true>(pl, stream);
             return pl->epi2 ? launch_conv<128, 16, false, false, true, false, false, true>(pl, stream)
                             : launch_conv<128, 16, false, false, false, false, false, true>(pl, stream);
         }
         if (pl->BN == 64) return launch_conv<64, 16, false, false>(pl, stream);
+        if (pl->pair) return launch_conv<128, 16, false, true>(pl, stream);
         return pl->epi2 ? launch_conv<128, 16, false, false, true>(pl, stream) : launch_conv<128, 16, false, false>(pl, stream);
     }
     if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);

@@ -256,6 +256,40 @@ def test_cta_pair_mode_matches(monkeypatch):
     assert torch.equal(outs[1][1].permute(0, 3, 1, 2), outs[1][0])
 
 
+@pytest.mark.parametrize("case", [(2, 256, 38, 63, 384, 3, 1, 1, False), (4, 1024, 38, 63, 256, 1, 0, 1, False),
+                                  (1, 512, 38, 63, 512, 3, 2, 2, False), (3, 256, 19, 32, 1519, 1, 0, 1, False),
+                                  (2, 128, 38, 63, 512, 1, 0, 1, True)])
+def test_cta_pair_mode_fp16_split(monkeypatch, case):
+    """3xFP16 as CTA pairs (cta_group::2, M = 256: each CTA converts its own activation tile into its own tensor memory and
+    stages HALF of the weight tile): the same products as single-CTA mode; only the stream-K split points differ (units are
+    dealt to 74 pairs instead of 148 CTAs), i.e. the order of a few fp32 additions -- outputs agree to 2e-6 of the scale and
+    both are within 1e-5 of float64.  Odd m-tile counts (the pair's second tile does not exist), stream-K splits across
+    pairs, a residual, Cout not a multiple of the tile, NCHW + NHWC outputs, repeated launches."""
+    N, Cin, H, W, Cout, k, pad, dil, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(21 + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    sc, sh = torch.rand(Cout, device="cuda", generator=g) + 0.5, torch.randn(Cout, device="cuda", generator=g)
+    res = dc.ActTensor.from_nchw(torch.randn(N, Cout, H, W, device="cuda", generator=g), cstride=Cout) if use_res else None
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("D2T_CONV_PAIR", pair)
+        layer = dc.ConvLayer(dc.ActTensor.from_nchw(x), w, sc, sh, 1, pad, dil, True, res, passes=16, want_nhwc=(Cout % 4 == 0),
+                             want_nchw=True)
+        assert layer.info["grid"] % 10 == (int(pair) if Cout % 4 == 0 else 0)       # (pairs need the NHWC output path)
+        for _ in range(2):
+            layer.run()
+        torch.cuda.synchronize()
+        outs.append((layer.out_nchw.clone(), layer.out.x.clone() if layer.out is not None else None, layer.out.amax.clone() if layer.out is not None else None))
+    want = _ref(x, w, sc, sh, 1, pad, dil, True, res.to_nchw() if use_res else None)
+    scale = float(want.abs().max())
+    assert float((outs[1][0] - want).abs().max()) / scale < 1e-5 and float((outs[0][0] - want).abs().max()) / scale < 1e-5
+    assert float((outs[0][0] - outs[1][0]).abs().max()) / scale < 2e-6
+    if outs[0][1] is not None:
+        assert torch.equal(outs[1][1][..., :Cout].permute(0, 3, 1, 2), outs[1][0])      # NHWC and NCHW outputs carry the same values
+        assert abs(float(outs[0][2]) - float(outs[1][2])) <= 2e-6 * scale
+
+
 def test_two_engines_on_two_streams_with_private_scratch():
     """Two conv chains may overlap on different streams only with their own stream-K scratch (partial tiles + flags):
     results must equal the sequential runs (sharing the device-wide scratch would deadlock a finisher on a clobbered flag)."""
