@@ -55,12 +55,16 @@ def peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch from the committed ncu captures (profiles/r01_traffic.json); bench.py cannot run ncu itself."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(path))
-    except (OSError, ValueError):
-        return {}
+    """DRAM bytes per launch from the committed ncu captures (profiles/r02_traffic.json, else round 1's); bench.py cannot
+    run ncu itself."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            d["_file"] = "profiles/" + name
+            return d
+        except (OSError, ValueError):
+            continue
+    return {}
 
 
 def make_inputs(pairs, seed):
@@ -477,7 +481,7 @@ def run_b200(args):
                     "bound": "tensor", "achieved": tf_useful, "peak": _tf, "unit": "TFLOP/s", "frac": tf_useful / _tf,
                     "traffic": ncu_traffic().get("conv_igemm", {}).get("dram_bytes_per_launch") if args.passes == 16 else None,
                     "traffic_note": "dram__bytes_read + write per launch, mean over the step's conv launches, ncu (cold cache, "
-                                    "serialised: every layer re-reads its input from DRAM); profiles/r01_traffic.json",
+                                    "serialised: every layer re-reads its input from DRAM); " + str(ncu_traffic().get("_file")),
                     "peak_source": peak_src + " (cuBLAS bf16 burst = the kind::f16 peak at the clocks of this run; kind::tf32 peaks at half of it)",
                     "peak_sustained": peaks.sustained, "frac_vs_sustained_peak": tf_useful / peaks.sustained,
                     "algorithmic_flops_per_launch": conv_flops / n_conv, "avg_launch_ms": conv_ms / n_conv,

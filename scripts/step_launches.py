@@ -35,3 +35,26 @@ for d in step:
     e[4] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) * d.get("gpu__time_duration.sum", 0) / 1e6
 for n, e in sorted(g.items(), key=lambda kv: -kv[1][1]):
     print("%-72s n=%4d  %8.3f ms %5.1f%%  dram rd %8.1f MB wr %8.1f MB  tensor-pipe active %4.1f%%" % (n, e[0], e[1], 100 * e[1] / tot, e[2], e[3], e[4] / e[1] if e[1] else 0))
+
+if len(sys.argv) > 3:      # also write the traffic summary bench.py reads (profiles/rNN_traffic.json)
+    import json
+    conv = [d for d in step if "conv_igemm" in d["name"]]
+    t_ns = sum(d.get("gpu__time_duration.sum", 0) for d in conv)
+    out = {"source": "ncu launch list of `bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train` (cold-cache, serialised), "
+                     "summarised by scripts/step_launches.py",
+           "conv_igemm": {
+               "launches_per_step": len(conv),
+               "dram_bytes_per_launch": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in conv) / max(1, len(conv)),
+               "dram_read_bytes_per_step": sum(d.get("dram__bytes_read.sum", 0) for d in conv),
+               "dram_write_bytes_per_step": sum(d.get("dram__bytes_write.sum", 0) for d in conv),
+               "ncu_time_ms_per_step": t_ns / 1e6,
+               "share_of_step_kernel_time": t_ns / 1e6 / tot,
+               "tensor_pipe_active_pct_time_weighted": sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) *
+                                                           d.get("gpu__time_duration.sum", 0) for d in conv) / max(1.0, t_ns)}}
+    try:
+        prev = json.load(open(sys.argv[3]))
+        for k, v in prev.items():
+            out.setdefault(k, v)
+    except (OSError, ValueError):
+        pass
+    json.dump(out, open(sys.argv[3], "w"), indent=1)
