@@ -180,7 +180,10 @@ struct Sched {
     }
 };
 
-template <int BN, int PASSES, bool PAIR = false, bool EPI2 = false>
+// ARES ("A resident", an EPI2 sub-variant for 1x1 layers of at most 4 K blocks): the activation tile of an m tile is converted
+// into tensor memory ONCE and reused by all the n tiles the CTA runs on it (see the kernel comment).  Shared memory then
+// holds one fp32 staging buffer for A, a ring of weight-only stages and the full-tile output staging.
+template <int BN, int PASSES, bool PAIR = false, bool EPI2 = false, bool ARES = false>
 struct Cfg {
     static constexpr bool F16 = PASSES == 16;
     static constexpr bool SPLIT = PASSES != 1;                        // three products per K step
@@ -195,7 +198,8 @@ struct Cfg {
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KBLK * (F16 ? 2 : 4);   // (a CTA pair holds half of B each)
     static constexpr int NOPER = PASSES == 3 ? 2 : 1;                 // TF32: hi (+ lo) copies of each operand
     // smem per stage -- TF32: A x | A lo | B x | B lo;  FP16: A (hi | lo) | B hi | B lo
-    static constexpr int STAGE_BYTES = F16 ? A_BYTES + 2 * B_BYTES : NOPER * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = ARES ? 2 * B_BYTES : (F16 ? A_BYTES + 2 * B_BYTES : NOPER * (A_BYTES + B_BYTES));
+    static constexpr int A_STAGING = ARES ? A_BYTES : 0;              // ARES: one fp32 activation K block in front of the ring
     static constexpr int OFF_ALO = F16 ? A_BYTES / 2 : A_BYTES;
     static constexpr int OFF_BHI = F16 ? A_BYTES : NOPER * A_BYTES;
     static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
@@ -203,11 +207,20 @@ struct Cfg {
     // epilogue group, reused by the BN/64 slabs of a tile.  EPI2 (layers whose time is the epilogue, not the K loop: short
     // K, residual): one buffer for EVERY slab of the tile, paid for with one pipeline stage.
     static constexpr int OUT_SLABS = EPI2 ? BN / 64 : 1;             // buffers per group
-    static constexpr int OUT_STAGE_BYTES = 2 * OUT_SLABS * kBlockM * 128;
-    static constexpr int STAGES_RAW = (228 * 1024 - OUT_STAGE_BYTES) / STAGE_BYTES;
+    static constexpr int OUT_BUF_BYTES = 2 * OUT_SLABS * kBlockM * 128;
+    // ARES: TWO full-tile buffers -- the residual of tile i + 1 lands while tile i is being added / stored, and no TMA wait
+    // sits on the epilogue's critical path
+    static constexpr int OUT_STAGE_BYTES = (ARES ? 2 : 1) * OUT_BUF_BYTES;
+    static constexpr int STAGES_RAW = (228 * 1024 - OUT_STAGE_BYTES - A_STAGING) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/ +
-                                      1024 /*scale | shift of the current n tile*/;
+    static constexpr int OUT_OFF = A_STAGING + STAGES * STAGE_BYTES;  // output staging follows the operand stages
+    static constexpr int SMEM_BYTES = OUT_OFF + OUT_STAGE_BYTES + 1024 /*align slack*/ + 384 /*barriers*/ +
+                                      1024 /*scale | shift of the current n tile*/ + (ARES ? 512 : 0) /*third shift buffer*/;
+    // barrier block (8-byte slots from `bars`)
+    static constexpr int NCVT = ARES ? 4 : STAGES;
+    static constexpr int BAR_CVT = 2 * STAGES + 6, BAR_RFULL = BAR_CVT + NCVT, BAR_TSLOT = BAR_RFULL + 2;
+    static constexpr int BAR_AFULL = BAR_TSLOT + 1, BAR_AEMPTY = BAR_AFULL + 1, BAR_AFREE = BAR_AEMPTY + 1, BAR_RFULL2 = BAR_AFREE + 4;
+    static_assert((BAR_RFULL2 + 2) * 8 <= 384, "barrier block");
     // TMEM columns: main[2] chunk buffers (+ cross[2] whole-tile buffers in 3-pass mode), BN each
     // TMEM columns.  TF32: main[2] chunk accumulators (+ cross[2] whole-tile accumulators in 3-pass mode), BN each.
     // 3xFP16: main[2] only (the cross terms join the chunk accumulator) + the A OPERAND RING: per pipeline stage 32 columns
@@ -216,9 +229,12 @@ struct Cfg {
     static constexpr bool ATMEM = F16;
     static constexpr int A_TMEM_COLS = 64;
     static constexpr int A_TMEM_BASE = 2 * BN;
-    static constexpr int TMEM_USED = ATMEM ? 2 * BN + STAGES * A_TMEM_COLS : (SPLIT ? 4 : 2) * BN;
+    static constexpr int A_SLOTS = ARES ? 4 : STAGES;                 // ARES: slot = K block of the tile, resident across n tiles
+    static constexpr int TMEM_USED = ATMEM ? 2 * BN + A_SLOTS * A_TMEM_COLS : (SPLIT ? 4 : 2) * BN;
     static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
     static_assert(TMEM_USED <= 512, "tensor memory budget");
+    static_assert(!ARES || (EPI2 && F16 && !PAIR && BN == 128 && STAGES >= 2), "ARES is an EPI2 sub-variant");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -441,7 +457,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 // (re)initialised here, per layer; tensors written by earlier layers of the same launch are only read through the TMA or
 // with L2-coherent loads; a publisher waits for its stream-K flag to be consumed before it reuses its scratch slot (layers
 // that do not depend on each other run without a grid-wide barrier between them); no setmaxnreg.
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD, bool CORRB, bool MASK, bool CHAIN>
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD, bool CORRB, bool MASK, bool CHAIN, bool ARES = false>
 __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activation (A operand)
                                           const CUtensorMap& tmB_hi,   // weights w (CORR: the second frame's activation)
                                           const CUtensorMap& tmB_lo,   // weights w_lo (unused in CORR / 1-pass mode)
@@ -450,23 +466,31 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                                           const ConvArgs& p, uint8_t* smem /*1024-B aligned*/, uint64_t* bars,
                                           const uint32_t tmem_base, const uint32_t crank, const int prev_nbars,
                                           const Sched* pre_sched = nullptr) {
-    using C = Cfg<BN, PASSES, PAIR, EPI2>;
+    using C = Cfg<BN, PASSES, PAIR, EPI2, ARES>;
     static_assert(!EPI2 || (PASSES == 16 && !CORR && !PAIR), "EPI2 is a 3xFP16 convolution variant");
+    static_assert(!ARES || (!CHAIN && !WGRAD && !CORRB && !CORR), "ARES is a stand-alone convolution variant");
     constexpr bool F16 = C::F16, SPLIT = C::SPLIT, ATMEM = C::ATMEM;
     constexpr int kChunkK = C::CHUNK, kBlockK = C::KBLK, kCvtThreads = C::CVT_THREADS;
     static_assert(!(F16 && PAIR) || (BN == 128 && !CORR && !WGRAD && !CORRB && !MASK), "3xFP16 pairs: plain forward convolutions");
     static_assert(!WGRAD || (F16 && !EPI2), "the weight-gradient mode is a plain 3xFP16 variant");
     static_assert(!CORRB || (F16 && !EPI2 && !WGRAD && BN == 128), "the correlation-backward mode is a plain 3xFP16 variant");
     static_assert(!CHAIN || (F16 && !CORR && !PAIR && !WGRAD && !CORRB), "the chain kernel runs 3xFP16 convolutions");
-    uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;                   // [2 groups][128 rows][128 B], swizzled
+    uint8_t* out_stage = smem + C::OUT_OFF;                                   // [2 groups][128 rows][128 B], swizzled
     uint64_t* full = bars;                        // [STAGES]   TMA -> MMA
     uint64_t* empty = bars + C::STAGES;           // [STAGES]   MMA -> TMA
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]        MMA -> epilogue: chunk buffer complete
     uint64_t* tempty = tfull + 2;                 // [2]        epilogue -> MMA: chunk buffer drained
     uint64_t* xempty = tempty + 2;                // [2]        epilogue -> MMA: cross-term buffer read
-    uint64_t* cvt = xempty + 2;                   // [STAGES]   converters -> MMA: lo tile(s) of the stage written
-    uint64_t* rfull = cvt + C::STAGES;            // [2]        TMA -> epilogue group: residual slabs landed (EPI2)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
+    uint64_t* cvt = bars + C::BAR_CVT;            // [STAGES]   converters -> MMA: lo tile(s) of the stage written (ARES: [4], per A slot)
+    uint64_t* rfull = bars + C::BAR_RFULL;        // [2]        TMA -> epilogue group: residual slabs landed (EPI2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::BAR_TSLOT);
+    // ARES only: the A staging buffer's hand-shake, "slot k may be overwritten" (the MMAs that read it have retired), and the
+    // residual barriers of the odd tiles (two output buffers in flight)
+    uint64_t* afull = bars + C::BAR_AFULL;        // [1]        TMA -> converters: fp32 K block landed
+    uint64_t* aempty = bars + C::BAR_AEMPTY;      // [1]        converters -> TMA: staging buffer read
+    uint64_t* afree = bars + C::BAR_AFREE;        // [4]        MMA -> converters
+    uint64_t* rfull2 = bars + C::BAR_RFULL2;      // [2]
+    (void)afull; (void)aempty; (void)afree; (void)rfull2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CS = PAIR ? 2 : 1;               // CTAs per work unit
@@ -487,8 +511,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             for (int i = 0; i < C::STAGES; ++i) {
                 mbar_init(&full[i], 1);
                 mbar_init(&empty[i], 1);
-                mbar_init(&cvt[i], kCvtThreads);
             }
+            for (int i = 0; i < C::NCVT; ++i) mbar_init(&cvt[i], kCvtThreads);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull[i], 1);
                 mbar_init(&tempty[i], kEpiThreads);
@@ -518,6 +542,144 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
     if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
     // ---- warpgroups 0 (and 3 in 3xFP16 mode): TMA producer, MMA issuer, converters
     if constexpr (F16) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if constexpr (ARES) {
+        // ===================== A-resident variant: 1x1 layers of 2..4 K blocks, several n tiles per m tile =====================
+        // Tiles run n-inner (t = m_tile * n_tiles + n_tile), every tile is whole (one chunk), so consecutive tiles of a CTA
+        // mostly share their m tile: its activation K blocks are loaded + converted into tensor memory slots 0..k_iters-1 ONCE
+        // ("fresh" tile) and the following tiles only stream weights -- per tile 128 KB of TMA traffic and 32 KB of converter
+        // reads less, on layers whose time is shared-memory bandwidth.  Rings: A staging (1 buffer,
+        // afull / aempty), weight stages (4, full / empty), A slots (cvt[k]: converted, afree[k]: last reader retired).
+        const int nt = p.n_tiles;
+        if (warp == 0) {
+            // ---- weight producer: lanes 0 / 1 = hi / lo halves of the stage
+            if (lane < 2) {
+                const CUtensorMap* map = lane == 0 ? &tmB_hi : &tmB_lo;
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int e = 0; e < sched.nseg; ++e) {
+                    const int n0 = (sched.get(e).tile % nt) * BN;
+                    for (int k = 0; k < k_iters; ++k) {
+                        mbar_wait_sleep(&empty[stage], phase ^ 1);
+                        uint8_t* dst = smem + C::A_STAGING + stage * C::STAGE_BYTES + lane * C::B_BYTES;
+                        if (lane == 0) mbar_expect_tx(&full[stage], 2 * C::B_BYTES);
+                        tma_load_2d(dst, map, &full[stage], k * kBlockK, n0);
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == kEpiWarp0 + 10) {
+            // ---- activation producer (warp 14): the two 32-channel sub-tiles of a K block, fresh tiles only
+            if (lane < 2) {
+                uint32_t aphase = 0;
+                int prev_m = -1;
+                for (int e = 0; e < sched.nseg; ++e) {
+                    const int m_tile = sched.get(e).tile / nt;
+                    if (m_tile == prev_m) continue;
+                    prev_m = m_tile;
+                    const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
+                    const int iw0 = (tw << p.TW_log2) * p.stride - p.pad, ih0 = th * p.TH * p.stride - p.pad;
+                    for (int k = 0; k < k_iters; ++k) {
+                        mbar_wait_sleep(aempty, aphase ^ 1);           // the converters have read the previous K block
+                        aphase ^= 1;
+                        if (lane == 0) mbar_expect_tx(afull, C::A_BYTES);
+                        tma_load_4d(smem + lane * (kBlockM * kBoxC * 4), &tmA, afull, k * kBlockK + lane * kBoxC, iw0, ih0, img);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ---- MMA issuer
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_f16<BN>();
+                const uint64_t desc0 = make_smem_desc(smem_u32(smem + C::A_STAGING));
+                int stage = 0, cbuf = 0, prev_m = -1, fresh_idx = -1;
+                uint32_t phase = 0, cphase = 0;
+                for (int e = 0; e < sched.nseg; ++e) {
+                    const int m_tile = sched.get(e).tile / nt;
+                    const bool fresh = m_tile != prev_m;
+                    prev_m = m_tile;
+                    if (fresh) ++fresh_idx;
+                    const bool last_of_group = e + 1 == sched.nseg || sched.get(e + 1).tile / nt != m_tile;
+                    mbar_wait_sleep(&tempty[cbuf], cphase ^ 1);        // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_main = tmem_base + cbuf * BN;
+                    for (int k = 0; k < k_iters; ++k) {
+                        mbar_wait_sleep(&full[stage], phase);
+                        if (fresh) mbar_wait_sleep(&cvt[k], (uint32_t)(fresh_idx & 1));
+                        tc_fence_after();
+                        const uint64_t b_hi = desc0 + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
+                        const uint64_t b_lo = b_hi + (C::B_BYTES >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t o = (uint64_t)(kk * 32 >> 4);
+                            const uint32_t at_hi = tmem_base + C::A_TMEM_BASE + k * C::A_TMEM_COLS + kk * 8;
+                            umma_f16_ts(d_main, at_hi, b_hi + o, idesc, (k | kk) != 0);
+                            umma_f16_ts(d_main, at_hi, b_lo + o, idesc, 1);
+                            umma_f16_ts(d_main, at_hi + 32, b_hi + o, idesc, 1);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (last_of_group) umma_commit(&afree[k]);     // slot k may be overwritten once these have retired
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tfull[cbuf]);
+                    cbuf ^= 1;
+                    if (cbuf == 0) cphase ^= 1;
+                }
+            }
+        } else if (warp < kEpiWarp0 || warp == kEpiWarp0 + 8 || warp == kEpiWarp0 + 9) {
+            // ---- converters (warps 2, 3, 12, 13 = tensor-memory lane quarters 2, 3, 0, 1): fresh tiles only
+            const int m = (warp & 3) * 32 + lane;
+            const uint32_t sw = (uint32_t)m & 7u;
+            const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_TMEM_BASE;
+            const float sa = pow2f(act_exp(p.amax_in));
+            uint32_t aphase = 0;
+            int prev_m = -1, fresh_idx = -1;
+            for (int e = 0; e < sched.nseg; ++e) {
+                const int m_tile = sched.get(e).tile / nt;
+                if (m_tile == prev_m) continue;
+                prev_m = m_tile;
+                ++fresh_idx;
+                for (int k = 0; k < k_iters; ++k) {
+                    if (fresh_idx > 0) mbar_wait_sleep(&afree[k], (uint32_t)((fresh_idx - 1) & 1));
+                    mbar_wait_sleep(afull, aphase);
+                    aphase ^= 1;
+                    tc_fence_after();
+                    const uint8_t* row = smem + m * 128;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint8_t* src = row + half * (kBlockM * kBoxC * 4);
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
+                            const float a0 = v.x * sa, a1 = v.y * sa, a2 = v.z * sa, a3 = v.w * sa;
+                            const float h0 = __uint_as_float(__float_as_uint(a0) & 0xffffe000u);
+                            const float h1 = __uint_as_float(__float_as_uint(a1) & 0xffffe000u);
+                            const float h2 = __uint_as_float(__float_as_uint(a2) & 0xffffe000u);
+                            const float h3 = __uint_as_float(__float_as_uint(a3) & 0xffffe000u);
+                            __half2 t;
+                            t = __floats2half2_rn(h0, h1); hi[2 * c] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(h2, h3); hi[2 * c + 1] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(a0 - h0, a1 - h1); lo[2 * c] = *reinterpret_cast<uint32_t*>(&t);
+                            t = __floats2half2_rn(a2 - h2, a3 - h3); lo[2 * c + 1] = *reinterpret_cast<uint32_t*>(&t);
+                        }
+                        const uint32_t slot = a_lane + k * C::A_TMEM_COLS + half * 16;
+                        tmem_st16(slot, hi);
+                        tmem_st16(slot + 32, lo);
+                    }
+                    mbar_arrive(aempty);                               // (the staging rows are in registers / tensor memory)
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(&cvt[k]);
+                }
+            }
+        }
+    } else
     if (warp == 0) {
         // ===================== TMA producer =====================
         // One lane per operand copy (A x, A lo, B x, B lo), all four walking the same K loop; (r, s, kc) advance
@@ -961,10 +1123,38 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             return src ? __ldg(src + chn) : (is_shift ? 0.f : 1.f);
         };
         float scsh_next = sched.nseg > 0 ? fetch_scsh(sched.get(0).tile) : 0.f;
+        // ARES: the epilogue is software-pipelined over the CTA's tiles.  Output / residual staging is double-buffered (tile i
+        // uses buffer i & 1) and the residual of tile i + 1 is requested during tile i, once the buffer's previous store has
+        // been read; the shifts sit in THREE small buffers written one tile ahead, so one named barrier per tile orders them.
+        auto res_request = [&](int e2) {                     // (thread m == 0 of each group) residual slabs of segment e2
+            const int t2 = sched.get(e2).tile;
+            const int n02 = (t2 % p.n_tiles) * BN, m2 = t2 / p.n_tiles;
+            const int tw2 = m2 % p.tiles_w, th2 = (m2 / p.tiles_w) % p.tiles_h, img2 = m2 / (p.tiles_w * p.tiles_h);
+            uint64_t* rb = (e2 & 1) ? &rfull2[grp] : &rfull[grp];
+            int nsl = 0;
+#pragma unroll
+            for (int sl = 0; sl < HN / 32; ++sl) nsl += (n02 + cofs + sl * 32 < p.Cout) ? 1 : 0;
+            mbar_expect_tx(rb, nsl * (kBlockM * 128));
+#pragma unroll
+            for (int sl = 0; sl < HN / 32; ++sl) {
+                const int chs = n02 + cofs + sl * 32;
+                if (chs < p.Cout)
+                    tma_load_4d(out_stage + (e2 & 1) * C::OUT_BUF_BYTES + (grp * C::OUT_SLABS + sl) * (kBlockM * 128), &tmR, rb, chs,
+                                tw2 << p.TW_log2, th2 * p.TH, img2);
+            }
+        };
+        if constexpr (ARES) {
+            if (sched.nseg > 0) {
+                if (p.res != nullptr && m == 0) res_request(0);
+                if (et >= BN && et < 2 * BN) scsh[et - BN] = scsh_next;                 // shift buffer 0 <- tile 0
+                scsh_next = sched.nseg > 1 ? fetch_scsh(sched.get(1).tile) : 0.f;        // (fetched one more tile ahead)
+            }
+        }
         for (; local < sched.nseg; ++local) {
             const Seg sg = sched.get(local);
             const float scsh_cur = scsh_next;
-            if (local + 1 < sched.nseg) scsh_next = fetch_scsh(sched.get(local + 1).tile);
+            if (local + (ARES ? 2 : 1) < sched.nseg) scsh_next = fetch_scsh(sched.get(local + (ARES ? 2 : 1)).tile);
+            uint8_t* const obuf = out_stage + (ARES ? (local & 1) * C::OUT_BUF_BYTES : 0);
             const int t = sg.tile, nchunks = sg.c1 - sg.c0;
             const int xacc = local & 1;
             const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
@@ -981,7 +1171,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             // its own row): 64 KB per SM in flight on the TMA engine, which plain loads cannot sustain (the LSU keeps
             // ~16 KB in flight per SM: measured ~10 B/clk/SM for register-prefetched residual rows)
             const bool res_tma = EPI2 && !CORR && p.res != nullptr && sg.role != 1;
-            if constexpr (EPI2) {
+            if constexpr (EPI2 && !ARES) {
                 if (res_tma && m == 0) {
                     tma_store_wait_read();                  // the previous tile's stores have read the slabs
                     int nsl = 0;
@@ -999,11 +1189,17 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             }
             float acc[HN];
             if constexpr (FOLDED) {
+                if constexpr (ARES) {
+                    // shift buffer (i + 1) % 3 <- tile i + 1 (its last readers, tile i - 2, passed the previous barrier)
+                    if (local + 1 < sched.nseg && et >= BN && et < 2 * BN) scsh[((local + 1) % 3) * BN + et - BN] = scsh_cur;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                } else {
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue thread has read the previous tile's shifts
                 if (et >= BN && et < 2 * BN) scsh[et] = scsh_cur;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
                 if (sg.role != 1) {                              // (a published partial tile must not carry the shift)
-                    const float4* sh4 = reinterpret_cast<const float4*>(scsh + BN + cofs);
+                    const float4* sh4 = reinterpret_cast<const float4*>(scsh + (ARES ? (local % 3) * BN : BN) + cofs);
 #pragma unroll
                     for (int j = 0; j < HN; j += 4) {
                         const float4 sh = sh4[j >> 2];
@@ -1046,6 +1242,12 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                 else mbar_arrive(&xempty[xacc]);
             }
             // ---- from here on the tile lives in registers; the tensor core is already on the next segment
+            if constexpr (ARES) {
+                if (p.res != nullptr && m == 0 && local + 1 < sched.nseg) {
+                    tma_store_wait_read();                   // buffer (i + 1) & 1: the store of tile i - 1 (issued a drain ago) has read it
+                    res_request(local + 1);
+                }
+            }
 #ifdef D2T_CONV_TRACE
             const long long t_post__ = clock64();
 #endif
@@ -1134,8 +1336,12 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             }
             if constexpr (EPI2) {
                 if (res_tma) {                               // the residual slabs of this group have landed
-                    TRACED_WAIT(2, &rfull[grp], rphase);
-                    rphase ^= 1;
+                    if constexpr (ARES) {
+                        mbar_wait_sleep((local & 1) ? &rfull2[grp] : &rfull[grp], (uint32_t)((local >> 1) & 1));
+                    } else {
+                        TRACED_WAIT(2, &rfull[grp], rphase);
+                        rphase ^= 1;
+                    }
                 }
             }
 #pragma unroll
@@ -1156,7 +1362,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                 }
                 if (res_tma) {
                     // (channels / pixels outside the tensor were zero-filled by the TMA)
-                    const uint8_t* rrow = out_stage + (grp * C::OUT_SLABS + (c >> 1)) * (kBlockM * 128) + (uint32_t)m * 128u;
+                    const uint8_t* rrow = obuf + (grp * C::OUT_SLABS + (c >> 1)) * (kBlockM * 128) + (uint32_t)m * 128u;
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(rrow + (((uint32_t)((c & 1) * 4 + (j >> 2)) ^ ((uint32_t)m & 7u)) << 4));
@@ -1242,13 +1448,17 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                 const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)m & 7u;
                 if constexpr (EPI2) {
                     if (!res_tma) {
-                        if (m == 0) tma_store_wait_read();    // the previous tile's stores have read the slabs
+                        // the slabs' previous store has read them (ARES: that was two tiles ago -- one group may stay pending)
+                        if (m == 0) {
+                            if constexpr (ARES) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else tma_store_wait_read();
+                        }
                         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
                     }
 #pragma unroll
                     for (int sl = 0; sl < HN / 32; ++sl) {
                         if (n0 + cofs + sl * 32 >= p.Cout) continue;   // (uniform over the group)
-                        uint8_t* slab = out_stage + (grp * C::OUT_SLABS + sl) * (kBlockM * 128);
+                        uint8_t* slab = obuf + (grp * C::OUT_SLABS + sl) * (kBlockM * 128);
                         const float* v = acc + sl * 32;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -1262,7 +1472,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                         for (int sl = 0; sl < HN / 32; ++sl) {
                             const int chs = n0 + cofs + sl * 32;
                             if (chs < p.Cout)
-                                tma_store_4d_nocommit(&tmO, out_stage + (grp * C::OUT_SLABS + sl) * (kBlockM * 128), chs,
+                                tma_store_4d_nocommit(&tmO, obuf + (grp * C::OUT_SLABS + sl) * (kBlockM * 128), chs,
                                                       tw << p.TW_log2, th * p.TH, img);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1317,30 +1527,31 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
     tc_fence_before();
 }
 
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false, bool CORRB = false, bool MASK = false>
-__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2>::THREADS), 1)
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2, bool WGRAD = false, bool CORRB = false, bool MASK = false,
+          bool ARES = false>
+__global__ void __launch_bounds__((Cfg<BN, PASSES, PAIR, EPI2, ARES>::THREADS), 1)
 conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
            const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO,
            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvArgs p) {
 #ifdef D2T_CONV_TRACE
     const long long t_entry__ = clock64();
 #endif
-    using C = Cfg<BN, PASSES, PAIR, EPI2>;
+    using C = Cfg<BN, PASSES, PAIR, EPI2, ARES>;
     constexpr bool SPLIT = C::SPLIT;
     constexpr int kCvtThreads = C::CVT_THREADS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // 1024-B aligned (swizzle atom)
-    uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;
+    uint8_t* out_stage = smem + C::OUT_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* xempty = tempty + 2;
-    uint64_t* cvt = xempty + 2;
-    uint64_t* rfull = cvt + C::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
+    uint64_t* cvt = bars + C::BAR_CVT;
+    uint64_t* rfull = bars + C::BAR_RFULL;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::BAR_TSLOT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CS = PAIR ? 2 : 1;
     uint32_t crank = 0;                            // 0 = leader
@@ -1357,13 +1568,20 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
-            mbar_init(&cvt[i], (PAIR && C::F16) ? 2 : CS * kCvtThreads);   // (leader's copy collects both CTAs' converters; 3xFP16 pairs: one elected arrival per CTA)
         }
+        for (int i = 0; i < C::NCVT; ++i)
+            mbar_init(&cvt[i], (PAIR && C::F16) ? 2 : CS * kCvtThreads);   // (leader's copy collects both CTAs' converters; 3xFP16 pairs: one elected arrival per CTA)
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], CS * kEpiThreads);       // (leader's copy collects both CTAs' epilogue threads)
             mbar_init(&xempty[i], CS * kEpiThreads);
             mbar_init(&rfull[i], 1);
+        }
+        if (ARES) {                                        // (see conv_body)
+            mbar_init(bars + C::BAR_AFULL, 1);
+            mbar_init(bars + C::BAR_AEMPTY, kCvtThreads);
+            for (int i = 0; i < 4; ++i) mbar_init(bars + C::BAR_AFREE + i, 1);
+            for (int i = 0; i < 2; ++i) mbar_init(bars + C::BAR_RFULL2 + i, 1);
         }
         fence_mbar_init();
     }
@@ -1415,8 +1633,8 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const long long t_dep__ = clock64();
 #endif
 
-    conv_body<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK, false>(tmA, tmB_hi, tmB_lo, tmO, tmR, p, smem, bars, tmem_base,
-                                                                        crank, 0, &sched);
+    conv_body<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK, false, ARES>(tmA, tmB_hi, tmB_lo, tmO, tmR, p, smem, bars,
+                                                                              tmem_base, crank, 0, &sched);
     __syncthreads();
     if (p.done_self && threadIdx.x == 0) {         // every thread's stores (and the flag resets above) precede the barrier
         __threadfence();
@@ -1691,15 +1909,17 @@ struct d2t_conv_plan {
     int epi2;                  // 3xFP16, BN = 128: the full-tile output staging / TMA residual variant
     int pair;                  // run as CTA pairs (tcgen05 cta_group::2)
     int private_scratch;       // 1: the caller supplied the stream-K scratch (no cross-stream guard needed)
+    int ares;                  // EPI2 sub-variant: activation tile resident in tensor memory across the n tiles of an m tile
     int wgrad;                 // weight-gradient plan (d2t_wgrad_plan_create)
     int corrb;                 // correlation-backward plan (d2t_corrb_plan_create)
 };
 
-template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false, bool WGRAD = false, bool CORRB = false, bool MASK = false>
+template <int BN, int PASSES, bool CORR, bool PAIR, bool EPI2 = false, bool WGRAD = false, bool CORRB = false, bool MASK = false,
+          bool ARES = false>
 static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
-    using C = Cfg<BN, PASSES, PAIR, EPI2>;
+    using C = Cfg<BN, PASSES, PAIR, EPI2, ARES>;
     static SmemAttrOnce once;
-    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK>, C::SMEM_BYTES, "conv smem attr")) return 0;
+    if (!once.ensure(conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK, ARES>, C::SMEM_BYTES, "conv smem attr")) return 0;
     ConvArgs args = pl->args;
     args.sk_epoch = ++g_sk_epoch;
     cudaLaunchConfig_t cfg = {};
@@ -1727,7 +1947,7 @@ static int launch_conv(const d2t_conv_plan* pl, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     D2T_REQUIRE(PASSES != 16 || args.amax_in, "conv plan: the fp16-split mode needs the input's amax (d2t_conv_plan_set_amax)");
-    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK>, pl->tmA,
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm<BN, PASSES, CORR, PAIR, EPI2, WGRAD, CORRB, MASK, ARES>, pl->tmA,
                                    PAIR ? pl->tmBh_hi : pl->tmB_hi, PAIR ? pl->tmBh_lo : pl->tmB_lo, pl->tmO, pl->tmR, args),
                 "conv_igemm launch");
     return 1;
@@ -1895,6 +2115,10 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     if (f16 && pl->BN == 128 && out && getenv("D2T_CONV_EPI2")) pl->epi2 = atoi(getenv("D2T_CONV_EPI2")) ? 1 : 0;
     // (a pair plan that later receives a ReLU mask falls back to the single-CTA kernel, d2t_conv_plan_set_mask: EPI2 is
     // decided as if it had never been a pair)
+    // A-resident sub-variant: 1x1 layers of 2..4 K blocks with several n tiles per m tile (the residual 1x1 convs that close
+    // a bottleneck in layer2 / layer3, the 256 -> 512 / 1024 shortcut convs).  D2T_CONV_ARES=0 turns it off (experiments).
+    pl->ares = (pl->epi2 && !pl->pair && a.R == 1 && a.S == 1 && a.kc_blocks >= 2 && a.kc_blocks <= 4 && a.n_tiles >= 2 &&
+                !(getenv("D2T_CONV_ARES") && atoi(getenv("D2T_CONV_ARES")) == 0)) ? 1 : 0;
     pl->tmR = pl->tmA;
     if (ok && pl->epi2 && res)
         ok = encode_out_map(&pl->tmR, const_cast<float*>(res), d->N, OH, OW, d->Cout, a.res_cstride, 0, TH, TW);
@@ -2273,6 +2497,7 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
         }
         if (pl->BN == 64) return launch_conv<64, 16, false, false>(pl, stream);
         if (pl->pair) return launch_conv<128, 16, false, true>(pl, stream);
+        if (pl->epi2 && pl->ares) return launch_conv<128, 16, false, false, true, false, false, false, true>(pl, stream);
         return pl->epi2 ? launch_conv<128, 16, false, false, true>(pl, stream) : launch_conv<128, 16, false, false>(pl, stream);
     }
     if (pl->passes == 3) return pl->BN == 64 ? D2T_RUN(64, 3) : D2T_RUN(128, 3);
@@ -2324,7 +2549,7 @@ extern "C" d2t_conv_chain* d2t_conv_chain_create(const d2t_conv_plan* const* pla
         L.tmA = pl->tmA; L.tmB_hi = pl->tmB_hi; L.tmB_lo = pl->tmB_lo; L.tmO = pl->tmO; L.tmR = pl->tmR;
         L.args = pl->args;
         L.args.sk_epoch = i + 1;            // unique per layer: un-barriered neighbours must not mistake each other's partials
-        L.variant = pl->BN == 64 ? 2 : (pl->epi2 ? 1 : 0);
+        L.variant = pl->BN == 64 ? 2 : (pl->epi2 ? 1 : 0);      // (the A-resident sub-variant is a stand-alone kernel: plain EPI2 here)
         L.sync_before = sync_before ? (sync_before[i] != 0) : 1;
         if (getenv("D2T_CHAIN_NOSYNC") && atoi(getenv("D2T_CHAIN_NOSYNC")) == 1) L.sync_before = 0;    // timing experiments only (wrong results)
     }

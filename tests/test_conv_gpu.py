@@ -35,6 +35,10 @@ CASES = [
     (1, 64, 30, 250, 64, 1, 1, 0, 1, True, False),         # W > 128: two tiles per row
     (1, 512, 38, 63, 1519, 1, 1, 0, 1, False, False),      # R-FCN cls head: Cout not a multiple of 16
     (1, 1051, 19, 32, 196, 1, 1, 0, 1, False, False),      # tracking head: Cin padded to 1056
+    (4, 256, 38, 63, 1024, 1, 1, 0, 1, True, True),        # layer3 closing 1x1 + residual: A-resident variant, 8 n tiles
+    (2, 128, 75, 125, 512, 1, 1, 0, 1, True, True),        # layer2 closing 1x1 (2 K blocks)
+    (2, 256, 75, 125, 512, 1, 2, 0, 1, False, False),      # stride-2 shortcut conv (A-resident, no residual)
+    (1, 192, 19, 32, 300, 1, 1, 0, 1, True, False),        # 3 K blocks, Cout not a multiple of the tile
 ]
 
 
@@ -288,6 +292,33 @@ def test_cta_pair_mode_fp16_split(monkeypatch, case):
     if outs[0][1] is not None:
         assert torch.equal(outs[1][1][..., :Cout].permute(0, 3, 1, 2), outs[1][0])      # NHWC and NCHW outputs carry the same values
         assert abs(float(outs[0][2]) - float(outs[1][2])) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("case", [(4, 256, 38, 63, 1024, 1, True), (2, 128, 75, 125, 512, 1, True), (2, 256, 75, 125, 512, 2, False),
+                                  (1, 192, 19, 32, 300, 1, False)])
+def test_a_resident_variant_bit_identical(monkeypatch, case):
+    """The A-resident sub-variant (the activation tile of an m tile converted into tensor memory once, the n tiles that
+    follow stream weights only) issues the same MMAs on the same operands in the same order as the plain EPI2 kernel: the
+    outputs are bit-identical, launch after launch."""
+    N, Cin, H, W, Cout, stride, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(31 + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) * (2.0 / Cin) ** 0.5
+    sc, sh = torch.rand(Cout, device="cuda", generator=g) + 0.5, torch.randn(Cout, device="cuda", generator=g)
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    res = dc.ActTensor.from_nchw(torch.randn(N, Cout, OH, OW, device="cuda", generator=g), cstride=Cout) if use_res else None
+    outs = []
+    for ares in ("0", "1"):
+        monkeypatch.setenv("D2T_CONV_ARES", ares)
+        layer = dc.ConvLayer(dc.ActTensor.from_nchw(x), w, sc, sh, stride, 0, 1, True, res, passes=16)
+        for _ in range(3):
+            layer.out.x.fill_(-3.0)
+            layer.run()
+        torch.cuda.synchronize()
+        outs.append((layer.out.x.clone(), layer.out.amax.clone()))
+    want = _ref(x, w, sc, sh, stride, 0, 1, True, res.to_nchw() if use_res else None)
+    assert float((outs[1][0][..., :Cout].permute(0, 3, 1, 2) - want).abs().max() / want.abs().max()) < 1e-5
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 def test_two_engines_on_two_streams_with_private_scratch():
