@@ -374,6 +374,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load without the wait: several may be in flight before one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 // mbarrier.try_wait already suspends the thread for a hardware-chosen interval, so the poll loop is a plain spin
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
@@ -1213,6 +1221,22 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
 #pragma unroll
                 for (int j = 0; j < HN; ++j) acc[j] = 0.f;
             }
+            if constexpr (ARES) {
+                // one chunk per tile: all four tensor-memory loads of the row in flight before ONE wait (the generic drain
+                // below pays a round trip per 16 columns), then value = accumulator * 2^-(ea + w_exp) + shift
+                TRACED_WAIT(0, &tfull[cbuf], cphase);
+                tc_fence_after();
+                uint32_t raw[HN];
+#pragma unroll
+                for (int c = 0; c < HN / 16; ++c) tmem_ld16_nowait(lane_base + cbuf * BN + cofs + c * 16, raw + c * 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < HN; ++j) acc[j] = fmaf(__uint_as_float(raw[j]), descale, acc[j]);
+                tc_fence_before();
+                mbar_arrive(&tempty[cbuf]);
+                cbuf ^= 1;
+                if (cbuf == 0) cphase ^= 1;
+            } else
             for (int ch = 0; ch < nchunks; ++ch) {          // drain finished chunks: fp32 round-to-nearest adds
                 TRACED_WAIT(0, &tfull[cbuf], cphase);
                 tc_fence_after();
@@ -2115,9 +2139,9 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     if (f16 && pl->BN == 128 && out && getenv("D2T_CONV_EPI2")) pl->epi2 = atoi(getenv("D2T_CONV_EPI2")) ? 1 : 0;
     // (a pair plan that later receives a ReLU mask falls back to the single-CTA kernel, d2t_conv_plan_set_mask: EPI2 is
     // decided as if it had never been a pair)
-    // A-resident sub-variant: 1x1 layers of 2..4 K blocks with several n tiles per m tile (the residual 1x1 convs that close
-    // a bottleneck in layer2 / layer3, the 256 -> 512 / 1024 shortcut convs).  D2T_CONV_ARES=0 turns it off (experiments).
-    pl->ares = (pl->epi2 && !pl->pair && a.R == 1 && a.S == 1 && a.kc_blocks >= 2 && a.kc_blocks <= 4 && a.n_tiles >= 2 &&
+    // A-resident sub-variant: 1x1 layers of at most 4 K blocks with several n tiles per m tile (the residual 1x1 convs that
+    // close a bottleneck in layer1 / layer2 / layer3, the shortcut convs of those stages).  D2T_CONV_ARES=0 turns it off (experiments).
+    pl->ares = (pl->epi2 && !pl->pair && a.R == 1 && a.S == 1 && a.kc_blocks >= 1 && a.kc_blocks <= 4 && a.n_tiles >= 2 &&
                 !(getenv("D2T_CONV_ARES") && atoi(getenv("D2T_CONV_ARES")) == 0)) ? 1 : 0;
     pl->tmR = pl->tmA;
     if (ok && pl->epi2 && res)

@@ -295,7 +295,7 @@ def test_cta_pair_mode_fp16_split(monkeypatch, case):
 
 
 @pytest.mark.parametrize("case", [(4, 256, 38, 63, 1024, 1, True), (2, 128, 75, 125, 512, 1, True), (2, 256, 75, 125, 512, 2, False),
-                                  (1, 192, 19, 32, 300, 1, False)])
+                                  (1, 192, 19, 32, 300, 1, False), (2, 64, 150, 250, 256, 1, True), (2, 64, 38, 63, 256, 1, False)])
 def test_a_resident_variant_bit_identical(monkeypatch, case):
     """The A-resident sub-variant (the activation tile of an m tile converted into tensor memory once, the n tiles that
     follow stream weights only) issues the same MMAs on the same operands in the same order as the plain EPI2 kernel: the
