@@ -214,6 +214,47 @@ def op_microbench(flush, hbm_gbs):
                      "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_useful": flops / ms / 1e9,
                      "kernel": "conv_igemm CORR mode, 3xFP16 (kind::f16); 3xTF32 variant: %.4f ms" % ms_tf32,
                      "ms_3xtf32": ms_tf32, "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
+        # backward: the exact-adjoint SIMT gather kernels behind the operator API (d2t_correlation_backward, both inputs)
+        go = torch.randn(Bc, oc, oh, ow, device="cuda")
+        ms_bwd = time_kernel(lambda: ops.correlation_backward(a, b, go, *p), 5, flush)
+        out[name]["bwd_simt_gather_ms_both_inputs"] = ms_bwd
+        out[name]["bwd_frac_hbm"] = 4.0 * (4 * C_ * Hh * Ww + oc * oh * ow) * Bc / ms_bwd / 1e6 / hbm_gbs
+        del a, b, o, go, layer, layer3
+    # fused PSRoI + 7x7 vote (+ softmax) on the model's own head shapes (4 frames x 300 RoIs, D = 31 classes / 4 deltas)
+    for name, (Dv, sm) in {"psroi_vote_cls_softmax": (31, True), "psroi_vote_bbox": (4, False)}.items():
+        fv = torch.randn(4, Dv * 49, 38, 63, device="cuda")
+        rv = torch.from_numpy(common.make_rois(300, 4, seed=23)).cuda()
+        ms_v = time_kernel(lambda: ops.psroi_vote(fv, rv, 7, 7, 1 / 16., 7, Dv, softmax=sm), 20, flush)
+        ms_u = time_kernel(lambda: ops.psroi_forward(fv, rv, 7, 7, 1 / 16., 7, Dv)[0].mean((2, 3)), 10, flush)
+        alg_v = 4.0 * (4 * Dv * 49 * 2394 + 5 * 1200 + 1200 * Dv)
+        out[name] = {"shape": "feat[4,%d,38,63] rois 300/img" % (Dv * 49), "ms": ms_v, "ms_unfused_psroi_plus_mean": ms_u,
+                     "algorithmic_bytes": alg_v, "frac_hbm": alg_v / ms_v / 1e6 / hbm_gbs}
+        del fv, rv
+    # the three RoI operators that are not on the D&T graph (roi_align / roi_pooling / roi_crop: SURVEY 8 rows a8-a10), on a
+    # conv4-sized map: 2 images x 1024 channels x 38 x 63, 256 RoIs, 7x7 bins
+    fr = torch.randn(2, 1024, 38, 63, device="cuda")
+    rr = torch.from_numpy(common.make_rois(128, 2, seed=24)).cuda()
+    alg_r = 4.0 * (fr.numel() + rr.numel() + 256 * 1024 * 49)
+    top_a = ops.roi_align_forward(fr, rr, 7, 7, 1 / 16.)
+    ms_f = time_kernel(lambda: ops.roi_align_forward(fr, rr, 7, 7, 1 / 16.), 10, flush)
+    ga = torch.randn_like(top_a)
+    ms_b = time_kernel(lambda: ops.roi_align_backward(ga, rr, tuple(fr.shape), 7, 7, 1 / 16.), 10, flush)
+    out["roi_align_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs,
+                                "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
+    top_p, arg_p = ops.roi_pool_forward(fr, rr, 7, 7, 1 / 16.)
+    ms_f = time_kernel(lambda: ops.roi_pool_forward(fr, rr, 7, 7, 1 / 16.), 10, flush)
+    ms_b = time_kernel(lambda: ops.roi_pool_backward(ga, arg_p, rr, tuple(fr.shape), 7, 7, 1 / 16.), 10, flush)
+    out["roi_pool_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs,
+                               "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
+    gridc = (torch.rand(2, 38, 63, 2, device="cuda") * 2 - 1).contiguous()
+    oc_ = ops.roi_crop_forward(fr, gridc)
+    ms_f = time_kernel(lambda: ops.roi_crop_forward(fr, gridc), 10, flush)
+    gc = torch.randn_like(oc_)
+    ms_b = time_kernel(lambda: ops.roi_crop_backward(fr, gridc, gc), 10, flush)
+    alg_c = 4.0 * (2 * fr.numel() + gridc.numel())
+    out["roi_crop_38x63_grid"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_c / ms_f / 1e6 / hbm_gbs,
+                                  "bwd_frac_hbm": 1.5 * alg_c / ms_b / 1e6 / hbm_gbs}
+    del fr, rr, top_a, ga, top_p, arg_p, gridc, oc_, gc
     # detection decode + per-class NMS after the network (test_net.py:232-301), 4 frames x 30 classes
     from d2t_b200 import detect
     g = torch.Generator().manual_seed(50)

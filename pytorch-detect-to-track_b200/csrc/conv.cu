@@ -74,6 +74,11 @@ constexpr int kChunkC = 256;       // channels (x taps) accumulated in TMEM befo
 // channels per K block / K blocks per TMEM chunk for a given operand mode (PASSES: 1 = TF32, 3 = 3xTF32, 16 = 3xFP16)
 __host__ __device__ constexpr int kblk_of(int passes) { return passes == 16 ? 64 : 32; }
 __host__ __device__ constexpr int chunk_of(int passes) { return kChunkC / kblk_of(passes); }
+// Stream-K work unit in K blocks.  Tiles of at most one chunk stay whole (the short-K layers: their epilogue variants assume
+// it); everything else is dealt out K BLOCK by K block -- with whole chunks as units, 608 chunks on 148 CTAs left 16 CTAs
+// with 5 chunks against 4 (measured: those CTAs set the layer's time, profiles/r02_chain_timeline_trace.txt); a segment may
+// now start or end inside a chunk, the accumulation chunks stay aligned to absolute K positions.
+__host__ __device__ constexpr int unit_of(int k_iters, int chunk) { return k_iters <= chunk ? chunk : 1; }
 
 struct ConvArgs {
     int N, OH, OW, Cout;
@@ -507,7 +512,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
     // the stream-K split needs every participating CTA to own at least one unit (a finisher waits for ALL CTAs between the
     // tile's first chunk and itself): the stand-alone launch sizes its grid accordingly (sk_grid), a chain layer with fewer
     // units than CTAs leaves the surplus CTAs idle
-    const long long units_total = (long long)tiles * ((k_iters + kChunkK - 1) / kChunkK);
+    const int kUnit = unit_of(k_iters, kChunkK);
+    const long long units_total = (long long)tiles * ((k_iters + kUnit - 1) / kUnit);
     const int unit_id = blockIdx.x / CS;
     const int n_units = CHAIN ? (int)(units_total < (long long)gridDim.x ? units_total : (long long)gridDim.x) : gridDim.x / CS;
     if constexpr (CHAIN) {
@@ -544,7 +550,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
 #endif
     }
     // (a stand-alone launch computes its schedule -- 64-bit divisions -- before griddepcontrol.wait and hands it in)
-    Sched sched = pre_sched ? *pre_sched : Sched(tiles, k_iters, kChunkK, CHAIN && unit_id >= n_units ? 0 : unit_id, n_units);
+    Sched sched = pre_sched ? *pre_sched : Sched(tiles, k_iters, kUnit, CHAIN && unit_id >= n_units ? 0 : unit_id, n_units);
     if (CHAIN && unit_id >= n_units) sched.nseg = 0;
 
     if (warp < kEpiWarp0 || warp >= kEpiWarp0 + 8) {
@@ -716,7 +722,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                     const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
                     const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
                     const int x0 = tw << p.TW_log2, y0 = th * p.TH;
-                    const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                    const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                     for (int hr = k_beg; hr < k_end; ++hr) {        // K block = halo row y0 - r + hr
                         mbar_wait_sleep(&empty[stage], phase ^ 1);
                         uint8_t* dst = smem + stage * C::STAGE_BYTES + dst_off;
@@ -750,7 +756,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                     // (image, oy) starting at column 64 * xb
                     const int RS = p.R * p.S, tap = m_tile % RS, ci0 = (m_tile / RS) * kBlockM;
                     const int dy = (tap / p.S) * p.dil - p.pad, sx = tap % p.S;     // (column shift sx: pre-shifted B planes)
-                    const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                    const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                     int xb = k_beg % p.wg_xblocks, oy = (k_beg / p.wg_xblocks) % p.OH, im = k_beg / (p.wg_xblocks * p.OH);
                     for (int k = k_beg; k < k_end; ++k) {
                         TRACED_WAIT(0, &empty[stage], phase ^ 1);
@@ -780,7 +786,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                 // correlation: chunk n_tile = halo rows [4*n_tile, 4*n_tile + 4) x 32 columns of frame t+tau
                 const int bw0 = (ow0 - p.corr_r) * p.stride - p.pad;
                 const int bh0 = (oh0 - p.corr_r + 4 * n_tile) * p.stride - p.pad;
-                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                 const int kcb = p.kc_blocks, fS = p.S, dil = p.dil, stem = p.stem;
                 int kc = k_beg % kcb, rs = k_beg / kcb, s = rs % fS, r = rs / fS;
                 for (int k = k_beg; k < k_end; ++k) {
@@ -840,16 +846,17 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             for (; local < sched.nseg; ++local) {
                 const Seg sg = sched.get(local);
                 const int xacc = local & 1;
-                issued += min(sg.c1 * kChunkK, k_iters) - sg.c0 * kChunkK;
+                issued += min(sg.c1 * kUnit, k_iters) - sg.c0 * kUnit;
                 const uint32_t d_cross = tmem_base + (2 + xacc) * BN;
                 if (SPLIT && !ATMEM) {
                     TRACED_WAIT(0, &xempty[xacc], ((local >> 1) & 1) ^ 1);   // epilogue has read this cross buffer
                     tc_fence_after();
                 }
-                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
                     const int kin = k % kChunkK;
-                    if (kin == 0) {
+                    const bool chunk_start = kin == 0 || k == k_beg;         // (a segment may begin inside a chunk)
+                    if (chunk_start) {
                         TRACED_WAIT(1, &tempty[cbuf], cphase ^ 1);          // epilogue drained this chunk buffer
                         tc_fence_after();
                     }
@@ -873,22 +880,22 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                                 // go to the chunk accumulator (48 accumulation steps per 256-channel chunk)
                                 const uint32_t at_hi = tmem_base + C::A_TMEM_BASE + stage * C::A_TMEM_COLS + kk * 8;
                                 if (PAIR) {
-                                    umma_f16_ts_pair(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
+                                    umma_f16_ts_pair(d_main, at_hi, b_hi + o, idesc, !(chunk_start && kk == 0));
                                     umma_f16_ts_pair(d_main, at_hi, b_lo + o, idesc, 1);
                                     umma_f16_ts_pair(d_main, at_hi + 32, b_hi + o, idesc, 1);
                                 } else {
-                                    umma_f16_ts(d_main, at_hi, b_hi + o, idesc, (kin | kk) != 0);
+                                    umma_f16_ts(d_main, at_hi, b_hi + o, idesc, !(chunk_start && kk == 0));
                                     umma_f16_ts(d_main, at_hi, b_lo + o, idesc, 1);
                                     umma_f16_ts(d_main, at_hi + 32, b_hi + o, idesc, 1);
                                 }
                             } else if (PAIR) {
                                 umma_tf32_pair(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                                 umma_tf32_pair(d_cross, a_hi + o, b_lo + o, idesc, 1);
-                                umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                                umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, !(chunk_start && kk == 0));
                             } else {
                                 umma_tf32(d_cross, a_lo + o, b_hi + o, idesc, ((k - k_beg) | kk) != 0);
                                 umma_tf32(d_cross, a_hi + o, b_lo + o, idesc, 1);
-                                umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                                umma_tf32(d_main, a_hi + o, b_hi + o, idesc, !(chunk_start && kk == 0));
                             }
                         }
                     } else {
@@ -896,8 +903,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint64_t o = (uint64_t)(kk * 32 >> 4);
-                            if (PAIR) umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
-                            else umma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kin | kk) != 0);
+                            if (PAIR) umma_tf32_pair(d_main, a_hi + o, b_hi + o, idesc, !(chunk_start && kk == 0));
+                            else umma_tf32(d_main, a_hi + o, b_hi + o, idesc, !(chunk_start && kk == 0));
                         }
                     }
                     // smem slot free once these MMAs retire (in a pair: in BOTH CTAs)
@@ -948,7 +955,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             TRACE_BEGIN();
             for (int e = 0; e < sched.nseg; ++e) {
                 const Seg sg = sched.get(e);
-                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
                     // (the slot's previous MMAs have retired: the TMA refilled this stage only after their commit)
                     TRACED_WAIT(0, &full[stage], phase);
@@ -1055,7 +1062,7 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             uint32_t phase = 0;
             for (int e = 0; e < sched.nseg; ++e) {
                 const Seg sg = sched.get(e);
-                const int k_beg = sg.c0 * kChunkK, k_end = min(sg.c1 * kChunkK, k_iters);
+                const int k_beg = sg.c0 * kUnit, k_end = min(sg.c1 * kUnit, k_iters);
                 for (int k = k_beg; k < k_end; ++k) {
                     mbar_wait_sleep(&full[stage], phase);           // this CTA's copies of the stage have landed
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
@@ -1163,7 +1170,9 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
             const float scsh_cur = scsh_next;
             if (local + (ARES ? 2 : 1) < sched.nseg) scsh_next = fetch_scsh(sched.get(local + (ARES ? 2 : 1)).tile);
             uint8_t* const obuf = out_stage + (ARES ? (local & 1) * C::OUT_BUF_BYTES : 0);
-            const int t = sg.tile, nchunks = sg.c1 - sg.c0;
+            const int t = sg.tile;
+            const int seg_k0 = sg.c0 * kUnit, seg_k1 = min(sg.c1 * kUnit, k_iters);
+            const int nchunks = (seg_k1 - 1) / kChunkK - seg_k0 / kChunkK + 1;      // accumulation chunks the segment touches
             const int xacc = local & 1;
             const int n_tile = t % p.n_tiles, m_tile = (t / p.n_tiles) * CS + (int)crank;
             const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, img = m_tile / (p.tiles_w * p.tiles_h);
@@ -1625,9 +1634,9 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (PAIR) cluster_sync_all();                  // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const Sched sched(((p.m_tiles + CS - 1) / CS) * p.n_tiles,
-                      WGRAD ? p.wg_kiters : (CORRB ? p.TH + 2 * p.corr_r : p.R * p.S * p.kc_blocks), C::CHUNK,
-                      (int)blockIdx.x / CS, (int)gridDim.x / CS);
+    const int k_iters_ = WGRAD ? p.wg_kiters : (CORRB ? p.TH + 2 * p.corr_r : p.R * p.S * p.kc_blocks);
+    const Sched sched(((p.m_tiles + CS - 1) / CS) * p.n_tiles, k_iters_, unit_of(k_iters_, C::CHUNK), (int)blockIdx.x / CS,
+                      (int)gridDim.x / CS);
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
     // overlapped the tail of the previous layer; from here on we touch its output.
 #ifdef D2T_CONV_TRACE
@@ -1898,8 +1907,8 @@ bool sk_serialize(cudaStream_t stream) {
 
 // grid = one CTA per SM, fewer only when the layer has fewer K chunks than SMs
 int sk_grid(int tiles, int k_iters, int passes) {
-    const int chunk = chunk_of(passes);
-    const long long units = (long long)tiles * ((k_iters + chunk - 1) / chunk);
+    const int unit = unit_of(k_iters, chunk_of(passes));
+    const long long units = (long long)tiles * ((k_iters + unit - 1) / unit);
     return (int)(units < sm_count() ? units : sm_count());
 }
 }  // namespace
@@ -2088,7 +2097,7 @@ extern "C" d2t_conv_plan* d2t_conv_plan_create(const d2t_conv_desc* d, const flo
     pl->pair = (a.m_tiles >= 2 && ((!f16 && pair_env == 1) || pair_f16_ok)) ? 1 : 0;
     if (pl->pair) {
         const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
-        const int ch = chunk_of(d->passes);
+        const int ch = unit_of(a.R * a.S * a.kc_blocks, chunk_of(d->passes));
         const long long units = (long long)pair_tiles * ((a.R * a.S * a.kc_blocks + ch - 1) / ch);
         const int maxp = f16 ? max_pairs<128, 16>()
                              : (d->passes == 3 ? (pl->BN == 64 ? max_pairs<64, 3>() : max_pairs<128, 3>())

@@ -55,3 +55,15 @@ for i, t in enumerate(T):
     for r, nm in zip((0, 1, 2, 6), names):
         m = t[:, r, :5]
         print("      %-48s mean %s max-total %d" % (nm, [int(v) for v in m.mean(0)], int(m[:, 0].max())))
+
+# distribution of one (a) layer's main phase over the CTAs: who is the straggler?
+import numpy as np
+t = T[3]
+dur = (t[:, 6, 5] - t[:, 1, 5]).numpy()
+order = np.argsort(dur)
+print("layer 3 (a): main phase per CTA, sorted: min %d p25 %d median %d p75 %d p90 %d max %d" % tuple(np.percentile(dur, [0, 25, 50, 75, 90, 100])))
+print("slowest 12 CTAs (index: cycles, epilogue wait-tfull, post):", [(int(i), int(dur[i]), int(t[i, 6, 1]), int(t[i, 6, 2])) for i in order[-12:]])
+print("fastest 6 CTAs:", [(int(i), int(dur[i]), int(t[i, 6, 1]), int(t[i, 6, 2])) for i in order[:6]])
+mma = t[:, 1, :5].numpy()
+print("mma totals of the slowest 6:", [(int(i), [int(v) for v in mma[i]]) for i in order[-6:]])
+print("mma totals of the median 3:", [(int(i), [int(v) for v in mma[i]]) for i in order[72:75]])
