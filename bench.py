@@ -214,10 +214,15 @@ def op_microbench(flush, hbm_gbs):
                      "frac_hbm": alg / ms / 1e6 / hbm_gbs, "tflops_useful": flops / ms / 1e9,
                      "kernel": "conv_igemm CORR mode, 3xFP16 (kind::f16); 3xTF32 variant: %.4f ms" % ms_tf32,
                      "ms_3xtf32": ms_tf32, "ms_operator_api_nchw": ms_api, "ms_fp32_simt_kernel": ms_simt}
-        # backward: the exact-adjoint SIMT gather kernels behind the operator API (d2t_correlation_backward, both inputs)
+        # backward through the reference-layout operator, both inputs: banded GEMMs on the tensor cores (CORRB mode; re-layouts
+        # and operand packers included) against the exact-adjoint fp32 SIMT gather kernels it replaced
         go = torch.randn(Bc, oc, oh, ow, device="cuda")
         ms_bwd = time_kernel(lambda: ops.correlation_backward(a, b, go, *p), 5, flush)
-        out[name]["bwd_simt_gather_ms_both_inputs"] = ms_bwd
+        ops.TENSOR_CORE_CORRELATION = False
+        ms_bwd_simt = time_kernel(lambda: ops.correlation_backward(a, b, go, *p), 3, flush)
+        ops.TENSOR_CORE_CORRELATION = True
+        out[name]["bwd_operator_api_ms_both_inputs"] = ms_bwd
+        out[name]["bwd_simt_gather_ms_both_inputs"] = ms_bwd_simt
         out[name]["bwd_frac_hbm"] = 4.0 * (4 * C_ * Hh * Ww + oc * oh * ow) * Bc / ms_bwd / 1e6 / hbm_gbs
         del a, b, o, go, layer, layer3
     # fused PSRoI + 7x7 vote (+ softmax) on the model's own head shapes (4 frames x 300 RoIs, D = 31 classes / 4 deltas)

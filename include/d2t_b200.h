@@ -392,6 +392,10 @@ int d2t_conv_pack_weights_f16(const float* w_oihw, const float* scale, int Cout,
  * per pixel (the C source channels, then zeros); and back */
 int d2t_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,
                      float* out, cudaStream_t stream);
+/* d2t_nchw_to_nhwc with the tensor's max |x| folded into *amax (device float, zeroed by the caller; NaN-free inputs): the
+ * operand scale of a 3xFP16 consumer without a separate reduction pass. */
+int d2t_nchw_to_nhwc_amax(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,
+                          float* out, float* amax, cudaStream_t stream);
 int d2t_nhwc_to_nchw(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, float* out,
                      cudaStream_t stream);
 /* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on NHWC (faster_rcnn/resnet.py:120) */

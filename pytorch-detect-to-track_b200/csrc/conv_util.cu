@@ -63,6 +63,33 @@ nchw_to_nhwc(const float* __restrict__ x, int N, int C, int H, int W, int cs, in
     }
 }
 
+// the same with the tensor's max |x| folded into *amax (one atomicMax per block; values >= 0: unsigned order is float order)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_amax(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, int cw, float* __restrict__ out,
+                  float* __restrict__ amax) {
+    __shared__ float tile[32][33];
+    __shared__ unsigned int smax;
+    const int wt = blockIdx.x * 32, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / H, h = nh % H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (threadIdx.x == 0) smax = 0u;
+    float m = 0.f;
+    for (int j = ty; j < 32; j += 8) {
+        const int c = ct + j, w = wt + tx;
+        const float v = (c < C && w < W) ? __ldg(x + (((size_t)n * C + c) * H + h) * W + w) : 0.f;
+        tile[j][tx] = v;
+        m = fmaxf(m, fabsf(v));
+    }
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    __syncthreads();
+    if (tx == 0 && wm) atomicMax(&smax, wm);
+    for (int j = ty; j < 32; j += 8) {
+        const int w = wt + j, c = ct + tx;
+        if (w < W && c < cw) out[(((size_t)n * H + h) * W + w) * cs + coff + c] = tile[tx][j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && smax) atomicMax(reinterpret_cast<unsigned int*>(amax), smax);
+}
+
 // channels [coff, coff + C) of [N,H,W,cs] -> [N,C,H,W]
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw(const float* __restrict__ x, int N, int C, int H, int W, int cs, int coff, float* __restrict__ out) {
@@ -326,6 +353,18 @@ extern "C" int d2t_nchw_to_nhwc(const float* x, int N, int C, int H, int W, int 
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc: tensor too large for the launch grid");
     nchw_to_nhwc<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, c_width, out);
     D2T_CHECK_LAUNCH("nchw_to_nhwc");
+    return 1;
+}
+
+extern "C" int d2t_nchw_to_nhwc_amax(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, int c_width,
+                                     float* out, float* amax, cudaStream_t stream) {
+    D2T_REQUIRE(x && out && amax && N > 0 && C > 0 && H > 0 && W > 0 && c_offset >= 0 && c_width >= C &&
+                    c_stride >= c_offset + c_width,
+                "d2t_nchw_to_nhwc_amax: bad arguments");
+    dim3 grid((W + 31) / 32, (c_width + 31) / 32, N * H);
+    D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_nchw_to_nhwc_amax: tensor too large for the launch grid");
+    nchw_to_nhwc_amax<<<grid, 256, 0, stream>>>(x, N, C, H, W, c_stride, c_offset, c_width, out, amax);
+    D2T_CHECK_LAUNCH("nchw_to_nhwc_amax");
     return 1;
 }
 

@@ -64,10 +64,10 @@ def _p(t):
 class ActTensor(object):
     """[N, H, W, cstride] fp32; channels [0, C) are meaningful, the rest are zero."""
 
-    def __init__(self, N, H, W, C_, cstride=None, device="cuda", amax=None):
+    def __init__(self, N, H, W, C_, cstride=None, device="cuda", amax=None, zero=True):
         self.N, self.H, self.W, self.C = N, H, W, C_
         self.cstride = cstride if cstride is not None else (C_ + 3) // 4 * 4
-        self.x = torch.zeros(N, H, W, self.cstride, device=device)
+        self.x = (torch.zeros if zero else torch.empty)(N, H, W, self.cstride, device=device)
         arena = AmaxArena._active
         self.arena_owned = amax is None and arena is not None      # an engine zeroes it once per forward
         self.amax = amax if amax is not None else (arena.take() if arena is not None else torch.zeros(1, device=device))
@@ -77,6 +77,15 @@ class ActTensor(object):
         N, C_, H, W = x.shape
         t = ActTensor(N, H, W, C_, cstride if cstride is not None else _pad32(C_), x.device)
         return t.load_nchw(x, amax=amax)
+
+    def load_nchw_amax(self, x):
+        """the whole buffer <- x [N, C, H, W] (padding channels zero) and amax <- max |x|, in ONE launch after a 4-byte memset"""
+        N, C_, H, W = x.shape
+        self.amax.zero_()
+        check(lib().d2t_nchw_to_nhwc_amax(x.contiguous().data_ptr(), N, C_, H, W, self.cstride, 0, self.cstride,
+                                          self.x.data_ptr(), self.amax.data_ptr(), _stream()), "d2t_nchw_to_nhwc_amax")
+        ops._count(2)
+        return self
 
     def load_nchw(self, x, coffset=0, cwidth=None, amax=True):
         """write x [N, C, H, W] into channels [coffset, coffset + cwidth) (x's channels, then zeros)"""

@@ -149,6 +149,9 @@ def correlation_shape(H, W, pad, k, md, s1, s2):
     return out[0], out[1], out[2]
 
 
+_CORR_CACHE = {}      # (shape, pad, md, stride, passes, device) -> (x1, x2, CorrLayer); not for concurrent use from several threads
+
+
 def correlation_forward(in1, in2, pad, k, md, s1, s2):
     _req(in1, "input1"), _req(in2, "input2")
     if in1.shape != in2.shape:
@@ -160,8 +163,21 @@ def correlation_forward(in1, in2, pad, k, md, s1, s2):
         # fp32-accurate 3xFP16; the NCHW operands are first re-laid out as NHWC (+ each tensor's max |x| for its scale)
         from . import conv as dc
         with torch.cuda.device_of(in1):
-            x1, x2 = dc.ActTensor.from_nchw(in1), dc.ActTensor.from_nchw(in2)
-            return dc.CorrLayer(x1, x2, pad, md, s1, passes=CORRELATION_PASSES, want_nchw=True).run()
+            # plan + NHWC staging buffers are cached per (shape, parameters, device): a call is two re-layout launches (each
+            # folds its tensor's max |x| in), the correlation, and a copy out of the plan's fixed output buffer
+            key = (tuple(in1.shape), pad, md, s1, CORRELATION_PASSES, in1.device)
+            ent = _CORR_CACHE.get(key)
+            if ent is None:
+                x1 = dc.ActTensor(B, H, W, Cc, cstride=(Cc + 31) // 32 * 32, device=in1.device, zero=False)
+                x2 = dc.ActTensor(B, H, W, Cc, cstride=(Cc + 31) // 32 * 32, device=in1.device, zero=False)
+                layer = dc.CorrLayer(x1, x2, pad, md, s1, passes=CORRELATION_PASSES, want_nchw=True)
+                if len(_CORR_CACHE) >= 16:
+                    _CORR_CACHE.clear()
+                ent = _CORR_CACHE[key] = (x1, x2, layer)
+            x1, x2, layer = ent
+            x1.load_nchw_amax(in1)
+            x2.load_nchw_amax(in2)
+            return layer.run().clone()
     with torch.cuda.device_of(in1):
         out = torch.empty(B, oc, oh, ow, device=in1.device)
         check(lib().d2t_correlation_forward(in1.data_ptr(), in2.data_ptr(), B, Cc, H, W, pad, k, md, s1, s2,
@@ -170,9 +186,43 @@ def correlation_forward(in1, in2, pad, k, md, s1, s2):
     return out
 
 
+def _correlation_backward_tc(in1, in2, grad_out, pad, md, stride, need1, need2):
+    """Every D&T configuration (kernel_size 1, stride1 == stride2, pad == max_displacement): the gradients w.r.t. both
+    inputs as banded GEMMs on the tensor cores (csrc/conv.cu, CORRB; 3xFP16, fp32-accurate) -- 0.3 ms where the SIMT gather
+    kernels take 12 ms on conv4 (bench.py ops.corr_conv4).  The NCHW operands are re-laid out as NHWC first; for stride 2
+    the gradient lives on the even positions of the input (the correlation lattice), the rest is zero."""
+    from . import conv as dc
+    B, Cc, H, W = in1.shape
+    r = md // stride
+    Hl, Wl = -(-H // stride), -(-W // stride)
+    x1, x2 = dc.ActTensor.from_nchw(in1), dc.ActTensor.from_nchw(in2)
+    g = dc.ActTensor.from_nchw(grad_out)
+    scratch = dc.CorrBwdScratch(*dc.CorrBwdScratch.need(B, Cc, Hl, Wl, r), device=in1.device)
+    outs = []
+    for which, need, other in ((1, need1, x2), (2, need2, x1)):
+        if not need:
+            outs.append(None)
+            continue
+        lat = dc.ActTensor(B, Hl, Wl, Cc, cstride=(Cc + 3) // 4 * 4, device=in1.device)
+        dc.CorrBwdLayer(g, 0, other, lat, md, stride, which, scratch).run()
+        low = lat.to_nchw()
+        if stride == 1:
+            outs.append(low)
+        else:
+            full = torch.zeros(B, Cc, H, W, device=in1.device)
+            full[:, :, ::stride, ::stride] = low
+            _count(2)
+            outs.append(full)
+    return outs[0], outs[1]
+
+
 def correlation_backward(in1, in2, grad_out, pad, k, md, s1, s2, need1=True, need2=True):
     _req(in1, "input1"), _req(in2, "input2"), _req(grad_out, "grad_output")
     B, Cc, H, W = in1.shape
+    if (k == 1 and s1 == s2 and pad == md and 1 <= md // s2 <= 8 and md % s2 == 0 and Cc >= 32 and Cc % 4 == 0
+            and TENSOR_CORE_CORRELATION):
+        with torch.cuda.device_of(in1):
+            return _correlation_backward_tc(in1, in2, grad_out, pad, md, s1, need1, need2)
     with torch.cuda.device_of(in1):
         g1 = torch.empty_like(in1) if need1 else None
         g2 = torch.empty_like(in2) if need2 else None

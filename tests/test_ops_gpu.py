@@ -400,6 +400,27 @@ def test_correlation_backward_full_size_vs_reference_kernel():
     assert float(g2[:, :, 1::2, :].abs().max()) == 0.0 and float(g2[:, :, :, 1::2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("C,H,W,p,B", [(1024, 38, 63, (8, 1, 8, 1, 1), 2), (512, 75, 125, (8, 1, 8, 2, 2), 2), (96, 21, 30, (4, 1, 4, 1, 1), 3)])
+def test_correlation_backward_tensor_core_path_vs_simt(C, H, W, p, B):
+    """ops.correlation_backward takes the tensor-core banded-GEMM path (CORRB) for every D&T configuration; the exact-adjoint
+    fp32 SIMT gather kernels are the comparator (both deterministic)."""
+    torch.manual_seed(13)
+    a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    out = ops.correlation_forward(a, b, *p)
+    g = torch.randn_like(out)
+    t1, t2 = ops.correlation_backward(a, b, g, *p)
+    ops.TENSOR_CORE_CORRELATION = False
+    try:
+        s1, s2 = ops.correlation_backward(a, b, g, *p)
+    finally:
+        ops.TENSOR_CORE_CORRELATION = True
+    for t_, s_ in ((t1, s1), (t2, s2)):
+        assert t_.shape == s_.shape
+        assert float((t_ - s_).abs().max() / s_.abs().max()) < 2e-5
+    only1, none2 = ops.correlation_backward(a, b, g, *p, need2=False)
+    assert none2 is None and torch.equal(only1, t1)
+
+
 def test_correlation_adjoint_property():
     """<corr(a,b), g> is bilinear: d/da <out, g> = grad1 exactly => <out, g> == <a, grad1> == <b, grad2>."""
     torch.manual_seed(12)
