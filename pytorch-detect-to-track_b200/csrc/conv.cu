@@ -74,11 +74,16 @@ constexpr int kChunkC = 256;       // channels (x taps) accumulated in TMEM befo
 // channels per K block / K blocks per TMEM chunk for a given operand mode (PASSES: 1 = TF32, 3 = 3xTF32, 16 = 3xFP16)
 __host__ __device__ constexpr int kblk_of(int passes) { return passes == 16 ? 64 : 32; }
 __host__ __device__ constexpr int chunk_of(int passes) { return kChunkC / kblk_of(passes); }
-// Stream-K work unit in K blocks.  Tiles of at most one chunk stay whole (the short-K layers: their epilogue variants assume
-// it); everything else is dealt out K BLOCK by K block -- with whole chunks as units, 608 chunks on 148 CTAs left 16 CTAs
-// with 5 chunks against 4 (measured: those CTAs set the layer's time, profiles/r02_chain_timeline_trace.txt); a segment may
-// now start or end inside a chunk, the accumulation chunks stay aligned to absolute K positions.
+// Stream-K work unit in K blocks: one accumulation chunk.  The scheduler and every role take any unit (a segment may start
+// or end inside a chunk; the accumulation chunks stay aligned to absolute K positions), and units of ONE K block were
+// measured: 608 chunks on 148 CTAs leave 16 CTAs with 5 chunks against 4, which K-block units even out -- but the layer
+// times did not move (5.57 -> 5.55 ms per step, within noise: the stragglers are the CTAs with two fix-up epilogues, not
+// the ones with an extra chunk, profiles/r02_chain_timeline_trace.txt), so the unit stays the chunk.
+#ifndef D2T_SK_UNIT_KBLOCK
+__host__ __device__ constexpr int unit_of(int /*k_iters*/, int chunk) { return chunk; }
+#else
 __host__ __device__ constexpr int unit_of(int k_iters, int chunk) { return k_iters <= chunk ? chunk : 1; }
+#endif
 
 struct ConvArgs {
     int N, OH, OW, Cout;
@@ -803,7 +808,8 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                         if (is_a) {
                             // stem: filter row r = 32 consecutive floats (8 pixels x 4 channels) of padded input row
                             // 2*oh + r starting at padded pixel 2*ow; rows are indexed (pair, parity)
-                            if (stem) tma_load_5d(dst, map, fbar, 0, ow0, r & 1, oh0 + (r >> 1), img);
+                            // (3xFP16: a K block = TWO filter rows, one per 32-float sub-tile: rows 2r and 2r + 1)
+                            if (stem) tma_load_5d(dst, map, fbar, 0, ow0, (F16 ? 2 * r + lane : r) & 1, oh0 + ((F16 ? 2 * r + lane : r) >> 1), img);
                             else tma_load_4d(dst, map, fbar, kc * kBlockK + a_c0, iw0 + s * dil, ih0 + r * dil, img);
                         } else if (CORR) {
                             tma_load_4d(dst, map, fbar, kc * kBlockK + (F16 ? (lane - NA) * kBoxC : 0), bw0, bh0, img);
@@ -2173,10 +2179,12 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
                                                     const float* w_hi, const float* w_lo, const float* scale,
                                                     const float* shift, int relu, float* out, int out_cstride) {
     if (N <= 0 || H < 7 || W < 7 || Cout <= 0 || !in || !w_hi || !out || out_cstride % 4 != 0 ||
-        (passes != 1 && passes != 3) || (passes == 3 && !w_lo)) {
-        set_error("d2t_conv_stem_plan_create: bad arguments");
+        (passes != 1 && passes != 3 && passes != 16) || (passes != 1 && !w_lo) || (passes == 16 && (scale || Cout > 64))) {
+        set_error("d2t_conv_stem_plan_create: bad arguments (passes = 16: fp16 (hi, lo) weights [Cout][4][64] with the scale "
+                  "folded in, Cout <= 64, then d2t_conv_plan_set_amax + d2t_conv_plan_set_weight_amax)");
         return nullptr;
     }
+    const bool f16 = passes == 16;
     const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
     const int Hp = (H + 7) & ~1, Wp = W + 8;                  // padded buffer geometry (d2t_stem_pack_input)
     int twl = 0;
@@ -2190,7 +2198,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     d2t_conv_plan* pl = new (mem) d2t_conv_plan();
     ConvArgs& a = pl->args;
     a.N = N; a.OH = OH; a.OW = OW; a.Cout = Cout;
-    a.R = 7; a.S = 1; a.stride = 2; a.pad = 3; a.dil = 1; a.kc_blocks = 1;
+    a.R = f16 ? 4 : 7; a.S = 1; a.stride = 2; a.pad = 3; a.dil = 1; a.kc_blocks = 1;   // 3xFP16: K blocks of two filter rows
     a.TW_log2 = twl; a.TH = TH; a.stem = 1;
     a.tiles_w = (OW + TW - 1) / TW; a.tiles_h = (OH + TH - 1) / TH;
     a.m_tiles = N * a.tiles_h * a.tiles_w;
@@ -2200,7 +2208,7 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     a.out = out; a.out_cstride = out_cstride; a.out_coffset = 0; a.out_nchw = nullptr;
     pl->passes = passes; pl->corr = 0; pl->pair = 0;
     a.amax_in = nullptr; a.amax_out = nullptr; a.w_exp = 0; a.trace = nullptr; a.exp = 0; a.done_prev = nullptr; a.done_target = 0; a.done_self = nullptr;
-    pl->grid = sk_grid(a.m_tiles * a.n_tiles, 7, passes);
+    pl->grid = sk_grid(a.m_tiles * a.n_tiles, a.R, passes);
     {
         SkScratch sk;
         if (!sk_scratch(&sk)) {
@@ -2214,13 +2222,13 @@ extern "C" d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cou
     const cuuint64_t astr[4] = {32, row, 2 * row, (cuuint64_t)Hp * row};
     const cuuint32_t abox[5] = {32u, (cuuint32_t)TW, 1u, (cuuint32_t)TH, 1u};
     const cuuint32_t aestr[5] = {1u, 1u, 1u, 1u, 1u};
-    const cuuint64_t bdims[2] = {7 * 32, (cuuint64_t)Cout};
-    const cuuint64_t bstr[1] = {7 * 32 * 4};
-    const cuuint32_t bbox[2] = {32u, (cuuint32_t)pl->BN};
+    const cuuint64_t bdims[2] = {(cuuint64_t)(f16 ? 4 * 64 : 7 * 32), (cuuint64_t)Cout};
+    const cuuint64_t bstr[1] = {(cuuint64_t)(f16 ? 4 * 64 * 2 : 7 * 32 * 4)};
+    const cuuint32_t bbox[2] = {f16 ? 64u : 32u, (cuuint32_t)pl->BN};
     const cuuint32_t bestr[2] = {1u, 1u};
     bool ok = encode(&pl->tmA, in, 5, adims, astr, abox, aestr, "stem A") &&
-              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "stem B hi");
-    if (ok && passes == 3) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "stem B lo");
+              encode(&pl->tmB_hi, w_hi, 2, bdims, bstr, bbox, bestr, "stem B hi", f16);
+    if (ok && passes != 1) ok = encode(&pl->tmB_lo, w_lo, 2, bdims, bstr, bbox, bestr, "stem B lo", f16);
     if (ok && passes == 1) pl->tmB_lo = pl->tmB_hi;
     if (ok) ok = encode_out_map(&pl->tmO, out, N, OH, OW, Cout, out_cstride, 0, TH, TW);
     if (!ok) {

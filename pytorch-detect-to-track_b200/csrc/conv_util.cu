@@ -34,6 +34,30 @@ __global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H
     }
 }
 
+// the same with max |x| folded into *amax (the 3xFP16 stem's operand scale)
+__global__ void __launch_bounds__(256)
+stem_pack_input_amax(const float* __restrict__ x, int N, int C, int H, int W, int Hp, int Wp, float4* __restrict__ out,
+                     float* __restrict__ amax) {
+    const size_t total = (size_t)N * Hp * Wp;
+    float m = 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int wp = (int)(idx % Wp), hp = (int)((idx / Wp) % Hp), n = (int)(idx / Wp / Hp);
+        const int h = hp - 3, w = wp - 3;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (h >= 0 && h < H && w >= 0 && w < W)
+            for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)n * C + c) * H + h) * W + w);
+        out[idx] = make_float4(v[0], v[1], v[2], v[3]);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+    }
+    __shared__ unsigned int smax;
+    if (threadIdx.x == 0) smax = 0u;
+    __syncthreads();
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && wm) atomicMax(&smax, wm);
+    __syncthreads();
+    if (threadIdx.x == 0 && smax) atomicMax(reinterpret_cast<unsigned int*>(amax), smax);
+}
+
 // stem weights [O, C<=4, 7, 7] -> [O][7 rows][32] with column s*4 + c (zeros elsewhere)
 __global__ void stem_pack_weights(const float* __restrict__ w, int O, int C, float* __restrict__ hi, float* __restrict__ lo) {
     const int total = O * 7 * 32;
@@ -497,6 +521,16 @@ extern "C" int d2t_stem_pack_input(const float* x, int N, int C, int H, int W, f
     const size_t total = (size_t)N * Hp * Wp;
     stem_pack_input<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(packed));
     D2T_CHECK_LAUNCH("stem_pack_input");
+    return 1;
+}
+
+extern "C" int d2t_stem_pack_input_amax(const float* x, int N, int C, int H, int W, float* packed, float* amax,
+                                        cudaStream_t stream) {
+    D2T_REQUIRE(x && packed && amax && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "d2t_stem_pack_input_amax: bad arguments");
+    const int Hp = (H + 7) & ~1, Wp = W + 8;
+    const size_t total = (size_t)N * Hp * Wp;
+    stem_pack_input_amax<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(packed), amax);
+    D2T_CHECK_LAUNCH("stem_pack_input_amax");
     return 1;
 }
 

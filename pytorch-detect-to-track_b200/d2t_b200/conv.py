@@ -489,39 +489,72 @@ def upsample2_add_mask(low, out, extra=None, mask=None):
 
 class StemConv(_Planned):
     """conv1 7x7 / stride 2 / pad 3 (+ folded bn1 + ReLU) on the tcgen05 kernel via the row-window TMA map
-    (csrc/conv.cu: d2t_conv_stem_plan_create)."""
+    (csrc/conv.cu: d2t_conv_stem_plan_create).  passes = 16 (3xFP16): a K block is TWO filter rows, the weights are packed
+    once as fp16 (hi, lo) with the BatchNorm scale folded in, and the image's max |x| (its operand scale) comes out of the
+    input packing kernel."""
 
     def __init__(self, N, H, W, weight, scale, shift, relu=True, passes=3, device="cuda"):
         O, I, R, S = weight.shape
         assert (R, S) == (7, 7) and I <= 4
-        self.N, self.C, self.H, self.W = N, I, H, W
+        self.N, self.C, self.H, self.W, self.passes = N, I, H, W, passes
         Hp, Wp = (H + 7) & ~1, W + 8
         self.packed = torch.empty(N, Hp, Wp, 4, device=device)
-        self.w_hi = torch.empty(O, 7 * 32, device=device)
-        self.w_lo = torch.empty(O, 7 * 32, device=device)
+        w32 = torch.empty(O, 7 * 32, device=device)
+        w32_lo = torch.empty(O, 7 * 32, device=device)
         w = weight.detach().float().contiguous()
-        check(lib().d2t_stem_pack_weights(w.data_ptr(), O, I, self.w_hi.data_ptr(), self.w_lo.data_ptr(), _stream()),
+        check(lib().d2t_stem_pack_weights(w.data_ptr(), O, I, w32.data_ptr(), w32_lo.data_ptr(), _stream()),
               "d2t_stem_pack_weights")
         torch.cuda.current_stream().synchronize()   # `w` may be a temporary
         self.scale = scale.detach().float().contiguous().to(device) if scale is not None else None
         self.shift = shift.detach().float().contiguous().to(device) if shift is not None else None
         OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         self.out = ActTensor(N, OH, OW, O, device=device)
+        if passes == 16:
+            ws = F_pad_rows(w32 * (self.scale.view(-1, 1) if self.scale is not None else 1.0))      # [O][8 rows x 32] = [O][4][64]
+            wmax = float(ws.abs().max())
+            w_exp = max(-100, min(100, 15 - math.frexp(wmax)[1])) if wmax > 0 and math.isfinite(wmax) else 0
+            ws = ws * (2.0 ** w_exp)
+            self.w_hi = ws.half().contiguous()                                     # (hi, lo) as the weight packers split: rn, rn
+            self.w_lo = (ws - self.w_hi.float()).half().contiguous()
+            self.amax_w = torch.full((1,), wmax, device=device)                    # the kernel derives the same 2^k from it
+            arena = AmaxArena._active
+            self.amax_in = arena.take() if arena is not None else torch.zeros(1, device=device)
+            self._own_amax_in = arena is None
+            plan_scale = None
+        else:
+            self.w_hi, self.w_lo, plan_scale = w32, w32_lo, self.scale
         self.plan = lib().d2t_conv_stem_plan_create(N, H, W, O, passes, _p(self.packed), _p(self.w_hi), _p(self.w_lo),
-                                                    _p(self.scale), _p(self.shift), int(relu), _p(self.out.x),
+                                                    _p(plan_scale), _p(self.shift), int(relu), _p(self.out.x),
                                                     self.out.cstride)
         if not self.plan:
             raise D2TError("d2t_conv_stem_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * N * OH * OW * O * I * 49
-        self._bind_amax(None, self.out)
+        if passes == 16:
+            check(lib().d2t_conv_plan_set_amax(self.plan, _p(self.amax_in), _p(self.out.amax)), "d2t_conv_plan_set_amax")
+            check(lib().d2t_conv_plan_set_weight_amax(self.plan, _p(self.amax_w)), "d2t_conv_plan_set_weight_amax")
+            if not self.out.arena_owned:
+                self.zero_amax = self.out.amax
+        else:
+            self._bind_amax(None, self.out)
 
     def run(self, x):
         """x: [N, C, H, W] fp32 image batch"""
-        check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(), _stream()),
-              "d2t_stem_pack_input")
+        if self.passes == 16:
+            if self._own_amax_in:
+                self.amax_in.zero_()
+            check(lib().d2t_stem_pack_input_amax(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(),
+                                                 self.amax_in.data_ptr(), _stream()), "d2t_stem_pack_input_amax")
+        else:
+            check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(), _stream()),
+                  "d2t_stem_pack_input")
         ops._count(1)
         _Planned.run(self)
         return self.out
+
+
+def F_pad_rows(w32):
+    """[O][7 rows x 32] -> [O][8 rows x 32] (a zero eighth filter row: 3xFP16 K blocks are pairs of rows)"""
+    return torch.cat([w32, torch.zeros(w32.size(0), 32, device=w32.device)], 1).contiguous()
 
 
 class CorrLayer(_Planned):

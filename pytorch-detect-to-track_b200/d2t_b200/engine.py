@@ -78,7 +78,8 @@ class D2TEngine(object):
     def _build(self, net, pairs, height, width, passes, cfg_key, keep_features):
         from model.utils.config import cfg
         self.net, self.B, self.H, self.W, self.passes = net, pairs, height, width, passes
-        tf32_passes = 3 if passes == 16 else passes     # stem (3 input channels) and correlations: TF32 kinds only
+        # the 3-channel stem: 3xFP16 too (K blocks of two filter rows); D2T_STEM_PASSES=3 keeps the 3xTF32 kernel (A/B runs)
+        tf32_passes = passes if passes != 16 else int(os.environ.get("D2T_STEM_PASSES", "16"))
         self.cfg_key = cfg_key
         self.keep_features = keep_features   # also emit conv3/4/5 as plain NCHW (tests / inspection)
         self.post_nms = cfg[cfg_key].RPN_POST_NMS_TOP_N

@@ -107,14 +107,15 @@ def test_maxpool_ceil_mode():
     assert out.shape == want.shape == (1, 64, 150, 250) and torch.equal(out, want)
 
 
-def test_stem_conv_7x7_stride2():
+@pytest.mark.parametrize("passes", [3, 16])
+def test_stem_conv_7x7_stride2(passes):
     g = torch.Generator(device="cuda").manual_seed(5)
     for (N, H, W) in [(1, 64, 96), (2, 75, 101), (1, 600, 1000)]:
         x = torch.rand(N, 3, H, W, device="cuda", generator=g) * 256 - 128
         w = torch.randn(64, 3, 7, 7, device="cuda", generator=g) * (2.0 / (49 * 64)) ** 0.5
         scale = torch.rand(64, device="cuda", generator=g) + 0.5
         shift = torch.randn(64, device="cuda", generator=g)
-        stem = dc.StemConv(N, H, W, w, scale, shift, relu=True, passes=3)
+        stem = dc.StemConv(N, H, W, w, scale, shift, relu=True, passes=passes)
         out = stem.run(x).to_nchw()
         want = _ref(x, w, scale, shift, 2, 3, 1, True, None)
         assert out.shape == want.shape
