@@ -62,6 +62,9 @@ class D2TEngine(object):
         if os.environ.get("D2T_CONV_EARLY_B", "1") != "0" and type(self) is D2TEngine:
             for layer in self.layers + [self.trk_layer]:       # weights packed once at build time: nothing upstream writes them
                 layer.set_early_weights(True)
+        # the engine computes with PACKED copies of the parameters (folded BatchNorm, fp16 operand pairs): remember their
+        # version counters so that a later load_state_dict / optimizer step is noticed instead of silently ignored
+        self._param_versions = self._versions()
         if chain is None:
             chain = os.environ.get("D2T_CONV_CHAIN", "0") == "1"
         # the launch list of forward(): with chains, maximal runs of plain 3xFP16 layers collapse into one launch each
@@ -158,6 +161,16 @@ class D2TEngine(object):
                 1: "kind::tf32 x1 pass"}[passes]
         self.conv_backend = "d2t_b200 tcgen05 implicit GEMM, %s, TMA-fed, fused BN/ReLU/residual" % kind
 
+    def _versions(self):
+        return tuple(t._version for t in list(self.net.parameters()) + list(self.net.buffers()))
+
+    def check_fresh(self):
+        """raise if a parameter or BatchNorm buffer of the module was modified in place after the engine packed it
+        (load_state_dict, an optimizer step, .data.copy_): rebuild the engine -- or use D2TTrainEngine, which re-packs"""
+        if self._param_versions is not None and self._versions() != self._param_versions:
+            raise RuntimeError("D2TEngine: the module's parameters changed after the engine was built (it computes with packed "
+                               "copies); build a new engine after load_state_dict / parameter updates")
+
     # ------------------------------------------------------------------ construction helpers
     def _make_layer(self, x, weight, scale, shift, stride=1, pad=0, dil=1, relu=False, residual=None, **kw):
         """the one place a convolution plan is created (the training engine overrides it)"""
@@ -194,6 +207,7 @@ class D2TEngine(object):
     @torch.no_grad()
     def forward(self, im_data, im_info):
         """im_data [B, 2, 3, H, W], im_info [B, 2, 3] (CUDA fp32) -> the reference's 10-tuple (eval)."""
+        self.check_fresh()
         info = self._begin(im_data, im_info)
         if not self.fork:
             for item in self.run_list:
@@ -357,6 +371,8 @@ class GraphedEngine(object):
     def forward(self, im_data, im_info):
         self.im_data.copy_(im_data, non_blocking=True)
         self.im_info.copy_(im_info, non_blocking=True)
+        for eng in getattr(self.engine, "engines", [self.engine]):
+            eng.check_fresh()
         if self.graph is None:
             self._capture()
         self.graph.replay()

@@ -45,6 +45,7 @@ class D2TTrainEngine(D2TEngine):
         self._smax = torch.ones(512, device=dev)
         self._weights = []
         D2TEngine.__init__(self, net, pairs, height, width, passes=16, cfg_key="TRAIN", keep_features=True)
+        self._param_versions = None        # (this engine re-packs its weights after every optimizer step: refresh_weights)
         self.bucket_bytes = bucket_bytes
         with self.amax:
             self._build_backward()

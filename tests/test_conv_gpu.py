@@ -465,3 +465,21 @@ def test_engine_chain_bit_identical():
         torch.cuda.synchronize()
         for a, b in zip(want, out):
             assert torch.equal(a, b)
+
+
+def test_engine_notices_stale_parameters():
+    """the engine computes with packed copies of the parameters: an in-place update after it was built must raise, not be
+    silently ignored"""
+    from model.faster_rcnn.resnet import resnet
+    from d2t_b200.engine import D2TEngine
+    torch.manual_seed(3)
+    net = resnet(tuple(range(31)), 50, class_agnostic=True).create_architecture().cuda().eval()
+    B, H, W = 1, 160, 224
+    im_data = torch.zeros(B, 2, 3, H, W, device="cuda")
+    im_info = torch.tensor([H, W, 1.0]).view(1, 1, 3).expand(B, 2, 3).contiguous().cuda()
+    eng = D2TEngine(net, B, H, W)
+    eng(im_data, im_info)
+    net.load_state_dict(net.state_dict())          # (same values, but written in place)
+    with pytest.raises(RuntimeError):
+        eng(im_data, im_info)
+    D2TEngine(net, B, H, W)(im_data, im_info)      # a fresh engine is fine
