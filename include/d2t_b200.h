@@ -210,6 +210,14 @@ int d2t_proposal_gather(const float* boxes, const float* scores, const int64_t* 
                         int B, int n_total, int order_stride, int n_take, float* dets,
                         cudaStream_t stream);
 /* rois [B, post, 5]: col 0 = image index, rows >= num_keep[b] zero (proposal_layer.py:127,158-159) */
+/* Top-N selection + stable descending sort + gather in one launch: dets[b][j] = (box, score) of the j-th highest score of
+ * image b -- exactly what a stable descending sort of all scores (ties in index order, NaN first: torch.sort) followed by
+ * d2t_proposal_gather of the first n_take produces (proposal_layer.py:115-137), without sorting the other ~80 % of the list.
+ * One CTA per image: radix select (keys in registers), compaction, bitonic sort in shared memory.  n_take <= n_total <= 32768,
+ * n_take <= 16384 (d2t_proposal_topk_supported). */
+int d2t_proposal_topk_supported(int n_total, int n_take);
+int d2t_proposal_topk_gather(const float* boxes, const float* scores, int B, int n_total, int n_take, float* dets,
+                             cudaStream_t stream);
 int d2t_proposal_write_rois(const float* dets, const int* keep, int keep_stride,
                             const int* num_keep, int B, int n_take, int post, float* rois,
                             cudaStream_t stream);

@@ -89,6 +89,199 @@ __global__ void proposal_write_rois(const float* __restrict__ dets, const int* _
     }
 }
 
+// ---- top-N selection + stable descending sort + gather in ONE kernel (proposal_layer.py:115-137: the reference sorts all
+// ~29 k scores of an image and keeps the first pre_nms_topN; here torch.sort -- a cub segmented radix sort over everything --
+// and proposal_gather become one launch).  One 1024-thread CTA per image:
+//   1. radix select (4 passes of 8 bits, per-warp histograms, equal keys of a warp aggregated with match.any) finds the
+//      n_take-th key in descending order and how many of its equals are needed;
+//   2. compaction: every score above the threshold, and the first `needed` equal ones in index order, as 64-bit composites
+//      (descending-order key << 32 | index) in shared memory;
+//   3. bitonic sort of the composites (all distinct: equal scores stay in index order = torch.sort(stable=True));
+//   4. gather: dets[b][j] = (box, score) of the j-th composite.
+// Keys: float bits mapped so that unsigned ascending order = descending float order; +-0 compare equal and NaN sorts first,
+// as in torch.
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMaxList = 16384;
+constexpr int kTopkKeysPerThread = 32;                            // the image's keys stay in registers: n_total <= 32768
+
+__device__ __forceinline__ uint32_t desc_key(float s) {
+    uint32_t u = __float_as_uint(s);
+    if ((u << 1) == 0u) u = 0u;                                   // -0 -> +0
+    if ((u & 0x7fffffffu) > 0x7f800000u) u = 0x7fc00000u;         // every NaN is the largest value
+    const uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending float order
+    return ~k;                                                    // descending
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+proposal_topk_gather(const float* __restrict__ boxes, const float* __restrict__ scores, int n_total, int n_take, int P,
+                     float* __restrict__ dets) {
+    extern __shared__ unsigned long long list[];                  // [P] composites
+    __shared__ uint32_t whist[32][256];                           // per-warp histograms
+    __shared__ uint32_t s_prefix, s_remaining, s_cnt, s_eqbase;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* sc = scores + (size_t)b * n_total;
+    // element i = r * 1024 + tid lives in key[r] (coalesced loads; "index order" = r ascending, then tid ascending)
+    uint32_t key[kTopkKeysPerThread];
+#pragma unroll
+    for (int r = 0; r < kTopkKeysPerThread; ++r) {
+        const int i = r * kTopkThreads + tid;
+        key[r] = i < n_total ? desc_key(__ldg(sc + i)) : 0xffffffffu;      // (no real key is all ones)
+    }
+    const int nr = (n_total + kTopkThreads - 1) / kTopkThreads;   // rounds that hold elements
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)n_take;
+    const bool all = n_take >= n_total;
+    if (!all) {
+        for (int pass = 3; pass >= 0; --pass) {
+            for (int i = tid; i < 32 * 256; i += kTopkThreads) (&whist[0][0])[i] = 0u;
+            __syncthreads();
+            const int shift = 8 * pass;
+#pragma unroll
+            for (int r = 0; r < kTopkKeysPerThread; ++r) {
+                if (r < nr) {                                     // (uniform)
+                    const uint32_t kd = key[r];
+                    const bool in = kd != 0xffffffffu && (kd & mask) == prefix;
+                    const uint32_t bin = (kd >> shift) & 255u;
+                    // the leading digits of neighbouring scores mostly agree: one add for a warp whose lanes share the bin
+                    const uint32_t act = __ballot_sync(0xffffffffu, in);
+                    if (act) {
+                        const uint32_t ref = __shfl_sync(0xffffffffu, bin, __ffs(act) - 1);
+                        const uint32_t agree = __ballot_sync(0xffffffffu, in && bin == ref);
+                        if (agree == act) {
+                            if (lane == 0) whist[warp][ref] += __popc(act);
+                        } else if (in) {
+                            atomicAdd(&whist[warp][bin], 1u);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t t = 0;
+#pragma unroll 8
+                for (int w = 0; w < 32; ++w) t += whist[w][tid];
+                whist[0][tid] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // 256 bins, 8 per lane: find the bin in which the running count reaches `remaining`
+                uint32_t h[8], local = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    h[q] = whist[0][lane * 8 + q];
+                    local += h[q];
+                }
+                uint32_t incl = local;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                const uint32_t excl = incl - local;
+                const bool mine = excl < remaining && remaining <= incl;       // exactly one lane (total >= remaining)
+                if (mine) {
+                    uint32_t cum = excl, sel = 7;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (cum + h[q] >= remaining) {
+                            sel = q;
+                            break;
+                        }
+                        cum += h[q];
+                    }
+                    s_prefix = prefix | ((uint32_t)(lane * 8 + sel) << shift);
+                    s_remaining = remaining - cum;
+                }
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            remaining = s_remaining;
+            mask |= 255u << shift;
+        }
+    }
+    // prefix = the threshold key T; `remaining` = how many scores equal to T are taken (the first ones in index order)
+    if (tid == 0) {
+        s_cnt = 0u;
+        s_eqbase = 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTopkKeysPerThread; ++r) {
+        if (r < nr) {
+            const int i = r * kTopkThreads + tid;
+            const uint32_t kd = key[r];
+            const bool real = kd != 0xffffffffu;
+            const bool lt = real && (all || kd < prefix);
+            const bool eq = real && !all && kd == prefix;
+            // elements above the threshold: any slot (the sort follows); one counter add per warp
+            const uint32_t blt = __ballot_sync(0xffffffffu, lt);
+            uint32_t base = 0;
+            if (lane == 0 && blt) base = atomicAdd(&s_cnt, (uint32_t)__popc(blt));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lt) list[base + __popc(blt & ((1u << lane) - 1u))] = ((unsigned long long)kd << 32) | (uint32_t)i;
+            // equal elements: strictly in index order -> block-wide exclusive count of the round (rare: skipped when the
+            // whole block has none)
+            const uint32_t beq = __ballot_sync(0xffffffffu, eq);
+            if (__syncthreads_or(beq != 0u)) {
+                if (lane == 0) whist[1][warp] = (uint32_t)__popc(beq);
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t v = whist[1][lane], incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += n;
+                    }
+                    whist[2][lane] = incl - v;                     // exclusive prefix of the warps
+                    if (lane == 31) whist[3][0] = incl;            // round total
+                }
+                __syncthreads();
+                if (eq) {
+                    const uint32_t rank = s_eqbase + whist[2][warp] + __popc(beq & ((1u << lane) - 1u));
+                    if (rank < remaining) {
+                        const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                        list[pos] = ((unsigned long long)kd << 32) | (uint32_t)i;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_eqbase += whist[3][0];
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = (int)s_cnt;                            // == n_take
+    for (int i = cnt + tid; i < P; i += kTopkThreads) list[i] = ~0ull;
+    __syncthreads();
+    // bitonic sort, ascending.  Stages whose partner distance is < 32 stay inside a warp's 64 consecutive elements... kept
+    // simple: every stage goes through shared memory, one barrier per stage
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            // thread t handles comparator t of each group of 1024: i = element with bit j clear
+            for (int c = tid; c < (P >> 1); c += kTopkThreads) {
+                const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+                const int l = i | j;
+                const unsigned long long a = list[i], d = list[l];
+                const bool up = (i & k) == 0;
+                if ((a > d) == up) {
+                    list[i] = d;
+                    list[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < n_take; j += kTopkThreads) {
+        const uint32_t src = (uint32_t)(list[j] & 0xffffffffull);
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float v = 0.f;
+        if (j < cnt && src < (uint32_t)n_total) {
+            bx = reinterpret_cast<const float4*>(boxes)[(size_t)b * n_total + src];
+            v = sc[src];
+        }
+        float* o = dets + ((size_t)b * n_take + j) * 5;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = v;
+    }
+}
+
 inline int grid_for(size_t total) {
     size_t blocks = (total + 255) / 256, cap = (size_t)sm_count() * 8;
     return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
@@ -129,5 +322,28 @@ extern "C" int d2t_proposal_write_rois(const float* dets, const int* keep, int k
     proposal_write_rois<<<grid_for((size_t)B * post), 256, 0, stream>>>(dets, keep, keep_stride, num_keep, B, n_take,
                                                                        post, rois);
     D2T_CHECK_LAUNCH("proposal_write_rois");
+    return 1;
+}
+
+// 1 if d2t_proposal_topk_gather takes this problem (the sorted list must fit one CTA's shared memory)
+extern "C" int d2t_proposal_topk_supported(int n_total, int n_take) {
+    int P = 1;
+    while (P < n_take) P <<= 1;
+    return n_total > 0 && n_total <= kTopkKeysPerThread * kTopkThreads && n_take > 0 && n_take <= n_total && P <= kTopkMaxList ? 1 : 0;
+}
+
+// dets[b][j] = (x1, y1, x2, y2, score) of the j-th highest score of image b, j < n_take: what torch.sort(scores, 1,
+// descending=True, stable=True)[1][:, :n_take] followed by d2t_proposal_gather produces (proposal_layer.py:115-137).
+extern "C" int d2t_proposal_topk_gather(const float* boxes, const float* scores, int B, int n_total, int n_take, float* dets,
+                                        cudaStream_t stream) {
+    D2T_REQUIRE(B > 0 && boxes && scores && dets && ((uintptr_t)boxes & 15) == 0 && d2t_proposal_topk_supported(n_total, n_take),
+                "d2t_proposal_topk_gather: bad arguments (n_take <= n_total, n_take <= 16384, boxes 16-byte aligned)");
+    int P = 1;
+    while (P < n_take) P <<= 1;
+    const size_t smem = (size_t)P * 8;
+    static SmemAttrOnce once;
+    if (!once.ensure(proposal_topk_gather, kTopkMaxList * 8, "proposal_topk_gather smem attr")) return 0;
+    proposal_topk_gather<<<B, kTopkThreads, smem, stream>>>(boxes, scores, n_total, n_take, P, dets);
+    D2T_CHECK_LAUNCH("proposal_topk_gather");
     return 1;
 }

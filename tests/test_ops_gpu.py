@@ -622,3 +622,51 @@ def test_correlation_backward_legacy_launcher_symbol():
         g1.data_ptr(), *g1.stride(), g2.data_ptr(), Cc, *g2.stride(), None, None, pad, k, md, s1, s2, 1,
         torch.cuda.current_stream().cuda_stream)
     assert ok == 0 and b"contiguous" in lib().d2t_last_error()
+
+
+@pytest.mark.parametrize("n_total,n_take,B", [(28728, 6000, 4), (28728, 12000, 2), (28728, 300, 3), (7296, 6000, 2), (500, 500, 2),
+                                              (1000, 1, 2), (32768, 16384, 1)])
+def test_proposal_topk_gather_matches_stable_sort(n_total, n_take, B):
+    """d2t_proposal_topk_gather (radix select + compaction + bitonic sort + gather, one CTA per image) against what it
+    replaces: torch.sort(descending, stable) over all scores, the first n_take, d2t_proposal_gather -- bit for bit, with
+    heavy ties (scores on a coarse lattice: the tie order is the index order), zeros of both signs, and a few NaN / inf."""
+    from d2t_b200._lib import lib
+    assert lib().d2t_proposal_topk_supported(n_total, n_take) == 1 and lib().d2t_proposal_topk_supported(100, 200) == 0
+    assert lib().d2t_proposal_topk_supported(40000, 6000) == 0          # keys live in registers: n_total <= 32768
+    g = torch.Generator(device="cuda").manual_seed(70 + n_take)
+    for kind in ("smooth", "ties", "special"):
+        scores = torch.rand(B, n_total, device="cuda", generator=g)
+        if kind == "ties":
+            scores = (scores * 50).round() / 50
+        if kind == "special":
+            scores = (scores * 20).round() / 20 - 0.5
+            scores[:, 3::97] = 0.0
+            scores[:, 5::89] = -0.0
+            scores[0, 11] = float("nan")
+            scores[0, n_total - 1] = float("nan")
+            scores[B - 1, 7] = float("inf")
+            scores[B - 1, 8] = float("-inf")
+        boxes = torch.rand(B, n_total, 4, device="cuda", generator=g) * 100
+        order = torch.sort(scores, dim=1, descending=True, stable=True)[1]
+        want = ops.proposal_gather(boxes, scores, order, n_take)
+        got = ops.proposal_topk_gather(boxes, scores, n_take)
+        torch.cuda.synchronize()
+        same = (got == want) | (torch.isnan(got) & torch.isnan(want))
+        assert bool(same.all()), (kind, n_total, n_take, int((~same).sum()))
+
+
+def test_proposals_same_with_hand_written_topk():
+    """ops.proposals with the one-launch select + sort + gather kernel == with torch.sort + d2t_proposal_gather"""
+    prob, deltas, im_info = common.make_rpn_inputs(B=2, H=38, W=63, seed=33, im_h=600, im_w=1000)
+    from model.rpn.generate_anchors import generate_anchors
+    from model.utils.config import cfg
+    anchors = torch.from_numpy(generate_anchors(scales=np.array(cfg.ANCHOR_SCALES), ratios=np.array(cfg.ANCHOR_RATIOS))).float().cuda()
+    outs = []
+    saved = ops.HAND_WRITTEN_TOPK
+    try:
+        for flag in (False, True):
+            ops.HAND_WRITTEN_TOPK = flag
+            outs.append(ops.proposals(anchors, cu(deltas), cu(prob), cu(im_info), 16, 6000, 300, 0.7))
+    finally:
+        ops.HAND_WRITTEN_TOPK = saved
+    assert torch.equal(outs[0], outs[1])
