@@ -2533,6 +2533,7 @@ static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
     if (pl->passes == 16) {
         if (pl->args.mask) {        // backward-data plans: the epilogue with the ReLU mask compiled in (never pairs)
             if (pl->BN == 64) return launch_conv<64, 16, false, false, false, false, false, true>(pl, stream);
+            if (pl->epi2 && pl->ares) return launch_conv<128, 16, false, false, true, false, false, true, true>(pl, stream);
             return pl->epi2 ? launch_conv<128, 16, false, false, true, false, false, true>(pl, stream)
                             : launch_conv<128, 16, false, false, false, false, false, true>(pl, stream);
         }
