@@ -333,6 +333,15 @@ d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int 
                                     const float* in2, float* out, int out_cstride, int out_coffset,
                                     float* out_nchw);
 
+/* Re-pack MANY operands in one launch (a training engine after every optimizer step: ~630 operands of a Res-101 D&T net).
+ * items: device array of n_items records of d2t_conv_repack_item_bytes() bytes each, laid out as
+ *   { const float* w_oihw; const float* scale_or_null; const float* amax; void* hi; void* lo;
+ *     int O, I, R, S, pad (cin_pad | cout_pad), rows (backward-data: rows of the operand), dgrad (0 | 1), first_block; }
+ * = the arguments of d2t_conv_pack_weights_f16_dev (dgrad = 0) / _dgrad (dgrad = 1); item i owns blocks
+ * [first_block_i, first_block_{i+1}) with ceil(elements_i / 1024) blocks, first_block_0 = 0, total_blocks their sum.
+ * Same values, bit for bit, as the per-operand entry points. */
+size_t d2t_conv_repack_item_bytes(void);
+int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, cudaStream_t stream);
 /* ---- Training path of the convolution engine: backward-data and weight-gradient on the same tcgen05 kernel ----
  * Replaces the cuDNN dgrad / wgrad calls autograd makes for the trainable convolutions of the reference's training step
  * (trainval_net.py:365-373 over faster_rcnn/resnet.py:66-109, 279-295, rfcn.py:49-53, rpn/rpn.py:28-36); 3xFP16 like

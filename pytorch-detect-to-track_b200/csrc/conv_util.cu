@@ -230,6 +230,59 @@ __global__ void pack_weights_f16_dgrad(const float* __restrict__ w, const float*
     }
 }
 
+// ONE launch for every packed operand of a training engine (d2t_conv_repack_many): after an optimizer step a Res-101 D&T
+// engine re-packs ~330 forward operands and ~300 backward-data operands; as one small kernel each they are launch-bound
+// (1.1 ms per step for 0.5 GB of traffic).  Block b belongs to the item whose [first_block, first_block + blocks) contains
+// it (binary search over the items' first blocks) and packs 1024 consecutive output elements.
+struct RepackItem {
+    const float* w;        // OIHW weights
+    const float* scale;    // [O] or null
+    const float* amax;     // device scalar: max |w * scale| bound the 2^k is derived from
+    __half* hi;
+    __half* lo;
+    int O, I, R, S;
+    int pad;               // forward: cin_pad; backward-data: cout_pad
+    int rows;              // backward-data: rows of the transposed operand (>= I); forward: unused
+    int dgrad;             // 0: [O][R*S][cin_pad] of w;  1: [rows][R*S][cout_pad] of the flipped transpose
+    int first_block;
+};
+
+__global__ void __launch_bounds__(256) repack_many(const RepackItem* __restrict__ items, int n_items) {
+    int lo_i = 0, hi_i = n_items - 1;
+    const int b = (int)blockIdx.x;
+    while (lo_i < hi_i) {                                  // last item with first_block <= b
+        const int mid = (lo_i + hi_i + 1) >> 1;
+        if (__ldg(&items[mid].first_block) <= b) lo_i = mid;
+        else hi_i = mid - 1;
+    }
+    const RepackItem it = items[lo_i];
+    const float sw = pow2f(act_exp(it.amax));
+    const int RS = it.R * it.S;
+    const size_t total = (size_t)(it.dgrad ? it.rows : it.O) * RS * it.pad;
+    const size_t base = (size_t)(b - it.first_block) * 1024;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const size_t idx = base + q * 256 + threadIdx.x;
+        if (idx >= total) break;
+        const int c = (int)(idx % it.pad);
+        const int rs = (int)((idx / it.pad) % RS);
+        const int r0 = (int)(idx / it.pad / RS);
+        float v = 0.f;
+        if (!it.dgrad) {
+            if (c < it.I) {
+                v = __ldg(it.w + ((size_t)r0 * it.I + c) * RS + rs) * sw;
+                if (it.scale) v *= __ldg(it.scale + r0);
+            }
+        } else if (c < it.O && r0 < it.I) {
+            v = __ldg(it.w + ((size_t)c * it.I + r0) * RS + (RS - 1 - rs)) * sw;
+            if (it.scale) v *= __ldg(it.scale + c);
+        }
+        const __half h = __float2half_rn(v);
+        it.hi[idx] = h;
+        it.lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
 // channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> fp32 planes [N][C][OH][pitch]
 // (columns [OW, pitch) zero): the K-contiguous A operand of the weight-gradient GEMM.  A CTA transposes 64 positions x
 // 32 channels of one output row through shared memory: 128-byte loads (32 channels of a pixel), 256-byte stores (a lane
@@ -446,6 +499,16 @@ extern "C" int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float*
     pack_weights_f16_dgrad<<<grid_for(total), 256, 0, stream>>>(w_oihw, scale, Cout, Cin, rows, R, S, cout_pad, amax_wt,
                                                                 reinterpret_cast<__half*>(wt_hi), reinterpret_cast<__half*>(wt_lo));
     D2T_CHECK_LAUNCH("pack_weights_f16_dgrad");
+    return 1;
+}
+
+// items: device array of n_items descriptors, 8 x 8-byte words each (see d2t_b200.h); total_blocks = sum of the items' blocks
+extern "C" size_t d2t_conv_repack_item_bytes(void) { return sizeof(RepackItem); }
+
+extern "C" int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, cudaStream_t stream) {
+    D2T_REQUIRE(items && n_items > 0 && total_blocks > 0, "d2t_conv_repack_many: bad arguments");
+    repack_many<<<total_blocks, 256, 0, stream>>>(reinterpret_cast<const RepackItem*>(items), n_items);
+    D2T_CHECK_LAUNCH("repack_many");
     return 1;
 }
 

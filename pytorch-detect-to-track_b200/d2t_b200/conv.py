@@ -264,9 +264,40 @@ class ConvLayer(_Planned):
                                                   _p(self.w_hi), _p(self.w_lo), _stream()), "d2t_conv_pack_weights_f16_dev")
         ops._count(1)
 
+    def repack_item(self):
+        """arguments of repack() as a record for RepackMany"""
+        O, I, R, S = self.weight.shape
+        return (self.weight.detach(), self.scale, self.amax_w, self.w_hi, self.w_lo, O, I, R, S, _pad64(I), 0, 0)
+
     def run(self, stream=None):
         _Planned.run(self, stream)
         return self.out if self.out is not None else self.out_nchw
+
+
+class RepackMany(object):
+    """every packed operand of an engine refreshed by ONE launch (csrc/conv_util.cu: repack_many) instead of one small
+    kernel per operand; `layers`: ConvLayer / DgradConv objects built with a device-side weight scale (amax_w)"""
+
+    def __init__(self, layers):
+        import struct
+        assert lib().d2t_conv_repack_item_bytes() == 72
+        recs, first = [], 0
+        self.keep = []
+        for l in layers:
+            w, scale, amax, hi, lo, O, I, R, S, pad, rows, dgrad = l.repack_item()
+            assert w.is_contiguous() and w.dtype == torch.float32
+            self.keep.append((w, scale, amax, hi, lo))
+            total = (rows if dgrad else O) * R * S * pad
+            recs.append(struct.pack("<QQQQQiiiiiiii", w.data_ptr(), scale.data_ptr() if scale is not None else 0, amax.data_ptr(),
+                                    hi.data_ptr(), lo.data_ptr(), O, I, R, S, pad, rows, dgrad, first))
+            first += (total + 1023) // 1024
+        self.n, self.blocks = len(recs), first
+        self.items = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(hi.device)
+
+    def run(self, stream=None):
+        check(lib().d2t_conv_repack_many(self.items.data_ptr(), self.n, self.blocks, _stream() if stream is None else stream),
+              "d2t_conv_repack_many")
+        ops._count(1)
 
 
 class ConvChain(object):
@@ -360,6 +391,10 @@ class DgradConv(ConvLayer):
         geom = torch.empty(rows, O, R, S, device="meta")              # [O', I', R, S] of the equivalent forward conv
         ConvLayer.__init__(self, g, geom, None, None, 1, dil * (R - 1) - pad, dil, False, residual, passes=16, out=out,
                            amax_w=amax_wt, packed=(hi, lo), mask=mask)
+
+    def repack_item(self):
+        O, I, R, S = self.fwd_weight.shape
+        return (self.fwd_weight.detach(), self.fwd_scale, self.amax_w, self.w_hi, self.w_lo, O, I, R, S, _pad64(O), self.rows, 1)
 
     def repack(self):
         O, I, R, S = self.fwd_weight.shape

@@ -49,6 +49,7 @@ class D2TTrainEngine(D2TEngine):
         self.bucket_bytes = bucket_bytes
         with self.amax:
             self._build_backward()
+        self._repack_many = dc.RepackMany([self.trk_layer] + self.layers + self.dgrads)
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.ready = torch.cuda.Event()
         self.allreduce_ms = None
@@ -295,10 +296,7 @@ class D2TTrainEngine(D2TEngine):
         n = len(norms)
         torch.stack(norms, out=self.w_amax[:n])
         torch.mul(self.w_amax[:n], self._smax[:n], out=self.wt_amax[:n])
-        for l in [self.trk_layer] + self.layers:
-            l.repack()
-        for d in self.dgrads:
-            d.repack()
+        self._repack_many.run()                   # one launch for all ~630 forward / backward-data operands
 
     # ------------------------------------------------------------------ the step
     def _engine_forward(self, im_data, im_info):

@@ -193,3 +193,27 @@ def test_train_engine_graphed_heads():
     got = eng.grads_static[0]
     err = float((g - got).abs().max() / g.abs().max())
     assert err < 1e-5, err
+
+
+def test_repack_many_equals_per_operand_repack():
+    """the one-launch re-pack of every forward / backward-data operand (d2t_conv_repack_many) writes exactly what the
+    per-operand packers write"""
+    from d2t_b200.train import D2TTrainEngine
+    from d2t_b200 import conv as dc
+    B, H, W = 1, 160, 224
+    net, im_data, im_info, gt, nb = _setup(50, B, H, W)
+    eng = D2TTrainEngine(net, B, H, W)
+    with torch.no_grad():
+        for p in eng.params:
+            p.mul_(1.01)                               # new values: the packed copies are stale now
+        eng._refresh_weights()                         # (norms + RepackMany)
+    layers = [eng.trk_layer] + eng.layers + eng.dgrads
+    got = [(l.w_hi.clone(), l.w_lo.clone()) for l in layers]
+    for l in layers:
+        l.w_hi.zero_(); l.w_lo.zero_()
+        l.repack()
+    torch.cuda.synchronize()
+    assert len(layers) > 100
+    for l, (hi, lo) in zip(layers, got):
+        assert torch.equal(hi, l.w_hi) and torch.equal(lo, l.w_lo)
+    assert float(got[5][0].float().abs().max()) > 0
