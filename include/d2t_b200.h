@@ -381,6 +381,13 @@ d2t_conv_plan* d2t_wgrad_plan_create(int N, int Cin, int Cout, int xh, int xw, i
                                      int g_pitch, int R, int S, int pad, int dil, const float* xt,
                                      const void* g_hi, const void* g_lo, const float* amax_x,
                                      const float* amax_g, const float* scale, float* dw);
+/* Split-K reduction of a weight-gradient plan as a separate device-wide launch.  The GEMM has few tiles and K = every output
+ * pixel, so each tile is shared by ~9 CTAs; with a partials buffer (d2t_wgrad_partials_bytes() bytes of device memory, may be
+ * shared by all weight-gradient plans of a stream) every CTA parks its partial tiles there and d2t_conv_plan_run launches
+ * wgrad_reduce right after the GEMM, which adds them in CTA order (deterministic) -- instead of one finisher CTA per tile
+ * reading 8 partial tiles one after the other.  NULL restores the in-kernel finisher. */
+size_t d2t_wgrad_partials_bytes(void);
+int d2t_wgrad_plan_set_partials(d2t_conv_plan* plan, void* partials, size_t bytes);
 
 /* Correlation backward on the tensor cores (replaces Correlation_backward_input1 / _input2,
  * correlation/src/correlation_cuda_kernel.cu:108-290, for kernel_size 1, stride1 == stride2, pad == max_displacement):

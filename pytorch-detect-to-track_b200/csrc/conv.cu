@@ -122,6 +122,12 @@ struct ConvArgs {
     // WGRAD (see the kernel comment): K blocks per output row, K blocks in total, input channels, OIHW gradient
     int wg_xblocks, wg_kiters, wg_cin;
     float* wg_out;
+    // WGRAD with a separate reduction launch (d2t_wgrad_plan_set_partials): a weight-gradient GEMM has few tiles and a very
+    // long K (all pixels), so every tile is split over ~9 CTAs and the in-kernel finisher would read 8 partial tiles one
+    // after the other through one SM's load path (30 B/clk: ~20 us per launch, profiles/r02_mb_*).  Instead every CTA
+    // stores its partial tiles ([cta][slot: 0 = its first tile, 1 = its last][column][row]) and wgrad_reduce, a device-wide
+    // launch, adds them in CTA order.
+    float* wg_partials;
     // optional completion hand-shake between consecutive launches of one chain (d2t_conv_plan_set_done): every CTA adds
     // 1 to *done_self when all its outputs are globally visible; a launch whose done_prev is set polls that counter up
     // to done_target (= the previous launch's grid) INSTEAD of griddepcontrol.wait, i.e. it does not sit through the
@@ -1290,6 +1296,16 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
 #ifdef D2T_CONV_TRACE
             const long long t_post__ = clock64();
 #endif
+            if constexpr (WGRAD) {
+                if (p.wg_partials != nullptr && sg.role != 0) {
+                    // split tile: park the partial sum for wgrad_reduce (no flags: the kernel boundary orders it)
+                    const int slot = sg.tile == sched.first_tile ? 0 : 1;
+                    float* dst = p.wg_partials + (((size_t)blockIdx.x * 2 + slot) * BN + cofs) * kBlockM + m;
+#pragma unroll
+                    for (int j = 0; j < HN; ++j) dst[j * kBlockM] = acc[j];
+                    continue;
+                }
+            }
             if (sg.role == 1) {
                 // partial tile: publish registers -> scratch[cta][column][row] (coalesced across the warp)
                 float* dst = p.sk_scratch + ((size_t)blockIdx.x * BN + cofs) * kBlockM + m;
@@ -1702,6 +1718,43 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
 }
 
+// ------------------------------------------------------------------ split-K reduction of the weight-gradient GEMM
+// One block per (tile, 8 output channels): thread = tile row (an input channel); the partial tiles of the CTAs that shared
+// the tile are added in CTA order (deterministic), scaled by the folded BatchNorm factor and written as OIHW.  The unit ->
+// CTA arithmetic is the scheduler's (struct Sched).
+__global__ void __launch_bounds__(128)
+wgrad_reduce(const ConvArgs p, int BN, int G, int cpt) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int cols_per_block = 8;
+    const int blocks_per_tile = BN / cols_per_block;
+    const int t = (int)blockIdx.x / blocks_per_tile, cb = (int)blockIdx.x % blocks_per_tile;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const long long U = (long long)tiles * cpt;
+    const long long ufirst = (long long)t * cpt, ulast = ufirst + cpt - 1;
+    const int c_first = (int)(((ufirst + 1) * G + U - 1) / U) - 1;
+    const int c_last = (int)(((ulast + 1) * G + U - 1) / U) - 1;
+    if (c_first == c_last) return;                           // the tile was not split: its CTA wrote the gradient itself
+    const int m = threadIdx.x;
+    const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+    const int rs = p.R * p.S, tap = m_tile % rs, ci = (m_tile / rs) * kBlockM + m;
+    float sum[cols_per_block];
+#pragma unroll
+    for (int j = 0; j < cols_per_block; ++j) sum[j] = 0.f;
+    for (int c = c_first; c <= c_last; ++c) {
+        const int first_tile_c = (int)((U * c / G) / cpt);
+        const int slot = t == first_tile_c ? 0 : 1;
+        const float* src = p.wg_partials + (((size_t)c * 2 + slot) * BN + cb * cols_per_block) * kBlockM + m;
+#pragma unroll
+        for (int j = 0; j < cols_per_block; ++j) sum[j] += __ldcg(src + j * kBlockM);
+    }
+    if (ci >= p.wg_cin) return;
+#pragma unroll
+    for (int j = 0; j < cols_per_block; ++j) {
+        const int co = n_tile * BN + cb * cols_per_block + j;
+        if (co < p.Cout) p.wg_out[((size_t)co * p.wg_cin + ci) * rs + tap] = fmaf(sum[j], p.scale ? __ldg(p.scale + co) : 1.f, 0.f);
+    }
+}
+
 // ------------------------------------------------------------------ the multi-layer persistent kernel
 // Every dependent launch of the layer chain costs ~6 us in which the SMs idle (the next grid's CTAs become
 // resident as this grid's exit, then sit in griddepcontrol.wait until the LAST CTA is done and its writes are flushed) on top
@@ -1719,8 +1772,8 @@ struct alignas(128) ChainLayer {
 };
 constexpr int kChainBarsOff = 224 * 1024;     // the largest variant layout: 3 x 64 KB stages + 32 KB output staging
 constexpr int kChainSmem = kChainBarsOff + 1024 /*align slack*/ + 384 /*barriers*/ + 1024 /*shift of the current n tile*/ +
-                           2 * 288 /*ConvArgs + variant + sync_before of the current and the next layer*/;
-static_assert(sizeof(ConvArgs) + 8 <= 288 && sizeof(ConvArgs) % 4 == 0 && offsetof(ChainLayer, variant) == offsetof(ChainLayer, args) + sizeof(ConvArgs) &&
+                           2 * 304 /*ConvArgs + variant + sync_before of the current and the next layer*/;
+static_assert(sizeof(ConvArgs) + 8 <= 304 && sizeof(ConvArgs) % 4 == 0 && offsetof(ChainLayer, variant) == offsetof(ChainLayer, args) + sizeof(ConvArgs) &&
               offsetof(ChainLayer, sync_before) == offsetof(ChainLayer, variant) + 4 && kChainSmem <= 227 * 1024, "chain shared-memory budget");
 static_assert(Cfg<128, 16, false, false>::STAGES * Cfg<128, 16, false, false>::STAGE_BYTES + Cfg<128, 16, false, false>::OUT_STAGE_BYTES <= kChainBarsOff &&
               Cfg<128, 16, false, true>::STAGES * Cfg<128, 16, false, true>::STAGE_BYTES + Cfg<128, 16, false, true>::OUT_STAGE_BYTES <= kChainBarsOff &&
@@ -1771,7 +1824,7 @@ __global__ void __launch_bounds__(512, 1) conv_chain(const ChainLayer* __restric
     int prev_nbars = 0;
     for (int l = 0; l < n_layers; ++l) {
         const ChainLayer* L = layers + l;
-        const ConvArgs* sp = reinterpret_cast<const ConvArgs*>(argbuf + (l & 1) * 288);
+        const ConvArgs* sp = reinterpret_cast<const ConvArgs*>(argbuf + (l & 1) * 304);
         const int variant = reinterpret_cast<const int*>(sp + 1)[0], sync_before = reinterpret_cast<const int*>(sp + 1)[1];
         if (l > 0) {
             __syncthreads();                   // every role of this CTA has left layer l - 1: stores complete, fences done
@@ -1788,7 +1841,7 @@ __global__ void __launch_bounds__(512, 1) conv_chain(const ChainLayer* __restric
             // (the body's barrier after its pipeline reset releases the other warps)
         }
         if (l + 1 < n_layers && threadIdx.x >= 128 && threadIdx.x < 128 + kArgWords)      // (epilogue warps: idle at a layer's start)
-            reinterpret_cast<uint32_t*>(argbuf + ((l + 1) & 1) * 288)[threadIdx.x - 128] =
+            reinterpret_cast<uint32_t*>(argbuf + ((l + 1) & 1) * 304)[threadIdx.x - 128] =
                 __ldg(reinterpret_cast<const uint32_t*>(&L[1].args) + (threadIdx.x - 128));
         if (warp == 3 && lane == 0 && l + 1 < n_layers) {       // the next layer's descriptors: fetched while this one runs
             prefetch_tmap(&L[1].tmA);
@@ -2435,6 +2488,17 @@ extern "C" d2t_conv_plan* d2t_corrb_plan_create(int N, int C, int H, int W, int 
     return pl;
 }
 
+extern "C" size_t d2t_wgrad_partials_bytes(void) {
+    return (size_t)sm_count() * 2 * 128 * kBlockM * sizeof(float);
+}
+
+extern "C" int d2t_wgrad_plan_set_partials(d2t_conv_plan* pl, void* partials, size_t bytes) {
+    D2T_REQUIRE(pl && pl->wgrad && (!partials || (((uintptr_t)partials & 15) == 0 && bytes >= d2t_wgrad_partials_bytes())),
+                "d2t_wgrad_plan_set_partials: needs a weight-gradient plan and a 16-byte aligned buffer of d2t_wgrad_partials_bytes()");
+    pl->args.wg_partials = reinterpret_cast<float*>(partials);
+    return 1;
+}
+
 extern "C" int d2t_conv_plan_set_mask(d2t_conv_plan* pl, const float* mask, int mask_cstride) {
     D2T_REQUIRE(pl && pl->passes == 16 && !pl->corr && !pl->wgrad && !pl->corrb && (!mask || (mask_cstride % 4 == 0 && mask_cstride >= pl->args.Cout)),
                 "d2t_conv_plan_set_mask: needs a convolution plan and a mask with a channel stride that is a multiple of 4");
@@ -2518,9 +2582,24 @@ extern "C" int d2t_conv_plan_run(const d2t_conv_plan* pl, cudaStream_t stream) {
 }
 
 static int conv_plan_dispatch(const d2t_conv_plan* pl, cudaStream_t stream) {
-    if (pl->wgrad)
-        return pl->BN == 64 ? launch_conv<64, 16, false, false, false, true>(pl, stream)
-                            : launch_conv<128, 16, false, false, false, true>(pl, stream);
+    if (pl->wgrad) {
+        const int ok = pl->BN == 64 ? launch_conv<64, 16, false, false, false, true>(pl, stream)
+                                    : launch_conv<128, 16, false, false, false, true>(pl, stream);
+        if (!ok || !pl->args.wg_partials) return ok;
+        const int unit = unit_of(pl->args.wg_kiters, chunk_of(16));
+        const int cpt = (pl->args.wg_kiters + unit - 1) / unit;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl->args.m_tiles * pl->args.n_tiles * (pl->BN / 8));
+        cfg.blockDim = dim3(128);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_reduce, pl->args, pl->BN, pl->grid, cpt), "wgrad_reduce launch");
+        return 1;
+    }
     if (pl->corrb) return launch_conv<128, 16, false, false, false, false, true>(pl, stream);
     if (pl->corr) {
         if (pl->passes == 16) {

@@ -98,6 +98,8 @@ _SIGS = {
     "d2t_wgrad_pack_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "d2t_wgrad_pack_grad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_wgrad_plan_create": (_p, [_i] * 13 + [_p] * 7),
+    "d2t_wgrad_partials_bytes": (_sz, []),
+    "d2t_wgrad_plan_set_partials": (_i, [_p, _p, _sz]),
     "d2t_corrb_pack_band": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_corrb_pack_other": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_corrb_plan_create": (_p, [_i] * 5 + [_p] * 4 + [_i] + [_p] * 4 + [_i, _i]),

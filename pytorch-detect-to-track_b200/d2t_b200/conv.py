@@ -413,6 +413,10 @@ class WgradScratch(object):
         self.xt = torch.zeros(x_floats, device=device)
         self.g_hi = torch.zeros(g_halfs, device=device, dtype=torch.float16)
         self.g_lo = torch.zeros(g_halfs, device=device, dtype=torch.float16)
+        # partial tiles of the split-K reduction (d2t_wgrad_plan_set_partials); D2T_WGRAD_REDUCE=0: in-kernel finisher
+        import os
+        self.partials = (torch.empty(lib().d2t_wgrad_partials_bytes(), dtype=torch.uint8, device=device)
+                         if os.environ.get("D2T_WGRAD_REDUCE", "1") != "0" else None)
 
     @staticmethod
     def need(x, g, stride, S=1):
@@ -444,6 +448,11 @@ class WgradLayer(_Planned):
         if not self.plan:
             raise D2TError("d2t_wgrad_plan_create failed: %s" % lib().d2t_last_error().decode())
         self.flops = 2.0 * g.N * g.H * g.W * O * I * R * S
+        self.launches = 3
+        if getattr(scratch, "partials", None) is not None:
+            check(lib().d2t_wgrad_plan_set_partials(self.plan, scratch.partials.data_ptr(), scratch.partials.numel()),
+                  "d2t_wgrad_plan_set_partials")
+            self.launches = 4
 
     def run(self, stream=None):
         x, g, sc = self.x, self.g, self.scratch
@@ -454,7 +463,7 @@ class WgradLayer(_Planned):
         check(lib().d2t_wgrad_pack_grad(_p(g.x), g.N, g.H, g.W, g.cstride, O, self.gp, self.S, self.dil, self.pad,
                                         _p(g.amax), _p(sc.g_hi), _p(sc.g_lo), st), "d2t_wgrad_pack_grad")
         check(lib().d2t_conv_plan_run(self.plan, st), "d2t_conv_plan_run")
-        ops._count(3)
+        ops._count(self.launches)
         return self.grad_w
 
 
