@@ -1363,26 +1363,59 @@ __device__ __forceinline__ void conv_body(const CUtensorMap& tmA,      // activa
                 }
             }
             if constexpr (CORR) {
-                // tile row m = position (yl, xl) of the 8x16 tile; column n = halo (rl, cl) of this 4x32 chunk
-                const int r = p.corr_r, D = p.corr_D;
+                // tile row m = position (yl, xl) of the 8x16 tile; column n = halo (rl, cl) of this 4x32 chunk: the in-range
+                // displacements of position m are the columns cl = ti + r + xl of halo rows rl = tj + r + yl - 4 n_tile.
+                // Written straight from the accumulator rows, every store instruction would scatter 32 single floats over 32
+                // sectors (lanes = positions, and the channel depends on the lane): measured, the band loop took as long as
+                // the whole K loop (profiles/r02_corr_trace.txt).  So each halo row goes through a swizzled [128 x 32] staging
+                // tile (the output slabs, idle in this mode) and is written out transposed: NHWC -- lanes = the 2r+1
+                // consecutive channels of one pixel (one 68-byte run per instruction); NCHW -- lanes = consecutive x of one
+                // channel plane.
+                const int D = p.corr_D;
+                float* stage = reinterpret_cast<float*>(out_stage) + grp * (kBlockM * 32);       // 16 KB per group
+                const int wq = (warp - kEpiWarp0) & 3;                                            // rows wq*32 .. +31 of the tile
+                const int tile_y0 = th * p.TH, tile_x0 = tw << p.TW_log2;
+                const float nel = p.corr_nelems;
 #pragma unroll
                 for (int rh = 0; rh < HN / 32; ++rh) {
                     const int rl = grp * (HN / 32) + rh;             // halo row of the chunk (this group's half)
-                    const int tjr = 4 * n_tile + rl - hl;            // tj + r
-                    if (!pix_ok || tjr < 0 || tjr >= D) continue;
-                    const int tc0 = tjr * D - wl;                    // channel of column cl is tc0 + cl
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");      // the previous pass has been read
 #pragma unroll
-                    for (int cl = 0; cl < 32; ++cl) {
-                        const int tir = cl - wl;                     // ti + r
-                        if (tir < 0 || tir >= D) continue;
-                        const float val = __fdiv_rn(acc[rh * 32 + cl], p.corr_nelems);   // kernel.cu:100
-                        tmax = fmaxf(tmax, fabsf(val));
-                        if (p.out_nchw)
-                            p.out_nchw[(((size_t)img * D * D + tc0 + cl) * p.OH + oh) * p.OW + ow] = val;
-                        if (p.out) p.out[pix * p.out_cstride + p.out_coffset + tc0 + cl] = val;
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *reinterpret_cast<float4*>(stage + m * 32 + ((c4 ^ (m & 7)) << 2)) =
+                            make_float4(acc[rh * 32 + 4 * c4], acc[rh * 32 + 4 * c4 + 1], acc[rh * 32 + 4 * c4 + 2], acc[rh * 32 + 4 * c4 + 3]);
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                    if (p.out) {
+                        // one pixel per instruction: lane = ti + r
+                        for (int i = 0; i < 32; ++i) {
+                            const int m2 = wq * 32 + i, hl2 = m2 >> p.TW_log2, wl2 = m2 & (TW - 1);
+                            const int oh2 = tile_y0 + hl2, ow2 = tile_x0 + wl2, tjr = 4 * n_tile + rl - hl2;
+                            if (oh2 >= p.OH || ow2 >= p.OW || img >= p.N || tjr < 0 || tjr >= D) continue;   // (warp-uniform)
+                            if (lane < D) {
+                                const int col = lane + wl2;
+                                const float val = __fdiv_rn(stage[m2 * 32 + (((col >> 2) ^ (m2 & 7)) << 2) + (col & 3)], nel);   // kernel.cu:100
+                                tmax = fmaxf(tmax, fabsf(val));
+                                p.out[(((size_t)img * p.OH + oh2) * p.OW + ow2) * p.out_cstride + p.out_coffset + tjr * D + lane] = val;
+                            }
+                        }
+                    }
+                    if (p.out_nchw) {
+                        // one displacement per instruction: lane = position (consecutive x of one channel plane)
+                        const int m2 = wq * 32 + lane, hl2 = m2 >> p.TW_log2, wl2 = m2 & (TW - 1);
+                        const int oh2 = tile_y0 + hl2, ow2 = tile_x0 + wl2, tjr = 4 * n_tile + rl - hl2;
+                        const bool ok = oh2 < p.OH && ow2 < p.OW && img < p.N && tjr >= 0 && tjr < D;
+                        float* o = p.out_nchw + (((size_t)img * D * D + (size_t)(ok ? tjr : 0) * D) * p.OH + oh2) * p.OW + ow2;
+                        const size_t cs = (size_t)p.OH * p.OW;
+                        for (int tir = 0; tir < D; ++tir) {
+                            const int col = tir + wl2;
+                            const float val = __fdiv_rn(stage[m2 * 32 + (((col >> 2) ^ (m2 & 7)) << 2) + (col & 3)], nel);
+                            if (ok) {
+                                if (!p.out) tmax = fmaxf(tmax, fabsf(val));
+                                o[tir * cs] = val;
+                            }
+                        }
                     }
                 }
-                (void)r;
             } else {
             if constexpr (!FOLDED) {
             asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue thread is done with the previous tile's values

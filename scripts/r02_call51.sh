@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 300 python -m pytest tests/test_ops_gpu.py tests/test_conv_gpu.py tests/test_model_gpu.py tests/test_train_conv_gpu.py -q -x -k "corr or rfcn or engine" 2>&1 | tail -4 ) > gpurun_out/r02_c51_tests.log
+cat gpurun_out/r02_c51_tests.log
+timeout 300 python bench.py --ops-only > gpurun_out/r02_c51_ops.json 2> gpurun_out/r02_c51_ops.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r02_c51_ops.json").read().strip().splitlines()[-1])
+d = d.get("ops", d)
+for k, v in d.items():
+    if k.startswith("corr"):
+        print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a in ("ms", "ms_3xtf32", "ms_operator_api_nchw", "frac_hbm", "tflops_useful")})
+PY
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-train > gpurun_out/r02_c51_bench.json 2> gpurun_out/r02_c51_bench.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r02_c51_bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["roofline"]["conv_ms_per_step"], d["e2e"]["value"], d["parity"]["ok"], d["parity"]["bbox_pred_max_rel_err"])
+PY
