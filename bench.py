@@ -191,7 +191,12 @@ def op_microbench(flush, hbm_gbs):
         lib().d2t_psroi_backward(gt.data_ptr(), B, D * 49, 38, 63, rois.data_ptr(), B * R, 1 / 16., 7, 7, 7, D,
                                  grad.data_ptr(), 0, ws.data_ptr(), ws.numel(), st)
     ms = time_kernel(psroi_b, 20, flush)
-    out["psroi_bwd"] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / hbm_gbs}
+    out["psroi_bwd"] = {"kernel": "psroi_prep + psroi_bwd_amax + psroi_bwd_limb (two-limb integer difference tables)", "ms": ms,
+                        "algorithmic_bytes": alg, "gbs": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / hbm_gbs}
+    lib().d2t_psroi_set_mode(-1, 2)            # the fp64 difference tables (shared-memory CAS loops) it replaced
+    ms_x = time_kernel(psroi_b, 10, flush)
+    lib().d2t_psroi_set_mode(-1, 0)
+    out["psroi_bwd_fp64_tables"] = {"ms": ms_x, "gbs": alg / ms_x / 1e6, "frac_hbm": alg / ms_x / 1e6 / hbm_gbs}
     for name, (C_, Hh, Ww, p, Bc) in {"corr_conv4": (1024, 38, 63, (8, 1, 8, 1, 1), 2), "corr_conv5": (2048, 38, 63, (8, 1, 8, 1, 1), 2),
                                       "corr_conv3": (512, 75, 125, (8, 1, 8, 2, 2), 2)}.items():
         a, b = torch.randn(Bc, C_, Hh, Ww, device="cuda"), torch.randn(Bc, C_, Hh, Ww, device="cuda")

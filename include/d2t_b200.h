@@ -156,8 +156,9 @@ int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int bo
 
 /* Kernel variant of d2t_psroi_forward / _backward, process-wide (tests and A/B measurements; the defaults are the product):
  * forward_mode -1 = chosen by the geometry alone (integer tables when the plane fits, never by batch size or SM count),
- * 0 = exactly-rounded fp64 tables, 1..4 = development variants of the integer tables; backward_mode 0 = fp64 difference
- * tables, 1 = integer difference tables. */
+ * 0 = exactly-rounded fp64 tables, 1..4 = development variants of the integer tables; backward_mode 0 = two-limb integer
+ * difference tables (exact sums, native shared-memory atomics), 2 = fp64 difference
+ * tables, 1 = one-limb integer tables (experiment). */
 int d2t_psroi_set_mode(int forward_mode, int backward_mode);
 /* Fused PSRoI pooling + 7x7 vote (+ softmax) -- rfcn.py:62-64, 133-140, 194-196: vote[n][d] = the mean of the 49
  * pooled bins of (roi n, output channel d), optionally followed by the softmax over d, without the [R, D, 7, 7] tensor

@@ -76,10 +76,11 @@ __host__ __device__ inline size_t psroi_ws_bytes(int R, int PH, int PW) {
 // or a pre-zeroed table.
 __global__ void __launch_bounds__(128)
 psroi_prep(const float* __restrict__ rois, int R, int B, float scale, int PH, int PW, int H, int W, PsroiWs ws,
-           float* top, int D, int zero_invalid) {
+           float* top, int D, int zero_invalid, unsigned* gmax, int gmax_n) {
     asm volatile("griddepcontrol.launch_dependents;");   // let the plane kernel start staging features
     const int Rp = psroi_rp(R);
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = n; i < gmax_n; i += gridDim.x * blockDim.x) gmax[i] = 0u;      // backward: per-(image, class) maxima
     if (n >= Rp) return;
     int b = -1;
     if (n < R) {
@@ -733,7 +734,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             int ck = c_lo + warp;
             unsigned hbn[G], wbn[G];       // windows of the NEXT chunk, in flight while the current one is looked up
             if (ck <= c_hi) {
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < G; ++k) {
                     hbn[k] = __ldg(bhb + ck * 32 + nl_of(k));
                     wbn[k] = __ldg(ws.bw + (size_t)ck * 32 * G + k * 32 + lane);
@@ -741,20 +742,20 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             }
             for (; ck <= c_hi; ck += NW) {
                 unsigned hbv[G], wbv[G];
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < G; ++k) {
                     hbv[k] = hbn[k];
                     wbv[k] = wbn[k];
                 }
                 const int cn = ck + NW;
                 if (cn <= c_hi) {
-    #pragma unroll
+#pragma unroll
                     for (int k = 0; k < G; ++k) {
                         hbn[k] = __ldg(bhb + cn * 32 + nl_of(k));
                         wbn[k] = __ldg(ws.bw + (size_t)cn * 32 * G + k * 32 + lane);
                     }
                 }
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < G; ++k) {
                     if ((int)(hbv[k] >> 16) != b) continue;
                     const int pw = pw_of(k);
@@ -1038,6 +1039,255 @@ psroi_bwd_sat(const float* __restrict__ top_diff, int B, int C, int H, int W, in
     }
 }
 
+// ---- backward, two-limb fixed point: the same adjoint, NATIVE 32-bit shared-memory atomics ----
+// Shared-memory atomicAdd on a double (and on a float, and on a 64-bit integer) compiles to a load + compare-and-swap loop on
+// sm_100a (ATOMS.CAST.SPIN); only the 32-bit integer add is one instruction (ATOMS.ADD, no return value needed).  Here the
+// difference table is two int32 tables (the same 8 bytes per cell as the double):
+//     q  = rint(dv * 2^k)  as a 64-bit integer,  hi = q >> L,  lo = q & (2^L - 1)  (so q = hi 2^L + lo, lo >= 0)
+// and the four corners receive +-hi in one table and +-lo in the other -- fire-and-forget ATOMS.ADD, each instruction spread
+// over all 32 banks; corners in row H / column W are only ever "closing" entries that no cell reads: skipped (they are also
+// where the rois clipped at the image border would all collide).  Integer adds are exact and order-independent, wrap-around
+// in the middle of the scans is harmless (arithmetic modulo 2^32), and the FINAL value of a cell is a sum over the
+// n <= 2^RB bins covering it (RB = ceil(log2(rois + 1)), L = 30 - RB):
+//     |sum hi| <= n (max|q| / 2^L + 1) < 2^31   and   0 <= sum lo < n 2^L <= 2^30
+// when k = 156 + L - RB - eb, eb the biased exponent of max |top_diff| over the item's (image, class) -- |dv| <= |top_diff|:
+// areas are >= 1 -- which psroi_bwd_amax finds in one coalesced pass ahead of this kernel (a per-item pass inside it re-read
+// the 28-byte runs at a 5880-byte stride from DRAM: +60 % at B = 8).  The cell is then  (sum hi) 2^L + (sum lo)  converted to
+// float ONCE and scaled by 2^-k: the exact sum of the reference's fp32 dv terms (kernel.cu:161, same IEEE division), rounded
+// once, to within 2^-(k+1) per term -- 2^-34 of that max for 4000 rois.  Deterministic.  An (image, class) whose gradients
+// hold a NaN / Inf runs the fp64 loops of psroi_bwd_sat on the same memory.
+// Phases of an item (cycles: scripts/psroi_bwd_trace.py): zero the tables | corner updates (bound by the ATOMS pipe, ~5 cycles
+// per warp instruction with 32 random banks) | row scans, thread per row | column scans + write-out, two threads per column
+// (both bound by the shared-memory bandwidth).
+constexpr int kBwdChunkCache = 1024;     // chunk descriptors of the first 32768 rois live in shared memory
+constexpr int kBwdMaxD = 1024;           // workspace: one max |top_diff| word per (image, class), classes < kBwdMaxD
+
+// gmax[b * D + c] = max over the rois of image b of |top_diff[n][c][:][:]| as float bits (unsigned order = float order for
+// non-negative values; Inf and NaN sort above every finite value).  One block per roi, coalesced, every load of a thread in flight at once; zeroed by psroi_prep.
+__global__ void __launch_bounds__(128)
+psroi_bwd_amax(const float* __restrict__ top_diff, const int* __restrict__ rb, int D, int per_class,
+               unsigned* __restrict__ gmax) {
+    __shared__ unsigned smax[kBwdMaxD];
+    constexpr int NB = 12;                 // loads in flight per thread (D = 30, 7x7 bins: the whole roi in one batch)
+    const int n = blockIdx.x, lane = threadIdx.x & 31, total = D * per_class;
+    const float* g = top_diff + (size_t)n * total;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) smax[c] = 0u;
+    __syncthreads();
+    int b = -2;                            // (read after the first batch of loads is in flight: rb comes from psroi_prep, which
+    for (int base = 0; base < total; base += NB * 128) {       // this kernel overlaps -- programmatic dependent launch)
+        unsigned v[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int e = base + i * 128 + threadIdx.x;
+            v[i] = e < total ? __float_as_uint(__ldg(g + e)) & 0x7fffffffu : 0u;
+        }
+        if (b == -2) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            b = rb[n];
+        }
+        if (b < 0) return;                 // (block-uniform)
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {     // a warp's 32 consecutive elements: <= 2 classes when per_class >= 31
+            const int e = base + i * 128 + threadIdx.x;
+            const int c = min(e, total - 1) / per_class;
+            const int c_lo = __shfl_sync(0xffffffffu, c, 0), c_hi = __shfl_sync(0xffffffffu, c, 31);
+            if (c_hi - c_lo <= 1) {
+                const unsigned m_lo = __reduce_max_sync(0xffffffffu, c == c_lo ? v[i] : 0u);
+                const unsigned m_hi = __reduce_max_sync(0xffffffffu, c == c_hi ? v[i] : 0u);
+                if (lane == 0) atomicMax(&smax[c_lo], m_lo);
+                if (lane == 1) atomicMax(&smax[c_hi], m_hi);
+            } else {
+                atomicMax(&smax[c], v[i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const unsigned m = smax[c];
+        unsigned* dst = gmax + (size_t)b * D + c;
+        if (m > *reinterpret_cast<volatile unsigned*>(dst)) atomicMax(dst, m);     // (monotone: a stale read only costs an atomic)
+    }
+}
+
+template <int G, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+psroi_bwd_limb(const float* __restrict__ top_diff, int B, int C, int H, int W, int D, int R, PsroiWs ws,
+               float* __restrict__ bottom_diff, int accumulate, int L, int kbase, const unsigned* __restrict__ gmax) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    __shared__ int chunk_s[kBwdChunkCache];
+    const int HW = H * W;
+    const int Wp = (W + 1) | 1, Hp = H + 1, plane_d = Hp * Wp;
+    int* Thi = reinterpret_cast<int*>(smem4);              // [G][Hp][Wp]
+    int* Tlo = Thi + G * plane_d;
+    double* Td = reinterpret_cast<double*>(smem4);         // the same memory as [G][Hp][Wp] doubles (non-finite items)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int items = B * D * G;
+    const int Rp = psroi_rp(R), nchunks = Rp >> 5;
+    const int lomask = (1 << L) - 1;
+    const int per_roi = D * G * G;
+    auto desc = [&](int ck) { return ck < kBwdChunkCache ? chunk_s[ck] : __ldg(ws.chunk + ck); };
+    PT_DECL;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // windows, chunk descriptors, maxima: psroi_prep / psroi_bwd_amax
+    for (int i = tid; i < min(nchunks, kBwdChunkCache); i += THREADS) chunk_s[i] = __ldg(ws.chunk + i);
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
+        const unsigned short* __restrict__ bh = ws.bh + (size_t)ph * Rp;
+        const int obase = ctop * (G * G) + ph * G;
+        const unsigned mbits = __ldg(gmax + (size_t)b * D + ctop);
+        const bool f64 = mbits >= 0x7f800000u;              // (block-uniform)
+        int k = kbase - (int)(mbits >> 23);
+        k = k > 120 ? 120 : k;                              // (k >= -108 by construction)
+        const float sc = __uint_as_float((uint32_t)(127 + k) << 23), isc = __uint_as_float((uint32_t)(127 - k) << 23);
+        __syncthreads();               // the previous item is done with the table (first item: chunk_s filled)
+        {
+            int4* z = reinterpret_cast<int4*>(smem4);
+            for (int i = tid; i < (G * plane_d + 1) / 2; i += THREADS) z[i] = make_int4(0, 0, 0, 0);   // (launcher: + 16 bytes)
+        }
+        __syncthreads();
+        PT(0);                         // zero
+        // ---- corner updates: lane j = k*32 + lane of pass k works on (roi j / G, pw j % G) -- consecutive lanes read
+        // consecutive floats of top_diff
+        for (int ck = warp; ck < nchunks; ck += NW) {
+            const int mm = desc(ck);
+            if (b < (mm & 0xffff) || b > (mm >> 16)) continue;
+            int rbv[G], hbv[G], wbv[G];
+            float gv[G];
+#pragma unroll
+            for (int kk = 0; kk < G; ++kk) {
+                const int j = kk * 32 + lane, nl = j / G;
+                const int n = ck * 32 + nl;
+                rbv[kk] = __ldg(ws.rb + n);
+                hbv[kk] = __ldg(bh + n);
+                wbv[kk] = __ldg(ws.bw + (size_t)ck * 32 * G + j);
+                gv[kk] = n < R ? __ldg(top_diff + (size_t)n * per_roi + obase + (j - nl * G)) : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < G; ++kk) {
+                if (rbv[kk] != b) continue;
+                const int hs = hbv[kk] & 0xff, he = hbv[kk] >> 8, wsx = wbv[kk] & 0xff, we = wbv[kk] >> 8;
+                if (he <= hs || we <= wsx) continue;
+                const float dv = __fdiv_rn(gv[kk], (float)((he - hs) * (we - wsx)));   // kernel.cu:161
+                const int pw = (kk * 32 + lane) % G;
+                const int c00 = pw * plane_d + hs * Wp + wsx, c01 = c00 + (we - wsx);
+                const int c10 = c00 + (he - hs) * Wp, c11 = c10 + (we - wsx);
+                if (!f64) {
+                    const long long q = __float2ll_rn(dv * sc);
+                    const int hi = (int)(q >> L), lo = (int)q & lomask;
+                    const bool wi = we < W, hin = he < H;
+                    atomicAdd(Thi + c00, hi);
+                    atomicAdd(Tlo + c00, lo);
+                    if (wi) {
+                        atomicAdd(Thi + c01, -hi);
+                        atomicAdd(Tlo + c01, -lo);
+                    }
+                    if (hin) {
+                        atomicAdd(Thi + c10, -hi);
+                        atomicAdd(Tlo + c10, -lo);
+                    }
+                    if (wi && hin) {
+                        atomicAdd(Thi + c11, hi);
+                        atomicAdd(Tlo + c11, lo);
+                    }
+                } else {
+                    const double dd = (double)dv;
+                    atomicAdd(Td + c00, dd);
+                    atomicAdd(Td + c01, -dd);
+                    atomicAdd(Td + c10, -dd);
+                    atomicAdd(Td + c11, dd);
+                }
+            }
+        }
+        PT(1);                         // corner updates (own)
+        __syncthreads();
+        PT(2);                         // wait for the others
+        // ---- row scans: one thread per (plane, row); odd pitch: a warp's 32 rows sit in 32 different banks
+        for (int r = tid; r < G * H; r += THREADS) {
+            const int p = r / H, h = r - p * H;
+            if (!f64) {
+                int* rh = Thi + p * plane_d + h * Wp;
+                int* rl = Tlo + p * plane_d + h * Wp;
+                int ax = 0, ay = 0, x0 = 0;
+                for (; x0 + 8 <= W; x0 += 8) {
+                    int vh[8], vl[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        vh[j] = rh[x0 + j];
+                        vl[j] = rl[x0 + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ax += vh[j];
+                        ay += vl[j];
+                        rh[x0 + j] = ax;
+                        rl[x0 + j] = ay;
+                    }
+                }
+                for (; x0 < W; ++x0) {
+                    ax += rh[x0];
+                    ay += rl[x0];
+                    rh[x0] = ax;
+                    rl[x0] = ay;
+                }
+            } else {
+                double* row = Td + p * plane_d + h * Wp;
+                double acc = 0.0;
+                for (int x = 0; x < W; ++x) {
+                    acc += row[x];
+                    row[x] = acc;
+                }
+            }
+        }
+        PT(3);                         // row scans (own)
+        __syncthreads();
+        PT(5);                         // wait for the other rows
+        // ---- column scans + write-out: a warp's stores cover consecutive x; the table is only read.  Integer tables: two
+        // threads per column, the one for the lower half first sums the upper half (independent loads).
+        float* dst = bottom_diff + ((size_t)b * C + (size_t)cg * G) * HW;
+        if (!f64) {
+            const int hh = (H + 1) >> 1;
+            for (int i = tid; i < 2 * G * W; i += THREADS) {
+                const int half = i >= G * W ? 1 : 0, c = i - half * G * W;
+                const int p = c / W, x = c - p * W;
+                const int* ch = Thi + p * plane_d + x;
+                const int* cl = Tlo + p * plane_d + x;
+                float* o = dst + (size_t)p * HW + x;
+                int ax = 0, ay = 0;
+                if (half) {
+#pragma unroll 10
+                    for (int h = 0; h < hh; ++h) {
+                        ax += ch[h * Wp];
+                        ay += cl[h * Wp];
+                    }
+                }
+                const int h_begin = half ? hh : 0, h_end = half ? H : hh;
+#pragma unroll 10
+                for (int h = h_begin; h < h_end; ++h) {
+                    ax += ch[h * Wp];
+                    ay += cl[h * Wp];
+                    // (sum hi) 2^L + (sum lo) as a 64-bit integer: ONE rounding to float; 2^-k is a power of two
+                    const float val = __ll2float_rn(((long long)ax << L) + (long long)ay) * isc;
+                    float* oo = o + (size_t)h * W;
+                    *oo = accumulate ? *oo + val : val;
+                }
+            }
+        } else {
+            for (int i = tid; i < G * W; i += THREADS) {
+                const int p = i / W, x = i - p * W;
+                float* o = dst + (size_t)p * HW + x;
+                const double* col = Td + p * plane_d + x;
+                double acc = 0.0;
+                for (int h = 0; h < H; ++h) {
+                    acc += col[h * Wp];
+                    float* oo = o + (size_t)h * W;
+                    *oo = accumulate ? *oo + (float)acc : (float)acc;
+                }
+            }
+        }
+        PT(4);                         // column scans + write-out (own)
+    }
+}
+
 // ---- backward on integer difference tables, one item per CTA, several CTAs per SM (EXPERIMENT: D2T_PSROI_BWD_INT=1) ----
 // The execution shape of psroi_fwd_isat_mc applied to the adjoint: a 256-thread CTA owns one item (image, ctop, ph) and a
 // [G][H+1][W+2] int32 difference table (71 KB: three CTAs per SM), so the phases of different items overlap on the SM.
@@ -1302,10 +1552,10 @@ PsroiWs carve(void* workspace, int R, int PH, int PW) {
 }
 
 int run_prep(const float* rois, int R, int B, float scale, int PH, int PW, int H, int W, PsroiWs ws,
-             float* top, int D, int zero_invalid, cudaStream_t stream) {
+             float* top, int D, int zero_invalid, cudaStream_t stream, unsigned* gmax = nullptr, int gmax_n = 0) {
     if (R > 0) {
         psroi_prep<<<(psroi_rp(R) + 127) / 128, 128, 0, stream>>>(rois, R, B, scale, PH, PW, H, W, ws, top, D,
-                                                               zero_invalid);
+                                                               zero_invalid, gmax, gmax_n);
         D2T_CHECK_LAUNCH("psroi_prep");
     }
     return 1;
@@ -1330,21 +1580,22 @@ extern "C" __attribute__((visibility("default"))) int d2t_psroi_trace_read(long 
 
 // Kernel variant selection: process-wide, explicit (tests, A/B runs); the environment only seeds the initial value once.
 //   forward : -1 = by geometry (default), 0 = exactly-rounded fp64 tables, 1..4 = a development variant of the integer tables
-//   backward:  0 = fp64 difference tables (default), 1 = integer difference tables (measured slower: 144 vs 91 us, config 5)
+//   backward:  0 = two-limb integer difference tables, native shared atomics (default),
+//              2 = fp64 difference tables (CAS loops), 1 = one-limb integer tables, 3 CTAs / SM (measured slower, less exact)
 static std::atomic<int> g_psroi_fwd_mode{[] { const char* e = getenv("D2T_PSROI_INT"); return e ? atoi(e) : -1; }()};
 static std::atomic<int> g_psroi_bwd_mode{[] { const char* e = getenv("D2T_PSROI_BWD_INT"); return e ? atoi(e) : 0; }()};
 
 extern "C" int d2t_psroi_set_mode(int forward_mode, int backward_mode) {
-    D2T_REQUIRE(forward_mode >= -1 && forward_mode <= 4 && backward_mode >= 0 && backward_mode <= 1,
-                "d2t_psroi_set_mode: forward -1..4, backward 0..1");
+    D2T_REQUIRE(forward_mode >= -1 && forward_mode <= 4 && backward_mode >= 0 && backward_mode <= 2,
+                "d2t_psroi_set_mode: forward -1..4, backward 0..2");
     g_psroi_fwd_mode = forward_mode;
     g_psroi_bwd_mode = backward_mode;
     return 1;
 }
 
 extern "C" size_t d2t_psroi_workspace_bytes(int num_rois, int batch, int pooled_h, int pooled_w) {
-    (void)batch;
-    return align_up(psroi_ws_bytes(num_rois, pooled_h, pooled_w), 256);
+    // (+ the backward's max |top_diff| word per (image, class))
+    return align_up(psroi_ws_bytes(num_rois, pooled_h, pooled_w), 256) + (size_t)(batch > 0 ? batch : 0) * kBwdMaxD * sizeof(unsigned);
 }
 
 extern "C" int d2t_psroi_forward(const float* bottom, int batch, int channels, int height, int width,
@@ -1555,7 +1806,16 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
         ((uintptr_t)workspace & 3) == 0 &&
         workspace_bytes >= d2t_psroi_workspace_bytes(num_rois, batch, pooled_h, pooled_w)) {
         PsroiWs ws = carve(workspace, num_rois, pooled_h, pooled_w);
-        if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, nullptr, out_dim, 0, stream))
+        // default: two-limb integer difference tables (native shared atomics); backward mode 2 = the fp64 CAS loops
+        int RB = 0;
+        while ((1ll << RB) < (long long)psroi_rp(num_rois) + 1) ++RB;
+        const int L = 30 - RB;
+        constexpr size_t kLimbSmem = kMaxDynSmem - 8192;      // (the kernel keeps 4 KB of chunk descriptors in static smem)
+        const bool limb = g_psroi_bwd_mode.load() == 0 && L >= 8 && smem + 16 <= kLimbSmem && out_dim <= kBwdMaxD;
+        unsigned* gmax = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) +
+                                                     align_up(psroi_ws_bytes(num_rois, pooled_h, pooled_w), 256));
+        if (!run_prep(rois, num_rois, batch, scale, pooled_h, pooled_w, height, width, ws, nullptr, out_dim, 0, stream,
+                      limb ? gmax : nullptr, limb ? batch * out_dim : 0))
             return 0;
         static SmemAttrOnce once;
         if (!once.ensure(psroi_bwd_sat<7>, kMaxDynSmem, "psroi_bwd smem attr")) return 0;
@@ -1589,6 +1849,40 @@ extern "C" int d2t_psroi_backward(const float* top_diff, int batch, int channels
                 D2T_CHECK_LAUNCH("psroi_bwd_isat_mc");
                 return 1;
             }
+        }
+        if (limb) {
+            if (num_rois > 0) {
+                {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(num_rois);
+                    cfg.blockDim = dim3(128);
+                    cfg.stream = stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // its loads overlap psroi_prep
+                    attr[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, psroi_bwd_amax, top_diff, (const int*)ws.rb, out_dim, group * group, gmax),
+                                "psroi_bwd_amax launch");
+                }
+            }
+            auto kern = psroi_bwd_limb<7, 1024>;
+            static SmemAttrOnce once_l;
+            if (!once_l.ensure(kern, kLimbSmem, "psroi_bwd_limb smem attr")) return 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(items < sm_count() ? items : sm_count());   // persistent: one CTA per SM
+            cfg.blockDim = dim3(1024);
+            cfg.dynamicSmemBytes = smem + 16;                               // (+ 16: the table is zeroed in int4s)
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // CTA launch overlaps the tail of psroi_bwd_amax
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, top_diff, batch, channels, height, width, out_dim, num_rois, ws,
+                                           bottom_diff, accumulate, L, 156 + L - RB, (const unsigned*)gmax),
+                        "psroi_bwd_limb launch");
+            return 1;
         }
         psroi_bwd_sat<7><<<items < sm_count() ? items : sm_count(), 1024, smem, stream>>>(
             top_diff, batch, channels, height, width, out_dim, num_rois, ws, bottom_diff, accumulate);

@@ -107,7 +107,7 @@ def psroi_backward(top_diff, rois, feature_size, pooled_h, pooled_w, scale, grou
         check(lib().d2t_psroi_backward(top_diff.data_ptr(), B, Cc, H, W, rois.data_ptr(), R, scale, pooled_h, pooled_w,
                                        group, out_dim, grad.data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream()),
               "d2t_psroi_backward")
-        _count(2)
+        _count(3)                                   # psroi_prep, psroi_bwd_amax, psroi_bwd_limb
     return grad
 
 

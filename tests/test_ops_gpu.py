@@ -154,7 +154,7 @@ def test_psroi_backward_integer_tables_experiment(monkeypatch):
         rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
         gt = torch.randn(rois.size(0), D, 7, 7, device="cuda")
         shape = (B, D * 49 + 3, 38, 63)
-        lib().d2t_psroi_set_mode(-1, 0)
+        lib().d2t_psroi_set_mode(-1, 2)
         want = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
         lib().d2t_psroi_set_mode(-1, 1)
         got = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
@@ -162,6 +162,57 @@ def test_psroi_backward_integer_tables_experiment(monkeypatch):
         assert float(got[:, D * 49:].abs().max()) == 0.0
         err = float((got - want).abs().max())
         assert err <= 2e-5 * max(1.0, float(want.abs().max())), err
+
+
+def test_psroi_backward_two_limb_tables_exact():
+    """The default backward (csrc/psroi.cu, psroi_bwd_limb): every dv = top_diff / area is split into two 32-bit limbs of a
+    fixed-point integer and accumulated with native shared-memory integer atomics -- exact, order-independent sums, rounded
+    to fp32 once.  Against the fp64 difference tables (mode 2, themselves exact to 1e-13): equal to one fp32 rounding, for large / tiny gradient magnitudes, unsorted rois, accumulate=1; bit-identical from run to run; a NaN / Inf
+    gradient reaches exactly the cells the fp64 kernel gives it to."""
+    for B, D, R, shuffle, amp in ((2, 30, 2000, False, 1.0), (3, 4, 77, True, 3e4), (1, 2, 5, False, 1e-6), (2, 8, 300, True, 1.0)):
+        torch.manual_seed(R)
+        rois = cu(common.make_rois(R, B, seed=21, shuffle=shuffle))
+        gt = torch.randn(rois.size(0), D, 7, 7, device="cuda") * amp
+        shape = (B, D * 49 + 3, 38, 63)
+        lib().d2t_psroi_set_mode(-1, 2)
+        want = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+        for mode in (0,):
+            lib().d2t_psroi_set_mode(-1, mode)
+            got = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+            again = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+            assert torch.equal(got, again)                                         # deterministic
+            assert float(got[:, D * 49:].abs().max()) == 0.0
+            # one fp32 rounding of the same exact sum on both sides: <= 1 ulp of the cell, + the 2^-34 max|g| term bound
+            err = (got - want).abs()
+            bound = 1.2e-7 * want.abs() + 1e-9 * float(gt.abs().max())
+            assert bool((err <= bound).all()), float((err - bound).max())
+        lib().d2t_psroi_set_mode(-1, 0)
+    # non-finite gradients: the item falls back to the fp64 loops, everything else stays on the integer path
+    B, D, R = 2, 4, 120
+    rois = cu(common.make_rois(R, B, seed=3))
+    gt = torch.randn(R * B, D, 7, 7, device="cuda")
+    gt[7, 1, 3, 2] = float("nan")
+    gt[130, 2, 0, 6] = float("inf")
+    shape = (B, D * 49, 38, 63)
+    lib().d2t_psroi_set_mode(-1, 2)
+    want = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+    lib().d2t_psroi_set_mode(-1, 0)
+    got = ops.psroi_backward(gt, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and bool(torch.isnan(got).any())
+    assert torch.equal(torch.isinf(got), torch.isinf(want))
+    fin = torch.isfinite(want)
+    assert float((got[fin] - want[fin]).abs().max()) <= 1e-6
+    # accumulate = 1 adds to what is there
+    base = torch.randn(shape, device="cuda")
+    gt2 = torch.randn(R * B, D, 7, 7, device="cuda")
+    g0 = ops.psroi_backward(gt2, rois, shape, 7, 7, 1.0 / 16.0, 7, D)
+    acc = base.clone()
+    ws = torch.empty(lib().d2t_psroi_workspace_bytes(R * B, B, 7, 7), dtype=torch.uint8, device="cuda")
+    from d2t_b200._lib import check
+    check(lib().d2t_psroi_backward(gt2.data_ptr(), B, D * 49, 38, 63, rois.data_ptr(), R * B, 1.0 / 16.0, 7, 7, 7, D,
+                                   acc.data_ptr(), 1, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+          "d2t_psroi_backward")
+    assert float((acc - (base + g0)).abs().max()) <= 1e-6
 
 
 def test_psroi_edge_cases(oracle):
