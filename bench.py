@@ -249,20 +249,23 @@ def op_microbench(flush, hbm_gbs):
     ms_f = time_kernel(lambda: ops.roi_align_forward(fr, rr, 7, 7, 1 / 16.), 10, flush)
     ga = torch.randn_like(top_a)
     ms_b = time_kernel(lambda: ops.roi_align_backward(ga, rr, tuple(fr.shape), 7, 7, 1 / 16.), 10, flush)
-    out["roi_align_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs,
-                                "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
+    ms_d = time_kernel(lambda: ops.roi_align_backward(ga, rr, tuple(fr.shape), 7, 7, 1 / 16., deterministic=True), 10, flush)
+    out["roi_align_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "bwd_deterministic_ms": ms_d,
+                                "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs, "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
     top_p, arg_p = ops.roi_pool_forward(fr, rr, 7, 7, 1 / 16.)
     ms_f = time_kernel(lambda: ops.roi_pool_forward(fr, rr, 7, 7, 1 / 16.), 10, flush)
     ms_b = time_kernel(lambda: ops.roi_pool_backward(ga, arg_p, rr, tuple(fr.shape), 7, 7, 1 / 16.), 10, flush)
-    out["roi_pool_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs,
-                               "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
+    ms_d = time_kernel(lambda: ops.roi_pool_backward(ga, arg_p, rr, tuple(fr.shape), 7, 7, 1 / 16., deterministic=True), 10, flush)
+    out["roi_pool_256rois"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "bwd_deterministic_ms": ms_d,
+                               "fwd_frac_hbm": alg_r / ms_f / 1e6 / hbm_gbs, "bwd_frac_hbm": alg_r / ms_b / 1e6 / hbm_gbs}
     gridc = (torch.rand(2, 38, 63, 2, device="cuda") * 2 - 1).contiguous()
     oc_ = ops.roi_crop_forward(fr, gridc)
     ms_f = time_kernel(lambda: ops.roi_crop_forward(fr, gridc), 10, flush)
     gc = torch.randn_like(oc_)
     ms_b = time_kernel(lambda: ops.roi_crop_backward(fr, gridc, gc), 10, flush)
     alg_c = 4.0 * (2 * fr.numel() + gridc.numel())
-    out["roi_crop_38x63_grid"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac_hbm": alg_c / ms_f / 1e6 / hbm_gbs,
+    ms_d = time_kernel(lambda: ops.roi_crop_backward(fr, gridc, gc, deterministic=True), 10, flush)
+    out["roi_crop_38x63_grid"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "bwd_deterministic_ms": ms_d, "fwd_frac_hbm": alg_c / ms_f / 1e6 / hbm_gbs,
                                   "bwd_frac_hbm": 1.5 * alg_c / ms_b / 1e6 / hbm_gbs}
     del fr, rr, top_a, ga, top_p, arg_p, gridc, oc_, gc
     # detection decode + per-class NMS after the network (test_net.py:232-301), 4 frames x 30 classes

@@ -154,6 +154,25 @@ int d2t_nms_batched(const float* boxes, const int* n_valid, int B, int N, int bo
                     float thresh, int max_keep, int* keep, int keep_stride, int* num_keep,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Deterministic backward of the three RoI operators (the reference kernels -- roi_align_kernel.cu:94-143,
+ * roi_pooling_kernel.cu:128-203, roi_crop_cuda_kernel.cu:111-194 -- and the launchers of Part 1 add fp32 terms with
+ * atomicAdd in arrival order: last bits change from run to run).  Here every term is accumulated as a 64-bit fixed-point
+ * integer with the L2's native integer atomic (order-independent) and the finished sums are converted to float once:
+ * bit-identical from run to run, each term resolved to < 2^-37 of max |top_diff| for up to 2^24 terms.  A NaN / Inf
+ * gradient falls back to the float atomics.  scratch: d2t_roi_backward_scratch_bytes(elements of the gradient tensor) bytes,
+ * 8-byte aligned.  align / crop ADD to bottom_diff / grad_images (the caller zeroes, as for the reference launchers); pool
+ * assigns. */
+size_t d2t_roi_backward_scratch_bytes(size_t grad_elems);
+int d2t_roi_align_backward_det(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
+                               int width, int channels, int aligned_height, int aligned_width, const float* bottom_rois,
+                               float* bottom_diff, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+int d2t_roi_pool_backward_det(const float* top_diff, int batch_size, int num_rois, int height, int width, int channels,
+                              int pooled_height, int pooled_width, float* bottom_diff, const int* argmax_data,
+                              void* scratch, size_t scratch_bytes, cudaStream_t stream);
+int d2t_roi_crop_backward_det(const float* grids, const float* grad_output, float* grad_images, int batch_size,
+                              int channels, int height, int width, int num_rois, int grid_h, int grid_w, void* scratch,
+                              size_t scratch_bytes, cudaStream_t stream);
+
 /* Kernel variant of d2t_psroi_forward / _backward, process-wide (tests and A/B measurements; the defaults are the product):
  * forward_mode -1 = chosen by the geometry alone (integer tables when the plane fits, never by batch size or SM count),
  * 0 = exactly-rounded fp64 tables, 1..4 = development variants of the integer tables; backward_mode 0 = two-limb integer

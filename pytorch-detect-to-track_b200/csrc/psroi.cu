@@ -282,7 +282,7 @@ psroi_fwd_sat(const float* __restrict__ feat, int B, int C, int H, int W, int D,
 // (~5e-7 absolute for unit-variance features; the bin mean averages it down; the final division is __fdividef, 2 ulp).  Three items are resident per SM: the
 // copies for items i+1 and i+2 are in flight while item i is scanned and looked up.  Windows are the reference's, bit-exact.
 #ifdef D2T_CONV_TRACE
-__device__ long long g_psroi_trace[160 * 8];   // debug builds: per-CTA phase cycles (scripts/psroi_bench.py)
+__device__ long long g_psroi_trace[480 * 8];   // debug builds: per-CTA phase cycles (scripts/psroi_bench.py)
 #define PT(i) do { if (tid == 0) { const long long t__ = clock64(); g_psroi_trace[blockIdx.x * 8 + (i)] += t__ - pt_last__; pt_last__ = t__; } } while (0)
 #define PT_DECL long long pt_last__ = clock64(); if (tid == 0) for (int i__ = 0; i__ < 8; ++i__) g_psroi_trace[blockIdx.x * 8 + i__] = 0
 #else
@@ -536,6 +536,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
     }
     uint32_t phase = 0;
     bool waited_for_prep = false;
+    PT_DECL;
 
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / (D * G), cg = it % (D * G), ctop = cg / G, ph = cg % G;
@@ -575,6 +576,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             while (!mbar_try_wait(&bar, phase)) __nanosleep(64);   // other CTAs of the SM); the others sleep at the barrier
         }
         phase ^= 1;
+        PT(0);                         // issue + wait for the planes
         __syncthreads();               // planes landed, head/tail scalar stores of stage_issue visible, crange complete
         const int c_lo = crange[0], c_hi = crange[1];   // (read here: three barriers separate it from the next item's reset)
         // TROW (odd W only: thread r walks row r, the row pitch W is odd, so a warp's 32 rows hit 32 different banks): one
@@ -652,6 +654,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             inv[tid] = __uint_as_float((uint32_t)(127 - k) << 23);
         }
         __syncthreads();
+        PT(1);                         // L1 norms + scales
         bool direct = false;
 #pragma unroll
         for (int pq = 0; pq < G; ++pq) direct |= unsafe_p[pq] != 0;          // (block-uniform)
@@ -700,7 +703,9 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 if (2 * lane + 1 < W) irow[2 * lane + 1] = excl + sum2;
             }
         }
+        PT(2);                         // quantise + row scans (own)
         __syncthreads();
+        PT(3);                         // wait for the other rows
         // ---- (3) column scan: one thread per (plane, column)
         for (int i = tid; i < (direct ? 0 : G * W); i += THREADS) {
             const int p = i / W;
@@ -725,7 +730,9 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
                 col[h0 * W] = acc;
             }
         }
+        PT(4);                         // column scans (own)
         __syncthreads();
+        PT(5);                         // wait for the other columns
         if constexpr (!LROI) {
             // ---- (4) lookups: warp per 32-roi chunk of the image's range, lane j -> (roi j / G, pw j % G), G passes
             const unsigned int* __restrict__ bhb = ws.bhb + (size_t)ph * Rp;
@@ -907,6 +914,7 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
             }
         }
     }
+    PT(6);                             // lookups + stores (own)
     if (!waited_for_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
@@ -1574,7 +1582,7 @@ using namespace d2t;
 
 #ifdef D2T_CONV_TRACE
 extern "C" __attribute__((visibility("default"))) int d2t_psroi_trace_read(long long* host) {
-    return cudaMemcpyFromSymbol(host, g_psroi_trace, sizeof(long long) * 160 * 8) == cudaSuccess;
+    return cudaMemcpyFromSymbol(host, g_psroi_trace, sizeof(long long) * 480 * 8) == cudaSuccess;
 }
 #endif
 

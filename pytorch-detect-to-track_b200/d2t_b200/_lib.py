@@ -36,6 +36,10 @@ _SIGS = {
     "PSROIPoolForwardLauncher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "PSROIPoolBackwardLauncher": (_i, [_p, _p, _i, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ROIAlignForwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_roi_backward_scratch_bytes": (_sz, [_sz]),
+    "d2t_roi_align_backward_det": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "d2t_roi_pool_backward_det": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "d2t_roi_crop_backward_det": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "ROIAlignBackwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ROIPoolForwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ROIPoolBackwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -292,11 +292,28 @@ def roi_align_forward(features, rois, ah, aw, scale):
     return top
 
 
-def roi_align_backward(grad_top, rois, feature_size, ah, aw, scale):
+# RoIAlign / RoIPool / RoICrop backward: True = 64-bit fixed-point accumulation (bit-identical from run to run; d2t_roi_*_backward_det),
+# False = the reference's float atomics behind the reference-named launchers.  D2T_ROI_DETERMINISTIC=1 or set at run time.
+DETERMINISTIC_ROI_BACKWARD = os.environ.get("D2T_ROI_DETERMINISTIC", "0") == "1"
+
+
+def _roi_scratch(elems, device):
+    return _ws(lib().d2t_roi_backward_scratch_bytes(elems), device)
+
+
+def roi_align_backward(grad_top, rois, feature_size, ah, aw, scale, deterministic=None):
     _req(grad_top, "grad_output"), _req(rois, "rois")
     B, Cc, H, W = feature_size
+    det = DETERMINISTIC_ROI_BACKWARD if deterministic is None else deterministic
     with torch.cuda.device_of(grad_top):
         grad = torch.zeros(B, Cc, H, W, device=grad_top.device)
+        if det:
+            sc = _roi_scratch(grad.numel(), grad.device)
+            check(lib().d2t_roi_align_backward_det(grad_top.data_ptr(), scale, B, rois.size(0), H, W, Cc, ah, aw, rois.data_ptr(),
+                                                   grad.data_ptr(), sc.data_ptr(), sc.numel(), _stream()),
+                  "d2t_roi_align_backward_det")
+            _count(3)
+            return grad
         check(lib().ROIAlignBackwardLaucher(grad_top.data_ptr(), scale, B, rois.size(0), H, W, Cc, ah, aw,
                                             rois.data_ptr(), grad.data_ptr(), _stream()), "ROIAlignBackwardLaucher")
         _count(1)
@@ -333,11 +350,19 @@ def roi_pool_forward(features, rois, ph, pw, scale):
     return top, argmax
 
 
-def roi_pool_backward(grad_top, argmax, rois, feature_size, ph, pw, scale):
+def roi_pool_backward(grad_top, argmax, rois, feature_size, ph, pw, scale, deterministic=None):
     _req(grad_top, "grad_output")
     B, Cc, H, W = feature_size
+    det = DETERMINISTIC_ROI_BACKWARD if deterministic is None else deterministic
     with torch.cuda.device_of(grad_top):
         grad = torch.empty(B, Cc, H, W, device=grad_top.device)
+        if det:
+            sc = _roi_scratch(grad.numel(), grad.device)
+            check(lib().d2t_roi_pool_backward_det(grad_top.data_ptr(), B, rois.size(0), H, W, Cc, ph, pw, grad.data_ptr(),
+                                                  argmax.data_ptr(), sc.data_ptr(), sc.numel(), _stream()),
+                  "d2t_roi_pool_backward_det")
+            _count(3)
+            return grad
         check(lib().ROIPoolBackwardLaucher(grad_top.data_ptr(), scale, B, rois.size(0), H, W, Cc, ph, pw,
                                            rois.data_ptr(), grad.data_ptr(), argmax.data_ptr(), _stream()),
               "ROIPoolBackwardLaucher")
@@ -383,13 +408,20 @@ def roi_crop_forward(images, grid):
     return out
 
 
-def roi_crop_backward(images, grid, grad_out):
+def roi_crop_backward(images, grid, grad_out, deterministic=None):
     _req(grid, "input2"), _req(grad_out, "grad_output")
     B, Cc, H, W = images.shape
     R, gh, gw, _ = grid.shape
+    det = DETERMINISTIC_ROI_BACKWARD if deterministic is None else deterministic
     with torch.cuda.device_of(grad_out):
         gi = torch.zeros(B, Cc, H, W, device=grad_out.device)
         gg = torch.zeros_like(grid)   # never written by the reference either (roi_crop_cuda_kernel.cu:111-194)
+        if det and grid.is_contiguous() and grad_out.is_contiguous():
+            sc = _roi_scratch(gi.numel(), gi.device)
+            check(lib().d2t_roi_crop_backward_det(grid.data_ptr(), grad_out.data_ptr(), gi.data_ptr(), B, Cc, H, W, R, gh, gw,
+                                                  sc.data_ptr(), sc.numel(), _stream()), "d2t_roi_crop_backward_det")
+            _count(3)
+            return gi, gg
         check(lib().BilinearSamplerBHWD_updateGradInput_cuda_kernel(
             Cc, gw, gh, R, Cc, H, W, B, images.data_ptr(), *images.stride(),
             grid.data_ptr(), grid.stride(0), grid.stride(3), grid.stride(1), grid.stride(2),

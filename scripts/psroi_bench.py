@@ -28,9 +28,9 @@ if hasattr(lib(), "d2t_psroi_trace_read"):
     import ctypes, numpy as np
     os.environ["D2T_PSROI_INT"] = "1"
     psroi(); torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (160 * 8))()
+    buf = (ctypes.c_longlong * (480 * 8))()
     lib().d2t_psroi_trace_read(buf)
-    a = np.array(buf).reshape(160, 8)[:148]
+    a = np.array(buf).reshape(480, 8)[:148]
     print("per-CTA cycles (thread 0): wait data %d | pass 1 (load, L1) %d | scale %d... row scan %d | column scan %d | wait prep %d | lookups %d"
           % tuple(a[:, i].mean() for i in (0, 1, 1, 2, 3, 4, 5)))
     print("   total", a[:, :6].sum(1).mean())

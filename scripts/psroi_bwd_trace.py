@@ -13,8 +13,8 @@ for mode in (0,):
     for _ in range(3):
         ops.psroi_backward(gt, rois, (B, D * 49, 38, 63), 7, 7, 1 / 16., 7, D)
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (160 * 8))()
+    buf = (ctypes.c_longlong * (480 * 8))()
     lib().d2t_psroi_trace_read(buf)
-    a = np.array(buf).reshape(160, 8)[:148]
+    a = np.array(buf).reshape(480, 8)[:148]
     print("mode", mode, "cycles per CTA (3 items; thread 0): zero+scale %d | corners %d | wait others %d | row scans %d | wait rows %d | col scans+write %d | total %d"
           % (tuple(a[:, i].mean() for i in (0, 1, 2, 3, 5, 4)) + (a[:, :7].sum(1).mean(),)))

@@ -535,6 +535,54 @@ def test_roi_align_pool_crop_golden(oracle, golden_cuda):
     assert float(g.grad.abs().max()) == 0.0
 
 
+def test_roi_backward_deterministic(oracle, golden_cuda):
+    """d2t_roi_{align,pool,crop}_backward_det: every term accumulated as a 64-bit fixed-point integer (order-independent)
+    and converted once.  Bit-identical from run to run; equal to the reference goldens and to the float-atomic launchers within
+    the float atomics' own noise; tighter than they are against an fp64 host sum; NaN gradients still propagate."""
+    c = cases.roi_cases()
+    rois, grid, scale = cu(c["rois"]), cu(c["grid"]), c["scale"]
+    feat = cu(c["feat"])
+    shape = tuple(feat.shape)
+    for ah in (7, 8):
+        gt = cu(common.randn((rois.size(0), shape[1], ah, ah), 80 + ah))
+        a = ops.roi_align_backward(gt, rois, shape, ah, ah, scale, deterministic=True)
+        b = ops.roi_align_backward(gt, rois, shape, ah, ah, scale, deterministic=True)
+        assert torch.equal(a, b)
+        close(a, golden_cuda["align%d_grad" % ah], rtol=RTOL, atol=1e-5)
+        close(a, ops.roi_align_backward(gt, rois, shape, ah, ah, scale, deterministic=False), rtol=1e-5, atol=1e-5)
+    top, argmax = ops.roi_pool_forward(feat, rois, 7, 7, scale)
+    gt = cu(common.randn(tuple(top.shape), 90))
+    a = ops.roi_pool_backward(gt, argmax, rois, shape, 7, 7, scale, deterministic=True)
+    assert torch.equal(a, ops.roi_pool_backward(gt, argmax, rois, shape, 7, 7, scale, deterministic=True))
+    close(a, golden_cuda["pool_grad"], rtol=RTOL, atol=1e-5)
+    # exactness: the fixed-point sum against an fp64 scatter-add on the host is within one fp32 rounding
+    want = torch.zeros(feat.numel(), dtype=torch.float64)
+    am = argmax.flatten().cpu().long()
+    ok = am >= 0
+    want.index_add_(0, am[ok], gt.flatten().cpu().double()[ok])
+    err = (a.flatten().cpu().double() - want).abs()
+    assert bool((err <= 6.0e-8 * want.abs() + 1e-10).all()), float(err.max())
+    out = ops.roi_crop_forward(feat, grid)
+    go = cu(common.randn(tuple(out.shape), 91))
+    gi, gg = ops.roi_crop_backward(feat, grid, go, deterministic=True)
+    gi2, _ = ops.roi_crop_backward(feat, grid, go, deterministic=True)
+    assert torch.equal(gi, gi2) and float(gg.abs().max()) == 0.0
+    close(gi, golden_cuda["crop_gimg"], rtol=RTOL, atol=1e-5)
+    # full size, twice, plus a NaN gradient: falls back to the float atomics and propagates it
+    torch.manual_seed(5)
+    featL = torch.randn(2, 256, 38, 63, device="cuda")
+    roisL = cu(common.make_rois(256, 2, seed=24))
+    gtL = torch.randn(512, 256, 7, 7, device="cuda") * 37.0
+    a = ops.roi_align_backward(gtL, roisL, featL.shape, 7, 7, 1 / 16., deterministic=True)
+    assert torch.equal(a, ops.roi_align_backward(gtL, roisL, featL.shape, 7, 7, 1 / 16., deterministic=True))
+    b = ops.roi_align_backward(gtL, roisL, featL.shape, 7, 7, 1 / 16., deterministic=False)
+    assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
+    gtL[3, 5, 2, 2] = float("nan")
+    a = ops.roi_align_backward(gtL, roisL, featL.shape, 7, 7, 1 / 16., deterministic=True)
+    b = ops.roi_align_backward(gtL, roisL, featL.shape, 7, 7, 1 / 16., deterministic=False)
+    assert bool(torch.isnan(a).any()) and torch.equal(torch.isnan(a), torch.isnan(b))
+
+
 def test_roi_crop_is_grid_sample_align_corners():
     """net_utils.py:198-224 names F.grid_sample (torch 0.3 semantics = align_corners=True, zeros
     padding) with the grid's last axis swapped as the comparator for RoICrop."""
