@@ -1075,19 +1075,24 @@ constexpr int kBwdMaxD = 1024;           // workspace: one max |top_diff| word p
 __global__ void __launch_bounds__(128)
 psroi_bwd_amax(const float* __restrict__ top_diff, const int* __restrict__ rb, int D, int per_class,
                unsigned* __restrict__ gmax) {
+    constexpr int NC = 8;                  // classes per warp and batch: D <= 32 is one batch, all loads in flight together
     __shared__ unsigned smax[kBwdMaxD];
-    constexpr int NB = 12;                 // loads in flight per thread (D = 30, 7x7 bins: the whole roi in one batch)
-    const int n = blockIdx.x, lane = threadIdx.x & 31, total = D * per_class;
-    const float* g = top_diff + (size_t)n * total;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) smax[c] = 0u;
-    __syncthreads();
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* g = top_diff + (size_t)n * D * per_class;
     int b = -2;                            // (read after the first batch of loads is in flight: rb comes from psroi_prep, which
-    for (int base = 0; base < total; base += NB * 128) {       // this kernel overlaps -- programmatic dependent launch)
-        unsigned v[NB];
+    for (int c0 = warp; c0 < D; c0 += 4 * NC) {                // this kernel overlaps -- programmatic dependent launch)
+        unsigned m[NC];
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const int e = base + i * 128 + threadIdx.x;
-            v[i] = e < total ? __float_as_uint(__ldg(g + e)) & 0x7fffffffu : 0u;
+        for (int i = 0; i < NC; ++i) {     // a warp owns whole classes: per_class consecutive floats, no atomics inside the block
+            const int c = c0 + 4 * i;
+            const float* gc = g + (size_t)c * per_class;
+            unsigned v0 = 0u, v1 = 0u;
+            if (c < D) {
+                if (lane < per_class) v0 = __float_as_uint(__ldg(gc + lane)) & 0x7fffffffu;
+                if (lane + 32 < per_class) v1 = __float_as_uint(__ldg(gc + lane + 32)) & 0x7fffffffu;
+                for (int o = lane + 64; o < per_class; o += 32) v1 = max(v1, __float_as_uint(__ldg(gc + o)) & 0x7fffffffu);
+            }
+            m[i] = max(v0, v1);
         }
         if (b == -2) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1095,25 +1100,19 @@ psroi_bwd_amax(const float* __restrict__ top_diff, const int* __restrict__ rb, i
         }
         if (b < 0) return;                 // (block-uniform)
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {     // a warp's 32 consecutive elements: <= 2 classes when per_class >= 31
-            const int e = base + i * 128 + threadIdx.x;
-            const int c = min(e, total - 1) / per_class;
-            const int c_lo = __shfl_sync(0xffffffffu, c, 0), c_hi = __shfl_sync(0xffffffffu, c, 31);
-            if (c_hi - c_lo <= 1) {
-                const unsigned m_lo = __reduce_max_sync(0xffffffffu, c == c_lo ? v[i] : 0u);
-                const unsigned m_hi = __reduce_max_sync(0xffffffffu, c == c_hi ? v[i] : 0u);
-                if (lane == 0) atomicMax(&smax[c_lo], m_lo);
-                if (lane == 1) atomicMax(&smax[c_hi], m_hi);
-            } else {
-                atomicMax(&smax[c], v[i]);
-            }
+        for (int i = 0; i < NC; ++i) {
+            const int c = c0 + 4 * i;
+            const unsigned mm = __reduce_max_sync(0xffffffffu, m[i]);
+            if (lane == 0 && c < D) smax[c] = mm;
         }
     }
     __syncthreads();
+    // one coalesced read of the current maxima per block (every block of the grid looks at the same two cache lines: lane-by-
+    // lane reads would queue up in ONE L2 slice), atomics only where this roi raises a maximum
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        const unsigned m = smax[c];
+        const unsigned mm = smax[c];
         unsigned* dst = gmax + (size_t)b * D + c;
-        if (m > *reinterpret_cast<volatile unsigned*>(dst)) atomicMax(dst, m);     // (monotone: a stale read only costs an atomic)
+        if (mm > *reinterpret_cast<volatile unsigned*>(dst)) atomicMax(dst, mm);   // (monotone: a stale read only costs an atomic)
     }
 }
 

@@ -13,3 +13,6 @@ echo "ncu launch list exit $?" >> gpurun_out/r02_fin_status.txt
 cat gpurun_out/r02_fin_status.txt
 tail -n 3 gpurun_out/r02_fin_pytest.log
 tail -c 600 gpurun_out/r02_fin_bench.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"psroi_bwd_limb|psroi_bwd_amax|roi_align_bwd|det_finish" -c 8 -o gpurun_out/r02_fin_psroi_bwd python bench.py --ops-only > gpurun_out/r02_fin_psroi_bwd_ncu.log 2>&1
+echo "ncu psroi bwd exit $?" >> gpurun_out/r02_fin_status.txt
+tail -n 2 gpurun_out/r02_fin_status.txt
