@@ -922,33 +922,58 @@ psroi_fwd_isat_mc(const float* __restrict__ feat, int B, int C, int H, int W, in
 // followed by the softmax over the D classes (rfcn.py:139: F.softmax(cls_score, 1)).  One thread per roi; reads are
 // coalesced over the rois, the [R][D] result is a few hundred KB.
 template <int G>
-__global__ void psroi_vote_finish(const float* __restrict__ vpart, const int* __restrict__ rb, int R, int Rp, int D,
-                                  int softmax, float* __restrict__ vote) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= R) return;
-    float* o = vote + (size_t)n * D;
-    if (__ldg(rb + n) < 0) {                       // roi of no image: zeros, like the pooled output (then softmax of zeros)
-        for (int d = 0; d < D; ++d) o[d] = softmax ? 1.f / (float)D : 0.f;
-        return;
-    }
-    float mx = -3.402823466e+38f;
-    for (int d = 0; d < D; ++d) {
-        float sum = 0.f;
+__global__ void __launch_bounds__(256)
+psroi_vote_finish(const float* __restrict__ vpart, const int* __restrict__ rb, int R, int Rp, int D,
+                  int softmax, float* __restrict__ vote) {
+    // block = 32 rois (lanes: consecutive rois, so the partial sums are read coalesced) x 8 class groups (class d belongs to
+    // group d % 8): every load of a thread is in flight at once; the softmax statistics of a roi cross the groups through
+    // shared memory, added in a fixed order
+    constexpr int NG = 8, DMAX = 16;       // up to NG * DMAX = 128 classes per pass
+    __shared__ float red[NG][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const bool live = n < R;
+    const bool none = live && __ldg(rb + n) < 0;   // roi of no image: zeros, like the pooled output (then softmax of zeros)
+    float mx = -3.402823466e+38f, den = 0.f;
+    for (int pass = 0; pass < (softmax ? 3 : 1); ++pass) {         // softmax: max, sum, write (the partials are re-read: L1 / L2)
+        float acc = pass == 0 ? -3.402823466e+38f : 0.f;
+        for (int d0 = ty; d0 < D; d0 += NG * DMAX) {
+            float v[DMAX];
 #pragma unroll
-        for (int ph = 0; ph < G; ++ph) sum += __ldg(vpart + (size_t)(d * G + ph) * Rp + n);
-        const float v = sum * (1.f / (float)(G * G));
-        o[d] = v;
-        mx = fmaxf(mx, v);
-    }
-    if (softmax) {
-        float den = 0.f;
-        for (int d = 0; d < D; ++d) {
-            const float e = __expf(o[d] - mx);
-            o[d] = e;
-            den += e;
+            for (int i = 0; i < DMAX; ++i) {
+                const int d = d0 + i * NG;
+                float sum = 0.f;
+                if (live && !none && d < D) {
+#pragma unroll
+                    for (int ph = 0; ph < G; ++ph) sum += __ldg(vpart + (size_t)(d * G + ph) * Rp + n);
+                }
+                v[i] = sum * (1.f / (float)(G * G));
+            }
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i) {
+                const int d = d0 + i * NG;
+                if (d >= D) continue;
+                if (!softmax) {
+                    if (live) vote[(size_t)n * D + d] = v[i];
+                } else if (pass == 0) {
+                    acc = fmaxf(acc, v[i]);
+                } else if (pass == 1) {
+                    acc += __expf(v[i] - mx);
+                } else if (live) {
+                    vote[(size_t)n * D + d] = __expf(v[i] - mx) * den;
+                }
+            }
         }
-        const float inv = 1.f / den;
-        for (int d = 0; d < D; ++d) o[d] *= inv;
+        if (softmax && pass < 2) {
+            __syncthreads();                       // (the previous pass's reads of red are done)
+            red[ty][tx] = acc;
+            __syncthreads();
+            float r = red[0][tx];
+#pragma unroll
+            for (int g = 1; g < NG; ++g) r = pass == 0 ? fmaxf(r, red[g][tx]) : r + red[g][tx];
+            if (pass == 0) mx = r;
+            else den = 1.f / r;
+        }
     }
 }
 
@@ -1794,7 +1819,7 @@ extern "C" int d2t_psroi_vote_forward(const float* bottom, int batch, int channe
     D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bottom, batch, channels, height, width, out_dim, num_rois, ws,
                                    (float*)nullptr, (int*)nullptr, vpart),
                 "psroi_fwd_isat_mc (vote) launch");
-    psroi_vote_finish<7><<<(num_rois + 127) / 128, 128, 0, stream>>>(vpart, ws.rb, num_rois, psroi_rp(num_rois), out_dim,
+    psroi_vote_finish<7><<<(num_rois + 31) / 32, 256, 0, stream>>>(vpart, ws.rb, num_rois, psroi_rp(num_rois), out_dim,
                                                                      softmax, vote);
     D2T_CHECK_LAUNCH("psroi_vote_finish");
     return 1;

@@ -13,6 +13,12 @@ echo "ncu launch list exit $?" >> gpurun_out/r02_fin_status.txt
 cat gpurun_out/r02_fin_status.txt
 tail -n 3 gpurun_out/r02_fin_pytest.log
 tail -c 600 gpurun_out/r02_fin_bench.err
+timeout 300 python scripts/r02_heads_profile.py > gpurun_out/r02_fin_train_profile.txt 2>&1
+echo "train profile exit $?" >> gpurun_out/r02_fin_status.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_fin_smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/r02_fin_status.txt
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_fin_bench_reference.json 2> gpurun_out/r02_fin_bench_reference.err
+echo "reference arm exit $?" >> gpurun_out/r02_fin_status.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"psroi_bwd_limb|psroi_bwd_amax|roi_align_bwd|det_finish" -c 8 -o gpurun_out/r02_fin_psroi_bwd python bench.py --ops-only > gpurun_out/r02_fin_psroi_bwd_ncu.log 2>&1
 echo "ncu psroi bwd exit $?" >> gpurun_out/r02_fin_status.txt
-tail -n 2 gpurun_out/r02_fin_status.txt
+tail -n 5 gpurun_out/r02_fin_status.txt
