@@ -32,6 +32,19 @@ namespace {
 
 typedef unsigned long long u64;
 
+// fl(inter / den) > thresh -- the reference's test (nms_cuda_kernel.cu:31-39 divides in fp32) -- decided WITHOUT the division
+// unless the quotient is within 2^-21 of thresh: the rounding of thresh * den and the rounding of the quotient are 2^-24
+// each, so outside that band the comparison of inter with thresh * den (1 +- 2^-21) already fixes the outcome; inside it
+// (and for a non-positive, tiny or non-finite denominator, or thresh <= 0) the IEEE division decides.  Same bits always.
+__device__ __forceinline__ bool quotient_gt(float inter, float den, float thresh) {
+    const float p = __fmul_rn(thresh, den);
+    const bool up = inter > __fmul_rn(p, 1.00000048f);               // 1 + 2^-21: certainly above
+    const bool dn = inter < __fmul_rn(p, 0.99999952f);               // 1 - 2^-21: certainly not above
+    bool r = up;
+    if (!((up || dn) && den > 1e-10f && thresh > 0.f)) r = __fdiv_rn(inter, den) > thresh;     // (rare)
+    return r;
+}
+
 // a = earlier box, b = later box; both as (x1,y1,x2,y2).
 __device__ __forceinline__ bool iou_gt(float4 a, float Sa, float4 b, float thresh, bool fast_reject) {
     float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
@@ -44,7 +57,20 @@ __device__ __forceinline__ bool iou_gt(float4 a, float Sa, float4 b, float thres
     float wb = __fadd_rn(__fsub_rn(b.z, b.x), 1.f), hb = __fadd_rn(__fsub_rn(b.w, b.y), 1.f);
     float t = __fmaf_rn(wb, hb, Sa);
     float den = __fsub_rn(t, inter);
-    return __fdiv_rn(inter, den) > thresh;
+    return quotient_gt(inter, den, thresh);
+}
+// the same decision with the later box's width and height (wb, hb: the expressions above) supplied by the caller
+__device__ __forceinline__ bool iou_gt_wh(float4 a, float Sa, float4 b, float wb, float hb, float thresh, bool fast_reject) {
+    float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+    float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+    float inter = __fmul_rn(w, h);
+    // (inter == 0: `dn` of quotient_gt holds for every positive denominator, and 0 / den is 0, -0 or NaN otherwise -- never
+    // above a thresh >= 0: no separate early exit on this path)
+    (void)fast_reject;
+    float den = __fsub_rn(__fmaf_rn(wb, hb, Sa), inter);
+    return quotient_gt(inter, den, thresh);
 }
 __device__ __forceinline__ float box_area(float4 a) {
     return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
@@ -57,7 +83,7 @@ __device__ __forceinline__ float4 load_box(const float* p) {
 // diagonal.  `limit` (a multiple of 64, or >= N) restricts the problem to the first `limit` boxes of every list -- greedy
 // NMS on a sorted list decides a prefix without looking past it -- `skip_cb` skips the tiles an earlier prefix pass
 // already wrote, and images whose `done` flag is set leave at once (see d2t_nms_batched).
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 16)
 nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N, int box_dim, int cb,
          float thresh, u64* __restrict__ mask, u64* __restrict__ diag, int limit, int skip_cb,
          const int* __restrict__ done) {
@@ -70,6 +96,7 @@ nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N
     const bool fast = thresh >= 0.f;
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
+    __shared__ float2 cwh[64];       // width / height of the column boxes (the `wb`, `hb` of iou_gt: once per box, not per pair)
     // upper-triangle tiles only, row-major: row r starts at t0(r) = r * nb - r (r - 1) / 2
     const int ntri = nb * (nb + 1) / 2;
     for (int t = blockIdx.x; t < ntri; t += gridDim.x) {
@@ -85,6 +112,7 @@ nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N
             float4 b = load_box(bx + (size_t)(c * 64 + tid) * box_dim);
             cbox[tid] = b;
             carea[tid] = box_area(b);
+            cwh[tid] = make_float2(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
         }
         __syncthreads();
         if (tid < row_size) {
@@ -100,9 +128,28 @@ nms_mask(const float* __restrict__ boxes, const int* __restrict__ n_valid, int N
                 }
                 diag[(size_t)img * N + row] = bits;
             } else {
+                if (col_size == 64 && fast) {              // full tile: eight column boxes at a time, constant bit positions
+                    unsigned half[2] = {0u, 0u};
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+                        for (int g = 0; g < 4; ++g) {
+                            unsigned m8 = 0u;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int j = hf * 32 + g * 8 + u;
+                                const float2 wh = cwh[j];
+                                if (iou_gt_wh(a, Sa, cbox[j], wh.x, wh.y, thresh, true)) m8 |= 1u << u;
+                            }
+                            half[hf] |= m8 << (g * 8);
+                        }
+                    }
+                    bits = (u64)half[0] | ((u64)half[1] << 32);
+                } else {
 #pragma unroll 4
-                for (int j = 0; j < col_size; ++j)
-                    if (iou_gt(a, Sa, cbox[j], thresh, fast)) bits |= 1ull << j;
+                    for (int j = 0; j < col_size; ++j)
+                        if (iou_gt(a, Sa, cbox[j], thresh, fast)) bits |= 1ull << j;
+                }
                 mask[((size_t)img * N + row) * cb + c] = bits;
             }
         }
