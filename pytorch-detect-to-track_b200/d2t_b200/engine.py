@@ -147,6 +147,8 @@ class D2TEngine(object):
         self.trk_layer = self._make_layer(self.trk_in, tn.weight, None, tn.bias, want_nhwc=False, want_nchw=True)
         self.conv_flops += self.trk_layer.flops
         self.anchors = rpn.RPN_proposal._anchors.to(dev)
+        self.zero_losses = tuple(torch.zeros(2, 1, device=dev) for _ in range(4))
+        self.zero_track_loss = torch.zeros(1, device=dev)
         self.feat_stride = rpn.feat_stride
         # ---- correlations: straight from the NHWC split features of the two legs into the concat buffer
         self.corr_layers = []
@@ -260,9 +262,9 @@ class D2TEngine(object):
             self.trk_layer.run()
         tracking_pred = ops.psroi_vote(self.trk_layer.out_nchw, rois[0].reshape(-1, 5), 7, 7, 1.0 / 16.0, 7,
                                        4 * self.n_reg).view(B * R, -1)                  # rfcn.py:192-196
-        zero = im_data.new_zeros(L, 1)
-        return (rois, cls_prob, bbox_pred, tracking_pred, zero, zero.clone(), zero.clone(), zero.clone(), [],
-                im_data.new_zeros(1))
+        # (the four eval-mode losses and the tracking loss: constant zeros, allocated once -- five fill / copy launches fewer
+        # at the serial end of the step)
+        return (rois, cls_prob, bbox_pred, tracking_pred) + self.zero_losses + ([], self.zero_track_loss)
 
     __call__ = forward
 
