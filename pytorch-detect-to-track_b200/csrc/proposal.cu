@@ -112,10 +112,14 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
     return ~k;                                                    // descending
 }
 
+// SPLIT: steps 1 and 2 only, the n_take composites go to glist[b][n_take] in global memory (no order) and
+// proposal_rank_gather finishes the job on the whole device.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTopkThreads)
 proposal_topk_gather(const float* __restrict__ boxes, const float* __restrict__ scores, int n_total, int n_take, int P,
-                     float* __restrict__ dets) {
-    extern __shared__ unsigned long long list[];                  // [P] composites
+                     float* __restrict__ dets, unsigned long long* __restrict__ glist) {
+    extern __shared__ unsigned long long list_smem[];             // [P] composites (!SPLIT)
+    unsigned long long* list = SPLIT ? glist + (size_t)blockIdx.x * n_take : list_smem;
     __shared__ uint32_t whist[32][256];                           // per-warp histograms
     __shared__ uint32_t s_prefix, s_remaining, s_cnt, s_eqbase;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -248,6 +252,7 @@ proposal_topk_gather(const float* __restrict__ boxes, const float* __restrict__ 
         }
     }
     __syncthreads();
+    if constexpr (SPLIT) return;
     const int cnt = (int)s_cnt;                            // == n_take
     for (int i = cnt + tid; i < P; i += kTopkThreads) list[i] = ~0ull;
     __syncthreads();
@@ -342,8 +347,75 @@ extern "C" int d2t_proposal_topk_gather(const float* boxes, const float* scores,
     while (P < n_take) P <<= 1;
     const size_t smem = (size_t)P * 8;
     static SmemAttrOnce once;
-    if (!once.ensure(proposal_topk_gather, kTopkMaxList * 8, "proposal_topk_gather smem attr")) return 0;
-    proposal_topk_gather<<<B, kTopkThreads, smem, stream>>>(boxes, scores, n_total, n_take, P, dets);
+    if (!once.ensure(proposal_topk_gather<false>, kTopkMaxList * 8, "proposal_topk_gather smem attr")) return 0;
+    proposal_topk_gather<false><<<B, kTopkThreads, smem, stream>>>(boxes, scores, n_total, n_take, P, dets, nullptr);
     D2T_CHECK_LAUNCH("proposal_topk_gather");
+    return 1;
+}
+
+// ---- the same result in two launches that use the whole device: select + compaction (one CTA per image, above), then a
+// RANK sort -- the composites are all distinct, so the place of one of them in the sorted list is the number of composites
+// below it: n_take^2 independent 64-bit comparisons per image spread over all SMs instead of 91 barrier-separated bitonic
+// stages on one -- fused with the gather.
+namespace d2t {
+namespace {
+constexpr int kRankThreads = 128, kRankTile = 2048;
+__global__ void __launch_bounds__(kRankThreads)
+proposal_rank_gather(const unsigned long long* __restrict__ glist, const float* __restrict__ boxes,
+                     const float* __restrict__ scores, int n_total, int n_take, float* __restrict__ dets) {
+    __shared__ ulonglong2 tile[kRankTile / 2];
+    const int b = blockIdx.y, i = blockIdx.x * kRankThreads + threadIdx.x;
+    const unsigned long long* lst = glist + (size_t)b * n_take;
+    const unsigned long long mine = i < n_take ? lst[i] : ~0ull;
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;                           // (four independent counters: no serial add chain)
+    for (int t0 = 0; t0 < n_take; t0 += kRankTile) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < kRankTile; j += kRankThreads)
+            reinterpret_cast<unsigned long long*>(tile)[j] = t0 + j < n_take ? lst[t0 + j] : ~0ull;   // (padding: never below)
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < kRankTile / 2; j += 2) {
+            const ulonglong2 v = tile[j], w = tile[j + 1];        // (every thread reads the same 16 bytes: a broadcast)
+            r0 += v.x < mine;
+            r1 += v.y < mine;
+            r2 += w.x < mine;
+            r3 += w.y < mine;
+        }
+    }
+    const int rank = (r0 + r1) + (r2 + r3);
+    if (i < n_take) {
+        const uint32_t src = (uint32_t)(mine & 0xffffffffull);
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float v = 0.f;
+        if (src < (uint32_t)n_total) {
+            bx = reinterpret_cast<const float4*>(boxes)[(size_t)b * n_total + src];
+            v = scores[(size_t)b * n_total + src];
+        }
+        float* o = dets + ((size_t)b * n_take + rank) * 5;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = v;
+    }
+}
+}  // namespace
+}  // namespace d2t
+
+extern "C" size_t d2t_proposal_topk_scratch_bytes(int B, int n_take) {
+    return (size_t)(B > 0 ? B : 0) * (size_t)(n_take > 0 ? n_take : 0) * sizeof(unsigned long long);
+}
+
+// d2t_proposal_topk_gather in two launches (any n_take <= n_total <= 32768); scratch: d2t_proposal_topk_scratch_bytes(B,
+// n_take) bytes, 8-byte aligned.
+extern "C" int d2t_proposal_topk_gather_split(const float* boxes, const float* scores, int B, int n_total, int n_take,
+                                              float* dets, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    D2T_REQUIRE(B > 0 && boxes && scores && dets && ((uintptr_t)boxes & 15) == 0 && n_total > 0 &&
+                    n_total <= kTopkKeysPerThread * kTopkThreads && n_take > 0 && n_take <= n_total,
+                "d2t_proposal_topk_gather_split: bad arguments (n_take <= n_total <= 32768, boxes 16-byte aligned)");
+    D2T_REQUIRE(scratch && ((uintptr_t)scratch & 7) == 0 && scratch_bytes >= d2t_proposal_topk_scratch_bytes(B, n_take),
+                "d2t_proposal_topk_gather_split: scratch too small or misaligned");
+    unsigned long long* glist = reinterpret_cast<unsigned long long*>(scratch);
+    proposal_topk_gather<true><<<B, kTopkThreads, 0, stream>>>(boxes, scores, n_total, n_take, 0, dets, glist);
+    D2T_CHECK_LAUNCH("proposal_topk_gather<split>");
+    proposal_rank_gather<<<dim3((n_take + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, stream>>>(
+        glist, boxes, scores, n_total, n_take, dets);
+    D2T_CHECK_LAUNCH("proposal_rank_gather");
     return 1;
 }

@@ -65,6 +65,8 @@ _SIGS = {
     "d2t_proposal_write_rois": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     "d2t_proposal_topk_supported": (_i, [_i, _i]),
     "d2t_proposal_topk_gather": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "d2t_proposal_topk_scratch_bytes": (_sz, [_i, _i]),
+    "d2t_proposal_topk_gather_split": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     # ---- convolution engine
     "d2t_conv_plan_create": (_p, [_p] * 9),
     "d2t_conv_plan_destroy": (None, [_p]),

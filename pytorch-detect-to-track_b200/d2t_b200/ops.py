@@ -481,13 +481,24 @@ def proposal_gather(boxes, scores, order, n_take):
 # torch.sort (cub, device-wide) + d2t_proposal_gather.  Measured on B200 at 4 x 28728 scores -> top 6000: ~115 us against
 # ~40 us for the cub kernels + gather -- four CTAs cannot match a device-wide radix sort -- so it is off by default.
 HAND_WRITTEN_TOPK = os.environ.get("D2T_TOPK", "0") == "1"
+# D2T_TOPK=2: the two-launch form (select + compaction, then a device-wide rank sort fused with the gather): 85 us against
+# 124 us for torch.sort + gather when timed alone (scripts/topk_bench.py) -- but inside the step the 1024-thread select CTAs
+# take four SMs away from the persistent conv kernel that starts beside them, which then waits for its four late CTAs:
+# 5.51-5.55 ms against 5.46-5.47 ms per step.  cub's dozen tiny kernels slip into the gaps between conv launches.  Off.
+SPLIT_TOPK = os.environ.get("D2T_TOPK", "0") == "2"
 
 
-def proposal_topk_gather(boxes, scores, n_take):
+def proposal_topk_gather(boxes, scores, n_take, split=False):
     _req(boxes, "boxes"), _req(scores, "scores")
     B, n_total, _ = boxes.shape
     with torch.cuda.device_of(boxes):
         dets = torch.empty(B, n_take, 5, device=boxes.device)
+        if split:      # select + compaction (one CTA per image), then a device-wide rank sort fused with the gather
+            sc = _ws(lib().d2t_proposal_topk_scratch_bytes(B, n_take), boxes.device)
+            check(lib().d2t_proposal_topk_gather_split(boxes.data_ptr(), scores.data_ptr(), B, n_total, n_take, dets.data_ptr(),
+                                                       sc.data_ptr(), sc.numel(), _stream()), "d2t_proposal_topk_gather_split")
+            _count(2)
+            return dets
         check(lib().d2t_proposal_topk_gather(boxes.data_ptr(), scores.data_ptr(), B, n_total, n_take, dets.data_ptr(),
                                              _stream()), "d2t_proposal_topk_gather")
         _count(1)
@@ -511,7 +522,9 @@ def proposals(anchors, deltas, cls_prob, im_info, feat_stride, pre_nms_topN, pos
     boxes, scores = proposal_decode(anchors, deltas, cls_prob, im_info, feat_stride)
     n_total = scores.size(1)
     n_take = min(pre_nms_topN, n_total) if pre_nms_topN > 0 else n_total
-    if HAND_WRITTEN_TOPK and lib().d2t_proposal_topk_supported(n_total, n_take):
+    if SPLIT_TOPK and n_total <= 32768:
+        dets = proposal_topk_gather(boxes, scores, n_take, split=True)
+    elif HAND_WRITTEN_TOPK and lib().d2t_proposal_topk_supported(n_total, n_take):
         dets = proposal_topk_gather(boxes, scores, n_take)          # select + stable sort + gather, one launch
     else:
         order = torch.sort(scores, dim=1, descending=True, stable=True)[1]

@@ -748,10 +748,11 @@ def test_proposal_topk_gather_matches_stable_sort(n_total, n_take, B):
         boxes = torch.rand(B, n_total, 4, device="cuda", generator=g) * 100
         order = torch.sort(scores, dim=1, descending=True, stable=True)[1]
         want = ops.proposal_gather(boxes, scores, order, n_take)
-        got = ops.proposal_topk_gather(boxes, scores, n_take)
-        torch.cuda.synchronize()
-        same = (got == want) | (torch.isnan(got) & torch.isnan(want))
-        assert bool(same.all()), (kind, n_total, n_take, int((~same).sum()))
+        for split in (False, True):          # one launch (bitonic sort in one CTA) / two launches (device-wide rank sort)
+            got = ops.proposal_topk_gather(boxes, scores, n_take, split=split)
+            torch.cuda.synchronize()
+            same = (got == want) | (torch.isnan(got) & torch.isnan(want))
+            assert bool(same.all()), (kind, split, n_total, n_take, int((~same).sum()))
 
 
 def test_proposals_same_with_hand_written_topk():
@@ -761,11 +762,11 @@ def test_proposals_same_with_hand_written_topk():
     from model.utils.config import cfg
     anchors = torch.from_numpy(generate_anchors(scales=np.array(cfg.ANCHOR_SCALES), ratios=np.array(cfg.ANCHOR_RATIOS))).float().cuda()
     outs = []
-    saved = ops.HAND_WRITTEN_TOPK
+    saved = ops.HAND_WRITTEN_TOPK, ops.SPLIT_TOPK
     try:
-        for flag in (False, True):
-            ops.HAND_WRITTEN_TOPK = flag
+        for flag, split in ((False, False), (True, False), (False, True)):
+            ops.HAND_WRITTEN_TOPK, ops.SPLIT_TOPK = flag, split
             outs.append(ops.proposals(anchors, cu(deltas), cu(prob), cu(im_info), 16, 6000, 300, 0.7))
     finally:
-        ops.HAND_WRITTEN_TOPK = saved
-    assert torch.equal(outs[0], outs[1])
+        ops.HAND_WRITTEN_TOPK, ops.SPLIT_TOPK = saved
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
