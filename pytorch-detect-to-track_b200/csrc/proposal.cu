@@ -398,8 +398,160 @@ proposal_rank_gather(const unsigned long long* __restrict__ glist, const float* 
 }  // namespace
 }  // namespace d2t
 
+// ---- the selection itself spread over the device: two 16-bit histogram levels in global memory instead of four 8-bit
+// radix passes inside one 1024-thread CTA per image (which holds four SMs for tens of microseconds -- long enough to delay the
+// four CTAs of a persistent conv kernel that starts beside it).  Six short launches: hist (level 1) -> scan -> hist (level 2,
+// keys inside the threshold bucket) -> scan -> compaction -> rank sort + gather.
+namespace d2t {
+namespace {
+constexpr int kSelBins = 65536;
+struct TopkSel {          // per image, in the scratch
+    unsigned prefix16;    // the 16 leading bits of the threshold key T
+    unsigned remaining;   // how many keys inside the level-1 bucket are taken
+    unsigned T;           // the n_take-th key in descending score order
+    unsigned need_eq;     // how many keys equal to T are taken (the first ones in index order)
+};
+
+// level 1: all keys by their leading 16 bits; level 2: the keys of the threshold bucket by their trailing 16 bits
+template <int LEVEL>
+__global__ void __launch_bounds__(256)
+topk_hist(const float* __restrict__ scores, int n_total, unsigned* __restrict__ hist, const TopkSel* __restrict__ sel) {
+    const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_total) return;
+    const uint32_t k = desc_key(__ldg(scores + (size_t)b * n_total + i));
+    unsigned* h = hist + (size_t)b * kSelBins;
+    if (LEVEL == 1) atomicAdd(h + (k >> 16), 1u);
+    else if ((k >> 16) == sel[b].prefix16) atomicAdd(h + (k & 0xffffu), 1u);
+}
+
+// the bin in which the running count (ascending bins) reaches `want`: one CTA per image, a warp per 2048 consecutive bins
+template <int LEVEL>
+__global__ void __launch_bounds__(1024)
+topk_scan(const unsigned* __restrict__ hist, TopkSel* __restrict__ sel, int n_take) {
+    __shared__ unsigned wtot[32];
+    __shared__ unsigned s_warp, s_before;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned* h = hist + (size_t)b * kSelBins + warp * 2048;
+    const unsigned want = LEVEL == 1 ? (unsigned)n_take : sel[b].remaining;
+    unsigned part = 0;
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) part += h[r * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) wtot[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned v = wtot[lane];
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (incl - v < want && want <= incl) {       // exactly one lane (the total is >= want)
+            s_warp = (unsigned)lane;
+            s_before = incl - v;
+        }
+    }
+    __syncthreads();
+    if (warp != (int)s_warp) return;
+    unsigned before = s_before;
+    for (int r = 0; r < 64; ++r) {                   // 32 consecutive bins per round
+        const unsigned v = h[r * 32 + lane];
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const bool hit = before + incl - v < want && want <= before + incl;
+        if (__any_sync(0xffffffffu, hit)) {
+            if (hit) {
+                const unsigned bin = (unsigned)(warp * 2048 + r * 32 + lane), cum = before + incl - v;
+                if (LEVEL == 1) {
+                    sel[b].prefix16 = bin;
+                    sel[b].remaining = want - cum;
+                } else {
+                    sel[b].T = (sel[b].prefix16 << 16) | bin;
+                    sel[b].need_eq = want - cum;
+                }
+            }
+            return;
+        }
+        before += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// compaction: blocks x < gridDim.x - 1 append the keys above the threshold of their 1024 elements (any order: the rank sort
+// follows) behind a per-image counter; the last block of every image walks ALL elements in index order and places the first
+// need_eq keys equal to the threshold behind the n_take - need_eq keys above it.
+__global__ void __launch_bounds__(256)
+topk_compact(const float* __restrict__ scores, int n_total, int n_take, const TopkSel* __restrict__ sel,
+             unsigned* __restrict__ counter, unsigned long long* __restrict__ glist) {
+    __shared__ unsigned wcnt[8], wbase[8], s_total;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* sc = scores + (size_t)b * n_total;
+    const unsigned T = sel[b].T, need = sel[b].need_eq;
+    unsigned long long* lst = glist + (size_t)b * n_take;
+    if ((int)blockIdx.x < (int)gridDim.x - 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+            const uint32_t k = i < n_total ? desc_key(__ldg(sc + i)) : 0xffffffffu;
+            const bool lt = i < n_total && k < T;
+            const unsigned m = __ballot_sync(0xffffffffu, lt);
+            unsigned base = 0;
+            if (lane == 0 && m) base = atomicAdd(counter + b, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lt) lst[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)k << 32) | (uint32_t)i;
+        }
+        return;
+    }
+    const unsigned n_lt = (unsigned)n_take - need;
+    unsigned seen = 0;                                // equal keys before this round (block-uniform)
+    for (int i1 = 0; i1 < n_total && seen < need; i1 += 2048) {
+      uint32_t kk[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                   // eight rounds' loads in flight together
+          const int i = i1 + q * 256 + threadIdx.x;
+          kk[q] = i < n_total ? desc_key(__ldg(sc + i)) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = i1 + q * 256 + threadIdx.x;
+        const bool eq = i < n_total && kk[q] == T;
+        const unsigned m = __ballot_sync(0xffffffffu, eq);
+        if (!__syncthreads_or(m != 0u)) continue;
+        if (lane == 0) wcnt[warp] = (unsigned)__popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < 8; ++w) {
+                wbase[w] = t;
+                t += wcnt[w];
+            }
+            s_total = t;
+        }
+        __syncthreads();
+        if (eq) {
+            const unsigned rank = seen + wbase[warp] + __popc(m & ((1u << lane) - 1u));
+            if (rank < need) lst[n_lt + rank] = ((unsigned long long)T << 32) | (uint32_t)i;
+        }
+        seen += s_total;
+        __syncthreads();
+      }
+    }
+}
+}  // namespace
+}  // namespace d2t
+
+// [B][n_take] composites | [B] TopkSel | [B] counters (+ pad) | 2 x [B][65536] histogram levels
+static size_t topk_list_bytes(int B, int n_take) {
+    return ((size_t)(B > 0 ? B : 0) * (size_t)(n_take > 0 ? n_take : 0) * sizeof(unsigned long long) + 255) / 256 * 256;
+}
 extern "C" size_t d2t_proposal_topk_scratch_bytes(int B, int n_take) {
-    return (size_t)(B > 0 ? B : 0) * (size_t)(n_take > 0 ? n_take : 0) * sizeof(unsigned long long);
+    const size_t b = (size_t)(B > 0 ? B : 0);
+    return topk_list_bytes(B, n_take) + (b * (sizeof(TopkSel) + sizeof(unsigned)) + 255) / 256 * 256 + 2 * b * kSelBins * sizeof(unsigned);
 }
 
 // d2t_proposal_topk_gather in two launches (any n_take <= n_total <= 32768); scratch: d2t_proposal_topk_scratch_bytes(B,
@@ -412,8 +564,29 @@ extern "C" int d2t_proposal_topk_gather_split(const float* boxes, const float* s
     D2T_REQUIRE(scratch && ((uintptr_t)scratch & 7) == 0 && scratch_bytes >= d2t_proposal_topk_scratch_bytes(B, n_take),
                 "d2t_proposal_topk_gather_split: scratch too small or misaligned");
     unsigned long long* glist = reinterpret_cast<unsigned long long*>(scratch);
-    proposal_topk_gather<true><<<B, kTopkThreads, 0, stream>>>(boxes, scores, n_total, n_take, 0, dets, glist);
-    D2T_CHECK_LAUNCH("proposal_topk_gather<split>");
+    char* p = reinterpret_cast<char*>(scratch) + topk_list_bytes(B, n_take);
+    TopkSel* sel = reinterpret_cast<TopkSel*>(p);
+    unsigned* counter = reinterpret_cast<unsigned*>(sel + B);
+    const size_t meta = ((size_t)B * (sizeof(TopkSel) + sizeof(unsigned)) + 255) / 256 * 256;
+    unsigned* hist1 = reinterpret_cast<unsigned*>(p + meta);
+    unsigned* hist2 = hist1 + (size_t)B * kSelBins;
+    if (n_take >= n_total) {           // everything is taken: no selection (T = the all-ones key no real score maps to)
+        D2T_CUDA_OK(cudaMemsetAsync(p, 0xff, meta, stream), "topk scratch memset");
+        D2T_CUDA_OK(cudaMemsetAsync(counter, 0, (size_t)B * sizeof(unsigned), stream), "topk counter memset");
+    } else {
+        D2T_CUDA_OK(cudaMemsetAsync(p, 0, meta + 2 * (size_t)B * kSelBins * sizeof(unsigned), stream), "topk scratch memset");
+        const dim3 ge((n_total + 255) / 256, B);
+        topk_hist<1><<<ge, 256, 0, stream>>>(scores, n_total, hist1, sel);
+        D2T_CHECK_LAUNCH("topk_hist<1>");
+        topk_scan<1><<<B, 1024, 0, stream>>>(hist1, sel, n_take);
+        D2T_CHECK_LAUNCH("topk_scan<1>");
+        topk_hist<2><<<ge, 256, 0, stream>>>(scores, n_total, hist2, sel);
+        D2T_CHECK_LAUNCH("topk_hist<2>");
+        topk_scan<2><<<B, 1024, 0, stream>>>(hist2, sel, n_take);
+        D2T_CHECK_LAUNCH("topk_scan<2>");
+    }
+    topk_compact<<<dim3((n_total + 1023) / 1024 + 1, B), 256, 0, stream>>>(scores, n_total, n_take, sel, counter, glist);
+    D2T_CHECK_LAUNCH("topk_compact");
     proposal_rank_gather<<<dim3((n_take + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, stream>>>(
         glist, boxes, scores, n_total, n_take, dets);
     D2T_CHECK_LAUNCH("proposal_rank_gather");

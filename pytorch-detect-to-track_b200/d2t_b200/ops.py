@@ -481,10 +481,11 @@ def proposal_gather(boxes, scores, order, n_take):
 # torch.sort (cub, device-wide) + d2t_proposal_gather.  Measured on B200 at 4 x 28728 scores -> top 6000: ~115 us against
 # ~40 us for the cub kernels + gather -- four CTAs cannot match a device-wide radix sort -- so it is off by default.
 HAND_WRITTEN_TOPK = os.environ.get("D2T_TOPK", "0") == "1"
-# D2T_TOPK=2: the two-launch form (select + compaction, then a device-wide rank sort fused with the gather): 85 us against
-# 124 us for torch.sort + gather when timed alone (scripts/topk_bench.py) -- but inside the step the 1024-thread select CTAs
-# take four SMs away from the persistent conv kernel that starts beside them, which then waits for its four late CTAs:
-# 5.51-5.55 ms against 5.46-5.47 ms per step.  cub's dozen tiny kernels slip into the gaps between conv launches.  Off.
+# D2T_TOPK=2: the selection and sort in six short launches of our own (two 16-bit histogram levels + scans, compaction, a
+# device-wide rank sort fused with the gather; d2t_proposal_topk_gather_split), bit-identical to the stable sort.  On B200 at
+# 4 x 28728 -> 6000: 105 us against 118 us for torch.sort + gather alone (scripts/topk_bench.py), 1 % slower inside the step (5.49-5.51 against
+# 5.44-5.47 ms: the n_take^2 rank sort holds the SMs the next conv kernel wants); at n_take = 12000 (training) the rank
+# sort's quadratic cost loses outright (180 against 110 us).  Off by default.
 SPLIT_TOPK = os.environ.get("D2T_TOPK", "0") == "2"
 
 
@@ -493,11 +494,11 @@ def proposal_topk_gather(boxes, scores, n_take, split=False):
     B, n_total, _ = boxes.shape
     with torch.cuda.device_of(boxes):
         dets = torch.empty(B, n_take, 5, device=boxes.device)
-        if split:      # select + compaction (one CTA per image), then a device-wide rank sort fused with the gather
+        if split:      # two-level histogram select + compaction, then a device-wide rank sort fused with the gather
             sc = _ws(lib().d2t_proposal_topk_scratch_bytes(B, n_take), boxes.device)
             check(lib().d2t_proposal_topk_gather_split(boxes.data_ptr(), scores.data_ptr(), B, n_total, n_take, dets.data_ptr(),
                                                        sc.data_ptr(), sc.numel(), _stream()), "d2t_proposal_topk_gather_split")
-            _count(2)
+            _count(6)                                   # hist, scan, hist, scan, compaction, rank sort + gather
             return dets
         check(lib().d2t_proposal_topk_gather(boxes.data_ptr(), scores.data_ptr(), B, n_total, n_take, dets.data_ptr(),
                                              _stream()), "d2t_proposal_topk_gather")

@@ -14,7 +14,7 @@ for B, n_total, n_take in ((4, 28728, 6000), (4, 28728, 12000)):
         order = torch.sort(scores, dim=1, descending=True, stable=True)[1]
         return ops.proposal_gather(boxes, scores, order, n_take)
     t = {"cub_sort+gather": bench.time_kernel(cub, 20, flush),
-         "select+rank_sort (2 launches)": bench.time_kernel(lambda: ops.proposal_topk_gather(boxes, scores, n_take, split=True), 20, flush)}
+         "histogram select + rank sort (6 launches)": bench.time_kernel(lambda: ops.proposal_topk_gather(boxes, scores, n_take, split=True), 20, flush)}
     if n_take <= 8192:
         t["one_cta_bitonic"] = bench.time_kernel(lambda: ops.proposal_topk_gather(boxes, scores, n_take), 20, flush)
     print(B, n_total, n_take, {k: "%.1f us" % (v * 1e3) for k, v in t.items()}, flush=True)
