@@ -238,8 +238,9 @@ int d2t_proposal_gather(const float* boxes, const float* scores, const int64_t* 
 int d2t_proposal_topk_supported(int n_total, int n_take);
 int d2t_proposal_topk_gather(const float* boxes, const float* scores, int B, int n_total, int n_take, float* dets,
                              cudaStream_t stream);
-/* The same result in two launches that use the whole device -- select + compaction, then a rank sort of the n_take distinct
- * (score, index) composites fused with the gather -- for any n_take <= n_total <= 32768.  scratch:
+/* The same result in six short launches that use the whole device -- two 16-bit histogram levels in global memory with their
+ * scans (the n_take-th key), compaction, then a rank sort of the n_take distinct (score, index) composites fused with the
+ * gather -- for any n_take <= n_total <= 32768.  scratch:
  * d2t_proposal_topk_scratch_bytes(B, n_take) bytes, 8-byte aligned. */
 size_t d2t_proposal_topk_scratch_bytes(int B, int n_take);
 int d2t_proposal_topk_gather_split(const float* boxes, const float* scores, int B, int n_total, int n_take, float* dets,

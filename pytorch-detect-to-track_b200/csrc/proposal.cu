@@ -554,7 +554,7 @@ extern "C" size_t d2t_proposal_topk_scratch_bytes(int B, int n_take) {
     return topk_list_bytes(B, n_take) + (b * (sizeof(TopkSel) + sizeof(unsigned)) + 255) / 256 * 256 + 2 * b * kSelBins * sizeof(unsigned);
 }
 
-// d2t_proposal_topk_gather in two launches (any n_take <= n_total <= 32768); scratch: d2t_proposal_topk_scratch_bytes(B,
+// d2t_proposal_topk_gather in six short launches (any n_take <= n_total <= 32768); scratch: d2t_proposal_topk_scratch_bytes(B,
 // n_take) bytes, 8-byte aligned.
 extern "C" int d2t_proposal_topk_gather_split(const float* boxes, const float* scores, int B, int n_total, int n_take,
                                               float* dets, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
