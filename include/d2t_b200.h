@@ -365,10 +365,13 @@ d2t_conv_plan* d2t_corr_plan_create(int N, int C, int c_real, int H, int W, int 
  *   { const float* w_oihw; const float* scale_or_null; const float* amax; void* hi; void* lo;
  *     int O, I, R, S, pad (cin_pad | cout_pad), rows (backward-data: rows of the operand), dgrad (0 | 1), first_block; }
  * = the arguments of d2t_conv_pack_weights_f16_dev (dgrad = 0) / _dgrad (dgrad = 1); item i owns blocks
- * [first_block_i, first_block_{i+1}) with ceil(elements_i / 1024) blocks, first_block_0 = 0, total_blocks their sum.
- * Same values, bit for bit, as the per-operand entry points. */
+ * [first_block_i, first_block_{i+1}) with d2t_conv_repack_item_blocks(...) blocks (one per tile of 32 x 32 channels; 0: filter
+ * with more than 9 taps, not supported), first_block_0 = 0, total_blocks their sum.
+ * block_item (device, [total_blocks] int32, may be NULL): the item every block belongs to -- saves each block a binary search
+ * over the items.  Same values, bit for bit, as the per-operand entry points. */
 size_t d2t_conv_repack_item_bytes(void);
-int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, cudaStream_t stream);
+int d2t_conv_repack_item_blocks(int O, int I, int R, int S, int pad, int rows, int dgrad);
+int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, const int* block_item, cudaStream_t stream);
 /* ---- Training path of the convolution engine: backward-data and weight-gradient on the same tcgen05 kernel ----
  * Replaces the cuDNN dgrad / wgrad calls autograd makes for the trainable convolutions of the reference's training step
  * (trainval_net.py:365-373 over faster_rcnn/resnet.py:66-109, 279-295, rfcn.py:49-53, rpn/rpn.py:28-36); 3xFP16 like

@@ -247,9 +247,68 @@ struct RepackItem {
     int first_block;
 };
 
-__global__ void __launch_bounds__(256) repack_many(const RepackItem* __restrict__ items, int n_items) {
+// A block re-packs one tile of 32 output channels x 32 input channels x all R*S taps through shared memory: the OIHW source
+// is read in runs of 32 * R*S consecutive floats (one output channel's slice), the packed operand -- [O][R*S][cin_pad] for
+// the forward convolution, [rows][R*S][cout_pad] of the flipped transpose for backward-data -- is written in runs of 32
+// consecutive fp16 values.  (Element-by-element, the backward-data operand read its source with a stride of I*R*S floats
+// and every index took three 64-bit divisions: 0.65 ms per step for 0.4 GB of traffic.)  Taps: R*S <= kRepackMaxRS.
+constexpr int kRepackMaxRS = 9;
+__host__ __device__ inline int repack_item_blocks(int O, int I, int RS, int pad, int rows, int dgrad) {
+    (void)RS;
+    return dgrad ? ((rows + 31) / 32) * ((pad + 31) / 32) : ((O + 31) / 32) * ((pad + 31) / 32);
+}
+
+// (RS_ is a compile-time constant for the two filter sizes of the network -- the divisions by R*S below were most of the
+// kernel's instructions when it was a run-time value -- 0 = any R*S <= kRepackMaxRS)
+template <int RS_>
+__device__ __forceinline__ void repack_tile(const RepackItem& it, int tb, float sw, float (*tile)[32 * kRepackMaxRS + 1]) {
+    const int RS = RS_ ? RS_ : it.R * it.S, tid = threadIdx.x;
+    const int tiles_c = (it.pad + 31) / 32;                // tiles along the packed operand's channel (fastest) axis
+    const int tr = tb / tiles_c, tc = tb - tr * tiles_c;
+    // forward: rows of the operand = output channels o, its channel axis = input channels i; backward-data: rows = i, channels = o
+    const int o0 = (it.dgrad ? tc : tr) * 32, i0 = (it.dgrad ? tr : tc) * 32;
+    const int run = 32 * RS;                               // floats of one output channel's slice in the tile
+    for (int e = tid; e < 32 * run; e += 256) {
+        const int ol = e / run, j = e - ol * run;
+        const int o = o0 + ol, i = i0 + j / RS;
+        float v = 0.f;
+        if (o < it.O && i < it.I) {
+            v = __ldg(it.w + ((size_t)o * it.I + i0) * RS + j) * sw;
+            if (it.scale) v *= __ldg(it.scale + o);
+        }
+        tile[ol][j] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < 32 * run; e += 256) {
+        // 32 consecutive values of the packed operand's channel axis per run
+        const int cl = e & 31, rest = e >> 5, rl = rest / RS, rs = rest - rl * RS;
+        float v;
+        size_t idx;
+        if (!it.dgrad) {
+            const int o = o0 + rl, c = i0 + cl;
+            if (o >= it.O || c >= it.pad) continue;
+            v = tile[rl][cl * RS + rs];
+            idx = ((size_t)o * RS + rs) * it.pad + c;
+        } else {
+            const int r0 = i0 + rl, c = o0 + cl;
+            if (r0 >= it.rows || c >= it.pad) continue;
+            v = tile[cl][rl * RS + (RS - 1 - rs)];
+            idx = ((size_t)r0 * RS + rs) * it.pad + c;
+        }
+        const __half h = __float2half_rn(v);
+        it.hi[idx] = h;
+        it.lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+__global__ void __launch_bounds__(256) repack_many(const RepackItem* __restrict__ items, int n_items,
+                                                   const int* __restrict__ block_item) {
+    __shared__ float tile[32][32 * kRepackMaxRS + 1];
     int lo_i = 0, hi_i = n_items - 1;
     const int b = (int)blockIdx.x;
+    if (block_item) {                                      // the block's item, tabulated by the host: ONE load instead of the
+        lo_i = hi_i = __ldg(block_item + b);               // ~10 dependent ones of the search (most of a small block's life)
+    }
     while (lo_i < hi_i) {                                  // last item with first_block <= b
         const int mid = (lo_i + hi_i + 1) >> 1;
         if (__ldg(&items[mid].first_block) <= b) lo_i = mid;
@@ -257,30 +316,10 @@ __global__ void __launch_bounds__(256) repack_many(const RepackItem* __restrict_
     }
     const RepackItem it = items[lo_i];
     const float sw = pow2f(act_exp(it.amax));
-    const int RS = it.R * it.S;
-    const size_t total = (size_t)(it.dgrad ? it.rows : it.O) * RS * it.pad;
-    const size_t base = (size_t)(b - it.first_block) * 1024;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const size_t idx = base + q * 256 + threadIdx.x;
-        if (idx >= total) break;
-        const int c = (int)(idx % it.pad);
-        const int rs = (int)((idx / it.pad) % RS);
-        const int r0 = (int)(idx / it.pad / RS);
-        float v = 0.f;
-        if (!it.dgrad) {
-            if (c < it.I) {
-                v = __ldg(it.w + ((size_t)r0 * it.I + c) * RS + rs) * sw;
-                if (it.scale) v *= __ldg(it.scale + r0);
-            }
-        } else if (c < it.O && r0 < it.I) {
-            v = __ldg(it.w + ((size_t)c * it.I + r0) * RS + (RS - 1 - rs)) * sw;
-            if (it.scale) v *= __ldg(it.scale + c);
-        }
-        const __half h = __float2half_rn(v);
-        it.hi[idx] = h;
-        it.lo[idx] = __float2half_rn(v - __half2float(h));
-    }
+    const int RS = it.R * it.S, tb = b - it.first_block;
+    if (RS == 1) repack_tile<1>(it, tb, sw, tile);
+    else if (RS == 9) repack_tile<9>(it, tb, sw, tile);
+    else repack_tile<0>(it, tb, sw, tile);
 }
 
 // channels [0, C) of NHWC [N, H, W, cs], sampled at (oy * stride, ox * stride), -> fp32 planes [N][C][OH][pitch]
@@ -505,9 +544,16 @@ extern "C" int d2t_conv_pack_weights_f16_dgrad(const float* w_oihw, const float*
 // items: device array of n_items descriptors, 8 x 8-byte words each (see d2t_b200.h); total_blocks = sum of the items' blocks
 extern "C" size_t d2t_conv_repack_item_bytes(void) { return sizeof(RepackItem); }
 
-extern "C" int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, cudaStream_t stream) {
+// blocks of d2t_conv_repack_many that one item takes (its first_block is the running sum of these); 0: the item is not supported
+extern "C" int d2t_conv_repack_item_blocks(int O, int I, int R, int S, int pad, int rows, int dgrad) {
+    if (O <= 0 || I <= 0 || R <= 0 || S <= 0 || R * S > kRepackMaxRS || pad <= 0) return 0;
+    return repack_item_blocks(O, I, R * S, pad, rows, dgrad);
+}
+
+extern "C" int d2t_conv_repack_many(const void* items, int n_items, int total_blocks, const int* block_item,
+                                    cudaStream_t stream) {
     D2T_REQUIRE(items && n_items > 0 && total_blocks > 0, "d2t_conv_repack_many: bad arguments");
-    repack_many<<<total_blocks, 256, 0, stream>>>(reinterpret_cast<const RepackItem*>(items), n_items);
+    repack_many<<<total_blocks, 256, 0, stream>>>(reinterpret_cast<const RepackItem*>(items), n_items, block_item);
     D2T_CHECK_LAUNCH("repack_many");
     return 1;
 }

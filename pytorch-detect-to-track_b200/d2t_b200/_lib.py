@@ -99,7 +99,8 @@ _SIGS = {
     "d2t_conv_pack_weights_f16_dev": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_conv_pack_weights_f16_dgrad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "d2t_conv_repack_item_bytes": (_sz, []),
-    "d2t_conv_repack_many": (_i, [_p, _i, _i, _p]),
+    "d2t_conv_repack_item_blocks": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "d2t_conv_repack_many": (_i, [_p, _i, _i, _p, _p]),
     "d2t_upsample2_add_mask": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_wgrad_pack_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "d2t_wgrad_pack_grad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -281,21 +281,25 @@ class RepackMany(object):
     def __init__(self, layers):
         import struct
         assert lib().d2t_conv_repack_item_bytes() == 72
-        recs, first = [], 0
+        recs, first, owner = [], 0, []
         self.keep = []
         for l in layers:
             w, scale, amax, hi, lo, O, I, R, S, pad, rows, dgrad = l.repack_item()
             assert w.is_contiguous() and w.dtype == torch.float32
             self.keep.append((w, scale, amax, hi, lo))
-            total = (rows if dgrad else O) * R * S * pad
+            nblk = lib().d2t_conv_repack_item_blocks(O, I, R, S, pad, rows, dgrad)
+            assert nblk > 0, "repack_many: unsupported filter size"
             recs.append(struct.pack("<QQQQQiiiiiiii", w.data_ptr(), scale.data_ptr() if scale is not None else 0, amax.data_ptr(),
                                     hi.data_ptr(), lo.data_ptr(), O, I, R, S, pad, rows, dgrad, first))
-            first += (total + 1023) // 1024
+            owner.append(torch.full((nblk,), len(recs) - 1, dtype=torch.int32))
+            first += nblk
         self.n, self.blocks = len(recs), first
         self.items = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(hi.device)
+        self.block_item = torch.cat(owner).to(hi.device)          # the item of every block
 
     def run(self, stream=None):
-        check(lib().d2t_conv_repack_many(self.items.data_ptr(), self.n, self.blocks, _stream() if stream is None else stream),
+        check(lib().d2t_conv_repack_many(self.items.data_ptr(), self.n, self.blocks, self.block_item.data_ptr(),
+                                         _stream() if stream is None else stream),
               "d2t_conv_repack_many")
         ops._count(1)
 
