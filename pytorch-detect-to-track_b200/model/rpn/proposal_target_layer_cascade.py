@@ -83,11 +83,19 @@ def train_heads(net, B, conv3, conv4, conv5, base_feat, rfcn_cls, rfcn_bbox, inf
     nb = num_boxes.permute(1, 0, 2).contiguous()
     rois, rois_label, cls_prob, bbox_pred = [], [], [], []
     l_rpn_cls, l_rpn_box, l_cls, l_box = [], [], [], []
+    all_rois = None
+    if rpn_maps is not None:
+        # the proposal step of both legs in one pass over the 2B images (rfcn.py:104-105 runs it per leg): same proposals,
+        # half the launches, and the sequential NMS sweeps of all images side by side
+        with torch.no_grad():
+            all_rois = net.RFCN_rpn.proposals_from_maps(rpn_maps[0], rpn_maps[1], info)
+            all_rois = torch.cat([all_rois[..., :1] - (torch.arange(L * B, device=all_rois.device) // B * B).view(-1, 1, 1).to(all_rois.dtype),
+                                  all_rois[..., 1:]], dim=-1)                   # image index inside the leg
     for leg in range(L):
         sl = slice(leg * B, (leg + 1) * B)
         if rpn_maps is not None:
             leg_rois, lc, lb = net.RFCN_rpn.forward_from_maps(rpn_maps[0][sl], rpn_maps[1][sl], info[sl], gt[leg][:, :, :5],
-                                                              nb[leg])
+                                                              nb[leg], rois=all_rois[sl])
         else:
             leg_rois, lc, lb = net.RFCN_rpn(base_feat[sl], info[sl], gt[leg][:, :, :5], nb[leg])
         l_rpn_cls.append(lc.view(1)), l_rpn_box.append(lb.view(1))

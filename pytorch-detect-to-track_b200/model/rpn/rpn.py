@@ -44,12 +44,18 @@ class _RPN(nn.Module):
         return self.forward_from_maps(self.RPN_cls_score(rpn_conv1), self.RPN_bbox_pred(rpn_conv1), im_info, gt_boxes,
                                       num_boxes)
 
-    def forward_from_maps(self, rpn_cls_score, rpn_bbox_pred, im_info, gt_boxes=None, num_boxes=None):
-        """rpn.py:66-105 after the three convolutions (the training engine runs those on the tcgen05 kernel and hands
-        their outputs in as autograd leaves)."""
+    def proposals_from_maps(self, rpn_cls_score, rpn_bbox_pred, im_info):
+        """rpn.py:66-78: the proposal step alone, for any number of images (they are independent: the training heads run
+        it ONCE for both legs of all pairs instead of once per leg -- one NMS launch of 2B lists instead of two of B)"""
         rpn_cls_prob = self.cls_prob_from_score(rpn_cls_score, self.nc_score_out)
         cfg_key = 'TRAIN' if self.training else 'TEST'
-        rois = self.RPN_proposal((rpn_cls_prob.detach(), rpn_bbox_pred.detach(), im_info, cfg_key))
+        return self.RPN_proposal((rpn_cls_prob.detach(), rpn_bbox_pred.detach(), im_info, cfg_key))
+
+    def forward_from_maps(self, rpn_cls_score, rpn_bbox_pred, im_info, gt_boxes=None, num_boxes=None, rois=None):
+        """rpn.py:66-105 after the three convolutions (the training engine runs those on the tcgen05 kernel and hands
+        their outputs in as autograd leaves).  `rois`: proposals already computed by proposals_from_maps."""
+        if rois is None:
+            rois = self.proposals_from_maps(rpn_cls_score, rpn_bbox_pred, im_info)
         self.rpn_loss_cls = 0
         self.rpn_loss_box = 0
         if self.training:

@@ -83,3 +83,23 @@ def test_target_layers_device_equals_host_on_config2_ground_truth():
         assert bool((iw[b][fg] == 1).all()) and bool((iw[b][~fg] == 0).all())
         assert bool((tgt[b][~fg] == 0).all())
         assert bool(torch.isin(lab[b][fg], g0[b, :, 4].cuda()).all())            # foreground labels are ground-truth classes
+
+
+def test_rpn_proposals_of_both_legs_in_one_pass_equal_per_leg():
+    """train_heads runs the proposal step ONCE over the 2B images of both legs (model/rpn/rpn.py: proposals_from_maps) where
+    the reference runs the RPN per leg (rfcn.py:104-105): the images are independent, so the per-leg proposals must come out
+    bit for bit, with the image index counted inside the leg."""
+    from model.rpn.rpn import _RPN
+    torch.manual_seed(7)
+    B, L, H, W = 2, 2, 38, 63
+    rpn = _RPN(512).cuda().train()
+    score = torch.randn(L * B, rpn.nc_score_out, H, W, device="cuda")
+    delta = torch.randn(L * B, rpn.nc_bbox_out, H, W, device="cuda") * 0.3
+    info = torch.tensor([600.0, 1000.0, 1.0], device="cuda").repeat(L * B, 1)
+    with torch.no_grad():
+        both = rpn.proposals_from_maps(score, delta, info)
+        for leg in range(L):
+            sl = slice(leg * B, (leg + 1) * B)
+            one = rpn.proposals_from_maps(score[sl], delta[sl], info[sl])
+            assert torch.equal(both[sl][..., 1:], one[..., 1:])
+            assert torch.equal(both[sl][..., 0] - leg * B, one[..., 0])
