@@ -608,7 +608,8 @@ def train_measure(world, rank, steps, warmup):
     gt = torch.from_numpy(synth.make_gt_boxes(pairs, 30, seed=2 + rank, height=H, width=W)).cuda()
     nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
     engine = D2TTrainEngine(net, pairs, H, W)
-    opt = torch.optim.SGD(engine.params, lr=1e-5, momentum=0.9, weight_decay=1e-4)
+    # (fused: torch's single-kernel multi-tensor SGD -- the same update as the reference's torch.optim.SGD, trainval_net.py:340)
+    opt = torch.optim.SGD(engine.params, lr=1e-5, momentum=0.9, weight_decay=1e-4, fused=os.environ.get("D2T_SGD_FUSED", "1") != "0")
     n_grad = engine.flat.numel()
 
     def step():

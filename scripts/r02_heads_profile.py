@@ -19,7 +19,7 @@ net.train()
 gt = torch.from_numpy(synth.make_gt_boxes(pairs, 30, seed=2, height=H, width=W)).cuda()
 nb = (gt[..., 4] > 0).sum(-1, keepdim=True)
 eng = D2TTrainEngine(net, pairs, H, W)
-opt = torch.optim.SGD(eng.params, lr=1e-5, momentum=0.9, weight_decay=1e-4)
+opt = torch.optim.SGD(eng.params, lr=1e-5, momentum=0.9, weight_decay=1e-4, fused=True)
 for _ in range(4):
     out, loss = eng.forward_backward(im, info, gt, nb)
     opt.step(); eng.refresh_weights()
