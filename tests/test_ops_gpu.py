@@ -293,6 +293,41 @@ def test_nms_vs_oracle_and_reference_kernel(oracle, n, thresh, clustered):
         np.testing.assert_array_equal(keep, npy(ref_cuda.nms(cu(dets), thresh)).reshape(-1))
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_nms_quotients_on_the_threshold(oracle, seed):
+    """The mask kernel decides `inter / den > thresh` without the division unless the quotient is within 2^-21 of the
+    threshold (csrc/nms.cu: quotient_gt).  Boxes on a coarse integer lattice share a handful of IoU values; with the threshold
+    set to the fp32 quotient of one such pair (and to its fp32 neighbours) thousands of comparisons land exactly on, one ulp
+    above and one ulp below it -- the keep-sets must still be the oracle's and the reference kernel's, bit for bit."""
+    rng = np.random.RandomState(900 + seed)
+    n = 1500
+    x1 = rng.randint(0, 30, n).astype(np.float32)
+    y1 = rng.randint(0, 30, n).astype(np.float32)
+    w = rng.randint(4, 20, n).astype(np.float32)
+    h = rng.randint(4, 20, n).astype(np.float32)
+    score = np.sort(rng.rand(n).astype(np.float32))[::-1]
+    dets = np.stack([x1, y1, x1 + w, y1 + h, score], 1).astype(np.float32)
+    # the fp32 IoU of a few overlapping pairs, computed as the kernels do (nms_cuda_kernel.cu:31-39)
+    cands = []
+    for i, j in rng.randint(0, n, (400, 2)):
+        a, b = dets[i], dets[j]
+        iw = np.float32(max(min(a[2], b[2]) - max(a[0], b[0]) + 1, 0))
+        ih = np.float32(max(min(a[3], b[3]) - max(a[1], b[1]) + 1, 0))
+        inter = np.float32(iw * ih)
+        sa = np.float32((a[2] - a[0] + 1) * (a[3] - a[1] + 1))
+        sb = np.float32((b[2] - b[0] + 1) * (b[3] - b[1] + 1))
+        if inter > 0 and i != j:
+            cands.append(np.float32(inter / np.float32(sa + sb - inter)))
+    cands = [c for c in cands if 0.2 < c < 0.8][:4]
+    assert cands
+    for c in cands:
+        for thresh in (c, np.nextafter(c, np.float32(1)), np.nextafter(c, np.float32(0))):
+            keep = npy(ops.nms(cu(dets), float(thresh))).reshape(-1)
+            np.testing.assert_array_equal(keep, oracle.nms(dets, float(thresh)))
+            if have_ref():
+                np.testing.assert_array_equal(keep, npy(ref_cuda.nms(cu(dets), float(thresh))).reshape(-1))
+
+
 def test_nms_batched_ragged_and_capped(oracle):
     B, N = 5, 700
     dets = np.stack([common.make_clustered_dets(N, seed=200 + b) for b in range(B)])
