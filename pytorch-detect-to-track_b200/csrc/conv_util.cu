@@ -332,6 +332,11 @@ nhwc_to_planes(const float* __restrict__ x, int N, int H, int W, int cs, int C, 
     __shared__ float tile[64][33];
     const int wt = blockIdx.x * 64, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // programmatic dependent launch on both sides: this grid's blocks are scheduled while the kernel before it drains and
+    // wait here for its results; the kernel after it (the weight-gradient GEMM, which waits for THIS grid's completion before
+    // it reads the planes) may set up its CTAs as soon as SMs free up
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
 #pragma unroll
     for (int j = ty; j < 64; j += 8) {
         const int xo = wt + j, c = ct + tx;
@@ -359,6 +364,8 @@ nhwc_to_planes_split(const float* __restrict__ g, int N, int Hs, int Ws, int str
     __shared__ float tile[80][33];
     const int wt = blockIdx.x * 64, ct = blockIdx.y * 32, nh = blockIdx.z, n = nh / OH, oy = nh % OH;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // (see nhwc_to_planes)
+    asm volatile("griddepcontrol.launch_dependents;");
     const float sa = pow2f(act_exp(amax));
 #pragma unroll
     for (int j = ty; j < 80; j += 8) {
@@ -565,8 +572,16 @@ extern "C" int d2t_wgrad_pack_input(const float* x, int N, int H, int W, int c_s
                 "d2t_wgrad_pack_input: bad arguments (row pitch a multiple of 4)");
     dim3 grid((pitch + 63) / 64, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_input: tensor too large for the launch grid");
-    nhwc_to_planes<<<grid, 256, 0, stream>>>(x, N, H, W, c_stride, C, stride, OH, OW, pitch, xt);
-    D2T_CHECK_LAUNCH("nhwc_to_planes");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, nhwc_to_planes, x, N, H, W, c_stride, C, stride, OH, OW, pitch, xt), "nhwc_to_planes launch");
     return 1;
 }
 
@@ -577,9 +592,18 @@ extern "C" int d2t_wgrad_pack_grad(const float* g, int N, int OH, int OW, int c_
                 "d2t_wgrad_pack_grad: bad arguments (row pitch a multiple of 8, column shifts within +-8)");
     dim3 grid((pitch + 63) / 64, (C + 31) / 32, N * OH);
     D2T_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "d2t_wgrad_pack_grad: tensor too large for the launch grid");
-    nhwc_to_planes_split<<<grid, 256, 0, stream>>>(g, N, OH, OW, 1, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
-                                                   reinterpret_cast<__half*>(g_hi), reinterpret_cast<__half*>(g_lo));
-    D2T_CHECK_LAUNCH("nhwc_to_planes_split");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    D2T_CUDA_OK(cudaLaunchKernelEx(&cfg, nhwc_to_planes_split, g, N, OH, OW, 1, OH, OW, c_stride, C, pitch, S, dil, pad, amax_g,
+                                   reinterpret_cast<__half*>(g_hi), reinterpret_cast<__half*>(g_lo)),
+                "nhwc_to_planes_split launch");
     return 1;
 }
 
