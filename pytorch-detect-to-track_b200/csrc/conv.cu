@@ -1758,6 +1758,7 @@ conv_igemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 __global__ void __launch_bounds__(128)
 wgrad_reduce(const ConvArgs p, int BN, int G, int cpt) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");     // (the next layer's operand packers wait for this grid's completion)
     const int cols_per_block = 8;
     const int blocks_per_tile = BN / cols_per_block;
     const int t = (int)blockIdx.x / blocks_per_tile, cb = (int)blockIdx.x % blocks_per_tile;
