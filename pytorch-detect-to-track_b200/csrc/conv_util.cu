@@ -7,6 +7,8 @@
 // (/root/reference/lib/model/faster_rcnn/resnet.py:120).
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace d2t {

@@ -433,7 +433,7 @@ class WgradLayer(_Planned):
     input (ActTensor), g the gradient w.r.t. the convolution's pre-activation output (ActTensor, amax current).  Three
     launches: plane packs of x and g, then the tcgen05 GEMM, which writes every element of `grad_w`."""
 
-    def __init__(self, x, g, grad_w, scale, stride, pad, dil, scratch, cin=None):
+    def __init__(self, x, g, grad_w, scale, stride, pad, dil, scratch, cin=None, own_xt=False):
         O, I, R, S = grad_w.shape
         assert grad_w.is_contiguous() and grad_w.dtype == torch.float32
         assert stride == 1 or (R == 1 and S == 1 and pad == 0), "strided convolutions: 1x1 only"
@@ -444,10 +444,14 @@ class WgradLayer(_Planned):
         self.scratch = scratch
         self.S, self.pad, self.dil = S, pad, dil
         nx, ng = x.N * I * self.xh * self.xp, S * g.N * O * g.H * self.gp
-        if nx > scratch.xt.numel() or ng > scratch.g_hi.numel():
+        # own_xt: the layer keeps its OWN input planes, packed ahead of the backward pass by pack_input() (the forward
+        # activations exist as soon as the forward is done: a training engine packs them beside the latency-bound heads)
+        self.xt = torch.zeros(nx, device=grad_w.device) if own_xt else scratch.xt
+        self.prepacked = bool(own_xt)
+        if nx > self.xt.numel() or ng > scratch.g_hi.numel():
             raise ValueError("WgradScratch too small: need %d floats / %d halfs" % (nx, ng))
         self.plan = lib().d2t_wgrad_plan_create(x.N, I, O, self.xh, self.xw, self.xp, g.H, g.W, self.gp, R, S, pad, dil,
-                                                _p(scratch.xt), _p(scratch.g_hi), _p(scratch.g_lo), _p(x.amax), _p(g.amax),
+                                                _p(self.xt), _p(scratch.g_hi), _p(scratch.g_lo), _p(x.amax), _p(g.amax),
                                                 _p(self.scale), _p(grad_w))
         if not self.plan:
             raise D2TError("d2t_wgrad_plan_create failed: %s" % lib().d2t_last_error().decode())
@@ -458,16 +462,24 @@ class WgradLayer(_Planned):
                   "d2t_wgrad_plan_set_partials")
             self.launches = 4
 
+    def pack_input(self, stream=None):
+        """the forward input as channel-major planes (the A operand of the GEMM)"""
+        x = self.x
+        I = self.grad_w.shape[1]
+        check(lib().d2t_wgrad_pack_input(_p(x.x), x.N, x.H, x.W, x.cstride, I, self.stride, self.xh, self.xw, self.xp,
+                                         _p(self.xt), _stream() if stream is None else stream), "d2t_wgrad_pack_input")
+        ops._count(1)
+
     def run(self, stream=None):
         x, g, sc = self.x, self.g, self.scratch
         O, I = self.grad_w.shape[:2]
         st = _stream() if stream is None else stream
-        check(lib().d2t_wgrad_pack_input(_p(x.x), x.N, x.H, x.W, x.cstride, I, self.stride, self.xh, self.xw, self.xp,
-                                         _p(sc.xt), st), "d2t_wgrad_pack_input")
+        if not self.prepacked:
+            self.pack_input(st)
         check(lib().d2t_wgrad_pack_grad(_p(g.x), g.N, g.H, g.W, g.cstride, O, self.gp, self.S, self.dil, self.pad,
                                         _p(g.amax), _p(sc.g_hi), _p(sc.g_lo), st), "d2t_wgrad_pack_grad")
         check(lib().d2t_conv_plan_run(self.plan, st), "d2t_conv_plan_run")
-        ops._count(self.launches)
+        ops._count(self.launches - 1)
         return self.grad_w
 
 

@@ -20,6 +20,8 @@ trainval_net.py:310-311), SGD.  Here:
             stream as soon as the weight gradients that fill it have been enqueued, overlapping the rest of backward
   update    torch.optim.SGD on the same parameters (param.grad are views of the flat buffer)
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -113,7 +115,14 @@ class D2TTrainEngine(D2TEngine):
             nimg = N if l is not self.trk_layer else B
             need_x = max(need_x, nimg * I * (oh if m["stride"] > 1 else l.x.H) * dc._pad32(ow if m["stride"] > 1 else l.x.W))
             need_g = max(need_g, S * nimg * O * oh * dc._pad32(ow))
-        self.wscratch = dc.WgradScratch(need_x, need_g, dev)
+        # D2T_WGRAD_PREPACK=0: every weight-gradient layer packs its input planes inside the backward pass (one shared
+        # buffer); default: own planes per layer (+ ~3 GB), packed on a side stream while the heads run (backward 14.5 ->
+        # 13.5 ms, heads 4.3 -> 4.8 ms: step 24.06 -> 23.6 ms; capping the packer's blocks per SM so that the heads' small
+        # kernels find room only made the heads wait for the packs: measured worse at every setting)
+        self.prepack = os.environ.get("D2T_WGRAD_PREPACK", "1") != "0"
+        self.pack_stream = torch.cuda.Stream(device=dev)
+        self.g_xpack = None
+        self.wscratch = dc.WgradScratch(need_x if not self.prepack else 1, need_g, dev)
 
         # ---- gradient leaves coming out of the autograd part (NCHW -> NHWC each step)
         cn, bn_, rpn, tn = net.RFCN_cls_net, net.RFCN_bbox_net, net.RFCN_rpn, net.corr_bbox_net
@@ -212,7 +221,7 @@ class D2TTrainEngine(D2TEngine):
             return
         gw = self._grad_buf(w)
         scale = m["scale"]
-        wl = dc.WgradLayer(x, g, gw, scale, m["stride"], m["pad"], m["dil"], self.wscratch)
+        wl = dc.WgradLayer(x, g, gw, scale, m["stride"], m["pad"], m["dil"], self.wscratch, own_xt=self.prepack)
         wl.set_scratch(self.scratch)
         self.wgrads = getattr(self, "wgrads", []) + [wl]
         self.wgrad_flops = getattr(self, "wgrad_flops", 0.0) + wl.flops
@@ -308,6 +317,11 @@ class D2TTrainEngine(D2TEngine):
         self.trk_layer.run()
         return info
 
+    def _prepack_inputs(self):
+        """the input planes of every weight-gradient GEMM (needs the forward activations only)"""
+        for wl in self.wgrads:
+            wl.pack_input()
+
     def _load_leaf_grads(self, grads):
         for buf, gr in zip((self.g_cls, self.g_bbox, self.g_score, self.g_delta, self.g_trk), grads):
             buf.load_nchw(gr)
@@ -343,6 +357,12 @@ class D2TTrainEngine(D2TEngine):
                 for k in range(a, b):
                     self.bwd[k][0]()
             self.g_bwd.append((g, ops.LAUNCHES - count))
+        if self.prepack:
+            count = ops.LAUNCHES
+            self.g_xpack = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_xpack, pool=pool):
+                self._prepack_inputs()
+            self._xpack_launches = ops.LAUNCHES - count
         count = ops.LAUNCHES
         self.g_refresh = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_refresh, pool=pool):
@@ -371,7 +391,10 @@ class D2TTrainEngine(D2TEngine):
         torch.cuda.synchronize()
         count = ops.LAUNCHES
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # captured on a HIGH-priority stream: the graph's kernel nodes keep that priority, so the heads' many small kernels
+        # are scheduled ahead of the pending blocks of the input-plane packers that run beside them (pack_stream)
+        hp = torch.cuda.Stream(device=self.gt_static.device, priority=-1) if os.environ.get("D2T_HEADS_PRIORITY", "1") != "0" else None
+        with torch.cuda.graph(g, stream=hp):
             out, loss, grads = self._heads(self.info_graph, self.gt_static, self.nb_static)
             with torch.no_grad():
                 for dst, gr in zip(self.grads_static, grads):
@@ -402,6 +425,14 @@ class D2TTrainEngine(D2TEngine):
                 info = self.info_graph
             else:
                 info = self._engine_forward(im_data, im_info)
+            if self.prepack:           # the weight gradients' input planes: beside the heads (side stream) once graphed
+                if graphed and self.g_xpack is not None:
+                    self.pack_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(self.pack_stream):
+                        self.g_xpack.replay()
+                    ops._count(self._xpack_launches)
+                else:
+                    self._prepack_inputs()
         if graphed and self.g_heads is not None:
             with torch.no_grad():
                 self.gt_static.copy_(gt_boxes, non_blocking=True)
@@ -426,6 +457,8 @@ class D2TTrainEngine(D2TEngine):
     def _run_backward(self):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         main = torch.cuda.current_stream()
+        if self.prepack:
+            main.wait_stream(self.pack_stream)            # the input planes are in place
         self._comm_events = []
         graphed = self.g_fwd is not None
         for i, (a, b) in enumerate(self._segments()):
