@@ -345,8 +345,10 @@ d2t_conv_plan* d2t_conv_stem_plan_create(int N, int H, int W, int Cout, int pass
 int d2t_stem_pack_input(const float* x_nchw, int N, int C, int H, int W, float* packed, cudaStream_t stream);
 /* the same with max |x| folded into *amax (device float, zeroed by the caller): the operand scale of a passes = 16 stem plan,
  * whose weights are fp16 (hi, lo) [Cout][4][64] -- the [Cout][7][32] rows of d2t_stem_pack_weights padded to 8 rows, times the
- * per-channel scale and 2^k -- with max |w * scale| in a device scalar (d2t_conv_plan_set_weight_amax) */
-int d2t_stem_pack_input_amax(const float* x_nchw, int N, int C, int H, int W, float* packed, float* amax, cudaStream_t stream);
+ * per-channel scale and 2^k -- with max |w * scale| in a device scalar (d2t_conv_plan_set_weight_amax).  pairs > 0: x is the
+ * reference's [pairs][2 legs] frame batch (im_data) and the packed batch is leg-major, frame n = leg * pairs + pair (N = 2 pairs);
+ * pairs = 0: frames in order. */
+int d2t_stem_pack_input_amax(const float* x_nchw, int N, int C, int H, int W, float* packed, float* amax, int pairs, cudaStream_t stream);
 int d2t_stem_pack_weights(const float* w_oihw, int Cout, int Cin, float* w_hi, float* w_lo,
                           cudaStream_t stream);
 

@@ -39,15 +39,18 @@ __global__ void stem_pack_input(const float* __restrict__ x, int N, int C, int H
 // the same with max |x| folded into *amax (the 3xFP16 stem's operand scale)
 __global__ void __launch_bounds__(256)
 stem_pack_input_amax(const float* __restrict__ x, int N, int C, int H, int W, int Hp, int Wp, float4* __restrict__ out,
-                     float* __restrict__ amax) {
+                     float* __restrict__ amax, int pairs) {
     const size_t total = (size_t)N * Hp * Wp;
     float m = 0.f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int wp = (int)(idx % Wp), hp = (int)((idx / Wp) % Hp), n = (int)(idx / Wp / Hp);
         const int h = hp - 3, w = wp - 3;
+        // pairs > 0: x is [pairs][2 legs] frames (the reference's im_data), the packed batch is leg-major -- the permute
+        // the engine used to run as a copy of its own
+        const int ns = pairs > 0 ? (n % pairs) * 2 + n / pairs : n;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (h >= 0 && h < H && w >= 0 && w < W)
-            for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)n * C + c) * H + h) * W + w);
+            for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(x + (((size_t)ns * C + c) * H + h) * W + w);
         out[idx] = make_float4(v[0], v[1], v[2], v[3]);
         m = fmaxf(fmaxf(m, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
     }
@@ -659,12 +662,13 @@ extern "C" int d2t_stem_pack_input(const float* x, int N, int C, int H, int W, f
     return 1;
 }
 
-extern "C" int d2t_stem_pack_input_amax(const float* x, int N, int C, int H, int W, float* packed, float* amax,
+extern "C" int d2t_stem_pack_input_amax(const float* x, int N, int C, int H, int W, float* packed, float* amax, int pairs,
                                         cudaStream_t stream) {
-    D2T_REQUIRE(x && packed && amax && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "d2t_stem_pack_input_amax: bad arguments");
+    D2T_REQUIRE(x && packed && amax && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0 && (pairs == 0 || (pairs > 0 && N == 2 * pairs)),
+                "d2t_stem_pack_input_amax: bad arguments (pairs: 0, or N / 2 for a [pairs][2] frame batch)");
     const int Hp = (H + 7) & ~1, Wp = W + 8;
     const size_t total = (size_t)N * Hp * Wp;
-    stem_pack_input_amax<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(packed), amax);
+    stem_pack_input_amax<<<grid_for(total), 256, 0, stream>>>(x, N, C, H, W, Hp, Wp, reinterpret_cast<float4*>(packed), amax, pairs);
     D2T_CHECK_LAUNCH("stem_pack_input_amax");
     return 1;
 }

@@ -89,7 +89,7 @@ _SIGS = {
     "d2t_nchw_to_nhwc_amax": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "d2t_conv_stem_plan_create": (_p, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i]),
     "d2t_stem_pack_input": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "d2t_stem_pack_input_amax": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "d2t_stem_pack_input_amax": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "d2t_stem_pack_weights": (_i, [_p, _i, _i, _p, _p, _p]),
     "d2t_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "d2t_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),

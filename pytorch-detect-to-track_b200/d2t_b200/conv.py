@@ -597,13 +597,14 @@ class StemConv(_Planned):
         else:
             self._bind_amax(None, self.out)
 
-    def run(self, x):
-        """x: [N, C, H, W] fp32 image batch"""
+    def run(self, x, pairs=0):
+        """x: [N, C, H, W] fp32 image batch; pairs > 0 (3xFP16 stem): x is the reference's [pairs, 2, C, H, W] frame-pair
+        batch and the packed batch is leg-major (frame n = leg * pairs + pair) -- no permuted copy of the input"""
         if self.passes == 16:
             if self._own_amax_in:
                 self.amax_in.zero_()
             check(lib().d2t_stem_pack_input_amax(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(),
-                                                 self.amax_in.data_ptr(), _stream()), "d2t_stem_pack_input_amax")
+                                                 self.amax_in.data_ptr(), int(pairs), _stream()), "d2t_stem_pack_input_amax")
         else:
             check(lib().d2t_stem_pack_input(x.data_ptr(), self.N, self.C, self.H, self.W, self.packed.data_ptr(), _stream()),
                   "d2t_stem_pack_input")

@@ -228,10 +228,12 @@ class D2TEngine(object):
         """input re-layout, stem conv and max-pool; returns the per-frame im_info [2B, 3]"""
         N = self.N
         assert tuple(im_data.shape) == (self.B, 2, 3, self.H, self.W), "engine was built for a fixed geometry"
-        frames = im_data.permute(1, 0, 2, 3, 4).reshape(N, 3, self.H, self.W).contiguous()     # leg-major
         info = im_info.permute(1, 0, 2).reshape(N, 3).contiguous().float()
         self.amax.zero()
-        self.stem.run(frames)
+        if self.stem.passes == 16 and im_data.is_contiguous():
+            self.stem.run(im_data, pairs=self.B)               # (the leg-major order is the packer's read pattern)
+        else:
+            self.stem.run(im_data.permute(1, 0, 2, 3, 4).reshape(N, 3, self.H, self.W).contiguous())
         dc.maxpool3x3s2(self.stem.out, out=self.pool_out)
         return info
 
