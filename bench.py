@@ -285,6 +285,15 @@ def op_microbench(flush, hbm_gbs):
     out["detect_postproc_4frames_x30classes"] = {"ms_batched_device": ms_b, "ms_per_class_loop_wall": (time.time() - t0) * 1e3,
                                                  "note": "batched = one sort + gather + d2t_nms_batched over the (frame, class) axis; "
                                                          "loop = the reference's class-by-class nms with a host round trip each"}
+    # frame preparation (blob.py:20-52 + minibatch.py:77-78 + the loader's permute) for the step's 4 frames
+    fr_u8 = torch.from_numpy(np.stack([common.make_frame(720, 1280, 60 + i) for i in range(4)])).cuda()
+    fh, fw, fs = ops.frames_resized_shape(720, 1280, 600, 1000, cap=True)
+    blob = torch.empty(4, 3, fh, fw, device="cuda")
+    ms = time_kernel(lambda: ops.frames_prep(fr_u8, fs, out=blob), 10, flush)
+    alg_f = float(fr_u8.numel() + 4 * blob.numel())
+    out["frames_prep_4x720x1280_to_%dx%d" % (fh, fw)] = {"ms": ms, "algorithmic_bytes": alg_f, "gbs": alg_f / ms / 1e6,
+                                                         "frac_hbm": alg_f / ms / 1e6 / hbm_gbs}
+    del fr_u8, blob
     for n in (6000, 12000):
         dets = torch.from_numpy(np.stack([common.make_dets(n, seed=22 + i) for i in range(4)])).cuda()
         ms = time_kernel(lambda: ops.nms_batched(dets, 0.7, max_keep=300 if n == 6000 else 2000), 10, flush)
@@ -456,21 +465,36 @@ def run_b200(args):
     outs_pin = None
     d2h = 0
 
-    def upload(slot):
+    # the same loop fed with what the reference's loader starts from: uint8 BGR frames as cv2.imread
+    # returns them, 720x1200 -> im_scale 600/720 -> 600x1000; the float cast, mean subtraction, bilinear resize and NCHW
+    # permute of blob.py / minibatch.py / roibatchLoader.py run on the device (d2t_frames_prep), one launch per step
+    from d2t_b200 import synth
+    RAW_H, RAW_W = 720, 1200
+    raw_hw = ops.frames_resized_shape(RAW_H, RAW_W, 600, 1000, cap=False)
+    assert raw_hw[:2] == (H, W), raw_hw
+    raw_pin = torch.from_numpy(np.stack([synth.make_frame(RAW_H, RAW_W, 100 + 8 * rank + i) for i in range(2 * pairs)])).pin_memory()
+    raw_dev = [torch.empty(raw_pin.shape, dtype=torch.uint8, device="cuda") for _ in range(2)]
+
+    def upload(slot, raw=False):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the forward that last read this slot is done
-            dev_in[slot][0].copy_(im_pin, non_blocking=True)
+            if raw:
+                raw_dev[slot].copy_(raw_pin, non_blocking=True)
+            else:
+                dev_in[slot][0].copy_(im_pin, non_blocking=True)
             dev_in[slot][1].copy_(info_pin, non_blocking=True)
             up_done[slot].record(copy_stream)
 
-    def e2e_loop(n):
+    def e2e_loop(n, raw=False):
         nonlocal outs_pin, d2h
-        upload(0)
+        upload(0, raw)
         for it in range(n):
             slot = it & 1
             if it + 1 < n:
-                upload(slot ^ 1)
+                upload(slot ^ 1, raw)
             main_stream.wait_event(up_done[slot])
+            if raw:                                         # frames in [pair][leg] order = the reference's [pairs][2] batch
+                ops.frames_prep(raw_dev[slot], raw_hw[2], out=dev_in[slot][0].view(2 * pairs, 3, H, W))
             o = step(dev_in[slot][0], dev_in[slot][1])[:4]
             consumed[slot].record(main_stream)
             if outs_pin is None:
@@ -490,10 +514,20 @@ def run_b200(args):
     barrier()
     e2e_ms = a.elapsed_time(b)
     h2d = im_pin.numel() * 4 + info_pin.numel() * 4
+    e2e_loop(3, raw=True)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    e2e_loop(args.steps, raw=True)
+    b.record()
+    barrier()
+    e2e_raw_ms = a.elapsed_time(b)
+    check_finite([t.cuda() for t in outs_pin], "the outputs of the forward fed with uint8 frames")
+    h2d_raw = raw_pin.numel() + info_pin.numel() * 4
 
     from d2t_b200 import parallel
-    t = parallel.max_over_ranks(torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64))
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    t = parallel.max_over_ranks(torch.tensor([total_ms, e2e_ms, e2e_raw_ms], device="cuda", dtype=torch.float64))
+    total_ms, e2e_ms, e2e_raw_ms = float(t[0]), float(t[1]), float(t[2])
 
     # ---- the training step of configs[2] (data-parallel, the path's one collective) on every rank, after the eval numbers
     train = None
@@ -575,6 +609,10 @@ def run_b200(args):
                 "parity": parity, "train": train,
                 "e2e": {"value": world * pairs / (e2e_ms / args.steps / 1e3), "unit": "frame-pairs/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e_raw_frames": {"value": world * pairs / (e2e_raw_ms / args.steps / 1e3), "unit": "frame-pairs/s",
+                                   "h2d_bytes_per_step": h2d_raw, "d2h_bytes_per_step": d2h,
+                                   "source": "uint8 BGR %dx%d frames (pinned host) -> d2t_frames_prep on the device (cast, mean "
+                                             "subtraction, OpenCV float32 bilinear resize to %dx%d, NCHW) -> the same forward" % (RAW_H, RAW_W, H, W)},
                 "gpu_launches": my_launches, "roofline": roofline, "roofline_psroi": roofline_psroi,
                 "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "ops": ops_bench}

@@ -461,6 +461,26 @@ int d2t_nhwc_to_nchw(const float* x, int N, int C, int H, int W, int c_stride, i
 /* MaxPool2d(3, stride 2, padding 0, ceil_mode=True) on NHWC (faster_rcnn/resnet.py:120) */
 int d2t_maxpool3x3s2_nhwc(const float* in, int N, int H, int W, int C, float* out, cudaStream_t stream);
 
+/* ---- Frame preparation on the device (the data format ahead of the path) ----
+ * Replaces the reference's host chain for one batch of equally sized uint8 BGR frames (what cv2.imread returns):
+ *   prep_im_for_blob: float32 cast, PIXEL_MEANS subtraction, cv2.resize(fx = fy = im_scale, INTER_LINEAR)
+ *                                                                          (lib/model/utils/blob.py:35-52),
+ *   the horizontal flip of flipped roidb entries                           (lib/roi_data_layer/minibatch.py:77-78),
+ *   im_list_to_blob's zero padding                                         (lib/model/utils/blob.py:20-33),
+ *   the loader's permute(0, 3, 1, 2)                                       (lib/roi_data_layer/roibatchLoader.py:183).
+ * d2t_frames_resized_shape: im_scale = target_size / min(h, w), capped so that round(im_scale * max(h, w)) <= max_size
+ * when cap != 0 (demo.py:270-274, online_tubes.py:656-659; minibatch.py passes through blob.py, where the cap is
+ * commented out: cap = 0); out_hw = (round(h * im_scale), round(w * im_scale)), half to even as cv::resize rounds.
+ * d2t_frames_prep: frames [n, src_h, src_w, 3] uint8 (device) -> blob float32 (device), [n, 3, blob_h, blob_w] (nhwc = 0)
+ * or [n, blob_h, blob_w, 3] (nhwc = 1); rows >= dst_h and columns >= dst_w are written as zeros (the blob need not be
+ * cleared); pixel_means = 3 host doubles (B, G, R; config.py:257).  Arithmetic: OpenCV's own float32 bilinear code
+ * (coordinates in double, two fp32 passes) -- bit-identical to oracle/frames.py.  Returns 1, or 0 + d2t_last_error(). */
+int d2t_frames_resized_shape(int src_h, int src_w, int target_size, int max_size, int cap, int* out_hw,
+                             double* im_scale);
+int d2t_frames_prep(const uint8_t* frames, int n, int src_h, int src_w, const double* pixel_means, double im_scale,
+                    int flipped, int dst_h, int dst_w, float* blob, int blob_h, int blob_w, int nhwc,
+                    cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,9 @@ _SIGS = {
     "d2t_stem_pack_weights": (_i, [_p, _i, _i, _p, _p, _p]),
     "d2t_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "d2t_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    # ---- frame preparation (blob.py / minibatch.py on the device)
+    "d2t_frames_resized_shape": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(C.c_double)]),
+    "d2t_frames_prep": (_i, [_p, _i, _i, _i, C.POINTER(C.c_double), C.c_double, _i, _i, _i, _p, _i, _i, _i, _p]),
     # ---- training path (backward-data / weight-gradient)
     "d2t_conv_plan_set_mask": (_i, [_p, _p, _i]),
     "d2t_conv_plan_set_weight_amax": (_i, [_p, _p]),

@@ -532,3 +532,55 @@ def proposals(anchors, deltas, cls_prob, im_info, feat_stride, pre_nms_topN, pos
         dets = proposal_gather(boxes, scores, order, n_take)
     keep, num = nms_batched(dets, float(nms_thresh), max_keep=post_nms_topN)
     return proposal_write_rois(dets, keep, num, post_nms_topN)
+
+
+# ------------------------------------------------------------------------------- frame preparation
+PIXEL_MEANS = (102.9801, 115.9465, 122.7717)        # config.py:257 (B, G, R)
+
+
+def frames_resized_shape(src_h, src_w, target_size, max_size, cap):
+    """(dst_h, dst_w, im_scale) of `prep_im_for_blob` (blob.py:43-50; cap=False) / the eval loops' `_get_image_blob`
+    (demo.py:270-276; cap=True) -> d2t_frames_resized_shape (host arithmetic only)."""
+    hw, s = (C.c_int * 2)(), C.c_double()
+    check(lib().d2t_frames_resized_shape(int(src_h), int(src_w), int(target_size), int(max_size), int(bool(cap)), hw,
+                                         C.byref(s)), "d2t_frames_resized_shape")
+    return hw[0], hw[1], s.value
+
+
+def frames_prep(frames, im_scale, flipped=False, pixel_means=PIXEL_MEANS, blob_hw=None, nhwc=False, out=None):
+    """uint8 BGR frames [n, H, W, 3] on the device -> the float32 network input the reference builds on the host
+    (blob.py:20-52, minibatch.py:77-78, roibatchLoader.py:183): [n, 3, blob_h, blob_w], or [n, blob_h, blob_w, 3] with
+    nhwc=True; zero-padded to `blob_hw` (default: the resized size).  One launch of d2t_frames_prep."""
+    _req(frames, "frames", torch.uint8)
+    if frames.dim() != 4 or frames.size(3) != 3:
+        raise ValueError("frames must be [n, H, W, 3] uint8 (BGR, as cv2.imread returns them)")
+    n, H, W, _ = frames.shape
+    dst_h, dst_w = int(round_half_even(H * im_scale)), int(round_half_even(W * im_scale))
+    bh, bw = blob_hw if blob_hw is not None else (dst_h, dst_w)
+    shape = (n, bh, bw, 3) if nhwc else (n, 3, bh, bw)
+    with torch.cuda.device_of(frames):
+        if out is None:
+            out = torch.empty(shape, device=frames.device, dtype=torch.float32)
+        elif tuple(out.shape) != shape:
+            raise ValueError("out must be %s, got %s" % (shape, tuple(out.shape)))
+        _req(out, "out")
+        means = (C.c_double * 3)(*[float(m) for m in pixel_means])
+        check(lib().d2t_frames_prep(frames.data_ptr(), n, H, W, means, float(im_scale), int(bool(flipped)), dst_h, dst_w,
+                                    out.data_ptr(), bh, bw, int(bool(nhwc)), _stream()), "d2t_frames_prep")
+    _count(1)
+    return out
+
+
+def round_half_even(v):
+    """cvRound / np.round of a double (Python's round() is half-to-even as well)."""
+    return round(float(v))
+
+
+def frames_to_blob(frames, target_size=600, max_size=1000, cap=False, flipped=False, pixel_means=PIXEL_MEANS, out=None):
+    """`_get_image_blob` (minibatch.py:58-88 with cap=False; demo.py:252-283 with cap=True) + the loader's NCHW permute
+    for a batch of equally sized frames: (data [n, 3, h, w], im_info [n, 3] = (h, w, im_scale) on the host)."""
+    n, H, W, _ = frames.shape
+    dst_h, dst_w, s = frames_resized_shape(H, W, target_size, max_size, cap)
+    data = frames_prep(frames, s, flipped, pixel_means, out=out)
+    im_info = torch.tensor([[dst_h, dst_w, s]] * n, dtype=torch.float32)
+    return data, im_info

@@ -112,3 +112,12 @@ def calibrate_batchnorm(net, frames, chunk=2, var_floor=0.1):
         m.momentum = mom
         m.train(tr)
     return net
+
+
+def make_frame(h, w, seed):
+    """A uint8 BGR frame [h, w, 3] as cv2.imread would hand it to the frame preparation: blocky content plus noise
+    (edges and flat areas)."""
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, 256, size=(h // 4 + 2, w // 4 + 2, 3)).astype(np.float32)
+    im = np.kron(base, np.ones((4, 4, 1), np.float32))[:h, :w]
+    return np.clip(im + rng.randint(-20, 21, size=(h, w, 3)), 0, 255).astype(np.uint8)

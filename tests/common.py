@@ -12,6 +12,6 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from d2t_b200.synth import (make_clustered_dets, make_dets, make_gt_boxes, make_rois, make_rpn_inputs,  # noqa: E402,F401
+from d2t_b200.synth import (make_clustered_dets, make_dets, make_frame, make_gt_boxes, make_rois, make_rpn_inputs,  # noqa: E402,F401
                             randn)
 from d2t_b200.detect import detect_reference_loop  # noqa: E402,F401
