@@ -93,10 +93,13 @@ class resnet(_RFCN):
 
     Unlike the reference -- which always builds ResNet-101 whatever ``num_layers`` says
     (resnet.py:259) -- ``num_layers`` in {50, 101, 152} is honoured here; 101 is the default and
-    the D&T configuration.  Pretrained-file loading is out of scope (no checkpoints offline).
+    the D&T configuration.  ``pretrained`` / ``pretrained_rfcn`` load ``model_path`` / ``model_rfcn_path`` exactly as the
+    reference does (resnet.py:259-264, 304-309): only the keys the module owns are taken, the rest of the file is ignored.
     """
 
     def __init__(self, classes, num_layers=101, pretrained=False, pretrained_rfcn=False, class_agnostic=False):
+        self.model_path = 'data/pretrained_model/res101.pth'                  # resnet.py:248-249
+        self.model_rfcn_path = 'data/pretrained_model/rfcn_detect.pth'        # trained on ImageNet VID+DET
         self.dout_base_model = 512
         self.num_layers = num_layers
         self.pretrained = pretrained
@@ -106,6 +109,9 @@ class resnet(_RFCN):
 
     def _init_modules(self):
         trunk = {50: resnet50, 101: resnet101, 152: resnet152}[self.num_layers]()
+        if self.pretrained:                                                     # resnet.py:259-264: backbone weights
+            state_dict = torch.load(self.model_path, map_location="cpu")
+            trunk.load_state_dict({k: v for k, v in state_dict.items() if k in trunk.state_dict()})
         self.RFCN_base = nn.Sequential(trunk.conv1, trunk.bn1, trunk.relu, trunk.maxpool, trunk.layer1, trunk.layer2,
                                        trunk.layer3, trunk.layer4)
         for idx in (0, 1):
@@ -124,6 +130,10 @@ class resnet(_RFCN):
         self.RFCN_base.add_module("RFCN_net", self.RFCN_net)
         self.RFCN_base.add_module("resnet", trunk.relu)
         nn.init.kaiming_normal_(self.RFCN_net.weight.data)
+        if self.pretrained_rfcn:                                                # resnet.py:304-309: an R-FCN detector checkpoint
+            pretrained_rfcn_dict = torch.load(self.model_rfcn_path, map_location="cpu")['model']
+            pretrained_rfcn_dict = {k: v for k, v in pretrained_rfcn_dict.items() if k in self.state_dict()}
+            self.load_state_dict(pretrained_rfcn_dict, strict=False)           # (2018 torch ignored missing keys here)
         n_track_in = 2 * 4 * self.n_reg_classes * 49 + 81 + 289 + 289   # 1051 when class-agnostic (resnet.py:311)
         self.corr_bbox_net = nn.Conv2d(n_track_in, 4 * self.n_reg_classes * 7 * 7, [1, 1], padding=0, stride=1)
         nn.init.normal_(self.corr_bbox_net.weight.data, 0.0, 0.01)

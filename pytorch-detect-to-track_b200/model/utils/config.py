@@ -23,6 +23,8 @@ cfg = _NS(
     FEAT_STRIDE=[16],                      # config.py:300
     MAX_NUM_GT_BOXES=30,                   # trainval_net.py:165
     POOLING_SIZE=7,                        # config.py:286
+    POOLING_MODE='crop',                   # config.py:283 (carried by the checkpoint files; the R-FCN heads use PSRoI)
+    TRAIN_SCALES=(600,), TRAIN_MAX_SIZE=1000, TEST_SCALES=(600,), TEST_MAX_SIZE=1000,   # config.py:63,66,168,171 (frame preparation)
     PIXEL_MEANS=(102.9801, 115.9465, 122.7717),   # config.py:257 (BGR)
     N_CLASSES=31,                          # lib/datasets/imagenet_detect.py:28-36
     TRAIN=_NS(

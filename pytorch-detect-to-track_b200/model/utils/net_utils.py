@@ -26,3 +26,14 @@ def device_const(values, like):
     if t is None:
         t = _CONST_CACHE[key] = torch.tensor(list(key[0]), device=like.device, dtype=like.dtype)
     return t
+
+
+def save_checkpoint(state, filename):
+    """net_utils.py:70-71."""
+    torch.save(state, filename)
+
+
+def adjust_learning_rate(optimizer, decay=0.1):
+    """net_utils.py:63-67."""
+    for param_group in optimizer.param_groups:
+        param_group['lr'] = decay * param_group['lr']
