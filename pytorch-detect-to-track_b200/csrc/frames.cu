@@ -30,39 +30,43 @@ __device__ __forceinline__ void axis_coord(int d, double scale, int n_src, int& 
     if (s >= n_src - 1) { s = n_src - 1; a = 0.f; }
 }
 
-// One thread: kX consecutive destination columns of one destination row, all three channels.
-template <int kX, bool kVec, bool kNhwc>
+// float32(double(u8) - mean) without a table and without fp64: mean = hi + lo with hi a multiple of 2^-8 (so that u8 - hi is
+// exact in fp32) and lo = float(mean - hi); (u8 - hi) - lo then rounds once.  lo itself carries a 2^-33 error, so the host
+// checks all 3 x 256 values against the double formula before choosing this path (means_split); otherwise the table is used.
+struct MeanSplit { float hi[3], lo[3]; };
+
+// One thread: kX destination columns (blockDim apart: a warp reads neighbouring source bytes and writes 128 contiguous
+// bytes per plane) of one destination row, all three channels.
+template <int kX, bool kLut, bool kNhwc>
 __global__ void __launch_bounds__(256)
-frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Means means, double scale, int flipped,
-                   int dst_h, int dst_w, float* __restrict__ blob, int blob_h, int blob_w) {
-    __shared__ float lut[3][256];                                           // float32(double(u8) - mean[c])
-    for (int i = threadIdx.x; i < 768; i += blockDim.x)
-        lut[i >> 8][i & 255] = __double2float_rn(__dsub_rn((double)(i & 255), means.m[i >> 8]));
-    __syncthreads();
-
-    const int groups = (blob_w + kX - 1) / kX;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Means means, MeanSplit split, double scale,
+                   int flipped, int dst_h, int dst_w, float* __restrict__ blob, int blob_h, int blob_w) {
+    __shared__ float lut[kLut ? 3 : 1][256];                                // float32(double(u8) - mean[c])
+    if (kLut) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x)
+            lut[i >> 8][i & 255] = __double2float_rn(__dsub_rn((double)(i & 255), means.m[i >> 8]));
+        __syncthreads();
+    }
     const int y = blockIdx.y, n = blockIdx.z;
-    if (g >= groups) return;
-    const int x0 = g * kX;
-    float v[3][kX];
+    const bool row_live = y < dst_h;
+    int sy = 0; float b = 0.f;
+    if (row_live) axis_coord(y, scale, src_h, sy, b);
+    const int sy1 = min(sy + 1, src_h - 1);
+    const float b0 = __fsub_rn(1.f, b);
+    const uint8_t* img = frames + (size_t)n * src_h * src_w * 3;
+    const uint8_t* row0 = img + (size_t)sy * src_w * 3;
+    const uint8_t* row1 = img + (size_t)sy1 * src_w * 3;
+    auto sample = [&](const uint8_t* p, int c) -> float {
+        const uint8_t u = __ldg(p + c);
+        if (kLut) return lut[c][u];
+        return __fsub_rn(__fsub_rn((float)u, split.hi[c]), split.lo[c]);
+    };
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int j = 0; j < kX; ++j) v[c][j] = 0.f;
-
-    if (y < dst_h && x0 < dst_w) {
-        int sy; float b;
-        axis_coord(y, scale, src_h, sy, b);
-        const int sy1 = min(sy + 1, src_h - 1);
-        const float b0 = __fsub_rn(1.f, b);
-        const uint8_t* img = frames + (size_t)n * src_h * src_w * 3;
-        const uint8_t* row0 = img + (size_t)sy * src_w * 3;
-        const uint8_t* row1 = img + (size_t)sy1 * src_w * 3;
-#pragma unroll
-        for (int j = 0; j < kX; ++j) {
-            const int x = x0 + j;
-            if (x >= dst_w) break;
+    for (int j = 0; j < kX; ++j) {
+        const int x = (blockIdx.x * kX + j) * blockDim.x + threadIdx.x;
+        if (x >= blob_w) break;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (row_live && x < dst_w) {
             int sx; float a;
             axis_coord(x, scale, src_w, sx, a);
             int sx1 = min(sx + 1, src_w - 1);
@@ -70,37 +74,38 @@ frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Mea
             const float a0 = __fsub_rn(1.f, a);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float s00 = lut[c][__ldg(row0 + sx * 3 + c)], s01 = lut[c][__ldg(row0 + sx1 * 3 + c)];
-                const float s10 = lut[c][__ldg(row1 + sx * 3 + c)], s11 = lut[c][__ldg(row1 + sx1 * 3 + c)];
+                const float s00 = sample(row0 + sx * 3, c), s01 = sample(row0 + sx1 * 3, c);
+                const float s10 = sample(row1 + sx * 3, c), s11 = sample(row1 + sx1 * 3, c);
                 const float r0 = __fadd_rn(__fmul_rn(s00, a0), __fmul_rn(s01, a));
                 const float r1 = __fadd_rn(__fmul_rn(s10, a0), __fmul_rn(s11, a));
-                v[c][j] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b));
+                v[c] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b));
             }
         }
+        if (kNhwc) {
+            float* o = blob + (((size_t)n * blob_h + y) * blob_w + x) * 3;
+            o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) blob[(((size_t)n * 3 + c) * blob_h + y) * blob_w + x] = v[c];
+        }
     }
+}
 
-    if (kNhwc) {
-        float* o = blob + (((size_t)n * blob_h + y) * blob_w + x0) * 3;
-#pragma unroll
-        for (int j = 0; j < kX; ++j)
-            if (x0 + j < blob_w) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) o[j * 3 + c] = v[c][j];
-            }
-    } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float* o = blob + (((size_t)n * 3 + c) * blob_h + y) * blob_w + x0;
-            if (kVec) {                                                     // blob_w % 4 == 0, base 16-byte aligned
-                static_assert(kX == 4, "vector stores are float4");
-                *reinterpret_cast<float4*>(o) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < kX; ++j)
-                    if (x0 + j < blob_w) o[j] = v[c][j];
-            }
+// hi / lo split of the three means; false when (u8 - hi) - lo is not float32(double(u8) - mean) for every u8
+bool means_split(const double* m, MeanSplit& out) {
+    for (int c = 0; c < 3; ++c) {
+        const double hi = nearbyint(m[c] * 256.0) / 256.0;
+        if (!(fabs(hi) < 32768.0)) return false;
+        out.hi[c] = (float)hi;
+        out.lo[c] = (float)(m[c] - hi);
+        for (int i = 0; i < 256; ++i) {
+            volatile float t = (float)i - out.hi[c];
+            volatile float got = t - out.lo[c];
+            const float want = (float)((double)i - m[c]);
+            if (got != want) return false;
         }
     }
+    return true;
 }
 
 }  // namespace
@@ -133,21 +138,18 @@ int d2t_frames_prep(const uint8_t* frames, int n, int src_h, int src_w, const do
                 blob_h, blob_w, dst_h, dst_w);
     D2T_REQUIRE(blob_h <= 65535 && n <= 65535, "d2t_frames_prep: grid limits (blob_h, n <= 65535)");
     Means means{{pixel_means[0], pixel_means[1], pixel_means[2]}};
+    MeanSplit split{};
+    const bool lut = !means_split(pixel_means, split);
     const double scale = 1.0 / im_scale;                                    // cv::resize: scale_x = 1 / inv_scale_x
     constexpr int kX = 4;
-    const int groups = (blob_w + kX - 1) / kX;
-    const int threads = groups >= 256 ? 256 : (groups >= 128 ? 128 : 64);
-    dim3 grid((groups + threads - 1) / threads, blob_h, n);
-    const bool vec = !nhwc && blob_w % 4 == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0;
-    if (nhwc)
-        frames_prep_kernel<kX, false, true><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, scale, flipped, dst_h,
-                                                                          dst_w, blob, blob_h, blob_w);
-    else if (vec)
-        frames_prep_kernel<kX, true, false><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, scale, flipped, dst_h,
-                                                                          dst_w, blob, blob_h, blob_w);
-    else
-        frames_prep_kernel<kX, false, false><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, scale, flipped, dst_h,
-                                                                           dst_w, blob, blob_h, blob_w);
+    const int threads = blob_w >= 1024 ? 256 : (blob_w >= 512 ? 128 : 64);
+    dim3 grid((blob_w + threads * kX - 1) / (threads * kX), blob_h, n);
+#define D2T_FRAMES_LAUNCH(LUT, NHWC)                                                                                    \
+    frames_prep_kernel<kX, LUT, NHWC><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, split, scale, flipped, \
+                                                                    dst_h, dst_w, blob, blob_h, blob_w)
+    if (lut) { if (nhwc) D2T_FRAMES_LAUNCH(true, true); else D2T_FRAMES_LAUNCH(true, false); }
+    else     { if (nhwc) D2T_FRAMES_LAUNCH(false, true); else D2T_FRAMES_LAUNCH(false, false); }
+#undef D2T_FRAMES_LAUNCH
     D2T_CHECK_LAUNCH("d2t_frames_prep");
     return 1;
 }

@@ -7,8 +7,11 @@ a file written under ``nn.DataParallel`` holds ``RFCN.module.state_dict()`` -- t
 shapes and order are pinned against the reference's own module in tests/test_checkpoint_cpu.py, so a checkpoint trained
 with the reference loads here with ``strict=True`` and the other way round.
 
-The engines compute with packed copies of the weights (BatchNorm folded, fp16 hi/lo split): `load_checkpoint` re-packs a
-`D2TTrainEngine` passed as ``engine`` and refuses a frozen `D2TEngine`, which must be built AFTER the load.
+The engines compute with packed copies of the parameters (BatchNorm statistics folded into scale / shift, weights split
+into fp16 hi/lo pairs), so -- in the order the reference's scripts already follow (trainval_net.py:296-308 loads before the
+first step, test_net.py:161-165 before the first forward) -- load the checkpoint into the module FIRST and build
+`D2TEngine` / `D2TTrainEngine` afterwards; `load_checkpoint` refuses an engine that is already built (`engines=`), and
+`D2TEngine.check_fresh()` reports a module that changed underneath one.
 """
 import os
 
@@ -33,19 +36,17 @@ def save_checkpoint(filename, net, optimizer, session, epoch, class_agnostic, po
     return filename
 
 
-def load_checkpoint(filename, net, optimizer=None, engine=None, map_location="cpu"):
+def load_checkpoint(filename, net, optimizer=None, engines=(), map_location="cpu"):
     """trainval_net.py:296-308 (resume: model + optimizer + cfg.POOLING_MODE) and test_net.py:161-165 (model only).
-    Returns the file's dict without the two state_dicts (session, epoch, pooling_mode, class_agnostic)."""
-    from .engine import D2TEngine
-    if isinstance(engine, D2TEngine) and not hasattr(engine, "refresh_weights"):
-        raise ValueError("load_checkpoint: a D2TEngine keeps packed copies of the weights it was built from; load the "
-                         "checkpoint into the module first and build the engine afterwards")
+    Returns the file's dict without the two state_dicts (session, epoch, pooling_mode, class_agnostic).
+    `engines`: engines already built on `net` -- an error (their packed operands would be stale; see the module docstring)."""
+    if engines:
+        raise ValueError("load_checkpoint: an engine keeps packed copies of the parameters and folded BatchNorm statistics it "
+                         "was built from; load the checkpoint into the module first and build the engine afterwards")
     checkpoint = torch.load(filename, map_location=map_location)
     getattr(net, "module", net).load_state_dict(checkpoint['model'])
     if optimizer is not None:
         optimizer.load_state_dict(checkpoint['optimizer'])
     if 'pooling_mode' in checkpoint.keys():
         cfg.POOLING_MODE = checkpoint['pooling_mode']
-    if engine is not None:
-        engine.refresh_weights()
     return {k: v for k, v in checkpoint.items() if k not in ('model', 'optimizer')}

@@ -1,5 +1,5 @@
 """Checkpoint files and the engines: a module restored from a reference-format checkpoint gives the
-same engine outputs as the module it was saved from; a training engine re-packs its operands on load."""
+same engine outputs as the module it was saved from; engines are built after the load."""
 import pytest
 import torch
 
@@ -19,7 +19,7 @@ def _net(seed, layers=50):
     return net
 
 
-def test_engine_from_restored_module_and_train_engine_refresh(tmp_path):
+def test_engines_built_on_a_restored_module(tmp_path):
     from d2t_b200 import checkpoint
     from d2t_b200.engine import D2TEngine
     from d2t_b200.train import D2TTrainEngine
@@ -34,7 +34,7 @@ def test_engine_from_restored_module_and_train_engine_refresh(tmp_path):
     eng_a = D2TEngine(a, 1, H, W)
     eng_b_stale = D2TEngine(b, 1, H, W)
     with pytest.raises(ValueError):
-        checkpoint.load_checkpoint(path, b, engine=eng_b_stale)          # a frozen engine cannot follow a load
+        checkpoint.load_checkpoint(path, b, engines=[eng_b_stale])       # a built engine cannot follow a load
     meta = checkpoint.load_checkpoint(path, b)
     assert meta['epoch'] == 2 and meta['class_agnostic'] is True
     with pytest.raises(RuntimeError):
@@ -45,11 +45,11 @@ def test_engine_from_restored_module_and_train_engine_refresh(tmp_path):
     torch.cuda.synchronize()
     for x, y in zip(oa[:4], ob[:4]):
         assert torch.equal(x, y)
-    # training engine: load_checkpoint re-packs the fp16 operand pairs from the restored parameters
+    # training engine built on a restored module (the resume order of trainval_net.py:296-308)
     c = _net(2)
+    checkpoint.load_checkpoint(path, c)
     c.train()
     teng = D2TTrainEngine(c, 1, H, W, use_graphs=False, graph_heads=False)
-    checkpoint.load_checkpoint(path, c, engine=teng)
     with torch.no_grad():
         frames = im.permute(1, 0, 2, 3, 4).reshape(2, 3, H, W).contiguous()
         a.eval()

@@ -126,3 +126,38 @@ def test_argument_errors():
         ops.frames_prep(d.float(), 1.0)
     with pytest.raises(D2TError):
         ops.frames_prep(d, 2.0, blob_hw=(10, 10))                                # blob smaller than the resized frame
+
+
+def _split_formula_exact(m):
+    """csrc/frames.cu means_split: is (u8 - hi) - lo == float32(double(u8) - mean) for every u8?"""
+    for c in range(3):
+        hi = np.rint(m[c] * 256) / 256
+        lo = np.float32(m[c] - hi)
+        i = np.arange(256)
+        got = ((i.astype(np.float32) - np.float32(hi)).astype(np.float32) - lo).astype(np.float32)
+        if not np.array_equal(got, (i.astype(np.float64) - m[c]).astype(np.float32)):
+            return False
+    return True
+
+
+def test_other_pixel_means_table_and_table_free_paths():
+    """the mean subtraction is float32(double(u8) - mean): table-free when the kernel's hi/lo split reproduces it for all
+    256 values (the reference's PIXEL_MEANS do), a 768-entry table otherwise -- both bit-identical to the oracle"""
+    from d2t_b200 import ops
+    assert _split_formula_exact(oracle.PIXEL_MEANS.reshape(3))
+    rng = np.random.RandomState(0)
+    exact, table = None, None
+    while exact is None or table is None:
+        m = rng.uniform(0, 255, 3)
+        if _split_formula_exact(m):
+            exact = m if exact is None else exact
+        else:
+            table = m if table is None else table
+    ims = np.stack([common.make_frame(40, 56, s) for s in (41, 42)])
+    ims[0, :, :, 0] = np.arange(56, dtype=np.uint8)[None, :] * 4 + 3             # every byte value somewhere
+    ims[1, :, :, 1] = 255 - np.arange(40, dtype=np.uint8)[:, None] * 6
+    for means in (exact, table):
+        for s in (1.0, oracle.im_scale_for(40, 56, 33, 1000, False)):
+            want = np.stack([oracle.prep_im_for_blob(im, means.reshape(1, 1, 3), 33 if s != 1.0 else 40, 1000)[0] for im in ims])
+            got = ops.frames_prep(cu(ims), s, pixel_means=means, nhwc=True).cpu().numpy()
+            np.testing.assert_array_equal(got, want)
