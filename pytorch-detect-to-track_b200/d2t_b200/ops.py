@@ -584,3 +584,37 @@ def frames_to_blob(frames, target_size=600, max_size=1000, cap=False, flipped=Fa
     data = frames_prep(frames, s, flipped, pixel_means, out=out)
     im_info = torch.tensor([[dst_h, dst_w, s]] * n, dtype=torch.float32)
     return data, im_info
+
+
+class VideoPairBlobs(object):
+    """`VideoDataset._create_video_blob` (online_tubes.py:582-606 / tracking_utils.py:420-447) on the device: the
+    n - 1 consecutive frame pairs (t, t + 1) of one video.  The reference reads, prepares and uploads every inner frame
+    twice (as t1 of pair i - 1 and as t0 of pair i); here all n frames are prepared by ONE d2t_frames_prep launch and
+    sample i is the zero-copy window `data[i:i + 2]` of that blob.
+
+    `blobs[i]` -> {'data': [2, 3, h, w], 'im_info': [2, 3], 'frame_number': [2, 1, 1]} as the reference's sample dict;
+    `blobs.batch(first, pairs)` -> (im_data [pairs, 2, 3, h, w] contiguous, im_info [pairs, 2, 3]) for the engines."""
+
+    def __init__(self, frames, target_size=600, max_size=1000, pixel_means=PIXEL_MEANS):
+        self.data, info = frames_to_blob(frames, target_size, max_size, cap=True, pixel_means=pixel_means)
+        self.im_info = info.to(self.data.device)
+        n = self.data.size(0)
+        self.frame_number = torch.arange(n, device=self.data.device).view(n, 1, 1)
+
+    def __len__(self):
+        return self.data.size(0) - 1
+
+    def __getitem__(self, i):
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return {'data': self.data[i:i + 2], 'im_info': self.im_info[i:i + 2], 'frame_number': self.frame_number[i:i + 2]}
+
+    def batch(self, first, pairs):
+        if first < 0 or pairs < 1 or first + pairs > len(self):
+            raise IndexError("pairs [%d, %d) of %d" % (first, first + pairs, len(self)))
+        d = self.data
+        s = d.stride()
+        im = d.as_strided((pairs, 2) + tuple(d.shape[1:]), (s[0], s[0]) + tuple(s[1:]), d.storage_offset() + first * s[0])
+        i = self.im_info
+        info = i.as_strided((pairs, 2, 3), (i.stride(0), i.stride(0), 1), first * i.stride(0))
+        return im.contiguous(), info.contiguous()

@@ -161,3 +161,26 @@ def test_other_pixel_means_table_and_table_free_paths():
             want = np.stack([oracle.prep_im_for_blob(im, means.reshape(1, 1, 3), 33 if s != 1.0 else 40, 1000)[0] for im in ims])
             got = ops.frames_prep(cu(ims), s, pixel_means=means, nhwc=True).cpu().numpy()
             np.testing.assert_array_equal(got, want)
+
+
+def test_video_pair_blobs():
+    """online_tubes.py:582-606: consecutive frame pairs of one video, each frame prepared once."""
+    from d2t_b200 import ops
+    frames = np.stack([common.make_frame(45, 80, 70 + i) for i in range(5)])
+    blobs = ops.VideoPairBlobs(cu(frames), 30, 50)
+    assert len(blobs) == 4
+    want, info = oracle.frames_to_blob(frames, 30, 50, cap=True)                # = _get_image_blob per frame (cap applies)
+    for i in range(4):
+        s = blobs[i]
+        np.testing.assert_array_equal(s['data'].cpu().numpy(), want[i:i + 2])   # torch.cat([t0, t1]) of the reference
+        np.testing.assert_array_equal(s['im_info'].cpu().numpy(), info[i:i + 2])
+        assert s['frame_number'].view(-1).tolist() == [i, i + 1]
+    im, im_info = blobs.batch(1, 3)
+    assert im.is_contiguous() and tuple(im.shape) == (3, 2, 3) + want.shape[2:]
+    for p in range(3):
+        np.testing.assert_array_equal(im[p].cpu().numpy(), want[1 + p:3 + p])
+        np.testing.assert_array_equal(im_info[p].cpu().numpy(), info[1 + p:3 + p])
+    with pytest.raises(IndexError):
+        blobs.batch(2, 3)
+    with pytest.raises(IndexError):
+        blobs[4]
