@@ -129,13 +129,17 @@ def flush_l2(buf):
 
 def time_kernel(fn, iters, flush):
     """Average device time (ms) of fn() over `iters` launches, CUDA events on the current stream,
-    L2 flushed between launches."""
+    L2 flushed between launches, host launch latency hidden behind a device-side spin."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     tot = 0.0
     for _ in range(iters):
         flush_l2(flush)
+        # a ~50 us device-side spin ahead of the start event: the host enqueues event, launch(es) and end event while the
+        # GPU is still busy, so the interval is the kernels' device time and not the host's time to reach the launch
+        # (Python + ctypes: 5-20 us, comparable to the kernels timed here)
+        torch.cuda._sleep(100000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

@@ -33,7 +33,7 @@ __device__ __forceinline__ void axis_coord(int d, double scale, int n_src, int& 
 // float32(double(u8) - mean) without a table and without fp64: mean = hi + lo with hi a multiple of 2^-8 (so that u8 - hi is
 // exact in fp32) and lo = float(mean - hi); (u8 - hi) - lo then rounds once.  lo itself carries a 2^-33 error, so the host
 // checks all 3 x 256 values against the double formula before choosing this path (means_split); otherwise the table is used.
-struct MeanSplit { float hi[3], lo[3]; };
+struct MeanSplit { float hi32k[3], lo[3]; };     // 32768 + hi, lo
 
 // One thread: kX destination columns (blockDim apart: a warp reads neighbouring source bytes and writes 128 contiguous
 // bytes per plane) of one destination row, all three channels.
@@ -56,10 +56,14 @@ frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Mea
     const uint8_t* img = frames + (size_t)n * src_h * src_w * 3;
     const uint8_t* row0 = img + (size_t)sy * src_w * 3;
     const uint8_t* row1 = img + (size_t)sy1 * src_w * 3;
-    auto sample = [&](const uint8_t* p, int c) -> float {
-        const uint8_t u = __ldg(p + c);
+    // (the int -> float conversion instruction runs on the quarter-rate XU pipe, which ncu showed 60 % busy with 12
+    // conversions per pixel: 32768 + u is built with one byte permute instead -- the byte lands in mantissa bits 8..15 of
+    // 0x47000000 = 32768.0f, whose ulp is 2^-8 -- and hi32k = 32768 + hi, exact because hi is a multiple of 2^-8, is
+    // what gets subtracted)
+    auto sample = [&](const uint8_t* __restrict__ row, unsigned off, int c) -> float {
+        const unsigned u = __ldg(row + off + c);
         if (kLut) return lut[c][u];
-        return __fsub_rn(__fsub_rn((float)u, split.hi[c]), split.lo[c]);
+        return __fsub_rn(__fsub_rn(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)), split.hi32k[c]), split.lo[c]);
     };
 #pragma unroll
     for (int j = 0; j < kX; ++j) {
@@ -72,10 +76,11 @@ frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Mea
             int sx1 = min(sx + 1, src_w - 1);
             if (flipped) { sx = src_w - 1 - sx; sx1 = src_w - 1 - sx1; }
             const float a0 = __fsub_rn(1.f, a);
+            const unsigned o0 = (unsigned)sx * 3u, o1 = (unsigned)sx1 * 3u;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float s00 = sample(row0 + sx * 3, c), s01 = sample(row0 + sx1 * 3, c);
-                const float s10 = sample(row1 + sx * 3, c), s11 = sample(row1 + sx1 * 3, c);
+                const float s00 = sample(row0, o0, c), s01 = sample(row0, o1, c);
+                const float s10 = sample(row1, o0, c), s11 = sample(row1, o1, c);
                 const float r0 = __fadd_rn(__fmul_rn(s00, a0), __fmul_rn(s01, a));
                 const float r1 = __fadd_rn(__fmul_rn(s10, a0), __fmul_rn(s11, a));
                 v[c] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b));
@@ -95,11 +100,11 @@ frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Mea
 bool means_split(const double* m, MeanSplit& out) {
     for (int c = 0; c < 3; ++c) {
         const double hi = nearbyint(m[c] * 256.0) / 256.0;
-        if (!(fabs(hi) < 32768.0)) return false;
-        out.hi[c] = (float)hi;
+        if (!(hi > -16384.0 && hi < 16384.0)) return false;                  // 32768 + hi and u - hi stay exact in fp32
+        out.hi32k[c] = (float)(32768.0 + hi);
         out.lo[c] = (float)(m[c] - hi);
         for (int i = 0; i < 256; ++i) {
-            volatile float t = (float)i - out.hi[c];
+            volatile float t = (float)(32768 + i) - out.hi32k[c];
             volatile float got = t - out.lo[c];
             const float want = (float)((double)i - m[c]);
             if (got != want) return false;
