@@ -35,63 +35,101 @@ __device__ __forceinline__ void axis_coord(int d, double scale, int n_src, int& 
 // checks all 3 x 256 values against the double formula before choosing this path (means_split); otherwise the table is used.
 struct MeanSplit { float hi32k[3], lo[3]; };     // 32768 + hi, lo
 
-// One thread: kX destination columns (blockDim apart: a warp reads neighbouring source bytes and writes 128 contiguous
-// bytes per plane) of one destination row, all three channels.
-template <int kX, bool kLut, bool kNhwc>
-__global__ void __launch_bounds__(256)
+// One thread: one destination column of kRows consecutive destination rows, all three channels -- the two passes kept
+// separate as in OpenCV.  The horizontal pass of a SOURCE row (6 byte loads, mean subtraction, 3 two-tap sums) is computed
+// once and held in registers while consecutive destination rows need it: a reduction by 1.28 touches 1.28 new source rows
+// per destination row instead of 2 (ncu of the one-pass form: issue-bound at 165 instructions per pixel, profiles/
+// r02_frames_prep_ncu.txt).  Which rows are new depends on the row only, so the branches are uniform over the block; the
+// column coordinate (fp64 pipe) is computed once per thread, the block's row coordinates by its first kRows threads.
+// (Measured and dropped: the block's output rows staged in shared memory and written by 1-D TMA bulk stores -- same time.)
+template <int kRows, bool kLut, bool kNhwc>
+__global__ void __launch_bounds__(128)
 frames_prep_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w, Means means, MeanSplit split, double scale,
                    int flipped, int dst_h, int dst_w, float* __restrict__ blob, int blob_h, int blob_w) {
     __shared__ float lut[kLut ? 3 : 1][256];                                // float32(double(u8) - mean[c])
-    if (kLut) {
+    __shared__ int row_s[kRows];
+    __shared__ float row_b[kRows];
+    if (kLut)
         for (int i = threadIdx.x; i < 768; i += blockDim.x)
             lut[i >> 8][i & 255] = __double2float_rn(__dsub_rn((double)(i & 255), means.m[i >> 8]));
-        __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * kRows, n = blockIdx.z;
+    if (threadIdx.x < kRows) {
+        int sy = 0; float b = 0.f;
+        if (y0 + threadIdx.x < dst_h) axis_coord(y0 + threadIdx.x, scale, src_h, sy, b);
+        row_s[threadIdx.x] = sy;
+        row_b[threadIdx.x] = b;
     }
-    const int y = blockIdx.y, n = blockIdx.z;
-    const bool row_live = y < dst_h;
-    int sy = 0; float b = 0.f;
-    if (row_live) axis_coord(y, scale, src_h, sy, b);
-    const int sy1 = min(sy + 1, src_h - 1);
-    const float b0 = __fsub_rn(1.f, b);
-    const uint8_t* img = frames + (size_t)n * src_h * src_w * 3;
-    const uint8_t* row0 = img + (size_t)sy * src_w * 3;
-    const uint8_t* row1 = img + (size_t)sy1 * src_w * 3;
-    // (the int -> float conversion instruction runs on the quarter-rate XU pipe, which ncu showed 60 % busy with 12
-    // conversions per pixel: 32768 + u is built with one byte permute instead -- the byte lands in mantissa bits 8..15 of
-    // 0x47000000 = 32768.0f, whose ulp is 2^-8 -- and hi32k = 32768 + hi, exact because hi is a multiple of 2^-8, is
-    // what gets subtracted)
+    unsigned o0 = 0, o1 = 0; float a = 0.f;
+    const bool col_live = x < dst_w;
+    if (col_live) {
+        int sx;
+        axis_coord(x, scale, src_w, sx, a);
+        int sx1 = min(sx + 1, src_w - 1);
+        if (flipped) { sx = src_w - 1 - sx; sx1 = src_w - 1 - sx1; }
+        o0 = (unsigned)sx * 3u; o1 = (unsigned)sx1 * 3u;
+    }
+    const float a0 = __fsub_rn(1.f, a);
+    __syncthreads();
+    const bool active = x < blob_w;
+    const uint8_t* __restrict__ img = frames + (size_t)n * src_h * src_w * 3;
+    // (the int -> float conversion instruction runs on the quarter-rate XU pipe: 32768 + u is built with one byte permute
+    // instead -- the byte lands in mantissa bits 8..15 of 0x47000000 = 32768.0f, whose ulp is 2^-8 -- and hi32k =
+    // 32768 + hi, exact because hi is a multiple of 2^-8, is what gets subtracted)
     auto sample = [&](const uint8_t* __restrict__ row, unsigned off, int c) -> float {
         const unsigned u = __ldg(row + off + c);
         if (kLut) return lut[c][u];
         return __fsub_rn(__fsub_rn(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)), split.hi32k[c]), split.lo[c]);
     };
+    // address arithmetic in 32 bits (d2t_frames_prep checks that a frame and a blob image stay below 2^31 bytes /
+    // elements): 64-bit multiplies per row and channel were two thirds of the instructions ncu counted
+    const unsigned row_bytes = (unsigned)src_w * 3u;
+    auto hpass = [&](int sy, float (&h)[3]) {
+        const unsigned q0 = (unsigned)sy * row_bytes + o0, q1 = (unsigned)sy * row_bytes + o1;
 #pragma unroll
-    for (int j = 0; j < kX; ++j) {
-        const int x = (blockIdx.x * kX + j) * blockDim.x + threadIdx.x;
-        if (x >= blob_w) break;
+        for (int c = 0; c < 3; ++c)
+            h[c] = __fadd_rn(__fmul_rn(sample(img, q0, c), a0), __fmul_rn(sample(img, q1, c), a));
+    };
+    const int rows = min(kRows, blob_h - y0);
+    // The rows of the loop below are a dependent chain (load -> blend -> store, row after row): without help a thread
+    // waits out one cold DRAM access per new source row, ~11 in sequence.  All source rows of the tile are requested up
+    // front instead (both taps of a column share a sector, or neighbouring ones).
+    if (col_live && y0 < dst_h) {
+        const int first = row_s[0], last = min(row_s[min(rows, dst_h - y0) - 1] + 1, src_h - 1);
+        for (int sy = first; sy <= last; ++sy)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (unsigned)sy * row_bytes + min(o0, o1)));
+    }
+    float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};
+    int have0 = -1, have1 = -1;                                             // source rows held in h0 / h1
+    const unsigned plane = (unsigned)blob_h * (unsigned)blob_w;
+    float* __restrict__ out = kNhwc ? blob + ((size_t)n * plane + (size_t)y0 * blob_w + x) * 3
+                                    : blob + (size_t)n * 3 * plane + (size_t)y0 * blob_w + x;
+    for (int r = 0; r < rows; ++r) {
         float v[3] = {0.f, 0.f, 0.f};
-        if (row_live && x < dst_w) {
-            int sx; float a;
-            axis_coord(x, scale, src_w, sx, a);
-            int sx1 = min(sx + 1, src_w - 1);
-            if (flipped) { sx = src_w - 1 - sx; sx1 = src_w - 1 - sx1; }
-            const float a0 = __fsub_rn(1.f, a);
-            const unsigned o0 = (unsigned)sx * 3u, o1 = (unsigned)sx1 * 3u;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float s00 = sample(row0, o0, c), s01 = sample(row0, o1, c);
-                const float s10 = sample(row1, o0, c), s11 = sample(row1, o1, c);
-                const float r0 = __fadd_rn(__fmul_rn(s00, a0), __fmul_rn(s01, a));
-                const float r1 = __fadd_rn(__fmul_rn(s10, a0), __fmul_rn(s11, a));
-                v[c] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b));
+        if (col_live && y0 + r < dst_h) {
+            const int sy = row_s[r], sy1 = min(sy + 1, src_h - 1);
+            const float b = row_b[r], b0 = __fsub_rn(1.f, b);
+            if (sy != have0) {
+                if (sy == have1) { h0[0] = h1[0]; h0[1] = h1[1]; h0[2] = h1[2]; }
+                else hpass(sy, h0);
+                have0 = sy;
             }
-        }
-        if (kNhwc) {
-            float* o = blob + (((size_t)n * blob_h + y) * blob_w + x) * 3;
-            o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
-        } else {
+            if (sy1 != have1) {
+                if (sy1 == have0) { h1[0] = h0[0]; h1[1] = h0[1]; h1[2] = h0[2]; }
+                else hpass(sy1, h1);
+                have1 = sy1;
+            }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) blob[(((size_t)n * 3 + c) * blob_h + y) * blob_w + x] = v[c];
+            for (int c = 0; c < 3; ++c) v[c] = __fadd_rn(__fmul_rn(h0[c], b0), __fmul_rn(h1[c], b));
+        }
+        if (active) {
+            if (kNhwc) {
+                out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+                out += (size_t)blob_w * 3;
+            } else {
+                out[0] = v[0]; out[plane] = v[1]; out[2u * plane] = v[2];
+                out += blob_w;
+            }
         }
     }
 }
@@ -141,17 +179,19 @@ int d2t_frames_prep(const uint8_t* frames, int n, int src_h, int src_w, const do
                 (int)nearbyint(src_h * im_scale), (int)nearbyint(src_w * im_scale));
     D2T_REQUIRE(dst_h > 0 && dst_w > 0 && blob_h >= dst_h && blob_w >= dst_w, "d2t_frames_prep: blob %dx%d smaller than the resized frame %dx%d",
                 blob_h, blob_w, dst_h, dst_w);
-    D2T_REQUIRE(blob_h <= 65535 && n <= 65535, "d2t_frames_prep: grid limits (blob_h, n <= 65535)");
+    D2T_REQUIRE((double)src_h * src_w * 3 < 2147483648.0 && (double)blob_h * blob_w * 3 < 2147483648.0,
+                "d2t_frames_prep: a frame / a blob image must stay below 2^31 bytes / elements");
+    D2T_REQUIRE(blob_h <= 65535 * 8 && n <= 65535, "d2t_frames_prep: grid limits (blob_h <= 524280, n <= 65535)");
     Means means{{pixel_means[0], pixel_means[1], pixel_means[2]}};
     MeanSplit split{};
     const bool lut = !means_split(pixel_means, split);
     const double scale = 1.0 / im_scale;                                    // cv::resize: scale_x = 1 / inv_scale_x
-    constexpr int kX = 4;
-    const int threads = blob_w >= 1024 ? 256 : (blob_w >= 512 ? 128 : 64);
-    dim3 grid((blob_w + threads * kX - 1) / (threads * kX), blob_h, n);
-#define D2T_FRAMES_LAUNCH(LUT, NHWC)                                                                                    \
-    frames_prep_kernel<kX, LUT, NHWC><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, split, scale, flipped, \
-                                                                    dst_h, dst_w, blob, blob_h, blob_w)
+    constexpr int kRows = 8;
+    const int threads = blob_w >= 128 ? 128 : 64;
+    dim3 grid((blob_w + threads - 1) / threads, (blob_h + kRows - 1) / kRows, n);
+#define D2T_FRAMES_LAUNCH(LUT, NHWC)                                                                                  \
+    frames_prep_kernel<kRows, LUT, NHWC><<<grid, threads, 0, stream>>>(frames, src_h, src_w, means, split, scale,     \
+                                                                       flipped, dst_h, dst_w, blob, blob_h, blob_w)
     if (lut) { if (nhwc) D2T_FRAMES_LAUNCH(true, true); else D2T_FRAMES_LAUNCH(true, false); }
     else     { if (nhwc) D2T_FRAMES_LAUNCH(false, true); else D2T_FRAMES_LAUNCH(false, false); }
 #undef D2T_FRAMES_LAUNCH
