@@ -50,3 +50,25 @@ def load_checkpoint(filename, net, optimizer=None, engines=(), map_location="cpu
     if 'pooling_mode' in checkpoint.keys():
         cfg.POOLING_MODE = checkpoint['pooling_mode']
     return {k: v for k, v in checkpoint.items() if k not in ('model', 'optimizer')}
+
+
+def build_optimizer(net, lr=None, optimizer="sgd"):
+    """trainval_net.py:275-294: ONE parameter group per trainable parameter, in `named_parameters()` order -- the layout
+    the 'optimizer' entry of a reference checkpoint indexes by position -- biases at lr * (DOUBLE_BIAS + 1) with weight
+    decay only if BIAS_DECAY, everything else at lr with WEIGHT_DECAY; SGD with TRAIN.MOMENTUM, or Adam (the script's
+    own lr * 0.1 for Adam only changes the value it logs, not the groups: :289-291).
+    Returns (optimizer, lr)."""
+    lr = cfg.TRAIN.LEARNING_RATE if lr is None else lr
+    params = []
+    for key, value in dict(getattr(net, "module", net).named_parameters()).items():
+        if value.requires_grad:
+            if 'bias' in key:
+                params += [{'params': [value], 'lr': lr * (cfg.TRAIN.DOUBLE_BIAS + 1),
+                            'weight_decay': cfg.TRAIN.BIAS_DECAY and cfg.TRAIN.WEIGHT_DECAY or 0}]
+            else:
+                params += [{'params': [value], 'lr': lr, 'weight_decay': cfg.TRAIN.WEIGHT_DECAY}]
+    if optimizer == "adam":
+        return torch.optim.Adam(params), lr * 0.1
+    if optimizer == "sgd":
+        return torch.optim.SGD(params, momentum=cfg.TRAIN.MOMENTUM), lr
+    raise ValueError("optimizer must be 'sgd' or 'adam' (trainval_net.py:289-294)")

@@ -35,6 +35,7 @@ cfg = _NS(
         BBOX_NORMALIZE_TARGETS_PRECOMPUTED=True, BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0),
         BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2), BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0),     # config.py:113-119
         TRUNCATED=False,
+        LEARNING_RATE=0.001, MOMENTUM=0.9, WEIGHT_DECAY=0.0001, DOUBLE_BIAS=False, BIAS_DECAY=False,   # config.py:22-46 + cfgs/res101.yml:11-13
     ),
     TEST=_NS(
         RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=16,    # config.py:191-198

@@ -125,3 +125,30 @@ def test_net_utils_helpers(tmp_path):
     assert abs(opt.param_groups[0]['lr'] - 0.001) < 1e-12
     save_checkpoint({'a': 1}, str(tmp_path / "x.pth"))
     assert torch.load(str(tmp_path / "x.pth")) == {'a': 1}
+
+
+def test_build_optimizer_has_the_references_group_layout(golden):
+    """trainval_net.py:280-294: one group per trainable parameter in named_parameters() order (the 'optimizer' entry of a
+    reference checkpoint indexes parameters by that position), lr / weight decay per group under cfgs/res101.yml."""
+    from d2t_b200.checkpoint import build_optimizer
+    net = resnet(tuple(range(31)), 101, class_agnostic=True).create_architecture()
+    opt, lr = build_optimizer(net, 0.001)
+    names = {id(p): n for n, p in net.named_parameters()}
+    mine = [[names[id(g['params'][0])], g['lr'], g['weight_decay']] for g in opt.param_groups]
+    want = golden["optimizer_groups_res101_yml"]
+    assert len(mine) == len(want) == 107 and lr == 0.001
+    assert mine == want
+    assert all(len(g['params']) == 1 and g['momentum'] == 0.9 for g in opt.param_groups)
+    # a reference optimizer state (same layout) loads, and positions line up with the same parameters
+    ref_like = torch.optim.SGD([{'params': [torch.nn.Parameter(torch.zeros_like(g['params'][0]))], 'lr': 0.0005,
+                                 'weight_decay': g['weight_decay']} for g in opt.param_groups], momentum=0.9)
+    for g in ref_like.param_groups:
+        g['params'][0].grad = torch.ones_like(g['params'][0])
+    ref_like.step()
+    opt.load_state_dict(ref_like.state_dict())
+    assert opt.param_groups[0]['lr'] == 0.0005
+    assert all(opt.state[g['params'][0]]['momentum_buffer'].shape == g['params'][0].shape for g in opt.param_groups)
+    adam, lr_adam = build_optimizer(net, 0.001, "adam")
+    assert isinstance(adam, torch.optim.Adam) and abs(lr_adam - 0.0001) < 1e-12 and len(adam.param_groups) == 107
+    with pytest.raises(ValueError):
+        build_optimizer(net, 0.001, "lbfgs")
